@@ -1,0 +1,248 @@
+// extern "C" entry points of libekaid_b200.so (declared in include/ekaid_b200.h).
+#include <cstdarg>
+#include <cstring>
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "../../include/ekaid_b200.h"
+
+static thread_local char g_err[512] = "";
+
+void ek_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// launchers implemented in the kernel translation units
+int ek_gemm_f32_launch(int M, int N, int K, const float* A, long long sam, long long sak, const float* B,
+                       long long sbk, long long sbn, const EkEpilogue& ep, cudaStream_t stream);
+int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
+                           long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream);
+int ek_cast_f32_bf16_launch(const float*, long long, bf16*, long long, long long, int, cudaStream_t);
+int ek_cast_bf16_f32_launch(const bf16*, long long, float*, long long, long long, int, cudaStream_t);
+int ek_copy_f32_launch(const float*, long long, float*, long long, long long, int, cudaStream_t);
+int ek_colsum_launch(int, const void*, long long, long long, int, const float*, float*, float*, cudaStream_t);
+int ek_row_zero_flags_launch(const float*, long long, int, uint8_t*, cudaStream_t);
+int ek_group_rowsum_launch(int, const void*, long long, int, int, int, int, const uint8_t*, float*, cudaStream_t);
+int ek_combine_diff_fwd_launch(int, const float*, long long, int, int, float, float, float, float*, void*, cudaStream_t);
+int ek_combine_diff_bwd_launch(const float*, const float*, long long, int, int, float, float, float, float*,
+                               cudaStream_t);
+int ek_gate_fwd_launch(int, const float*, long long, int, void*, void*, void*, cudaStream_t);
+int ek_gate_bwd_launch(int, const float*, const void*, const void*, long long, int, void*, cudaStream_t);
+int ek_att_pool_fwd_launch(const float*, long long, int, int, int, const float*, const float*, const float*, float*,
+                           float*, cudaStream_t);
+int ek_att_pool_bwd_launch(int, const float*, const float*, const float*, const float*, const float*, const float*,
+                           long long, int, int, int, float*, void*, float*, cudaStream_t);
+int ek_onehot_adj_launch(const double*, int, int, int, int, float*, cudaStream_t);
+int ek_adam_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, const float*,
+                   cudaStream_t);
+int ek_adam_advance_launch(float*, float, float, cudaStream_t);
+int ek_adj_prep_fwd_launch(const float*, const float*, int, const float*, int, int, int, int, float*, float*,
+                           cudaStream_t);
+int ek_adj_prep_bwd_launch(const float*, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
+int ek_geom_bias_fwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
+                            int, float*, cudaStream_t);
+int ek_geom_bias_bwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
+                            int, const float*, float*, cudaStream_t);
+int ek_edge_softmax_fwd_launch(int, const void*, long long, int, const float*, const float*, const float*, int, int,
+                               int, int, float*, cudaStream_t);
+int ek_edge_aggregate_fwd_launch(int, const float*, const void*, long long, int, const float*, const float*, int, int,
+                                 int, int, float*, void*, long long, uint8_t*, cudaStream_t);
+int ek_edge_num_slices(int D);
+int ek_edge_aggregate_bwd_launch(int, const float*, const uint8_t*, const float*, const void*, long long, int, int, int,
+                                 int, int, void*, float*, float*, cudaStream_t);
+int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*, long long, int, const float*, int,
+                               int, int, int, void*, float*, float*, cudaStream_t);
+int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
+int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
+int ek_gru_cell_fwd_launch(int, const float*, const float*, const float*, int, int, float*, void*, float*,
+                           cudaStream_t);
+int ek_gru_cell_bwd_launch(int, const float*, const float*, const float*, int, int, float*, float*, void*, void*,
+                           float*, cudaStream_t);
+int ek_rowdot_launch(int, const void*, long long, long long, int, const float*, const float*, float*, cudaStream_t);
+int ek_qpool_fwd_launch(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
+int ek_qpool_bwd_launch(const float*, const float*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
+int ek_qatt_tanh_bwd_launch(int, const float*, const float*, const void*, long long, int, void*, cudaStream_t);
+int ek_add_inplace_launch(float*, const float*, long long, cudaStream_t);
+
+static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
+  EkEpilogue r;
+  r.bias = e->bias;
+  r.addend = e->addend;
+  r.ldadd = e->ldadd;
+  r.rowb = e->rowb;
+  r.ldrowb = e->ldrowb;
+  r.rowb_div = e->rowb_div > 0 ? e->rowb_div : 1;
+  r.rowb_mod = e->rowb_mod > 0 ? e->rowb_mod : 1;
+  r.rowflag = e->rowflag;
+  r.rowb_alt = e->rowb_alt;
+  r.act = e->act;
+  r.C = e->C;
+  r.ldc = e->ldc;
+  r.Cb = (bf16*)e->Cb;
+  r.ldcb = e->ldcb;
+  return r;
+}
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+
+int ekaid_abi_version(void) { return 1; }
+const char* ekaid_last_error(void) { return g_err; }
+
+int ekaid_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { ek_set_error("no CUDA device: %s", cudaGetErrorString(e)); return EK_ERR_CUDA; }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) { ek_set_error("device is sm_%d%d, this library is built for sm_100a only", major, minor); return EK_ERR_ARCH; }
+  return EK_OK;
+}
+
+int ekaid_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, const ekaid_epilogue_t* ep, void* stream) {
+  EK_REQUIRE(ep && (ep->C || ep->Cb), EK_ERR_SHAPE, "gemm_f32: no output");
+  const long long sam = transA ? 1 : lda, sak = transA ? lda : 1;
+  const long long sbk = transB ? ldb : 1, sbn = transB ? 1 : ldb;
+  return ek_gemm_f32_launch(M, N, K, A, sam, sak, B, sbk, sbn, to_ep(ep), ST);
+}
+int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
+                    int64_t ldb, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream) {
+  EK_REQUIRE(ep && (ep->C || ep->Cb), EK_ERR_SHAPE, "gemm_bf16: no output");
+  return ek_gemm_bf16_tc_launch(transA, transB, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, to_ep(ep), force_bn,
+                                splits, ST);
+}
+int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
+  return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, ST);
+}
+int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
+  return ek_cast_bf16_f32_launch((const bf16*)src, lds, dst, ldd, rows, cols, ST);
+}
+int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
+  return ek_copy_f32_launch(src, lds, dst, ldd, rows, cols, ST);
+}
+int ekaid_colsum(int is_bf16, const void* src, int64_t ld, int64_t M, int N, const float* rowscale, float* out,
+                 float* workspace, void* stream) {
+  return ek_colsum_launch(is_bf16, src, ld, M, N, rowscale, out, workspace, ST);
+}
+int ekaid_add_inplace(float* y, const float* x, int64_t n, void* stream) { return ek_add_inplace_launch(y, x, n, ST); }
+int ekaid_row_zero_flags(const float* X, int64_t M, int D, uint8_t* flags, void* stream) {
+  return ek_row_zero_flags_launch(X, M, D, flags, ST);
+}
+int ekaid_group_rowsum(int is_bf16, const void* src, int64_t ld, int N, int B, int S, int D, const uint8_t* flags,
+                       float* out, void* stream) {
+  return ek_group_rowsum_launch(is_bf16, src, ld, N, B, S, D, flags, out, ST);
+}
+int ekaid_onehot_adj(const double* labels, int B, int S, int N, int L, float* out, void* stream) {
+  EK_REQUIRE(N <= S && L >= 1, EK_ERR_SHAPE, "onehot_adj: N=%d > S=%d", N, S);
+  return ek_onehot_adj_launch(labels, B, S, N, L, out, ST);
+}
+int ekaid_adj_prep_fwd(const float* adj0, const float* adj1, int g_split, const float* w, int G, int N, int Kn, int L,
+                       float* cond, float* lbias, void* stream) {
+  EK_REQUIRE(Kn <= N && G > 0, EK_ERR_SHAPE, "adj_prep: bad shape");
+  return ek_adj_prep_fwd_launch(adj0, adj1, g_split, w, G, N, Kn, L, cond, lbias, ST);
+}
+int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const float* dlbias_part, int nparts, int G,
+                       int N, int Kn, int L, float* dw_part, void* stream) {
+  return ek_adj_prep_bwd_launch(adj0, adj1, g_split, dlbias_part, nparts, G, N, Kn, L, dw_part, ST);
+}
+int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
+                        const float* dim_t, int G, int N, int Kn, int H, float* gbias, void* stream) {
+  return ek_geom_bias_fwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, gbias, ST);
+}
+int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
+                        const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
+                        void* stream) {
+  return ek_geom_bias_bwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, dgbias, part, ST);
+}
+int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
+                           const float* gbias, int G, int N, int Kn, int H, float* P, void* stream) {
+  EK_REQUIRE(D % H == 0 && Kn <= N, EK_ERR_SHAPE, "edge_softmax: D=%d H=%d N=%d Kn=%d", D, H, N, Kn);
+  return ek_edge_softmax_fwd_launch(is_bf16, QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, ST);
+}
+int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
+                             const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
+                             uint8_t* mask, void* stream) {
+  return ek_edge_aggregate_fwd_launch(is_bf16, P, QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, XoutT, ldt, mask, ST);
+}
+int ekaid_edge_num_slices(int D) { return ek_edge_num_slices(D); }
+int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
+                             int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
+                             void* stream) {
+  return ek_edge_aggregate_bwd_launch(is_bf16, dXout, mask, P, QKZ, ld, D, G, N, Kn, H, dQKZ, dOut, dPpart, ST);
+}
+int ekaid_edge_softmax_bwd(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ, int64_t ld,
+                           int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ, float* dlbias_part,
+                           float* dgbias, void* stream) {
+  return ek_edge_softmax_bwd_launch(is_bf16, P, dPpart, nslices, QKZ, ld, D, cond, G, N, Kn, H, dQKZ, dlbias_part,
+                                    dgbias, ST);
+}
+int ekaid_combine_diff_fwd(int is_bf16, const float* X3, int64_t BN, int D, int mode, float c1, float c2, float c3,
+                           float* Xc, void* CAT, void* stream) {
+  return ek_combine_diff_fwd_launch(is_bf16, X3, BN, D, mode, c1, c2, c3, Xc, CAT, ST);
+}
+int ekaid_combine_diff_bwd(const float* dXc, const float* dCAT, int64_t BN, int D, int mode, float c1, float c2,
+                           float c3, float* dX3, void* stream) {
+  return ek_combine_diff_bwd_launch(dXc, dCAT, BN, D, mode, c1, c2, c3, dX3, ST);
+}
+int ekaid_gate_fwd(int is_bf16, const float* pre, int64_t M, int D, void* ctx, void* gate, void* CAT, void* stream) {
+  return ek_gate_fwd_launch(is_bf16, pre, M, D, ctx, gate, CAT, ST);
+}
+int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* gate, int64_t M, int D, void* dpre,
+                   void* stream) {
+  return ek_gate_bwd_launch(is_bf16, dCAT, ctx, gate, M, D, dpre, ST);
+}
+int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const float* w, const float* b,
+                       const float* Xc, float* att, float* attended, void* stream) {
+  EK_REQUIRE(N > 0 && M % N == 0, EK_ERR_SHAPE, "att_pool: M=%lld not a multiple of N=%d", (long long)M, N);
+  return ek_att_pool_fwd_launch(E, M, N, D, dim, w, b, Xc, att, attended, ST);
+}
+int ekaid_att_pool_bwd(int is_bf16, const float* dA, const float* dattw, const float* att, const float* Xc,
+                       const float* E, const float* w, int64_t M, int N, int D, int dim, float* dXc, void* dE,
+                       float* dpre, void* stream) {
+  return ek_att_pool_bwd_launch(is_bf16, dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, dE, dpre, ST);
+}
+int ekaid_embed_gather(int is_bf16, const int64_t* q, const float* emb, const float* emb2, int B, int L, int ed,
+                       void* E, void* stream) {
+  return ek_embed_gather_launch(is_bf16, (const long long*)q, emb, emb2, B, L, ed, E, ST);
+}
+int ekaid_embed_gather_bwd(const int64_t* q, const float* dE, int64_t ldde, int B, int L, int ed, int V, float* demb,
+                           void* stream) {
+  return ek_embed_gather_bwd_launch((const long long*)q, dE, ldde, B, L, ed, V, demb, ST);
+}
+int ekaid_gru_cell_fwd(int is_bf16, const float* gi, const float* gh, const float* hprev, int B, int H, float* h,
+                       void* hT, float* gates, void* stream) {
+  return ek_gru_cell_fwd_launch(is_bf16, gi, gh, hprev, B, H, h, hT, gates, ST);
+}
+int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H, float* dgi,
+                       float* dgh, void* dgiT, void* dghT, float* dhprev, void* stream) {
+  return ek_gru_cell_bwd_launch(is_bf16, dh, gates, hprev, B, H, dgi, dgh, dgiT, dghT, dhprev, ST);
+}
+int ekaid_rowdot(int is_bf16, const void* A, int64_t lda, int64_t M, int K, const float* w, const float* b, float* out,
+                 void* stream) {
+  return ek_rowdot_launch(is_bf16, A, lda, M, K, w, b, out, ST);
+}
+int ekaid_qpool_fwd(const float* a, const float* Hs, int B, int L, int H, float* S, float* qv, void* stream) {
+  return ek_qpool_fwd_launch(a, Hs, B, L, H, S, qv, ST);
+}
+int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, int L, int H, float* dS, float* da,
+                    float* dHs, void* stream) {
+  return ek_qpool_bwd_launch(dqv, S, Hs, B, L, H, dS, da, dHs, ST);
+}
+int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
+                        void* stream) {
+  return ek_qatt_tanh_bwd_launch(is_bf16, da, w2, a1, M, H, dpre, ST);
+}
+int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream) {
+  return ek_adam_advance_launch(pow_state, b1, b2, ST);
+}
+int ekaid_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                    float wd, const float* pow_state, void* stream) {
+  return ek_adam_launch(p, g, m, v, n, lr, b1, b2, eps, wd, pow_state, ST);
+}
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// Shared helpers for the ekaid_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+
+typedef __nv_bfloat16 bf16;
+
+// Error codes returned through the C ABI (0 = ok); see include/ekaid_b200.h
+#define EK_OK 0
+#define EK_ERR_SHAPE -1
+#define EK_ERR_ALIGN -2
+#define EK_ERR_ARCH -3
+#define EK_ERR_CUDA -4
+#define EK_ERR_UNSUPPORTED -5
+
+void ek_set_error(const char* fmt, ...);
+
+#define EK_CHECK_LAUNCH()                                                        \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) {                                                    \
+      ek_set_error("%s:%d launch failed: %s", __FILE__, __LINE__,                \
+                   cudaGetErrorString(e__));                                     \
+      return EK_ERR_CUDA;                                                        \
+    }                                                                            \
+  } while (0)
+
+#define EK_REQUIRE(cond, code, ...)                                              \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      ek_set_error(__VA_ARGS__);                                                 \
+      return code;                                                               \
+    }                                                                            \
+  } while (0)
+
+static inline int ek_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; `red` must hold >= 32 floats of shared memory; all threads must call
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) red[0] = r;
+  __syncthreads();
+  r = red[0];
+  return r;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }

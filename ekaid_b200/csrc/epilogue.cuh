@@ -1,0 +1,47 @@
+// Epilogue description shared by the SIMT fp32 GEMM and the tcgen05 bf16 GEMM.
+#pragma once
+#include "common.cuh"
+
+enum EkAct { EK_ACT_NONE = 0, EK_ACT_RELU = 1, EK_ACT_TANH = 2, EK_ACT_SIGMOID = 3 };
+
+// v = acc (+ bias[n]) (+ addend[m,n]) (+ rowflag[m] ? rowb_alt[n] : rowb[(m / rowb_div) % rowb_mod, n]);
+// v = act(v); C[m,n] = v (fp32, optional); Cb[m,n] = bf16(v) (optional)
+struct EkEpilogue {
+  const float* bias;
+  const float* addend;
+  long long ldadd;
+  const float* rowb;
+  long long ldrowb;
+  int rowb_div;
+  int rowb_mod;
+  const uint8_t* rowflag;
+  const float* rowb_alt;
+  int act;
+  float* C;
+  long long ldc;
+  bf16* Cb;
+  long long ldcb;
+};
+
+__device__ __forceinline__ float ek_act(float v, int act) {
+  switch (act) {
+    case EK_ACT_RELU: return fmaxf(v, 0.f);
+    case EK_ACT_TANH: return tanhf(v);
+    case EK_ACT_SIGMOID: return sigmoidf_(v);
+    default: return v;
+  }
+}
+
+// scalar epilogue for element (m, n)
+__device__ __forceinline__ void ek_epilogue_store(const EkEpilogue& e, long long m, int n, float acc) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + n);
+  if (e.addend) v += e.addend[m * e.ldadd + n];
+  if (e.rowb) {
+    if (e.rowflag && e.rowflag[m]) v += __ldg(e.rowb_alt + n);
+    else v += __ldg(e.rowb + (long long)((m / e.rowb_div) % e.rowb_mod) * e.ldrowb + n);
+  }
+  v = ek_act(v, e.act);
+  if (e.C) e.C[m * e.ldc + n] = v;
+  if (e.Cb) e.Cb[m * e.ldcb + n] = __float2bfloat16_rn(v);
+}

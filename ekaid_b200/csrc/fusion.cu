@@ -1,0 +1,420 @@
+// Element-wise / reduction kernels of the fusion half of the path and shared utilities
+// (reference models/modules.py:233-310, models/relation_encoder.py:19-29, utils/mimic_utils.py:119-149).
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- casts / copies
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst,
+                                     long long ldd, long long rows, int cols) {
+  const long long total = rows * (cols / 4);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / (cols / 4);
+    const int c = (int)(e % (cols / 4)) * 4;
+    const float4 v = *(const float4*)(src + r * lds + c);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *(uint32_t*)&a;
+    pk.y = *(uint32_t*)&b;
+    *(uint2*)(dst + r * ldd + c) = pk;
+  }
+}
+__global__ void copy_f32_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+                                long long rows, int cols) {
+  const long long total = rows * (cols / 4);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / (cols / 4);
+    const int c = (int)(e % (cols / 4)) * 4;
+    *(float4*)(dst + r * ldd + c) = *(const float4*)(src + r * lds + c);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds, float* __restrict__ dst,
+                                     long long ldd, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / cols;
+    const int c = (int)(e % cols);
+    dst[r * ldd + c] = __bfloat162float(src[r * lds + c]);
+  }
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients), two deterministic passes
+// part[p, n] = sum_{m in chunk p} scale[m] * src[m, n]
+template <typename T>
+__global__ void colsum_part_kernel(const T* __restrict__ src, long long ld, long long M, int N,
+                                   const float* __restrict__ rowscale, float* __restrict__ part, int nparts) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const long long rows_per = (M + nparts - 1) / nparts;
+  const long long r0 = (long long)blockIdx.y * rows_per;
+  const long long r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
+  float s = 0.f;
+  if (n < N)
+    for (long long m = r0 + ty; m < r1; m += 8) {
+      const float v = to_f32<T>(src[m * ld + n]);
+      s += rowscale ? v * rowscale[m] : v;
+    }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    part[(size_t)blockIdx.y * N + n] = t;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * N + n];
+  out[n] = s;
+}
+
+// ---------------------------------------------------------------- row flags for quirk Q10
+__global__ void row_zero_flags_kernel(const float* __restrict__ X, long long M, int D, uint8_t* __restrict__ flags) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) s += X[row * D + c];
+  s = warp_sum(s);
+  if (lane == 0) flags[row] = (s == 0.f) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------- per-sample row sums (backward of the q broadcast)
+// out[b, c] = sum_{s < S} sum_{n < N} (flags[row] ? 0 : src[row, c]),  row = (s*B + b)*N + n
+template <typename T>
+__global__ void group_rowsum_kernel(const T* __restrict__ src, long long ld, int N, int B, int S, int D,
+                                    const uint8_t* __restrict__ flags, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s)
+    for (int n = 0; n < N; ++n) {
+      const long long row = ((long long)s * B + b) * N + n;
+      if (!(flags && flags[row])) acc += to_f32<T>(src[row * ld + c]);
+    }
+  out[(size_t)b * D + c] = acc;
+}
+
+// ---------------------------------------------------------------- graph combine + difference (modules.py:233-250)
+// X3: [2*BN, D] (bef rows, then aft rows).  mode 0: identity, 1: 'all' (three fp32 products, quirk Q1),
+// 2: 'i+s' ((x+x)/2).  Outputs Xc fp32 [2BN, D] and the concat buffer CAT[2BN, 3D]:
+// [:, 0:D] = Xc, [:, D:2D] = diff (same diff for the bef and the aft row of a pair).
+template <typename T>
+__global__ void combine_diff_fwd_kernel(const float* __restrict__ X3, long long BN, int D, int mode, float c1, float c2,
+                                        float c3, float* __restrict__ Xc, T* __restrict__ CAT) {
+  const long long total = BN * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / D;
+    const int c = (int)(e % D);
+    float xb = X3[e], xa = X3[total + e];
+    if (mode == 1) {
+      xb = c1 * xb + c2 * xb + c3 * xb;
+      xa = c1 * xa + c2 * xa + c3 * xa;
+    } else if (mode == 2) {
+      xb = (xb + xb) / 2.f;
+      xa = (xa + xa) / 2.f;
+    }
+    const float d = xa - xb;
+    Xc[e] = xb;
+    Xc[total + e] = xa;
+    CAT[r * 3 * D + c] = from_f32<T>(xb);
+    CAT[(BN + r) * 3 * D + c] = from_f32<T>(xa);
+    CAT[r * 3 * D + D + c] = from_f32<T>(d);
+    CAT[(BN + r) * 3 * D + D + c] = from_f32<T>(d);
+  }
+}
+// dX3 = csum * (dXc_direct + dCAT[:, 0:D] -/+ (dCAT_bef[:, D:2D] + dCAT_aft[:, D:2D]))
+__global__ void combine_diff_bwd_kernel(const float* __restrict__ dXc, const float* __restrict__ dCAT, long long BN,
+                                        int D, int mode, float c1, float c2, float c3, float* __restrict__ dX3) {
+  const long long total = BN * D;
+  float cs = 1.f;
+  if (mode == 1) cs = c1 + c2 + c3;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / D;
+    const int c = (int)(e % D);
+    const float dd = dCAT[r * 3 * D + D + c] + dCAT[(BN + r) * 3 * D + D + c];
+    const float gb = dXc[e] + dCAT[r * 3 * D + c] - dd;
+    const float ga = dXc[total + e] + dCAT[(BN + r) * 3 * D + c] + dd;
+    if (mode == 1) {
+      dX3[e] = c1 * gb + c2 * gb + c3 * gb;
+      dX3[total + e] = c1 * ga + c2 * ga + c3 * ga;
+    } else {
+      dX3[e] = cs * gb;
+      dX3[total + e] = cs * ga;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- gated fusion (modules.py:278-288)
+// pre [M, 2D] fp32: [:, 0:D] = context pre-activation, [:, D:2D] = gate pre-activation (biases included)
+template <typename T>
+__global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int D, T* __restrict__ ctx,
+                                T* __restrict__ gate, T* __restrict__ CAT) {
+  const long long total = M * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / D;
+    const int c = (int)(e % D);
+    const float cv = tanhf(pre[r * 2 * D + c]);
+    const float gv = sigmoidf_(pre[r * 2 * D + D + c]);
+    ctx[e] = from_f32<T>(cv);
+    gate[e] = from_f32<T>(gv);
+    CAT[r * 3 * D + 2 * D + c] = from_f32<T>(gv * cv);
+  }
+}
+// dXs = dCAT[:, 2D:3D] (fp32) -> dpre [M, 2D] (T)
+template <typename T>
+__global__ void gate_bwd_kernel(const float* __restrict__ dCAT, const T* __restrict__ ctx, const T* __restrict__ gate,
+                                long long M, int D, T* __restrict__ dpre) {
+  const long long total = M * D;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / D;
+    const int c = (int)(e % D);
+    const float d = dCAT[r * 3 * D + 2 * D + c];
+    const float cv = to_f32<T>(ctx[e]), gv = to_f32<T>(gate[e]);
+    dpre[r * 2 * D + c] = from_f32<T>(d * gv * (1.f - cv * cv));
+    dpre[r * 2 * D + D + c] = from_f32<T>(d * cv * gv * (1.f - gv));
+  }
+}
+
+// ---------------------------------------------------------------- attention pooling (modules.py:302-308)
+// att[row] = sigmoid(e[row,:] . w + b)   one warp per row
+__global__ void att_score_kernel(const float* __restrict__ E, long long M, int dim, const float* __restrict__ w,
+                                 const float* __restrict__ b, float* __restrict__ att) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int c = lane; c < dim; c += 32) s = fmaf(E[row * dim + c], w[c], s);
+  s = warp_sum(s);
+  if (lane == 0) att[row] = sigmoidf_(s + b[0]);
+}
+// attended[g, c] = sum_n att[g*N + n] * Xc[g*N + n, c]
+__global__ void att_pool_kernel(const float* __restrict__ att, const float* __restrict__ Xc, int N, int D,
+                                float* __restrict__ attended) {
+  const int g = blockIdx.x;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s = fmaf(att[(size_t)g * N + n], Xc[((size_t)g * N + n) * D + c], s);
+  attended[(size_t)g * D + c] = s;
+}
+// backward, one warp per row:  d_att = Xc[row,:] . dA[g,:] (+ d_attw[row]);  dpre = d_att * att * (1 - att)
+//   dXc[row,:] = att[row] * dA[g,:] ; dE[row,:] = dpre * w * (e > 0)   (T) ; dpre_out[row] = dpre
+template <typename T>
+__global__ void att_pool_bwd_kernel(const float* __restrict__ dA, const float* __restrict__ dattw,
+                                    const float* __restrict__ att, const float* __restrict__ Xc,
+                                    const float* __restrict__ E, const float* __restrict__ w, long long M, int N, int D,
+                                    int dim, float* __restrict__ dXc, T* __restrict__ dE, float* __restrict__ dpre_out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const long long g = row / N;
+  const float a = att[row];
+  float s = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float da = dA[g * D + c];
+    s = fmaf(Xc[row * D + c], da, s);
+    dXc[row * D + c] = a * da;
+  }
+  s = warp_sum(s);
+  if (dattw) s += dattw[row];
+  const float dp = s * a * (1.f - a);
+  if (lane == 0) dpre_out[row] = dp;
+  for (int c = lane; c < dim; c += 32) dE[row * dim + c] = from_f32<T>(E[row * dim + c] > 0.f ? dp * w[c] : 0.f);
+}
+
+// ---------------------------------------------------------------- process_matrix (mimic_utils.py:119-149)
+// labels: float64 [B, S, S]; out fp32 [B, N, N, L]: plane c = (label == c+1)
+__global__ void onehot_adj_kernel(const double* __restrict__ labels, int S, int N, int L, long long total,
+                                  float* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / ((long long)N * N);
+    const int ij = (int)(e % ((long long)N * N));
+    const int i = ij / N, j = ij % N;
+    const double v = labels[(b * S + i) * S + j];
+    float* o = out + e * L;
+    for (int c = 0; c < L; ++c) o[c] = (v == (double)(c + 1)) ? 1.f : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- Adam (utils/utils.py:96-99 -> torch.optim.Adam)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                            const float* __restrict__ pow_state) {
+  // pow_state = {b1^t, b2^t} lives in device memory so a captured CUDA graph stays valid across steps
+  const float bc1 = 1.f - pow_state[0], bc2 = 1.f - pow_state[1];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float gr = g[e];
+    const float pv = p[e];
+    if (wd != 0.f) gr = fmaf(wd, pv, gr);
+    const float mv = b1 * m[e] + (1.f - b1) * gr;
+    const float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+    m[e] = mv;
+    v[e] = vv;
+    const float denom = sqrtf(vv) / sqrtf(bc2) + eps;
+    p[e] = pv - (lr / bc1) * (mv / denom);
+  }
+}
+
+__global__ void adam_advance_kernel(float* pow_state, float b1, float b2) {
+  pow_state[0] *= b1;
+  pow_state[1] *= b2;
+}
+
+inline int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int ek_cast_f32_bf16_launch(const float* src, long long lds, bf16* dst, long long ldd, long long rows, int cols,
+                            cudaStream_t st) {
+  EK_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0,
+             EK_ERR_ALIGN, "cast_f32_bf16: cols/pitch must be multiples of 4 and pointers aligned");
+  if (rows * cols == 0) return EK_OK;
+  cast_f32_bf16_kernel<<<grid_for(rows * cols / 4), 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_copy_f32_launch(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                       cudaStream_t st) {
+  EK_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0,
+             EK_ERR_ALIGN, "copy_f32: cols/pitch must be multiples of 4 and pointers aligned");
+  if (rows * cols == 0) return EK_OK;
+  copy_f32_kernel<<<grid_for(rows * cols / 4), 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_cast_bf16_f32_launch(const bf16* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                            cudaStream_t st) {
+  if (rows * cols == 0) return EK_OK;
+  cast_bf16_f32_kernel<<<grid_for(rows * cols), 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+// workspace: >= 64 * N floats
+int ek_colsum_launch(int is_bf16, const void* src, long long ld, long long M, int N, const float* rowscale, float* out,
+                     float* workspace, cudaStream_t st) {
+  int nparts = (int)((M + 255) / 256);
+  if (nparts > 64) nparts = 64;
+  if (nparts < 1) nparts = 1;
+  dim3 grid(ek_div_up(N, 32), nparts);
+  if (is_bf16)
+    colsum_part_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, ld, M, N, rowscale, workspace, nparts);
+  else
+    colsum_part_kernel<float><<<grid, 256, 0, st>>>((const float*)src, ld, M, N, rowscale, workspace, nparts);
+  EK_CHECK_LAUNCH();
+  colsum_final_kernel<<<ek_div_up(N, 128), 128, 0, st>>>(workspace, nparts, N, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_row_zero_flags_launch(const float* X, long long M, int D, uint8_t* flags, cudaStream_t st) {
+  row_zero_flags_kernel<<<ek_div_up(M, 8), 256, 0, st>>>(X, M, D, flags);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_group_rowsum_launch(int is_bf16, const void* src, long long ld, int N, int B, int S, int D, const uint8_t* flags,
+                           float* out, cudaStream_t st) {
+  dim3 grid(B, ek_div_up(D, 128));
+  if (is_bf16) group_rowsum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)src, ld, N, B, S, D, flags, out);
+  else group_rowsum_kernel<float><<<grid, 128, 0, st>>>((const float*)src, ld, N, B, S, D, flags, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_combine_diff_fwd_launch(int is_bf16, const float* X3, long long BN, int D, int mode, float c1, float c2,
+                               float c3, float* Xc, void* CAT, cudaStream_t st) {
+  if (is_bf16)
+    combine_diff_fwd_kernel<bf16><<<grid_for(BN * D), 256, 0, st>>>(X3, BN, D, mode, c1, c2, c3, Xc, (bf16*)CAT);
+  else
+    combine_diff_fwd_kernel<float><<<grid_for(BN * D), 256, 0, st>>>(X3, BN, D, mode, c1, c2, c3, Xc, (float*)CAT);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_combine_diff_bwd_launch(const float* dXc, const float* dCAT, long long BN, int D, int mode, float c1, float c2,
+                               float c3, float* dX3, cudaStream_t st) {
+  combine_diff_bwd_kernel<<<grid_for(BN * D), 256, 0, st>>>(dXc, dCAT, BN, D, mode, c1, c2, c3, dX3);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_gate_fwd_launch(int is_bf16, const float* pre, long long M, int D, void* ctx, void* gate, void* CAT,
+                       cudaStream_t st) {
+  if (is_bf16)
+    gate_fwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT);
+  else
+    gate_fwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (float*)ctx, (float*)gate, (float*)CAT);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_gate_bwd_launch(int is_bf16, const float* dCAT, const void* ctx, const void* gate, long long M, int D,
+                       void* dpre, cudaStream_t st) {
+  if (is_bf16)
+    gate_bwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre);
+  else
+    gate_bwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const float*)ctx, (const float*)gate, M, D,
+                                                            (float*)dpre);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_att_pool_fwd_launch(const float* E, long long M, int N, int D, int dim, const float* w, const float* b,
+                           const float* Xc, float* att, float* attended, cudaStream_t st) {
+  att_score_kernel<<<ek_div_up(M, 8), 256, 0, st>>>(E, M, dim, w, b, att);
+  EK_CHECK_LAUNCH();
+  att_pool_kernel<<<dim3((unsigned)(M / N), ek_div_up(D, 128)), 128, 0, st>>>(att, Xc, N, D, attended);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_att_pool_bwd_launch(int is_bf16, const float* dA, const float* dattw, const float* att, const float* Xc,
+                           const float* E, const float* w, long long M, int N, int D, int dim, float* dXc, void* dE,
+                           float* dpre, cudaStream_t st) {
+  if (is_bf16)
+    att_pool_bwd_kernel<bf16><<<ek_div_up(M, 8), 256, 0, st>>>(dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, (bf16*)dE,
+                                                                dpre);
+  else
+    att_pool_bwd_kernel<float><<<ek_div_up(M, 8), 256, 0, st>>>(dA, dattw, att, Xc, E, w, M, N, D, dim, dXc,
+                                                                 (float*)dE, dpre);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_onehot_adj_launch(const double* labels, int B, int S, int N, int L, float* out, cudaStream_t st) {
+  const long long total = (long long)B * N * N;
+  if (total == 0) return EK_OK;
+  onehot_adj_kernel<<<grid_for(total), 256, 0, st>>>(labels, S, N, L, total, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                   float wd, const float* pow_state, cudaStream_t st) {
+  if (n == 0) return EK_OK;
+  adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, pow_state);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_adam_advance_launch(float* pow_state, float b1, float b2, cudaStream_t st) {
+  adam_advance_kernel<<<1, 1, 0, st>>>(pow_state, b1, b2);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}

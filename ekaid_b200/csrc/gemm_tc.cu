@@ -1,0 +1,516 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared-memory ring ->
+// tcgen05.mma (single elected thread, fp32 accumulators in TMEM, double-buffered) -> tcgen05.ld epilogue.
+//
+//   C[M,N] = op(A) * op(B),  A(m,k), B(k,n) bf16;  fp32 accumulate;  fused epilogue (epilogue.cuh)
+//
+// Operand layouts (both served straight from the row-major tensors the rest of the path keeps in HBM,
+// no transposed copies):
+//   A_MN = 0: A stored [M, K] (K contiguous)   -> K-major UMMA operand      (forward, dgrad)
+//   A_MN = 1: A stored [K, M] (M contiguous)   -> MN-major UMMA operand     (wgrad: dY^T)
+//   B_MN = 0: B stored [N, K] (K contiguous)   -> K-major                   (forward: weight [out,in])
+//   B_MN = 1: B stored [K, N] (N contiguous)   -> MN-major                  (dgrad: weight, wgrad: X)
+//
+// Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
+// warps 2..5 = epilogue (one TMEM lane quarter each).  Tile 128 x BN x 64, BN in {64,128,256}.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <cstring>
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 1024) t0 = clock64();
+    if (spins > 1024 && (clock64() - t0) > 4000000000LL) {
+      printf("ekaid gemm_tc: mbarrier wait timeout (block %d thread %d parity %u)\n", blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+template <int BN, int A_MN, int B_MN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                    int K, EkEpilogue ep, int vec_ok, int splits) {
+  using C = Cfg<BN, A_MN, B_MN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = (num_kb + splits - 1) / splits;   // split-K: unit = (tile, split)
+  const int num_units = num_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int tile = unit % num_tiles;
+        const int kb0 = (unit / num_tiles) * kb_per;
+        const int kb1 = min(kb0 + kb_per, num_kb);
+        const int m0 = (tile % num_m) * BM;
+        const int n0 = (tile / num_m) * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN == 0) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                 // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)                                   // box {64 m, 64 k}
+              tma_load_2d(&tmA, &full_bar[stage], sa + i * (64 * BK * 2), m0 + 64 * i, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);                 // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)                                   // box {64 n, 64 k}
+              tma_load_2d(&tmB, &full_bar[stage], sb + i * (64 * BK * 2), n0 + 64 * i, k0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accum, bf16 x bf16
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int kb0 = (unit / num_tiles) * kb_per;
+        const int kb1 = min(kb0 + kb_per, num_kb);
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 8-row groups 1024 B apart, k-step = 32 B inside the swizzle span.
+            // MN-major: 64-element column chunks 8 KB apart (LBO), 8-k-row groups 1024 B apart (SBO),
+            //           k-step = 16 rows * 128 B.
+            const uint64_t adesc = A_MN ? make_smem_desc(sa + k * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                        : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                        : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[buf]);              // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (2..5)
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const int tile = unit % num_tiles;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile % num_m) * BM;
+      const int n0 = (tile / num_m) * BN;
+      mbar_wait(&tfull_bar[buf], acc_phase);
+      tc_fence_after();
+      const long long m = (long long)m0 + q * 32 + lane;
+      const bool row_ok = m < M;
+      const float* rowb_ptr = nullptr;
+      if (ep.rowb && row_ok) {
+        if (ep.rowflag && ep.rowflag[m]) rowb_ptr = ep.rowb_alt;
+        else rowb_ptr = ep.rowb + (long long)((m / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nb = n0 + c * 32;
+        if (nb >= N) break;                      // warp-uniform
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+        tc_wait_ld();
+        if (!row_ok) continue;
+        if (splits > 1) {                        // split-K partial sums: fp32 reduction in L2
+          float* cp = ep.C + m * ep.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < N) atomicAdd(cp + j, __uint_as_float(r[j]));
+        } else if (vec_ok && nb + 32 <= N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg((const float4*)(ep.bias + nb + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (ep.addend) {
+            const float* ap = ep.addend + m * ep.ldadd + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a4 = *(const float4*)(ap + j);
+              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+            }
+          }
+          if (rowb_ptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a4 = __ldg((const float4*)(rowb_ptr + nb + j));
+              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+            }
+          }
+          if (ep.act != EK_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ek_act(v[j], ep.act);
+          }
+          if (ep.C) {
+            float* cp = ep.C + m * ep.ldc + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (ep.Cb) {
+            bf16* cp = ep.Cb + m * ep.ldcb + nb;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
+              *(uint4*)(cp + j) = pk;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n < N) {
+              // ek_epilogue_store recomputes the row-broadcast pointer; fine on this cold path
+              ek_epilogue_store(ep, m, n, __uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  long long rows, cols, ld;
+  int box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = (size_t)k.ptr;
+    h ^= (size_t)k.rows * 1000003u + (size_t)k.cols * 10007u + (size_t)k.ld * 131u + (size_t)k.box_rows;
+    return h;
+  }
+};
+
+// 2-D bf16 row-major [rows, cols] with pitch ld; box = {64 cols, box_rows}, SWIZZLE_128B, zero OOB fill.
+int make_tmap(CUtensorMap* out, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{ptr, rows, cols, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return EK_OK; }
+  }
+  PFN_encodeTiled enc = get_encode();
+  EK_REQUIRE(enc != nullptr, EK_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  EK_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld % 8) == 0, EK_ERR_ALIGN,
+             "gemm_tc: operand must be 16-byte aligned with pitch %% 8 == 0 (ptr=%p ld=%lld)", ptr, ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EK_REQUIRE(r == CUDA_SUCCESS, EK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+             rows, cols, ld);
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return EK_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int A_MN, int B_MN>
+int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep, int vec_ok,
+               int splits, cudaStream_t stream) {
+  using C = Cfg<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cannot set smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int units = ek_div_up(M, BM) * ek_div_up(N, BN) * splits;
+  const int grid = units < num_sms() ? units : num_sms();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep, vec_ok, splits);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+template <int A_MN, int B_MN>
+int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep,
+              int vec_ok, int splits, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_cfg<64, A_MN, B_MN>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    case 128: return launch_cfg<128, A_MN, B_MN>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    default: return launch_cfg<256, A_MN, B_MN>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+  }
+}
+
+}  // namespace
+
+// transA: A stored [K, M];  transB: B stored [K, N]  (see file header)
+int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
+                           long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream) {
+  EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
+  // tile-N choice: fewest wasted SM-slots over whole waves, ties to the wider tile
+  int bn = 256;
+  if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
+    bn = force_bn;
+  } else {
+    double best = -1;
+    const int cand[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      const int c = cand[i];
+      const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, c);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      // useful fraction of issued MMA work: (real N columns / padded) * (tiles / slots); wide tiles are
+      // ~10% more efficient per flop (fewer A re-reads, shorter epilogue share)
+      const double useful = (double)N / ((double)ek_div_up(N, c) * c) * (double)tiles / (double)(waves * num_sms());
+      const double score = useful * (c == 256 ? 1.0 : (c == 128 ? 0.92 : 0.8));
+      if (score > best) { best = score; bn = c; }
+    }
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);   // [M rows, K cols], box {64, 128}
+  else rc = make_tmap(&ta, A, K, M, lda, BK);           // [K rows, M cols], box {64, 64}
+  if (rc) return rc;
+  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, bn);   // [N rows, K cols], box {64, bn}
+  else rc = make_tmap(&tb, B, K, N, ldb, BK);           // [K rows, N cols], box {64, 64}
+  if (rc) return rc;
+  int vec_ok = 1;
+  if (ep.C && (((uintptr_t)ep.C & 15) || (ep.ldc & 3))) vec_ok = 0;
+  if (ep.Cb && (((uintptr_t)ep.Cb & 15) || (ep.ldcb & 7))) vec_ok = 0;
+  if (ep.bias && ((uintptr_t)ep.bias & 15)) vec_ok = 0;
+  if (ep.addend && (((uintptr_t)ep.addend & 15) || (ep.ldadd & 3))) vec_ok = 0;
+  if (ep.rowb && (((uintptr_t)ep.rowb & 15) || (ep.ldrowb & 3) || ((uintptr_t)ep.rowb_alt & 15))) vec_ok = 0;
+  // split-K (auto when splits == 0): only for plain fp32 outputs with too few tiles to fill the chip
+  const bool plain = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE;
+  const int num_kb = ek_div_up(K, BK);
+  if (splits <= 0) {
+    splits = 1;
+    const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, bn);
+    if (plain && tiles * 2 <= num_sms() && num_kb >= 16) {
+      splits = (int)(num_sms() / tiles);
+      if (splits > num_kb / 8) splits = num_kb / 8;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (splits > 1) {
+    EK_REQUIRE(plain, EK_ERR_UNSUPPORTED, "gemm_tc: split-K needs a plain fp32 epilogue");
+    const int kb_per = ek_div_up(num_kb, splits);
+    splits = ek_div_up(num_kb, kb_per);        // no empty splits
+    if (splits > 1) {
+      cudaError_t e = cudaMemset2DAsync(ep.C, (size_t)ep.ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+      EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: memset failed: %s", cudaGetErrorString(e));
+    }
+  }
+  if (!transA && !transB) return launch_bn<0, 0>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
+  if (!transA && transB) return launch_bn<0, 1>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
+  if (transA && !transB) return launch_bn<1, 0>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
+  return launch_bn<1, 1>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
+}

@@ -1,0 +1,493 @@
+"""autograd.Functions that drive the sm_100a kernels through the C ABI (ekaid_b200.lib).
+
+Four stages make up the hot path; each has a hand-written forward and backward:
+
+  QuestionFn   word embedding gather -> GRU (20 steps) -> tanh-MLP attention with the batch-axis softmax (Q4)
+  LinearFn     y = x W^T + b                              (ROI projection `img`, modules.py:195-196)
+  RelationFn   one relation encoder step, in closed form (Q1-Q3, Q5-Q7, Q9, Q10, Q13):
+               self_feat GEMM (question half broadcast per sample) -> ONE GEMM for [query | key | Z_h] ->
+               fused edge kernels -> X + relu(2 out)
+  FusionFn     graph combine + difference -> gated fusion -> embed/att -> attention pooling (modules.py:233-308)
+
+Tensors that feed GEMMs are kept in the operand type T of the precision mode: bf16 (tcgen05 path) or fp32
+(SIMT parity path).  Residual stream, softmax, reductions and all gradients of parameters are fp32.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import lib
+from .lib import Epilogue, call, ptr
+
+ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
+
+
+class PC:
+    """precision config: 'bf16' (tensor cores) or 'fp32' (SIMT, 1e-4 parity mode)."""
+
+    def __init__(self, precision: str):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
+        self.bf16 = precision == "bf16"
+        self.T = torch.bfloat16 if self.bf16 else torch.float32
+        self.f = 1 if self.bf16 else 0
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers
+# ------------------------------------------------------------------------------------------------
+def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None, rowb_div=1, rowb_mod=1,
+         rowflag=None, rowb_alt=None, act=ACT_NONE, C=None, Cb=None, splits=0, force_bn=0):
+    """C[M,N] = op(A) op(B) with the fused epilogue; dtype of A selects tcgen05 (bf16) or SIMT (fp32)."""
+    ep = Epilogue()
+    ep.bias = ptr(bias)
+    ep.addend = ptr(addend)
+    ep.ldadd = addend.stride(0) if addend is not None else 0
+    ep.rowb = ptr(rowb)
+    ep.ldrowb = rowb.stride(0) if rowb is not None else 0
+    ep.rowb_div, ep.rowb_mod = rowb_div, rowb_mod
+    ep.rowflag = ptr(rowflag)
+    ep.rowb_alt = ptr(rowb_alt)
+    ep.act = act
+    ep.C = ptr(C)
+    ep.ldc = C.stride(0) if C is not None else 0
+    ep.Cb = ptr(Cb)
+    ep.ldcb = Cb.stride(0) if Cb is not None else 0
+    assert A.dtype == B.dtype and A.stride(-1) == 1 and B.stride(-1) == 1
+    if A.dtype == torch.bfloat16:
+        call("gemm_bf16", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+             ctypes.addressof(ep), force_bn, splits)
+    else:
+        assert A.dtype == torch.float32 and Cb is None
+        call("gemm_f32", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+             ctypes.addressof(ep))
+
+
+def gemm_T(pc: PC, A, B, M, N, K, transA=0, transB=0, *, want_f32=False, **kw):
+    """GEMM whose result is needed in the operand type T (and optionally also in fp32)."""
+    dev = A.device
+    if pc.bf16:
+        Cb = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+        C = torch.empty(M, N, dtype=torch.float32, device=dev) if want_f32 else None
+        gemm(A, B, M, N, K, transA, transB, C=C, Cb=Cb, **kw)
+        return Cb, C
+    C = torch.empty(M, N, dtype=torch.float32, device=dev)
+    gemm(A, B, M, N, K, transA, transB, C=C, **kw)
+    return C, C
+
+
+def gemm_f32out(A, B, M, N, K, transA=0, transB=0, out=None, **kw):
+    C = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=A.device)
+    gemm(A, B, M, N, K, transA, transB, C=C, **kw)
+    return C
+
+
+def to_T(pc: PC, w: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor -> operand type (own cast kernel for bf16; identity for fp32)."""
+    w = w.detach()
+    if w.dim() == 1:
+        w = w.view(1, -1)
+    if not w.is_contiguous():
+        w = w.contiguous()
+    if not pc.bf16:
+        return w
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    call("cast_f32_bf16", w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), w.shape[0], w.shape[1])
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(dev, n):
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < n:
+        ws = torch.empty(max(n, 64 * 8192), dtype=torch.float32, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def colsum(src, M, N, rowscale=None):
+    """out[n] = sum_m rowscale[m] * src[m, n]  (fp32 result)."""
+    out = torch.empty(N, dtype=torch.float32, device=src.device)
+    ws = torch.empty(64 * N, dtype=torch.float32, device=src.device)
+    call("colsum", 1 if src.dtype == torch.bfloat16 else 0, src.data_ptr(), src.stride(0) if src.dim() == 2 else 1,
+         M, N, ptr(rowscale), out.data_ptr(), ws.data_ptr())
+    return out
+
+
+def _f32c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# y = x W^T + b
+# ------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """nn.Linear (modules.py:93,195-196).  `x2` (optional) is stacked under `x` along the row axis so the main and
+    the reference image of every pair go through ONE GEMM.  Returns (y fp32 [rows, N], y in operand type or None)."""
+
+    @staticmethod
+    def forward(ctx, pc: PC, x, x2, W, b):
+        lib.require_device()
+        dev = x.device
+        K = x.shape[-1]
+        xa = _f32c(x).view(-1, K)
+        Ma = xa.shape[0]
+        Mb = 0
+        if x2 is not None:
+            xb = _f32c(x2).view(-1, K)
+            Mb = xb.shape[0]
+        M = Ma + Mb
+        N = W.shape[0]
+        xT = torch.empty(M, K, dtype=pc.T, device=dev)
+        fn = "cast_f32_bf16" if pc.bf16 else "copy_f32"
+        call(fn, xa.data_ptr(), K, xT.data_ptr(), K, Ma, K)
+        if Mb:
+            call(fn, xb.data_ptr(), K, xT[Ma:].data_ptr(), K, Mb, K)
+        WT = to_T(pc, W)
+        bb = _f32c(b) if b is not None else None
+        y = torch.empty(M, N, dtype=torch.float32, device=dev)
+        yT = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if pc.bf16 else None
+        gemm(xT, WT, M, N, K, bias=bb, C=y, Cb=yT)
+        ctx.pc, ctx.xT, ctx.WT, ctx.has_b = pc, xT, WT, b is not None
+        ctx.need = (x.requires_grad, x2 is not None and x2.requires_grad)
+        ctx.shapes = (x.shape, x2.shape if x2 is not None else None, Ma)
+        if yT is not None:
+            ctx.mark_non_differentiable(yT)
+        return y, yT
+
+    @staticmethod
+    def backward(ctx, dy, _dyT=None):
+        pc = ctx.pc
+        dy2 = _f32c(dy).view(-1, dy.shape[-1])
+        M, N = dy2.shape
+        K = ctx.xT.shape[1]
+        dyT = to_T(pc, dy2)
+        dW = gemm_f32out(dyT, ctx.xT, N, K, M, transA=1, transB=1)
+        db = colsum(dy2, M, N) if ctx.has_b else None
+        dx = dx2 = None
+        if ctx.need[0] or ctx.need[1]:
+            dfull = gemm_f32out(dyT, ctx.WT, M, K, N, transB=1)
+            sa, sb, Ma = ctx.shapes
+            if ctx.need[0]:
+                dx = dfull[:Ma].view(sa)
+            if ctx.need[1]:
+                dx2 = dfull[Ma:].view(sb)
+        return None, dx, dx2, dW, db
+
+
+# ------------------------------------------------------------------------------------------------
+# question path
+# ------------------------------------------------------------------------------------------------
+class QuestionFn(torch.autograd.Function):
+    """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156)."""
+
+    @staticmethod
+    def forward(ctx, pc: PC, question, emb, emb2, Wih, Whh, bih, bhh, W1, b1, w2, b2):
+        lib.require_device()
+        dev = emb.device
+        B, L = question.shape
+        ed = emb.shape[1]
+        H = Whh.shape[1]
+        q = question.detach().to(torch.int64).contiguous()
+        embc, emb2c = _f32c(emb), _f32c(emb2)
+        E = torch.empty(L * B, 2 * ed, dtype=pc.T, device=dev)
+        call("embed_gather", pc.f, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
+        WihT, WhhT, W1T = to_T(pc, Wih), to_T(pc, Whh), to_T(pc, W1)
+        bihc, bhhc, b1c, w2c, b2c = _f32c(bih), _f32c(bhh), _f32c(b1), _f32c(w2).view(-1), _f32c(b2).view(-1)
+        gi = gemm_f32out(E, WihT, L * B, 3 * H, 2 * ed, bias=bihc)
+        Hs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
+        # operand-type copy with one leading zero block: HsT[t] = h_{t-1}, so "previous h of every step" is a view
+        HsT = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev)
+        gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
+        gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
+        for t in range(L):
+            gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, bias=bhhc, C=gh)
+            hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+            call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
+                 Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr())
+        HsT_cur = HsT[B:]
+        a1, _ = gemm_T(pc, HsT_cur, W1T, L * B, H, H, bias=b1c, act=ACT_TANH)
+        a = torch.empty(L * B, dtype=torch.float32, device=dev)
+        call("rowdot", pc.f, a1.data_ptr(), a1.stride(0), L * B, H, w2c.data_ptr(), b2c.data_ptr(), a.data_ptr())
+        S = torch.empty(L * B, dtype=torch.float32, device=dev)
+        qv = torch.empty(B, H, dtype=torch.float32, device=dev)
+        call("qpool_fwd", a.data_ptr(), Hs.data_ptr(), B, L, H, S.data_ptr(), qv.data_ptr())
+        ctx.pc = pc
+        ctx.dims = (B, L, ed, H, emb.shape[0])
+        ctx.saved = (q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S)
+        return qv
+
+    @staticmethod
+    def backward(ctx, dqv):
+        pc = ctx.pc
+        B, L, ed, H, V = ctx.dims
+        q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S = ctx.saved
+        dev = Hs.device
+        dqv = _f32c(dqv)
+        dS = torch.empty(L * B, dtype=torch.float32, device=dev)
+        da = torch.empty(L * B, dtype=torch.float32, device=dev)
+        dHs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
+        call("qpool_bwd", dqv.data_ptr(), S.data_ptr(), Hs.data_ptr(), B, L, H, dS.data_ptr(), da.data_ptr(),
+             dHs.data_ptr())
+        dpre = torch.empty(L * B, H, dtype=pc.T, device=dev)
+        call("qatt_tanh_bwd", pc.f, da.data_ptr(), w2c.data_ptr(), a1.data_ptr(), L * B, H, dpre.data_ptr())
+        dw2 = colsum(a1, L * B, H, rowscale=da).view(1, H)
+        db2 = colsum(da.view(-1, 1), L * B, 1)
+        HsT_cur = HsT[B:]
+        dW1 = gemm_f32out(dpre, HsT_cur, H, H, L * B, transA=1, transB=1)
+        db1 = colsum(dpre, L * B, H)
+        gemm(dpre, W1T, L * B, H, H, transB=1, addend=dHs, C=dHs)         # dHs += dpre W1
+        # BPTT
+        dgi = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
+        dgh = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
+        dgiT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgi
+        dghT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgh
+        carry = torch.empty(B, H, dtype=torch.float32, device=dev)
+        dhz = torch.empty(B, H, dtype=torch.float32, device=dev)
+        for t in range(L - 1, -1, -1):
+            sl = slice(t * B, (t + 1) * B)
+            if t < L - 1:
+                call("add_inplace", dHs[sl].data_ptr(), carry.data_ptr(), B * H)
+            hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+            call("gru_cell_bwd", pc.f, dHs[sl].data_ptr(), gates[t].data_ptr(), ptr(hprev), B, H, dgi[sl].data_ptr(),
+                 dgh[sl].data_ptr(), dgiT[sl].data_ptr() if pc.bf16 else None,
+                 dghT[sl].data_ptr() if pc.bf16 else None, dhz.data_ptr())
+            if t > 0:
+                gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=dhz, C=carry)   # carry = dh*z + dgh W_hh
+        dWih = gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1)
+        dbih = colsum(dgi, L * B, 3 * H)
+        dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1)
+        dbhh = colsum(dgh, L * B, 3 * H)
+        dE = gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1)           # only the trainable table's columns
+        demb = torch.empty(V, ed, dtype=torch.float32, device=dev)
+        call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr())
+        return None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
+
+
+# ------------------------------------------------------------------------------------------------
+# one relation encoder step
+# ------------------------------------------------------------------------------------------------
+_dim_t_cache = {}
+
+
+def _dim_t(dev, feat_dim=64, wave_length=1000.0):
+    """The wave lengths exactly as utils/mimic_utils.py:195-197 computes them (fp32)."""
+    key = (str(dev), feat_dim)
+    if key not in _dim_t_cache:
+        feat_range = torch.arange(0, feat_dim / 8)
+        dim_mat = torch.pow(torch.ones((1,)) * wave_length, (8.0 / feat_dim) * feat_range)
+        _dim_t_cache[key] = dim_mat.float().contiguous().to(dev)
+    return _dim_t_cache[key]
+
+
+class RelationFn(torch.autograd.Function):
+    """X <- X + relu(2 * GAT_dir1(cat(X, q)))  for G stacked images (G = S*B; image g uses question g % B).
+
+    kind 'explicit': adj0/adj1 are one-hot/float adjacency [*, N, N, L]; wb = effective label-bias table [L].
+    kind 'implicit': adj0/adj1 are fp64 boxes [*, N, 4] (device); Wp [H,64], bp [H] = effective pair_pos_fc1.
+    Images [0, g_split) read adj0, the rest adj1."""
+
+    @staticmethod
+    def forward(ctx, pc: PC, kind: str, dims, X, XT, qv, Wsw, bsw, Wqkz, bqkz, bout, p0, p1, adj0, adj1, g_split):
+        lib.require_device()
+        G, B, N, Kn, D, H = dims
+        dev = X.device
+        M = G * N
+        X = _f32c(X).view(M, D)
+        qv = _f32c(qv)
+        if XT is None or XT.dtype != pc.T:
+            XT = to_T(pc, X)
+        WswT, WqkzT = to_T(pc, Wsw), to_T(pc, Wqkz)
+        Wsw32 = _f32c(Wsw)
+        bswc, bqkzc, boutc = _f32c(bsw), _f32c(bqkz), _f32c(bout)
+        flags = torch.empty(M, dtype=torch.uint8, device=dev)
+        call("row_zero_flags", X.data_ptr(), M, D, flags.data_ptr())
+        # question half of self_weights, once per sample (fp32 SIMT GEMM, M = B rows)
+        qpart = gemm_f32out(qv, Wsw32[:, D:], B, D, qv.shape[1], bias=bswc)
+        Sf, _ = gemm_T(pc, XT, WswT[:, :D], M, D, D, rowb=qpart, rowb_div=N, rowb_mod=B, rowflag=flags,
+                       rowb_alt=bswc)
+        W = (2 + H) * D
+        QKZ, _ = gemm_T(pc, Sf, WqkzT, M, W, D, bias=bqkzc)
+        cond = lbias = gbias = None
+        if kind == "explicit":
+            a0 = _f32c(adj0)
+            a1 = _f32c(adj1) if adj1 is not None else None
+            Lb = a0.shape[-1]
+            if a0.shape[1] != N or a0.shape[2] != N or (a1 is not None and a1.shape[1:] != a0.shape[1:]):
+                raise ValueError("adjacency must be [*, %d, %d, labels], got %s" % (N, N, tuple(a0.shape)))
+            wb = _f32c(p0).view(-1)
+            cond = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
+            lbias = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
+            call("adj_prep_fwd", a0.data_ptr(), ptr(a1), g_split, wb.data_ptr(), G, N, Kn, Lb, cond.data_ptr(),
+                 lbias.data_ptr())
+            ctx.geo = (a0, a1, Lb)
+        else:
+            a0 = adj0.detach().to(device=dev, dtype=torch.float64).contiguous()
+            a1 = adj1.detach().to(device=dev, dtype=torch.float64).contiguous() if adj1 is not None else None
+            Wp, bp = _f32c(p0), _f32c(p1)
+            gbias = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
+            call("geom_bias_fwd", a0.data_ptr(), ptr(a1), g_split, Wp.data_ptr(), bp.data_ptr(),
+                 _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr())
+            ctx.geo = (a0, a1, Wp, bp)
+        P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
+        call("edge_softmax_fwd", pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond), ptr(lbias), ptr(gbias), G, N, Kn, H,
+             P.data_ptr())
+        Xn = torch.empty(M, D, dtype=torch.float32, device=dev)
+        XnT = torch.empty(M, D, dtype=pc.T, device=dev) if pc.bf16 else None
+        mask = torch.empty(M, D, dtype=torch.uint8, device=dev)
+        call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, boutc.data_ptr(), X.data_ptr(),
+             G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr())
+        ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
+        ctx.saved = (XT, qv, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask)
+        if XnT is not None:
+            ctx.mark_non_differentiable(P, XnT)
+        else:
+            ctx.mark_non_differentiable(P)
+        return Xn, XnT, P
+
+    @staticmethod
+    def backward(ctx, dXn, _dXnT, _dP):
+        pc, kind = ctx.pc, ctx.kind
+        G, B, N, Kn, D, H = ctx.dims
+        XT, qv, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask = ctx.saved
+        dev = P.device
+        M = G * N
+        W = (2 + H) * D
+        dXn = _f32c(dXn).view(M, D)
+        ns = lib.load().ekaid_edge_num_slices(D)
+        alloc = torch.zeros if N > Kn else torch.empty
+        dQKZ = alloc(M, W, dtype=pc.T, device=dev)
+        dOut = torch.empty(M, D, dtype=torch.float32, device=dev)
+        dPpart = torch.empty(ns, G, N, H, Kn, dtype=torch.float32, device=dev)
+        call("edge_aggregate_bwd", pc.f, dXn.data_ptr(), mask.data_ptr(), P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D,
+             G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr())
+        dbout = colsum(dOut, M, D)
+        dlb = dgb = None
+        if kind == "explicit":
+            dlb = torch.empty(H, G, N, Kn, dtype=torch.float32, device=dev)
+        else:
+            dgb = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
+        call("edge_softmax_bwd", pc.f, P.data_ptr(), dPpart.data_ptr(), ns, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond),
+             G, N, Kn, H, dQKZ.data_ptr(), ptr(dlb), ptr(dgb))
+        dp0 = dp1 = None
+        if kind == "explicit":
+            a0, a1, Lb = ctx.geo
+            part = torch.empty(G, Lb, dtype=torch.float32, device=dev)
+            call("adj_prep_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, dlb.data_ptr(), H, G, N, Kn, Lb, part.data_ptr())
+            dp0 = colsum(part, G, Lb).view(1, Lb)
+        else:
+            a0, a1, Wp, bp = ctx.geo
+            part = torch.empty(G, H * 65, dtype=torch.float32, device=dev)
+            call("geom_bias_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, Wp.data_ptr(), bp.data_ptr(),
+                 _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr())
+            tot = colsum(part, G, H * 65).view(H, 65)
+            dp0, dp1 = tot[:, :64].contiguous(), tot[:, 64].contiguous()
+        # [query | key | Z] projection
+        dWqkz = gemm_f32out(dQKZ, Sf, W, D, M, transA=1, transB=1)
+        dbqkz = colsum(dQKZ, M, W)
+        dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
+        # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
+        dWsw = torch.empty(D, Wsw32.shape[1], dtype=torch.float32, device=dev)
+        gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
+        dbsw = colsum(dSf, M, D)
+        dqpart = torch.empty(B, D, dtype=torch.float32, device=dev)
+        call("group_rowsum", pc.f, dSf.data_ptr(), dSf.stride(0), N, B, G // B, D, flags.data_ptr(), dqpart.data_ptr())
+        Dq = qv.shape[1]
+        gemm(dqpart, qv, D, Dq, B, transA=1, transB=1, C=dWsw[:, D:])       # fp32 SIMT (K = B)
+        dqv = gemm_f32out(dqpart, Wsw32[:, D:], B, Dq, D, transB=1)
+        dX = torch.empty(M, D, dtype=torch.float32, device=dev)
+        gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
+        return (None, None, None, dX, None, dqv, dWsw, dbsw, dWqkz, dbqkz, dbout, dp0, dp1, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# difference + gated fusion + attention pooling
+# ------------------------------------------------------------------------------------------------
+class FusionFn(torch.autograd.Function):
+    """modules.py:233-308 for the stacked [bef; aft] residual stream X3 [2*B*N, D].
+
+    Wcg [2D, 2D] = [[context2 | context1], [gate2 | gate1]], bcg = [b_context2 ; b_gate2]; We [dim, 3D], be;
+    wa [1, dim], ba [1].  Returns att [2BN] and attended [2B, D]."""
+
+    @staticmethod
+    def forward(ctx, pc: PC, dims, mode, coefs, X3, Wcg, bcg, We, be, wa, ba):
+        lib.require_device()
+        B, N, D, dim = dims
+        dev = X3.device
+        BN = B * N
+        M = 2 * BN
+        X3 = _f32c(X3).view(M, D)
+        c1, c2, c3 = coefs
+        Xc = torch.empty(M, D, dtype=torch.float32, device=dev)
+        CAT = torch.empty(M, 3 * D, dtype=pc.T, device=dev)
+        call("combine_diff_fwd", pc.f, X3.data_ptr(), BN, D, mode, c1, c2, c3, Xc.data_ptr(), CAT.data_ptr())
+        WcgT, WeT = to_T(pc, Wcg), to_T(pc, We)
+        bcgc, bec, wac, bac = _f32c(bcg), _f32c(be), _f32c(wa).view(-1), _f32c(ba).view(-1)
+        pre = gemm_f32out(CAT[:, :2 * D], WcgT, M, 2 * D, 2 * D, bias=bcgc)
+        cx = torch.empty(M, D, dtype=pc.T, device=dev)
+        gt = torch.empty(M, D, dtype=pc.T, device=dev)
+        call("gate_fwd", pc.f, pre.data_ptr(), M, D, cx.data_ptr(), gt.data_ptr(), CAT.data_ptr())
+        E = gemm_f32out(CAT, WeT, M, dim, 3 * D, bias=bec, act=ACT_RELU)
+        att = torch.empty(M, dtype=torch.float32, device=dev)
+        attended = torch.empty(2 * B, D, dtype=torch.float32, device=dev)
+        call("att_pool_fwd", E.data_ptr(), M, N, D, dim, wac.data_ptr(), bac.data_ptr(), Xc.data_ptr(), att.data_ptr(),
+             attended.data_ptr())
+        ctx.pc, ctx.dims, ctx.mode, ctx.coefs = pc, dims, mode, coefs
+        ctx.saved = (Xc, CAT, WcgT, WeT, wac, cx, gt, E, att)
+        return att, attended
+
+    @staticmethod
+    def backward(ctx, datt, dattended):
+        pc = ctx.pc
+        B, N, D, dim = ctx.dims
+        Xc, CAT, WcgT, WeT, wac, cx, gt, E, att = ctx.saved
+        dev = Xc.device
+        BN = B * N
+        M = 2 * BN
+        c1, c2, c3 = ctx.coefs
+        dA = _f32c(dattended) if dattended is not None else torch.zeros(2 * B, D, dtype=torch.float32, device=dev)
+        dw_ = _f32c(datt).view(-1) if datt is not None else None
+        dXc = torch.empty(M, D, dtype=torch.float32, device=dev)
+        dE = torch.empty(M, dim, dtype=pc.T, device=dev)
+        dpa = torch.empty(M, dtype=torch.float32, device=dev)
+        call("att_pool_bwd", pc.f, dA.data_ptr(), ptr(dw_), att.data_ptr(), Xc.data_ptr(), E.data_ptr(), wac.data_ptr(),
+             M, N, D, dim, dXc.data_ptr(), dE.data_ptr(), dpa.data_ptr())
+        dwa = colsum(E, M, dim, rowscale=dpa).view(1, dim)
+        dba = colsum(dpa.view(-1, 1), M, 1)
+        dWe = gemm_f32out(dE, CAT, dim, 3 * D, M, transA=1, transB=1)
+        dbe = colsum(dE, M, dim)
+        dCAT = gemm_f32out(dE, WeT, M, 3 * D, dim, transB=1)
+        dpre = torch.empty(M, 2 * D, dtype=pc.T, device=dev)
+        call("gate_bwd", pc.f, dCAT.data_ptr(), cx.data_ptr(), gt.data_ptr(), M, D, dpre.data_ptr())
+        dWcg = gemm_f32out(dpre, CAT[:, :2 * D], 2 * D, 2 * D, M, transA=1, transB=1)
+        dbcg = colsum(dpre, M, 2 * D)
+        gemm(dpre, WcgT, M, 2 * D, 2 * D, transB=1, addend=dCAT[:, :2 * D], C=dCAT[:, :2 * D])
+        dX3 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        call("combine_diff_bwd", dXc.data_ptr(), dCAT.data_ptr(), BN, D, ctx.mode, c1, c2, c3, dX3.data_ptr())
+        return None, None, None, None, dX3, dWcg, dbcg, dWe, dbe, dwa, dba
+
+
+# ------------------------------------------------------------------------------------------------
+# step glue
+# ------------------------------------------------------------------------------------------------
+def onehot_adj(labels: torch.Tensor, num_objects: int, label_num: int) -> torch.Tensor:
+    """process_matrix (utils/mimic_utils.py:141-149) as one kernel: labels [B,S,S] (any real dtype) on the device
+    -> fp32 one-hot [B,N,N,L]."""
+    lib.require_device()
+    lab = labels.detach()
+    if lab.dtype != torch.float64:
+        lab = lab.double()
+    lab = lab.contiguous()
+    Bn, S = lab.shape[0], lab.shape[1]
+    out = torch.empty(Bn, num_objects, num_objects, label_num, dtype=torch.float32, device=lab.device)
+    call("onehot_adj", lab.data_ptr(), Bn, S, num_objects, label_num, out.data_ptr())
+    return out

@@ -1,0 +1,110 @@
+"""ctypes binding of libekaid_b200.so (the C ABI declared in include/ekaid_b200.h).
+
+The prototypes are parsed from the header so the binding can never drift from the declared ABI.
+There is no CPU fallback: if the shared library is missing the import of a kernel fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "ekaid_b200.h")
+LIB_PATH = os.path.join(_HERE, "libekaid_b200.so")
+
+
+class Epilogue(ctypes.Structure):
+    """struct ekaid_epilogue (include/ekaid_b200.h)."""
+    _fields_ = [
+        ("bias", ctypes.c_void_p), ("addend", ctypes.c_void_p), ("ldadd", ctypes.c_int64),
+        ("rowb", ctypes.c_void_p), ("ldrowb", ctypes.c_int64), ("rowb_div", ctypes.c_int32),
+        ("rowb_mod", ctypes.c_int32), ("rowflag", ctypes.c_void_p), ("rowb_alt", ctypes.c_void_p),
+        ("act", ctypes.c_int32), ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
+        ("Cb", ctypes.c_void_p), ("ldcb", ctypes.c_int64),
+    ]
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[str]]]:
+    """{name: (return type, [param types])} for every `ekaid_*` prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|const char\*)\s+(ekaid_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, params = m.group(1), m.group(2), m.group(3).strip()
+        types = []
+        if params and params != "void":
+            for p in params.split(","):
+                p = " ".join(p.split())
+                if "*" in p:
+                    types.append("ptr")
+                else:
+                    types.append(p.rsplit(" ", 1)[0])
+        protos[name] = (ret, types)
+    return protos
+
+
+_CT = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
+       "ptr": ctypes.c_void_p}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ekaid_b200.build` "
+            "(there is deliberately no CPU / PyTorch fallback for the CUDA path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (ret, types) in parse_header().items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_char_p if ret != "int" else ctypes.c_int
+        fn.argtypes = [_CT[t] for t in types]
+    _lib = lib
+    return lib
+
+
+class EkaidError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().ekaid_last_error().decode()
+        if rc in (-1, -2, -5):
+            raise ValueError(f"{what}: {msg} (code {rc})")
+        raise EkaidError(f"{what}: {msg} (code {rc})")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def call(name: str, *args) -> None:
+    """Call `ekaid_<name>` on the current torch CUDA stream (appended as last argument)."""
+    lib = load()
+    rc = getattr(lib, "ekaid_" + name)(*args, stream_ptr())
+    check(rc, name)
+
+
+_device_ok = False
+
+
+def require_device() -> None:
+    global _device_ok
+    if _device_ok:
+        return
+    if not torch.cuda.is_available():
+        raise EkaidError("ekaid_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+    check(load().ekaid_check_device(), "check_device")
+    _device_ok = True

@@ -1,0 +1,441 @@
+"""Drop-in nn.Modules for the EKAID graph+fusion hot path.
+
+Same class names, constructor signatures, forward signatures, error behaviour and state_dict keys as the
+reference modules (paths relative to /root/reference/model):
+
+    ChangeDetector                      models/modules.py:81-313
+    ExplicitRelationEncoder,
+    ImplicitRelationEncoder,
+    q_expand_v_cat                      models/relation_encoder.py:19-132
+    GAttNet                             models/graph_att.py:17-106
+    GraphSelfAttentionLayer             models/graph_att_layer.py:19-178
+    FCNet                               models/fc.py:15-49
+    WordEmbedding, QuestionEmbedding,
+    QuestionSelfAttention               models/language_model.py:17-156
+
+The module tree only owns parameters; the arithmetic runs in hand-written sm_100a kernels reached through
+the C ABI (ekaid_b200.functions).  There is no PyTorch/CPU fallback: calling forward without a B200 raises.
+
+`precision`: 'bf16' (tcgen05 tensor cores, 2e-2 parity) or 'fp32' (SIMT, 1e-4 parity).  Default from the
+environment variable EKAID_B200_PRECISION, else 'bf16'; settable per module tree via `set_precision`.
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    from torch.nn.utils import weight_norm as _weight_norm
+
+from .functions import PC, FusionFn, LinearFn, QuestionFn, RelationFn
+
+
+def _default_precision() -> str:
+    return os.environ.get("EKAID_B200_PRECISION", "bf16")
+
+
+def _wn(module: nn.Module) -> nn.Module:
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return _weight_norm(module, dim=None)
+
+
+def wn_weight(lin: nn.Module) -> torch.Tensor:
+    """Effective weight of a legacy weight_norm(dim=None) layer: g * v / ||v||_F (fc.py:33-34)."""
+    v, g = lin.weight_v, lin.weight_g
+    return v * (g / v.norm())
+
+
+class FCNet(nn.Module):
+    """[Dropout] -> weight_norm(Linear, dim=None) -> [activation], stacked (models/fc.py:15-49)."""
+
+    def __init__(self, dims, act='ReLU', dropout=0, bias=True):
+        super().__init__()
+        layers = []
+        for i in range(len(dims) - 2):
+            if 0 < dropout:
+                layers.append(nn.Dropout(dropout))
+            layers.append(_wn(nn.Linear(dims[i], dims[i + 1], bias=bias)))
+            if '' != act and act is not None:
+                layers.append(getattr(nn, act)())
+        if 0 < dropout:
+            layers.append(nn.Dropout(dropout))
+        layers.append(_wn(nn.Linear(dims[-2], dims[-1], bias=bias)))
+        if '' != act and act is not None:
+            layers.append(getattr(nn, act)())
+        self.main = nn.Sequential(*layers)
+        self.precision = _default_precision()
+
+    def linear(self, idx: int = -1) -> nn.Module:
+        lins = [m for m in self.main if isinstance(m, nn.Linear)]
+        return lins[idx]
+
+    def forward(self, x):
+        pc = PC(self.precision)
+        out = x
+        for m in self.main:
+            if isinstance(m, nn.Linear):
+                shp = out.shape
+                y, _ = LinearFn.apply(pc, out.reshape(-1, shp[-1]), None, wn_weight(m), m.bias)
+                out = y.view(*shp[:-1], y.shape[-1])
+            else:
+                out = m(out)
+        return out
+
+
+def q_expand_v_cat(q, v, mask=True):
+    """models/relation_encoder.py:19-29 (kept for API compatibility; the CUDA path never materialises it)."""
+    q = q.view(q.size(0), 1, q.size(1))
+    q_expand = q.expand(-1, v.shape[1], -1).clone()
+    if mask:
+        q_expand = q_expand * (v.sum(-1, keepdim=True) != 0).to(q_expand.dtype)
+    return torch.cat((v, q_expand), dim=-1)
+
+
+class GraphSelfAttentionLayer(nn.Module):
+    """Parameter container with the reference layout (models/graph_att_layer.py:20-57).  Inside a relation
+    encoder its arithmetic is executed by RelationFn."""
+
+    def __init__(self, feat_dim, nongt_dim=20, pos_emb_dim=-1, num_heads=16, dropout=[0.2, 0.5]):
+        super().__init__()
+        self.fc_dim = num_heads
+        self.feat_dim = feat_dim
+        self.dim = (feat_dim, feat_dim, feat_dim)
+        self.dim_group = (int(self.dim[0] / num_heads), int(self.dim[1] / num_heads), int(self.dim[2] / num_heads))
+        self.num_heads = num_heads
+        self.pos_emb_dim = pos_emb_dim
+        if self.pos_emb_dim > 0:
+            self.pair_pos_fc1 = FCNet([pos_emb_dim, self.fc_dim], None, dropout[0])
+        self.query = FCNet([feat_dim, self.dim[0]], None, dropout[0])
+        self.nongt_dim = nongt_dim
+        self.key = FCNet([feat_dim, self.dim[1]], None, dropout[0])
+        # never called in the reference either (quirk Q3) but part of the state_dict
+        self.linear_out_ = _wn(nn.Conv2d(in_channels=self.fc_dim * feat_dim, out_channels=self.dim[2],
+                                         kernel_size=(1, 1), groups=self.fc_dim))
+        self.linear_out_2 = nn.Linear(self.fc_dim * feat_dim, self.dim[2])
+
+    def qkz_weight(self):
+        """[Wq ; Wk ; Z-blocks] so ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T."""
+        D, H = self.feat_dim, self.num_heads
+        wq = wn_weight(self.query.linear())
+        wk = wn_weight(self.key.linear())
+        wz = self.linear_out_2.weight.view(D, H, D).permute(1, 0, 2).reshape(H * D, D)
+        bz = self.linear_out_2.bias.new_zeros(H * D)
+        return torch.cat([wq, wk, wz], 0), torch.cat([self.query.linear().bias, self.key.linear().bias, bz], 0)
+
+    def forward(self, roi_feat, adj_matrix, position_embedding, label_biases_att):
+        raise NotImplementedError(
+            "GraphSelfAttentionLayer is executed inside the fused relation kernels; call the owning "
+            "ExplicitRelationEncoder / ImplicitRelationEncoder (or ChangeDetector) instead")
+
+
+class GAttNet(nn.Module):
+    """models/graph_att.py:17-106 (parameters) + the fused relation step."""
+
+    def __init__(self, dir_num, label_num, in_feat_dim, out_feat_dim, nongt_dim=20, dropout=0.2, label_bias=True,
+                 num_heads=16, pos_emb_dim=-1):
+        super().__init__()
+        assert dir_num <= 2, "Got more than two directions in a graph."
+        self.dir_num = dir_num
+        self.label_num = label_num
+        self.in_feat_dim = in_feat_dim
+        self.out_feat_dim = out_feat_dim
+        self.dropout = nn.Dropout(dropout)
+        self.self_weights = FCNet([in_feat_dim, out_feat_dim], '', dropout)
+        self.bias = FCNet([label_num, 1], '', 0, label_bias)
+        self.nongt_dim = nongt_dim
+        self.pos_emb_dim = pos_emb_dim
+        self.num_heads = num_heads
+        self.neighbor_net = nn.ModuleList([
+            GraphSelfAttentionLayer(pos_emb_dim=pos_emb_dim, num_heads=num_heads, feat_dim=out_feat_dim,
+                                    nongt_dim=nongt_dim) for _ in range(dir_num)])
+
+    def live_layer(self) -> GraphSelfAttentionLayer:
+        # quirk Q2: the output of every direction but the last is overwritten
+        return self.neighbor_net[self.dir_num - 1]
+
+    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N):
+        """X [G*N, D] -> X + relu(2 * attention output).  geo*: adjacency (explicit) or fp64 boxes (implicit)."""
+        D = self.out_feat_dim
+        layer = self.live_layer()
+        H = layer.num_heads
+        Kn = min(self.nongt_dim, N)
+        if self.dir_num != 2:
+            raise NotImplementedError("only dir_num == 2 (the reference configuration) is implemented")
+        sw = self.self_weights.linear()
+        Wqkz, bqkz = layer.qkz_weight()
+        if self.pos_emb_dim > 0:
+            pp = layer.pair_pos_fc1.linear()
+            kind, p0, p1 = "implicit", wn_weight(pp), pp.bias
+        else:
+            kind, p0, p1 = "explicit", wn_weight(self.bias.linear()), None
+        dims = (G, B, N, Kn, D, H)
+        return RelationFn.apply(pc, kind, dims, X, XT, q, wn_weight(sw), sw.bias, Wqkz, bqkz,
+                                layer.linear_out_2.bias, p0, p1, geo0, geo1, g_split)
+
+    def forward(self, v_feat, adj_matrix, pos_emb=None):
+        if self.pos_emb_dim > 0 and pos_emb is None:
+            raise ValueError(f"position embedding is set to None with pos_emb_dim {self.pos_emb_dim}")
+        elif self.pos_emb_dim < 0 and pos_emb is not None:
+            raise ValueError("position embedding is NOT None with pos_emb_dim < 0")
+        raise NotImplementedError(
+            "GAttNet consumes the concatenated [v | q] tensor in the reference; the CUDA path never builds it. "
+            "Call ExplicitRelationEncoder / ImplicitRelationEncoder.forward(v, adj_or_boxes, q)")
+
+
+def _maybe_inplace(v: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Reference encoders mutate and return their first argument (quirk Q1).  Outside autograd we do the same."""
+    if not torch.is_grad_enabled() or (not v.requires_grad and not out.requires_grad):
+        v.copy_(out.view_as(v))
+        return v
+    return out.view_as(v)
+
+
+class ImplicitRelationEncoder(nn.Module):
+    """models/relation_encoder.py:33-84.  `position_embedding` may be the reference's [B,N,K,64] tensor -- not
+    supported on the CUDA path -- or, preferred, the raw boxes [B,N,4] (fp64): the geometry bias is computed in
+    the edge kernel straight from the boxes."""
+
+    def __init__(self, v_dim, q_dim, out_dim, dir_num, pos_emb_dim, nongt_dim, num_heads=16, num_steps=1,
+                 residual_connection=True, label_bias=True):
+        super().__init__()
+        self.v_dim, self.q_dim, self.out_dim = v_dim, q_dim, out_dim
+        self.residual_connection = residual_connection
+        self.num_steps = num_steps
+        print("In ImplicitRelationEncoder, num of graph propogate steps:",
+              "%d, residual_connection: %s" % (self.num_steps, self.residual_connection))
+        self.v_transform = FCNet([v_dim, out_dim]) if self.v_dim != self.out_dim else None
+        self.implicit_relation = GAttNet(dir_num, 1, out_dim + q_dim, out_dim, nongt_dim=nongt_dim,
+                                         label_bias=label_bias, num_heads=num_heads, pos_emb_dim=pos_emb_dim)
+        self.precision = _default_precision()
+
+    def forward(self, v, position_embedding, q):
+        if position_embedding.dim() != 3 or position_embedding.shape[-1] != 4:
+            raise ValueError("the CUDA implicit encoder takes the boxes [B, N, 4]; the 64-d position embedding is "
+                             "computed inside the kernel (got shape %s)" % (tuple(position_embedding.shape),))
+        if self.v_transform is not None or not self.residual_connection or self.num_steps != 1:
+            raise NotImplementedError("only v_dim == out_dim, residual_connection=True, num_steps=1 (reference config)")
+        pc = PC(self.precision)
+        B, N, D = v.shape
+        out, _, P = self.implicit_relation.relation_step(pc, v.reshape(B * N, D), None, q, position_embedding, None,
+                                                         B, B, B, N)
+        return _maybe_inplace(v, out), [None, P]
+
+
+class ExplicitRelationEncoder(nn.Module):
+    """models/relation_encoder.py:88-132."""
+
+    def __init__(self, v_dim, q_dim, out_dim, dir_num, label_num, nongt_dim=20, num_heads=16, num_steps=1,
+                 residual_connection=True, label_bias=True):
+        super().__init__()
+        self.v_dim, self.q_dim, self.out_dim = v_dim, q_dim, out_dim
+        self.num_steps = num_steps
+        self.residual_connection = residual_connection
+        print("In ExplicitRelationEncoder, num of graph propogation steps:",
+              "%d, residual_connection: %s" % (self.num_steps, self.residual_connection))
+        self.v_transform = FCNet([v_dim, out_dim]) if self.v_dim != self.out_dim else None
+        self.explicit_relation = GAttNet(dir_num, label_num, out_dim + q_dim, out_dim, nongt_dim=nongt_dim,
+                                         num_heads=num_heads, label_bias=label_bias, pos_emb_dim=-1)
+        self.precision = _default_precision()
+
+    def forward(self, v, exp_adj_matrix, q):
+        if self.v_transform is not None or not self.residual_connection or self.num_steps != 1:
+            raise NotImplementedError("only v_dim == out_dim, residual_connection=True, num_steps=1 (reference config)")
+        pc = PC(self.precision)
+        B, N, D = v.shape
+        out, _, P = self.explicit_relation.relation_step(pc, v.reshape(B * N, D), None, q, exp_adj_matrix, None,
+                                                         B, B, B, N)
+        return _maybe_inplace(v, out), [None, P]
+
+
+class WordEmbedding(nn.Module):
+    """models/language_model.py:17-53 (parameters; gather runs in QuestionFn)."""
+
+    def __init__(self, ntoken, emb_dim, dropout, op=''):
+        super().__init__()
+        self.op = op
+        self.emb = nn.Embedding(ntoken + 1, emb_dim, padding_idx=ntoken)
+        if 'c' in op:
+            self.emb_ = nn.Embedding(ntoken + 1, emb_dim, padding_idx=ntoken)
+            self.emb_.weight.requires_grad = False
+        self.dropout = nn.Dropout(dropout)
+        self.ntoken = ntoken
+        self.emb_dim = emb_dim
+
+    def forward(self, x):
+        # tiny gather; kept as a torch op for standalone use (the fused path gathers inside QuestionFn)
+        emb = self.emb(x)
+        if 'c' in self.op:
+            emb = torch.cat((emb, self.emb_(x)), 2)
+        return self.dropout(emb)
+
+
+class QuestionEmbedding(nn.Module):
+    """models/language_model.py:56-115 (parameters; recurrence runs in QuestionFn)."""
+
+    def __init__(self, in_dim, num_hid, nlayers, bidirect, dropout, rnn_type='GRU'):
+        super().__init__()
+        assert rnn_type == 'LSTM' or rnn_type == 'GRU'
+        rnn_cls = nn.LSTM if rnn_type == 'LSTM' else nn.GRU
+        self.rnn = rnn_cls(in_dim, num_hid, nlayers, bidirectional=bidirect, dropout=dropout, batch_first=True)
+        self.in_dim = in_dim
+        self.num_hid = num_hid
+        self.nlayers = nlayers
+        self.rnn_type = rnn_type
+        self.ndirections = 1 + int(bidirect)
+
+
+class QuestionSelfAttention(nn.Module):
+    """models/language_model.py:118-156 (parameters; pooling incl. quirk Q4 runs in QuestionFn)."""
+
+    def __init__(self, num_hid, dropout):
+        super().__init__()
+        self.num_hid = num_hid
+        self.drop = nn.Dropout(dropout)
+        self.W1_self_att_q = FCNet(dims=[num_hid, num_hid], dropout=dropout, act=None)
+        self.W2_self_att_q = FCNet(dims=[num_hid, 1], act=None)
+
+
+class SelfAttention(nn.Module):
+    """models/modules.py:17-77.  Dead in setting='mode2' (SSRE is constructed but never called); kept so that
+    reference checkpoints load (quirk Q11)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        cd = cfg.model.change_detector
+        if cd.att_dim % cd.att_head != 0:
+            raise ValueError("The hidden size (%d) is not a multiple of the number of attention "
+                             "heads (%d)" % (cd.att_dim, cd.att_head))
+        self.num_attention_heads = cd.att_head
+        self.attention_head_size = int(cd.att_dim / cd.att_head)
+        self.all_head_size = self.num_attention_heads * self.attention_head_size
+        self.query = nn.Linear(cd.att_dim * 2, self.all_head_size)
+        self.key = nn.Linear(cd.att_dim * 2, self.all_head_size)
+        self.value = nn.Linear(cd.att_dim * 2, self.all_head_size)
+        self.dropout = nn.Dropout(0.1)
+        self.layer_norm = nn.LayerNorm(cd.att_dim, eps=1e-6)
+
+
+class ChangeDetector(nn.Module):
+    """Drop-in for models/modules.py:81-313 (setting='mode2')."""
+
+    def __init__(self, cfg, word_to_idx):
+        super().__init__()
+        cd = cfg.model.change_detector
+        self.input_dim = cd.input_dim
+        self.dim = cd.dim
+        self.feat_dim = cd.feat_dim - 2
+        self.att_head = cd.att_head
+        self.att_dim = cd.att_dim
+        self.nongt_dim = cd.nongt_dim
+        self.pos_emb_dim = cd.pos_emb_dim
+        self.img = nn.Linear(self.feat_dim, self.att_dim)
+        self.SSRE = SelfAttention(cfg)
+        self.context1 = nn.Linear(self.att_dim, self.att_dim, bias=False)
+        self.context2 = nn.Linear(self.att_dim, self.att_dim)
+        self.gate1 = nn.Linear(self.att_dim, self.att_dim, bias=False)
+        self.gate2 = nn.Linear(self.att_dim, self.att_dim)
+        self.dropout = nn.Dropout(0.5)
+        self.embed = nn.Sequential(nn.Linear(self.att_dim * 3, self.dim), nn.Dropout(0.5), nn.ReLU())
+        self.att = nn.Linear(self.dim, 1)
+        self.fc1 = nn.Linear(self.att_dim, 6)
+        self.coef_sem = cd.coef_sem
+        self.coef_spa = cd.coef_spa
+        assert self.coef_sem + self.coef_spa <= 1
+        q_dim = cfg.model.speaker.embed_dim
+        if cfg.train.setting == 'mode2':
+            g = cfg.train.graph
+            if g == 'all' or g == 'semantic':
+                self.semantic_relation = ExplicitRelationEncoder(
+                    cd.att_dim, q_dim, cd.att_dim, cd.dir_num, cd.sem_label_num, num_heads=cd.att_head, num_steps=1,
+                    nongt_dim=cd.nongt_dim, residual_connection=True, label_bias=False)
+            if g == 'all' or g == 'spatial' or g == 'i+s':
+                self.spatial_relation = ExplicitRelationEncoder(
+                    cd.att_dim, q_dim, cd.att_dim, cd.dir_num, cd.spa_label_num, num_heads=cd.att_head, num_steps=1,
+                    nongt_dim=cd.nongt_dim, residual_connection=True, label_bias=False)
+            if g == 'all' or g == 'implicit' or g == 'i+s':
+                self.imp_relation = ImplicitRelationEncoder(
+                    cd.att_dim, q_dim, cd.att_dim, cd.dir_num, 64, cd.nongt_dim, num_heads=cd.att_head, num_steps=1,
+                    residual_connection=True, label_bias=False)
+        self.w_emb = WordEmbedding(len(word_to_idx), 300, .0, 'c')
+        self.q_emb = QuestionEmbedding(600, q_dim, 1, False, .0)
+        self.q_att = QuestionSelfAttention(q_dim, .2)
+        self.cfg = cfg
+        if cfg.data.feature_mode == 'mode0':
+            raise NotImplementedError("feature_mode 'mode0' (ResNet-101 on raw images) is outside the hot path")
+        self.precision = _default_precision()
+
+    def set_precision(self, precision: str) -> "ChangeDetector":
+        PC(precision)
+        for m in self.modules():
+            if hasattr(m, "precision"):
+                m.precision = precision
+        return self
+
+    # -- question path --------------------------------------------------------------------------
+    def question_vector(self, pc: PC, question: torch.Tensor) -> torch.Tensor:
+        rnn = self.q_emb.rnn
+        w1 = self.q_att.W1_self_att_q.linear()
+        w2 = self.q_att.W2_self_att_q.linear()
+        if self.training:
+            raise NotImplementedError("train-mode dropout inside the question attention is handled by "
+                                      "ChangeDetector.forward; call it instead")
+        return QuestionFn.apply(pc, question, self.w_emb.emb.weight, self.w_emb.emb_.weight, rnn.weight_ih_l0,
+                                rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0, wn_weight(w1), w1.bias,
+                                wn_weight(w2), w2.bias)
+
+    def position_emb(self, bb):
+        """The reference materialises a [B,N,K,64] fp64 embedding here (modules.py:162-166); the CUDA path
+        consumes the boxes directly, so this returns them unchanged."""
+        return bb
+
+    def forward(self, input_1, input_2, d_adj_matrix, q_adj_matrix, d_sem_adj_matrix, q_sem_adj_matrix, d_bb, q_bb,
+                question, setting='mode2', graph='all'):
+        if self.cfg.data.train.empty_image == True:  # noqa: E712  (modules.py:170-178)
+            input_1, input_2 = torch.ones_like(input_1), torch.ones_like(input_2)
+            d_adj_matrix, q_adj_matrix = torch.ones_like(d_adj_matrix), torch.ones_like(q_adj_matrix)
+            d_sem_adj_matrix, q_sem_adj_matrix = torch.ones_like(d_sem_adj_matrix), torch.ones_like(q_sem_adj_matrix)
+            d_bb, q_bb = torch.ones_like(d_bb), torch.ones_like(q_bb)
+        if setting != 'mode2':
+            raise NotImplementedError("only setting='mode2' is live in the reference (modes 1/3/4 use "
+                                      "self.graph_relation, which does not exist; mode0 is the SSRE ablation)")
+        if graph not in ('all', 'semantic', 'spatial', 'implicit', 'i+s'):
+            raise ValueError("unknown graph mode %r" % (graph,))
+        if self.training:
+            raise NotImplementedError("train-mode (dropout) forward is not implemented yet; use .eval() -- "
+                                      "gradients are available in eval mode")
+        pc = PC(self.precision)
+        B, N, C = input_1.size()
+        D = self.att_dim
+        G = 2 * B
+        X, XT = LinearFn.apply(pc, input_1, input_2, self.img.weight, self.img.bias)      # [2BN, D]
+        qv = self.question_vector(pc, question)
+        if graph in ('semantic', 'all'):
+            X, XT, _ = self.semantic_relation.explicit_relation.relation_step(
+                pc, X, XT, qv, d_sem_adj_matrix, q_sem_adj_matrix, B, G, B, N)
+        if graph in ('spatial', 'all', 'i+s'):
+            X, XT, _ = self.spatial_relation.explicit_relation.relation_step(
+                pc, X, XT, qv, d_adj_matrix, q_adj_matrix, B, G, B, N)
+        if graph in ('implicit', 'all', 'i+s'):
+            X, XT, _ = self.imp_relation.implicit_relation.relation_step(
+                pc, X, XT, qv, d_bb, q_bb, B, G, B, N)
+        mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
+        coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
+        Wcg = torch.cat([torch.cat([self.context2.weight, self.context1.weight], 1),
+                         torch.cat([self.gate2.weight, self.gate1.weight], 1)], 0)
+        bcg = torch.cat([self.context2.bias, self.gate2.bias], 0)
+        att, attended = FusionFn.apply(pc, (B, N, D, self.dim), mode, coefs, X, Wcg, bcg, self.embed[0].weight,
+                                       self.embed[0].bias, self.att.weight, self.att.bias)
+        BN = B * N
+        att_weight_before = att[:BN].view(B, 1, N)
+        att_weight_after = att[BN:].view(B, 1, N)
+        attended_1, attended_2 = attended[:B], attended[B:]
+        input_attended = attended_2 - attended_1
+        pred = F.linear(input_attended, self.fc1.weight, self.fc1.bias)      # [B,6], unused by the loss (Q11)
+        return pred, att_weight_before, att_weight_after, attended_1, attended_2, input_attended

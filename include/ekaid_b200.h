@@ -1,0 +1,184 @@
+/* ekaid_b200 -- C ABI of the B200-native EKAID graph+fusion hot path.
+ *
+ * The reference (Holipori/EKAID) is pure Python: it has no FFI/plugin layer, its "operators" are ATen calls
+ * made from nn.Module.forward.  This header is the boundary a maintainer binds instead (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference call site(s) it replaces; paths are relative to
+ * /root/reference/model.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no torch types; every pointer is a DEVICE pointer unless stated;
+ *   - the caller owns every buffer (outputs and workspaces); nothing here allocates or synchronises;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); CUDA-graph capturable;
+ *   - return value 0 = ok, negative = error (EKAID_ERR_*), message via ekaid_last_error();
+ *   - `is_bf16` selects the storage type of GEMM-operand activations: 0 = float, 1 = __nv_bfloat16
+ *     (fp32 parity path vs. bf16 tensor-core path); reductions / softmax / residuals are always fp32;
+ *   - sequence buffers of the question path are time-major (row = l*B + b);
+ *   - "stacked" image batches: G = number of images; images [0, g_split) read adj0/bb0, the rest adj1/bb1
+ *     (main and reference image of each pair share weights and are processed in one launch).
+ */
+#ifndef EKAID_B200_H
+#define EKAID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKAID_OK 0
+#define EKAID_ERR_SHAPE -1
+#define EKAID_ERR_ALIGN -2
+#define EKAID_ERR_ARCH -3
+#define EKAID_ERR_CUDA -4
+#define EKAID_ERR_UNSUPPORTED -5
+
+#define EKAID_ACT_NONE 0
+#define EKAID_ACT_RELU 1
+#define EKAID_ACT_TANH 2
+#define EKAID_ACT_SIGMOID 3
+
+/* Fused GEMM epilogue:  v = acc (+ bias[n]) (+ addend[m,n])
+ *                           (+ rowflag[m] ? rowb_alt[n] : rowb[(m / rowb_div) % rowb_mod, n]);  v = act(v);
+ *                       C[m,n] = v (fp32, may be NULL);  Cb[m,n] = bf16(v) (may be NULL).
+ * rowb/rowflag implement q_expand_v_cat (models/relation_encoder.py:19-29, quirk Q10) without materialising
+ * the [B,N,2048] concat: the question half of self_weights is applied once per sample and broadcast per row. */
+typedef struct ekaid_epilogue {
+  const float* bias;
+  const float* addend;
+  int64_t ldadd;
+  const float* rowb;
+  int64_t ldrowb;
+  int32_t rowb_div;
+  int32_t rowb_mod;
+  const uint8_t* rowflag;
+  const float* rowb_alt;
+  int32_t act;
+  float* C;
+  int64_t ldc;
+  void* Cb; /* __nv_bfloat16* */
+  int64_t ldcb;
+} ekaid_epilogue_t;
+
+int ekaid_abi_version(void);
+const char* ekaid_last_error(void);
+/* 0 if the current device is sm_100 (B200), EKAID_ERR_ARCH otherwise */
+int ekaid_check_device(void);
+
+/* ---- dense contractions ---------------------------------------------------------------------------------
+ * C[M,N] = op(A) op(B):  transA = 0: A is [M,K] (lda), 1: A is [K,M];  transB = 0: B is [N,K] (ldb) i.e. an
+ * nn.Linear weight, 1: B is [K,N].  Replaces every addmm/mm on the path: modules.py:195-196 (img),
+ * graph_att.py:80 (self_weights), graph_att_layer.py:79,90,174 (query, key, linear_out_2),
+ * modules.py:278-288 (context/gate), :300-303 (embed), language_model.py:113 (GRU), :138 (W1), and their
+ * autograd backward (dgrad: transB=1, wgrad: transA=1,transB=1). */
+int ekaid_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, const ekaid_epilogue_t* ep, void* stream);
+/* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  force_bn: 0 = auto, else 64/128/256.
+ * splits: 0 = auto split-K (plain fp32 C only), 1 = off. Operands 16-byte aligned, pitches multiples of 8. */
+int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
+                    int64_t ldb, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream);
+
+/* ---- casts / reductions / glue -------------------------------------------------------------------------- */
+int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+/* out[n] = sum_m rowscale[m] * src[m,n]  (bias gradients); workspace >= 64*N floats */
+int ekaid_colsum(int is_bf16, const void* src, int64_t ld, int64_t M, int N, const float* rowscale, float* out,
+                 float* workspace, void* stream);
+int ekaid_add_inplace(float* y, const float* x, int64_t n, void* stream);
+/* flags[m] = (sum_c X[m,c] == 0): the mask of q_expand_v_cat (relation_encoder.py:23-27) */
+int ekaid_row_zero_flags(const float* X, int64_t M, int D, uint8_t* flags, void* stream);
+/* backward of the per-sample question broadcast: out[b,:] = sum over the rows of sample b (S stacked images x N
+ * nodes) whose flag is clear */
+int ekaid_group_rowsum(int is_bf16, const void* src, int64_t ld, int N, int B, int S, int D, const uint8_t* flags,
+                       float* out, void* stream);
+/* process_matrix / torch_broadcast_adj_matrix (utils/mimic_utils.py:119-149): float64 labels [B,S,S] ->
+ * one-hot fp32 [B,N,N,L] in ONE launch (the reference loops over labels with a host sync each) */
+int ekaid_onehot_adj(const double* labels, int B, int S, int N, int L, float* out, void* stream);
+
+/* ---- relation-aware graph attention (models/graph_att.py:53-106, models/graph_att_layer.py:60-178) ------- */
+/* cond[g,i,j] = sum_c adj[g,j,i,c], lbias[g,i,j] = sum_c adj[g,j,i,c] w[c]   (graph_att.py:76,88-92; Q2,Q5) */
+int ekaid_adj_prep_fwd(const float* adj0, const float* adj1, int g_split, const float* w, int G, int N, int Kn, int L,
+                       float* cond, float* lbias, void* stream);
+/* dw_part[g,c] = sum_ij adj[g,j,i,c] * sum_p dlbias_part[p,g,i,j] */
+int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const float* dlbias_part, int nparts, int G,
+                       int N, int Kn, int L, float* dw_part, void* stream);
+/* gbias[g,i,j,h] = log(max(relu(Wp[h,:] . posemb(pair) + bp[h]), 1e-6)) straight from fp64 boxes [G,N,4]
+ * (modules.py:162-166, utils/mimic_utils.py:152-208, graph_att_layer.py:113-135; Q7, Q13).
+ * dim_t: 8 fp32 wave lengths 1000^(t/8) */
+int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
+                        const float* dim_t, int G, int N, int Kn, int H, float* gbias, void* stream);
+/* part[g, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h] */
+int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
+                        const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
+                        void* stream);
+/* QKZ [G*N, ld]: cols [0,D) query, [D,2D) key, [2D + h*D, 2D + (h+1)*D) Z_h.  P [G,N,H,Kn] fp32.
+ * scores/sqrt(dh) (+gbias) -> where(cond>0, s, -9e15) + lbias -> softmax over keys
+ * (graph_att_layer.py:105-157; Q6).  cond / lbias / gbias may be NULL. */
+int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
+                           const float* gbias, int G, int N, int Kn, int H, float* P, void* stream);
+/* out = sum_h P_h Z_h + b_out;  Xout = Xin + relu(2 out);  mask = (out > 0)
+ * (graph_att_layer.py:164-176 re-associated per Q3, graph_att.py:95-104 (Q2), relation_encoder.py:81,129 (Q1)).
+ * XoutT: optional copy of Xout in the operand type with pitch ldt (may be NULL). */
+int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
+                             const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
+                             uint8_t* mask, void* stream);
+int ekaid_edge_num_slices(int D);
+/* dOut [G*N, D] = 2*mask*dXout; dQKZ[:, 2D:] = dZ; dPpart [slices, G,N,H,Kn] */
+int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
+                             int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
+                             void* stream);
+/* dQKZ[:, 0:2D] = (dQ, dK); dlbias_part [H, G,N,Kn] and dgbias [G,N,Kn,H] may be NULL */
+int ekaid_edge_softmax_bwd(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ, int64_t ld,
+                           int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ, float* dlbias_part,
+                           float* dgbias, void* stream);
+
+/* ---- difference + gated fusion + attention pooling (modules.py:233-310) --------------------------------- */
+/* X3 [2*BN, D] (main rows then reference rows).  mode 0 single graph, 1 'all' (Q1), 2 'i+s'.
+ * Xc fp32 [2BN, D]; CAT [2BN, 3D] operand type: [:,0:D]=Xc, [:,D:2D]=Xaft-Xbef (modules.py:234-250,297-298) */
+int ekaid_combine_diff_fwd(int is_bf16, const float* X3, int64_t BN, int D, int mode, float c1, float c2, float c3,
+                           float* Xc, void* CAT, void* stream);
+int ekaid_combine_diff_bwd(const float* dXc, const float* dCAT, int64_t BN, int D, int mode, float c1, float c2,
+                           float c3, float* dX3, void* stream);
+/* pre [M,2D] fp32 = (context | gate) pre-activations -> ctx=tanh, gate=sigmoid, CAT[:,2D:3D] = gate*ctx
+ * (modules.py:278-288) */
+int ekaid_gate_fwd(int is_bf16, const float* pre, int64_t M, int D, void* ctx, void* gate, void* CAT, void* stream);
+int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* gate, int64_t M, int D, void* dpre,
+                   void* stream);
+/* att = sigmoid(E w + b) [M];  attended[g,:] = sum_n att[g,n] Xc[g,n,:]   (modules.py:302-308) */
+int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const float* w, const float* b,
+                       const float* Xc, float* att, float* attended, void* stream);
+int ekaid_att_pool_bwd(int is_bf16, const float* dA, const float* dattw, const float* att, const float* Xc,
+                       const float* E, const float* w, int64_t M, int N, int D, int dim, float* dXc, void* dE,
+                       float* dpre, void* stream);
+
+/* ---- question path (models/language_model.py) ------------------------------------------------------------ */
+/* E[l*B+b,:] = [emb[q[b,l]] | emb_[q[b,l]]]   (:48-53) */
+int ekaid_embed_gather(int is_bf16, const int64_t* q, const float* emb, const float* emb2, int B, int L, int ed,
+                       void* E, void* stream);
+int ekaid_embed_gather_bwd(const int64_t* q, const float* dE, int64_t ldde, int B, int L, int ed, int V, float* demb,
+                           void* stream);
+/* one GRU step (:106-115): gi, gh [B,3H] incl. biases; gates [B,4H] saves (r,z,n,gh_n) */
+int ekaid_gru_cell_fwd(int is_bf16, const float* gi, const float* gh, const float* hprev, int B, int H, float* h,
+                       void* hT, float* gates, void* stream);
+int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H, float* dgi,
+                       float* dgh, void* dgiT, void* dghT, float* dhprev, void* stream);
+/* out[m] = A[m,:] . w + b[0]   (W2_self_att_q, :142) */
+int ekaid_rowdot(int is_bf16, const void* A, int64_t lda, int64_t M, int K, const float* w, const float* b, float* out,
+                 void* stream);
+/* batch-axis softmax + reinterpret + weighted sum (:149-153, quirk Q4). a,S: [L*B]; Hs [L*B,H]; qv [B,H] */
+int ekaid_qpool_fwd(const float* a, const float* Hs, int B, int L, int H, float* S, float* qv, void* stream);
+int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, int L, int H, float* dS, float* da,
+                    float* dHs, void* stream);
+int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
+                        void* stream);
+
+/* ---- optimizer (utils/utils.py:96-99 -> torch.optim.Adam semantics) -------------------------------------- */
+/* pow_state: device float[2] = {beta1^t, beta2^t}; call ekaid_adam_advance once per step before the updates */
+int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream);
+int ekaid_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                    float wd, const float* pow_state, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKAID_B200_H */

@@ -1,0 +1,77 @@
+"""The CPU oracle (oracle/ekaid_oracle.py) against golden vectors produced by the reference itself
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ekaid_oracle as O
+from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
+from helpers import (CASES, OUT_NAMES, case_inputs, check_fixture_inputs, grad_summary, load_case, loss_weights,
+                     oracle_forward, rel_err, speaker_spec, checksum)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_outputs(name):
+    z, meta = load_case(name)
+    sd, inp, _ = case_inputs(meta)
+    check_fixture_inputs(z, sd, inp)
+    with torch.no_grad():
+        outs = oracle_forward(sd, inp, meta)
+    for k, o in zip(OUT_NAMES, outs):
+        assert tuple(o.shape) == z[k].shape
+        assert rel_err(o, z[k]) < 2e-5, (name, k, rel_err(o, z[k]))
+
+
+@pytest.mark.parametrize("name", ["c1_b3_n52_all_grads", "c7_b2_n52_zero_bias"])
+def test_oracle_matches_reference_gradients(name):
+    z, meta = load_case(name)
+    sd, inp, _ = case_inputs(meta)
+    # w_emb.emb_ is frozen in the reference (language_model.py:28-29)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()}
+    outs = oracle_forward(sdg, inp, meta)
+    loss = sum((o * w).sum() for o, w in zip(outs[1:], loss_weights(outs)))
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
+    loss.backward()
+    names = [str(n) for n in z["grad_names"]]
+    rows = z["grad_rows"]
+    assert len(names) > 40
+    for n, row in zip(names, rows):
+        g = sdg[n].grad
+        assert g is not None, n
+        s = grad_summary(g)
+        ref = row[:len(s)]
+        scale = max(abs(ref[0]), 1e-12)          # gradient norm
+        # atol: parameters whose gradient is analytically zero (key bias, implicit label bias, W2 bias: softmax
+        # shift invariance) only carry rounding noise ~1e-5
+        assert abs(s[0] - ref[0]) < 2e-4 * scale + 5e-5, (n, s[0], ref[0])
+        assert np.abs(s[2:] - ref[2:]).max() < 5e-4 * scale + 5e-5, (n, np.abs(s[2:] - ref[2:]).max(), scale)
+    # parameters the reference leaves without gradient (quirks Q2, Q3, Q11) get none from the oracle either
+    dead = [k for k in sdg if sdg[k].requires_grad and k not in names]
+    for k in dead:
+        g = sdg[k].grad
+        assert g is None or float(g.abs().max()) == 0.0 or k.startswith("fc1."), k
+
+
+@pytest.mark.parametrize("name", ["c0_b2_n52_all", "c1_b3_n52_all_grads"])
+def test_oracle_speaker_tokens(name):
+    z, meta = load_case(name)
+    ssd = synthetic_state_dict(speaker_spec(), 4321)
+    bef, aft, diff = (torch.from_numpy(z[k]) for k in ("attended_1", "attended_2", "input_attended"))
+    with torch.no_grad():
+        seq = O.speaker_greedy(ssd, bef, aft, diff, 90, 512)
+    assert np.array_equal(seq.numpy(), z["tokens"])
+    batch = synthetic_batch(meta["B"], meta["N"], seed=meta["seed"])
+    with torch.no_grad():
+        logp = O.speaker_teacher_forced(ssd, bef, aft, diff, batch[2].squeeze(1), 90, 512)
+    np.testing.assert_allclose(checksum(logp), z["tf_logp_checksum"], rtol=1e-4)
+
+
+def test_process_matrix_fixture():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "process_matrix.npz"))
+    b = synthetic_batch(2, 52, seed=3)
+    pm = O.process_matrix(b[6], 52, 11)
+    ps = O.process_matrix(b[8], 52, 3)
+    assert np.array_equal(pm.sum((0, 3)).numpy(), z["spa_sum"])
+    assert np.array_equal(ps.sum((0, 3)).numpy(), z["sem_sum"])
+    np.testing.assert_allclose(checksum(pm), z["spa_chk"])
+    np.testing.assert_allclose(checksum(ps), z["sem_chk"])
