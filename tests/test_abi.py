@@ -1,0 +1,112 @@
+"""CPU-side checks: the C-ABI library loads without a GPU and exports every symbol the header declares; the drop-in
+modules keep the reference's constructor contract and state_dict keys; host-side helpers."""
+import contextlib
+import ctypes
+import io
+import json
+import os
+
+import pytest
+import torch
+
+from helpers import GOLDEN, spec_for
+
+
+def test_library_exports_every_declared_symbol():
+    from ekaid_b200 import lib
+    protos = lib.parse_header()
+    assert len(protos) >= 35
+    assert os.path.exists(lib.LIB_PATH), "build with python -m ekaid_b200.build"
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(so, name), name
+    so.ekaid_abi_version.restype = ctypes.c_int
+    assert so.ekaid_abi_version() == 1
+    lib.load()
+
+
+def test_epilogue_struct_layout_matches_header(tmp_path):
+    """ctypes mirror of struct ekaid_epilogue == what a C compiler lays out from the header."""
+    import subprocess
+    from ekaid_b200.lib import Epilogue, HEADER
+    src = tmp_path / "lay.c"
+    fields = [f[0] for f in Epilogue._fields_]
+    body = "".join('printf("%%zu\\n", offsetof(ekaid_epilogue_t, %s));' % f for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(){printf("%%zu\\n", '
+                   'sizeof(ekaid_epilogue_t));%s return 0;}' % (HEADER, body))
+    exe = tmp_path / "lay"
+    subprocess.check_call(["gcc", str(src), "-o", str(exe)])
+    nums = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert nums[0] == ctypes.sizeof(Epilogue)
+    assert nums[1:] == [getattr(Epilogue, f).offset for f in fields]
+
+
+def test_no_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ekaid_b200 import lib
+    with pytest.raises(lib.EkaidError):
+        lib.require_device()
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ChangeDetector(default_cfg(), WORD_TO_IDX).eval()
+    x = torch.zeros(1, 52, 1024)
+    with pytest.raises(lib.EkaidError):
+        m(x, x, torch.zeros(1, 52, 52, 11), torch.zeros(1, 52, 52, 11), torch.zeros(1, 52, 52, 3),
+          torch.zeros(1, 52, 52, 3), torch.zeros(1, 52, 4).double(), torch.zeros(1, 52, 4).double(),
+          torch.zeros(1, 20, dtype=torch.long))
+
+
+@pytest.mark.parametrize("graph", ["all", "semantic", "spatial", "implicit", "i+s"])
+def test_state_dict_contract(graph):
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ChangeDetector(default_cfg(graph), WORD_TO_IDX)
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    ref = spec_for(graph)
+    assert list(mine.keys()) == list(ref.keys())
+    assert mine == ref
+    assert not m.w_emb.emb_.weight.requires_grad          # frozen table (language_model.py:28-29)
+
+
+def test_constructor_errors_like_reference():
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    cfg = default_cfg()
+    cfg.model.change_detector.att_head = 3                 # 1024 % 3 != 0 -> ValueError (modules.py:20-23)
+    with pytest.raises(ValueError), contextlib.redirect_stdout(io.StringIO()):
+        ChangeDetector(cfg, WORD_TO_IDX)
+    cfg = default_cfg()
+    cfg.model.change_detector.coef_sem = 0.8               # coef_sem + coef_spa > 1 -> AssertionError (:120)
+    with pytest.raises(AssertionError), contextlib.redirect_stdout(io.StringIO()):
+        ChangeDetector(cfg, WORD_TO_IDX)
+
+
+def test_synthetic_loader_shapes_and_rules():
+    from ekaid_b200.synthetic import spatial_labels_from_boxes, synthetic_batch
+    b = synthetic_batch(4, 52, seed=1)
+    assert len(b) == 13
+    assert b[0].shape == (4, 52, 1024) and b[0].dtype == torch.float32 and float(b[0].min()) >= 0
+    assert b[2].shape == (4, 1, 91) and b[4].shape == (4, 1, 91) and b[12].shape == (4, 20)
+    assert b[6].shape == (4, 100, 100) and b[6].dtype == torch.float64 and b[10].dtype == torch.float64
+    assert int(b[6].max()) <= 11 and int(b[8].max()) <= 2
+    assert torch.equal(b[8], b[8].transpose(1, 2))          # semantic labels are symmetric
+    # spatial: self edge is label 3 (IoU = 1), transposed entry is reverse_type
+    bb = torch.tensor([[[0., 0., 100., 100.], [10., 10., 50., 50.], [400., 0., 500., 100.], [0., 900., 50., 1000.]]])
+    lab = spatial_labels_from_boxes(bb)[0]
+    assert lab.diagonal().tolist() == [3, 3, 3, 3]
+    assert lab[0, 1] == 1 and lab[1, 0] == 2                # box 0 strictly contains box 1
+    assert lab[0, 2] == 3 + 0 or lab[0, 2] >= 3             # right neighbour: angle 0 -> ceil(0/45)+3 = 3
+    assert lab[0, 3] == 0 and lab[3, 0] == 0                # further than (1024+1024)/3 apart
+    same = synthetic_batch(4, 52, seed=1)
+    assert all(torch.equal(x, y) for x, y in zip(b, same))
+
+
+def test_golden_manifest_complete():
+    from helpers import CASES
+    for c in CASES:
+        assert os.path.exists(os.path.join(GOLDEN, c + ".npz")), c
+    assert os.path.exists(os.path.join(GOLDEN, "make_golden.py"))
+    json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))

@@ -1,0 +1,124 @@
+"""Kernel-level checks on a B200, through the C ABI: the tcgen05 GEMM (all operand layouts, tails, split-K,
+fused epilogues) and the SIMT fp32 GEMM against torch matmul on the same (bf16-rounded) operands, and the
+small kernels against closed-form torch expressions."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    from ekaid_b200 import lib
+    lib.require_device()
+    return torch.device("cuda:0")
+
+
+def _mk(shape, dev, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * 0.5).to(dev).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("transA,transB", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 200, 136), (1040, 1024, 1024), (64, 3072, 1024),
+                                   (208, 6144, 1024), (1024, 600, 416)])
+def test_gemm_layouts(dtype, transA, transB, M, N, K):
+    from ekaid_b200.functions import gemm
+    dev = _dev()
+    A = _mk((K, M) if transA else (M, K), dev, 1, dtype)
+    B = _mk((K, N) if transB else (N, K), dev, 2, dtype)
+    C = torch.full((M, N), float("nan"), device=dev)
+    gemm(A, B, M, N, K, transA, transB, C=C, splits=1)
+    Af = A.float().t() if transA else A.float()
+    Bf = B.float() if transB else B.float().t()
+    ref = Af.double() @ Bf.double()
+    err = float((C.double() - ref).abs().max() / ref.abs().max())
+    assert err < (2e-5 if dtype == torch.float32 else 1e-5), err      # operands identical -> only fp32 accumulation order
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_tc_tile_widths_and_splitk(bn):
+    from ekaid_b200.functions import gemm
+    dev = _dev()
+    M, N, K = 1024, 1024, 3328
+    A = _mk((K, M), dev, 3, torch.bfloat16)
+    B = _mk((K, N), dev, 4, torch.bfloat16)
+    ref = A.float().t().double() @ B.float().double()
+    for splits in (1, 0, 5):
+        C = torch.full((M, N), float("nan"), device=dev)
+        gemm(A, B, M, N, K, 1, 1, C=C, splits=splits, force_bn=bn)
+        err = float((C.double() - ref).abs().max() / ref.abs().max())
+        assert err < 1e-5, (bn, splits, err)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gemm_epilogue(dtype):
+    from ekaid_b200.functions import gemm, ACT_TANH, ACT_RELU
+    dev = _dev()
+    Bsz, Nn = 3, 52
+    M, N, K = 2 * Bsz * Nn, 1024, 512
+    A = _mk((M, K), dev, 5, dtype)
+    W = _mk((N, 2 * K), dev, 6, dtype)          # pitch 2K: use the left half as a strided view
+    bias = _mk((N,), dev, 7, torch.float32)
+    add = _mk((M, N), dev, 8, torch.float32)
+    rowb = _mk((Bsz, N), dev, 9, torch.float32)
+    alt = _mk((N,), dev, 10, torch.float32)
+    flags = (torch.arange(M, device=dev) % 7 == 0).to(torch.uint8)
+    ref = A.float() @ W[:, :K].float().t() + bias + add
+    rows = (torch.arange(M, device=dev) // Nn) % Bsz
+    ref = ref + torch.where(flags.bool().unsqueeze(1), alt.unsqueeze(0), rowb[rows])
+    C = torch.empty(M, N, device=dev)
+    Cb = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if dtype == torch.bfloat16 else None
+    gemm(A, W[:, :K], M, N, K, bias=bias, addend=add, rowb=rowb, rowb_div=Nn, rowb_mod=Bsz, rowflag=flags,
+         rowb_alt=alt, act=ACT_TANH, C=C, Cb=Cb)
+    assert float((C - torch.tanh(ref)).abs().max()) < 2e-5
+    if Cb is not None:
+        assert float((Cb.float() - torch.tanh(ref)).abs().max()) < 1e-2
+    # in-place accumulate (addend aliases C), narrow N with scalar tail path
+    C2 = add[:, :100].clone()
+    gemm(A, W[:100, :K], M, 100, K, addend=C2, act=ACT_RELU, C=C2)
+    ref2 = torch.relu(A.float() @ W[:100, :K].float().t() + add[:, :100])
+    assert float((C2 - ref2).abs().max()) < 2e-5
+
+
+def test_colsum_rowflags_onehot():
+    from ekaid_b200.functions import colsum, onehot_adj
+    from ekaid_b200.lib import call
+    from oracle import ekaid_oracle as O
+    from ekaid_b200.synthetic import synthetic_batch
+    dev = _dev()
+    x = _mk((777, 130), dev, 11, torch.float32)
+    sc = _mk((777,), dev, 12, torch.float32)
+    assert float((colsum(x, 777, 130) - x.sum(0)).abs().max()) < 1e-3
+    assert float((colsum(x, 777, 130, rowscale=sc) - (x * sc[:, None]).sum(0)).abs().max()) < 1e-3
+    xb = x.to(torch.bfloat16)
+    assert float((colsum(xb, 777, 130) - xb.float().sum(0)).abs().max()) < 1e-3
+    X = _mk((100, 256), dev, 13, torch.float32)
+    X[3] = 0
+    X[17] = 0
+    flags = torch.empty(100, dtype=torch.uint8, device=dev)
+    call("row_zero_flags", X.data_ptr(), 100, 256, flags.data_ptr())
+    assert flags.nonzero().flatten().tolist() == [3, 17]
+    b = synthetic_batch(3, 52, seed=3)
+    for idx, L in ((6, 11), (8, 3)):
+        got = onehot_adj(b[idx].to(dev), 52, L)
+        assert torch.equal(got.cpu(), O.process_matrix(b[idx], 52, L))
+
+
+def test_adam_matches_torch():
+    from ekaid_b200.lib import call
+    dev = _dev()
+    p = _mk((10000,), dev, 14, torch.float32)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pw = torch.ones(2, device=dev)
+    for step in range(3):
+        g = _mk((10000,), dev, 20 + step, torch.float32)
+        ref.grad = g.clone()
+        opt.step()
+        call("adam_advance", pw.data_ptr(), 0.9, 0.999)
+        call("adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
+             0.0, pw.data_ptr())
+    assert float((p - ref.detach()).abs().max()) < 1e-6

@@ -1,0 +1,226 @@
+"""Parity of the CUDA path (through the drop-in modules -> C ABI) with the CPU oracle and with the golden vectors
+the reference produced.  Tolerances are the north-star's: 1e-4 relative (fp32 path), 2e-2 (bf16 tensor-core path),
+measured as max|a-b| / max|b| per output tensor; gradients likewise per parameter."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (CASES, OUT_NAMES, case_inputs, check_fixture_inputs, load_case, loss_weights, oracle_forward,
+                     rel_err, spec_for, speaker_spec)
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+GTOL = {"fp32": 5e-4, "bf16": 4e-2}     # gradients: same bar on the dominant entries, see rel_err
+
+
+def _dev():
+    from ekaid_b200 import lib
+    lib.require_device()
+    return torch.device("cuda:0")
+
+
+def build_model(meta, sd, precision, dev):
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    cfg = default_cfg(meta["graph"], nongt_dim=meta["nongt_dim"])
+    cfg.data.train.empty_image = meta["empty_image"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ChangeDetector(cfg, WORD_TO_IDX)
+    m.load_state_dict(sd)
+    m.to(dev).eval().set_precision(precision)
+    return m
+
+
+def to_dev(inp, dev):
+    # boxes (6, 7) stay on the CPU as float64, like the reference step (train_mimic.py:206-218)
+    return tuple(t if i in (6, 7) else t.to(dev) for i, t in enumerate(inp))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_golden_and_oracle(name, precision):
+    dev = _dev()
+    z, meta = load_case(name)
+    sd, inp, _ = case_inputs(meta)
+    check_fixture_inputs(z, sd, inp)
+    m = build_model(meta, sd, precision, dev)
+    with torch.no_grad():
+        outs = m(*to_dev(inp, dev), setting="mode2", graph=meta["graph"])
+        ref = oracle_forward(sd, inp, meta)
+    errs = {}
+    for k, o, r in zip(OUT_NAMES, outs, ref):
+        assert tuple(o.shape) == z[k].shape, k
+        errs[k] = (rel_err(o, z[k]), rel_err(o, r))
+    print(name, precision, {k: "%.1e/%.1e" % v for k, v in errs.items()})
+    for k, (eg, eo) in errs.items():
+        if k == "pred":
+            continue        # fc1 head of the (cancelling) difference vector; not consumed by anything (Q11)
+        assert eg < TOL[precision], (name, precision, k, "vs golden", eg)
+        assert eo < TOL[precision], (name, precision, k, "vs oracle", eo)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["c1_b3_n52_all_grads", "c7_b2_n52_zero_bias", "c4_b2_n60_k52_all",
+                                  "c2_b2_n52_ips"])
+def test_gradients_match_oracle(name, precision):
+    dev = _dev()
+    z, meta = load_case(name)
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    outs = m(*to_dev(inp, dev), setting="mode2", graph=meta["graph"])
+    ws = loss_weights(outs)
+    loss = sum((o * w.to(dev)).sum() for o, w in zip(outs[1:], ws))
+    loss.backward()
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()}
+    ro = oracle_forward(sdg, inp, meta)
+    rl = sum((o * w).sum() for o, w in zip(ro[1:], ws))
+    rl.backward()
+    bad = []
+    worst = 0.0
+    for k, p in m.named_parameters():
+        g_ref = sdg[k].grad
+        if g_ref is None or float(g_ref.abs().max()) < 1e-4:
+            # dead parameters (Q2, Q3, Q11) and analytically-zero gradients (softmax shift invariance)
+            if p.grad is not None:
+                assert float(p.grad.abs().max()) < (1e-3 if precision == "fp32" else 0.5), (k, float(p.grad.abs().max()))
+            continue
+        assert p.grad is not None, k
+        e = rel_err(p.grad, g_ref)
+        worst = max(worst, e)
+        if e > GTOL[precision]:
+            bad.append((k, e))
+    print(name, precision, "worst grad rel err %.2e" % worst)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["c0_b2_n52_all", "c1_b3_n52_all_grads"])
+def test_argmax_answer_tokens(name, precision):
+    """Identical greedy tokens through the answer decoder (oracle restatement of DynamicSpeaker._sample, pinned to
+    the reference's tokens in tests/test_oracle_golden.py)."""
+    from ekaid_b200.synthetic import synthetic_state_dict
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z, meta = load_case(name)
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    with torch.no_grad():
+        outs = m(*to_dev(inp, dev), setting="mode2", graph=meta["graph"])
+        ssd = synthetic_state_dict(speaker_spec(), 4321)
+        seq = O.speaker_greedy(ssd, outs[3].cpu(), outs[4].cpu(), outs[5].cpu(), 90, 512)
+    assert np.array_equal(seq.numpy(), z["tokens"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_relation_encoders_standalone(precision):
+    """ExplicitRelationEncoder / ImplicitRelationEncoder as individually swappable modules (single image batch)."""
+    from ekaid_b200.modules import ExplicitRelationEncoder, ImplicitRelationEncoder
+    from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B, N, D = 3, 52, 1024
+    full = synthetic_state_dict(spec_for("all"), 1238)
+    batch = synthetic_batch(B, N, seed=21)
+    g = torch.Generator().manual_seed(5)
+    v = torch.randn(B, N, D, generator=g)
+    v[1, 7] = 0                                   # a zero row: quirk Q10
+    q = torch.randn(B, D, generator=g)
+    adj = O.process_matrix(batch[6], N, 11)
+    for kind in ("explicit", "implicit"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            if kind == "explicit":
+                enc = ExplicitRelationEncoder(D, D, D, 2, 11, num_heads=4, nongt_dim=52, label_bias=False)
+                prefix, R = "spatial_relation.", O.REL_SPA
+            else:
+                enc = ImplicitRelationEncoder(D, D, D, 2, 64, 52, num_heads=4, label_bias=False)
+                prefix, R = "imp_relation.", O.REL_IMP
+        sub = {k[len(prefix):]: t for k, t in full.items() if k.startswith(prefix)}
+        enc.load_state_dict(sub)
+        enc.to(dev).eval()
+        enc.precision = precision
+        vd = v.clone().to(dev).requires_grad_(True)
+        qd = q.clone().to(dev).requires_grad_(True)
+        geo = adj.to(dev) if kind == "explicit" else batch[10]
+        out, aff = enc(vd, geo, qd)
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(6))
+        (out * w.to(dev)).sum().backward()
+        sdg = {k: t.clone().requires_grad_(True) for k, t in full.items() if k.startswith(prefix)}
+        vr = v.clone().requires_grad_(True)
+        qr = q.clone().requires_grad_(True)
+        pe = None if kind == "explicit" else O.position_embedding(O.position_matrix(batch[10], 52), 64)
+        ref, aux = O.gat_relation(sdg, R, vr, qr, adj if kind == "explicit" else None, pe, 4, 52, return_aux=True)
+        (ref * w).sum().backward()
+        assert rel_err(out, ref) < TOL[precision], (kind, rel_err(out, ref))
+        assert rel_err(aff[1], aux["P"]) < TOL[precision] * 5, (kind, "P", rel_err(aff[1], aux["P"]))
+        assert rel_err(vd.grad, vr.grad) < GTOL[precision], (kind, "dv", rel_err(vd.grad, vr.grad))
+        assert rel_err(qd.grad, qr.grad) < GTOL[precision], (kind, "dq", rel_err(qd.grad, qr.grad))
+        for k, p in enc.named_parameters():
+            gr = sdg[prefix + k].grad
+            if gr is None or float(gr.abs().max()) < 1e-4:
+                continue
+            assert rel_err(p.grad, gr) < GTOL[precision], (kind, k, rel_err(p.grad, gr))
+        # outside autograd the encoder mutates and returns its first argument (quirk Q1)
+        with torch.no_grad():
+            v2 = v.clone().to(dev)
+            o2, _ = enc(v2, geo, q.to(dev))
+            assert o2 is v2 and rel_err(v2, ref) < TOL[precision]
+
+
+def test_question_path_matches_oracle():
+    from ekaid_b200.functions import PC
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z, meta = load_case("c1_b3_n52_all_grads")
+    sd, inp, _ = case_inputs(meta)
+    for precision in ("fp32", "bf16"):
+        m = build_model(meta, sd, precision, dev)
+        qv = m.question_vector(PC(precision), inp[8].to(dev))
+        w = torch.randn(qv.shape, generator=torch.Generator().manual_seed(3))
+        (qv * w.to(dev)).sum().backward()
+        sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()
+               if k.startswith(("w_emb", "q_emb", "q_att"))}
+        ref = O.question_vector(sdg, inp[8])
+        (ref * w).sum().backward()
+        assert rel_err(qv, ref) < TOL[precision], rel_err(qv, ref)
+        for k, p in m.named_parameters():
+            if k in sdg and sdg[k].grad is not None and float(sdg[k].grad.abs().max()) > 1e-4:
+                e = rel_err(p.grad, sdg[k].grad)
+                assert e < GTOL[precision], (precision, k, e)
+
+
+def test_batch_coupling_q4_and_local_batch_contract():
+    """Quirk Q4: outputs of one sample depend on the others in the batch; a shard processed alone must equal the
+    oracle on that shard (the data-parallel contract of SURVEY.md section 8(e))."""
+    dev = _dev()
+    z, meta = load_case("c1_b3_n52_all_grads")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, "fp32", dev)
+    shard = tuple(t[:2] for t in inp)
+    with torch.no_grad():
+        full = m(*to_dev(inp, dev))
+        part = m(*to_dev(shard, dev))
+        ref_part = oracle_forward(sd, shard, dict(meta, B=2))
+    assert rel_err(part[3], ref_part[3]) < 1e-4
+    assert rel_err(part[3], full[3][:2]) > 1e-3        # genuinely different function of the batch
+
+
+def test_error_behaviour():
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, "fp32", dev)
+    with pytest.raises(NotImplementedError):
+        m(*to_dev(inp, dev), setting="mode1")
+    with pytest.raises(ValueError):
+        m(*to_dev(inp, dev), graph="bogus")
+    bad = list(to_dev(inp, dev))
+    bad[2] = bad[2][:, :40]                     # adjacency with the wrong node count
+    with pytest.raises(ValueError):
+        m(*bad)
