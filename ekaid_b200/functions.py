@@ -24,6 +24,10 @@ from .lib import Epilogue, call, ptr
 
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 
+# tests only: when set to a list, the ReLU active sets chosen by the kernels are appended (relation steps, then the
+# embed ReLU) so the oracle can evaluate gradients on the same piecewise-linear branch
+DEBUG_SINK = None
+
 
 class PC:
     """precision config: 'bf16' (tensor cores) or 'fp32' (SIMT, 1e-4 parity mode)."""
@@ -57,13 +61,14 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
     ep.Cb = ptr(Cb)
     ep.ldcb = Cb.stride(0) if Cb is not None else 0
     assert A.dtype == B.dtype and A.stride(-1) == 1 and B.stride(-1) == 1
+    info = {"flops": 2.0 * M * N * K, "shape": (M, N, K, transA, transB)}
     if A.dtype == torch.bfloat16:
         call("gemm_bf16", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
-             ctypes.addressof(ep), force_bn, splits)
+             ctypes.addressof(ep), force_bn, splits, info=info)
     else:
         assert A.dtype == torch.float32 and Cb is None
         call("gemm_f32", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
-             ctypes.addressof(ep))
+             ctypes.addressof(ep), info=info)
 
 
 def gemm_T(pc: PC, A, B, M, N, K, transA=0, transB=0, *, want_f32=False, **kw):
@@ -339,15 +344,19 @@ class RelationFn(torch.autograd.Function):
                  _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr())
             ctx.geo = (a0, a1, Wp, bp)
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
+        es = 2 if pc.bf16 else 4
         call("edge_softmax_fwd", pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond), ptr(lbias), ptr(gbias), G, N, Kn, H,
-             P.data_ptr())
+             P.data_ptr(), info={"bytes": G * ((N + Kn) * D * es + N * H * Kn * 4 + N * Kn * 4 * (2 if cond is not None else H))})
         Xn = torch.empty(M, D, dtype=torch.float32, device=dev)
         XnT = torch.empty(M, D, dtype=pc.T, device=dev) if pc.bf16 else None
         mask = torch.empty(M, D, dtype=torch.uint8, device=dev)
         call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, boutc.data_ptr(), X.data_ptr(),
-             G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr())
+             G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr(),
+             info={"bytes": G * (N * H * Kn * 4 + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
         ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
         ctx.saved = (XT, qv, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask)
+        if DEBUG_SINK is not None:
+            DEBUG_SINK.append(mask.bool().cpu())
         if XnT is not None:
             ctx.mark_non_differentiable(P, XnT)
         else:
@@ -368,8 +377,10 @@ class RelationFn(torch.autograd.Function):
         dQKZ = alloc(M, W, dtype=pc.T, device=dev)
         dOut = torch.empty(M, D, dtype=torch.float32, device=dev)
         dPpart = torch.empty(ns, G, N, H, Kn, dtype=torch.float32, device=dev)
+        es = 2 if pc.bf16 else 4
         call("edge_aggregate_bwd", pc.f, dXn.data_ptr(), mask.data_ptr(), P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D,
-             G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr())
+             G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr(),
+             info={"bytes": G * (N * D * (4 + 1 + 4) + N * H * Kn * 4 * (1 + ns) + 2 * Kn * H * D * es)})
         dbout = colsum(dOut, M, D)
         dlb = dgb = None
         if kind == "explicit":
@@ -377,7 +388,8 @@ class RelationFn(torch.autograd.Function):
         else:
             dgb = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
         call("edge_softmax_bwd", pc.f, P.data_ptr(), dPpart.data_ptr(), ns, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond),
-             G, N, Kn, H, dQKZ.data_ptr(), ptr(dlb), ptr(dgb))
+             G, N, Kn, H, dQKZ.data_ptr(), ptr(dlb), ptr(dgb),
+             info={"bytes": G * (N * H * Kn * 4 * (2 + ns) + 2 * (N + Kn) * D * es)})
         dp0 = dp1 = None
         if kind == "explicit":
             a0, a1, Lb = ctx.geo
@@ -443,6 +455,8 @@ class FusionFn(torch.autograd.Function):
              attended.data_ptr())
         ctx.pc, ctx.dims, ctx.mode, ctx.coefs = pc, dims, mode, coefs
         ctx.saved = (Xc, CAT, WcgT, WeT, wac, cx, gt, E, att)
+        if DEBUG_SINK is not None:
+            DEBUG_SINK.append((E > 0).cpu())
         return att, attended
 
     @staticmethod

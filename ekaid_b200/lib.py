@@ -90,10 +90,29 @@ def ptr(t) -> int | None:
     return None if t is None else t.data_ptr()
 
 
-def call(name: str, *args) -> None:
+# kernels launched per C-ABI call (for the bench's `gpu_launches` count)
+KERNELS_PER_CALL = {"colsum": 2, "att_pool_fwd": 2, "qpool_fwd": 2, "qpool_bwd": 2}
+LAUNCHES = 0
+# bench only: when a list, every call is bracketed by CUDA events on the launching stream:
+# (name, start_event, end_event, info)
+PROFILE = None
+
+
+def call(name: str, *args, info=None) -> None:
     """Call `ekaid_<name>` on the current torch CUDA stream (appended as last argument)."""
+    global LAUNCHES
     lib = load()
-    rc = getattr(lib, "ekaid_" + name)(*args, stream_ptr())
+    fn = getattr(lib, "ekaid_" + name)
+    if PROFILE is None:
+        rc = fn(*args, stream_ptr())
+    else:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, stream_ptr())
+        e1.record()
+        PROFILE.append((name, e0, e1, info))
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 

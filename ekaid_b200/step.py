@@ -1,0 +1,121 @@
+"""Training / inference step glue for the graph+fusion path (reference model/train_mimic.py:203-269 and
+model/test_mimic.py:92-132), as a reusable object instead of script-level code.
+
+    unpack the 13-tuple -> H2D -> process_matrix x4 (ONE kernel each instead of 14 host-syncing label loops)
+    -> ChangeDetector -> loss terms that touch the path -> backward -> (NCCL gradient all-reduce) -> Adam
+
+The answer decoder (DynamicSpeaker) is the boundary consumer (SURVEY.md section 8(f) "next"): a caller-supplied
+`decoder_loss(bef, aft, diff, labels, masks)` closes the loop exactly like `speaker._forward` + LanguageModelCriterion
+do in the reference; without one, a fixed cotangent stands in for the decoder gradient (bench / tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from . import lib
+from .functions import onehot_adj
+from .modules import ChangeDetector
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (reference utils/utils.py:96-99: lr 1e-4, betas (0.9, 0.999), eps 1e-8, wd 0) on
+    ONE flat fp32 buffer: parameters and gradients of the module are re-pointed into two contiguous buffers, so the
+    optimizer is a single kernel launch and the data-parallel gradient exchange a single NCCL all-reduce."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        params = [p for p in params]
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.pow_state = torch.ones(2, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view(p.shape)
+            p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+        self.params = params
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self):
+        lib.call("adam_advance", self.pow_state.data_ptr(), self.betas[0], self.betas[1])
+        lib.call("adam_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.pow_state.data_ptr())
+
+
+def process_batch(batch, cfg, device):
+    """train_mimic.py:206-227: move the loader's 13-tuple to the device and expand the four integer adjacency
+    matrices to one-hot planes.  Boxes stay where they are (the reference never moves them)."""
+    (d_feats, sc_feats, labels, sc_pos_labels, masks, pair_index, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb,
+     question) = batch
+    nb = True
+    d_feats, sc_feats = d_feats.to(device, non_blocking=nb), sc_feats.to(device, non_blocking=nb)
+    question = question.to(device, non_blocking=nb)
+    labels = labels.squeeze(1).to(device, non_blocking=nb)
+    masks = masks.squeeze(1).float().to(device, non_blocking=nb)
+    n = d_feats.shape[1]
+    cd = cfg.model.change_detector
+    d_adj = onehot_adj(d_adj.to(device, non_blocking=nb), n, cd.spa_label_num)
+    q_adj = onehot_adj(q_adj.to(device, non_blocking=nb), n, cd.spa_label_num)
+    d_sem = onehot_adj(d_sem.to(device, non_blocking=nb), n, cd.sem_label_num)
+    q_sem = onehot_adj(q_sem.to(device, non_blocking=nb), n, cd.sem_label_num)
+    d_bb = d_bb.to(device, non_blocking=nb)
+    q_bb = q_bb.to(device, non_blocking=nb)
+    return (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question), labels, masks
+
+
+class GraphFusionStep:
+    """One data-parallel rank of the reference's train/test step for the graph+fusion path."""
+
+    def __init__(self, change_detector: ChangeDetector, cfg, graph: str = "all", lr: float = 1e-4,
+                 decoder_loss: Optional[Callable] = None, process_group=None):
+        self.cd = change_detector
+        self.cfg = cfg
+        self.graph = graph
+        self.decoder_loss = decoder_loss
+        self.pg = process_group
+        self.opt = FlatAdam(list(change_detector.parameters()), lr=lr)
+        self._cot = None
+
+    def _surrogate(self, bef, aft, diff):
+        # stands in for d(decoder NLL)/d(bef, aft, diff): fixed unit-scale cotangents
+        if self._cot is None or self._cot[0].shape != bef.shape:
+            g = torch.Generator(device="cpu").manual_seed(4242)
+            self._cot = [torch.randn(bef.shape, generator=g).to(bef.device) / bef.shape[1] for _ in range(3)]
+        return (bef * self._cot[0]).sum() + (aft * self._cot[1]).sum() + (diff * self._cot[2]).sum()
+
+    def loss(self, inputs, labels=None, masks=None):
+        pred, att_bef, att_aft, bef, aft, diff = self.cd(*inputs, setting="mode2", graph=self.graph)
+        if self.decoder_loss is not None:
+            dec = self.decoder_loss(bef, aft, diff, labels, masks)
+        else:
+            dec = self._surrogate(bef, aft, diff)
+        bsz = bef.shape[0]
+        att_sum = (att_bef.sum() + att_aft.sum()) / (2 * bsz)                 # train_mimic.py:246
+        return dec + 2.5e-03 * att_sum                                        # train_mimic.py:247
+
+    def train_step(self, inputs, labels=None, masks=None) -> torch.Tensor:
+        """optimizer.zero_grad -> forward -> backward -> [all-reduce(mean)] -> Adam  (train_mimic.py:220-269).
+        Returns the (device) loss tensor; no host sync happens here."""
+        self.opt.zero_grad()
+        total = self.loss(inputs, labels, masks)
+        total.backward()
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.opt.grad, op=dist.ReduceOp.AVG, group=self.pg)
+        self.opt.step()
+        return total.detach()
+
+    @torch.no_grad()
+    def infer_step(self, inputs):
+        """test_mimic.py:116-117: the three vectors the decoder consumes, plus the attention maps."""
+        return self.cd(*inputs, setting="mode2", graph=self.graph)

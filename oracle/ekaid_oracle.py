@@ -116,7 +116,7 @@ def position_embedding(pos_mat: Tensor, feat_dim: int = 64, wave_length: float =
 # one relation encoder step (GAT)
 # ----------------------------------------------------------------------------------------------
 def gat_relation(sd, R: str, X: Tensor, qv: Tensor, adj: Optional[Tensor], pos_emb: Optional[Tensor],
-                 num_heads: int, nongt_dim: int, return_aux: bool = False):
+                 num_heads: int, nongt_dim: int, return_aux: bool = False, relu_mask: Optional[Tensor] = None):
     """X <- X + GAT(cat(X, q), adj)   (models/relation_encoder.py:57-84 / :112-132,
     models/graph_att.py:53-106, models/graph_att_layer.py:60-178), eval mode.
 
@@ -155,7 +155,12 @@ def gat_relation(sd, R: str, X: Tensor, qv: Tensor, adj: Optional[Tensor], pos_e
     out_t = P.reshape(B, N * Hn, K) @ sf[:, :K]                       # Q3
     out = out_t.reshape(B * N, Hn * D) @ sd[nn_ + ".linear_out_2.weight"].t() + sd[nn_ + ".linear_out_2.bias"]
     out = out.view(B, N, D)
-    Xn = X + F.relu(out + out)                                        # Q2 doubling; graph_att.py:102-104
+    if relu_mask is None:
+        Xn = X + F.relu(out + out)                                    # Q2 doubling; graph_att.py:102-104
+    else:
+        # gradient checks only: use the active set chosen by the implementation under test, so that ReLU kinks
+        # (pre-activations within rounding distance of 0) do not show up as gradient differences
+        Xn = X + (out + out) * relu_mask.to(out.dtype).view_as(out)
     if return_aux:
         return Xn, {"self_feat": sf, "P": P, "out": out}
     return Xn
@@ -168,7 +173,8 @@ def change_detector_forward(sd: Dict[str, Tensor], input_1: Tensor, input_2: Ten
                             d_adj: Tensor, q_adj: Tensor, d_sem_adj: Tensor, q_sem_adj: Tensor,
                             d_bb: Tensor, q_bb: Tensor, question: Tensor, *, graph: str = "all",
                             num_heads: int = 4, nongt_dim: int = 52, pos_emb_dim: int = 64,
-                            coef_sem: float = 0.333, coef_spa: float = 0.333, return_aux: bool = False):
+                            coef_sem: float = 0.333, coef_spa: float = 0.333, return_aux: bool = False,
+                            relu_masks: Optional[Sequence[Tensor]] = None):
     """models/modules.py:169-313 (eval mode, empty_image False, feature_mode != 'mode0')."""
     dt = input_1.dtype
     aux = {}
@@ -177,18 +183,32 @@ def change_detector_forward(sd: Dict[str, Tensor], input_1: Tensor, input_2: Ten
     qv = question_vector(sd, question)                                # modules.py:200-206
     aux["qv"] = qv
     kw = dict(num_heads=num_heads, nongt_dim=nongt_dim)
-    n_steps = 0
+    # relu_masks (gradient checks only): one [2*B*N, D] mask per relation in execution order (main rows, then
+    # reference rows), then one [2*B*N, dim] mask for the embed ReLU
+    masks = list(relu_masks) if relu_masks is not None else None
+    BN = Xb.shape[0] * Xb.shape[1]
+
+    def nxt():
+        if masks is None:
+            return None, None
+        mk = masks.pop(0)
+        return mk[:BN], mk[BN:]
+
     if graph in ("semantic", "all"):                                  # modules.py:216-218
-        Xb = gat_relation(sd, REL_SEM, Xb, qv, d_sem_adj, None, **kw)
-        Xa = gat_relation(sd, REL_SEM, Xa, qv, q_sem_adj, None, **kw)
+        mb, ma = nxt()
+        Xb = gat_relation(sd, REL_SEM, Xb, qv, d_sem_adj, None, relu_mask=mb, **kw)
+        Xa = gat_relation(sd, REL_SEM, Xa, qv, q_sem_adj, None, relu_mask=ma, **kw)
     if graph in ("spatial", "all", "i+s"):                            # modules.py:221-223
-        Xb = gat_relation(sd, REL_SPA, Xb, qv, d_adj, None, **kw)
-        Xa = gat_relation(sd, REL_SPA, Xa, qv, q_adj, None, **kw)
+        mb, ma = nxt()
+        Xb = gat_relation(sd, REL_SPA, Xb, qv, d_adj, None, relu_mask=mb, **kw)
+        Xa = gat_relation(sd, REL_SPA, Xa, qv, q_adj, None, relu_mask=ma, **kw)
     if graph in ("implicit", "all", "i+s"):                           # modules.py:226-230
         pe_b = position_embedding(position_matrix(d_bb, nongt_dim), pos_emb_dim)
         pe_a = position_embedding(position_matrix(q_bb, nongt_dim), pos_emb_dim)
-        Xb = gat_relation(sd, REL_IMP, Xb, qv, None, pe_b, **kw)
-        Xa = gat_relation(sd, REL_IMP, Xa, qv, None, pe_a, **kw)
+        mb, ma = nxt()
+        Xb = gat_relation(sd, REL_IMP, Xb, qv, None, pe_b, relu_mask=mb, **kw)
+        Xa = gat_relation(sd, REL_IMP, Xa, qv, None, pe_a, relu_mask=ma, **kw)
+    emb, ema = nxt()
     # Q1: input_bef1/2/3 alias ONE tensor  (modules.py:233-247)
     if graph == "all":
         Xb = coef_sem * Xb + coef_spa * Xb + (1 - coef_sem - coef_spa) * Xb
@@ -206,13 +226,14 @@ def change_detector_forward(sd: Dict[str, Tensor], input_1: Tensor, input_2: Ten
         gate = torch.sigmoid(diff @ g1.t() + X @ g2.t() + sd["gate2.bias"])
         return gate * ctx
 
-    def pool(X, Xs):                                                  # modules.py:290-308
-        e = F.relu(torch.cat([X, diff, Xs], -1) @ sd["embed.0.weight"].t() + sd["embed.0.bias"])
+    def pool(X, Xs, emask):                                           # modules.py:290-308
+        pre = torch.cat([X, diff, Xs], -1) @ sd["embed.0.weight"].t() + sd["embed.0.bias"]
+        e = F.relu(pre) if emask is None else pre * emask.to(pre.dtype).view_as(pre)
         att = torch.sigmoid(e @ sd["att.weight"].t() + sd["att.bias"])          # [B,N,1]
         return att.transpose(1, 2), (X * att).sum(1)
 
-    att_b, attended_1 = pool(Xb, fuse(Xb))
-    att_a, attended_2 = pool(Xa, fuse(Xa))
+    att_b, attended_1 = pool(Xb, fuse(Xb), emb)
+    att_a, attended_2 = pool(Xa, fuse(Xa), ema)
     input_attended = attended_2 - attended_1                          # modules.py:309
     pred = input_attended @ sd["fc1.weight"].t() + sd["fc1.bias"]     # modules.py:310
     outs = (pred.to(dt), att_b, att_a, attended_1, attended_2, input_attended)
