@@ -132,28 +132,31 @@ __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const doubl
   }
 }
 
-// dWp_part[g, h, 0:64], dbp_part[g, h]  (layout [G, H*65]: 64 weights then bias)
-__global__ void geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
-                                     const float* __restrict__ Wp, const float* __restrict__ bp,
-                                     const float* __restrict__ dim_t, int N, int Kn, int H,
-                                     const float* __restrict__ dgbias, float* __restrict__ part) {
-  extern __shared__ float sm[];      // H*64 + H weights, then H*65 accumulators, then 8 wave lengths
+// part[g, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h].
+// Two phases per tile of 128 pairs: (1) one thread per pair recomputes the embedding and df = dgbias / f (f > 1e-6),
+// parks both in shared memory; (2) one thread per (h,k) output accumulates over the tile.  No shuffles, no atomics.
+constexpr int GB_TILE = 128;
+__global__ void __launch_bounds__(GB_TILE)
+geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
+                     const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ dim_t, int N,
+                     int Kn, int H, const float* __restrict__ dgbias, float* __restrict__ part) {
+  extern __shared__ float sm[];      // weights H*65 | 8 wave lengths | emb [GB_TILE][65] | df [GB_TILE][8]
   float* sW = sm;
-  float* acc = sm + H * 64 + H;
-  float* sDim = sm + 2 * H * 65;
-  if (threadIdx.x < 8) sDim[threadIdx.x] = dim_t[threadIdx.x];
-  for (int e = threadIdx.x; e < H * 64; e += blockDim.x) sW[e] = Wp[e];
-  for (int e = threadIdx.x; e < H; e += blockDim.x) sW[H * 64 + e] = bp[e];
-  for (int e = threadIdx.x; e < H * 65; e += blockDim.x) acc[e] = 0.f;
-  __syncthreads();
+  float* sDim = sm + H * 65;
+  float* sE = sDim + 8;
+  float* sDf = sE + GB_TILE * 65;
+  const int tid = threadIdx.x;
+  if (tid < 8) sDim[tid] = dim_t[tid];
+  for (int e = tid; e < H * 64; e += GB_TILE) sW[e] = Wp[e];
+  for (int e = tid; e < H; e += GB_TILE) sW[H * 64 + e] = bp[e];
   const int g = blockIdx.x;
   const double* bb = (g < g_split) ? bb0 + (size_t)g * N * 4 : bb1 + (size_t)(g - g_split) * N * 4;
-  const int lane = threadIdx.x & 31;
-  // warp-cooperative: every lane handles one pair, then the warp reduces each of the 65*H sums
   const int total = N * Kn;
-  const int iters = (total + blockDim.x - 1) / blockDim.x;
-  for (int itn = 0; itn < iters; ++itn) {
-    const int e = itn * blockDim.x + threadIdx.x;
+  const int nout = H * 65;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};         // outputs tid, tid+128, ... (H <= 8 -> <= 520 outputs)
+  __syncthreads();
+  for (int t0 = 0; t0 < total; t0 += GB_TILE) {
+    const int e = t0 + tid;
     float emb[64];
     float df[8];
 #pragma unroll
@@ -170,18 +173,29 @@ __global__ void geom_bias_bwd_kernel(const double* __restrict__ bb0, const doubl
 #pragma unroll
       for (int k = 0; k < 64; ++k) emb[k] = 0.f;
     }
-    for (int h = 0; h < H; ++h) {
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        const float s = warp_sum(df[h] * emb[k]);
-        if (lane == 0) atomicAdd(&acc[h * 65 + k], s);     // shared-memory atomics, per-block
+    for (int k = 0; k < 64; ++k) sE[tid * 65 + k] = emb[k];
+    sE[tid * 65 + 64] = 1.f;                           // bias column
+#pragma unroll
+    for (int h = 0; h < 8; ++h) sDf[tid * 8 + h] = df[h];
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const int o = tid + a * GB_TILE;
+      if (o < nout) {
+        const int h = o / 65, k = o % 65;
+        float s = acc[a];
+        for (int p = 0; p < GB_TILE; ++p) s = fmaf(sDf[p * 8 + h], sE[p * 65 + k], s);
+        acc[a] = s;
       }
-      const float sb = warp_sum(df[h]);
-      if (lane == 0) atomicAdd(&acc[h * 65 + 64], sb);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < H * 65; e += blockDim.x) part[(size_t)g * H * 65 + e] = acc[e];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    const int o = tid + a * GB_TILE;
+    if (o < nout) part[(size_t)g * nout + o] = acc[a];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -510,8 +524,8 @@ int ek_geom_bias_bwd_launch(const double* bb0, const double* bb1, int g_split, c
                             const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
                             cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
-  geom_bias_bwd_kernel<<<G, 128, (2 * H * 65 + 8) * sizeof(float), st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
-                                                                          dgbias, part);
+  const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float);
+  geom_bias_bwd_kernel<<<G, GB_TILE, smem, st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -555,9 +569,20 @@ static int edge_aggregate_fwd_t(const float* P, const T* QKZ, long long ld, int 
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
+int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
+                          int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
+                          cudaStream_t st);
+int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
+                          int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, cudaStream_t st);
+
 int ek_edge_aggregate_fwd_launch(int is_bf16, const float* P, const void* QKZ, long long ld, int D, const float* b_out,
                                  const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT,
                                  long long ldt, uint8_t* mask, cudaStream_t st) {
+  if (is_bf16) {   // tensor-core kernel (edge_mma.cu); SIMT template only for shapes it does not take
+    const int rc = ek_agg_fwd_mma_launch(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT, ldt,
+                                         mask, st);
+    if (rc != EK_ERR_UNSUPPORTED) return rc;
+  }
   return is_bf16 ? edge_aggregate_fwd_t<bf16>(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT,
                                               ldt, mask, st)
                  : edge_aggregate_fwd_t<float>(P, (const float*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout,
@@ -585,6 +610,11 @@ static int edge_aggregate_bwd_t(const float* dXout, const uint8_t* mask, const f
 int ek_edge_aggregate_bwd_launch(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                                  long long ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut,
                                  float* dPpart, cudaStream_t st) {
+  if (is_bf16) {
+    const int rc = ek_agg_bwd_mma_launch(dXout, mask, P, (const bf16*)QKZ, ld, D, G, N, Kn, H, (bf16*)dQKZ, dOut,
+                                         dPpart, st);
+    if (rc != EK_ERR_UNSUPPORTED) return rc;
+  }
   return is_bf16 ? edge_aggregate_bwd_t<bf16>(dXout, mask, P, (const bf16*)QKZ, ld, D, G, N, Kn, H, (bf16*)dQKZ, dOut,
                                               dPpart, st)
                  : edge_aggregate_bwd_t<float>(dXout, mask, P, (const float*)QKZ, ld, D, G, N, Kn, H, (float*)dQKZ,

@@ -1,0 +1,342 @@
+// bf16 path of the per-image edge kernels on tensor cores (warp-level mma.sync m16n8k16, fp32 accumulate).
+// The per-image problems are tiny GEMMs (52 x 208 x 1024 and 52 x 52 x 256), far below a tcgen05 128-row tile,
+// and the kernels are bound by the Z / X traffic, so the legacy warp MMA is the right tool here: operands are
+// staged once in shared memory (cp.async for the 16-byte-aligned Z rows), fragments come from ldmatrix.
+//
+//   aggregate fwd : out[i, c]   = sum_{(h,j)} P[i,(h,j)] Z[(h,j), c] + b ;  Xout = Xin + relu(2 out)
+//   aggregate bwd : dZ[(h,j),c] = sum_i P[i,(h,j)] dout[i,c] ;  dPpart[slice][i,(h,j)] = sum_{c in slice} dout[i,c] Z[(h,j),c]
+//
+// P is split into bf16 hi + lo parts in the forward so the attention weights keep 16 significant bits.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NC = 128;          // output columns per CTA
+constexpr int ZS = NC + 8;       // shared-memory row pitch (elements) of Z / dout tiles: 272 B = odd multiple of 16 B
+constexpr int MAXCH = 256;       // (h,j) rows staged per chunk
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// stage rows k0..k0+kc of the (h,j)-indexed Z matrix, columns [c0, c0+NC), into Zs[kc_pad][ZS]
+__device__ __forceinline__ void load_z_chunk(bf16* Zs, const bf16* __restrict__ QKZ, long long ld, int D, int g, int N,
+                                             int Kn, int HK, int k0, int kc_pad, int c0) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < kc_pad * (NC / 8); e += blockDim.x) {
+    const int kk = e / (NC / 8), ch = e % (NC / 8);
+    const int k = k0 + kk;
+    bf16* dst = Zs + kk * ZS + ch * 8;
+    if (k < HK && c0 + ch * 8 < D) {
+      const int h = k / Kn, j = k % Kn;
+      cp_async16(dst, QKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + ch * 8);
+    } else {
+      *(uint4*)dst = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int MR>   // padded query rows per CTA pass: 64 or 128
+__global__ void __launch_bounds__(256)
+agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, long long ld, int D,
+                   const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
+                   float* __restrict__ Xout, bf16* __restrict__ XoutT, long long ldt, uint8_t* __restrict__ mask,
+                   int kchunk) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int PS = kchunk + 8;                        // P row pitch (elements)
+  bf16* Zs = (bf16*)smraw;                          // [kchunk][ZS]
+  bf16* Phi = Zs + (size_t)kchunk * ZS;             // [MR][PS]
+  bf16* Plo = Phi + (size_t)MR * PS;                // [MR][PS]
+  const int g = blockIdx.x, c0 = blockIdx.y * NC;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HK = H * Kn;
+  constexpr int ITEMS = (MR / 16) * 2;              // (16-row tile, 64-column half)
+  constexpr int IPW = ITEMS / 8;                    // items per warp
+  for (int r0 = 0; r0 < N; r0 += MR) {
+    float acc[IPW][8][4];
+#pragma unroll
+    for (int a = 0; a < IPW; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    for (int k0 = 0; k0 < HK; k0 += kchunk) {
+      const int kc = min(kchunk, HK - k0);
+      const int kc_pad = (kc + 15) & ~15;
+      __syncthreads();
+      load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0);
+      for (int e = tid; e < MR * kc_pad; e += 256) {
+        const int i = e / kc_pad, kk = e % kc_pad;
+        float p = 0.f;
+        if (r0 + i < N && kk < kc) p = P[((size_t)g * N + r0 + i) * HK + k0 + kk];
+        const bf16 hi = __float2bfloat16_rn(p);
+        Phi[i * PS + kk] = hi;
+        Plo[i * PS + kk] = __float2bfloat16_rn(p - __bfloat162float(hi));
+      }
+      cp_async_wait_all();
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < IPW; ++it) {
+        const int item = warp + it * 8;
+        const int mt = item >> 1, nh = item & 1;
+        for (int kt = 0; kt < kc_pad / 16; ++kt) {
+          uint32_t ah[4], al[4];
+          const int arow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int acol = kt * 16 + (lane >> 4) * 8;
+          ldsm_x4(ah, Phi + arow * PS + acol);
+          ldsm_x4(al, Plo + arow * PS + acol);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {           // pairs of 8-column tiles
+            uint32_t bfr[4];
+            const int brow = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+            const int bcol = nh * 64 + np * 16 + (lane >> 4) * 8;
+            ldsm_x4_t(bfr, Zs + brow * ZS + bcol);
+            mma_bf16_16816(acc[it][2 * np], ah, bfr[0], bfr[1]);
+            mma_bf16_16816(acc[it][2 * np], al, bfr[0], bfr[1]);
+            mma_bf16_16816(acc[it][2 * np + 1], ah, bfr[2], bfr[3]);
+            mma_bf16_16816(acc[it][2 * np + 1], al, bfr[2], bfr[3]);
+          }
+        }
+      }
+    }
+    // epilogue: + b_out, doubled ReLU, residual
+#pragma unroll
+    for (int it = 0; it < IPW; ++it) {
+      const int item = warp + it * 8;
+      const int mt = item >> 1, nh = item & 1;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = c0 + nh * 64 + nt * 8 + 2 * (lane & 3);
+        if (col >= D) continue;
+        const float2 bo = *(const float2*)(b_out + col);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int i = r0 + mt * 16 + (lane >> 2) + hh * 8;
+          if (i >= N) continue;
+          const size_t row = (size_t)g * N + i;
+          const float o0 = acc[it][nt][2 * hh] + bo.x, o1 = acc[it][nt][2 * hh + 1] + bo.y;
+          const float2 xi = *(const float2*)(Xin + row * D + col);
+          const float x0 = xi.x + fmaxf(o0 + o0, 0.f), x1 = xi.y + fmaxf(o1 + o1, 0.f);
+          *(float2*)(Xout + row * D + col) = make_float2(x0, x1);
+          if (XoutT) *(__nv_bfloat162*)(XoutT + row * ldt + col) = __floats2bfloat162_rn(x0, x1);
+          uchar2 mk;
+          mk.x = (o0 + o0) > 0.f ? 1 : 0;
+          mk.y = (o1 + o1) > 0.f ? 1 : 0;
+          *(uchar2*)(mask + row * D + col) = mk;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int MR>   // padded query rows (all of them are staged): 64 or 128
+__global__ void __launch_bounds__(256)
+agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ mask, const float* __restrict__ P,
+                   const bf16* __restrict__ QKZ, long long ld, int D, int N, int Kn, int H, bf16* __restrict__ dQKZ,
+                   float* __restrict__ dOut, float* __restrict__ dPpart, int kchunk) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int PS = kchunk + 8;
+  bf16* dOs = (bf16*)smraw;                         // [MR][ZS]   dout tile (i, c)
+  bf16* Zs = dOs + (size_t)MR * ZS;                 // [kchunk][ZS]
+  bf16* Ps = Zs + (size_t)kchunk * ZS;              // [MR][PS]   P (i, (h,j)) chunk
+  const int g = blockIdx.x, slice = blockIdx.y, c0 = slice * NC;
+  const int G = gridDim.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int HK = H * Kn;
+  // dout = 2 * mask * dX  -> global (fp32, for the b_out column sum) and shared (bf16 operand)
+  for (int e = tid; e < MR * (NC / 4); e += 256) {
+    const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < N && c0 + c < D) {
+      const size_t idx = ((size_t)g * N + i) * D + c0 + c;
+      const float4 d = *(const float4*)(dXout + idx);
+      const uchar4 m = *(const uchar4*)(mask + idx);
+      v = make_float4(m.x ? 2.f * d.x : 0.f, m.y ? 2.f * d.y : 0.f, m.z ? 2.f * d.z : 0.f, m.w ? 2.f * d.w : 0.f);
+      *(float4*)(dOut + idx) = v;
+    }
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *(uint32_t*)&a;
+    pk.y = *(uint32_t*)&b;
+    *(uint2*)(dOs + i * ZS + c) = pk;
+  }
+  float* dPg = dPpart + ((size_t)slice * G + g) * N * HK;
+  for (int k0 = 0; k0 < HK; k0 += kchunk) {
+    const int kc = min(kchunk, HK - k0);
+    const int kc_pad = (kc + 15) & ~15;
+    __syncthreads();
+    load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0);
+    for (int e = tid; e < MR * kc_pad; e += 256) {
+      const int i = e / kc_pad, kk = e % kc_pad;
+      float p = 0.f;
+      if (i < N && kk < kc) p = P[((size_t)g * N + i) * HK + k0 + kk];
+      Ps[i * PS + kk] = __float2bfloat16_rn(p);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- dZ[(h,j), c] = sum_i P[i,(h,j)] dout[i,c] : rows = (h,j) tiles, round-robin over warps
+    for (int mt = warp; mt < kc_pad / 16; mt += 8) {
+      float acc[16][4];
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < MR / 16; ++kt) {
+        uint32_t af[4];
+        // A = P^T: stored [i (k)][(h,j) (m)] -> transposed ldmatrix
+        const int arow = kt * 16 + (lane >> 4) * 8 + (lane & 7);
+        const int acol = mt * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4_t(af, Ps + arow * PS + acol);
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+          uint32_t bfr[4];
+          const int brow = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+          const int bcol = np * 16 + (lane >> 4) * 8;
+          ldsm_x4_t(bfr, dOs + brow * ZS + bcol);
+          mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
+          mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const int col = c0 + nt * 8 + 2 * (lane & 3);
+        if (col >= D) continue;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int kk = mt * 16 + (lane >> 2) + hh * 8;
+          if (kk >= kc) continue;
+          const int k = k0 + kk, h = k / Kn, j = k % Kn;
+          *(__nv_bfloat162*)(dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + col) =
+              __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
+        }
+      }
+    }
+    // ---- dPpart[i, (h,j)] = sum_c dout[i,c] Z[(h,j),c] : items = (16-row tile of i, half of the (h,j) tiles)
+    const int ntiles = kc_pad / 8;
+    const int nhalf = (ntiles + 1) / 2;              // <= 16
+    for (int item = warp; item < (MR / 16) * 2; item += 8) {
+      const int mt = item >> 1, nb = (item & 1) * nhalf;
+      const int ncnt = min(nhalf, ntiles - nb);
+      float acc[16][4];
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < NC / 16; ++kt) {
+        uint32_t af[4];
+        const int arow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int acol = kt * 16 + (lane >> 4) * 8;
+        ldsm_x4(af, dOs + arow * ZS + acol);
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+          if (2 * np < ncnt) {
+            // B(k = c, n = (h,j)) = Z[(h,j)][c]: stored [n][k] -> plain ldmatrix
+            uint32_t bfr[4];
+            int nrow = (nb + 2 * np) * 8 + (lane >> 4) * 8 + (lane & 7);
+            if (nrow >= kc_pad) nrow = kc_pad - 1;   // odd tile count: second tile unused
+            const int kcol = kt * 16 + ((lane >> 3) & 1) * 8;
+            ldsm_x4(bfr, Zs + nrow * ZS + kcol);
+            mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
+            if (2 * np + 1 < ncnt) mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        if (nt >= ncnt) continue;
+        const int kk = (nb + nt) * 8 + 2 * (lane & 3);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int i = mt * 16 + (lane >> 2) + hh * 8;
+          if (i >= N) continue;
+          float* dst = dPg + (size_t)i * HK + k0 + kk;
+          if (kk < kc) dst[0] = acc[nt][2 * hh];
+          if (kk + 1 < kc) dst[1] = acc[nt][2 * hh + 1];
+        }
+      }
+    }
+  }
+}
+
+template <typename K>
+int set_smem(K kern, size_t smem, size_t& configured, const char* what) {
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { ek_set_error("%s: smem %zu: %s", what, smem, cudaGetErrorString(e)); return EK_ERR_CUDA; }
+    configured = smem;
+  }
+  return EK_OK;
+}
+
+}  // namespace
+
+// returns EK_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the SIMT template)
+int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
+                          int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
+                          cudaStream_t st) {
+  if ((D % 8) || (ld % 8) || (ldt % 2) || ((uintptr_t)QKZ & 15)) return EK_ERR_UNSUPPORTED;
+  const int HK = H * Kn;
+  const int HKp = (HK + 15) & ~15;
+  const int kchunk = HKp < MAXCH ? HKp : MAXCH;
+  const int MR = N <= 64 ? 64 : 128;
+  const size_t smem = ((size_t)kchunk * ZS + 2 * (size_t)MR * (kchunk + 8)) * sizeof(bf16);
+  dim3 grid(G, ek_div_up(D, NC));
+  static size_t c64 = 0, c128 = 0;
+  if (MR == 64) {
+    int rc = set_smem(agg_fwd_mma_kernel<64>, smem, c64, "agg_fwd_mma");
+    if (rc) return rc;
+    agg_fwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk);
+  } else {
+    int rc = set_smem(agg_fwd_mma_kernel<128>, smem, c128, "agg_fwd_mma");
+    if (rc) return rc;
+    agg_fwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk);
+  }
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
+                          int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, cudaStream_t st) {
+  if ((D % 8) || (ld % 8) || ((uintptr_t)QKZ & 15) || ((uintptr_t)dQKZ & 3) || N > 128) return EK_ERR_UNSUPPORTED;
+  const int HK = H * Kn;
+  const int HKp = (HK + 15) & ~15;
+  const int kchunk = HKp < MAXCH ? HKp : MAXCH;
+  const int MR = N <= 64 ? 64 : 128;
+  const size_t smem = ((size_t)MR * ZS + (size_t)kchunk * ZS + (size_t)MR * (kchunk + 8)) * sizeof(bf16);
+  dim3 grid(G, ek_div_up(D, NC));
+  static size_t c64 = 0, c128 = 0;
+  if (MR == 64) {
+    int rc = set_smem(agg_bwd_mma_kernel<64>, smem, c64, "agg_bwd_mma");
+    if (rc) return rc;
+    agg_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk);
+  } else {
+    int rc = set_smem(agg_bwd_mma_kernel<128>, smem, c128, "agg_bwd_mma");
+    if (rc) return rc;
+    agg_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk);
+  }
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}

@@ -274,30 +274,45 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (nb + j < N) atomicAdd(cp + j, __uint_as_float(r[j]));
-        } else if (vec_ok && nb + 32 <= N) {
+        } else if ((vec_ok & 1) && nb + 32 <= N) {
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (ep.bias) {
+            if (vec_ok & 2) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg((const float4*)(ep.bias + nb + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg((const float4*)(ep.bias + nb + j));
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + nb + j);
             }
           }
           if (ep.addend) {
             const float* ap = ep.addend + m * ep.ldadd + nb;
+            if (vec_ok & 4) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a4 = *(const float4*)(ap + j);
-              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 a4 = *(const float4*)(ap + j);
+                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += ap[j];
             }
           }
           if (rowb_ptr) {
+            if (vec_ok & 8) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a4 = __ldg((const float4*)(rowb_ptr + nb + j));
-              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 a4 = __ldg((const float4*)(rowb_ptr + nb + j));
+                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(rowb_ptr + nb + j);
             }
           }
           if (ep.act != EK_ACT_NONE) {
@@ -482,12 +497,13 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   if (!transB) rc = make_tmap(&tb, B, N, K, ldb, bn);   // [N rows, K cols], box {64, bn}
   else rc = make_tmap(&tb, B, K, N, ldb, BK);           // [K rows, N cols], box {64, 64}
   if (rc) return rc;
-  int vec_ok = 1;
-  if (ep.C && (((uintptr_t)ep.C & 15) || (ep.ldc & 3))) vec_ok = 0;
-  if (ep.Cb && (((uintptr_t)ep.Cb & 15) || (ep.ldcb & 7))) vec_ok = 0;
-  if (ep.bias && ((uintptr_t)ep.bias & 15)) vec_ok = 0;
-  if (ep.addend && (((uintptr_t)ep.addend & 15) || (ep.ldadd & 3))) vec_ok = 0;
-  if (ep.rowb && (((uintptr_t)ep.rowb & 15) || (ep.ldrowb & 3) || ((uintptr_t)ep.rowb_alt & 15))) vec_ok = 0;
+  // bit 0: 16-byte vector stores possible; bits 1..3: vector loads of bias / addend / row-broadcast operands
+  int vec_ok = 15;
+  if (ep.C && (((uintptr_t)ep.C & 15) || (ep.ldc & 3))) vec_ok &= ~1;
+  if (ep.Cb && (((uintptr_t)ep.Cb & 15) || (ep.ldcb & 7))) vec_ok &= ~1;
+  if (ep.bias && ((uintptr_t)ep.bias & 15)) vec_ok &= ~2;
+  if (ep.addend && (((uintptr_t)ep.addend & 15) || (ep.ldadd & 3))) vec_ok &= ~4;
+  if (ep.rowb && (((uintptr_t)ep.rowb & 15) || (ep.ldrowb & 3) || ((uintptr_t)ep.rowb_alt & 15))) vec_ok &= ~8;
   // split-K (auto when splits == 0): only for plain fp32 outputs with too few tiles to fill the chip
   const bool plain = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE;
   const int num_kb = ek_div_up(K, BK);

@@ -17,16 +17,34 @@ __global__ void embed_gather_kernel(const long long* __restrict__ q, const float
   }
 }
 // demb[v, c] = sum over tokens equal to v of dE[row, c]  (c < ed; the second table is frozen).
-// One CTA per vocabulary row: deterministic, no atomics.
+// One CTA per vocabulary row: warp 0 builds the ordered list of matching rows (ballot compaction), then all threads
+// sum those rows.  Deterministic, no atomics.
 __global__ void embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict__ dE, long long ldde,
                                         int B, int L, int ed, float* __restrict__ demb) {
+  extern __shared__ int rows[];        // up to B*L matching rows
+  __shared__ int count;
   const int v = blockIdx.x;
+  const int total = B * L;
+  if (threadIdx.x < 32) {
+    int n = 0;
+    for (int r0 = 0; r0 < total; r0 += 32) {
+      const int row = r0 + threadIdx.x;
+      bool hit = false;
+      if (row < total) {
+        const int l = row / B, b = row % B;
+        hit = (q[(size_t)b * L + l] == v);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) rows[n + __popc(m & ((1u << threadIdx.x) - 1))] = row;
+      n += __popc(m);
+    }
+    if (threadIdx.x == 0) count = n;
+  }
+  __syncthreads();
+  const int n = count;
   for (int c = threadIdx.x; c < ed; c += blockDim.x) {
     float s = 0.f;
-    for (int row = 0; row < B * L; ++row) {
-      const int l = row / B, b = row % B;
-      if (q[(size_t)b * L + l] == v) s += dE[(size_t)row * ldde + c];
-    }
+    for (int k = 0; k < n; ++k) s += dE[(size_t)rows[k] * ldde + c];
     demb[(size_t)v * ed + c] = s;
   }
 }
@@ -192,7 +210,7 @@ int ek_embed_gather_launch(int is_bf16, const long long* q, const float* emb, co
 }
 int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ldde, int B, int L, int ed, int V,
                                float* demb, cudaStream_t st) {
-  embed_gather_bwd_kernel<<<V, 128, 0, st>>>(q, dE, ldde, B, L, ed, demb);
+  embed_gather_bwd_kernel<<<V, 128, (size_t)B * L * sizeof(int), st>>>(q, dE, ldde, B, L, ed, demb);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

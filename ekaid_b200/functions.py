@@ -316,8 +316,9 @@ class RelationFn(torch.autograd.Function):
         bswc, bqkzc, boutc = _f32c(bsw), _f32c(bqkz), _f32c(bout)
         flags = torch.empty(M, dtype=torch.uint8, device=dev)
         call("row_zero_flags", X.data_ptr(), M, D, flags.data_ptr())
-        # question half of self_weights, once per sample (fp32 SIMT GEMM, M = B rows)
-        qpart = gemm_f32out(qv, Wsw32[:, D:], B, D, qv.shape[1], bias=bswc)
+        # question half of self_weights, once per sample (M = B rows)
+        qvT = to_T(pc, qv)
+        qpart = gemm_f32out(qvT, WswT[:, D:], B, D, qv.shape[1], bias=bswc)
         Sf, _ = gemm_T(pc, XT, WswT[:, :D], M, D, D, rowb=qpart, rowb_div=N, rowb_mod=B, rowflag=flags,
                        rowb_alt=bswc)
         W = (2 + H) * D
@@ -354,7 +355,7 @@ class RelationFn(torch.autograd.Function):
              G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr(),
              info={"bytes": G * (N * H * Kn * 4 + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
         ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
-        ctx.saved = (XT, qv, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask)
+        ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append(mask.bool().cpu())
         if XnT is not None:
@@ -367,7 +368,7 @@ class RelationFn(torch.autograd.Function):
     def backward(ctx, dXn, _dXnT, _dP):
         pc, kind = ctx.pc, ctx.kind
         G, B, N, Kn, D, H = ctx.dims
-        XT, qv, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask = ctx.saved
+        XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask = ctx.saved
         dev = P.device
         M = G * N
         W = (2 + H) * D
@@ -413,9 +414,10 @@ class RelationFn(torch.autograd.Function):
         dbsw = colsum(dSf, M, D)
         dqpart = torch.empty(B, D, dtype=torch.float32, device=dev)
         call("group_rowsum", pc.f, dSf.data_ptr(), dSf.stride(0), N, B, G // B, D, flags.data_ptr(), dqpart.data_ptr())
-        Dq = qv.shape[1]
-        gemm(dqpart, qv, D, Dq, B, transA=1, transB=1, C=dWsw[:, D:])       # fp32 SIMT (K = B)
-        dqv = gemm_f32out(dqpart, Wsw32[:, D:], B, Dq, D, transB=1)
+        Dq = qvT.shape[1]
+        dqpT = to_T(pc, dqpart)
+        gemm(dqpT, qvT, D, Dq, B, transA=1, transB=1, C=dWsw[:, D:], splits=1)   # K = B
+        dqv = gemm_f32out(dqpT, WswT[:, D:], B, Dq, D, transB=1)
         dX = torch.empty(M, D, dtype=torch.float32, device=dev)
         gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
         return (None, None, None, dX, None, dqv, dWsw, dbsw, dWqkz, dbqkz, dbout, dp0, dp1, None, None, None)

@@ -27,8 +27,9 @@ class FlatAdam:
     def __init__(self, params: Sequence[torch.nn.Parameter], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         params = [p for p in params]
         dev = params[0].device
-        n = sum(p.numel() for p in params)
-        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        al = 64                                   # every parameter starts on a 256-byte boundary (vector loads, TMA)
+        n = sum((p.numel() + al - 1) // al * al for p in params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -39,7 +40,7 @@ class FlatAdam:
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             p.grad = self.grad[off:off + k].view(p.shape)
-            off += k
+            off += (k + al - 1) // al * al
         self.params = params
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
 
