@@ -546,9 +546,19 @@ static int edge_softmax_fwd_t(const T* QKZ, long long ld, int D, const float* co
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
+int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float* cond, const float* lbias,
+                              const float* gbias, int G, int N, int Kn, int H, float* P, cudaStream_t st);
+int ek_softmax_bwd_mma_launch(const float* P, const float* dPpart, int nslices, const bf16* QKZ, long long ld, int D,
+                              const float* cond, int G, int N, int Kn, int H, bf16* dQKZ, float* dlbias_part,
+                              float* dgbias, cudaStream_t st);
+
 int ek_edge_softmax_fwd_launch(int is_bf16, const void* QKZ, long long ld, int D, const float* cond,
                                const float* lbias, const float* gbias, int G, int N, int Kn, int H, float* P,
                                cudaStream_t st) {
+  if (is_bf16) {
+    const int rc = ek_softmax_fwd_mma_launch((const bf16*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, st);
+    if (rc != EK_ERR_UNSUPPORTED) return rc;
+  }
   return is_bf16 ? edge_softmax_fwd_t<bf16>((const bf16*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, st)
                  : edge_softmax_fwd_t<float>((const float*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, st);
 }
@@ -641,6 +651,11 @@ static int edge_softmax_bwd_t(const float* P, const float* dPpart, int nslices, 
 int ek_edge_softmax_bwd_launch(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ,
                                long long ld, int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ,
                                float* dlbias_part, float* dgbias, cudaStream_t st) {
+  if (is_bf16) {
+    const int rc = ek_softmax_bwd_mma_launch(P, dPpart, nslices, (const bf16*)QKZ, ld, D, cond, G, N, Kn, H,
+                                             (bf16*)dQKZ, dlbias_part, dgbias, st);
+    if (rc != EK_ERR_UNSUPPORTED) return rc;
+  }
   return is_bf16 ? edge_softmax_bwd_t<bf16>(P, dPpart, nslices, (const bf16*)QKZ, ld, D, cond, G, N, Kn, H,
                                             (bf16*)dQKZ, dlbias_part, dgbias, st)
                  : edge_softmax_bwd_t<float>(P, dPpart, nslices, (const float*)QKZ, ld, D, cond, G, N, Kn, H,

@@ -281,6 +281,230 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// scores + mask/bias + softmax on tensor cores: one CTA per (image, head), one warp per 16 query rows
+// ------------------------------------------------------------------------------------------------
+constexpr float NEG_MASK_MMA = -9e15f;
+
+template <int NT>   // 8-column key tiles held per warp: 8 (Kn <= 64) or 16 (Kn <= 128)
+__global__ void __launch_bounds__(256)
+softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond,
+                       const float* __restrict__ lbias, const float* __restrict__ gbias, int N, int Kn, int H,
+                       float* __restrict__ P, int MR) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int g = blockIdx.x, h = blockIdx.y;
+  const int dh = D / H;
+  const int DS = dh + 8;                         // row pitch (elements); dh % 16 == 0 -> conflict-free ldmatrix
+  constexpr int KR = NT * 8;
+  bf16* Qs = (bf16*)smraw;                       // [MR][DS]
+  bf16* Ks = Qs + (size_t)MR * DS;               // [KR][DS]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunks = dh / 8;
+  for (int e = tid; e < (MR + KR) * chunks; e += 256) {
+    const int r = e / chunks, ch = e % chunks;
+    const bool isq = r < MR;
+    const int row = isq ? r : r - MR;
+    bf16* dst = (isq ? Qs + row * DS : Ks + row * DS) + ch * 8;
+    const bool ok = isq ? (row < N) : (row < Kn);
+    if (ok) cp_async16(dst, QKZ + ((size_t)g * N + row) * ld + (isq ? 0 : D) + h * dh + ch * 8);
+    else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int mt = warp;
+  if (mt * 16 >= N) return;
+  float acc[NT][4];
+#pragma unroll
+  for (int a = 0; a < NT; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  for (int kt = 0; kt < dh / 16; ++kt) {
+    uint32_t af[4];
+    ldsm_x4(af, Qs + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DS + kt * 16 + (lane >> 4) * 8);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t bfr[4];
+      // B(k = d, n = j) = K[j][d]: stored [n][k] -> plain ldmatrix
+      ldsm_x4(bfr, Ks + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * DS + kt * 16 + ((lane >> 3) & 1) * 8);
+      mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
+      mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
+    }
+  }
+  const float scale = 1.0f / sqrtf((float)dh);
+  const size_t total = (size_t)N * Kn;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int i = mt * 16 + (lane >> 2) + hh * 8;
+    const bool rok = i < N;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = nt * 8 + 2 * (lane & 3) + c;
+        float sv = -INFINITY;
+        if (rok && j < Kn) {
+          sv = scale * acc[nt][2 * hh + c];
+          const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
+          if (gbias) sv += gbias[ge * H + h];
+          if (cond) sv = (cond[ge] > 0.f) ? sv : NEG_MASK_MMA;
+          if (lbias) sv += lbias[ge];
+        }
+        acc[nt][2 * hh + c] = sv;
+        mx = fmaxf(mx, sv);
+      }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int j = nt * 8 + 2 * (lane & 3) + c;
+        const float ev = (rok && j < Kn) ? expf(acc[nt][2 * hh + c] - mx) : 0.f;
+        acc[nt][2 * hh + c] = ev;
+        sum += ev;
+      }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    if (rok) {
+      const float inv = 1.f / sum;
+      float* Pr = P + (((size_t)g * N + i) * H + h) * Kn;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = nt * 8 + 2 * (lane & 3) + c;
+          if (j < Kn) Pr[j] = acc[nt][2 * hh + c] * inv;
+        }
+    }
+  }
+}
+
+// backward of scores/softmax on tensor cores: one CTA per (image, head).
+//   ds = P * (dP - sum_j P dP), dP = sum_slices dPpart;  outputs dgbias / dlbias_part;  ds_m = cond > 0 ? ds : 0
+//   dQ = scale * ds_m K,  dK = scale * ds_m^T Q      (ds_m kept as bf16 hi + lo)
+template <int MR>   // padded rows for both queries and keys: 64 or 128
+__global__ void __launch_bounds__(256)
+softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dPpart, int nslices,
+                       const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond, int N, int Kn,
+                       int H, bf16* __restrict__ dQKZ, float* __restrict__ dlbias_part, float* __restrict__ dgbias) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int g = blockIdx.x, h = blockIdx.y, G = gridDim.x;
+  const int dh = D / H, HK = H * Kn;
+  const int DS = dh + 8;
+  constexpr int SS = MR + 8;
+  bf16* Qs = (bf16*)smraw;                       // [MR][DS]
+  bf16* Ks = Qs + (size_t)MR * DS;               // [MR][DS]
+  bf16* Shi = Ks + (size_t)MR * DS;              // [MR][SS]  ds_m (i, j)
+  bf16* Slo = Shi + (size_t)MR * SS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunks = dh / 8;
+  for (int e = tid; e < 2 * MR * chunks; e += 256) {
+    const int r = e / chunks, ch = e % chunks;
+    const bool isq = r < MR;
+    const int row = isq ? r : r - MR;
+    bf16* dst = (isq ? Qs + row * DS : Ks + row * DS) + ch * 8;
+    const bool ok = isq ? (row < N) : (row < Kn);
+    if (ok) cp_async16(dst, QKZ + ((size_t)g * N + row) * ld + (isq ? 0 : D) + h * dh + ch * 8);
+    else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+  }
+  const size_t total = (size_t)N * Kn;
+  for (int i = warp; i < MR; i += 8) {
+    if (i < N) {
+      const float* Pr = P + (((size_t)g * N + i) * H + h) * Kn;
+      float dot = 0.f;
+      float dpv[(MR + 31) / 32];
+#pragma unroll
+      for (int r = 0; r < (MR + 31) / 32; ++r) {
+        const int j = lane + 32 * r;
+        float dp = 0.f;
+        if (j < Kn) {
+          for (int sidx = 0; sidx < nslices; ++sidx) dp += dPpart[(((size_t)sidx * G + g) * N + i) * HK + h * Kn + j];
+          dot = fmaf(Pr[j], dp, dot);
+        }
+        dpv[r] = dp;
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int r = 0; r < (MR + 31) / 32; ++r) {
+        const int j = lane + 32 * r;
+        if (j < MR) {
+          float ds = 0.f;
+          if (j < Kn) {
+            ds = Pr[j] * (dpv[r] - dot);
+            const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
+            if (dgbias) dgbias[ge * H + h] = ds;
+            if (dlbias_part) dlbias_part[(size_t)h * G * total + ge] = ds;
+            if (cond && !(cond[ge] > 0.f)) ds = 0.f;
+          }
+          const bf16 hi = __float2bfloat16_rn(ds);
+          Shi[i * SS + j] = hi;
+          Slo[i * SS + j] = __float2bfloat16_rn(ds - __bfloat162float(hi));
+        }
+      }
+    } else {
+      for (int j = lane; j < MR; j += 32) { Shi[i * SS + j] = __float2bfloat16_rn(0.f); Slo[i * SS + j] = __float2bfloat16_rn(0.f); }
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const float scale = 1.0f / sqrtf((float)dh);
+  // items: (which: dQ/dK, 16-row tile, 128-column block of d); every item has MR/16 k-steps
+  const int nblk = dh / 128 + ((dh % 128) ? 1 : 0);
+  const int per = (MR / 16) * nblk;
+  for (int item = warp; item < 2 * per; item += 8) {
+    const int which = item / per;
+    const int mt = (item % per) / nblk, nb = (item % per) % nblk;
+    float acc[16][4];
+#pragma unroll
+    for (int a = 0; a < 16; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    const bf16* Bs = which == 0 ? Ks : Qs;       // dQ = ds K ; dK = ds^T Q  -> B(k, n = d) stored [k][n]: trans
+#pragma unroll
+    for (int kt = 0; kt < MR / 16; ++kt) {
+      uint32_t ah[4], al[4];
+      if (which == 0) {
+        const int off = (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * SS + kt * 16 + (lane >> 4) * 8;
+        ldsm_x4(ah, Shi + off);
+        ldsm_x4(al, Slo + off);
+      } else {
+        const int off = (kt * 16 + (lane >> 4) * 8 + (lane & 7)) * SS + mt * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4_t(ah, Shi + off);
+        ldsm_x4_t(al, Slo + off);
+      }
+#pragma unroll
+      for (int np = 0; np < 8; ++np) {
+        const int ncol = nb * 128 + np * 16;
+        if (ncol < dh) {
+          uint32_t bfr[4];
+          ldsm_x4_t(bfr, Bs + (kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * DS + ncol + (lane >> 4) * 8);
+          mma_bf16_16816(acc[2 * np], ah, bfr[0], bfr[1]);
+          mma_bf16_16816(acc[2 * np], al, bfr[0], bfr[1]);
+          mma_bf16_16816(acc[2 * np + 1], ah, bfr[2], bfr[3]);
+          mma_bf16_16816(acc[2 * np + 1], al, bfr[2], bfr[3]);
+        }
+      }
+    }
+    // rows of dK beyond Kn are zero by construction (ds columns j >= Kn are zero), rows >= N are not written
+    bf16* dst = dQKZ + (size_t)g * N * ld + (which == 0 ? 0 : D) + h * dh;
+#pragma unroll
+    for (int nt = 0; nt < 16; ++nt) {
+      const int d = nb * 128 + nt * 8 + 2 * (lane & 3);
+      if (d >= dh) continue;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = mt * 16 + (lane >> 2) + hh * 8;
+        if (r < N)
+          *(__nv_bfloat162*)(dst + (size_t)r * ld + d) =
+              __floats2bfloat162_rn(scale * acc[nt][2 * hh], scale * acc[nt][2 * hh + 1]);
+      }
+    }
+  }
+}
+
 template <typename K>
 int set_smem(K kern, size_t smem, size_t& configured, const char* what) {
   if (smem > 48 * 1024 && smem > configured) {
@@ -336,6 +560,53 @@ int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* 
     int rc = set_smem(agg_bwd_mma_kernel<128>, smem, c128, "agg_bwd_mma");
     if (rc) return rc;
     agg_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk);
+  }
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float* cond, const float* lbias,
+                              const float* gbias, int G, int N, int Kn, int H, float* P, cudaStream_t st) {
+  if ((D % H) || ((D / H) % 16) || (ld % 8) || ((uintptr_t)QKZ & 15) || N > 128 || Kn > 128) return EK_ERR_UNSUPPORTED;
+  const int dh = D / H;
+  const int MR = ((N + 15) / 16) * 16;
+  const int NT = Kn <= 64 ? 8 : 16;
+  const size_t smem = (size_t)(MR + NT * 8) * (dh + 8) * sizeof(bf16);
+  static size_t c8 = 0, c16 = 0;
+  dim3 grid(G, H);
+  if (NT == 8) {
+    int rc = set_smem(softmax_fwd_mma_kernel<8>, smem, c8, "softmax_fwd_mma");
+    if (rc) return rc;
+    softmax_fwd_mma_kernel<8><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR);
+  } else {
+    int rc = set_smem(softmax_fwd_mma_kernel<16>, smem, c16, "softmax_fwd_mma");
+    if (rc) return rc;
+    softmax_fwd_mma_kernel<16><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR);
+  }
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_softmax_bwd_mma_launch(const float* P, const float* dPpart, int nslices, const bf16* QKZ, long long ld, int D,
+                              const float* cond, int G, int N, int Kn, int H, bf16* dQKZ, float* dlbias_part,
+                              float* dgbias, cudaStream_t st) {
+  if ((D % H) || ((D / H) % 16) || (ld % 8) || ((uintptr_t)QKZ & 15) || ((uintptr_t)dQKZ & 3) || N > 128)
+    return EK_ERR_UNSUPPORTED;
+  const int dh = D / H;
+  const int MR = N <= 64 ? 64 : 128;
+  const size_t smem = ((size_t)2 * MR * (dh + 8) + (size_t)2 * MR * (MR + 8)) * sizeof(bf16);
+  static size_t c64 = 0, c128 = 0;
+  dim3 grid(G, H);
+  if (MR == 64) {
+    int rc = set_smem(softmax_bwd_mma_kernel<64>, smem, c64, "softmax_bwd_mma");
+    if (rc) return rc;
+    softmax_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ,
+                                                         dlbias_part, dgbias);
+  } else {
+    int rc = set_smem(softmax_bwd_mma_kernel<128>, smem, c128, "softmax_bwd_mma");
+    if (rc) return rc;
+    softmax_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ,
+                                                          dlbias_part, dgbias);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;
