@@ -17,7 +17,6 @@ import contextlib
 import io
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -44,6 +43,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", default="all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     return ap.parse_args()
 
@@ -57,55 +57,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled in-process through NVML
+    every 50 ms (an external `nvidia-smi -lms` loop was measured to slow a launch-heavy step several-fold)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.mask = 0
+        self.smmax = None
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except ValueError:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:           # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:            # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.05)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.ok:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smmax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smmax = float(f[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag.set()
+        self.t.join(timeout=2)
+        sm = sorted(self.samples)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": smmax, "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted(n for bit, n in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": med, "sm_max_mhz": self.smmax, "reasons": reasons, "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -192,7 +196,7 @@ def main():
     from ekaid_b200 import lib
     from ekaid_b200.config import WORD_TO_IDX, default_cfg
     from ekaid_b200.modules import ChangeDetector
-    from ekaid_b200.step import GraphFusionStep, process_batch
+    from ekaid_b200.step import GraphFusionStep, expand_adjacency, select_fields, to_device
     from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
 
     torch.cuda.set_device(local)
@@ -216,21 +220,31 @@ def main():
     host = []
     for i in range(4):
         b = synthetic_batch(B, N, seed=1234 + 17 * rank + i)
-        host.append(tuple(t.pin_memory() if torch.is_tensor(t) else t for t in b))
-    resident = [process_batch(hb, cfg, dev) for hb in host]
+        host.append(tuple(t.contiguous().pin_memory() for t in select_fields(b)))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
     torch.cuda.synchronize()
+    train = args.mode == "train"
+
+    def eager(raw):
+        inputs = expand_adjacency(raw, cfg)
+        if train:
+            return step.train_step(inputs, raw[9], raw[10].float())
+        return step.infer_step(inputs)[5].sum()
+
+    use_graph = not args.no_graph
+    if use_graph:
+        step.capture(resident[0], train=train)
 
     def one(i, e2e=False):
-        if e2e:
-            inputs, labels, masks = process_batch(host[i % 4], cfg, dev)
+        src = host[i % 4] if e2e else resident[i % 4]
+        if use_graph:
+            out = step.replay(src)
+            out = out if train else out[5]
         else:
-            inputs, labels, masks = resident[i % 4]
-        if args.mode == "train":
-            out = step.train_step(inputs, labels, masks)
-        else:
-            out = step.infer_step(inputs)[5].sum()
+            raw = tuple(t.to(dev, non_blocking=True) for t in src) if e2e else src
+            out = eager(raw)
         if e2e:
-            return float(out)          # device -> host read of the step's result
+            return float(out.sum())    # device -> host read of the step's result
         return out
 
     def barrier():
@@ -273,15 +287,18 @@ def main():
         one(i, True)
     ms_e2e = timed(args.steps, True) / args.steps
     e2e_val = B * world / (ms_e2e * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for j, t in enumerate(host[0]) if torch.is_tensor(t) and j not in (3, 5))
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = 4
 
     # per-kernel timing pass with CUDA events on the launching stream (same step, same inputs)
+    # (eager launches: a graph replay cannot be bracketed per kernel; same kernels, same shapes)
+    for i in range(2):
+        eager(resident[i % 4])
     lib.PROFILE = []
     torch.cuda.synchronize()
     nprof = min(args.steps, 5)
     for i in range(nprof):
-        one(i)
+        eager(resident[i % 4])
     torch.cuda.synchronize()
     prof, lib.PROFILE = lib.PROFILE, None
     agg = {}
@@ -322,7 +339,7 @@ def main():
             "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "roofline": roof, "kernel_time_share_pct": breakdown}
+            "gpu_launches": launches, "cuda_graph": use_graph, "roofline": roof, "kernel_time_share_pct": breakdown}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

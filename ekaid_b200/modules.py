@@ -371,6 +371,24 @@ class ChangeDetector(nn.Module):
             raise NotImplementedError("feature_mode 'mode0' (ResNet-101 on raw images) is outside the hot path")
         self.precision = _default_precision()
 
+    def live_parameters(self):
+        """Parameters that can receive a gradient in setting='mode2'.  The rest exist only so reference checkpoints
+        load (quirk Q11): SSRE.*, direction-0 attention layers (Q2), the never-called grouped conv linear_out_ (Q3)
+        and the frozen embedding table.  torch.optim.Adam skips them too (their .grad stays None)."""
+        out = []
+        for name, p in self.named_parameters():
+            if not p.requires_grad or name.startswith("SSRE."):
+                continue
+            if ".linear_out_." in name:
+                continue
+            parts = name.split(".")
+            if "neighbor_net" in parts:
+                owner = self.get_submodule(".".join(parts[:parts.index("neighbor_net")]))
+                if int(parts[parts.index("neighbor_net") + 1]) != owner.dir_num - 1:
+                    continue
+            out.append(p)
+        return out
+
     def set_precision(self, precision: str) -> "ChangeDetector":
         PC(precision)
         for m in self.modules():

@@ -53,25 +53,32 @@ class FlatAdam:
                  self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.pow_state.data_ptr())
 
 
-def process_batch(batch, cfg, device):
-    """train_mimic.py:206-227: move the loader's 13-tuple to the device and expand the four integer adjacency
-    matrices to one-hot planes.  Boxes stay where they are (the reference never moves them)."""
+def select_fields(batch):
+    """The 11 tensors of the loader's 13-tuple that the step consumes (train_mimic.py:206-218), in step order:
+    (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question, labels, masks); adjacency still as integer
+    label matrices [B,S,S]."""
     (d_feats, sc_feats, labels, sc_pos_labels, masks, pair_index, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb,
      question) = batch
-    nb = True
-    d_feats, sc_feats = d_feats.to(device, non_blocking=nb), sc_feats.to(device, non_blocking=nb)
-    question = question.to(device, non_blocking=nb)
-    labels = labels.squeeze(1).to(device, non_blocking=nb)
-    masks = masks.squeeze(1).float().to(device, non_blocking=nb)
-    n = d_feats.shape[1]
+    return (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question, labels.squeeze(1), masks.squeeze(1))
+
+
+def to_device(batch, device):
+    """Host 13-tuple -> device tensors (pinned host memory makes the copies asynchronous)."""
+    return tuple(t.to(device, non_blocking=True) for t in select_fields(batch))
+
+
+def expand_adjacency(raw, cfg):
+    """train_mimic.py:223-227 (process_matrix x4), one kernel per matrix.  -> the 9 ChangeDetector inputs."""
     cd = cfg.model.change_detector
-    d_adj = onehot_adj(d_adj.to(device, non_blocking=nb), n, cd.spa_label_num)
-    q_adj = onehot_adj(q_adj.to(device, non_blocking=nb), n, cd.spa_label_num)
-    d_sem = onehot_adj(d_sem.to(device, non_blocking=nb), n, cd.sem_label_num)
-    q_sem = onehot_adj(q_sem.to(device, non_blocking=nb), n, cd.sem_label_num)
-    d_bb = d_bb.to(device, non_blocking=nb)
-    q_bb = q_bb.to(device, non_blocking=nb)
-    return (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question), labels, masks
+    n = raw[0].shape[1]
+    return (raw[0], raw[1], onehot_adj(raw[2], n, cd.spa_label_num), onehot_adj(raw[3], n, cd.spa_label_num),
+            onehot_adj(raw[4], n, cd.sem_label_num), onehot_adj(raw[5], n, cd.sem_label_num), raw[6], raw[7], raw[8])
+
+
+def process_batch(batch, cfg, device):
+    """to_device + expand_adjacency.  Returns (inputs, labels, masks)."""
+    raw = to_device(batch, device)
+    return expand_adjacency(raw, cfg), raw[9], raw[10].float()
 
 
 class GraphFusionStep:
@@ -84,8 +91,9 @@ class GraphFusionStep:
         self.graph = graph
         self.decoder_loss = decoder_loss
         self.pg = process_group
-        self.opt = FlatAdam(list(change_detector.parameters()), lr=lr)
+        self.opt = FlatAdam(change_detector.live_parameters(), lr=lr)
         self._cot = None
+        self._graph = None
 
     def _surrogate(self, bef, aft, diff):
         # stands in for d(decoder NLL)/d(bef, aft, diff): fixed unit-scale cotangents
@@ -115,6 +123,42 @@ class GraphFusionStep:
             dist.all_reduce(self.opt.grad, op=dist.ReduceOp.AVG, group=self.pg)
         self.opt.step()
         return total.detach()
+
+    # -- CUDA-graph replay of the whole step ------------------------------------------------------------------
+    def capture(self, raw_example, train: bool = True, warmup: int = 3):
+        """Capture  process_matrix x4 -> forward -> backward -> [all-reduce] -> Adam  (or the inference forward) into
+        one CUDA graph.  `raw_example` fixes the shapes: the device tuple `to_device` returns.  The step is ~600 small
+        launches at batch 64; replaying a graph removes the Python/launch overhead between them."""
+        self._static = [t.clone() for t in raw_example]
+        self._train = train
+
+        def body():
+            inputs = expand_adjacency(self._static, self.cfg)
+            if train:
+                return self.train_step(inputs, self._static[9], self._static[10].float())
+            return self.infer_step(inputs)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = lib.LAUNCHES
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = body()
+        self.launches_per_replay = lib.LAUNCHES - before
+        return self
+
+    def replay(self, raw):
+        """Copy a new raw device (or pinned host) batch into the captured buffers and replay the step."""
+        for dst, src in zip(self._static, raw):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        lib.LAUNCHES += self.launches_per_replay
+        return self._static_out
 
     @torch.no_grad()
     def infer_step(self, inputs):
