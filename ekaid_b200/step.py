@@ -53,6 +53,25 @@ class FlatAdam:
                  self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.pow_state.data_ptr())
 
 
+def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Data-parallel gradient exchange: ONE all-reduce over the flat gradient buffer, mean over ranks
+    (NCCL: ReduceOp.AVG over NVLink; gloo, used by the CPU tests, has no AVG -> SUM then scale)."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(dist.get_world_size(group))
+    return flat
+
+
+def shard_batch(batch, rank: int, world: int):
+    """Contiguous shard of the loader's 13-tuple for one rank: no data-path collective."""
+    b = batch[0].shape[0]
+    per = b // world
+    return tuple(t[rank * per:(rank + 1) * per] for t in batch)
+
+
 def select_fields(batch):
     """The 11 tensors of the loader's 13-tuple that the step consumes (train_mimic.py:206-218), in step order:
     (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question, labels, masks); adjacency still as integer
@@ -119,8 +138,7 @@ class GraphFusionStep:
         total = self.loss(inputs, labels, masks)
         total.backward()
         if self.pg is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.opt.grad, op=dist.ReduceOp.AVG, group=self.pg)
+            allreduce_mean_(self.opt.grad, self.pg)
         self.opt.step()
         return total.detach()
 
