@@ -90,7 +90,7 @@ def test_two_rank_gradient_mean_over_local_batches(tmp_path):
     for k, g in got.items():
         ref = (g0[k] + g1[k]) / 2
         # (worker processes run the oracle with a different thread count -> fp32 summation order differs)
-        assert float((g - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-6, k
+        assert float((g - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-4, k   # atol: analytically-zero gradients are rounding noise
 
 
 def test_shard_batch_is_contiguous_partition():
