@@ -358,9 +358,20 @@ def main():
                                 "sample": "%d %s steps of the oracle port on %d image pairs x %d nodes, fp32 torch CPU, "
                                           "%.1f s" % (n, args.mode, bs, N, el)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # tear down: release the captured graph (it references NCCL kernels) before the communicator; a watchdog
+        # makes sure a stuck communicator teardown can never hold the GPUs after the result has been printed
+        def _bail():
+            time.sleep(20)
+            os._exit(0)
+        threading.Thread(target=_bail, daemon=True).start()
+        step._graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
