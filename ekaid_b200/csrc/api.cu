@@ -28,12 +28,17 @@ int ek_group_rowsum_launch(int, const void*, long long, int, int, int, int, cons
 int ek_combine_diff_fwd_launch(int, const float*, long long, int, int, float, float, float, float*, void*, cudaStream_t);
 int ek_combine_diff_bwd_launch(const float*, const float*, long long, int, int, float, float, float, float*,
                                cudaStream_t);
-int ek_gate_fwd_launch(int, const float*, long long, int, void*, void*, void*, cudaStream_t);
-int ek_gate_bwd_launch(int, const float*, const void*, const void*, long long, int, void*, cudaStream_t);
+int ek_gate_fwd_launch(int, const float*, long long, int, void*, void*, void*, EkDrop, EkDrop, cudaStream_t);
+int ek_gate_bwd_launch(int, const float*, const void*, const void*, long long, int, void*, EkDrop, EkDrop, cudaStream_t);
+int ek_build_vq_launch(int, const float*, const float*, const uint8_t*, long long, int, int, int, int, void*, EkDrop,
+                       cudaStream_t);
+int ek_drop_combine_launch(int, int, int, const void*, const void*, const void*, long long, EkDrop, EkDrop, EkDrop,
+                           long long, int, float*, long long, int, void*, long long, cudaStream_t);
+int ek_rng_advance_launch(unsigned long long*, cudaStream_t);
 int ek_att_pool_fwd_launch(const float*, long long, int, int, int, const float*, const float*, const float*, float*,
                            float*, cudaStream_t);
 int ek_att_pool_bwd_launch(int, const float*, const float*, const float*, const float*, const float*, const float*,
-                           long long, int, int, int, float*, void*, float*, cudaStream_t);
+                           long long, int, int, int, float*, void*, float*, float, cudaStream_t);
 int ek_onehot_adj_launch(const double*, int, int, int, int, float*, cudaStream_t);
 int ek_adam_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, const float*,
                    cudaStream_t);
@@ -42,16 +47,16 @@ int ek_adj_prep_fwd_launch(const float*, const float*, int, const float*, int, i
                            cudaStream_t);
 int ek_adj_prep_bwd_launch(const float*, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
 int ek_geom_bias_fwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
-                            int, float*, cudaStream_t);
+                            int, float*, EkDrop, cudaStream_t);
 int ek_geom_bias_bwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
-                            int, const float*, float*, cudaStream_t);
+                            int, const float*, float*, EkDrop, cudaStream_t);
 int ek_edge_softmax_fwd_launch(int, const void*, long long, int, const float*, const float*, const float*, int, int,
                                int, int, float*, cudaStream_t);
 int ek_edge_aggregate_fwd_launch(int, const float*, const void*, long long, int, const float*, const float*, int, int,
-                                 int, int, float*, void*, long long, uint8_t*, cudaStream_t);
+                                 int, int, float*, void*, long long, uint8_t*, EkDrop, cudaStream_t);
 int ek_edge_num_slices(int D);
 int ek_edge_aggregate_bwd_launch(int, const float*, const uint8_t*, const float*, const void*, long long, int, int, int,
-                                 int, int, void*, float*, float*, cudaStream_t);
+                                 int, int, void*, float*, float*, float, cudaStream_t);
 int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*, long long, int, const float*, int,
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
@@ -78,6 +83,10 @@ static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
   r.rowflag = e->rowflag;
   r.rowb_alt = e->rowb_alt;
   r.act = e->act;
+  r.drop.seed = (const unsigned long long*)e->drop_seed;
+  r.drop.site = e->drop_site;
+  r.drop.p = e->drop_p;
+  r.dropN = e->drop_n;
   r.C = e->C;
   r.ldc = e->ldc;
   r.Cb = (bf16*)e->Cb;
@@ -86,6 +95,13 @@ static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
 }
 
 #define ST ((cudaStream_t)stream)
+static EkDrop mk_drop(const uint64_t* seed, uint32_t site, float p) {
+  EkDrop d;
+  d.seed = (p > 0.f) ? (const unsigned long long*)seed : nullptr;
+  d.site = site;
+  d.p = p;
+  return d;
+}
 
 extern "C" {
 
@@ -151,13 +167,15 @@ int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const 
   return ek_adj_prep_bwd_launch(adj0, adj1, g_split, dlbias_part, nparts, G, N, Kn, L, dw_part, ST);
 }
 int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
-                        const float* dim_t, int G, int N, int Kn, int H, float* gbias, void* stream) {
-  return ek_geom_bias_fwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, gbias, ST);
+                        const float* dim_t, int G, int N, int Kn, int H, float* gbias, const uint64_t* seed,
+                        uint32_t site, float p, void* stream) {
+  return ek_geom_bias_fwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, gbias, mk_drop(seed, site, p), ST);
 }
 int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
-                        void* stream) {
-  return ek_geom_bias_bwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, dgbias, part, ST);
+                        const uint64_t* seed, uint32_t site, float p, void* stream) {
+  return ek_geom_bias_bwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, dgbias, part, mk_drop(seed, site, p),
+                                 ST);
 }
 int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
                            const float* gbias, int G, int N, int Kn, int H, float* P, void* stream) {
@@ -166,14 +184,15 @@ int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, cons
 }
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
-                             uint8_t* mask, void* stream) {
-  return ek_edge_aggregate_fwd_launch(is_bf16, P, QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, XoutT, ldt, mask, ST);
+                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, void* stream) {
+  return ek_edge_aggregate_fwd_launch(is_bf16, P, QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, XoutT, ldt, mask,
+                                      mk_drop(seed, site, p), ST);
 }
 int ekaid_edge_num_slices(int D) { return ek_edge_num_slices(D); }
 int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                              int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
-                             void* stream) {
-  return ek_edge_aggregate_bwd_launch(is_bf16, dXout, mask, P, QKZ, ld, D, G, N, Kn, H, dQKZ, dOut, dPpart, ST);
+                             float gscale, void* stream) {
+  return ek_edge_aggregate_bwd_launch(is_bf16, dXout, mask, P, QKZ, ld, D, G, N, Kn, H, dQKZ, dOut, dPpart, gscale, ST);
 }
 int ekaid_edge_softmax_bwd(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ, int64_t ld,
                            int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ, float* dlbias_part,
@@ -189,12 +208,29 @@ int ekaid_combine_diff_bwd(const float* dXc, const float* dCAT, int64_t BN, int 
                            float c3, float* dX3, void* stream) {
   return ek_combine_diff_bwd_launch(dXc, dCAT, BN, D, mode, c1, c2, c3, dX3, ST);
 }
-int ekaid_gate_fwd(int is_bf16, const float* pre, int64_t M, int D, void* ctx, void* gate, void* CAT, void* stream) {
-  return ek_gate_fwd_launch(is_bf16, pre, M, D, ctx, gate, CAT, ST);
+int ekaid_gate_fwd(int is_bf16, const float* pre, int64_t M, int D, void* ctx, void* gate, void* CAT,
+                   const uint64_t* seed, uint32_t site_ctx, uint32_t site_gate, float p, void* stream) {
+  return ek_gate_fwd_launch(is_bf16, pre, M, D, ctx, gate, CAT, mk_drop(seed, site_ctx, p), mk_drop(seed, site_gate, p),
+                            ST);
 }
 int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* gate, int64_t M, int D, void* dpre,
-                   void* stream) {
-  return ek_gate_bwd_launch(is_bf16, dCAT, ctx, gate, M, D, dpre, ST);
+                   const uint64_t* seed, uint32_t site_ctx, uint32_t site_gate, float p, void* stream) {
+  return ek_gate_bwd_launch(is_bf16, dCAT, ctx, gate, M, D, dpre, mk_drop(seed, site_ctx, p),
+                            mk_drop(seed, site_gate, p), ST);
+}
+int ekaid_rng_advance(uint64_t* seed, void* stream) { return ek_rng_advance_launch((unsigned long long*)seed, ST); }
+int ekaid_build_vq(int is_bf16, const float* X, const float* qv, const uint8_t* flags, int64_t M, int N, int B, int D,
+                   int Dq, void* VQ, const uint64_t* seed, uint32_t site, float p, void* stream) {
+  return ek_build_vq_launch(is_bf16, X, qv, flags, M, N, B, D, Dq, VQ, mk_drop(seed, site, p), ST);
+}
+int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
+                       int64_t ldi, const uint64_t* seed, uint32_t site0, float p0, uint32_t site1, float p1,
+                       uint32_t site2, float p2, int64_t M, int C, float* outf, int64_t ldf, int accumulate,
+                       void* outT, int64_t ldo, void* stream) {
+  EK_REQUIRE(nin >= 1 && nin <= 3 && (outf || outT), EK_ERR_SHAPE, "drop_combine: nin=%d", nin);
+  return ek_drop_combine_launch(in_bf16, out_bf16, nin, in0, in1, in2, ldi, mk_drop(seed, site0, p0),
+                                mk_drop(seed, site1, p1), mk_drop(seed, site2, p2), M, C, outf, ldf, accumulate, outT,
+                                ldo, ST);
 }
 int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const float* w, const float* b,
                        const float* Xc, float* att, float* attended, void* stream) {
@@ -203,8 +239,8 @@ int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const f
 }
 int ekaid_att_pool_bwd(int is_bf16, const float* dA, const float* dattw, const float* att, const float* Xc,
                        const float* E, const float* w, int64_t M, int N, int D, int dim, float* dXc, void* dE,
-                       float* dpre, void* stream) {
-  return ek_att_pool_bwd_launch(is_bf16, dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, dE, dpre, ST);
+                       float* dpre, float escale, void* stream) {
+  return ek_att_pool_bwd_launch(is_bf16, dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, dE, dpre, escale, ST);
 }
 int ekaid_embed_gather(int is_bf16, const int64_t* q, const float* emb, const float* emb2, int B, int L, int ed,
                        void* E, void* stream) {

@@ -72,3 +72,25 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Counter-based dropout RNG (splitmix64 finaliser): the mask of element `idx` at dropout site `site` for the step
+// whose seed lives in device memory (CUDA-graph safe) -- regenerated, never stored, identical in forward and backward.
+struct EkDrop {
+  const unsigned long long* seed;   // device pointer, nullptr = dropout off
+  unsigned int site;
+  float p;
+};
+__device__ __forceinline__ unsigned int ek_rand32(unsigned long long seed, unsigned int site, unsigned long long idx) {
+  unsigned long long z = seed + (unsigned long long)site * 0x9E3779B97F4A7C15ull + idx * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned int)(z >> 32);
+}
+// multiplier of element idx: 0 (dropped) or 1/(1-p) (kept); 1 when dropout is off
+__device__ __forceinline__ float ek_drop_mult(const EkDrop& d, unsigned long long seedv, unsigned long long idx) {
+  if (d.seed == nullptr || d.p <= 0.f) return 1.f;
+  const unsigned int thr = (unsigned int)(d.p * 4294967296.0f);
+  return ek_rand32(seedv, d.site, idx) >= thr ? 1.f / (1.f - d.p) : 0.f;
+}
+__device__ __forceinline__ unsigned long long ek_seed(const EkDrop& d) { return d.seed ? *d.seed : 0ull; }

@@ -87,7 +87,8 @@ __device__ __forceinline__ void pos_feats(const double* __restrict__ bb, int r, 
 // Computes f[h] = W[h,:] . emb + b[h] for h < H (H <= 8), optionally returns emb.
 template <int MAXH>
 __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __restrict__ Wp, const float* __restrict__ bp,
-                                            int H, const float* __restrict__ dim_t, float f[MAXH], float* emb_out) {
+                                            int H, const float* __restrict__ dim_t, float f[MAXH], float* emb_out,
+                                            const EkDrop& dr, unsigned long long seedv, unsigned long long pair_idx) {
 #pragma unroll
   for (int h = 0; h < MAXH; ++h) f[h] = (h < H) ? bp[h] : 0.f;
 #pragma unroll
@@ -97,7 +98,10 @@ __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __re
       const double a = (100.0 * g[q]) / (double)dim_t[t];
       double sv, cv;
       sincos(a, &sv, &cv);
-      const float s = (float)sv, c = (float)cv;      // reference casts the fp64 embedding to fp32 (graph_att_layer.py:115)
+      // reference casts the fp64 embedding to fp32 (graph_att_layer.py:115); train mode: Dropout(0.2) on the
+      // 64-d embedding before pair_pos_fc1 (fc.py:25-32), element index pair*64 + k
+      const float s = (float)sv * ek_drop_mult(dr, seedv, pair_idx * 64 + q * 16 + t);
+      const float c = (float)cv * ek_drop_mult(dr, seedv, pair_idx * 64 + q * 16 + 8 + t);
       if (emb_out) { emb_out[q * 16 + t] = s; emb_out[q * 16 + 8 + t] = c; }
 #pragma unroll
       for (int h = 0; h < MAXH; ++h)
@@ -110,7 +114,7 @@ __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __re
 __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
                                      const float* __restrict__ Wp, const float* __restrict__ bp,
                                      const float* __restrict__ dim_t, int N, int Kn, int H,
-                                     float* __restrict__ gbias) {
+                                     float* __restrict__ gbias, EkDrop dr) {
   extern __shared__ float sW[];      // H*64 + H, then 8 wave lengths
   float* sDim = sW + H * 65;
   for (int e = threadIdx.x; e < H * 64; e += blockDim.x) sW[e] = Wp[e];
@@ -124,7 +128,7 @@ __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const doubl
     double gq[4];
     pos_feats(bb, r, c, gq);
     float f[8];
-    pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, nullptr);
+    pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, nullptr, dr, ek_seed(dr), (unsigned long long)g * N * Kn + e);
     for (int h = 0; h < H; ++h) {
       const float v = fmaxf(fmaxf(f[h], 0.f), 1e-6f);
       gbias[((size_t)g * N * Kn + e) * H + h] = logf(v);
@@ -139,7 +143,7 @@ constexpr int GB_TILE = 128;
 __global__ void __launch_bounds__(GB_TILE)
 geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
                      const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ dim_t, int N,
-                     int Kn, int H, const float* __restrict__ dgbias, float* __restrict__ part) {
+                     int Kn, int H, const float* __restrict__ dgbias, float* __restrict__ part, EkDrop dr) {
   extern __shared__ float sm[];      // weights H*65 | 8 wave lengths | emb [GB_TILE][65] | df [GB_TILE][8]
   float* sW = sm;
   float* sDim = sm + H * 65;
@@ -166,7 +170,7 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
       double gq[4];
       pos_feats(bb, r, c, gq);
       float f[8];
-      pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, emb);
+      pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, emb, dr, ek_seed(dr), (unsigned long long)g * total + e);
       for (int h = 0; h < H; ++h)
         df[h] = (f[h] > 1e-6f) ? dgbias[((size_t)g * total + e) * H + h] / f[h] : 0.f;
     } else {
@@ -297,8 +301,9 @@ __global__ void __launch_bounds__(256)
 edge_aggregate_fwd_kernel(const float* __restrict__ P, const T* __restrict__ QKZ, long long ld, int D,
                           const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                           float* __restrict__ Xout, T* __restrict__ XoutT, long long ldt,
-                          uint8_t* __restrict__ mask) {
+                          uint8_t* __restrict__ mask, EkDrop dr) {
   extern __shared__ float smf[];
+  const unsigned long long sd = ek_seed(dr);
   float* Ps = smf;                               // [AG_ROWS][H*Kn]
   const int g = blockIdx.x;
   const int c0 = blockIdx.y * AG_COLS;
@@ -335,11 +340,12 @@ edge_aggregate_fwd_kernel(const float* __restrict__ P, const T* __restrict__ QKZ
         if (i < rows) {
           const size_t row = (size_t)g * N + i0 + i;
           const float o = acc[r] + bo;
-          const float act = fmaxf(o + o, 0.f);
-          const float xn = Xin[row * D + c0 + cl] + act;
+          // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
+          const float o2 = (o + o) * ek_drop_mult(dr, sd, row * D + c0 + cl);
+          const float xn = Xin[row * D + c0 + cl] + fmaxf(o2, 0.f);
           Xout[row * D + c0 + cl] = xn;
           if (XoutT) XoutT[row * ldt + c0 + cl] = from_f32<T>(xn);
-          mask[row * D + c0 + cl] = (o + o) > 0.f ? 1 : 0;
+          mask[row * D + c0 + cl] = o2 > 0.f ? 1 : 0;
         }
       }
     }
@@ -354,7 +360,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 edge_aggregate_bwd_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ mask,
                           const float* __restrict__ P, const T* __restrict__ QKZ, long long ld, int D, int N, int Kn,
-                          int H, T* __restrict__ dQKZ, float* __restrict__ dOut, float* __restrict__ dPpart) {
+                          int H, T* __restrict__ dQKZ, float* __restrict__ dOut, float* __restrict__ dPpart,
+                          float gscale) {
   extern __shared__ float smf[];
   const int g = blockIdx.x;
   const int slice = blockIdx.y;
@@ -370,7 +377,7 @@ edge_aggregate_bwd_kernel(const float* __restrict__ dXout, const uint8_t* __rest
     float v = 0.f;
     if (c0 + c < D) {
       const size_t idx = ((size_t)g * N + i) * D + c0 + c;
-      v = mask[idx] ? 2.f * dXout[idx] : 0.f;
+      v = mask[idx] ? gscale * dXout[idx] : 0.f;      // gscale = 2 / (1 - p_dropout)
       dOut[idx] = v;
     }
     dO[i * (AG_COLS + 1) + c] = v;
@@ -512,20 +519,20 @@ int ek_adj_prep_bwd_launch(const float* adj0, const float* adj1, int g_split, co
 }
 
 int ek_geom_bias_fwd_launch(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
-                            const float* dim_t, int G, int N, int Kn, int H, float* gbias, cudaStream_t st) {
+                            const float* dim_t, int G, int N, int Kn, int H, float* gbias, EkDrop dr, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   dim3 grid(G, ek_div_up(N * Kn, 128 * 4));
   geom_bias_fwd_kernel<<<grid, 128, (H * 65 + 8) * sizeof(float), st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
-                                                                         gbias);
+                                                                         gbias, dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_geom_bias_bwd_launch(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                             const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
-                            cudaStream_t st) {
+                            EkDrop dr, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float);
-  geom_bias_bwd_kernel<<<G, GB_TILE, smem, st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part);
+  geom_bias_bwd_kernel<<<G, GB_TILE, smem, st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part, dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -566,7 +573,7 @@ int ek_edge_softmax_fwd_launch(int is_bf16, const void* QKZ, long long ld, int D
 template <typename T>
 static int edge_aggregate_fwd_t(const float* P, const T* QKZ, long long ld, int D, const float* b_out,
                                 const float* Xin, int G, int N, int Kn, int H, float* Xout, T* XoutT, long long ldt,
-                                uint8_t* mask, cudaStream_t st) {
+                                uint8_t* mask, EkDrop dr, cudaStream_t st) {
   const size_t smem = (size_t)AG_ROWS * H * Kn * sizeof(float);
   static size_t configured = 0;
   auto kern = edge_aggregate_fwd_kernel<T>;
@@ -575,35 +582,37 @@ static int edge_aggregate_fwd_t(const float* P, const T* QKZ, long long ld, int 
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "edge_aggregate: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask);
+  kern<<<dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
+                                                          dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
                           int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
-                          cudaStream_t st);
+                          EkDrop dr, cudaStream_t st);
 int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
-                          int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, cudaStream_t st);
+                          int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, float gscale,
+                          cudaStream_t st);
 
 int ek_edge_aggregate_fwd_launch(int is_bf16, const float* P, const void* QKZ, long long ld, int D, const float* b_out,
                                  const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT,
-                                 long long ldt, uint8_t* mask, cudaStream_t st) {
+                                 long long ldt, uint8_t* mask, EkDrop dr, cudaStream_t st) {
   if (is_bf16) {   // tensor-core kernel (edge_mma.cu); SIMT template only for shapes it does not take
     const int rc = ek_agg_fwd_mma_launch(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT, ldt,
-                                         mask, st);
+                                         mask, dr, st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
   }
   return is_bf16 ? edge_aggregate_fwd_t<bf16>(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT,
-                                              ldt, mask, st)
+                                              ldt, mask, dr, st)
                  : edge_aggregate_fwd_t<float>(P, (const float*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout,
-                                               (float*)XoutT, ldt, mask, st);
+                                               (float*)XoutT, ldt, mask, dr, st);
 }
 
 int ek_edge_num_slices(int D) { return ek_div_up(D, AG_COLS); }
 
 template <typename T>
 static int edge_aggregate_bwd_t(const float* dXout, const uint8_t* mask, const float* P, const T* QKZ, long long ld,
-                                int D, int G, int N, int Kn, int H, T* dQKZ, float* dOut, float* dPpart,
+                                int D, int G, int N, int Kn, int H, T* dQKZ, float* dOut, float* dPpart, float gscale,
                                 cudaStream_t st) {
   const size_t smem = ((size_t)N * (AG_COLS + 1) + 32 * (AG_COLS + 1) + (size_t)N * 32) * sizeof(float);
   static size_t configured = 0;
@@ -613,22 +622,23 @@ static int edge_aggregate_bwd_t(const float* dXout, const uint8_t* mask, const f
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "edge_aggregate_bwd: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart);
+  kern<<<dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart,
+                                                          gscale);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_edge_aggregate_bwd_launch(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                                  long long ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut,
-                                 float* dPpart, cudaStream_t st) {
+                                 float* dPpart, float gscale, cudaStream_t st) {
   if (is_bf16) {
     const int rc = ek_agg_bwd_mma_launch(dXout, mask, P, (const bf16*)QKZ, ld, D, G, N, Kn, H, (bf16*)dQKZ, dOut,
-                                         dPpart, st);
+                                         dPpart, gscale, st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
   }
   return is_bf16 ? edge_aggregate_bwd_t<bf16>(dXout, mask, P, (const bf16*)QKZ, ld, D, G, N, Kn, H, (bf16*)dQKZ, dOut,
-                                              dPpart, st)
+                                              dPpart, gscale, st)
                  : edge_aggregate_bwd_t<float>(dXout, mask, P, (const float*)QKZ, ld, D, G, N, Kn, H, (float*)dQKZ,
-                                               dOut, dPpart, st);
+                                               dOut, dPpart, gscale, st);
 }
 
 template <typename T>

@@ -59,8 +59,9 @@ __global__ void __launch_bounds__(256)
 agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, long long ld, int D,
                    const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                    float* __restrict__ Xout, bf16* __restrict__ XoutT, long long ldt, uint8_t* __restrict__ mask,
-                   int kchunk) {
+                   int kchunk, EkDrop dr) {
   extern __shared__ __align__(16) uint8_t smraw[];
+  const unsigned long long sd = ek_seed(dr);
   const int PS = kchunk + 8;                        // P row pitch (elements)
   bf16* Zs = (bf16*)smraw;                          // [kchunk][ZS]
   bf16* Phi = Zs + (size_t)kchunk * ZS;             // [MR][PS]
@@ -134,12 +135,15 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
           const size_t row = (size_t)g * N + i;
           const float o0 = acc[it][nt][2 * hh] + bo.x, o1 = acc[it][nt][2 * hh + 1] + bo.y;
           const float2 xi = *(const float2*)(Xin + row * D + col);
-          const float x0 = xi.x + fmaxf(o0 + o0, 0.f), x1 = xi.y + fmaxf(o1 + o1, 0.f);
+          // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
+          const float p0 = (o0 + o0) * ek_drop_mult(dr, sd, row * D + col);
+          const float p1 = (o1 + o1) * ek_drop_mult(dr, sd, row * D + col + 1);
+          const float x0 = xi.x + fmaxf(p0, 0.f), x1 = xi.y + fmaxf(p1, 0.f);
           *(float2*)(Xout + row * D + col) = make_float2(x0, x1);
           if (XoutT) *(__nv_bfloat162*)(XoutT + row * ldt + col) = __floats2bfloat162_rn(x0, x1);
           uchar2 mk;
-          mk.x = (o0 + o0) > 0.f ? 1 : 0;
-          mk.y = (o1 + o1) > 0.f ? 1 : 0;
+          mk.x = p0 > 0.f ? 1 : 0;
+          mk.y = p1 > 0.f ? 1 : 0;
           *(uchar2*)(mask + row * D + col) = mk;
         }
       }
@@ -154,7 +158,7 @@ template <int MR>   // padded query rows (all of them are staged): 64 or 128
 __global__ void __launch_bounds__(256)
 agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ mask, const float* __restrict__ P,
                    const bf16* __restrict__ QKZ, long long ld, int D, int N, int Kn, int H, bf16* __restrict__ dQKZ,
-                   float* __restrict__ dOut, float* __restrict__ dPpart, int kchunk) {
+                   float* __restrict__ dOut, float* __restrict__ dPpart, int kchunk, float gscale) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int PS = kchunk + 8;
   bf16* dOs = (bf16*)smraw;                         // [MR][ZS]   dout tile (i, c)
@@ -172,7 +176,8 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
       const size_t idx = ((size_t)g * N + i) * D + c0 + c;
       const float4 d = *(const float4*)(dXout + idx);
       const uchar4 m = *(const uchar4*)(mask + idx);
-      v = make_float4(m.x ? 2.f * d.x : 0.f, m.y ? 2.f * d.y : 0.f, m.z ? 2.f * d.z : 0.f, m.w ? 2.f * d.w : 0.f);
+      v = make_float4(m.x ? gscale * d.x : 0.f, m.y ? gscale * d.y : 0.f, m.z ? gscale * d.z : 0.f,
+                      m.w ? gscale * d.w : 0.f);
       *(float4*)(dOut + idx) = v;
     }
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
@@ -520,7 +525,7 @@ int set_smem(K kern, size_t smem, size_t& configured, const char* what) {
 // returns EK_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the SIMT template)
 int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
                           int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
-                          cudaStream_t st) {
+                          EkDrop dr, cudaStream_t st) {
   if ((D % 8) || (ld % 8) || (ldt % 2) || ((uintptr_t)QKZ & 15)) return EK_ERR_UNSUPPORTED;
   const int HK = H * Kn;
   const int HKp = (HK + 15) & ~15;
@@ -532,18 +537,21 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
   if (MR == 64) {
     int rc = set_smem(agg_fwd_mma_kernel<64>, smem, c64, "agg_fwd_mma");
     if (rc) return rc;
-    agg_fwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk);
+    agg_fwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
+                                                    dr);
   } else {
     int rc = set_smem(agg_fwd_mma_kernel<128>, smem, c128, "agg_fwd_mma");
     if (rc) return rc;
-    agg_fwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk);
+    agg_fwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
+                                                     dr);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 
 int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
-                          int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, cudaStream_t st) {
+                          int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, float gscale,
+                          cudaStream_t st) {
   if ((D % 8) || (ld % 8) || ((uintptr_t)QKZ & 15) || ((uintptr_t)dQKZ & 3) || N > 128) return EK_ERR_UNSUPPORTED;
   const int HK = H * Kn;
   const int HKp = (HK + 15) & ~15;
@@ -555,11 +563,13 @@ int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* 
   if (MR == 64) {
     int rc = set_smem(agg_bwd_mma_kernel<64>, smem, c64, "agg_bwd_mma");
     if (rc) return rc;
-    agg_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk);
+    agg_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
+                                                    gscale);
   } else {
     int rc = set_smem(agg_bwd_mma_kernel<128>, smem, c128, "agg_bwd_mma");
     if (rc) return rc;
-    agg_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk);
+    agg_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
+                                                     gscale);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;

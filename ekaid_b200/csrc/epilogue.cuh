@@ -17,6 +17,8 @@ struct EkEpilogue {
   const uint8_t* rowflag;
   const float* rowb_alt;
   int act;
+  EkDrop drop;        // applied to (acc + bias + ...) BEFORE the activation, element index m*dropN + n
+  int dropN;
   float* C;
   long long ldc;
   bf16* Cb;
@@ -41,6 +43,7 @@ __device__ __forceinline__ void ek_epilogue_store(const EkEpilogue& e, long long
     if (e.rowflag && e.rowflag[m]) v += __ldg(e.rowb_alt + n);
     else v += __ldg(e.rowb + (long long)((m / e.rowb_div) % e.rowb_mod) * e.ldrowb + n);
   }
+  if (e.drop.seed) v *= ek_drop_mult(e.drop, ek_seed(e.drop), (unsigned long long)m * e.dropN + n);
   v = ek_act(v, e.act);
   if (e.C) e.C[m * e.ldc + n] = v;
   if (e.Cb) e.Cb[m * e.ldcb + n] = __float2bfloat16_rn(v);

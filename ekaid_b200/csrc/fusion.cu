@@ -159,8 +159,9 @@ __global__ void combine_diff_bwd_kernel(const float* __restrict__ dXc, const flo
 // pre [M, 2D] fp32: [:, 0:D] = context pre-activation, [:, D:2D] = gate pre-activation (biases included)
 template <typename T>
 __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int D, T* __restrict__ ctx,
-                                T* __restrict__ gate, T* __restrict__ CAT) {
+                                T* __restrict__ gate, T* __restrict__ CAT, EkDrop dc, EkDrop dg) {
   const long long total = M * D;
+  const unsigned long long sc = ek_seed(dc), sg = ek_seed(dg);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / D;
@@ -169,19 +170,21 @@ __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int 
     const float gv = sigmoidf_(pre[r * 2 * D + D + c]);
     ctx[e] = from_f32<T>(cv);
     gate[e] = from_f32<T>(gv);
-    CAT[r * 3 * D + 2 * D + c] = from_f32<T>(gv * cv);
+    // train mode: Dropout(0.5) on the tanh output and, independently, on the sigmoid output (modules.py:279,281)
+    CAT[r * 3 * D + 2 * D + c] = from_f32<T>((gv * ek_drop_mult(dg, sg, e)) * (cv * ek_drop_mult(dc, sc, e)));
   }
 }
 // dXs = dCAT[:, 2D:3D] (fp32) -> dpre [M, 2D] (T)
 template <typename T>
 __global__ void gate_bwd_kernel(const float* __restrict__ dCAT, const T* __restrict__ ctx, const T* __restrict__ gate,
-                                long long M, int D, T* __restrict__ dpre) {
+                                long long M, int D, T* __restrict__ dpre, EkDrop dc, EkDrop dg) {
   const long long total = M * D;
+  const unsigned long long sc = ek_seed(dc), sg = ek_seed(dg);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / D;
     const int c = (int)(e % D);
-    const float d = dCAT[r * 3 * D + 2 * D + c];
+    const float d = dCAT[r * 3 * D + 2 * D + c] * ek_drop_mult(dc, sc, e) * ek_drop_mult(dg, sg, e);
     const float cv = to_f32<T>(ctx[e]), gv = to_f32<T>(gate[e]);
     dpre[r * 2 * D + c] = from_f32<T>(d * gv * (1.f - cv * cv));
     dpre[r * 2 * D + D + c] = from_f32<T>(d * cv * gv * (1.f - gv));
@@ -216,7 +219,8 @@ template <typename T>
 __global__ void att_pool_bwd_kernel(const float* __restrict__ dA, const float* __restrict__ dattw,
                                     const float* __restrict__ att, const float* __restrict__ Xc,
                                     const float* __restrict__ E, const float* __restrict__ w, long long M, int N, int D,
-                                    int dim, float* __restrict__ dXc, T* __restrict__ dE, float* __restrict__ dpre_out) {
+                                    int dim, float* __restrict__ dXc, T* __restrict__ dE, float* __restrict__ dpre_out,
+                                    float escale) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -232,7 +236,9 @@ __global__ void att_pool_bwd_kernel(const float* __restrict__ dA, const float* _
   if (dattw) s += dattw[row];
   const float dp = s * a * (1.f - a);
   if (lane == 0) dpre_out[row] = dp;
-  for (int c = lane; c < dim; c += 32) dE[row * dim + c] = from_f32<T>(E[row * dim + c] > 0.f ? dp * w[c] : 0.f);
+  // escale = 1/(1-p) of the embed Dropout(0.5) in train mode (E > 0 implies the element was kept)
+  for (int c = lane; c < dim; c += 32)
+    dE[row * dim + c] = from_f32<T>(E[row * dim + c] > 0.f ? dp * w[c] * escale : 0.f);
 }
 
 // ---------------------------------------------------------------- process_matrix (mimic_utils.py:119-149)
@@ -273,6 +279,51 @@ __global__ void adam_advance_kernel(float* pow_state, float b1, float b2) {
   pow_state[0] *= b1;
   pow_state[1] *= b2;
 }
+
+// ---------------------------------------------------------------- train-mode dropout helpers
+// VQ[m, 0:D] = drop(X[m,:]), VQ[m, D:D+Dq] = drop(flag[m] ? 0 : qv[(m / N) % B, :])
+// = Dropout(0.2)(q_expand_v_cat(q, v))   (relation_encoder.py:19-29 + fc.py:25-32); element index m*(D+Dq) + c
+template <typename T>
+__global__ void build_vq_kernel(const float* __restrict__ X, const float* __restrict__ qv,
+                                const uint8_t* __restrict__ flags, long long M, int N, int B, int D, int Dq,
+                                T* __restrict__ VQ, EkDrop dr) {
+  const int W = D + Dq;
+  const long long total = M * W;
+  const unsigned long long sd = ek_seed(dr);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long m = e / W;
+    const int c = (int)(e % W);
+    float v;
+    if (c < D) v = X[m * D + c];
+    else v = flags[m] ? 0.f : qv[(size_t)((m / N) % B) * Dq + (c - D)];
+    VQ[e] = from_f32<T>(v * ek_drop_mult(dr, sd, e));
+  }
+}
+// out = sum_k mult_k(idx) * in_k   (k < nin <= 3; mult_k = 1 when site k has p = 0);  idx = m*C + c
+// optional fp32 output (optionally accumulated into) and/or operand-type output
+template <typename TI, typename TO>
+__global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const TI* __restrict__ in1,
+                                    const TI* __restrict__ in2, long long ldi, EkDrop d0, EkDrop d1, EkDrop d2,
+                                    long long M, int C, float* __restrict__ outf, long long ldf, int accumulate,
+                                    TO* __restrict__ outT, long long ldo) {
+  const long long total = M * C;
+  const unsigned long long s0 = ek_seed(d0), s1 = ek_seed(d1), s2 = ek_seed(d2);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long m = e / C;
+    const int c = (int)(e % C);
+    float v = to_f32<TI>(in0[m * ldi + c]) * ek_drop_mult(d0, s0, e);
+    if (nin > 1) v += to_f32<TI>(in1[m * ldi + c]) * ek_drop_mult(d1, s1, e);
+    if (nin > 2) v += to_f32<TI>(in2[m * ldi + c]) * ek_drop_mult(d2, s2, e);
+    if (outf) {
+      if (accumulate) v += outf[m * ldf + c];
+      outf[m * ldf + c] = v;
+    }
+    if (outT) outT[m * ldo + c] = from_f32<TO>(v);
+  }
+}
+__global__ void rng_advance_kernel(unsigned long long* seed) { *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
 
 inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
@@ -356,22 +407,23 @@ int ek_combine_diff_bwd_launch(const float* dXc, const float* dCAT, long long BN
   return EK_OK;
 }
 
-int ek_gate_fwd_launch(int is_bf16, const float* pre, long long M, int D, void* ctx, void* gate, void* CAT,
-                       cudaStream_t st) {
+int ek_gate_fwd_launch(int is_bf16, const float* pre, long long M, int D, void* ctx, void* gate, void* CAT, EkDrop dc,
+                       EkDrop dg, cudaStream_t st) {
   if (is_bf16)
-    gate_fwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT);
+    gate_fwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT, dc, dg);
   else
-    gate_fwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (float*)ctx, (float*)gate, (float*)CAT);
+    gate_fwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (float*)ctx, (float*)gate, (float*)CAT, dc, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_gate_bwd_launch(int is_bf16, const float* dCAT, const void* ctx, const void* gate, long long M, int D,
-                       void* dpre, cudaStream_t st) {
+                       void* dpre, EkDrop dc, EkDrop dg, cudaStream_t st) {
   if (is_bf16)
-    gate_bwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre);
+    gate_bwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre,
+                                                           dc, dg);
   else
     gate_bwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const float*)ctx, (const float*)gate, M, D,
-                                                            (float*)dpre);
+                                                            (float*)dpre, dc, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -386,13 +438,13 @@ int ek_att_pool_fwd_launch(const float* E, long long M, int N, int D, int dim, c
 }
 int ek_att_pool_bwd_launch(int is_bf16, const float* dA, const float* dattw, const float* att, const float* Xc,
                            const float* E, const float* w, long long M, int N, int D, int dim, float* dXc, void* dE,
-                           float* dpre, cudaStream_t st) {
+                           float* dpre, float escale, cudaStream_t st) {
   if (is_bf16)
     att_pool_bwd_kernel<bf16><<<ek_div_up(M, 8), 256, 0, st>>>(dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, (bf16*)dE,
-                                                                dpre);
+                                                                dpre, escale);
   else
     att_pool_bwd_kernel<float><<<ek_div_up(M, 8), 256, 0, st>>>(dA, dattw, att, Xc, E, w, M, N, D, dim, dXc,
-                                                                 (float*)dE, dpre);
+                                                                 (float*)dE, dpre, escale);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -415,6 +467,38 @@ int ek_adam_launch(float* p, const float* g, float* m, float* v, long long n, fl
 
 int ek_adam_advance_launch(float* pow_state, float b1, float b2, cudaStream_t st) {
   adam_advance_kernel<<<1, 1, 0, st>>>(pow_state, b1, b2);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_build_vq_launch(int is_bf16, const float* X, const float* qv, const uint8_t* flags, long long M, int N, int B,
+                       int D, int Dq, void* VQ, EkDrop dr, cudaStream_t st) {
+  if (is_bf16) build_vq_kernel<bf16><<<grid_for(M * (D + Dq)), 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
+  else build_vq_kernel<float><<<grid_for(M * (D + Dq)), 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
+                           long long ldi, EkDrop d0, EkDrop d1, EkDrop d2, long long M, int C, float* outf,
+                           long long ldf, int accumulate, void* outT, long long ldo, cudaStream_t st) {
+  const int g = grid_for(M * C);
+  if (in_bf16 && out_bf16)
+    drop_combine_kernel<bf16, bf16><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi, d0,
+                                                      d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
+  else if (in_bf16)
+    drop_combine_kernel<bf16, float><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
+                                                       d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
+  else if (out_bf16)
+    drop_combine_kernel<float, bf16><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1, (const float*)in2,
+                                                       ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
+  else
+    drop_combine_kernel<float, float><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1, (const float*)in2,
+                                                        ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_rng_advance_launch(unsigned long long* seed, cudaStream_t st) {
+  rng_advance_kernel<<<1, 1, 0, st>>>(seed);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

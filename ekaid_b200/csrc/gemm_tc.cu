@@ -315,6 +315,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j) v[j] += __ldg(rowb_ptr + nb + j);
             }
           }
+          if (ep.drop.seed) {
+            const unsigned long long sd = ek_seed(ep.drop);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= ek_drop_mult(ep.drop, sd, (unsigned long long)m * ep.dropN + nb + j);
+          }
           if (ep.act != EK_ACT_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ek_act(v[j], ep.act);
@@ -505,7 +510,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   if (ep.addend && (((uintptr_t)ep.addend & 15) || (ep.ldadd & 3))) vec_ok &= ~4;
   if (ep.rowb && (((uintptr_t)ep.rowb & 15) || (ep.ldrowb & 3) || ((uintptr_t)ep.rowb_alt & 15))) vec_ok &= ~8;
   // split-K (auto when splits == 0): only for plain fp32 outputs with too few tiles to fill the chip
-  const bool plain = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE;
+  const bool plain = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE && !ep.drop.seed;
   const int num_kb = ek_div_up(K, BK);
   if (splits <= 0) {
     splits = 1;

@@ -29,6 +29,49 @@ ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 DEBUG_SINK = None
 
 
+_rng_state = {}
+
+
+def rng_state(dev) -> torch.Tensor:
+    """Device-resident 64-bit seed of the dropout masks (one per device), initialised from torch's seed."""
+    key = str(dev)
+    if key not in _rng_state:
+        _rng_state[key] = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
+    return _rng_state[key]
+
+
+def rng_advance(dev) -> None:
+    """Draw fresh dropout masks for the next step (a kernel: stays valid inside a captured CUDA graph)."""
+    call("rng_advance", rng_state(dev).data_ptr())
+
+
+class Drop:
+    """Train-mode dropout description handed to the stage functions: probabilities per site group, or off."""
+
+    def __init__(self, dev, on: bool, p_fc=0.2, p_gat=0.2, p_qv=0.2, p_fuse=0.5, p_embed=0.5):
+        self.on = on
+        self.seed = rng_state(dev).data_ptr() if on else None
+        self.p_fc, self.p_gat, self.p_qv, self.p_fuse, self.p_embed = p_fc, p_gat, p_qv, p_fuse, p_embed
+
+    def a(self, site, p):
+        """(seed pointer, site, p) triple of one dropout site for the C ABI."""
+        return (self.seed, site, float(p) if self.on else 0.0)
+
+
+def drop_combine(ins, sites, M, C, outf=None, accumulate=0, outT=None):
+    """out = sum_k dropout_k(in_k); `sites` = [(seed, site, p)] per input."""
+    nin = len(ins)
+    i0 = ins[0]
+    pad = [None] * (3 - nin)
+    ptrs = [t.data_ptr() for t in ins] + pad
+    sp = list(sites) + [(None, 0, 0.0)] * (3 - nin)
+    seed = next((x[0] for x in sp if x[0] is not None and x[2] > 0), None)
+    call("drop_combine", 1 if i0.dtype == torch.bfloat16 else 0, 1 if (outT is not None and outT.dtype == torch.bfloat16) else 0,
+         nin, ptrs[0], ptrs[1], ptrs[2], i0.stride(0), seed, sp[0][1], sp[0][2], sp[1][1], sp[1][2], sp[2][1], sp[2][2],
+         M, C, ptr(outf), outf.stride(0) if outf is not None else 0, accumulate, ptr(outT),
+         outT.stride(0) if outT is not None else 0)
+
+
 class PC:
     """precision config: 'bf16' (tensor cores) or 'fp32' (SIMT, 1e-4 parity mode)."""
 
@@ -44,7 +87,7 @@ class PC:
 # thin wrappers
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None, rowb_div=1, rowb_mod=1,
-         rowflag=None, rowb_alt=None, act=ACT_NONE, C=None, Cb=None, splits=0, force_bn=0):
+         rowflag=None, rowb_alt=None, act=ACT_NONE, C=None, Cb=None, splits=0, force_bn=0, drop=None):
     """C[M,N] = op(A) op(B) with the fused epilogue; dtype of A selects tcgen05 (bf16) or SIMT (fp32)."""
     ep = Epilogue()
     ep.bias = ptr(bias)
@@ -56,6 +99,8 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
     ep.rowflag = ptr(rowflag)
     ep.rowb_alt = ptr(rowb_alt)
     ep.act = act
+    if drop is not None and drop[2] > 0.0:
+        ep.drop_seed, ep.drop_site, ep.drop_p, ep.drop_n = drop[0], drop[1], drop[2], N
     ep.C = ptr(C)
     ep.ldc = C.stride(0) if C is not None else 0
     ep.Cb = ptr(Cb)
@@ -196,7 +241,7 @@ class QuestionFn(torch.autograd.Function):
     """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156)."""
 
     @staticmethod
-    def forward(ctx, pc: PC, question, emb, emb2, Wih, Whh, bih, bhh, W1, b1, w2, b2):
+    def forward(ctx, pc: PC, drop, question, emb, emb2, Wih, Whh, bih, bhh, W1, b1, w2, b2):
         lib.require_device()
         dev = emb.device
         B, L = question.shape
@@ -220,24 +265,37 @@ class QuestionFn(torch.autograd.Function):
             call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
                  Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr())
         HsT_cur = HsT[B:]
-        a1, _ = gemm_T(pc, HsT_cur, W1T, L * B, H, H, bias=b1c, act=ACT_TANH)
+        if drop is not None and drop.on:          # Dropout(0.2) on the input of W1 (language_model.py:123-124)
+            Hd = torch.empty(L * B, H, dtype=pc.T, device=dev)
+            drop_combine([HsT_cur], [drop.a(10, drop.p_fc)], L * B, H, outT=Hd)
+        else:
+            Hd = HsT_cur
+        a1, _ = gemm_T(pc, Hd, W1T, L * B, H, H, bias=b1c, act=ACT_TANH)
         a = torch.empty(L * B, dtype=torch.float32, device=dev)
         call("rowdot", pc.f, a1.data_ptr(), a1.stride(0), L * B, H, w2c.data_ptr(), b2c.data_ptr(), a.data_ptr())
         S = torch.empty(L * B, dtype=torch.float32, device=dev)
         qv = torch.empty(B, H, dtype=torch.float32, device=dev)
         call("qpool_fwd", a.data_ptr(), Hs.data_ptr(), B, L, H, S.data_ptr(), qv.data_ptr())
-        ctx.pc = pc
+        if drop is not None and drop.on:          # self.drop on the pooled vector (language_model.py:155)
+            drop_combine([qv], [drop.a(11, drop.p_qv)], B, H, outf=qv)
+        ctx.pc, ctx.drop = pc, drop
         ctx.dims = (B, L, ed, H, emb.shape[0])
-        ctx.saved = (q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S)
+        ctx.saved = (q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd)
         return qv
 
     @staticmethod
     def backward(ctx, dqv):
         pc = ctx.pc
         B, L, ed, H, V = ctx.dims
-        q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S = ctx.saved
+        q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd = ctx.saved
+        drop = ctx.drop
+        don = drop is not None and drop.on
         dev = Hs.device
         dqv = _f32c(dqv)
+        if don:
+            dq2 = torch.empty_like(dqv)
+            drop_combine([dqv], [drop.a(11, drop.p_qv)], B, H, outf=dq2)
+            dqv = dq2
         dS = torch.empty(L * B, dtype=torch.float32, device=dev)
         da = torch.empty(L * B, dtype=torch.float32, device=dev)
         dHs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
@@ -247,10 +305,13 @@ class QuestionFn(torch.autograd.Function):
         call("qatt_tanh_bwd", pc.f, da.data_ptr(), w2c.data_ptr(), a1.data_ptr(), L * B, H, dpre.data_ptr())
         dw2 = colsum(a1, L * B, H, rowscale=da).view(1, H)
         db2 = colsum(da.view(-1, 1), L * B, 1)
-        HsT_cur = HsT[B:]
-        dW1 = gemm_f32out(dpre, HsT_cur, H, H, L * B, transA=1, transB=1)
+        dW1 = gemm_f32out(dpre, Hd, H, H, L * B, transA=1, transB=1)
         db1 = colsum(dpre, L * B, H)
-        gemm(dpre, W1T, L * B, H, H, transB=1, addend=dHs, C=dHs)         # dHs += dpre W1
+        if don:
+            tmp = gemm_f32out(dpre, W1T, L * B, H, H, transB=1)
+            drop_combine([tmp], [drop.a(10, drop.p_fc)], L * B, H, outf=dHs, accumulate=1)
+        else:
+            gemm(dpre, W1T, L * B, H, H, transB=1, addend=dHs, C=dHs)     # dHs += dpre W1
         # BPTT
         dgi = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
         dgh = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
@@ -275,7 +336,7 @@ class QuestionFn(torch.autograd.Function):
         dE = gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1)           # only the trainable table's columns
         demb = torch.empty(V, ed, dtype=torch.float32, device=dev)
         call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr())
-        return None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
+        return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
 
 
 # ------------------------------------------------------------------------------------------------
@@ -302,27 +363,48 @@ class RelationFn(torch.autograd.Function):
     Images [0, g_split) read adj0, the rest adj1."""
 
     @staticmethod
-    def forward(ctx, pc: PC, kind: str, dims, X, XT, qv, Wsw, bsw, Wqkz, bqkz, bout, p0, p1, adj0, adj1, g_split):
+    def forward(ctx, pc: PC, drop, site0, kind: str, dims, X, XT, qv, Wsw, bsw, Wqkz, bqkz, bout, p0, p1, adj0, adj1,
+                g_split):
         lib.require_device()
         G, B, N, Kn, D, H = dims
         dev = X.device
         M = G * N
         X = _f32c(X).view(M, D)
         qv = _f32c(qv)
-        if XT is None or XT.dtype != pc.T:
-            XT = to_T(pc, X)
+        don = drop is not None and drop.on
         WswT, WqkzT = to_T(pc, Wsw), to_T(pc, Wqkz)
         Wsw32 = _f32c(Wsw)
         bswc, bqkzc, boutc = _f32c(bsw), _f32c(bqkz), _f32c(bout)
         flags = torch.empty(M, dtype=torch.uint8, device=dev)
         call("row_zero_flags", X.data_ptr(), M, D, flags.data_ptr())
-        # question half of self_weights, once per sample (M = B rows)
-        qvT = to_T(pc, qv)
-        qpart = gemm_f32out(qvT, WswT[:, D:], B, D, qv.shape[1], bias=bswc)
-        Sf, _ = gemm_T(pc, XT, WswT[:, :D], M, D, D, rowb=qpart, rowb_div=N, rowb_mod=B, rowflag=flags,
-                       rowb_alt=bswc)
         W = (2 + H) * D
-        QKZ, _ = gemm_T(pc, Sf, WqkzT, M, W, D, bias=bqkzc)
+        Dq = qv.shape[1]
+        qvT = to_T(pc, qv)
+        if not don:
+            if XT is None or XT.dtype != pc.T:
+                XT = to_T(pc, X)
+            # question half of self_weights, once per sample (M = B rows), broadcast per row in the GEMM epilogue
+            qpart = gemm_f32out(qvT, WswT[:, D:], B, D, Dq, bias=bswc)
+            Sf, _ = gemm_T(pc, XT, WswT[:, :D], M, D, D, rowb=qpart, rowb_div=N, rowb_mod=B, rowflag=flags,
+                           rowb_alt=bswc)
+            QKZ, _ = gemm_T(pc, Sf, WqkzT, M, W, D, bias=bqkzc)
+            Sq = Sk = Sf
+        else:
+            # train mode: Dropout(0.2) hits the concatenated [v | q] element-wise, so the question half is no longer
+            # the same for every node -> K = D + Dq GEMM on the dropped concat; query / key see two more masks
+            XT = torch.empty(M, D + Dq, dtype=pc.T, device=dev)          # the dropped [v | q] operand
+            call("build_vq", pc.f, X.data_ptr(), qv.data_ptr(), flags.data_ptr(), M, N, B, D, Dq, XT.data_ptr(),
+                 *drop.a(site0 + 1, drop.p_fc))
+            Sf, _ = gemm_T(pc, XT, WswT, M, D, D + Dq, bias=bswc)
+            Sq = torch.empty(M, D, dtype=pc.T, device=dev)
+            Sk = torch.empty(M, D, dtype=pc.T, device=dev)
+            drop_combine([Sf], [drop.a(site0 + 2, drop.p_fc)], M, D, outT=Sq)
+            drop_combine([Sf], [drop.a(site0 + 3, drop.p_fc)], M, D, outT=Sk)
+            QKZ = torch.empty(M, W, dtype=pc.T, device=dev)
+            for src, lo, hi in ((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W)):
+                out = QKZ[:, lo:hi]
+                gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=None if pc.bf16 else out,
+                     Cb=out if pc.bf16 else None)
         cond = lbias = gbias = None
         if kind == "explicit":
             a0 = _f32c(adj0)
@@ -341,8 +423,9 @@ class RelationFn(torch.autograd.Function):
             a1 = adj1.detach().to(device=dev, dtype=torch.float64).contiguous() if adj1 is not None else None
             Wp, bp = _f32c(p0), _f32c(p1)
             gbias = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
+            dgeo = drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)
             call("geom_bias_fwd", a0.data_ptr(), ptr(a1), g_split, Wp.data_ptr(), bp.data_ptr(),
-                 _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr())
+                 _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr(), *dgeo)
             ctx.geo = (a0, a1, Wp, bp)
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
         es = 2 if pc.bf16 else 4
@@ -353,9 +436,11 @@ class RelationFn(torch.autograd.Function):
         mask = torch.empty(M, D, dtype=torch.uint8, device=dev)
         call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, boutc.data_ptr(), X.data_ptr(),
              G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr(),
+             *(drop.a(site0 + 5, drop.p_gat) if don else (None, 0, 0.0)),
              info={"bytes": G * (N * H * Kn * 4 + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
         ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
-        ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask)
+        ctx.drop, ctx.site0 = drop, site0
+        ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append(mask.bool().cpu())
         if XnT is not None:
@@ -368,7 +453,9 @@ class RelationFn(torch.autograd.Function):
     def backward(ctx, dXn, _dXnT, _dP):
         pc, kind = ctx.pc, ctx.kind
         G, B, N, Kn, D, H = ctx.dims
-        XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, QKZ, cond, P, mask = ctx.saved
+        XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask = ctx.saved
+        drop, site0 = ctx.drop, ctx.site0
+        don = drop is not None and drop.on
         dev = P.device
         M = G * N
         W = (2 + H) * D
@@ -381,6 +468,7 @@ class RelationFn(torch.autograd.Function):
         es = 2 if pc.bf16 else 4
         call("edge_aggregate_bwd", pc.f, dXn.data_ptr(), mask.data_ptr(), P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D,
              G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr(),
+             2.0 / (1.0 - drop.p_gat) if don else 2.0,
              info={"bytes": G * (N * D * (4 + 1 + 4) + N * H * Kn * 4 * (1 + ns) + 2 * Kn * H * D * es)})
         dbout = colsum(dOut, M, D)
         dlb = dgb = None
@@ -401,26 +489,48 @@ class RelationFn(torch.autograd.Function):
             a0, a1, Wp, bp = ctx.geo
             part = torch.empty(G, H * 65, dtype=torch.float32, device=dev)
             call("geom_bias_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, Wp.data_ptr(), bp.data_ptr(),
-                 _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr())
+                 _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr(),
+                 *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)))
             tot = colsum(part, G, H * 65).view(H, 65)
             dp0, dp1 = tot[:, :64].contiguous(), tot[:, 64].contiguous()
-        # [query | key | Z] projection
-        dWqkz = gemm_f32out(dQKZ, Sf, W, D, M, transA=1, transB=1)
-        dbqkz = colsum(dQKZ, M, W)
-        dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
-        # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
-        dWsw = torch.empty(D, Wsw32.shape[1], dtype=torch.float32, device=dev)
-        gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
-        dbsw = colsum(dSf, M, D)
-        dqpart = torch.empty(B, D, dtype=torch.float32, device=dev)
-        call("group_rowsum", pc.f, dSf.data_ptr(), dSf.stride(0), N, B, G // B, D, flags.data_ptr(), dqpart.data_ptr())
         Dq = qvT.shape[1]
-        dqpT = to_T(pc, dqpart)
-        gemm(dqpT, qvT, D, Dq, B, transA=1, transB=1, C=dWsw[:, D:], splits=1)   # K = B
-        dqv = gemm_f32out(dqpT, WswT[:, D:], B, Dq, D, transB=1)
+        dbqkz = colsum(dQKZ, M, W)
+        dWsw = torch.empty(D, D + Dq, dtype=torch.float32, device=dev)
         dX = torch.empty(M, D, dtype=torch.float32, device=dev)
-        gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
-        return (None, None, None, dX, None, dqv, dWsw, dbsw, dWqkz, dbqkz, dbout, dp0, dp1, None, None, None)
+        if not don:
+            # [query | key | Z] projection
+            dWqkz = gemm_f32out(dQKZ, Sf, W, D, M, transA=1, transB=1)
+            dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
+            # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
+            gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
+            dbsw = colsum(dSf, M, D)
+            dqpart = torch.empty(B, D, dtype=torch.float32, device=dev)
+            call("group_rowsum", pc.f, dSf.data_ptr(), dSf.stride(0), N, B, G // B, D, flags.data_ptr(),
+                 dqpart.data_ptr())
+            dqpT = to_T(pc, dqpart)
+            gemm(dqpT, qvT, D, Dq, B, transA=1, transB=1, C=dWsw[:, D:], splits=1)   # K = B
+            dqv = gemm_f32out(dqpT, WswT[:, D:], B, Dq, D, transB=1)
+            gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
+        else:
+            dWqkz = torch.empty(W, D, dtype=torch.float32, device=dev)
+            parts = []
+            for src, lo, hi in ((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W)):
+                gemm(dQKZ[:, lo:hi], src, hi - lo, D, M, transA=1, transB=1, C=dWqkz[lo:hi])
+                parts.append(gemm_f32out(dQKZ[:, lo:hi], WqkzT[lo:hi], M, D, hi - lo, transB=1))
+            dSf = torch.empty(M, D, dtype=pc.T, device=dev)
+            drop_combine(parts, [drop.a(site0 + 2, drop.p_fc), drop.a(site0 + 3, drop.p_fc), (None, 0, 0.0)], M, D,
+                         outT=dSf)
+            gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
+            dbsw = colsum(dSf, M, D)
+            dVQ = gemm_f32out(dSf, WswT, M, D + Dq, D, transB=1)
+            drop_combine([dVQ], [drop.a(site0 + 1, drop.p_fc)], M, D + Dq, outf=dVQ)     # mask in place
+            call("copy_f32", dXn.data_ptr(), D, dX.data_ptr(), D, M, D)
+            drop_combine([dVQ[:, :D]], [(None, 0, 0.0)], M, D, outf=dX, accumulate=1)   # residual + masked grad
+            dqv = torch.empty(B, Dq, dtype=torch.float32, device=dev)
+            call("group_rowsum", 0, dVQ[:, D:].data_ptr(), dVQ.stride(0), N, B, G // B, Dq, flags.data_ptr(),
+                 dqv.data_ptr())
+        return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWqkz, dbqkz, dbout, dp0, dp1, None, None,
+                None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -433,7 +543,7 @@ class FusionFn(torch.autograd.Function):
     wa [1, dim], ba [1].  Returns att [2BN] and attended [2B, D]."""
 
     @staticmethod
-    def forward(ctx, pc: PC, dims, mode, coefs, X3, Wcg, bcg, We, be, wa, ba):
+    def forward(ctx, pc: PC, drop, dims, mode, coefs, X3, Wcg, bcg, We, be, wa, ba):
         lib.require_device()
         B, N, D, dim = dims
         dev = X3.device
@@ -449,13 +559,18 @@ class FusionFn(torch.autograd.Function):
         pre = gemm_f32out(CAT[:, :2 * D], WcgT, M, 2 * D, 2 * D, bias=bcgc)
         cx = torch.empty(M, D, dtype=pc.T, device=dev)
         gt = torch.empty(M, D, dtype=pc.T, device=dev)
-        call("gate_fwd", pc.f, pre.data_ptr(), M, D, cx.data_ptr(), gt.data_ptr(), CAT.data_ptr())
-        E = gemm_f32out(CAT, WeT, M, dim, 3 * D, bias=bec, act=ACT_RELU)
+        don = drop is not None and drop.on
+        pf = drop.p_fuse if don else 0.0
+        call("gate_fwd", pc.f, pre.data_ptr(), M, D, cx.data_ptr(), gt.data_ptr(), CAT.data_ptr(),
+             drop.seed if don else None, 20, 21, pf)
+        # embed = Linear -> Dropout(0.5) -> ReLU (modules.py:105-111): dropout fused before the ReLU in the epilogue
+        E = gemm_f32out(CAT, WeT, M, dim, 3 * D, bias=bec, act=ACT_RELU,
+                        drop=drop.a(22, drop.p_embed) if don else None)
         att = torch.empty(M, dtype=torch.float32, device=dev)
         attended = torch.empty(2 * B, D, dtype=torch.float32, device=dev)
         call("att_pool_fwd", E.data_ptr(), M, N, D, dim, wac.data_ptr(), bac.data_ptr(), Xc.data_ptr(), att.data_ptr(),
              attended.data_ptr())
-        ctx.pc, ctx.dims, ctx.mode, ctx.coefs = pc, dims, mode, coefs
+        ctx.pc, ctx.dims, ctx.mode, ctx.coefs, ctx.drop = pc, dims, mode, coefs, drop
         ctx.saved = (Xc, CAT, WcgT, WeT, wac, cx, gt, E, att)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append((E > 0).cpu())
@@ -467,6 +582,8 @@ class FusionFn(torch.autograd.Function):
         B, N, D, dim = ctx.dims
         Xc, CAT, WcgT, WeT, wac, cx, gt, E, att = ctx.saved
         dev = Xc.device
+        drop = ctx.drop
+        don = drop is not None and drop.on
         BN = B * N
         M = 2 * BN
         c1, c2, c3 = ctx.coefs
@@ -476,20 +593,22 @@ class FusionFn(torch.autograd.Function):
         dE = torch.empty(M, dim, dtype=pc.T, device=dev)
         dpa = torch.empty(M, dtype=torch.float32, device=dev)
         call("att_pool_bwd", pc.f, dA.data_ptr(), ptr(dw_), att.data_ptr(), Xc.data_ptr(), E.data_ptr(), wac.data_ptr(),
-             M, N, D, dim, dXc.data_ptr(), dE.data_ptr(), dpa.data_ptr())
+             M, N, D, dim, dXc.data_ptr(), dE.data_ptr(), dpa.data_ptr(),
+             1.0 / (1.0 - drop.p_embed) if don else 1.0)
         dwa = colsum(E, M, dim, rowscale=dpa).view(1, dim)
         dba = colsum(dpa.view(-1, 1), M, 1)
         dWe = gemm_f32out(dE, CAT, dim, 3 * D, M, transA=1, transB=1)
         dbe = colsum(dE, M, dim)
         dCAT = gemm_f32out(dE, WeT, M, 3 * D, dim, transB=1)
         dpre = torch.empty(M, 2 * D, dtype=pc.T, device=dev)
-        call("gate_bwd", pc.f, dCAT.data_ptr(), cx.data_ptr(), gt.data_ptr(), M, D, dpre.data_ptr())
+        call("gate_bwd", pc.f, dCAT.data_ptr(), cx.data_ptr(), gt.data_ptr(), M, D, dpre.data_ptr(),
+             drop.seed if don else None, 20, 21, drop.p_fuse if don else 0.0)
         dWcg = gemm_f32out(dpre, CAT[:, :2 * D], 2 * D, 2 * D, M, transA=1, transB=1)
         dbcg = colsum(dpre, M, 2 * D)
         gemm(dpre, WcgT, M, 2 * D, 2 * D, transB=1, addend=dCAT[:, :2 * D], C=dCAT[:, :2 * D])
         dX3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         call("combine_diff_bwd", dXc.data_ptr(), dCAT.data_ptr(), BN, D, ctx.mode, c1, c2, c3, dX3.data_ptr())
-        return None, None, None, None, dX3, dWcg, dbcg, dWe, dbe, dwa, dba
+        return None, None, None, None, None, dX3, dWcg, dbcg, dWe, dbe, dwa, dba
 
 
 # ------------------------------------------------------------------------------------------------

@@ -23,7 +23,8 @@ class Epilogue(ctypes.Structure):
         ("bias", ctypes.c_void_p), ("addend", ctypes.c_void_p), ("ldadd", ctypes.c_int64),
         ("rowb", ctypes.c_void_p), ("ldrowb", ctypes.c_int64), ("rowb_div", ctypes.c_int32),
         ("rowb_mod", ctypes.c_int32), ("rowflag", ctypes.c_void_p), ("rowb_alt", ctypes.c_void_p),
-        ("act", ctypes.c_int32), ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
+        ("act", ctypes.c_int32), ("drop_seed", ctypes.c_void_p), ("drop_site", ctypes.c_uint32),
+        ("drop_p", ctypes.c_float), ("drop_n", ctypes.c_int32), ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
         ("Cb", ctypes.c_void_p), ("ldcb", ctypes.c_int64),
     ]
 
@@ -47,7 +48,8 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[str]]]:
     return protos
 
 
-_CT = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
+_CT = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32,
+       "float": ctypes.c_float,
        "ptr": ctypes.c_void_p}
 
 _lib = None

@@ -33,7 +33,7 @@ with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     from torch.nn.utils import weight_norm as _weight_norm
 
-from .functions import PC, FusionFn, LinearFn, QuestionFn, RelationFn
+from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn
 
 
 def _default_precision() -> str:
@@ -160,8 +160,19 @@ class GAttNet(nn.Module):
         # quirk Q2: the output of every direction but the last is overwritten
         return self.neighbor_net[self.dir_num - 1]
 
-    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N):
+    def make_drop(self, dev, override=None) -> Drop:
+        """Train-mode dropout of this GAT: 0.2 on the inputs of self_weights / query / key / pair_pos_fc1 (fc.py:25-32)
+        and 0.2 on the doubled output before the ReLU (graph_att.py:103)."""
+        p_fc = self.self_weights.main[0].p if isinstance(self.self_weights.main[0], nn.Dropout) else 0.0
+        p_gat = self.dropout.p
+        if override is not None:
+            p_fc = p_gat = override
+        return Drop(dev, self.training, p_fc=p_fc, p_gat=p_gat)
+
+    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N, drop=None, site0=100):
         """X [G*N, D] -> X + relu(2 * attention output).  geo*: adjacency (explicit) or fp64 boxes (implicit)."""
+        if drop is None:
+            drop = self.make_drop(X.device)
         D = self.out_feat_dim
         layer = self.live_layer()
         H = layer.num_heads
@@ -176,7 +187,7 @@ class GAttNet(nn.Module):
         else:
             kind, p0, p1 = "explicit", wn_weight(self.bias.linear()), None
         dims = (G, B, N, Kn, D, H)
-        return RelationFn.apply(pc, kind, dims, X, XT, q, wn_weight(sw), sw.bias, Wqkz, bqkz,
+        return RelationFn.apply(pc, drop, site0, kind, dims, X, XT, q, wn_weight(sw), sw.bias, Wqkz, bqkz,
                                 layer.linear_out_2.bias, p0, p1, geo0, geo1, g_split)
 
     def forward(self, v_feat, adj_matrix, pos_emb=None):
@@ -370,6 +381,8 @@ class ChangeDetector(nn.Module):
         if cfg.data.feature_mode == 'mode0':
             raise NotImplementedError("feature_mode 'mode0' (ResNet-101 on raw images) is outside the hot path")
         self.precision = _default_precision()
+        # tests only: force every dropout probability (0.0 runs the train-mode code path without masks)
+        self.dropout_override = None
 
     def live_parameters(self):
         """Parameters that can receive a gradient in setting='mode2'.  The rest exist only so reference checkpoints
@@ -401,10 +414,11 @@ class ChangeDetector(nn.Module):
         rnn = self.q_emb.rnn
         w1 = self.q_att.W1_self_att_q.linear()
         w2 = self.q_att.W2_self_att_q.linear()
-        if self.training:
-            raise NotImplementedError("train-mode dropout inside the question attention is handled by "
-                                      "ChangeDetector.forward; call it instead")
-        return QuestionFn.apply(pc, question, self.w_emb.emb.weight, self.w_emb.emb_.weight, rnn.weight_ih_l0,
+        ov = self.dropout_override
+        drop = Drop(question.device, self.training,
+                    p_fc=self.q_att.W1_self_att_q.main[0].p if ov is None else ov,
+                    p_qv=self.q_att.drop.p if ov is None else ov)
+        return QuestionFn.apply(pc, drop, question, self.w_emb.emb.weight, self.w_emb.emb_.weight, rnn.weight_ih_l0,
                                 rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0, wn_weight(w1), w1.bias,
                                 wn_weight(w2), w2.bias)
 
@@ -425,30 +439,34 @@ class ChangeDetector(nn.Module):
                                       "self.graph_relation, which does not exist; mode0 is the SSRE ablation)")
         if graph not in ('all', 'semantic', 'spatial', 'implicit', 'i+s'):
             raise ValueError("unknown graph mode %r" % (graph,))
-        if self.training:
-            raise NotImplementedError("train-mode (dropout) forward is not implemented yet; use .eval() -- "
-                                      "gradients are available in eval mode")
         pc = PC(self.precision)
+        ov = self.dropout_override
         B, N, C = input_1.size()
         D = self.att_dim
         G = 2 * B
         X, XT = LinearFn.apply(pc, input_1, input_2, self.img.weight, self.img.bias)      # [2BN, D]
         qv = self.question_vector(pc, question)
+        dev = X.device
         if graph in ('semantic', 'all'):
-            X, XT, _ = self.semantic_relation.explicit_relation.relation_step(
-                pc, X, XT, qv, d_sem_adj_matrix, q_sem_adj_matrix, B, G, B, N)
+            gat = self.semantic_relation.explicit_relation
+            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_sem_adj_matrix, q_sem_adj_matrix, B, G, B, N,
+                                         drop=gat.make_drop(dev, ov), site0=100)
         if graph in ('spatial', 'all', 'i+s'):
-            X, XT, _ = self.spatial_relation.explicit_relation.relation_step(
-                pc, X, XT, qv, d_adj_matrix, q_adj_matrix, B, G, B, N)
+            gat = self.spatial_relation.explicit_relation
+            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_adj_matrix, q_adj_matrix, B, G, B, N,
+                                         drop=gat.make_drop(dev, ov), site0=200)
         if graph in ('implicit', 'all', 'i+s'):
-            X, XT, _ = self.imp_relation.implicit_relation.relation_step(
-                pc, X, XT, qv, d_bb, q_bb, B, G, B, N)
+            gat = self.imp_relation.implicit_relation
+            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_bb, q_bb, B, G, B, N,
+                                         drop=gat.make_drop(dev, ov), site0=300)
         mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
         coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
         Wcg = torch.cat([torch.cat([self.context2.weight, self.context1.weight], 1),
                          torch.cat([self.gate2.weight, self.gate1.weight], 1)], 0)
         bcg = torch.cat([self.context2.bias, self.gate2.bias], 0)
-        att, attended = FusionFn.apply(pc, (B, N, D, self.dim), mode, coefs, X, Wcg, bcg, self.embed[0].weight,
+        fdrop = Drop(dev, self.training, p_fuse=self.dropout.p if ov is None else ov,
+                     p_embed=self.embed[1].p if ov is None else ov)
+        att, attended = FusionFn.apply(pc, fdrop, (B, N, D, self.dim), mode, coefs, X, Wcg, bcg, self.embed[0].weight,
                                        self.embed[0].bias, self.att.weight, self.att.bias)
         BN = B * N
         att_weight_before = att[:BN].view(B, 1, N)

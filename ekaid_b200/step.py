@@ -15,7 +15,7 @@ from typing import Callable, Optional, Sequence
 import torch
 
 from . import lib
-from .functions import onehot_adj
+from .functions import onehot_adj, rng_advance
 from .modules import ChangeDetector
 
 
@@ -135,6 +135,8 @@ class GraphFusionStep:
         """optimizer.zero_grad -> forward -> backward -> [all-reduce(mean)] -> Adam  (train_mimic.py:220-269).
         Returns the (device) loss tensor; no host sync happens here."""
         self.opt.zero_grad()
+        if self.cd.training:
+            rng_advance(self.opt.flat.device)      # fresh dropout masks (a kernel: replays draw new masks too)
         total = self.loss(inputs, labels, masks)
         total.backward()
         if self.pg is not None:

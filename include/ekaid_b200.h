@@ -53,11 +53,22 @@ typedef struct ekaid_epilogue {
   const uint8_t* rowflag;
   const float* rowb_alt;
   int32_t act;
+  /* train-mode dropout applied BEFORE the activation (embed: Linear -> Dropout(0.5) -> ReLU, modules.py:105-111):
+   * element (m,n) uses counter m*drop_n + n of site drop_site; drop_seed = device pointer to the step seed, NULL = off */
+  const uint64_t* drop_seed;
+  uint32_t drop_site;
+  float drop_p;
+  int32_t drop_n;
   float* C;
   int64_t ldc;
   void* Cb; /* __nv_bfloat16* */
   int64_t ldcb;
 } ekaid_epilogue_t;
+
+/* Dropout convention (train mode; eval / p = 0 passes seed = NULL): masks are never stored.  Every dropout site of the
+ * reference has a site id; element idx of that site is kept iff hash(*seed, site, idx) >= p * 2^32 and scaled by
+ * 1/(1-p).  The seed lives in device memory (ekaid_rng_advance once per step) so a captured CUDA graph draws fresh
+ * masks at every replay; forward and backward regenerate identical masks from (seed, site, idx). */
 
 int ekaid_abi_version(void);
 const char* ekaid_last_error(void);
@@ -106,11 +117,12 @@ int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const 
  * (modules.py:162-166, utils/mimic_utils.py:152-208, graph_att_layer.py:113-135; Q7, Q13).
  * dim_t: 8 fp32 wave lengths 1000^(t/8) */
 int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
-                        const float* dim_t, int G, int N, int Kn, int H, float* gbias, void* stream);
+                        const float* dim_t, int G, int N, int Kn, int H, float* gbias, const uint64_t* seed,
+                        uint32_t site, float p, void* stream);
 /* part[g, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h] */
 int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
-                        void* stream);
+                        const uint64_t* seed, uint32_t site, float p, void* stream);
 /* QKZ [G*N, ld]: cols [0,D) query, [D,2D) key, [2D + h*D, 2D + (h+1)*D) Z_h.  P [G,N,H,Kn] fp32.
  * scores/sqrt(dh) (+gbias) -> where(cond>0, s, -9e15) + lbias -> softmax over keys
  * (graph_att_layer.py:105-157; Q6).  cond / lbias / gbias may be NULL. */
@@ -121,12 +133,12 @@ int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, cons
  * XoutT: optional copy of Xout in the operand type with pitch ldt (may be NULL). */
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
-                             uint8_t* mask, void* stream);
+                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, void* stream);
 int ekaid_edge_num_slices(int D);
-/* dOut [G*N, D] = 2*mask*dXout; dQKZ[:, 2D:] = dZ; dPpart [slices, G,N,H,Kn] */
+/* dOut [G*N, D] = gscale*mask*dXout (gscale = 2/(1-p)); dQKZ[:, 2D:] = dZ; dPpart [slices, G,N,H,Kn] */
 int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                              int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
-                             void* stream);
+                             float gscale, void* stream);
 /* dQKZ[:, 0:2D] = (dQ, dK); dlbias_part [H, G,N,Kn] and dgbias [G,N,Kn,H] may be NULL */
 int ekaid_edge_softmax_bwd(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ, int64_t ld,
                            int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ, float* dlbias_part,
@@ -141,15 +153,16 @@ int ekaid_combine_diff_bwd(const float* dXc, const float* dCAT, int64_t BN, int 
                            float c3, float* dX3, void* stream);
 /* pre [M,2D] fp32 = (context | gate) pre-activations -> ctx=tanh, gate=sigmoid, CAT[:,2D:3D] = gate*ctx
  * (modules.py:278-288) */
-int ekaid_gate_fwd(int is_bf16, const float* pre, int64_t M, int D, void* ctx, void* gate, void* CAT, void* stream);
+int ekaid_gate_fwd(int is_bf16, const float* pre, int64_t M, int D, void* ctx, void* gate, void* CAT,
+                   const uint64_t* seed, uint32_t site_ctx, uint32_t site_gate, float p, void* stream);
 int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* gate, int64_t M, int D, void* dpre,
-                   void* stream);
+                   const uint64_t* seed, uint32_t site_ctx, uint32_t site_gate, float p, void* stream);
 /* att = sigmoid(E w + b) [M];  attended[g,:] = sum_n att[g,n] Xc[g,n,:]   (modules.py:302-308) */
 int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const float* w, const float* b,
                        const float* Xc, float* att, float* attended, void* stream);
 int ekaid_att_pool_bwd(int is_bf16, const float* dA, const float* dattw, const float* att, const float* Xc,
                        const float* E, const float* w, int64_t M, int N, int D, int dim, float* dXc, void* dE,
-                       float* dpre, void* stream);
+                       float* dpre, float escale, void* stream);
 
 /* ---- question path (models/language_model.py) ------------------------------------------------------------ */
 /* E[l*B+b,:] = [emb[q[b,l]] | emb_[q[b,l]]]   (:48-53) */
@@ -171,6 +184,19 @@ int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, in
                     float* dHs, void* stream);
 int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
                         void* stream);
+
+/* ---- train-mode dropout helpers -------------------------------------------------------------------------- */
+int ekaid_rng_advance(uint64_t* seed, void* stream);
+/* VQ [M, D+Dq] = Dropout(cat(X, flag ? 0 : q))  -- the input of self_weights in train mode (relation_encoder.py:19-29,
+ * fc.py:25-32; graph_att.py:80), operand type */
+int ekaid_build_vq(int is_bf16, const float* X, const float* qv, const uint8_t* flags, int64_t M, int N, int B, int D,
+                   int Dq, void* VQ, const uint64_t* seed, uint32_t site, float p, void* stream);
+/* out = sum_{k<nin} mult_k * in_k  (mult_k = dropout multiplier of site k, 1 when p_k = 0); index m*C + c.
+ * outf (fp32, optional, accumulate != 0 adds to its old value) and/or outT (operand type, optional). */
+int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
+                       int64_t ldi, const uint64_t* seed, uint32_t site0, float p0, uint32_t site1, float p1,
+                       uint32_t site2, float p2, int64_t M, int C, float* outf, int64_t ldf, int accumulate,
+                       void* outT, int64_t ldo, void* stream);
 
 /* ---- optimizer (utils/utils.py:96-99 -> torch.optim.Adam semantics) -------------------------------------- */
 /* pow_state: device float[2] = {beta1^t, beta2^t}; call ekaid_adam_advance once per step before the updates */

@@ -1,0 +1,146 @@
+"""Train-mode (dropout) path on a B200.  Bitwise RNG parity with ATen is impossible, so:
+  * the dropout RNG is checked statistically and for determinism / site independence;
+  * the train-mode code path (K = 2048 self_weights GEMM on the dropped concat, separate query/key/Z GEMMs, masked
+    backward) is run with every probability forced to 0 and must reproduce the eval-mode oracle parity exactly;
+  * with the real probabilities, the analytic gradients are checked against central finite differences of the SAME
+    masked function (the seed is frozen), which validates that forward and backward regenerate identical masks."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from helpers import OUT_NAMES, case_inputs, load_case, loss_weights, oracle_forward, rel_err
+from test_gpu_parity import build_model, to_dev, grad_err, gtol, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    from ekaid_b200 import lib
+    lib.require_device()
+    return torch.device("cuda:0")
+
+
+def test_dropout_rng_statistics_and_determinism():
+    from ekaid_b200.functions import drop_combine, rng_advance, rng_state
+    dev = _dev()
+    seed = rng_state(dev).data_ptr()
+    x = torch.ones(2048, 1024, device=dev)
+    outs = {}
+    for site, p in ((1, 0.2), (2, 0.2), (3, 0.5)):
+        y = torch.empty_like(x)
+        drop_combine([x], [(seed, site, p)], 2048, 1024, outf=y)
+        zero = float((y == 0).float().mean())
+        assert abs(zero - p) < 4e-3, (site, p, zero)
+        kept = y[y != 0]
+        assert float((kept - 1.0 / (1.0 - p)).abs().max()) < 1e-6
+        assert abs(float(y.mean()) - 1.0) < 1e-2
+        outs[site] = y
+    assert float(((outs[1] == 0) == (outs[2] == 0)).float().mean()) < 0.75      # independent sites (0.68 expected)
+    again = torch.empty_like(x)
+    drop_combine([x], [(seed, 1, 0.2)], 2048, 1024, outf=again)
+    assert torch.equal(again, outs[1])                                           # same (seed, site, idx) -> same mask
+    xb = x.to(torch.bfloat16)
+    yb = torch.empty(2048, 1024, device=dev, dtype=torch.bfloat16)
+    drop_combine([xb], [(seed, 1, 0.2)], 2048, 1024, outT=yb)
+    assert torch.equal(yb == 0, outs[1] == 0)                                    # mask independent of storage type
+    rng_advance(dev)
+    drop_combine([x], [(seed, 1, 0.2)], 2048, 1024, outf=again)
+    assert not torch.equal(again, outs[1])
+    # row/col structure: no correlation between neighbouring elements
+    m = (outs[1] != 0).float()
+    assert abs(float((m[:, 1:] * m[:, :-1]).mean()) - 0.64) < 5e-3
+    assert abs(float((m[1:] * m[:-1]).mean()) - 0.64) < 5e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_path_with_p0_matches_oracle(precision):
+    from ekaid_b200 import functions
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z, meta = load_case("c1_b3_n52_all_grads")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    m.train()
+    m.dropout_override = 0.0
+    functions.DEBUG_SINK = []
+    try:
+        outs = m(*to_dev(inp, dev), setting="mode2", graph=meta["graph"])
+        masks = functions.DEBUG_SINK
+    finally:
+        functions.DEBUG_SINK = None
+    with torch.no_grad():
+        ref = oracle_forward(sd, inp, meta)
+    for k, o, r in zip(OUT_NAMES[1:5], outs[1:5], ref[1:5]):
+        assert rel_err(o, r) < TOL[precision], (k, rel_err(o, r))
+    ws = loss_weights(outs)
+    sum((o * w.to(dev)).sum() for o, w in zip(outs[1:], ws)).backward()
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()}
+    cd = m.cfg.model.change_detector
+    ro = O.change_detector_forward(sdg, *inp, graph=meta["graph"], num_heads=cd.att_head, nongt_dim=meta["nongt_dim"],
+                                   relu_masks=masks)
+    sum((o * w).sum() for o, w in zip(ro[1:], ws)).backward()
+    bad = []
+    for k, p in m.named_parameters():
+        g_ref = sdg[k].grad
+        if g_ref is None or float(g_ref.abs().max()) < 1e-4:
+            continue
+        e = grad_err(p.grad, g_ref, precision)
+        if e > gtol(precision, k, g_ref):
+            bad.append((k, e))
+    assert not bad, bad
+
+
+def test_train_mode_gradients_match_finite_differences():
+    """fp32 path, real dropout probabilities, frozen seed: <analytic grad, d> == (L(w + e d) - L(w - e d)) / 2e."""
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, "fp32", dev)
+    m.train()
+    dinp = to_dev(inp, dev)
+    gw = torch.Generator().manual_seed(7)
+    cot = None
+
+    def loss():
+        nonlocal cot
+        outs = m(*dinp, setting="mode2", graph="all")
+        if cot is None:
+            cot = [torch.randn(o.shape, generator=gw).to(dev) for o in outs[1:]]
+        return sum((o.double() * c.double()).sum() for o, c in zip(outs[1:], cot))
+
+    l0 = loss()
+    l0.backward()
+    with torch.no_grad():
+        l0b = loss()
+    assert float((l0 - l0b).abs()) < 1e-6 * max(1.0, float(l0.abs()))         # frozen seed -> same masks
+    eval_out = m.eval()(*dinp)[3]
+    m.train()
+    assert rel_err(m(*dinp)[3], eval_out) > 1e-2                               # dropout is really active
+    names = ["img.weight", "semantic_relation.explicit_relation.self_weights.main.1.weight_v",
+             "spatial_relation.explicit_relation.neighbor_net.1.query.main.1.weight_v",
+             "spatial_relation.explicit_relation.neighbor_net.1.key.main.1.weight_v",
+             "imp_relation.implicit_relation.neighbor_net.1.pair_pos_fc1.main.1.weight_v",
+             "imp_relation.implicit_relation.neighbor_net.1.linear_out_2.weight",
+             "spatial_relation.explicit_relation.bias.main.0.weight_v",
+             "context1.weight", "gate2.weight", "embed.0.weight", "att.weight",
+             "q_emb.rnn.weight_hh_l0", "w_emb.emb.weight", "q_att.W1_self_att_q.main.1.weight_v"]
+    params = dict(m.named_parameters())
+    report = []
+    for k in names:
+        p = params[k]
+        g = p.grad.detach().clone()
+        d = g / (g.norm() + 1e-30)
+        analytic = float((g.double() * d.double()).sum())
+        eps = 2e-3 * float(p.detach().norm()) / max(1.0, float(p.numel()) ** 0.5) * float(p.numel()) ** 0.5 * 1e-1
+        with torch.no_grad():
+            p.add_(eps * d)
+            lp = float(loss())
+            p.sub_(2 * eps * d)
+            lm = float(loss())
+            p.add_(eps * d)
+        fd = (lp - lm) / (2 * eps)
+        report.append((k, analytic, fd))
+        assert abs(fd - analytic) < 3e-2 * abs(analytic) + 1e-3, (k, analytic, fd, eps)
+    print("finite-difference check:", [(k.split(".")[-3:], round(a, 4), round(f, 4)) for k, a, f in report])
