@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
+    ap.add_argument("--no-dropout", action="store_true", help="train step with modules in eval mode (no dropout)")
     return ap.parse_args()
 
 
@@ -179,6 +180,7 @@ def workload_config(args):
             "scope": "graph+fusion (ChangeDetector) fwd+bwd + Adam on its parameters; decoder gradient = fixed cotangent",
             "batch_per_gpu": args.batch, "nodes": args.nodes, "feat_dim": 1024, "graph": args.graph, "mode": args.mode,
             "precision": args.precision, "parallelism": "dp%d" % args.gpus,
+            "dropout": bool(args.mode == "train" and not args.no_dropout),
             "l2": "per-step working set (activations > 400 MB at batch 64) exceeds the 126 MB L2; inputs rotate over 4 "
                   "resident batches"}
 
@@ -213,7 +215,10 @@ def main():
     spec = {k: tuple(v.shape) for k, v in cd.state_dict().items()}
     cd.load_state_dict(synthetic_state_dict(spec, 1238))
     cd.to(dev).set_precision(args.precision)
-    cd.eval()          # dropout-free graph; see DESIGN.md (train-mode dropout) -- gradients flow in eval mode
+    if args.mode == "train" and not args.no_dropout:
+        cd.train()     # reference train mode: all dropout sites active (masks from the device-resident counter RNG)
+    else:
+        cd.eval()
     step = GraphFusionStep(cd, cfg, graph=args.graph, process_group=pg)
 
     # synthetic loader: 4 distinct host batches (pinned), per-rank seeds
