@@ -35,6 +35,9 @@ int ek_build_vq_launch(int, const float*, const float*, const uint8_t*, long lon
 int ek_drop_combine_launch(int, int, int, const void*, const void*, const void*, long long, EkDrop, EkDrop, EkDrop,
                            long long, int, float*, long long, int, void*, long long, cudaStream_t);
 int ek_rng_advance_launch(unsigned long long*, cudaStream_t);
+int ek_wn_fwd_launch(const float*, const float*, long long, float*, float*, float*, cudaStream_t);
+int ek_wn_bwd_launch(const float*, const float*, const float*, const float*, long long, float*, float*, float*,
+                     cudaStream_t);
 int ek_att_pool_fwd_launch(const float*, long long, int, int, int, const float*, const float*, const float*, float*,
                            float*, cudaStream_t);
 int ek_att_pool_bwd_launch(int, const float*, const float*, const float*, const float*, const float*, const float*,
@@ -47,9 +50,9 @@ int ek_adj_prep_fwd_launch(const float*, const float*, int, const float*, int, i
                            cudaStream_t);
 int ek_adj_prep_bwd_launch(const float*, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
 int ek_geom_bias_fwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
-                            int, float*, EkDrop, cudaStream_t);
+                            int, float*, EkDrop, float*, int, cudaStream_t);
 int ek_geom_bias_bwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
-                            int, const float*, float*, EkDrop, cudaStream_t);
+                            int, const float*, float*, EkDrop, const float*, int, cudaStream_t);
 int ek_edge_softmax_fwd_launch(int, const void*, long long, int, const float*, const float*, const float*, int, int,
                                int, int, float*, cudaStream_t);
 int ek_edge_aggregate_fwd_launch(int, const float*, const void*, long long, int, const float*, const float*, int, int,
@@ -168,14 +171,16 @@ int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const 
 }
 int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, float* gbias, const uint64_t* seed,
-                        uint32_t site, float p, void* stream) {
-  return ek_geom_bias_fwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, gbias, mk_drop(seed, site, p), ST);
+                        uint32_t site, float p, float* emb_cache, int fast_trig, void* stream) {
+  return ek_geom_bias_fwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, gbias, mk_drop(seed, site, p),
+                                 emb_cache, fast_trig, ST);
 }
 int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
-                        const uint64_t* seed, uint32_t site, float p, void* stream) {
+                        const uint64_t* seed, uint32_t site, float p, const float* emb_cache, int fast_trig,
+                        void* stream) {
   return ek_geom_bias_bwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, dgbias, part, mk_drop(seed, site, p),
-                                 ST);
+                                 emb_cache, fast_trig, ST);
 }
 int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
                            const float* gbias, int G, int N, int Kn, int H, float* P, void* stream) {
@@ -217,6 +222,13 @@ int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* 
                    const uint64_t* seed, uint32_t site_ctx, uint32_t site_gate, float p, void* stream) {
   return ek_gate_bwd_launch(is_bf16, dCAT, ctx, gate, M, D, dpre, mk_drop(seed, site_ctx, p),
                             mk_drop(seed, site_gate, p), ST);
+}
+int ekaid_wn_fwd(const float* v, const float* g, int64_t n, float* w, float* norm_out, float* workspace, void* stream) {
+  return ek_wn_fwd_launch(v, g, n, w, norm_out, workspace, ST);
+}
+int ekaid_wn_bwd(const float* dw, const float* v, const float* g, const float* norm, int64_t n, float* dv, float* dg,
+                 float* workspace, void* stream) {
+  return ek_wn_bwd_launch(dw, v, g, norm, n, dv, dg, workspace, ST);
 }
 int ekaid_rng_advance(uint64_t* seed, void* stream) { return ek_rng_advance_launch((unsigned long long*)seed, ST); }
 int ekaid_build_vq(int is_bf16, const float* X, const float* qv, const uint8_t* flags, int64_t M, int N, int B, int D,

@@ -88,7 +88,8 @@ __device__ __forceinline__ void pos_feats(const double* __restrict__ bb, int r, 
 template <int MAXH>
 __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __restrict__ Wp, const float* __restrict__ bp,
                                             int H, const float* __restrict__ dim_t, float f[MAXH], float* emb_out,
-                                            const EkDrop& dr, unsigned long long seedv, unsigned long long pair_idx) {
+                                            const EkDrop& dr, unsigned long long seedv, unsigned long long pair_idx,
+                                            bool fast_trig) {
 #pragma unroll
   for (int h = 0; h < MAXH; ++h) f[h] = (h < H) ? bp[h] : 0.f;
 #pragma unroll
@@ -97,7 +98,14 @@ __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __re
     for (int t = 0; t < 8; ++t) {
       const double a = (100.0 * g[q]) / (double)dim_t[t];
       double sv, cv;
-      sincos(a, &sv, &cv);
+      if (fast_trig) {      // bf16 path: fp32 sincosf (full-range reduction, ~2 ulp) on the fp64-computed argument
+        float sf, cf;
+        sincosf((float)a, &sf, &cf);
+        sv = sf;
+        cv = cf;
+      } else {
+        sincos(a, &sv, &cv);
+      }
       // reference casts the fp64 embedding to fp32 (graph_att_layer.py:115); train mode: Dropout(0.2) on the
       // 64-d embedding before pair_pos_fc1 (fc.py:25-32), element index pair*64 + k
       const float s = (float)sv * ek_drop_mult(dr, seedv, pair_idx * 64 + q * 16 + t);
@@ -114,7 +122,8 @@ __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __re
 __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
                                      const float* __restrict__ Wp, const float* __restrict__ bp,
                                      const float* __restrict__ dim_t, int N, int Kn, int H,
-                                     float* __restrict__ gbias, EkDrop dr) {
+                                     float* __restrict__ gbias, EkDrop dr, float* __restrict__ emb_cache,
+                                     int fast_trig) {
   extern __shared__ float sW[];      // H*64 + H, then 8 wave lengths
   float* sDim = sW + H * 65;
   for (int e = threadIdx.x; e < H * 64; e += blockDim.x) sW[e] = Wp[e];
@@ -128,7 +137,17 @@ __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const doubl
     double gq[4];
     pos_feats(bb, r, c, gq);
     float f[8];
-    pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, nullptr, dr, ek_seed(dr), (unsigned long long)g * N * Kn + e);
+    if (emb_cache) {      // keep the (dropped) embedding for the backward pass: 256 B per pair instead of 32 sincos
+      float emb[64];
+      pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, emb, dr, ek_seed(dr), (unsigned long long)g * N * Kn + e,
+                     fast_trig != 0);
+      float4* dst = (float4*)(emb_cache + ((size_t)g * N * Kn + e) * 64);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dst[k] = make_float4(emb[4 * k], emb[4 * k + 1], emb[4 * k + 2], emb[4 * k + 3]);
+    } else {
+      pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, nullptr, dr, ek_seed(dr), (unsigned long long)g * N * Kn + e,
+                     fast_trig != 0);
+    }
     for (int h = 0; h < H; ++h) {
       const float v = fmaxf(fmaxf(f[h], 0.f), 1e-6f);
       gbias[((size_t)g * N * Kn + e) * H + h] = logf(v);
@@ -143,7 +162,8 @@ constexpr int GB_TILE = 128;
 __global__ void __launch_bounds__(GB_TILE)
 geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
                      const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ dim_t, int N,
-                     int Kn, int H, const float* __restrict__ dgbias, float* __restrict__ part, EkDrop dr) {
+                     int Kn, int H, const float* __restrict__ dgbias, float* __restrict__ part, EkDrop dr,
+                     const float* __restrict__ emb_cache, int fast_trig) {
   extern __shared__ float sm[];      // weights H*65 | 8 wave lengths | emb [GB_TILE][65] | df [GB_TILE][8]
   float* sW = sm;
   float* sDim = sm + H * 65;
@@ -166,11 +186,29 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
 #pragma unroll
     for (int h = 0; h < 8; ++h) df[h] = 0.f;
     if (e < total) {
-      const int r = e / N, c = e % N;
-      double gq[4];
-      pos_feats(bb, r, c, gq);
       float f[8];
-      pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, emb, dr, ek_seed(dr), (unsigned long long)g * total + e);
+      if (emb_cache) {
+        const float4* src = (const float4*)(emb_cache + ((size_t)g * total + e) * 64);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float4 v = src[k];
+          emb[4 * k] = v.x; emb[4 * k + 1] = v.y; emb[4 * k + 2] = v.z; emb[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          float a = (h < H) ? sW[H * 64 + h] : 0.f;
+          if (h < H)
+#pragma unroll
+            for (int k = 0; k < 64; ++k) a = fmaf(sW[h * 64 + k], emb[k], a);
+          f[h] = a;
+        }
+      } else {
+        const int r = e / N, c = e % N;
+        double gq[4];
+        pos_feats(bb, r, c, gq);
+        pair_pos_fc<8>(gq, sW, sW + H * 64, H, sDim, f, emb, dr, ek_seed(dr), (unsigned long long)g * total + e,
+                       fast_trig != 0);
+      }
       for (int h = 0; h < H; ++h)
         df[h] = (f[h] > 1e-6f) ? dgbias[((size_t)g * total + e) * H + h] / f[h] : 0.f;
     } else {
@@ -519,20 +557,22 @@ int ek_adj_prep_bwd_launch(const float* adj0, const float* adj1, int g_split, co
 }
 
 int ek_geom_bias_fwd_launch(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
-                            const float* dim_t, int G, int N, int Kn, int H, float* gbias, EkDrop dr, cudaStream_t st) {
+                            const float* dim_t, int G, int N, int Kn, int H, float* gbias, EkDrop dr, float* emb_cache,
+                            int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   dim3 grid(G, ek_div_up(N * Kn, 128 * 4));
   geom_bias_fwd_kernel<<<grid, 128, (H * 65 + 8) * sizeof(float), st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
-                                                                         gbias, dr);
+                                                                         gbias, dr, emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_geom_bias_bwd_launch(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                             const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
-                            EkDrop dr, cudaStream_t st) {
+                            EkDrop dr, const float* emb_cache, int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float);
-  geom_bias_bwd_kernel<<<G, GB_TILE, smem, st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part, dr);
+  geom_bias_bwd_kernel<<<G, GB_TILE, smem, st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part, dr,
+                                                 emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -323,6 +323,44 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
     if (outT) outT[m * ldo + c] = from_f32<TO>(v);
   }
 }
+// ---------------------------------------------------------------- legacy weight_norm(dim=None) (fc.py:33-34)
+// w = v * g / ||v||_F.  Two launches forward (partials; scale) and two backward, all deterministic.
+constexpr int WN_BLOCKS = 128;
+__global__ void wn_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                  float* __restrict__ part) {     // part[blk] = sum a*b over the block's slice
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    s = fmaf(a[e], b[e], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__device__ __forceinline__ float wn_total(const float* __restrict__ part, float* red) {
+  float s = (threadIdx.x < WN_BLOCKS) ? part[threadIdx.x] : 0.f;
+  return block_sum(s, red);
+}
+__global__ void wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ part,
+                                long long n, float* __restrict__ w, float* __restrict__ norm_out) {
+  __shared__ float red[32];
+  const float nrm = sqrtf(wn_total(part, red));
+  const float sc = g[0] / nrm;
+  if (blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = nrm;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    w[e] = v[e] * sc;
+}
+// dv = (g/n) dw - (g dot / n^3) v ;  dg = dot / n ;  dot = sum dw*v
+__global__ void wn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
+                              const float* __restrict__ norm, const float* __restrict__ part, long long n,
+                              float* __restrict__ dv, float* __restrict__ dg) {
+  __shared__ float red[32];
+  const float dot = wn_total(part, red);
+  const float nrm = norm[0], gv = g[0];
+  const float c1 = gv / nrm, c2 = gv * dot / (nrm * nrm * nrm);
+  if (blockIdx.x == 0 && threadIdx.x == 0) dg[0] = dot / nrm;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    dv[e] = c1 * dw[e] - c2 * v[e];
+}
+
 __global__ void rng_advance_kernel(unsigned long long* seed) { *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
 
 inline int grid_for(long long total, int block = 256) {
@@ -499,6 +537,24 @@ int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, 
 }
 int ek_rng_advance_launch(unsigned long long* seed, cudaStream_t st) {
   rng_advance_kernel<<<1, 1, 0, st>>>(seed);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+// workspace: WN_BLOCKS (128) floats
+int ek_wn_fwd_launch(const float* v, const float* g, long long n, float* w, float* norm_out, float* workspace,
+                     cudaStream_t st) {
+  wn_partial_kernel<<<WN_BLOCKS, 256, 0, st>>>(v, v, n, workspace);
+  EK_CHECK_LAUNCH();
+  wn_scale_kernel<<<grid_for(n), 256, 0, st>>>(v, g, workspace, n, w, norm_out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_wn_bwd_launch(const float* dw, const float* v, const float* g, const float* norm, long long n, float* dv,
+                     float* dg, float* workspace, cudaStream_t st) {
+  wn_partial_kernel<<<WN_BLOCKS, 256, 0, st>>>(dw, v, n, workspace);
+  EK_CHECK_LAUNCH();
+  wn_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dw, v, g, norm, workspace, n, dv, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

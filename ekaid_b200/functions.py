@@ -178,6 +178,47 @@ def _f32c(t):
 
 
 # ------------------------------------------------------------------------------------------------
+# legacy weight_norm(dim=None)
+# ------------------------------------------------------------------------------------------------
+class WNormFn(torch.autograd.Function):
+    """w = v * g / ||v||_F  (models/fc.py:33-34; torch's `_weight_norm` with dim=None), two launches each way instead
+    of the ~10 element-wise / reduction ATen kernels of the composite implementation."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        lib.require_device()
+        vc, gc = _f32c(v), _f32c(g).reshape(1)
+        w = torch.empty_like(vc)
+        norm = torch.empty(1, dtype=torch.float32, device=vc.device)
+        ws = torch.empty(128, dtype=torch.float32, device=vc.device)
+        call("wn_fwd", vc.data_ptr(), gc.data_ptr(), vc.numel(), w.data_ptr(), norm.data_ptr(), ws.data_ptr())
+        ctx.saved = (vc, gc, norm)
+        ctx.gshape = g.shape
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        vc, gc, norm = ctx.saved
+        dwc = _f32c(dw)
+        dv = torch.empty_like(vc)
+        dg = torch.empty(1, dtype=torch.float32, device=vc.device)
+        ws = torch.empty(128, dtype=torch.float32, device=vc.device)
+        call("wn_bwd", dwc.data_ptr(), vc.data_ptr(), gc.data_ptr(), norm.data_ptr(), vc.numel(), dv.data_ptr(),
+             dg.data_ptr(), ws.data_ptr())
+        return dv, dg.reshape(ctx.gshape)
+
+
+def cast_into(pc: PC, src: torch.Tensor, dst: torch.Tensor) -> None:
+    """fp32 2-D `src` (any row pitch) -> operand-type view `dst` (any row pitch), own kernels."""
+    src = src.detach()
+    if src.dim() == 1:
+        src = src.view(1, -1)
+    assert src.stride(-1) == 1 and dst.stride(-1) == 1 and src.shape == dst.shape
+    call("cast_f32_bf16" if pc.bf16 else "copy_f32", src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0),
+         src.shape[0], src.shape[1])
+
+
+# ------------------------------------------------------------------------------------------------
 # y = x W^T + b
 # ------------------------------------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
@@ -363,8 +404,8 @@ class RelationFn(torch.autograd.Function):
     Images [0, g_split) read adj0, the rest adj1."""
 
     @staticmethod
-    def forward(ctx, pc: PC, drop, site0, kind: str, dims, X, XT, qv, Wsw, bsw, Wqkz, bqkz, bout, p0, p1, adj0, adj1,
-                g_split):
+    def forward(ctx, pc: PC, drop, site0, kind: str, dims, X, XT, qv, Wsw, bsw, Wq, bq, Wk, bk, Wo2, bout, p0, p1,
+                adj0, adj1, g_split):
         lib.require_device()
         G, B, N, Kn, D, H = dims
         dev = X.device
@@ -372,9 +413,19 @@ class RelationFn(torch.autograd.Function):
         X = _f32c(X).view(M, D)
         qv = _f32c(qv)
         don = drop is not None and drop.on
-        WswT, WqkzT = to_T(pc, Wsw), to_T(pc, Wqkz)
+        WswT = to_T(pc, Wsw)
         Wsw32 = _f32c(Wsw)
-        bswc, bqkzc, boutc = _f32c(bsw), _f32c(bqkz), _f32c(bout)
+        # [Wq ; Wk ; Z-blocks] operand: ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T (Q3)
+        WqkzT = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
+        cast_into(pc, Wq, WqkzT[0:D])
+        cast_into(pc, Wk, WqkzT[D:2 * D])
+        Wo2c = _f32c(Wo2)
+        for h in range(H):
+            cast_into(pc, Wo2c[:, h * D:(h + 1) * D], WqkzT[(2 + h) * D:(3 + h) * D])
+        bqkzc = torch.zeros((2 + H) * D, dtype=torch.float32, device=dev)
+        call("copy_f32", _f32c(bq).data_ptr(), D, bqkzc.data_ptr(), D, 1, D)
+        call("copy_f32", _f32c(bk).data_ptr(), D, bqkzc[D:].data_ptr(), D, 1, D)
+        bswc, boutc = _f32c(bsw), _f32c(bout)
         flags = torch.empty(M, dtype=torch.uint8, device=dev)
         call("row_zero_flags", X.data_ptr(), M, D, flags.data_ptr())
         W = (2 + H) * D
@@ -424,9 +475,11 @@ class RelationFn(torch.autograd.Function):
             Wp, bp = _f32c(p0), _f32c(p1)
             gbias = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
             dgeo = drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)
+            need_bwd = any(t is not None and t.requires_grad for t in (p0, p1))
+            emb_cache = torch.empty(G, N * Kn, 64, dtype=torch.float32, device=dev) if need_bwd else None
             call("geom_bias_fwd", a0.data_ptr(), ptr(a1), g_split, Wp.data_ptr(), bp.data_ptr(),
-                 _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr(), *dgeo)
-            ctx.geo = (a0, a1, Wp, bp)
+                 _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr(), *dgeo, ptr(emb_cache), pc.f)
+            ctx.geo = (a0, a1, Wp, bp, emb_cache)
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
         es = 2 if pc.bf16 else 4
         call("edge_softmax_fwd", pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond), ptr(lbias), ptr(gbias), G, N, Kn, H,
@@ -486,20 +539,27 @@ class RelationFn(torch.autograd.Function):
             call("adj_prep_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, dlb.data_ptr(), H, G, N, Kn, Lb, part.data_ptr())
             dp0 = colsum(part, G, Lb).view(1, Lb)
         else:
-            a0, a1, Wp, bp = ctx.geo
+            a0, a1, Wp, bp, emb_cache = ctx.geo
             part = torch.empty(G, H * 65, dtype=torch.float32, device=dev)
             call("geom_bias_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, Wp.data_ptr(), bp.data_ptr(),
                  _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr(),
-                 *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)))
+                 *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)), ptr(emb_cache), pc.f)
             tot = colsum(part, G, H * 65).view(H, 65)
             dp0, dp1 = tot[:, :64].contiguous(), tot[:, 64].contiguous()
         Dq = qvT.shape[1]
-        dbqkz = colsum(dQKZ, M, W)
+        dbqk = colsum(dQKZ, M, 2 * D)
+        dbq, dbk = dbqk[:D], dbqk[D:]
+        dWq = torch.empty(D, D, dtype=torch.float32, device=dev)
+        dWk = torch.empty(D, D, dtype=torch.float32, device=dev)
+        dWo2 = torch.empty(D, H * D, dtype=torch.float32, device=dev)
         dWsw = torch.empty(D, D + Dq, dtype=torch.float32, device=dev)
         dX = torch.empty(M, D, dtype=torch.float32, device=dev)
         if not don:
-            # [query | key | Z] projection
-            dWqkz = gemm_f32out(dQKZ, Sf, W, D, M, transA=1, transB=1)
+            # [query | key | Z] projection: weight gradients land directly in parameter-shaped tensors
+            for dst, lo in ((dWq, 0), (dWk, D)):
+                gemm(dQKZ[:, lo:lo + D], Sf, D, D, M, transA=1, transB=1, C=dst)
+            for h in range(H):
+                gemm(dQKZ[:, (2 + h) * D:(3 + h) * D], Sf, D, D, M, transA=1, transB=1, C=dWo2[:, h * D:(h + 1) * D])
             dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
             # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
             gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
@@ -512,10 +572,14 @@ class RelationFn(torch.autograd.Function):
             dqv = gemm_f32out(dqpT, WswT[:, D:], B, Dq, D, transB=1)
             gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
         else:
-            dWqkz = torch.empty(W, D, dtype=torch.float32, device=dev)
             parts = []
-            for src, lo, hi in ((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W)):
-                gemm(dQKZ[:, lo:hi], src, hi - lo, D, M, transA=1, transB=1, C=dWqkz[lo:hi])
+            for src, lo, hi, dst in ((Sq, 0, D, dWq), (Sk, D, 2 * D, dWk), (Sf, 2 * D, W, None)):
+                if dst is not None:
+                    gemm(dQKZ[:, lo:hi], src, D, D, M, transA=1, transB=1, C=dst)
+                else:
+                    for h in range(H):
+                        gemm(dQKZ[:, (2 + h) * D:(3 + h) * D], Sf, D, D, M, transA=1, transB=1,
+                             C=dWo2[:, h * D:(h + 1) * D])
                 parts.append(gemm_f32out(dQKZ[:, lo:hi], WqkzT[lo:hi], M, D, hi - lo, transB=1))
             dSf = torch.empty(M, D, dtype=pc.T, device=dev)
             drop_combine(parts, [drop.a(site0 + 2, drop.p_fc), drop.a(site0 + 3, drop.p_fc), (None, 0, 0.0)], M, D,
@@ -529,8 +593,8 @@ class RelationFn(torch.autograd.Function):
             dqv = torch.empty(B, Dq, dtype=torch.float32, device=dev)
             call("group_rowsum", 0, dVQ[:, D:].data_ptr(), dVQ.stride(0), N, B, G // B, Dq, flags.data_ptr(),
                  dqv.data_ptr())
-        return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWqkz, dbqkz, dbout, dp0, dp1, None, None,
-                None)
+        return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWq, dbq, dWk, dbk, dWo2, dbout, dp0, dp1,
+                None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -543,7 +607,7 @@ class FusionFn(torch.autograd.Function):
     wa [1, dim], ba [1].  Returns att [2BN] and attended [2B, D]."""
 
     @staticmethod
-    def forward(ctx, pc: PC, drop, dims, mode, coefs, X3, Wcg, bcg, We, be, wa, ba):
+    def forward(ctx, pc: PC, drop, dims, mode, coefs, X3, C1, C2, bC2, G1, G2, bG2, We, be, wa, ba):
         lib.require_device()
         B, N, D, dim = dims
         dev = X3.device
@@ -554,8 +618,17 @@ class FusionFn(torch.autograd.Function):
         Xc = torch.empty(M, D, dtype=torch.float32, device=dev)
         CAT = torch.empty(M, 3 * D, dtype=pc.T, device=dev)
         call("combine_diff_fwd", pc.f, X3.data_ptr(), BN, D, mode, c1, c2, c3, Xc.data_ptr(), CAT.data_ptr())
-        WcgT, WeT = to_T(pc, Wcg), to_T(pc, We)
-        bcgc, bec, wac, bac = _f32c(bcg), _f32c(be), _f32c(wa).view(-1), _f32c(ba).view(-1)
+        # [[context2 | context1], [gate2 | gate1]]: one GEMM over CAT[:, :2D] = [X | diff] gives both pre-activations
+        WcgT = torch.empty(2 * D, 2 * D, dtype=pc.T, device=dev)
+        cast_into(pc, C2, WcgT[:D, :D])
+        cast_into(pc, C1, WcgT[:D, D:])
+        cast_into(pc, G2, WcgT[D:, :D])
+        cast_into(pc, G1, WcgT[D:, D:])
+        bcgc = torch.empty(2 * D, dtype=torch.float32, device=dev)
+        call("copy_f32", _f32c(bC2).data_ptr(), D, bcgc.data_ptr(), D, 1, D)
+        call("copy_f32", _f32c(bG2).data_ptr(), D, bcgc[D:].data_ptr(), D, 1, D)
+        WeT = to_T(pc, We)
+        bec, wac, bac = _f32c(be), _f32c(wa).view(-1), _f32c(ba).view(-1)
         pre = gemm_f32out(CAT[:, :2 * D], WcgT, M, 2 * D, 2 * D, bias=bcgc)
         cx = torch.empty(M, D, dtype=pc.T, device=dev)
         gt = torch.empty(M, D, dtype=pc.T, device=dev)
@@ -608,7 +681,8 @@ class FusionFn(torch.autograd.Function):
         gemm(dpre, WcgT, M, 2 * D, 2 * D, transB=1, addend=dCAT[:, :2 * D], C=dCAT[:, :2 * D])
         dX3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         call("combine_diff_bwd", dXc.data_ptr(), dCAT.data_ptr(), BN, D, ctx.mode, c1, c2, c3, dX3.data_ptr())
-        return None, None, None, None, None, dX3, dWcg, dbcg, dWe, dbe, dwa, dba
+        return (None, None, None, None, None, dX3, dWcg[:D, D:], dWcg[:D, :D], dbcg[:D], dWcg[D:, D:], dWcg[D:, :D],
+                dbcg[D:], dWe, dbe, dwa, dba)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -33,7 +33,7 @@ with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     from torch.nn.utils import weight_norm as _weight_norm
 
-from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn
+from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn, WNormFn
 
 
 def _default_precision() -> str:
@@ -49,6 +49,8 @@ def _wn(module: nn.Module) -> nn.Module:
 def wn_weight(lin: nn.Module) -> torch.Tensor:
     """Effective weight of a legacy weight_norm(dim=None) layer: g * v / ||v||_F (fc.py:33-34)."""
     v, g = lin.weight_v, lin.weight_g
+    if v.is_cuda:
+        return WNormFn.apply(v, g)
     return v * (g / v.norm())
 
 
@@ -120,14 +122,6 @@ class GraphSelfAttentionLayer(nn.Module):
                                          kernel_size=(1, 1), groups=self.fc_dim))
         self.linear_out_2 = nn.Linear(self.fc_dim * feat_dim, self.dim[2])
 
-    def qkz_weight(self):
-        """[Wq ; Wk ; Z-blocks] so ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T."""
-        D, H = self.feat_dim, self.num_heads
-        wq = wn_weight(self.query.linear())
-        wk = wn_weight(self.key.linear())
-        wz = self.linear_out_2.weight.view(D, H, D).permute(1, 0, 2).reshape(H * D, D)
-        bz = self.linear_out_2.bias.new_zeros(H * D)
-        return torch.cat([wq, wk, wz], 0), torch.cat([self.query.linear().bias, self.key.linear().bias, bz], 0)
 
     def forward(self, roi_feat, adj_matrix, position_embedding, label_biases_att):
         raise NotImplementedError(
@@ -180,15 +174,16 @@ class GAttNet(nn.Module):
         if self.dir_num != 2:
             raise NotImplementedError("only dir_num == 2 (the reference configuration) is implemented")
         sw = self.self_weights.linear()
-        Wqkz, bqkz = layer.qkz_weight()
+        ql, kl = layer.query.linear(), layer.key.linear()
         if self.pos_emb_dim > 0:
             pp = layer.pair_pos_fc1.linear()
             kind, p0, p1 = "implicit", wn_weight(pp), pp.bias
         else:
             kind, p0, p1 = "explicit", wn_weight(self.bias.linear()), None
         dims = (G, B, N, Kn, D, H)
-        return RelationFn.apply(pc, drop, site0, kind, dims, X, XT, q, wn_weight(sw), sw.bias, Wqkz, bqkz,
-                                layer.linear_out_2.bias, p0, p1, geo0, geo1, g_split)
+        return RelationFn.apply(pc, drop, site0, kind, dims, X, XT, q, wn_weight(sw), sw.bias, wn_weight(ql), ql.bias,
+                                wn_weight(kl), kl.bias, layer.linear_out_2.weight, layer.linear_out_2.bias, p0, p1,
+                                geo0, geo1, g_split)
 
     def forward(self, v_feat, adj_matrix, pos_emb=None):
         if self.pos_emb_dim > 0 and pos_emb is None:
@@ -461,13 +456,12 @@ class ChangeDetector(nn.Module):
                                          drop=gat.make_drop(dev, ov), site0=300)
         mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
         coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
-        Wcg = torch.cat([torch.cat([self.context2.weight, self.context1.weight], 1),
-                         torch.cat([self.gate2.weight, self.gate1.weight], 1)], 0)
-        bcg = torch.cat([self.context2.bias, self.gate2.bias], 0)
         fdrop = Drop(dev, self.training, p_fuse=self.dropout.p if ov is None else ov,
                      p_embed=self.embed[1].p if ov is None else ov)
-        att, attended = FusionFn.apply(pc, fdrop, (B, N, D, self.dim), mode, coefs, X, Wcg, bcg, self.embed[0].weight,
-                                       self.embed[0].bias, self.att.weight, self.att.bias)
+        att, attended = FusionFn.apply(pc, fdrop, (B, N, D, self.dim), mode, coefs, X, self.context1.weight,
+                                       self.context2.weight, self.context2.bias, self.gate1.weight, self.gate2.weight,
+                                       self.gate2.bias, self.embed[0].weight, self.embed[0].bias, self.att.weight,
+                                       self.att.bias)
         BN = B * N
         att_weight_before = att[:BN].view(B, 1, N)
         att_weight_after = att[BN:].view(B, 1, N)

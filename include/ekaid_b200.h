@@ -118,11 +118,14 @@ int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const 
  * dim_t: 8 fp32 wave lengths 1000^(t/8) */
 int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, float* gbias, const uint64_t* seed,
-                        uint32_t site, float p, void* stream);
+                        uint32_t site, float p, float* emb_cache, int fast_trig, void* stream);
 /* part[g, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h] */
 int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
-                        const uint64_t* seed, uint32_t site, float p, void* stream);
+                        const uint64_t* seed, uint32_t site, float p, const float* emb_cache, int fast_trig,
+                        void* stream);
+/* emb_cache (optional, fp32 [G, N*Kn, 64]): the forward stores the (dropped) 64-d embedding of every pair so the
+ * backward does not redo the 32 sincos per pair; fast_trig = 1 uses fp32 sincosf on the fp64 argument (bf16 path). */
 /* QKZ [G*N, ld]: cols [0,D) query, [D,2D) key, [2D + h*D, 2D + (h+1)*D) Z_h.  P [G,N,H,Kn] fp32.
  * scores/sqrt(dh) (+gbias) -> where(cond>0, s, -9e15) + lbias -> softmax over keys
  * (graph_att_layer.py:105-157; Q6).  cond / lbias / gbias may be NULL. */
@@ -184,6 +187,13 @@ int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, in
                     float* dHs, void* stream);
 int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
                         void* stream);
+
+/* ---- legacy weight_norm(dim=None) (models/fc.py:33-34): w = v * g / ||v||_F over the whole tensor -------------- */
+/* workspace: 128 floats; norm_out: 1 float kept for the backward */
+int ekaid_wn_fwd(const float* v, const float* g, int64_t n, float* w, float* norm_out, float* workspace, void* stream);
+/* dv = (g/n) dw - (g <dw,v> / n^3) v ; dg = <dw,v> / n */
+int ekaid_wn_bwd(const float* dw, const float* v, const float* g, const float* norm, int64_t n, float* dv, float* dg,
+                 float* workspace, void* stream);
 
 /* ---- train-mode dropout helpers -------------------------------------------------------------------------- */
 int ekaid_rng_advance(uint64_t* seed, void* stream);
