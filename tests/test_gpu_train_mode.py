@@ -133,7 +133,7 @@ def test_train_mode_gradients_match_finite_differences():
         g = p.grad.detach().clone()
         d = g / (g.norm() + 1e-30)
         analytic = float((g.double() * d.double()).sum())
-        eps = 2e-3 * float(p.detach().norm()) / max(1.0, float(p.numel()) ** 0.5) * float(p.numel()) ** 0.5 * 1e-1
+        eps = max(2e-4 * float(p.detach().norm()), 2e-3)     # large enough that fp32 loss rounding stays < 1 %
         with torch.no_grad():
             p.add_(eps * d)
             lp = float(loss())
