@@ -476,10 +476,14 @@ int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream) {
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
-  // tile-N choice: fewest wasted SM-slots over whole waves, ties to the wider tile
+  // tile-N choice.  Plain fp32 outputs can be split along K, so the widest tile (best flop/byte from L2) wins and
+  // split-K fills the machine; otherwise pick the width that wastes the fewest SM-slots over whole waves.
+  const bool plain_out = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE && !ep.drop.seed;
   int bn = 256;
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
     bn = force_bn;
+  } else if (plain_out && splits != 1 && ek_div_up(K, BK) >= 32 && N >= 128) {
+    bn = N >= 256 ? 256 : 128;
   } else {
     double best = -1;
     const int cand[3] = {256, 128, 64};
@@ -517,7 +521,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
     const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, bn);
     if (plain && tiles * 2 <= num_sms() && num_kb >= 16) {
       splits = (int)(num_sms() / tiles);
-      if (splits > num_kb / 8) splits = num_kb / 8;
+      if (splits > num_kb / 4) splits = num_kb / 4;
       if (splits < 1) splits = 1;
     }
   }

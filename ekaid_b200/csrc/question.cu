@@ -17,12 +17,15 @@ __global__ void embed_gather_kernel(const long long* __restrict__ q, const float
   }
 }
 // demb[v, c] = sum over tokens equal to v of dE[row, c]  (c < ed; the second table is frozen).
-// One CTA per vocabulary row: warp 0 builds the ordered list of matching rows (ballot compaction), then all threads
-// sum those rows.  Deterministic, no atomics.
-__global__ void embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict__ dE, long long ldde,
-                                        int B, int L, int ed, float* __restrict__ demb) {
+// One CTA per (vocabulary row, 32-column chunk): warp 0 builds the ordered list of matching rows (ballot compaction),
+// four row lanes sum interleaved rows, fixed-order combine.  Deterministic, no atomics; the padding token (most of the
+// positions) is spread over ed/32 CTAs instead of serialising one.
+__global__ void __launch_bounds__(128)
+embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict__ dE, long long ldde, int B, int L,
+                        int ed, float* __restrict__ demb) {
   extern __shared__ int rows[];        // up to B*L matching rows
   __shared__ int count;
+  __shared__ float part[4][32];
   const int v = blockIdx.x;
   const int total = B * L;
   if (threadIdx.x < 32) {
@@ -42,11 +45,14 @@ __global__ void embed_gather_bwd_kernel(const long long* __restrict__ q, const f
   }
   __syncthreads();
   const int n = count;
-  for (int c = threadIdx.x; c < ed; c += blockDim.x) {
-    float s = 0.f;
-    for (int k = 0; k < n; ++k) s += dE[(size_t)rows[k] * ldde + c];
-    demb[(size_t)v * ed + c] = s;
-  }
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + lane;
+  float s = 0.f;
+  if (c < ed)
+    for (int k = rl; k < n; k += 4) s += dE[(size_t)rows[k] * ldde + c];
+  part[rl][lane] = s;
+  __syncthreads();
+  if (rl == 0 && c < ed) demb[(size_t)v * ed + c] = ((part[0][lane] + part[1][lane]) + part[2][lane]) + part[3][lane];
 }
 
 // GRU cell (torch.nn.GRU gate order r,z,n).  gi, gh: [B, 3H] (biases included)
@@ -210,7 +216,8 @@ int ek_embed_gather_launch(int is_bf16, const long long* q, const float* emb, co
 }
 int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ldde, int B, int L, int ed, int V,
                                float* demb, cudaStream_t st) {
-  embed_gather_bwd_kernel<<<V, 128, (size_t)B * L * sizeof(int), st>>>(q, dE, ldde, B, L, ed, demb);
+  embed_gather_bwd_kernel<<<dim3(V, ek_div_up(ed, 32)), 128, (size_t)B * L * sizeof(int), st>>>(q, dE, ldde, B, L, ed,
+                                                                                                  demb);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

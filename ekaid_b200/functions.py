@@ -549,17 +549,19 @@ class RelationFn(torch.autograd.Function):
         Dq = qvT.shape[1]
         dbqk = colsum(dQKZ, M, 2 * D)
         dbq, dbk = dbqk[:D], dbqk[D:]
-        dWq = torch.empty(D, D, dtype=torch.float32, device=dev)
-        dWk = torch.empty(D, D, dtype=torch.float32, device=dev)
         dWo2 = torch.empty(D, H * D, dtype=torch.float32, device=dev)
+        if don:
+            dWq = torch.empty(D, D, dtype=torch.float32, device=dev)
+            dWk = torch.empty(D, D, dtype=torch.float32, device=dev)
         dWsw = torch.empty(D, D + Dq, dtype=torch.float32, device=dev)
         dX = torch.empty(M, D, dtype=torch.float32, device=dev)
         if not don:
-            # [query | key | Z] projection: weight gradients land directly in parameter-shaped tensors
-            for dst, lo in ((dWq, 0), (dWk, D)):
-                gemm(dQKZ[:, lo:lo + D], Sf, D, D, M, transA=1, transB=1, C=dst)
+            # [query | key | Z] projection: ONE wgrad GEMM, then the Z blocks are copied into linear_out_2's layout
+            dWqkz = gemm_f32out(dQKZ, Sf, W, D, M, transA=1, transB=1)
+            dWq, dWk = dWqkz[:D], dWqkz[D:2 * D]
             for h in range(H):
-                gemm(dQKZ[:, (2 + h) * D:(3 + h) * D], Sf, D, D, M, transA=1, transB=1, C=dWo2[:, h * D:(h + 1) * D])
+                call("copy_f32", dWqkz[(2 + h) * D:(3 + h) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(),
+                     H * D, D, D)
             dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
             # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
             gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
@@ -573,14 +575,12 @@ class RelationFn(torch.autograd.Function):
             gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
         else:
             parts = []
-            for src, lo, hi, dst in ((Sq, 0, D, dWq), (Sk, D, 2 * D, dWk), (Sf, 2 * D, W, None)):
-                if dst is not None:
-                    gemm(dQKZ[:, lo:hi], src, D, D, M, transA=1, transB=1, C=dst)
-                else:
-                    for h in range(H):
-                        gemm(dQKZ[:, (2 + h) * D:(3 + h) * D], Sf, D, D, M, transA=1, transB=1,
-                             C=dWo2[:, h * D:(h + 1) * D])
+            dWz = torch.empty(H * D, D, dtype=torch.float32, device=dev)
+            for src, lo, hi, dst in ((Sq, 0, D, dWq), (Sk, D, 2 * D, dWk), (Sf, 2 * D, W, dWz)):
+                gemm(dQKZ[:, lo:hi], src, hi - lo, D, M, transA=1, transB=1, C=dst)
                 parts.append(gemm_f32out(dQKZ[:, lo:hi], WqkzT[lo:hi], M, D, hi - lo, transB=1))
+            for h in range(H):
+                call("copy_f32", dWz[h * D:(h + 1) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(), H * D, D, D)
             dSf = torch.empty(M, D, dtype=pc.T, device=dev)
             drop_combine(parts, [drop.a(site0 + 2, drop.p_fc), drop.a(site0 + 3, drop.p_fc), (None, 0, 0.0)], M, D,
                          outT=dSf)
