@@ -54,12 +54,12 @@ int ek_geom_bias_fwd_launch(const double*, const double*, int, const float*, con
 int ek_geom_bias_bwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
                             int, const float*, float*, EkDrop, const float*, int, cudaStream_t);
 int ek_edge_softmax_fwd_launch(int, const void*, long long, int, const float*, const float*, const float*, int, int,
-                               int, int, float*, cudaStream_t);
+                               int, int, float*, void*, cudaStream_t);
 int ek_edge_aggregate_fwd_launch(int, const float*, const void*, long long, int, const float*, const float*, int, int,
-                                 int, int, float*, void*, long long, uint8_t*, EkDrop, cudaStream_t);
+                                 int, int, float*, void*, long long, uint8_t*, EkDrop, const void*, cudaStream_t);
 int ek_edge_num_slices(int D);
 int ek_edge_aggregate_bwd_launch(int, const float*, const uint8_t*, const float*, const void*, long long, int, int, int,
-                                 int, int, void*, float*, float*, float, cudaStream_t);
+                                 int, int, void*, float*, float*, float, const void*, cudaStream_t);
 int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*, long long, int, const float*, int,
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
@@ -183,21 +183,24 @@ int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const
                                  emb_cache, fast_trig, ST);
 }
 int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
-                           const float* gbias, int G, int N, int Kn, int H, float* P, void* stream) {
+                           const float* gbias, int G, int N, int Kn, int H, float* P, void* Phl, void* stream) {
   EK_REQUIRE(D % H == 0 && Kn <= N, EK_ERR_SHAPE, "edge_softmax: D=%d H=%d N=%d Kn=%d", D, H, N, Kn);
-  return ek_edge_softmax_fwd_launch(is_bf16, QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, ST);
+  return ek_edge_softmax_fwd_launch(is_bf16, QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, is_bf16 ? Phl : nullptr,
+                                    ST);
 }
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
-                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, void* stream) {
+                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl,
+                             void* stream) {
   return ek_edge_aggregate_fwd_launch(is_bf16, P, QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, XoutT, ldt, mask,
-                                      mk_drop(seed, site, p), ST);
+                                      mk_drop(seed, site, p), Phl, ST);
 }
 int ekaid_edge_num_slices(int D) { return ek_edge_num_slices(D); }
 int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                              int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
-                             float gscale, void* stream) {
-  return ek_edge_aggregate_bwd_launch(is_bf16, dXout, mask, P, QKZ, ld, D, G, N, Kn, H, dQKZ, dOut, dPpart, gscale, ST);
+                             float gscale, const void* Phl, void* stream) {
+  return ek_edge_aggregate_bwd_launch(is_bf16, dXout, mask, P, QKZ, ld, D, G, N, Kn, H, dQKZ, dOut, dPpart, gscale, Phl,
+                                      ST);
 }
 int ekaid_edge_softmax_bwd(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ, int64_t ld,
                            int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ, float* dlbias_part,

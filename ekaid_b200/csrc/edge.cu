@@ -594,17 +594,19 @@ static int edge_softmax_fwd_t(const T* QKZ, long long ld, int D, const float* co
   return EK_OK;
 }
 int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float* cond, const float* lbias,
-                              const float* gbias, int G, int N, int Kn, int H, float* P, cudaStream_t st);
+                              const float* gbias, int G, int N, int Kn, int H, float* P, bf16* Phl, cudaStream_t st);
 int ek_softmax_bwd_mma_launch(const float* P, const float* dPpart, int nslices, const bf16* QKZ, long long ld, int D,
                               const float* cond, int G, int N, int Kn, int H, bf16* dQKZ, float* dlbias_part,
                               float* dgbias, cudaStream_t st);
 
 int ek_edge_softmax_fwd_launch(int is_bf16, const void* QKZ, long long ld, int D, const float* cond,
                                const float* lbias, const float* gbias, int G, int N, int Kn, int H, float* P,
-                               cudaStream_t st) {
+                               void* Phl, cudaStream_t st) {
   if (is_bf16) {
-    const int rc = ek_softmax_fwd_mma_launch((const bf16*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, st);
+    const int rc = ek_softmax_fwd_mma_launch((const bf16*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, (bf16*)Phl,
+                                             st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
+    if (Phl) { ek_set_error("edge_softmax: bf16 planes requested but the tensor-core kernel does not take this shape"); return EK_ERR_UNSUPPORTED; }
   }
   return is_bf16 ? edge_softmax_fwd_t<bf16>((const bf16*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, st)
                  : edge_softmax_fwd_t<float>((const float*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, st);
@@ -629,17 +631,17 @@ static int edge_aggregate_fwd_t(const float* P, const T* QKZ, long long ld, int 
 }
 int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
                           int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
-                          EkDrop dr, cudaStream_t st);
+                          EkDrop dr, const bf16* Phl, cudaStream_t st);
 int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
                           int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, float gscale,
-                          cudaStream_t st);
+                          const bf16* Phl, cudaStream_t st);
 
 int ek_edge_aggregate_fwd_launch(int is_bf16, const float* P, const void* QKZ, long long ld, int D, const float* b_out,
                                  const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT,
-                                 long long ldt, uint8_t* mask, EkDrop dr, cudaStream_t st) {
+                                 long long ldt, uint8_t* mask, EkDrop dr, const void* Phl, cudaStream_t st) {
   if (is_bf16) {   // tensor-core kernel (edge_mma.cu); SIMT template only for shapes it does not take
     const int rc = ek_agg_fwd_mma_launch(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT, ldt,
-                                         mask, dr, st);
+                                         mask, dr, (const bf16*)Phl, st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
   }
   return is_bf16 ? edge_aggregate_fwd_t<bf16>(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT,
@@ -669,10 +671,10 @@ static int edge_aggregate_bwd_t(const float* dXout, const uint8_t* mask, const f
 }
 int ek_edge_aggregate_bwd_launch(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                                  long long ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut,
-                                 float* dPpart, float gscale, cudaStream_t st) {
+                                 float* dPpart, float gscale, const void* Phl, cudaStream_t st) {
   if (is_bf16) {
     const int rc = ek_agg_bwd_mma_launch(dXout, mask, P, (const bf16*)QKZ, ld, D, G, N, Kn, H, (bf16*)dQKZ, dOut,
-                                         dPpart, gscale, st);
+                                         dPpart, gscale, (const bf16*)Phl, st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
   }
   return is_bf16 ? edge_aggregate_bwd_t<bf16>(dXout, mask, P, (const bf16*)QKZ, ld, D, G, N, Kn, H, (bf16*)dQKZ, dOut,

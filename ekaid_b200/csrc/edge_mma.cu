@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256)
 agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, long long ld, int D,
                    const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                    float* __restrict__ Xout, bf16* __restrict__ XoutT, long long ldt, uint8_t* __restrict__ mask,
-                   int kchunk, EkDrop dr) {
+                   int kchunk, EkDrop dr, const bf16* __restrict__ Phl, long long plane) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const unsigned long long sd = ek_seed(dr);
   const int PS = kchunk + 8;                        // P row pitch (elements)
@@ -84,13 +84,33 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
       const int kc_pad = (kc + 15) & ~15;
       __syncthreads();
       load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0);
-      for (int e = tid; e < MR * kc_pad; e += 256) {
-        const int i = e / kc_pad, kk = e % kc_pad;
-        float p = 0.f;
-        if (r0 + i < N && kk < kc) p = P[((size_t)g * N + r0 + i) * HK + k0 + kk];
-        const bf16 hi = __float2bfloat16_rn(p);
-        Phi[i * PS + kk] = hi;
-        Plo[i * PS + kk] = __float2bfloat16_rn(p - __bfloat162float(hi));
+      if (Phl) {
+        // attention weights pre-split into bf16 hi/lo planes by the softmax kernel: pure async copies
+        const int cpr = kc_pad / 8;                  // 16-byte chunks per row
+        for (int e = tid; e < 2 * MR * cpr; e += 256) {
+          const int pl = e / (MR * cpr), rem = e % (MR * cpr);
+          const int i = rem / cpr, ch = rem % cpr;
+          bf16* dst = (pl ? Plo : Phi) + i * PS + ch * 8;
+          if (r0 + i < N && ch * 8 < kc)             // HK % 8 == 0 (checked by the launcher): chunks never straddle kc
+            cp_async16(dst, Phl + pl * plane + ((size_t)g * N + r0 + i) * HK + k0 + ch * 8);
+          else
+            *(uint4*)dst = make_uint4(0, 0, 0, 0);
+        }
+      } else {
+        for (int i = warp; i < MR; i += 8) {         // one row per warp pass: all loads of a row are independent
+          const bool rok = r0 + i < N;
+          const float* Pr = P + ((size_t)g * N + r0 + i) * HK + k0;
+#pragma unroll
+          for (int r = 0; r < MAXCH / 32; ++r) {
+            const int kk = lane + 32 * r;
+            if (kk < kc_pad) {
+              const float p = (rok && kk < kc) ? Pr[kk] : 0.f;
+              const bf16 hi = __float2bfloat16_rn(p);
+              Phi[i * PS + kk] = hi;
+              Plo[i * PS + kk] = __float2bfloat16_rn(p - __bfloat162float(hi));
+            }
+          }
+        }
       }
       cp_async_wait_all();
       __syncthreads();
@@ -158,7 +178,8 @@ template <int MR>   // padded query rows (all of them are staged): 64 or 128
 __global__ void __launch_bounds__(256)
 agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ mask, const float* __restrict__ P,
                    const bf16* __restrict__ QKZ, long long ld, int D, int N, int Kn, int H, bf16* __restrict__ dQKZ,
-                   float* __restrict__ dOut, float* __restrict__ dPpart, int kchunk, float gscale) {
+                   float* __restrict__ dOut, float* __restrict__ dPpart, int kchunk, float gscale,
+                   const bf16* __restrict__ Phl) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int PS = kchunk + 8;
   bf16* dOs = (bf16*)smraw;                         // [MR][ZS]   dout tile (i, c)
@@ -169,6 +190,7 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int HK = H * Kn;
   // dout = 2 * mask * dX  -> global (fp32, for the b_out column sum) and shared (bf16 operand)
+#pragma unroll 4
   for (int e = tid; e < MR * (NC / 4); e += 256) {
     const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -192,11 +214,24 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
     const int kc_pad = (kc + 15) & ~15;
     __syncthreads();
     load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0);
-    for (int e = tid; e < MR * kc_pad; e += 256) {
-      const int i = e / kc_pad, kk = e % kc_pad;
-      float p = 0.f;
-      if (i < N && kk < kc) p = P[((size_t)g * N + i) * HK + k0 + kk];
-      Ps[i * PS + kk] = __float2bfloat16_rn(p);
+    if (Phl) {
+      const int cpr = kc_pad / 8;
+      for (int e = tid; e < MR * cpr; e += 256) {
+        const int i = e / cpr, ch = e % cpr;
+        bf16* dst = Ps + i * PS + ch * 8;
+        if (i < N && ch * 8 < kc) cp_async16(dst, Phl + ((size_t)g * N + i) * HK + k0 + ch * 8);
+        else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+      }
+    } else {
+      for (int i = warp; i < MR; i += 8) {
+        const bool rok = i < N;
+        const float* Pr = P + ((size_t)g * N + i) * HK + k0;
+#pragma unroll
+        for (int r = 0; r < MAXCH / 32; ++r) {
+          const int kk = lane + 32 * r;
+          if (kk < kc_pad) Ps[i * PS + kk] = __float2bfloat16_rn((rok && kk < kc) ? Pr[kk] : 0.f);
+        }
+      }
     }
     cp_async_wait_all();
     __syncthreads();
@@ -296,7 +331,7 @@ template <int NT>   // 8-column key tiles held per warp: 8 (Kn <= 64) or 16 (Kn 
 __global__ void __launch_bounds__(256)
 softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond,
                        const float* __restrict__ lbias, const float* __restrict__ gbias, int N, int Kn, int H,
-                       float* __restrict__ P, int MR) {
+                       float* __restrict__ P, int MR, bf16* __restrict__ Phl, long long plane) {
   extern __shared__ __align__(16) uint8_t smraw[];
   const int g = blockIdx.x, h = blockIdx.y;
   const int dh = D / H;
@@ -381,7 +416,16 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int j = nt * 8 + 2 * (lane & 3) + c;
-          if (j < Kn) Pr[j] = acc[nt][2 * hh + c] * inv;
+          if (j < Kn) {
+            const float pv = acc[nt][2 * hh + c] * inv;
+            Pr[j] = pv;
+            if (Phl) {      // bf16 hi + lo planes for the aggregation kernels (16 significant bits)
+              const bf16 hi = __float2bfloat16_rn(pv);
+              const size_t o = (((size_t)g * N + i) * H + h) * Kn + j;
+              Phl[o] = hi;
+              Phl[plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+            }
+          }
         }
     }
   }
@@ -525,12 +569,14 @@ int set_smem(K kern, size_t smem, size_t& configured, const char* what) {
 // returns EK_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the SIMT template)
 int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
                           int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
-                          EkDrop dr, cudaStream_t st) {
+                          EkDrop dr, const bf16* Phl, cudaStream_t st) {
   if ((D % 8) || (ld % 8) || (ldt % 2) || ((uintptr_t)QKZ & 15)) return EK_ERR_UNSUPPORTED;
   const int HK = H * Kn;
   const int HKp = (HK + 15) & ~15;
   const int kchunk = HKp < MAXCH ? HKp : MAXCH;
   const int MR = N <= 64 ? 64 : 128;
+  if (Phl && ((HK % 8) || ((uintptr_t)Phl & 15))) Phl = nullptr;      // planes need 16-byte-aligned rows
+  const long long plane = (long long)G * N * HK;
   const size_t smem = ((size_t)kchunk * ZS + 2 * (size_t)MR * (kchunk + 8)) * sizeof(bf16);
   dim3 grid(G, ek_div_up(D, NC));
   static size_t c64 = 0, c128 = 0;
@@ -538,12 +584,12 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
     int rc = set_smem(agg_fwd_mma_kernel<64>, smem, c64, "agg_fwd_mma");
     if (rc) return rc;
     agg_fwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
-                                                    dr);
+                                                    dr, Phl, plane);
   } else {
     int rc = set_smem(agg_fwd_mma_kernel<128>, smem, c128, "agg_fwd_mma");
     if (rc) return rc;
     agg_fwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
-                                                     dr);
+                                                     dr, Phl, plane);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -551,8 +597,9 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
 
 int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
                           int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, float gscale,
-                          cudaStream_t st) {
+                          const bf16* Phl, cudaStream_t st) {
   if ((D % 8) || (ld % 8) || ((uintptr_t)QKZ & 15) || ((uintptr_t)dQKZ & 3) || N > 128) return EK_ERR_UNSUPPORTED;
+  if (Phl && (((H * Kn) % 8) || ((uintptr_t)Phl & 15))) Phl = nullptr;
   const int HK = H * Kn;
   const int HKp = (HK + 15) & ~15;
   const int kchunk = HKp < MAXCH ? HKp : MAXCH;
@@ -564,19 +611,20 @@ int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* 
     int rc = set_smem(agg_bwd_mma_kernel<64>, smem, c64, "agg_bwd_mma");
     if (rc) return rc;
     agg_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
-                                                    gscale);
+                                                    gscale, Phl);
   } else {
     int rc = set_smem(agg_bwd_mma_kernel<128>, smem, c128, "agg_bwd_mma");
     if (rc) return rc;
     agg_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
-                                                     gscale);
+                                                     gscale, Phl);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 
 int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float* cond, const float* lbias,
-                              const float* gbias, int G, int N, int Kn, int H, float* P, cudaStream_t st) {
+                              const float* gbias, int G, int N, int Kn, int H, float* P, bf16* Phl, cudaStream_t st) {
+  const long long plane = (long long)G * N * H * Kn;
   if ((D % H) || ((D / H) % 16) || (ld % 8) || ((uintptr_t)QKZ & 15) || N > 128 || Kn > 128) return EK_ERR_UNSUPPORTED;
   const int dh = D / H;
   const int MR = ((N + 15) / 16) * 16;
@@ -587,11 +635,11 @@ int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float*
   if (NT == 8) {
     int rc = set_smem(softmax_fwd_mma_kernel<8>, smem, c8, "softmax_fwd_mma");
     if (rc) return rc;
-    softmax_fwd_mma_kernel<8><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR);
+    softmax_fwd_mma_kernel<8><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
   } else {
     int rc = set_smem(softmax_fwd_mma_kernel<16>, smem, c16, "softmax_fwd_mma");
     if (rc) return rc;
-    softmax_fwd_mma_kernel<16><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR);
+    softmax_fwd_mma_kernel<16><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;

@@ -482,18 +482,22 @@ class RelationFn(torch.autograd.Function):
             ctx.geo = (a0, a1, Wp, bp, emb_cache)
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
         es = 2 if pc.bf16 else 4
+        # bf16 path: P also as bf16 hi/lo planes, staged by the aggregation kernels with async 16-byte copies
+        Phl = None
+        if pc.bf16 and (H * Kn) % 8 == 0 and N <= 128 and (D // H) % 16 == 0:
+            Phl = torch.empty(2, G, N, H * Kn, dtype=torch.bfloat16, device=dev)
         call("edge_softmax_fwd", pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond), ptr(lbias), ptr(gbias), G, N, Kn, H,
-             P.data_ptr(), info={"bytes": G * ((N + Kn) * D * es + N * H * Kn * 4 + N * Kn * 4 * (2 if cond is not None else H))})
+             P.data_ptr(), ptr(Phl), info={"bytes": G * ((N + Kn) * D * es + N * H * Kn * 4 + N * Kn * 4 * (2 if cond is not None else H))})
         Xn = torch.empty(M, D, dtype=torch.float32, device=dev)
         XnT = torch.empty(M, D, dtype=pc.T, device=dev) if pc.bf16 else None
         mask = torch.empty(M, D, dtype=torch.uint8, device=dev)
         call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, boutc.data_ptr(), X.data_ptr(),
              G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr(),
-             *(drop.a(site0 + 5, drop.p_gat) if don else (None, 0, 0.0)),
+             *(drop.a(site0 + 5, drop.p_gat) if don else (None, 0, 0.0)), ptr(Phl),
              info={"bytes": G * (N * H * Kn * 4 + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
         ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
         ctx.drop, ctx.site0 = drop, site0
-        ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask)
+        ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask, Phl)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append(mask.bool().cpu())
         if XnT is not None:
@@ -506,7 +510,7 @@ class RelationFn(torch.autograd.Function):
     def backward(ctx, dXn, _dXnT, _dP):
         pc, kind = ctx.pc, ctx.kind
         G, B, N, Kn, D, H = ctx.dims
-        XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask = ctx.saved
+        XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask, Phl = ctx.saved
         drop, site0 = ctx.drop, ctx.site0
         don = drop is not None and drop.on
         dev = P.device
@@ -521,7 +525,7 @@ class RelationFn(torch.autograd.Function):
         es = 2 if pc.bf16 else 4
         call("edge_aggregate_bwd", pc.f, dXn.data_ptr(), mask.data_ptr(), P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D,
              G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr(),
-             2.0 / (1.0 - drop.p_gat) if don else 2.0,
+             2.0 / (1.0 - drop.p_gat) if don else 2.0, ptr(Phl),
              info={"bytes": G * (N * D * (4 + 1 + 4) + N * H * Kn * 4 * (1 + ns) + 2 * Kn * H * D * es)})
         dbout = colsum(dOut, M, D)
         dlb = dgb = None

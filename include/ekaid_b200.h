@@ -130,18 +130,20 @@ int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const
  * scores/sqrt(dh) (+gbias) -> where(cond>0, s, -9e15) + lbias -> softmax over keys
  * (graph_att_layer.py:105-157; Q6).  cond / lbias / gbias may be NULL. */
 int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
-                           const float* gbias, int G, int N, int Kn, int H, float* P, void* stream);
+                           const float* gbias, int G, int N, int Kn, int H, float* P, void* Phl, void* stream);
+/* Phl (optional, bf16 path only, needs H*Kn % 8 == 0): [2, G, N, H*Kn] bf16 = P split into hi and lo planes, which the
+ * aggregation kernels stage with 16-byte async copies (pass the same pointer to edge_aggregate_fwd/bwd, or NULL). */
 /* out = sum_h P_h Z_h + b_out;  Xout = Xin + relu(2 out);  mask = (out > 0)
  * (graph_att_layer.py:164-176 re-associated per Q3, graph_att.py:95-104 (Q2), relation_encoder.py:81,129 (Q1)).
  * XoutT: optional copy of Xout in the operand type with pitch ldt (may be NULL). */
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
-                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, void* stream);
+                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl, void* stream);
 int ekaid_edge_num_slices(int D);
 /* dOut [G*N, D] = gscale*mask*dXout (gscale = 2/(1-p)); dQKZ[:, 2D:] = dZ; dPpart [slices, G,N,H,Kn] */
 int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                              int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
-                             float gscale, void* stream);
+                             float gscale, const void* Phl, void* stream);
 /* dQKZ[:, 0:2D] = (dQ, dK); dlbias_part [H, G,N,Kn] and dgbias [G,N,Kn,H] may be NULL */
 int ekaid_edge_softmax_bwd(int is_bf16, const float* P, const float* dPpart, int nslices, const void* QKZ, int64_t ld,
                            int D, const float* cond, int G, int N, int Kn, int H, void* dQKZ, float* dlbias_part,
