@@ -315,6 +315,16 @@ def main():
         if info:
             d["flops"] += info.get("flops", 0.0)
             d["bytes"] += info.get("bytes", 0.0)
+    shapes = {}
+    for name, a, b_, info in prof:
+        if name == "gemm_bf16" and info:
+            d = shapes.setdefault(info["shape"], {"ms": 0.0, "n": 0, "flops": 0.0})
+            d["ms"] += a.elapsed_time(b_)
+            d["n"] += 1
+            d["flops"] += info["flops"]
+    gemm_shapes = [{"MNK_tAtB": list(k), "launches_per_step": v["n"] / nprof, "us_per_launch": 1e3 * v["ms"] / v["n"],
+                    "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / nprof}
+                   for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:14]]
     tot_ms = sum(d["ms"] for d in agg.values())
     top = max(agg.items(), key=lambda kv: kv[1]["ms"])
     pk, pk_kind = peaks()
@@ -344,7 +354,8 @@ def main():
             "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "cuda_graph": use_graph, "roofline": roof, "kernel_time_share_pct": breakdown}
+            "gpu_launches": launches, "cuda_graph": use_graph, "roofline": roof, "kernel_time_share_pct": breakdown,
+            "gemm_shapes": gemm_shapes}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
