@@ -64,7 +64,7 @@ int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
 int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
-int ek_gru_cell_fwd_launch(int, const float*, const float*, const float*, int, int, float*, void*, float*,
+int ek_gru_cell_fwd_launch(int, const float*, float*, const float*, int, int, float*, void*, float*, const float*,
                            cudaStream_t);
 int ek_gru_cell_bwd_launch(int, const float*, const float*, const float*, int, int, float*, float*, void*, void*,
                            float*, cudaStream_t);
@@ -265,9 +265,9 @@ int ekaid_embed_gather_bwd(const int64_t* q, const float* dE, int64_t ldde, int 
                            void* stream) {
   return ek_embed_gather_bwd_launch((const long long*)q, dE, ldde, B, L, ed, V, demb, ST);
 }
-int ekaid_gru_cell_fwd(int is_bf16, const float* gi, const float* gh, const float* hprev, int B, int H, float* h,
-                       void* hT, float* gates, void* stream) {
-  return ek_gru_cell_fwd_launch(is_bf16, gi, gh, hprev, B, H, h, hT, gates, ST);
+int ekaid_gru_cell_fwd(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h, void* hT,
+                       float* gates, const float* gh_reset, void* stream) {
+  return ek_gru_cell_fwd_launch(is_bf16, gi, gh, hprev, B, H, h, hT, gates, gh_reset, ST);
 }
 int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H, float* dgi,
                        float* dgh, void* dgiT, void* dghT, float* dhprev, void* stream) {

@@ -476,14 +476,25 @@ int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream) {
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
-  // tile-N choice.  Plain fp32 outputs can be split along K, so the widest tile (best flop/byte from L2) wins and
-  // split-K fills the machine; otherwise pick the width that wastes the fewest SM-slots over whole waves.
-  const bool plain_out = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE && !ep.drop.seed;
+  // Split-K candidates: plain fp32 outputs, or "C += A B" (addend aliases C, nothing else in the epilogue) where the
+  // partial sums are reduced straight onto the existing values.
+  const bool acc_alias = ep.addend && ep.addend == ep.C && ep.ldadd == ep.ldc;
+  const bool plain_out = ep.C && !ep.Cb && !ep.bias && (!ep.addend || acc_alias) && !ep.rowb &&
+                         ep.act == EK_ACT_NONE && !ep.drop.seed;
+  const int nkb = ek_div_up(K, BK);
   int bn = 256;
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
     bn = force_bn;
-  } else if (plain_out && splits != 1 && ek_div_up(K, BK) >= 32 && N >= 128) {
-    bn = N >= 256 ? 256 : 128;
+  } else if (plain_out && splits != 1 && nkb >= 16 && N >= 64) {
+    // widest tile (best flop/byte from L2) whose tiles x possible splits still fill the machine
+    const int cand[3] = {256, 128, 64};
+    bn = 64;
+    for (int i = 0; i < 3; ++i) {
+      const int c = cand[i];
+      if (c > 64 && N < c) continue;
+      const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, c);
+      if (tiles * (nkb / 4) >= (long long)(0.85 * num_sms()) || tiles >= num_sms()) { bn = c; break; }
+    }
   } else {
     double best = -1;
     const int cand[3] = {256, 128, 64};
@@ -513,29 +524,32 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   if (ep.bias && ((uintptr_t)ep.bias & 15)) vec_ok &= ~2;
   if (ep.addend && (((uintptr_t)ep.addend & 15) || (ep.ldadd & 3))) vec_ok &= ~4;
   if (ep.rowb && (((uintptr_t)ep.rowb & 15) || (ep.ldrowb & 3) || ((uintptr_t)ep.rowb_alt & 15))) vec_ok &= ~8;
-  // split-K (auto when splits == 0): only for plain fp32 outputs with too few tiles to fill the chip
-  const bool plain = ep.C && !ep.Cb && !ep.bias && !ep.addend && !ep.rowb && ep.act == EK_ACT_NONE && !ep.drop.seed;
-  const int num_kb = ek_div_up(K, BK);
+  // split-K (auto when splits == 0): too few tiles to fill the chip and a splittable epilogue
+  const int num_kb = nkb;
   if (splits <= 0) {
     splits = 1;
     const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, bn);
-    if (plain && tiles * 2 <= num_sms() && num_kb >= 16) {
+    if (plain_out && tiles * 2 <= num_sms() && num_kb >= 16) {
       splits = (int)(num_sms() / tiles);
       if (splits > num_kb / 4) splits = num_kb / 4;
       if (splits < 1) splits = 1;
     }
   }
+  EkEpilogue epk = ep;
   if (splits > 1) {
-    EK_REQUIRE(plain, EK_ERR_UNSUPPORTED, "gemm_tc: split-K needs a plain fp32 epilogue");
+    EK_REQUIRE(plain_out, EK_ERR_UNSUPPORTED, "gemm_tc: split-K needs a plain fp32 (or C += AB) epilogue");
     const int kb_per = ek_div_up(num_kb, splits);
     splits = ek_div_up(num_kb, kb_per);        // no empty splits
     if (splits > 1) {
-      cudaError_t e = cudaMemset2DAsync(ep.C, (size_t)ep.ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
-      EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: memset failed: %s", cudaGetErrorString(e));
+      if (!acc_alias) {
+        cudaError_t e = cudaMemset2DAsync(ep.C, (size_t)ep.ldc * 4, 0, (size_t)N * 4, (size_t)M, stream);
+        EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: memset failed: %s", cudaGetErrorString(e));
+      }
+      epk.addend = nullptr;                    // partial sums are atomically added onto C (zeroed or pre-existing)
     }
   }
-  if (!transA && !transB) return launch_bn<0, 0>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
-  if (!transA && transB) return launch_bn<0, 1>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
-  if (transA && !transB) return launch_bn<1, 0>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
-  return launch_bn<1, 1>(bn, ta, tb, M, N, K, ep, vec_ok, splits, stream);
+  if (!transA && !transB) return launch_bn<0, 0>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  if (!transA && transB) return launch_bn<0, 1>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  if (transA && !transB) return launch_bn<1, 0>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  return launch_bn<1, 1>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
 }

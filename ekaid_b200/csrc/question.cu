@@ -59,17 +59,22 @@ embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict
 //   r = s(gi_r + gh_r), z = s(gi_z + gh_z), n = tanh(gi_n + r*gh_n), h = (1-z)*n + z*hprev
 // saves (r, z, n, gh_n) in gates [B, 4H]
 template <typename T>
-__global__ void gru_cell_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+__global__ void gru_cell_fwd_kernel(const float* __restrict__ gi, float* __restrict__ gh,
                                     const float* __restrict__ hprev, int B, int H, float* __restrict__ h,
-                                    T* __restrict__ hT, float* __restrict__ gates) {
+                                    T* __restrict__ hT, float* __restrict__ gates, const float* __restrict__ gh_reset) {
   const int total = B * H;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int b = e / H, c = e % H;
     const float* gib = gi + (size_t)b * 3 * H;
-    const float* ghb = gh + (size_t)b * 3 * H;
+    float* ghb = gh + (size_t)b * 3 * H;
     const float r = sigmoidf_(gib[c] + ghb[c]);
     const float z = sigmoidf_(gib[H + c] + ghb[H + c]);
     const float ghn = ghb[2 * H + c];
+    if (gh_reset) {      // re-arm the accumulator of the next step's split-K GEMM with the bias b_hh
+      ghb[c] = gh_reset[c];
+      ghb[H + c] = gh_reset[H + c];
+      ghb[2 * H + c] = gh_reset[2 * H + c];
+    }
     const float n = tanhf(gib[2 * H + c] + r * ghn);
     const float hp = hprev ? hprev[e] : 0.f;
     const float hv = (1.f - z) * n + z * hp;
@@ -221,10 +226,14 @@ int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ld
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
-int ek_gru_cell_fwd_launch(int is_bf16, const float* gi, const float* gh, const float* hprev, int B, int H, float* h,
-                           void* hT, float* gates, cudaStream_t st) {
-  if (is_bf16) gru_cell_fwd_kernel<bf16><<<grid_for((long long)B * H), 256, 0, st>>>(gi, gh, hprev, B, H, h, (bf16*)hT, gates);
-  else gru_cell_fwd_kernel<float><<<grid_for((long long)B * H), 256, 0, st>>>(gi, gh, hprev, B, H, h, (float*)hT, gates);
+int ek_gru_cell_fwd_launch(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h,
+                           void* hT, float* gates, const float* gh_reset, cudaStream_t st) {
+  if (is_bf16)
+    gru_cell_fwd_kernel<bf16><<<grid_for((long long)B * H), 256, 0, st>>>(gi, gh, hprev, B, H, h, (bf16*)hT, gates,
+                                                                           gh_reset);
+  else
+    gru_cell_fwd_kernel<float><<<grid_for((long long)B * H), 256, 0, st>>>(gi, gh, hprev, B, H, h, (float*)hT, gates,
+                                                                            gh_reset);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

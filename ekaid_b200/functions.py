@@ -299,12 +299,16 @@ class QuestionFn(torch.autograd.Function):
         # operand-type copy with one leading zero block: HsT[t] = h_{t-1}, so "previous h of every step" is a view
         HsT = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev)
         gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
+        # gh accumulator: armed with b_hh (broadcast copy), "gh += h W_hh^T" as a split-K GEMM (M = B is tiny, so the
+        # K loop is what can be spread over the SMs), re-armed by the cell kernel
         gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
+        call("copy_f32", bhhc.data_ptr(), 0, gh.data_ptr(), 3 * H, B, 3 * H)
         for t in range(L):
-            gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, bias=bhhc, C=gh)
+            gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, addend=gh, C=gh)
             hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
             call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
-                 Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr())
+                 Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr(),
+                 bhhc.data_ptr())
         HsT_cur = HsT[B:]
         if drop is not None and drop.on:          # Dropout(0.2) on the input of W1 (language_model.py:123-124)
             Hd = torch.empty(L * B, H, dtype=pc.T, device=dev)
@@ -359,17 +363,17 @@ class QuestionFn(torch.autograd.Function):
         dgiT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgi
         dghT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgh
         carry = torch.empty(B, H, dtype=torch.float32, device=dev)
-        dhz = torch.empty(B, H, dtype=torch.float32, device=dev)
         for t in range(L - 1, -1, -1):
             sl = slice(t * B, (t + 1) * B)
             if t < L - 1:
                 call("add_inplace", dHs[sl].data_ptr(), carry.data_ptr(), B * H)
             hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+            # the cell kernel writes dh*z into `carry`; the split-K GEMM then adds dgh W_hh onto it
             call("gru_cell_bwd", pc.f, dHs[sl].data_ptr(), gates[t].data_ptr(), ptr(hprev), B, H, dgi[sl].data_ptr(),
                  dgh[sl].data_ptr(), dgiT[sl].data_ptr() if pc.bf16 else None,
-                 dghT[sl].data_ptr() if pc.bf16 else None, dhz.data_ptr())
+                 dghT[sl].data_ptr() if pc.bf16 else None, carry.data_ptr())
             if t > 0:
-                gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=dhz, C=carry)   # carry = dh*z + dgh W_hh
+                gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=carry, C=carry)   # carry = dh*z + dgh W_hh
         dWih = gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1)
         dbih = colsum(dgi, L * B, 3 * H)
         dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1)

@@ -175,9 +175,10 @@ int ekaid_embed_gather(int is_bf16, const int64_t* q, const float* emb, const fl
                        void* E, void* stream);
 int ekaid_embed_gather_bwd(const int64_t* q, const float* dE, int64_t ldde, int B, int L, int ed, int V, float* demb,
                            void* stream);
-/* one GRU step (:106-115): gi, gh [B,3H] incl. biases; gates [B,4H] saves (r,z,n,gh_n) */
-int ekaid_gru_cell_fwd(int is_bf16, const float* gi, const float* gh, const float* hprev, int B, int H, float* h,
-                       void* hT, float* gates, void* stream);
+/* one GRU step (:106-115): gi, gh [B,3H] incl. biases; gates [B,4H] saves (r,z,n,gh_n).  gh_reset (optional, [3H]):
+ * after use gh is overwritten with it, so the next step's split-K "gh += h W_hh^T" GEMM starts from the bias */
+int ekaid_gru_cell_fwd(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h, void* hT,
+                       float* gates, const float* gh_reset, void* stream);
 int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H, float* dgi,
                        float* dgh, void* dgiT, void* dghT, float* dhprev, void* stream);
 /* out[m] = A[m,:] . w + b[0]   (W2_self_att_q, :142) */
