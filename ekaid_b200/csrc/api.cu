@@ -90,6 +90,7 @@ static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
   r.drop.site = e->drop_site;
   r.drop.p = e->drop_p;
   r.dropN = e->drop_n;
+  r.dropOff = e->drop_off;
   r.C = e->C;
   r.ldc = e->ldc;
   r.Cb = (bf16*)e->Cb;

@@ -4,7 +4,7 @@
 
 enum EkAct { EK_ACT_NONE = 0, EK_ACT_RELU = 1, EK_ACT_TANH = 2, EK_ACT_SIGMOID = 3 };
 
-// v = acc (+ bias[n]) (+ addend[m,n]) (+ rowflag[m] ? rowb_alt[n] : rowb[(m / rowb_div) % rowb_mod, n]);
+// v = (acc (+ bias[n])) * dropout(m,n) (+ addend[m,n]) (+ rowflag[m] ? rowb_alt[n] : rowb[(m / rowb_div) % rowb_mod, n]);
 // v = act(v); C[m,n] = v (fp32, optional); Cb[m,n] = bf16(v) (optional)
 struct EkEpilogue {
   const float* bias;
@@ -17,8 +17,9 @@ struct EkEpilogue {
   const uint8_t* rowflag;
   const float* rowb_alt;
   int act;
-  EkDrop drop;        // applied to (acc + bias + ...) BEFORE the activation, element index m*dropN + n
+  EkDrop drop;        // applied to (acc + bias), before addend / row-broadcast / activation; index m*dropN + dropOff + n
   int dropN;
+  int dropOff;
   float* C;
   long long ldc;
   bf16* Cb;
@@ -38,12 +39,12 @@ __device__ __forceinline__ float ek_act(float v, int act) {
 __device__ __forceinline__ void ek_epilogue_store(const EkEpilogue& e, long long m, int n, float acc) {
   float v = acc;
   if (e.bias) v += __ldg(e.bias + n);
+  if (e.drop.seed) v *= ek_drop_mult(e.drop, ek_seed(e.drop), (unsigned long long)m * e.dropN + e.dropOff + n);
   if (e.addend) v += e.addend[m * e.ldadd + n];
   if (e.rowb) {
     if (e.rowflag && e.rowflag[m]) v += __ldg(e.rowb_alt + n);
     else v += __ldg(e.rowb + (long long)((m / e.rowb_div) % e.rowb_mod) * e.ldrowb + n);
   }
-  if (e.drop.seed) v *= ek_drop_mult(e.drop, ek_seed(e.drop), (unsigned long long)m * e.dropN + n);
   v = ek_act(v, e.act);
   if (e.C) e.C[m * e.ldc + n] = v;
   if (e.Cb) e.Cb[m * e.ldcb + n] = __float2bfloat16_rn(v);

@@ -290,6 +290,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + nb + j);
             }
           }
+          if (ep.drop.seed) {
+            const unsigned long long sd = ek_seed(ep.drop);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] *= ek_drop_mult(ep.drop, sd, (unsigned long long)m * ep.dropN + ep.dropOff + nb + j);
+          }
           if (ep.addend) {
             const float* ap = ep.addend + m * ep.ldadd + nb;
             if (vec_ok & 4) {
@@ -314,11 +320,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] += __ldg(rowb_ptr + nb + j);
             }
-          }
-          if (ep.drop.seed) {
-            const unsigned long long sd = ek_seed(ep.drop);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= ek_drop_mult(ep.drop, sd, (unsigned long long)m * ep.dropN + nb + j);
           }
           if (ep.act != EK_ACT_NONE) {
 #pragma unroll

@@ -100,7 +100,10 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
     ep.rowb_alt = ptr(rowb_alt)
     ep.act = act
     if drop is not None and drop[2] > 0.0:
-        ep.drop_seed, ep.drop_site, ep.drop_p, ep.drop_n = drop[0], drop[1], drop[2], N
+        # drop = (seed, site, p[, row pitch of the mask index, column offset])
+        ep.drop_seed, ep.drop_site, ep.drop_p = drop[0], drop[1], drop[2]
+        ep.drop_n = drop[3] if len(drop) > 3 else N
+        ep.drop_off = drop[4] if len(drop) > 4 else 0
     ep.C = ptr(C)
     ep.ldc = C.stride(0) if C is not None else 0
     ep.Cb = ptr(Cb)
@@ -594,13 +597,13 @@ class RelationFn(torch.autograd.Function):
                          outT=dSf)
             gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
             dbsw = colsum(dSf, M, D)
-            dVQ = gemm_f32out(dSf, WswT, M, D + Dq, D, transB=1)
-            drop_combine([dVQ], [drop.a(site0 + 1, drop.p_fc)], M, D + Dq, outf=dVQ)     # mask in place
-            call("copy_f32", dXn.data_ptr(), D, dX.data_ptr(), D, M, D)
-            drop_combine([dVQ[:, :D]], [(None, 0, 0.0)], M, D, outf=dX, accumulate=1)   # residual + masked grad
+            # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
+            # (index = row * (D + Dq) + column); the node half also adds the residual gradient
+            s1 = drop.a(site0 + 1, drop.p_fc)
+            gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX, drop=s1 + (D + Dq, 0))
+            dVq = gemm_f32out(dSf, WswT[:, D:], M, Dq, D, transB=1, drop=s1 + (D + Dq, D))
             dqv = torch.empty(B, Dq, dtype=torch.float32, device=dev)
-            call("group_rowsum", 0, dVQ[:, D:].data_ptr(), dVQ.stride(0), N, B, G // B, Dq, flags.data_ptr(),
-                 dqv.data_ptr())
+            call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(), dqv.data_ptr())
         return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWq, dbq, dWk, dbk, dWo2, dbout, dp0, dp1,
                 None, None, None)
 

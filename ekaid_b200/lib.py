@@ -24,7 +24,8 @@ class Epilogue(ctypes.Structure):
         ("rowb", ctypes.c_void_p), ("ldrowb", ctypes.c_int64), ("rowb_div", ctypes.c_int32),
         ("rowb_mod", ctypes.c_int32), ("rowflag", ctypes.c_void_p), ("rowb_alt", ctypes.c_void_p),
         ("act", ctypes.c_int32), ("drop_seed", ctypes.c_void_p), ("drop_site", ctypes.c_uint32),
-        ("drop_p", ctypes.c_float), ("drop_n", ctypes.c_int32), ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
+        ("drop_p", ctypes.c_float), ("drop_n", ctypes.c_int32), ("drop_off", ctypes.c_int32),
+        ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
         ("Cb", ctypes.c_void_p), ("ldcb", ctypes.c_int64),
     ]
 

@@ -37,7 +37,7 @@ extern "C" {
 #define EKAID_ACT_TANH 2
 #define EKAID_ACT_SIGMOID 3
 
-/* Fused GEMM epilogue:  v = acc (+ bias[n]) (+ addend[m,n])
+/* Fused GEMM epilogue:  v = (acc (+ bias[n])) * dropout (+ addend[m,n])
  *                           (+ rowflag[m] ? rowb_alt[n] : rowb[(m / rowb_div) % rowb_mod, n]);  v = act(v);
  *                       C[m,n] = v (fp32, may be NULL);  Cb[m,n] = bf16(v) (may be NULL).
  * rowb/rowflag implement q_expand_v_cat (models/relation_encoder.py:19-29, quirk Q10) without materialising
@@ -53,12 +53,14 @@ typedef struct ekaid_epilogue {
   const uint8_t* rowflag;
   const float* rowb_alt;
   int32_t act;
-  /* train-mode dropout applied BEFORE the activation (embed: Linear -> Dropout(0.5) -> ReLU, modules.py:105-111):
-   * element (m,n) uses counter m*drop_n + n of site drop_site; drop_seed = device pointer to the step seed, NULL = off */
+  /* train-mode dropout applied to (acc + bias), before addend / row broadcast / activation (embed: Linear ->
+   * Dropout(0.5) -> ReLU, modules.py:105-111; masked dgrad of a dropped GEMM input): element (m,n) uses counter
+   * m*drop_n + drop_off + n of site drop_site; drop_seed = device pointer to the step seed, NULL = off */
   const uint64_t* drop_seed;
   uint32_t drop_site;
   float drop_p;
   int32_t drop_n;
+  int32_t drop_off;
   float* C;
   int64_t ldc;
   void* Cb; /* __nv_bfloat16* */
