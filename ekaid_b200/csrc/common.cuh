@@ -94,3 +94,16 @@ __device__ __forceinline__ float ek_drop_mult(const EkDrop& d, unsigned long lon
   return ek_rand32(seedv, d.site, idx) >= thr ? 1.f / (1.f - d.p) : 0.f;
 }
 __device__ __forceinline__ unsigned long long ek_seed(const EkDrop& d) { return d.seed ? *d.seed : 0ull; }
+// four independent 16-bit lanes from one 64-bit draw: multipliers of elements 4*group .. 4*group+3 (p resolved to 2^-16)
+__device__ __forceinline__ void ek_drop_mult4(const EkDrop& d, unsigned long long seedv, unsigned long long group,
+                                              float out[4]) {
+  if (d.seed == nullptr || d.p <= 0.f) { out[0] = out[1] = out[2] = out[3] = 1.f; return; }
+  unsigned long long z = seedv + (unsigned long long)d.site * 0x9E3779B97F4A7C15ull + group * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const unsigned int thr = (unsigned int)(d.p * 65536.0f);
+  const float keep = 1.f / (1.f - d.p);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out[k] = ((unsigned int)(z >> (16 * k)) & 0xFFFFu) >= thr ? keep : 0.f;
+}

@@ -94,6 +94,12 @@ __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __re
   for (int h = 0; h < MAXH; ++h) f[h] = (h < H) ? bp[h] : 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    // train mode: Dropout(0.2) on the 64-d embedding before pair_pos_fc1 (fc.py:25-32); one 64-bit draw per 4 elements
+    float ms[8], mc[8];
+    ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 0, ms);
+    ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 1, ms + 4);
+    ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 2, mc);
+    ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 3, mc + 4);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const double a = (100.0 * g[q]) / (double)dim_t[t];
@@ -106,10 +112,9 @@ __device__ __forceinline__ void pair_pos_fc(const double g[4], const float* __re
       } else {
         sincos(a, &sv, &cv);
       }
-      // reference casts the fp64 embedding to fp32 (graph_att_layer.py:115); train mode: Dropout(0.2) on the
-      // 64-d embedding before pair_pos_fc1 (fc.py:25-32), element index pair*64 + k
-      const float s = (float)sv * ek_drop_mult(dr, seedv, pair_idx * 64 + q * 16 + t);
-      const float c = (float)cv * ek_drop_mult(dr, seedv, pair_idx * 64 + q * 16 + 8 + t);
+      // reference casts the fp64 embedding to fp32 (graph_att_layer.py:115)
+      const float s = (float)sv * ms[t];
+      const float c = (float)cv * mc[t];
       if (emb_out) { emb_out[q * 16 + t] = s; emb_out[q * 16 + 8 + t] = c; }
 #pragma unroll
       for (int h = 0; h < MAXH; ++h)

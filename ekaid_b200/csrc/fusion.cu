@@ -287,40 +287,69 @@ template <typename T>
 __global__ void build_vq_kernel(const float* __restrict__ X, const float* __restrict__ qv,
                                 const uint8_t* __restrict__ flags, long long M, int N, int B, int D, int Dq,
                                 T* __restrict__ VQ, EkDrop dr) {
+  // 8 consecutive columns per thread (D, Dq multiples of 8): one row lookup, 2 x 16-byte loads, one 16-byte store
   const int W = D + Dq;
-  const long long total = M * W;
+  const int W8 = W / 8;
+  const long long total = M * W8;
   const unsigned long long sd = ek_seed(dr);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const long long m = e / W;
-    const int c = (int)(e % W);
-    float v;
-    if (c < D) v = X[m * D + c];
-    else v = flags[m] ? 0.f : qv[(size_t)((m / N) % B) * Dq + (c - D)];
-    VQ[e] = from_f32<T>(v * ek_drop_mult(dr, sd, e));
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / W8;
+    const int c = (int)(t % W8) * 8;
+    float v[8];
+    if (c < D) {
+      const float4 a = *(const float4*)(X + m * D + c), b = *(const float4*)(X + m * D + c + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if (flags[m]) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    } else {
+      const float* q = qv + (size_t)((m / N) % B) * Dq + (c - D);
+      const float4 a = *(const float4*)q, b = *(const float4*)(q + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    const unsigned long long e0 = (unsigned long long)m * W + c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] *= ek_drop_mult(dr, sd, e0 + k);
+    T* dst = VQ + m * W + c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = from_f32<T>(v[k]);
   }
 }
 // out = sum_k mult_k(idx) * in_k   (k < nin <= 3; mult_k = 1 when site k has p = 0);  idx = m*C + c
 // optional fp32 output (optionally accumulated into) and/or operand-type output
-template <typename TI, typename TO>
+template <typename TI, typename TO, int V>
 __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const TI* __restrict__ in1,
                                     const TI* __restrict__ in2, long long ldi, EkDrop d0, EkDrop d1, EkDrop d2,
                                     long long M, int C, float* __restrict__ outf, long long ldf, int accumulate,
                                     TO* __restrict__ outT, long long ldo) {
-  const long long total = M * C;
+  // V consecutive columns per thread (V = 4 needs C, pitches % 4 == 0; the compiler merges the accesses)
+  const int CV = C / V;
+  const long long total = M * CV;
   const unsigned long long s0 = ek_seed(d0), s1 = ek_seed(d1), s2 = ek_seed(d2);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const long long m = e / C;
-    const int c = (int)(e % C);
-    float v = to_f32<TI>(in0[m * ldi + c]) * ek_drop_mult(d0, s0, e);
-    if (nin > 1) v += to_f32<TI>(in1[m * ldi + c]) * ek_drop_mult(d1, s1, e);
-    if (nin > 2) v += to_f32<TI>(in2[m * ldi + c]) * ek_drop_mult(d2, s2, e);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / CV;
+    const int c = (int)(t % CV) * V;
+    const unsigned long long e0 = (unsigned long long)m * C + c;
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = to_f32<TI>(in0[m * ldi + c + k]) * ek_drop_mult(d0, s0, e0 + k);
+    if (nin > 1)
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in1[m * ldi + c + k]) * ek_drop_mult(d1, s1, e0 + k);
+    if (nin > 2)
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in2[m * ldi + c + k]) * ek_drop_mult(d2, s2, e0 + k);
     if (outf) {
-      if (accumulate) v += outf[m * ldf + c];
-      outf[m * ldf + c] = v;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (accumulate) v[k] += outf[m * ldf + c + k];
+        outf[m * ldf + c + k] = v[k];
+      }
     }
-    if (outT) outT[m * ldo + c] = from_f32<TO>(v);
+    if (outT) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) outT[m * ldo + c + k] = from_f32<TO>(v[k]);
+    }
   }
 }
 // ---------------------------------------------------------------- legacy weight_norm(dim=None) (fc.py:33-34)
@@ -330,7 +359,12 @@ __global__ void wn_partial_kernel(const float* __restrict__ a, const float* __re
                                   float* __restrict__ part) {     // part[blk] = sum a*b over the block's slice
   __shared__ float red[32];
   float s = 0.f;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+  const long long n4 = ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) ? n / 4 : 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 x = ((const float4*)a)[e], y = ((const float4*)b)[e];
+    s = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, s))));
+  }
+  for (long long e = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
     s = fmaf(a[e], b[e], s);
   s = block_sum(s, red);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
@@ -511,27 +545,38 @@ int ek_adam_advance_launch(float* pow_state, float b1, float b2, cudaStream_t st
 
 int ek_build_vq_launch(int is_bf16, const float* X, const float* qv, const uint8_t* flags, long long M, int N, int B,
                        int D, int Dq, void* VQ, EkDrop dr, cudaStream_t st) {
-  if (is_bf16) build_vq_kernel<bf16><<<grid_for(M * (D + Dq)), 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
-  else build_vq_kernel<float><<<grid_for(M * (D + Dq)), 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
+  EK_REQUIRE(D % 8 == 0 && Dq % 8 == 0, EK_ERR_SHAPE, "build_vq: D=%d Dq=%d must be multiples of 8", D, Dq);
+  const int g = grid_for(M * ((D + Dq) / 8));
+  if (is_bf16) build_vq_kernel<bf16><<<g, 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
+  else build_vq_kernel<float><<<g, 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
+}
+template <int V>
+static void drop_combine_dispatch(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
+                                  long long ldi, EkDrop d0, EkDrop d1, EkDrop d2, long long M, int C, float* outf,
+                                  long long ldf, int accumulate, void* outT, long long ldo, cudaStream_t st) {
+  const int g = grid_for(M * (C / V));
+  if (in_bf16 && out_bf16)
+    drop_combine_kernel<bf16, bf16, V><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
+                                                         d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
+  else if (in_bf16)
+    drop_combine_kernel<bf16, float, V><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
+                                                          d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
+  else if (out_bf16)
+    drop_combine_kernel<float, bf16, V><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1, (const float*)in2,
+                                                          ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
+  else
+    drop_combine_kernel<float, float, V><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1,
+                                                           (const float*)in2, ldi, d0, d1, d2, M, C, outf, ldf,
+                                                           accumulate, (float*)outT, ldo);
 }
 int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
                            long long ldi, EkDrop d0, EkDrop d1, EkDrop d2, long long M, int C, float* outf,
                            long long ldf, int accumulate, void* outT, long long ldo, cudaStream_t st) {
-  const int g = grid_for(M * C);
-  if (in_bf16 && out_bf16)
-    drop_combine_kernel<bf16, bf16><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi, d0,
-                                                      d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
-  else if (in_bf16)
-    drop_combine_kernel<bf16, float><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
-                                                       d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
-  else if (out_bf16)
-    drop_combine_kernel<float, bf16><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1, (const float*)in2,
-                                                       ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
-  else
-    drop_combine_kernel<float, float><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1, (const float*)in2,
-                                                        ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
+  const bool v4 = (C % 4 == 0) && (ldi % 4 == 0) && (!outf || ldf % 4 == 0) && (!outT || ldo % 4 == 0);
+  if (v4) drop_combine_dispatch<4>(in_bf16, out_bf16, nin, in0, in1, in2, ldi, d0, d1, d2, M, C, outf, ldf, accumulate, outT, ldo, st);
+  else drop_combine_dispatch<1>(in_bf16, out_bf16, nin, in0, in1, in2, ldi, d0, d1, d2, M, C, outf, ldf, accumulate, outT, ldo, st);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
