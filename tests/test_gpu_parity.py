@@ -319,3 +319,48 @@ def test_error_behaviour():
     bad[2] = bad[2][:, :40]                     # adjacency with the wrong node count
     with pytest.raises(ValueError):
         m(*bad)
+
+
+def test_full_size_batch64_forward_and_consistency():
+    """BASELINE.json configs[1] size (batch 64 x 52 nodes x 1024-d): both precision paths against the CPU oracle
+    (forward, a few seconds of CPU), run-to-run determinism of the fp32 path, and the size-independent property that
+    the relation encoders treat images independently given the question vector (rows of a sub-batch are unchanged)."""
+    from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B, N = 64, 52
+    meta = dict(graph="all", nongt_dim=52, empty_image=False, B=B, N=N)
+    sd = synthetic_state_dict(spec_for("all"), 1238)
+    b = synthetic_batch(B, N, seed=4321)
+    inp = (b[0], b[1], O.process_matrix(b[6], N, 11), O.process_matrix(b[7], N, 11), O.process_matrix(b[8], N, 3),
+           O.process_matrix(b[9], N, 3), b[10], b[11], b[12])
+    with torch.no_grad():
+        ref = oracle_forward(sd, inp, meta)
+    outs = {}
+    for precision in ("fp32", "bf16"):
+        m = build_model(meta, sd, precision, dev)
+        with torch.no_grad():
+            outs[precision] = m(*to_dev(inp, dev))
+            again = m(*to_dev(inp, dev))
+        for k, o, r in zip(OUT_NAMES[1:5], outs[precision][1:5], ref[1:5]):
+            assert rel_err(o, r) < TOL[precision], (precision, k, rel_err(o, r))
+        if precision == "fp32":
+            assert all(torch.equal(x, y) for x, y in zip(outs[precision], again))       # deterministic
+    assert rel_err(outs["fp32"][5], ref[5]) < 1e-4
+    scale = max(float(ref[3].abs().max()), float(ref[4].abs().max()))
+    assert float((outs["bf16"][5].cpu() - ref[5]).abs().max()) / scale < 2e-2
+    # image independence of one relation step given q: first 8 samples alone == first 8 rows of the full batch
+    from ekaid_b200.modules import ExplicitRelationEncoder
+    with contextlib.redirect_stdout(io.StringIO()):
+        enc = ExplicitRelationEncoder(1024, 1024, 1024, 2, 11, num_heads=4, nongt_dim=52, label_bias=False)
+    enc.load_state_dict({k[len("spatial_relation."):]: t for k, t in sd.items() if k.startswith("spatial_relation.")})
+    enc.to(dev).eval()
+    enc.precision = "fp32"
+    g = torch.Generator().manual_seed(1)
+    v = torch.randn(B, N, 1024, generator=g).to(dev)
+    q = torch.randn(B, 1024, generator=g).to(dev)
+    adj = inp[2].to(dev)
+    with torch.no_grad():
+        full, _ = enc(v.clone(), adj, q)
+        part, _ = enc(v[:8].clone(), adj[:8], q[:8])
+    assert torch.equal(full[:8], part)
