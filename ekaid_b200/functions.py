@@ -29,6 +29,21 @@ ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 DEBUG_SINK = None
 
 
+# Gradient slots (step.FlatAdam): {parameter data_ptr: preallocated fp32 gradient view in the flat gradient buffer}.
+# When a parameter has a slot, the backward kernels write its gradient straight into the slot and hand that tensor to
+# autograd, whose AccumulateGrad adopts it without a copy (the parameter's .grad must be None at backward time) -- no
+# per-parameter "grad += new" kernels and no gradient memset.  Empty dict = plain autograd behaviour.
+GRAD_SLOTS = {}
+
+
+def _dst(key_ptr, shape, dev):
+    """Destination of a parameter gradient: its slot when registered, else a fresh tensor."""
+    slot = GRAD_SLOTS.get(key_ptr) if GRAD_SLOTS else None
+    if slot is not None and tuple(slot.shape) == tuple(shape):
+        return slot
+    return torch.empty(shape, dtype=torch.float32, device=dev)
+
+
 _rng_state = {}
 
 
@@ -164,9 +179,10 @@ def _workspace(dev, n):
     return ws
 
 
-def colsum(src, M, N, rowscale=None):
+def colsum(src, M, N, rowscale=None, out=None):
     """out[n] = sum_m rowscale[m] * src[m, n]  (fp32 result)."""
-    out = torch.empty(N, dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=src.device)
     ws = torch.empty(64 * N, dtype=torch.float32, device=src.device)
     call("colsum", 1 if src.dtype == torch.bfloat16 else 0, src.data_ptr(), src.stride(0) if src.dim() == 2 else 1,
          M, N, ptr(rowscale), out.data_ptr(), ws.data_ptr())
@@ -197,18 +213,19 @@ class WNormFn(torch.autograd.Function):
         call("wn_fwd", vc.data_ptr(), gc.data_ptr(), vc.numel(), w.data_ptr(), norm.data_ptr(), ws.data_ptr())
         ctx.saved = (vc, gc, norm)
         ctx.gshape = g.shape
+        ctx.keys = (v.data_ptr(), g.data_ptr())
         return w
 
     @staticmethod
     def backward(ctx, dw):
         vc, gc, norm = ctx.saved
         dwc = _f32c(dw)
-        dv = torch.empty_like(vc)
-        dg = torch.empty(1, dtype=torch.float32, device=vc.device)
+        dv = _dst(ctx.keys[0], vc.shape, vc.device)
+        dg = _dst(ctx.keys[1], ctx.gshape, vc.device)
         ws = torch.empty(128, dtype=torch.float32, device=vc.device)
         call("wn_bwd", dwc.data_ptr(), vc.data_ptr(), gc.data_ptr(), norm.data_ptr(), vc.numel(), dv.data_ptr(),
              dg.data_ptr(), ws.data_ptr())
-        return dv, dg.reshape(ctx.gshape)
+        return dv, dg
 
 
 def cast_into(pc: PC, src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -252,6 +269,7 @@ class LinearFn(torch.autograd.Function):
         yT = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if pc.bf16 else None
         gemm(xT, WT, M, N, K, bias=bb, C=y, Cb=yT)
         ctx.pc, ctx.xT, ctx.WT, ctx.has_b = pc, xT, WT, b is not None
+        ctx.keys = (W.data_ptr(), b.data_ptr() if b is not None else 0)
         ctx.need = (x.requires_grad, x2 is not None and x2.requires_grad)
         ctx.shapes = (x.shape, x2.shape if x2 is not None else None, Ma)
         if yT is not None:
@@ -265,8 +283,8 @@ class LinearFn(torch.autograd.Function):
         M, N = dy2.shape
         K = ctx.xT.shape[1]
         dyT = to_T(pc, dy2)
-        dW = gemm_f32out(dyT, ctx.xT, N, K, M, transA=1, transB=1)
-        db = colsum(dy2, M, N) if ctx.has_b else None
+        dW = gemm_f32out(dyT, ctx.xT, N, K, M, transA=1, transB=1, out=_dst(ctx.keys[0], (N, K), dy2.device))
+        db = colsum(dy2, M, N, out=_dst(ctx.keys[1], (N,), dy2.device)) if ctx.has_b else None
         dx = dx2 = None
         if ctx.need[0] or ctx.need[1]:
             dfull = gemm_f32out(dyT, ctx.WT, M, K, N, transB=1)
@@ -327,6 +345,8 @@ class QuestionFn(torch.autograd.Function):
         if drop is not None and drop.on:          # self.drop on the pooled vector (language_model.py:155)
             drop_combine([qv], [drop.a(11, drop.p_qv)], B, H, outf=qv)
         ctx.pc, ctx.drop = pc, drop
+        ctx.keys = {k: t.data_ptr() for k, t in (("emb", emb), ("Wih", Wih), ("Whh", Whh), ("bih", bih), ("bhh", bhh),
+                                                 ("b1", b1), ("b2", b2))}
         ctx.dims = (B, L, ed, H, emb.shape[0])
         ctx.saved = (q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd)
         return qv
@@ -351,10 +371,11 @@ class QuestionFn(torch.autograd.Function):
              dHs.data_ptr())
         dpre = torch.empty(L * B, H, dtype=pc.T, device=dev)
         call("qatt_tanh_bwd", pc.f, da.data_ptr(), w2c.data_ptr(), a1.data_ptr(), L * B, H, dpre.data_ptr())
+        kk = ctx.keys
         dw2 = colsum(a1, L * B, H, rowscale=da).view(1, H)
-        db2 = colsum(da.view(-1, 1), L * B, 1)
+        db2 = colsum(da.view(-1, 1), L * B, 1, out=_dst(kk["b2"], (1,), dev))
         dW1 = gemm_f32out(dpre, Hd, H, H, L * B, transA=1, transB=1)
-        db1 = colsum(dpre, L * B, H)
+        db1 = colsum(dpre, L * B, H, out=_dst(kk["b1"], (H,), dev))
         if don:
             tmp = gemm_f32out(dpre, W1T, L * B, H, H, transB=1)
             drop_combine([tmp], [drop.a(10, drop.p_fc)], L * B, H, outf=dHs, accumulate=1)
@@ -377,12 +398,12 @@ class QuestionFn(torch.autograd.Function):
                  dghT[sl].data_ptr() if pc.bf16 else None, carry.data_ptr())
             if t > 0:
                 gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=carry, C=carry)   # carry = dh*z + dgh W_hh
-        dWih = gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1)
-        dbih = colsum(dgi, L * B, 3 * H)
-        dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1)
-        dbhh = colsum(dgh, L * B, 3 * H)
+        dWih = gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=_dst(kk["Wih"], (3 * H, 2 * ed), dev))
+        dbih = colsum(dgi, L * B, 3 * H, out=_dst(kk["bih"], (3 * H,), dev))
+        dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1, out=_dst(kk["Whh"], (3 * H, H), dev))
+        dbhh = colsum(dgh, L * B, 3 * H, out=_dst(kk["bhh"], (3 * H,), dev))
         dE = gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1)           # only the trainable table's columns
-        demb = torch.empty(V, ed, dtype=torch.float32, device=dev)
+        demb = _dst(kk["emb"], (V, ed), dev)
         call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr())
         return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
 
@@ -504,6 +525,8 @@ class RelationFn(torch.autograd.Function):
              info={"bytes": G * (N * H * Kn * 4 + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
         ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
         ctx.drop, ctx.site0 = drop, site0
+        ctx.keys = {k: (t.data_ptr() if t is not None else 0) for k, t in (("bsw", bsw), ("bq", bq), ("bk", bk),
+                                                                          ("Wo2", Wo2), ("bout", bout), ("p1", p1))}
         ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask, Phl)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append(mask.bool().cpu())
@@ -534,7 +557,8 @@ class RelationFn(torch.autograd.Function):
              G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr(),
              2.0 / (1.0 - drop.p_gat) if don else 2.0, ptr(Phl),
              info={"bytes": G * (N * D * (4 + 1 + 4) + N * H * Kn * 4 * (1 + ns) + 2 * Kn * H * D * es)})
-        dbout = colsum(dOut, M, D)
+        kk = ctx.keys
+        dbout = colsum(dOut, M, D, out=_dst(kk["bout"], (D,), dev))
         dlb = dgb = None
         if kind == "explicit":
             dlb = torch.empty(H, G, N, Kn, dtype=torch.float32, device=dev)
@@ -556,11 +580,13 @@ class RelationFn(torch.autograd.Function):
                  _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr(),
                  *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)), ptr(emb_cache), pc.f)
             tot = colsum(part, G, H * 65).view(H, 65)
-            dp0, dp1 = tot[:, :64].contiguous(), tot[:, 64].contiguous()
+            dp0 = tot[:, :64].contiguous()
+            dp1 = _dst(kk["p1"], (H,), dev)
+            dp1.copy_(tot[:, 64])
         Dq = qvT.shape[1]
-        dbqk = colsum(dQKZ, M, 2 * D)
-        dbq, dbk = dbqk[:D], dbqk[D:]
-        dWo2 = torch.empty(D, H * D, dtype=torch.float32, device=dev)
+        dbq = colsum(dQKZ[:, :D], M, D, out=_dst(kk["bq"], (D,), dev))
+        dbk = colsum(dQKZ[:, D:2 * D], M, D, out=_dst(kk["bk"], (D,), dev))
+        dWo2 = _dst(kk["Wo2"], (D, H * D), dev)
         if don:
             dWq = torch.empty(D, D, dtype=torch.float32, device=dev)
             dWk = torch.empty(D, D, dtype=torch.float32, device=dev)
@@ -576,7 +602,7 @@ class RelationFn(torch.autograd.Function):
             dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
             # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
             gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
-            dbsw = colsum(dSf, M, D)
+            dbsw = colsum(dSf, M, D, out=_dst(kk["bsw"], (D,), dev))
             dqpart = torch.empty(B, D, dtype=torch.float32, device=dev)
             call("group_rowsum", pc.f, dSf.data_ptr(), dSf.stride(0), N, B, G // B, D, flags.data_ptr(),
                  dqpart.data_ptr())
@@ -596,7 +622,7 @@ class RelationFn(torch.autograd.Function):
             drop_combine(parts, [drop.a(site0 + 2, drop.p_fc), drop.a(site0 + 3, drop.p_fc), (None, 0, 0.0)], M, D,
                          outT=dSf)
             gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
-            dbsw = colsum(dSf, M, D)
+            dbsw = colsum(dSf, M, D, out=_dst(kk["bsw"], (D,), dev))
             # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
             # (index = row * (D + Dq) + column); the node half also adds the residual gradient
             s1 = drop.a(site0 + 1, drop.p_fc)
@@ -655,6 +681,8 @@ class FusionFn(torch.autograd.Function):
         call("att_pool_fwd", E.data_ptr(), M, N, D, dim, wac.data_ptr(), bac.data_ptr(), Xc.data_ptr(), att.data_ptr(),
              attended.data_ptr())
         ctx.pc, ctx.dims, ctx.mode, ctx.coefs, ctx.drop = pc, dims, mode, coefs, drop
+        ctx.keys = {k: t.data_ptr() for k, t in (("C1", C1), ("C2", C2), ("bC2", bC2), ("G1", G1), ("G2", G2),
+                                                 ("bG2", bG2), ("We", We), ("be", be), ("wa", wa), ("ba", ba))}
         ctx.saved = (Xc, CAT, WcgT, WeT, wac, cx, gt, E, att)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append((E > 0).cpu())
@@ -679,21 +707,30 @@ class FusionFn(torch.autograd.Function):
         call("att_pool_bwd", pc.f, dA.data_ptr(), ptr(dw_), att.data_ptr(), Xc.data_ptr(), E.data_ptr(), wac.data_ptr(),
              M, N, D, dim, dXc.data_ptr(), dE.data_ptr(), dpa.data_ptr(),
              1.0 / (1.0 - drop.p_embed) if don else 1.0)
-        dwa = colsum(E, M, dim, rowscale=dpa).view(1, dim)
-        dba = colsum(dpa.view(-1, 1), M, 1)
-        dWe = gemm_f32out(dE, CAT, dim, 3 * D, M, transA=1, transB=1)
-        dbe = colsum(dE, M, dim)
+        kk = ctx.keys
+        dwa = _dst(kk["wa"], (1, dim), dev)
+        colsum(E, M, dim, rowscale=dpa, out=dwa.view(dim))
+        dba = colsum(dpa.view(-1, 1), M, 1, out=_dst(kk["ba"], (1,), dev))
+        dWe = gemm_f32out(dE, CAT, dim, 3 * D, M, transA=1, transB=1, out=_dst(kk["We"], (dim, 3 * D), dev))
+        dbe = colsum(dE, M, dim, out=_dst(kk["be"], (dim,), dev))
         dCAT = gemm_f32out(dE, WeT, M, 3 * D, dim, transB=1)
         dpre = torch.empty(M, 2 * D, dtype=pc.T, device=dev)
         call("gate_bwd", pc.f, dCAT.data_ptr(), cx.data_ptr(), gt.data_ptr(), M, D, dpre.data_ptr(),
              drop.seed if don else None, 20, 21, drop.p_fuse if don else 0.0)
         dWcg = gemm_f32out(dpre, CAT[:, :2 * D], 2 * D, 2 * D, M, transA=1, transB=1)
-        dbcg = colsum(dpre, M, 2 * D)
+        # blocks of the fused [[context2 | context1], [gate2 | gate1]] gradient -> parameter-shaped (contiguous) tensors
+        blocks = {}
+        for name, r0, c0 in (("C2", 0, 0), ("C1", 0, D), ("G2", D, 0), ("G1", D, D)):
+            dstb = _dst(kk[name], (D, D), dev)
+            call("copy_f32", dWcg[r0:r0 + D, c0:c0 + D].data_ptr(), 2 * D, dstb.data_ptr(), D, D, D)
+            blocks[name] = dstb
+        dbC2 = colsum(dpre[:, :D], M, D, out=_dst(kk["bC2"], (D,), dev))
+        dbG2 = colsum(dpre[:, D:], M, D, out=_dst(kk["bG2"], (D,), dev))
         gemm(dpre, WcgT, M, 2 * D, 2 * D, transB=1, addend=dCAT[:, :2 * D], C=dCAT[:, :2 * D])
         dX3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         call("combine_diff_bwd", dXc.data_ptr(), dCAT.data_ptr(), BN, D, ctx.mode, c1, c2, c3, dX3.data_ptr())
-        return (None, None, None, None, None, dX3, dWcg[:D, D:], dWcg[:D, :D], dbcg[:D], dWcg[D:, D:], dWcg[D:, :D],
-                dbcg[D:], dWe, dbe, dwa, dba)
+        return (None, None, None, None, None, dX3, blocks["C1"], blocks["C2"], dbC2, blocks["G1"], blocks["G2"], dbG2, dWe,
+                dbe, dwa, dba)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ from typing import Callable, Optional, Sequence
 
 import torch
 
-from . import lib
+from . import functions, lib
 from .functions import onehot_adj, rng_advance
 from .modules import ChangeDetector
 
@@ -35,17 +35,32 @@ class FlatAdam:
         self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.pow_state = torch.ones(2, dtype=torch.float32, device=dev)
         off = 0
+        self.slots = []
         for p in params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
-            p.grad = self.grad[off:off + k].view(p.shape)
+            slot = self.grad[off:off + k].view(p.shape)
+            self.slots.append(slot)
+            p.grad = None
+            # the backward kernels write this parameter's gradient straight into its slot (functions.GRAD_SLOTS)
+            functions.GRAD_SLOTS[p.data_ptr()] = slot
             off += (k + al - 1) // al * al
         self.params = params
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self._checked = 0
 
     def zero_grad(self):
-        self.grad.zero_()
+        """set_to_none semantics: every live slot is fully overwritten by the next backward, so no memset is needed and
+        autograd adopts the slot tensors instead of launching one `grad += new` kernel per parameter."""
+        for p in self.params:
+            p.grad = None
+
+    def check_slots(self):
+        """After a backward: every gradient autograd holds must BE its slot (otherwise Adam would miss it)."""
+        for p, slot in zip(self.params, self.slots):
+            if p.grad is not None and p.grad.data_ptr() != slot.data_ptr():
+                raise RuntimeError("gradient of a parameter of shape %s did not land in its flat slot" % (tuple(p.shape),))
 
     def step(self):
         lib.call("adam_advance", self.pow_state.data_ptr(), self.betas[0], self.betas[1])
@@ -139,6 +154,9 @@ class GraphFusionStep:
             rng_advance(self.opt.flat.device)      # fresh dropout masks (a kernel: replays draw new masks too)
         total = self.loss(inputs, labels, masks)
         total.backward()
+        if self.opt._checked < 2 and not torch.cuda.is_current_stream_capturing():
+            self.opt.check_slots()
+            self.opt._checked += 1
         if self.pg is not None:
             allreduce_mean_(self.opt.grad, self.pg)
         self.opt.step()
