@@ -40,7 +40,8 @@ def _dst(key_ptr, shape, dev):
     """Destination of a parameter gradient: its slot when registered, else a fresh tensor."""
     slot = GRAD_SLOTS.get(key_ptr) if GRAD_SLOTS else None
     if slot is not None and tuple(slot.shape) == tuple(shape):
-        return slot
+        # a FRESH view object: AccumulateGrad only adopts a gradient nobody else references (use_count == 1)
+        return slot.view(slot.shape)
     return torch.empty(shape, dtype=torch.float32, device=dev)
 
 

@@ -54,13 +54,17 @@ def _worker(rank, world, port, outfile):
     names = {id(p): k for k, p in cd.named_parameters()}
     grads = _rank_grads(rank, world, sd)
     opt.zero_grad()
-    for p in live:
+    from ekaid_b200 import functions
+    assert len(functions.GRAD_SLOTS) == len(live)
+    opt.grad.zero_()
+    for p, slot in zip(opt.params, opt.slots):
         k = names[id(p)]
-        assert p.grad.data_ptr() >= opt.grad.data_ptr() and p.data_ptr() % 256 == opt.flat.data_ptr() % 256
+        assert slot.data_ptr() >= opt.grad.data_ptr() and p.data_ptr() % 256 == opt.flat.data_ptr() % 256
+        assert functions.GRAD_SLOTS[p.data_ptr()] is slot and slot.shape == p.shape
         if k in grads:
-            p.grad.copy_(grads[k])
+            slot.copy_(grads[k])
     allreduce_mean_(opt.grad)
-    out = {names[id(p)]: p.grad.clone() for p in live if names[id(p)] in grads}
+    out = {names[id(p)]: slot.clone() for p, slot in zip(opt.params, opt.slots) if names[id(p)] in grads}
     stats = {"n_live": len(live), "numel": int(sum(p.numel() for p in live)),
              "dead_with_grad": [k for k in grads if k not in out]}
     if rank == 0:
