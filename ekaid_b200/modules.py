@@ -33,6 +33,7 @@ with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     from torch.nn.utils import weight_norm as _weight_norm
 
+from . import lib as _lib
 from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn, WNormFn
 
 
@@ -163,7 +164,21 @@ class GAttNet(nn.Module):
             p_fc = p_gat = override
         return Drop(dev, self.training, p_fc=p_fc, p_gat=p_gat)
 
-    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N, drop=None, site0=100):
+    def effective_weights(self):
+        """Weight-normalised matrices of the live branch (independent of the inputs: ChangeDetector computes them while
+        the question GRU runs on its own stream)."""
+        if self.dir_num != 2:
+            raise NotImplementedError("only dir_num == 2 (the reference configuration) is implemented")
+        layer = self.live_layer()
+        w = {"sw": wn_weight(self.self_weights.linear()), "q": wn_weight(layer.query.linear()),
+             "k": wn_weight(layer.key.linear())}
+        if self.pos_emb_dim > 0:
+            w["p0"] = wn_weight(layer.pair_pos_fc1.linear())
+        else:
+            w["p0"] = wn_weight(self.bias.linear())
+        return w
+
+    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N, drop=None, site0=100, weights=None):
         """X [G*N, D] -> X + relu(2 * attention output).  geo*: adjacency (explicit) or fp64 boxes (implicit)."""
         if drop is None:
             drop = self.make_drop(X.device)
@@ -171,19 +186,16 @@ class GAttNet(nn.Module):
         layer = self.live_layer()
         H = layer.num_heads
         Kn = min(self.nongt_dim, N)
-        if self.dir_num != 2:
-            raise NotImplementedError("only dir_num == 2 (the reference configuration) is implemented")
+        w = weights if weights is not None else self.effective_weights()
         sw = self.self_weights.linear()
         ql, kl = layer.query.linear(), layer.key.linear()
         if self.pos_emb_dim > 0:
-            pp = layer.pair_pos_fc1.linear()
-            kind, p0, p1 = "implicit", wn_weight(pp), pp.bias
+            kind, p1 = "implicit", layer.pair_pos_fc1.linear().bias
         else:
-            kind, p0, p1 = "explicit", wn_weight(self.bias.linear()), None
+            kind, p1 = "explicit", None
         dims = (G, B, N, Kn, D, H)
-        return RelationFn.apply(pc, drop, site0, kind, dims, X, XT, q, wn_weight(sw), sw.bias, wn_weight(ql), ql.bias,
-                                wn_weight(kl), kl.bias, layer.linear_out_2.weight, layer.linear_out_2.bias, p0, p1,
-                                geo0, geo1, g_split)
+        return RelationFn.apply(pc, drop, site0, kind, dims, X, XT, q, w["sw"], sw.bias, w["q"], ql.bias, w["k"], kl.bias,
+                                layer.linear_out_2.weight, layer.linear_out_2.bias, w["p0"], p1, geo0, geo1, g_split)
 
     def forward(self, v_feat, adj_matrix, pos_emb=None):
         if self.pos_emb_dim > 0 and pos_emb is None:
@@ -378,6 +390,8 @@ class ChangeDetector(nn.Module):
         self.precision = _default_precision()
         # tests only: force every dropout probability (0.0 runs the train-mode code path without masks)
         self.dropout_override = None
+        self._side = None
+        self._qv_keepalive = None
 
     def live_parameters(self):
         """Parameters that can receive a gradient in setting='mode2'.  The rest exist only so reference checkpoints
@@ -439,21 +453,41 @@ class ChangeDetector(nn.Module):
         B, N, C = input_1.size()
         D = self.att_dim
         G = 2 * B
+        _lib.require_device()            # no CPU / PyTorch fallback: fail loudly without an sm_100 device
+        dev = input_1.device
+        # The question path is a chain of 20 small, latency-bound GRU steps: it runs on its own stream while this
+        # stream does the work that does not depend on it (ROI projection, weight normalisation).  Autograd replays
+        # the same split in backward (BPTT next to the weight-norm / img gradients); a captured CUDA graph keeps it.
+        cur = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        side = self._side
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            qv = self.question_vector(pc, question)
+        self._qv_keepalive = qv          # allocated on the side stream, consumed on this one
         X, XT = LinearFn.apply(pc, input_1, input_2, self.img.weight, self.img.bias)      # [2BN, D]
-        qv = self.question_vector(pc, question)
-        dev = X.device
+        gats = {}
         if graph in ('semantic', 'all'):
-            gat = self.semantic_relation.explicit_relation
-            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_sem_adj_matrix, q_sem_adj_matrix, B, G, B, N,
-                                         drop=gat.make_drop(dev, ov), site0=100)
+            gats['sem'] = self.semantic_relation.explicit_relation
         if graph in ('spatial', 'all', 'i+s'):
-            gat = self.spatial_relation.explicit_relation
-            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_adj_matrix, q_adj_matrix, B, G, B, N,
-                                         drop=gat.make_drop(dev, ov), site0=200)
+            gats['spa'] = self.spatial_relation.explicit_relation
         if graph in ('implicit', 'all', 'i+s'):
-            gat = self.imp_relation.implicit_relation
+            gats['imp'] = self.imp_relation.implicit_relation
+        eff = {k: g.effective_weights() for k, g in gats.items()}
+        cur.wait_stream(side)
+        if 'sem' in gats:
+            gat = gats['sem']
+            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_sem_adj_matrix, q_sem_adj_matrix, B, G, B, N,
+                                         drop=gat.make_drop(dev, ov), site0=100, weights=eff['sem'])
+        if 'spa' in gats:
+            gat = gats['spa']
+            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_adj_matrix, q_adj_matrix, B, G, B, N,
+                                         drop=gat.make_drop(dev, ov), site0=200, weights=eff['spa'])
+        if 'imp' in gats:
+            gat = gats['imp']
             X, XT, _ = gat.relation_step(pc, X, XT, qv, d_bb, q_bb, B, G, B, N,
-                                         drop=gat.make_drop(dev, ov), site0=300)
+                                         drop=gat.make_drop(dev, ov), site0=300, weights=eff['imp'])
         mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
         coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
         fdrop = Drop(dev, self.training, p_fuse=self.dropout.p if ov is None else ov,
