@@ -69,6 +69,29 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint64_t* b
       ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each destination CTA's
+// mbarrier (same CTA-relative offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tmap, uint64_t* bar, void* dst, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
 }
@@ -122,11 +145,15 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int A_MN, int B_MN>
+// CL = 1: independent CTAs.  CL = 2: thread-block cluster of two CTAs on neighbouring M tiles of the SAME N tile; each
+// loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory -> 1.5x fewer bytes pulled
+// from L2 per flop (the single-CTA 128x256 tile is L2-bandwidth bound at ~85 flop/B).
+template <int BN, int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, EkEpilogue ep, int vec_ok, int splits) {
   using C = Cfg<BN, A_MN, B_MN>;
+  static_assert(CL == 1 || BN >= 128, "the shared B tile must split into two TMA boxes");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
@@ -139,17 +166,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (N + BN - 1) / BN;
-  const int num_tiles = num_m * num_n;
+  // work unit = (M tile group of CL tiles, N tile, K split); every CTA of a cluster walks the same unit sequence
+  const int num_mg = (num_m + CL - 1) / CL;
+  const int num_tiles = num_mg * num_n;
   const int num_kb = (K + BK - 1) / BK;
-  const int kb_per = (num_kb + splits - 1) / splits;   // split-K: unit = (tile, split)
+  const int kb_per = (num_kb + splits - 1) / splits;
   const int num_units = num_tiles * splits;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / CL;
+  const int unit_stride = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);      // one commit-arrive per CTA whose MMAs read this slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -165,6 +197,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // peer barriers initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -173,12 +206,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < num_units; unit += unit_stride) {
         const int tile = unit % num_tiles;
         const int kb0 = (unit / num_tiles) * kb_per;
         const int kb1 = min(kb0 + kb_per, num_kb);
-        const int m0 = (tile % num_m) * BM;
-        const int n0 = (tile / num_m) * BN;
+        const int m0 = ((tile % num_mg) * CL + (int)crank) * BM;
+        const int n0 = (tile / num_mg) * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -192,12 +225,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int i = 0; i < BM / 64; ++i)                                   // box {64 m, 64 k}
               tma_load_2d(&tmA, &full_bar[stage], sa + i * (64 * BK * 2), m0 + 64 * i, k0);
           }
-          if (B_MN == 0) {
-            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);                 // box {64 k, BN n}
-          } else {
+          if (CL == 1) {
+            if (B_MN == 0) {
+              tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);               // box {64 k, BN n}
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)                                   // box {64 n, 64 k}
-              tma_load_2d(&tmB, &full_bar[stage], sb + i * (64 * BK * 2), n0 + 64 * i, k0);
+              for (int i = 0; i < BN / 64; ++i)                                 // box {64 n, 64 k}
+                tma_load_2d(&tmB, &full_bar[stage], sb + i * (64 * BK * 2), n0 + 64 * i, k0);
+            }
+          } else {
+            // this CTA fetches half of the shared B tile and multicasts it to both CTAs of the pair
+            if (B_MN == 0) {                                                    // box {64 k, BN/2 n}
+              tma_load_2d_mc(&tmB, &full_bar[stage], sb + crank * (BN / 2 * BK * 2), k0, n0 + (int)crank * (BN / 2), 3);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) {                              // boxes {64 n, 64 k}
+                const int bi = (int)crank * (BN / 128) + i;
+                tma_load_2d_mc(&tmB, &full_bar[stage], sb + bi * (64 * BK * 2), n0 + 64 * bi, k0, 3);
+              }
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -212,7 +258,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
         const int kb0 = (unit / num_tiles) * kb_per;
         const int kb1 = min(kb0 + kb_per, num_kb);
         const int buf = it & 1;
@@ -236,7 +282,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
             tc_mma_bf16(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);          // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (in both CTAs of a pair: the peer multicasts into it too)
+          if (CL == 1) tc_commit(&empty_bar[stage]);
+          else tc_commit_mc(&empty_bar[stage], 3);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull_bar[buf]);              // accumulator complete -> epilogue
@@ -246,12 +294,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ epilogue warps (2..5)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     int it = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+    for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int tile = unit % num_tiles;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (tile % num_m) * BM;
-      const int n0 = (tile / num_m) * BN;
+      const int m0 = ((tile % num_mg) * CL + (int)crank) * BM;
+      const int n0 = (tile / num_mg) * BN;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
       const long long m = (long long)m0 + q * 32 + lane;
@@ -361,6 +409,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it / arrive on it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -443,31 +492,53 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CL>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep, int vec_ok,
                int splits, cudaStream_t stream) {
   using C = Cfg<BN, A_MN, B_MN>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN, CL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cannot set smem attr: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int units = ek_div_up(M, BM) * ek_div_up(N, BN) * splits;
-  const int grid = units < num_sms() ? units : num_sms();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep, vec_ok, splits);
+  const int units = ek_div_up(ek_div_up(M, BM), CL) * ek_div_up(N, BN) * splits;
+  const int slots = num_sms() / CL;
+  const int grid = CL * (units < slots ? units : slots);
+  if (CL == 1) {
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep, vec_ok, splits);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, vec_ok, splits);
+    EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
+  }
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 
 template <int A_MN, int B_MN>
-int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep,
+int launch_bn(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep,
               int vec_ok, int splits, cudaStream_t stream) {
+  if (cl == 2) {
+    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    return launch_cfg<256, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+  }
   switch (bn) {
-    case 64: return launch_cfg<64, A_MN, B_MN>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
-    case 128: return launch_cfg<128, A_MN, B_MN>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
-    default: return launch_cfg<256, A_MN, B_MN>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    case 64: return launch_cfg<64, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    case 128: return launch_cfg<128, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    default: return launch_cfg<256, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
   }
 }
 
@@ -477,6 +548,8 @@ int launch_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream) {
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
+  bool no_cluster = false;
+  if (force_bn < 0) { no_cluster = true; force_bn = -force_bn; }
   // Split-K candidates: plain fp32 outputs, or "C += A B" (addend aliases C, nothing else in the epilogue) where the
   // partial sums are reduced straight onto the existing values.
   const bool acc_alias = ep.addend && ep.addend == ep.C && ep.ldadd == ep.ldc;
@@ -510,13 +583,17 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       if (score > best) { best = score; bn = c; }
     }
   }
+  // CTA pairs (cluster of 2 along M sharing the B tile): whenever there are at least two M tiles and a >= 128 wide tile.
+  // force_bn < 0 requests the unclustered kernel with |force_bn| (tests / A-B comparisons).
+  int cl = (bn >= 128 && ek_div_up(M, BM) >= 2) ? 2 : 1;
+  if (no_cluster) cl = 1;
   CUtensorMap ta, tb;
   int rc;
-  if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);   // [M rows, K cols], box {64, 128}
-  else rc = make_tmap(&ta, A, K, M, lda, BK);           // [K rows, M cols], box {64, 64}
+  if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);                 // [M rows, K cols], box {64, 128}
+  else rc = make_tmap(&ta, A, K, M, lda, BK);                         // [K rows, M cols], box {64, 64}
   if (rc) return rc;
-  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, bn);   // [N rows, K cols], box {64, bn}
-  else rc = make_tmap(&tb, B, K, N, ldb, BK);           // [K rows, N cols], box {64, 64}
+  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, cl == 2 ? bn / 2 : bn);   // [N rows, K cols], box {64, bn or bn/2}
+  else rc = make_tmap(&tb, B, K, N, ldb, BK);                         // [K rows, N cols], box {64, 64}
   if (rc) return rc;
   // bit 0: 16-byte vector stores possible; bits 1..3: vector loads of bias / addend / row-broadcast operands
   int vec_ok = 15;
@@ -529,7 +606,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   const int num_kb = nkb;
   if (splits <= 0) {
     splits = 1;
-    const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, bn);
+    const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, bn);   // (pairs of tiles fill two SMs)
     if (plain_out && tiles * 2 <= num_sms() && num_kb >= 16) {
       splits = (int)(num_sms() / tiles);
       if (splits > num_kb / 4) splits = num_kb / 4;
@@ -549,8 +626,8 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       epk.addend = nullptr;                    // partial sums are atomically added onto C (zeroed or pre-existing)
     }
   }
-  if (!transA && !transB) return launch_bn<0, 0>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
-  if (!transA && transB) return launch_bn<0, 1>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
-  if (transA && !transB) return launch_bn<1, 0>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
-  return launch_bn<1, 1>(bn, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  if (!transA && !transB) return launch_bn<0, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  if (!transA && transB) return launch_bn<0, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  if (transA && !transB) return launch_bn<1, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  return launch_bn<1, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
 }

@@ -36,7 +36,7 @@ def test_gemm_layouts(dtype, transA, transB, M, N, K):
     assert err < (2e-5 if dtype == torch.float32 else 1e-5), err      # operands identical -> only fp32 accumulation order
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("bn", [64, 128, 256, -128, -256])     # negative: same width without the CTA-pair multicast
 def test_gemm_tc_tile_widths_and_splitk(bn):
     from ekaid_b200.functions import gemm
     dev = _dev()
@@ -49,6 +49,15 @@ def test_gemm_tc_tile_widths_and_splitk(bn):
         gemm(A, B, M, N, K, 1, 1, C=C, splits=splits, force_bn=bn)
         err = float((C.double() - ref).abs().max() / ref.abs().max())
         assert err < 1e-5, (bn, splits, err)
+    # K-major operands, odd number of M tiles (the second CTA of the last pair has no rows), fused epilogue
+    M2, N2, K2 = 128 * 5 + 40, 512, 1024
+    A2 = _mk((M2, K2), dev, 5, torch.bfloat16)
+    B2 = _mk((N2, K2), dev, 6, torch.bfloat16)
+    bias = _mk((N2,), dev, 7, torch.float32)
+    ref2 = A2.float().double() @ B2.float().double().t() + bias.double()
+    C2 = torch.full((M2, N2), float("nan"), device=dev)
+    gemm(A2, B2, M2, N2, K2, 0, 0, bias=bias, C=C2, force_bn=bn)
+    assert float((C2.double() - ref2).abs().max() / ref2.abs().max()) < 1e-5, bn
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
