@@ -548,8 +548,11 @@ int launch_bn(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, int 
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream) {
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
-  bool no_cluster = false;
-  if (force_bn < 0) { no_cluster = true; force_bn = -force_bn; }
+  // force_bn = 1000 + width selects the CTA-pair (cluster of 2, multicast B) variant of that width.  It is NOT the
+  // default: measured on B200 it is no faster than independent CTAs (L2 already merges the two CTAs' requests for the
+  // same B tile), and the lock-step coupling costs ~10-40 % on some shapes (profiles/r01_notes.md).
+  bool want_cluster = false;
+  if (force_bn > 1000) { want_cluster = true; force_bn -= 1000; }
   // Split-K candidates: plain fp32 outputs, or "C += A B" (addend aliases C, nothing else in the epilogue) where the
   // partial sums are reduced straight onto the existing values.
   const bool acc_alias = ep.addend && ep.addend == ep.C && ep.ldadd == ep.ldc;
@@ -583,10 +586,8 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       if (score > best) { best = score; bn = c; }
     }
   }
-  // CTA pairs (cluster of 2 along M sharing the B tile): whenever there are at least two M tiles and a >= 128 wide tile.
-  // force_bn < 0 requests the unclustered kernel with |force_bn| (tests / A-B comparisons).
-  int cl = (bn >= 128 && ek_div_up(M, BM) >= 2) ? 2 : 1;
-  if (no_cluster) cl = 1;
+  // CTA pairs (cluster of 2 along M sharing the B tile): opt-in, needs two M tiles and a >= 128 wide tile
+  const int cl = (want_cluster && bn >= 128 && ek_div_up(M, BM) >= 2) ? 2 : 1;
   CUtensorMap ta, tb;
   int rc;
   if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);                 // [M rows, K cols], box {64, 128}

@@ -85,7 +85,8 @@ int ekaid_check_device(void);
  * autograd backward (dgrad: transB=1, wgrad: transA=1,transB=1). */
 int ekaid_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, int64_t lda, const float* B,
                    int64_t ldb, const ekaid_epilogue_t* ep, void* stream);
-/* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  force_bn: 0 = auto, else 64/128/256.
+/* bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed).  force_bn: 0 = auto, else 64/128/256, or
+ * 1128/1256 for the CTA-pair variant (cluster of 2, TMA multicast of the shared weight tile).
  * splits: 0 = auto split-K (plain fp32 C only), 1 = off. Operands 16-byte aligned, pitches multiples of 8. */
 int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
                     int64_t ldb, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream);
