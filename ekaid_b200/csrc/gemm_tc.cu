@@ -142,7 +142,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;                     // transposition buffers of the 4 epilogue warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
 // CL = 1: independent CTAs.  CL = 2: thread-block cluster of two CTAs on neighbouring M tiles of the SAME N tile; each
@@ -293,6 +294,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------------------------------------------ epilogue warps (2..5)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int tile = unit % num_tiles;
@@ -302,13 +304,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile / num_mg) * BN;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
-      const long long m = (long long)m0 + q * 32 + lane;
-      const bool row_ok = m < M;
-      const float* rowb_ptr = nullptr;
-      if (ep.rowb && row_ok) {
-        if (ep.rowflag && ep.rowflag[m]) rowb_ptr = ep.rowb_alt;
-        else rowb_ptr = ep.rowb + (long long)((m / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
+      // Each lane owns accumulator row (q*32 + lane).  The 32x32 chunk is transposed through shared memory so that every
+      // global access of the epilogue is one fully coalesced 128-byte row segment per warp instruction.
+      const long long mlane = (long long)m0 + q * 32 + lane;
+      const float* rowb_lane = nullptr;
+      if (ep.rowb && mlane < M) {
+        if (ep.rowflag && ep.rowflag[mlane]) rowb_lane = ep.rowb_alt;
+        else rowb_lane = ep.rowb + (long long)((mlane / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
       }
+      const unsigned long long dseed = ep.drop.seed ? ek_seed(ep.drop) : 0ull;
+      int rows_here = (int)((long long)M - ((long long)m0 + q * 32));
+      rows_here = rows_here < 0 ? 0 : (rows_here > 32 ? 32 : rows_here);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nb = n0 + c * 32;
@@ -316,91 +322,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
         tc_wait_ld();
-        if (!row_ok) continue;
-        if (splits > 1) {                        // split-K partial sums: fp32 reduction in L2
-          float* cp = ep.C + m * ep.ldc + nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nb + j < N) atomicAdd(cp + j, __uint_as_float(r[j]));
-        } else if ((vec_ok & 1) && nb + 32 <= N) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (ep.bias) {
-            if (vec_ok & 2) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg((const float4*)(ep.bias + nb + j));
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + nb + j);
-            }
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int n = nb + lane;
+        const bool nok = n < N;
+        const float bv = (ep.bias && nok) ? __ldg(ep.bias + n) : 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < rows_here; ++rr) {
+          const long long mm = (long long)m0 + q * 32 + rr;
+          float v = stg[rr * 33 + lane];
+          if (splits > 1) {                      // split-K partial sums: fp32 reduction in L2
+            if (nok) atomicAdd(ep.C + mm * ep.ldc + n, v);
+            continue;
           }
-          if (ep.drop.seed) {
-            const unsigned long long sd = ek_seed(ep.drop);
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] *= ek_drop_mult(ep.drop, sd, (unsigned long long)m * ep.dropN + ep.dropOff + nb + j);
+          v += bv;
+          if (ep.drop.seed) v *= ek_drop_mult(ep.drop, dseed, (unsigned long long)mm * ep.dropN + ep.dropOff + n);
+          if (ep.addend && nok) v += ep.addend[mm * ep.ldadd + n];
+          if (ep.rowb) {
+            const unsigned long long pr = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr);
+            if (nok) v += __ldg((const float*)(uintptr_t)pr + n);
           }
-          if (ep.addend) {
-            const float* ap = ep.addend + m * ep.ldadd + nb;
-            if (vec_ok & 4) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 a4 = *(const float4*)(ap + j);
-                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += ap[j];
-            }
-          }
-          if (rowb_ptr) {
-            if (vec_ok & 8) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 a4 = __ldg((const float4*)(rowb_ptr + nb + j));
-                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __ldg(rowb_ptr + nb + j);
-            }
-          }
-          if (ep.act != EK_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = ek_act(v[j], ep.act);
-          }
-          if (ep.C) {
-            float* cp = ep.C + m * ep.ldc + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (ep.Cb) {
-            bf16* cp = ep.Cb + m * ep.ldcb + nb;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
-              *(uint4*)(cp + j) = pk;
-            }
-          }
-        } else {
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (n < N) {
-              // ek_epilogue_store recomputes the row-broadcast pointer; fine on this cold path
-              ek_epilogue_store(ep, m, n, __uint_as_float(r[j]));
-            }
+          v = ek_act(v, ep.act);
+          if (nok) {
+            if (ep.C) ep.C[mm * ep.ldc + n] = v;
+            if (ep.Cb) ep.Cb[mm * ep.ldcb + n] = __float2bfloat16_rn(v);
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
