@@ -142,7 +142,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
-  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;                     // transposition buffers of the 4 epilogue warps
+  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;                     // transposition buffers of the 4 epilogue warps
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
@@ -294,7 +294,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------------------------------------------ epilogue warps (2..5)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
+    float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * 36);
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int tile = unit % num_tiles;
@@ -304,8 +304,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile / num_mg) * BN;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
-      // Each lane owns accumulator row (q*32 + lane).  The 32x32 chunk is transposed through shared memory so that every
-      // global access of the epilogue is one fully coalesced 128-byte row segment per warp instruction.
+      // Each lane owns accumulator row (q*32 + lane) in TMEM.  A 32x32 chunk is transposed through shared memory (16-byte
+      // accesses, pitch 36 floats: conflict-free both ways) so that one warp instruction stores 4 rows x 128 contiguous
+      // bytes instead of 32 scattered 16-byte pieces.
       const long long mlane = (long long)m0 + q * 32 + lane;
       const float* rowb_lane = nullptr;
       if (ep.rowb && mlane < M) {
@@ -315,6 +316,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const unsigned long long dseed = ep.drop.seed ? ek_seed(ep.drop) : 0ull;
       int rows_here = (int)((long long)M - ((long long)m0 + q * 32));
       rows_here = rows_here < 0 ? 0 : (rows_here > 32 ? 32 : rows_here);
+      const int rg = lane >> 3, c4 = (lane & 7) * 4;        // this lane's row group / 4-column group after transposition
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int nb = n0 + c * 32;
@@ -322,34 +324,66 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
         tc_wait_ld();
+        if ((vec_ok == 15) && nb + 32 <= N) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
-        const int n = nb + lane;
-        const bool nok = n < N;
-        const float bv = (ep.bias && nok) ? __ldg(ep.bias + n) : 0.f;
-#pragma unroll 4
-        for (int rr = 0; rr < rows_here; ++rr) {
-          const long long mm = (long long)m0 + q * 32 + rr;
-          float v = stg[rr * 33 + lane];
-          if (splits > 1) {                      // split-K partial sums: fp32 reduction in L2
-            if (nok) atomicAdd(ep.C + mm * ep.ldc + n, v);
-            continue;
+          for (int j = 0; j < 32; j += 4)
+            *(float4*)(stg + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          __syncwarp();
+          const int n = nb + c4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rg;
+            const unsigned long long pr = ep.rowb ? __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr) : 0ull;
+            if (rr < rows_here) {
+              const long long mm = (long long)m0 + q * 32 + rr;
+              float4 v = *(const float4*)(stg + rr * 36 + c4);
+              if (splits > 1) {                  // split-K partial sums: fp32 reduction in L2
+                float* cp = ep.C + mm * ep.ldc + n;
+                atomicAdd(cp, v.x); atomicAdd(cp + 1, v.y); atomicAdd(cp + 2, v.z); atomicAdd(cp + 3, v.w);
+              } else {
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                if (ep.drop.seed) {
+                  const unsigned long long e0 = (unsigned long long)mm * ep.dropN + ep.dropOff + n;
+                  v.x *= ek_drop_mult(ep.drop, dseed, e0);     v.y *= ek_drop_mult(ep.drop, dseed, e0 + 1);
+                  v.z *= ek_drop_mult(ep.drop, dseed, e0 + 2); v.w *= ek_drop_mult(ep.drop, dseed, e0 + 3);
+                }
+                if (ep.addend) {
+                  const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + n);
+                  v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+                }
+                if (ep.rowb) {
+                  const float4 a4 = __ldg((const float4*)((const float*)(uintptr_t)pr + n));
+                  v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+                }
+                if (ep.act != EK_ACT_NONE) {
+                  v.x = ek_act(v.x, ep.act); v.y = ek_act(v.y, ep.act); v.z = ek_act(v.z, ep.act); v.w = ek_act(v.w, ep.act);
+                }
+                if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
+                if (ep.Cb) {
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+                  uint2 pk;
+                  pk.x = *(uint32_t*)&t0;
+                  pk.y = *(uint32_t*)&t1;
+                  *(uint2*)(ep.Cb + mm * ep.ldcb + n) = pk;
+                }
+              }
+            }
           }
-          v += bv;
-          if (ep.drop.seed) v *= ek_drop_mult(ep.drop, dseed, (unsigned long long)mm * ep.dropN + ep.dropOff + n);
-          if (ep.addend && nok) v += ep.addend[mm * ep.ldadd + n];
-          if (ep.rowb) {
-            const unsigned long long pr = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr);
-            if (nok) v += __ldg((const float*)(uintptr_t)pr + n);
-          }
-          v = ek_act(v, ep.act);
-          if (nok) {
-            if (ep.C) ep.C[mm * ep.ldc + n] = v;
-            if (ep.Cb) ep.Cb[mm * ep.ldcb + n] = __float2bfloat16_rn(v);
+          __syncwarp();
+        } else if (mlane < M) {
+          // cold path (unaligned operands / partial last chunk): this lane's row, element by element
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n < N) {
+              if (splits > 1) atomicAdd(ep.C + mlane * ep.ldc + n, __uint_as_float(r[j]));
+              else ek_epilogue_store(ep, mlane, n, __uint_as_float(r[j]));
+            }
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
