@@ -11,7 +11,7 @@
 //   B_MN = 1: B stored [K, N] (N contiguous)   -> MN-major                  (dgrad: weight, wgrad: X)
 //
 // Persistent: grid = min(#tiles, #SMs); warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2..5 = epilogue (one TMEM lane quarter each).  Tile 128 x BN x 64, BN in {64,128,256}.
+// warps 2..9 = epilogue (two per TMEM lane quarter, alternate 32-column chunks).  Tile 128 x BN x 64, BN in {64,128,256}.
 #include <cuda.h>
 #include <mutex>
 #include <unordered_map>
@@ -24,7 +24,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -146,6 +146,87 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
+// Direct epilogue of one 32-column chunk: this lane owns one accumulator row and stores 32 consecutive columns.
+__device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uint32_t* r, long long m, int nb, int N,
+                                                 int vec_ok, const float* rowb_ptr) {
+  if ((vec_ok & 1) && nb + 32 <= N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (ep.bias) {
+              if (vec_ok & 2) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg((const float4*)(ep.bias + nb + j));
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + nb + j);
+              }
+            }
+            if (ep.drop.seed) {
+              const unsigned long long sd = ek_seed(ep.drop);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] *= ek_drop_mult(ep.drop, sd, (unsigned long long)m * ep.dropN + ep.dropOff + nb + j);
+            }
+            if (ep.addend) {
+              const float* ap = ep.addend + m * ep.ldadd + nb;
+              if (vec_ok & 4) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a4 = *(const float4*)(ap + j);
+                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += ap[j];
+              }
+            }
+            if (rowb_ptr) {
+              if (vec_ok & 8) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a4 = __ldg((const float4*)(rowb_ptr + nb + j));
+                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(rowb_ptr + nb + j);
+              }
+            }
+            if (ep.act != EK_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = ek_act(v[j], ep.act);
+            }
+            if (ep.C) {
+              float* cp = ep.C + m * ep.ldc + nb;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (ep.Cb) {
+              bf16* cp = ep.Cb + m * ep.ldcb + nb;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
+                *(uint4*)(cp + j) = pk;
+              }
+            }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {         // cold path (static indexing keeps r[] in registers)
+      const int n = nb + j;
+      if (n < N) ek_epilogue_store(ep, m, n, __uint_as_float(r[j]));
+    }
+  }
+}
+
 // CL = 1: independent CTAs.  CL = 2: thread-block cluster of two CTAs on neighbouring M tiles of the SAME N tile; each
 // loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory -> 1.5x fewer bytes pulled
 // from L2 per flop (the single-CTA 128x256 tile is L2-bandwidth bound at ~85 flop/B).
@@ -186,7 +267,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], 8);   // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -292,9 +373,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps (2..5)
+    // ------------------------------------------------------------------ epilogue warps (2..9)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * (32 * 36);
+    const int half = (warp - 2) >> 2;            // which of the two warps of this quarter
+    float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp & 3) * (32 * 36);   // split-K path, half 0 only
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       const int tile = unit % num_tiles;
@@ -304,84 +386,116 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int n0 = (tile / num_mg) * BN;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
-      // Each lane owns accumulator row (q*32 + lane) in TMEM.  A 32x32 chunk is transposed through shared memory (16-byte
-      // accesses, pitch 36 floats: conflict-free both ways) so that one warp instruction stores 4 rows x 128 contiguous
-      // bytes instead of 32 scattered 16-byte pieces.
-      const long long mlane = (long long)m0 + q * 32 + lane;
-      const float* rowb_lane = nullptr;
-      if (ep.rowb && mlane < M) {
-        if (ep.rowflag && ep.rowflag[mlane]) rowb_lane = ep.rowb_alt;
-        else rowb_lane = ep.rowb + (long long)((mlane / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
-      }
-      const unsigned long long dseed = ep.drop.seed ? ek_seed(ep.drop) : 0ull;
-      int rows_here = (int)((long long)M - ((long long)m0 + q * 32));
-      rows_here = rows_here < 0 ? 0 : (rows_here > 32 ? 32 : rows_here);
-      const int rg = lane >> 3, c4 = (lane & 7) * 4;        // this lane's row group / 4-column group after transposition
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int nb = n0 + c * 32;
-        if (nb >= N) break;                      // warp-uniform
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
-        tc_wait_ld();
-        if ((vec_ok == 15) && nb + 32 <= N) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *(float4*)(stg + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          __syncwarp();
-          const int n = nb + c4;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rg;
-            const unsigned long long pr = ep.rowb ? __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr) : 0ull;
-            if (rr < rows_here) {
-              const long long mm = (long long)m0 + q * 32 + rr;
-              float4 v = *(const float4*)(stg + rr * 36 + c4);
-              if (splits > 1) {                  // split-K partial sums: fp32 reduction in L2
-                float* cp = ep.C + mm * ep.ldc + n;
-                atomicAdd(cp, v.x); atomicAdd(cp + 1, v.y); atomicAdd(cp + 2, v.z); atomicAdd(cp + 3, v.w);
-              } else {
-                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                if (ep.drop.seed) {
-                  const unsigned long long e0 = (unsigned long long)mm * ep.dropN + ep.dropOff + n;
-                  v.x *= ek_drop_mult(ep.drop, dseed, e0);     v.y *= ek_drop_mult(ep.drop, dseed, e0 + 1);
-                  v.z *= ek_drop_mult(ep.drop, dseed, e0 + 2); v.w *= ek_drop_mult(ep.drop, dseed, e0 + 3);
-                }
-                if (ep.addend) {
-                  const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + n);
-                  v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
-                }
-                if (ep.rowb) {
-                  const float4 a4 = __ldg((const float4*)((const float*)(uintptr_t)pr + n));
-                  v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
-                }
-                if (ep.act != EK_ACT_NONE) {
-                  v.x = ek_act(v.x, ep.act); v.y = ek_act(v.y, ep.act); v.z = ek_act(v.z, ep.act); v.w = ek_act(v.w, ep.act);
-                }
-                if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
-                if (ep.Cb) {
-                  __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
-                  uint2 pk;
-                  pk.x = *(uint32_t*)&t0;
-                  pk.y = *(uint32_t*)&t1;
-                  *(uint2*)(ep.Cb + mm * ep.ldcb + n) = pk;
+      const long long mlane0 = (long long)m0 + q * 32;
+      if (splits > 1 && half == 1) {
+        // split-K partial sums are reduced by the first warp of each quarter (one staging buffer per quarter)
+      } else if (splits > 1) {
+        // Each lane owns accumulator row (q*32 + lane) in TMEM.  A 32x32 chunk is transposed through shared memory (16-byte
+        // accesses, pitch 36 floats: conflict-free both ways) so that one warp instruction stores 4 rows x 128 contiguous
+        // bytes instead of 32 scattered 16-byte pieces.
+        const long long mlane = (long long)m0 + q * 32 + lane;
+        const float* rowb_lane = nullptr;
+        if (ep.rowb && mlane < M) {
+          if (ep.rowflag && ep.rowflag[mlane]) rowb_lane = ep.rowb_alt;
+          else rowb_lane = ep.rowb + (long long)((mlane / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
+        }
+        const unsigned long long dseed = ep.drop.seed ? ek_seed(ep.drop) : 0ull;
+        int rows_here = (int)((long long)M - ((long long)m0 + q * 32));
+        rows_here = rows_here < 0 ? 0 : (rows_here > 32 ? 32 : rows_here);
+        const int rg = lane >> 3, c4 = (lane & 7) * 4;        // this lane's row group / 4-column group after transposition
+  #pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int nb = n0 + c * 32;
+          if (nb >= N) break;                      // warp-uniform
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+          tc_wait_ld();
+          if ((vec_ok == 15) && nb + 32 <= N) {
+  #pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *(float4*)(stg + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            __syncwarp();
+            const int n = nb + c4;
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
+  #pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + rg;
+              const unsigned long long pr = ep.rowb ? __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr) : 0ull;
+              if (rr < rows_here) {
+                const long long mm = (long long)m0 + q * 32 + rr;
+                float4 v = *(const float4*)(stg + rr * 36 + c4);
+                if (splits > 1) {                  // split-K partial sums: fp32 reduction in L2
+                  float* cp = ep.C + mm * ep.ldc + n;
+                  atomicAdd(cp, v.x); atomicAdd(cp + 1, v.y); atomicAdd(cp + 2, v.z); atomicAdd(cp + 3, v.w);
+                } else {
+                  v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                  if (ep.drop.seed) {
+                    const unsigned long long e0 = (unsigned long long)mm * ep.dropN + ep.dropOff + n;
+                    v.x *= ek_drop_mult(ep.drop, dseed, e0);     v.y *= ek_drop_mult(ep.drop, dseed, e0 + 1);
+                    v.z *= ek_drop_mult(ep.drop, dseed, e0 + 2); v.w *= ek_drop_mult(ep.drop, dseed, e0 + 3);
+                  }
+                  if (ep.addend) {
+                    const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + n);
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+                  }
+                  if (ep.rowb) {
+                    const float4 a4 = __ldg((const float4*)((const float*)(uintptr_t)pr + n));
+                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+                  }
+                  if (ep.act != EK_ACT_NONE) {
+                    v.x = ek_act(v.x, ep.act); v.y = ek_act(v.y, ep.act); v.z = ek_act(v.z, ep.act); v.w = ek_act(v.w, ep.act);
+                  }
+                  if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
+                  if (ep.Cb) {
+                    __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+                    uint2 pk;
+                    pk.x = *(uint32_t*)&t0;
+                    pk.y = *(uint32_t*)&t1;
+                    *(uint2*)(ep.Cb + mm * ep.ldcb + n) = pk;
+                  }
                 }
               }
             }
-          }
-          __syncwarp();
-        } else if (mlane < M) {
-          // cold path (unaligned operands / partial last chunk): this lane's row, element by element
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (n < N) {
-              if (splits > 1) atomicAdd(ep.C + mlane * ep.ldc + n, __uint_as_float(r[j]));
-              else ek_epilogue_store(ep, mlane, n, __uint_as_float(r[j]));
+            __syncwarp();
+          } else if (mlane < M) {
+            // cold path (unaligned operands / partial last chunk): this lane's row, element by element
+  #pragma unroll 1
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              if (n < N) {
+                if (splits > 1) atomicAdd(ep.C + mlane * ep.ldc + n, __uint_as_float(r[j]));
+                else ek_epilogue_store(ep, mlane, n, __uint_as_float(r[j]));
+              }
             }
+          }
+        }
+      } else {
+        // direct path, software-pipelined: the TMEM load of the next chunk is in flight while this one is stored.
+        // Two warps share each TMEM lane quarter and take alternate 32-column chunks.
+        const long long m = mlane0 + lane;
+        const bool row_ok = m < M;
+        const float* rowb_ptr = nullptr;
+        if (ep.rowb && row_ok) {
+          if (ep.rowflag && ep.rowflag[m]) rowb_ptr = ep.rowb_alt;
+          else rowb_ptr = ep.rowb + (long long)((m / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
+        }
+        int nch = (N - n0 + 31) / 32;
+        nch = nch > BN / 32 ? BN / 32 : nch;
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+        uint32_t ra[32], rb[32];
+        int c = half;
+        if (c < nch) tc_ld32(tbase + c * 32, ra);
+#pragma unroll 1
+        for (; c < nch; c += 4) {
+          tc_wait_ld();
+          if (c + 2 < nch) tc_ld32(tbase + (c + 2) * 32, rb);
+          if (row_ok) epi_direct_chunk(ep, ra, m, n0 + c * 32, N, vec_ok, rowb_ptr);
+          if (c + 2 < nch) {
+            tc_wait_ld();
+            if (c + 4 < nch) tc_ld32(tbase + (c + 4) * 32, ra);
+            if (row_ok) epi_direct_chunk(ep, rb, m, n0 + (c + 2) * 32, N, vec_ok, rowb_ptr);
           }
         }
       }
