@@ -679,7 +679,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       // useful fraction of issued MMA work: (real N columns / padded) * (tiles / slots); wide tiles are
       // ~10% more efficient per flop (fewer A re-reads, shorter epilogue share)
       const double useful = (double)N / ((double)ek_div_up(N, c) * c) * (double)tiles / (double)(waves * num_sms());
-      const double score = useful * (c == 256 ? 1.0 : (c == 128 ? 0.92 : 0.8));
+      const double score = useful * (c == 256 ? 1.0 : (c == 128 ? 0.72 : 0.5));   // measured: scripts/gemm_bench.py
       if (score > best) { best = score; bn = c; }
     }
   }
