@@ -169,7 +169,7 @@ def run_reference(args, rank):
             "config": workload_config(args), "gpu_launches": 0,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -186,8 +186,28 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Point fd 1 at stderr for the run so that library chatter (e.g. NCCL's version banner) cannot land on
+    stdout; the one JSON line goes to the saved descriptor through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse()
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -374,7 +394,7 @@ def main():
                                 "sample": "%d %s steps of the oracle port on %d image pairs x %d nodes, fp32 torch CPU, "
                                           "%.1f s" % (n, args.mode, bs, N, el)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # tear down: release the captured graph (it references NCCL kernels) before the communicator; a watchdog
         # makes sure a stuck communicator teardown can never hold the GPUs after the result has been printed
