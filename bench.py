@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--graph", default="all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-pdl", action="store_true", help="turn programmatic dependent launch between kernels off")
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-dropout", action="store_true", help="train step with modules in eval mode (no dropout)")
     return ap.parse_args()
@@ -224,6 +225,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib.require_device()
+    if args.no_pdl:
+        lib.load().ekaid_set_pdl(0)
     pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)

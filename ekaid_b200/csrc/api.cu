@@ -1,5 +1,6 @@
 // extern "C" entry points of libekaid_b200.so (declared in include/ekaid_b200.h).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -12,6 +13,15 @@ void ek_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static int g_pdl = -1;
+int ek_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("EKAID_B200_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
 }
 
 // launchers implemented in the kernel translation units
@@ -110,6 +120,11 @@ static EkDrop mk_drop(const uint64_t* seed, uint32_t site, float p) {
 extern "C" {
 
 int ekaid_abi_version(void) { return 1; }
+int ekaid_set_pdl(int on) {
+  const int prev = ek_pdl_enabled();
+  g_pdl = on ? 1 : 0;
+  return prev;
+}
 const char* ekaid_last_error(void) { return g_err; }
 
 int ekaid_check_device(void) {

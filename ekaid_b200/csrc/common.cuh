@@ -37,6 +37,34 @@ void ek_set_error(const char* fmt, ...);
 
 static inline int ek_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch.  Every kernel is launched with the programmatic-stream-serialization attribute and
+// starts with ek_pdl_prologue() = griddepcontrol.wait, which blocks until the previous kernel of the stream has
+// completed and flushed its memory.  No global memory is touched before the wait, so ordering is exactly stream
+// order; what overlaps with the previous kernel's tail is launch latency and, for the GEMM, barrier / TMEM /
+// tensor-map set-up.  Measured on the training step: 5.33 -> 5.15 ms.  An explicit early trigger
+// (griddepcontrol.launch_dependents at kernel entry) was tried and rejected: the step got slower (5.73 ms) and fp32
+// parity broke, so dependents are released by the implicit trigger at grid completion only.
+// EKAID_B200_PDL=0 / ekaid_set_pdl(0) turn the attribute off (the wait becomes a no-op).
+__device__ __forceinline__ void ek_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ek_pdl_prologue() { ek_pdl_wait(); }
+int ek_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t ek_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = ek_pdl_enabled();
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -24,6 +24,7 @@ constexpr float NEG_MASK = -9e15f;
 __global__ void adj_prep_fwd_kernel(const float* __restrict__ adj0, const float* __restrict__ adj1, int g_split,
                                     const float* __restrict__ w, int N, int Kn, int L, float* __restrict__ cond,
                                     float* __restrict__ lbias) {
+  ek_pdl_prologue();
   const int g = blockIdx.x;
   const float* adj = (g < g_split) ? adj0 + (size_t)g * N * N * L : adj1 + (size_t)(g - g_split) * N * N * L;
   for (int e = threadIdx.x; e < N * Kn; e += blockDim.x) {
@@ -44,6 +45,7 @@ __global__ void adj_prep_fwd_kernel(const float* __restrict__ adj0, const float*
 __global__ void adj_prep_bwd_kernel(const float* __restrict__ adj0, const float* __restrict__ adj1, int g_split,
                                     const float* __restrict__ dlbias_part, int nparts, int N, int Kn, int L,
                                     float* __restrict__ dw_part) {
+  ek_pdl_prologue();
   __shared__ float red[32];
   const int g = blockIdx.x;
   const float* adj = (g < g_split) ? adj0 + (size_t)g * N * N * L : adj1 + (size_t)(g - g_split) * N * N * L;
@@ -129,6 +131,7 @@ __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const doubl
                                      const float* __restrict__ dim_t, int N, int Kn, int H,
                                      float* __restrict__ gbias, EkDrop dr, float* __restrict__ emb_cache,
                                      int fast_trig) {
+  ek_pdl_prologue();
   extern __shared__ float sW[];      // H*64 + H, then 8 wave lengths
   float* sDim = sW + H * 65;
   for (int e = threadIdx.x; e < H * 64; e += blockDim.x) sW[e] = Wp[e];
@@ -169,6 +172,7 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
                      const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ dim_t, int N,
                      int Kn, int H, const float* __restrict__ dgbias, float* __restrict__ part, EkDrop dr,
                      const float* __restrict__ emb_cache, int fast_trig) {
+  ek_pdl_prologue();
   extern __shared__ float sm[];      // weights H*65 | 8 wave lengths | emb [GB_TILE][65] | df [GB_TILE][8]
   float* sW = sm;
   float* sDim = sm + H * 65;
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(256)
 edge_softmax_fwd_kernel(const T* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond,
                         const float* __restrict__ lbias, const float* __restrict__ gbias, int N, int Kn, int H,
                         float* __restrict__ P) {
+  ek_pdl_prologue();
   extern __shared__ float smf[];
   const int g = blockIdx.x, h = blockIdx.y;
   const int dh = D / H;
@@ -345,6 +350,7 @@ edge_aggregate_fwd_kernel(const float* __restrict__ P, const T* __restrict__ QKZ
                           const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                           float* __restrict__ Xout, T* __restrict__ XoutT, long long ldt,
                           uint8_t* __restrict__ mask, EkDrop dr) {
+  ek_pdl_prologue();
   extern __shared__ float smf[];
   const unsigned long long sd = ek_seed(dr);
   float* Ps = smf;                               // [AG_ROWS][H*Kn]
@@ -405,6 +411,7 @@ edge_aggregate_bwd_kernel(const float* __restrict__ dXout, const uint8_t* __rest
                           const float* __restrict__ P, const T* __restrict__ QKZ, long long ld, int D, int N, int Kn,
                           int H, T* __restrict__ dQKZ, float* __restrict__ dOut, float* __restrict__ dPpart,
                           float gscale) {
+  ek_pdl_prologue();
   extern __shared__ float smf[];
   const int g = blockIdx.x;
   const int slice = blockIdx.y;
@@ -475,6 +482,7 @@ __global__ void __launch_bounds__(256)
 edge_softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ dPpart, int nslices,
                         const T* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond, int N, int Kn,
                         int H, T* __restrict__ dQKZ, float* __restrict__ dlbias_part, float* __restrict__ dgbias) {
+  ek_pdl_prologue();
   extern __shared__ float smf[];
   const int g = blockIdx.x, h = blockIdx.y;
   const int G = gridDim.x;
@@ -550,13 +558,13 @@ edge_softmax_bwd_kernel(const float* __restrict__ P, const float* __restrict__ d
 // ------------------------------------------------------------------------------------------------
 int ek_adj_prep_fwd_launch(const float* adj0, const float* adj1, int g_split, const float* w, int G, int N, int Kn,
                            int L, float* cond, float* lbias, cudaStream_t st) {
-  adj_prep_fwd_kernel<<<G, 256, 0, st>>>(adj0, adj1, g_split, w, N, Kn, L, cond, lbias);
+  ek_launch(adj_prep_fwd_kernel, G, 256, 0, st, adj0, adj1, g_split, w, N, Kn, L, cond, lbias);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_adj_prep_bwd_launch(const float* adj0, const float* adj1, int g_split, const float* dlbias_part, int nparts,
                            int G, int N, int Kn, int L, float* dw_part, cudaStream_t st) {
-  adj_prep_bwd_kernel<<<G, 256, 0, st>>>(adj0, adj1, g_split, dlbias_part, nparts, N, Kn, L, dw_part);
+  ek_launch(adj_prep_bwd_kernel, G, 256, 0, st, adj0, adj1, g_split, dlbias_part, nparts, N, Kn, L, dw_part);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -566,7 +574,7 @@ int ek_geom_bias_fwd_launch(const double* bb0, const double* bb1, int g_split, c
                             int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   dim3 grid(G, ek_div_up(N * Kn, 128 * 4));
-  geom_bias_fwd_kernel<<<grid, 128, (H * 65 + 8) * sizeof(float), st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
+  ek_launch(geom_bias_fwd_kernel, grid, 128, (H * 65 + 8) * sizeof(float), st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
                                                                          gbias, dr, emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -576,7 +584,7 @@ int ek_geom_bias_bwd_launch(const double* bb0, const double* bb1, int g_split, c
                             EkDrop dr, const float* emb_cache, int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float);
-  geom_bias_bwd_kernel<<<G, GB_TILE, smem, st>>>(bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part, dr,
+  ek_launch(geom_bias_bwd_kernel, G, GB_TILE, smem, st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part, dr,
                                                  emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -594,7 +602,7 @@ static int edge_softmax_fwd_t(const T* QKZ, long long ld, int D, const float* co
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "edge_softmax: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(G, H), 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P);
+  ek_launch(kern, dim3(G, H), 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -629,7 +637,7 @@ static int edge_aggregate_fwd_t(const float* P, const T* QKZ, long long ld, int 
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "edge_aggregate: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
+  ek_launch(kern, dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
                                                           dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -669,7 +677,7 @@ static int edge_aggregate_bwd_t(const float* dXout, const uint8_t* mask, const f
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "edge_aggregate_bwd: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart,
+  ek_launch(kern, dim3(G, ek_div_up(D, AG_COLS)), 256, smem, st, dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart,
                                                           gscale);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -701,7 +709,7 @@ static int edge_softmax_bwd_t(const float* P, const float* dPpart, int nslices, 
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "edge_softmax_bwd: smem %zu: %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  kern<<<dim3(G, H), 256, smem, st>>>(P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ, dlbias_part, dgbias);
+  ek_launch(kern, dim3(G, H), 256, smem, st, P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ, dlbias_part, dgbias);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

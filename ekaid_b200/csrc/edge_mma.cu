@@ -60,6 +60,7 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
                    const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                    float* __restrict__ Xout, bf16* __restrict__ XoutT, long long ldt, uint8_t* __restrict__ mask,
                    int kchunk, EkDrop dr, const bf16* __restrict__ Phl, long long plane) {
+  ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const unsigned long long sd = ek_seed(dr);
   const int PS = kchunk + 8;                        // P row pitch (elements)
@@ -180,6 +181,7 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
                    const bf16* __restrict__ QKZ, long long ld, int D, int N, int Kn, int H, bf16* __restrict__ dQKZ,
                    float* __restrict__ dOut, float* __restrict__ dPpart, int kchunk, float gscale,
                    const bf16* __restrict__ Phl) {
+  ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int PS = kchunk + 8;
   bf16* dOs = (bf16*)smraw;                         // [MR][ZS]   dout tile (i, c)
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(256)
 softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond,
                        const float* __restrict__ lbias, const float* __restrict__ gbias, int N, int Kn, int H,
                        float* __restrict__ P, int MR, bf16* __restrict__ Phl, long long plane) {
+  ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int g = blockIdx.x, h = blockIdx.y;
   const int dh = D / H;
@@ -439,6 +442,7 @@ __global__ void __launch_bounds__(256)
 softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dPpart, int nslices,
                        const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond, int N, int Kn,
                        int H, bf16* __restrict__ dQKZ, float* __restrict__ dlbias_part, float* __restrict__ dgbias) {
+  ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int g = blockIdx.x, h = blockIdx.y, G = gridDim.x;
   const int dh = D / H, HK = H * Kn;
@@ -583,12 +587,12 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
   if (MR == 64) {
     int rc = set_smem(agg_fwd_mma_kernel<64>, smem, c64, "agg_fwd_mma");
     if (rc) return rc;
-    agg_fwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
+    ek_launch(agg_fwd_mma_kernel<64>, grid, 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
                                                     dr, Phl, plane);
   } else {
     int rc = set_smem(agg_fwd_mma_kernel<128>, smem, c128, "agg_fwd_mma");
     if (rc) return rc;
-    agg_fwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
+    ek_launch(agg_fwd_mma_kernel<128>, grid, 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
                                                      dr, Phl, plane);
   }
   EK_CHECK_LAUNCH();
@@ -610,12 +614,12 @@ int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* 
   if (MR == 64) {
     int rc = set_smem(agg_bwd_mma_kernel<64>, smem, c64, "agg_bwd_mma");
     if (rc) return rc;
-    agg_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
+    ek_launch(agg_bwd_mma_kernel<64>, grid, 256, smem, st, dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
                                                     gscale, Phl);
   } else {
     int rc = set_smem(agg_bwd_mma_kernel<128>, smem, c128, "agg_bwd_mma");
     if (rc) return rc;
-    agg_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
+    ek_launch(agg_bwd_mma_kernel<128>, grid, 256, smem, st, dXout, mask, P, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, kchunk,
                                                      gscale, Phl);
   }
   EK_CHECK_LAUNCH();
@@ -635,11 +639,11 @@ int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float*
   if (NT == 8) {
     int rc = set_smem(softmax_fwd_mma_kernel<8>, smem, c8, "softmax_fwd_mma");
     if (rc) return rc;
-    softmax_fwd_mma_kernel<8><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
+    ek_launch(softmax_fwd_mma_kernel<8>, grid, 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
   } else {
     int rc = set_smem(softmax_fwd_mma_kernel<16>, smem, c16, "softmax_fwd_mma");
     if (rc) return rc;
-    softmax_fwd_mma_kernel<16><<<grid, 256, smem, st>>>(QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
+    ek_launch(softmax_fwd_mma_kernel<16>, grid, 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -658,12 +662,12 @@ int ek_softmax_bwd_mma_launch(const float* P, const float* dPpart, int nslices, 
   if (MR == 64) {
     int rc = set_smem(softmax_bwd_mma_kernel<64>, smem, c64, "softmax_bwd_mma");
     if (rc) return rc;
-    softmax_bwd_mma_kernel<64><<<grid, 256, smem, st>>>(P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ,
+    ek_launch(softmax_bwd_mma_kernel<64>, grid, 256, smem, st, P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ,
                                                          dlbias_part, dgbias);
   } else {
     int rc = set_smem(softmax_bwd_mma_kernel<128>, smem, c128, "softmax_bwd_mma");
     if (rc) return rc;
-    softmax_bwd_mma_kernel<128><<<grid, 256, smem, st>>>(P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ,
+    ek_launch(softmax_bwd_mma_kernel<128>, grid, 256, smem, st, P, dPpart, nslices, QKZ, ld, D, cond, N, Kn, H, dQKZ,
                                                           dlbias_part, dgbias);
   }
   EK_CHECK_LAUNCH();

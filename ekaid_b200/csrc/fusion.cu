@@ -7,6 +7,7 @@ namespace {
 // ---------------------------------------------------------------- casts / copies
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst,
                                      long long ldd, long long rows, int cols) {
+  ek_pdl_prologue();
   const long long total = rows * (cols / 4);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -22,6 +23,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
 }
 __global__ void copy_f32_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
                                 long long rows, int cols) {
+  ek_pdl_prologue();
   const long long total = rows * (cols / 4);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -32,6 +34,7 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, long long lds, fl
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds, float* __restrict__ dst,
                                      long long ldd, long long rows, int cols) {
+  ek_pdl_prologue();
   const long long total = rows * cols;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -46,6 +49,7 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds
 template <typename T>
 __global__ void colsum_part_kernel(const T* __restrict__ src, long long ld, long long M, int N,
                                    const float* __restrict__ rowscale, float* __restrict__ part, int nparts) {
+  ek_pdl_prologue();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -68,6 +72,7 @@ __global__ void colsum_part_kernel(const T* __restrict__ src, long long ld, long
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ out) {
+  ek_pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float s = 0.f;
@@ -77,6 +82,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, 
 
 // ---------------------------------------------------------------- row flags for quirk Q10
 __global__ void row_zero_flags_kernel(const float* __restrict__ X, long long M, int D, uint8_t* __restrict__ flags) {
+  ek_pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -91,6 +97,7 @@ __global__ void row_zero_flags_kernel(const float* __restrict__ X, long long M, 
 template <typename T>
 __global__ void group_rowsum_kernel(const T* __restrict__ src, long long ld, int N, int B, int S, int D,
                                     const uint8_t* __restrict__ flags, float* __restrict__ out) {
+  ek_pdl_prologue();
   const int b = blockIdx.x;
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= D) return;
@@ -110,6 +117,7 @@ __global__ void group_rowsum_kernel(const T* __restrict__ src, long long ld, int
 template <typename T>
 __global__ void combine_diff_fwd_kernel(const float* __restrict__ X3, long long BN, int D, int mode, float c1, float c2,
                                         float c3, float* __restrict__ Xc, T* __restrict__ CAT) {
+  ek_pdl_prologue();
   const long long total = BN * D;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -135,6 +143,7 @@ __global__ void combine_diff_fwd_kernel(const float* __restrict__ X3, long long 
 // dX3 = csum * (dXc_direct + dCAT[:, 0:D] -/+ (dCAT_bef[:, D:2D] + dCAT_aft[:, D:2D]))
 __global__ void combine_diff_bwd_kernel(const float* __restrict__ dXc, const float* __restrict__ dCAT, long long BN,
                                         int D, int mode, float c1, float c2, float c3, float* __restrict__ dX3) {
+  ek_pdl_prologue();
   const long long total = BN * D;
   float cs = 1.f;
   if (mode == 1) cs = c1 + c2 + c3;
@@ -160,6 +169,7 @@ __global__ void combine_diff_bwd_kernel(const float* __restrict__ dXc, const flo
 template <typename T>
 __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int D, T* __restrict__ ctx,
                                 T* __restrict__ gate, T* __restrict__ CAT, EkDrop dc, EkDrop dg) {
+  ek_pdl_prologue();
   const long long total = M * D;
   const unsigned long long sc = ek_seed(dc), sg = ek_seed(dg);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -178,6 +188,7 @@ __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int 
 template <typename T>
 __global__ void gate_bwd_kernel(const float* __restrict__ dCAT, const T* __restrict__ ctx, const T* __restrict__ gate,
                                 long long M, int D, T* __restrict__ dpre, EkDrop dc, EkDrop dg) {
+  ek_pdl_prologue();
   const long long total = M * D;
   const unsigned long long sc = ek_seed(dc), sg = ek_seed(dg);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -195,6 +206,7 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dCAT, const T* __restr
 // att[row] = sigmoid(e[row,:] . w + b)   one warp per row
 __global__ void att_score_kernel(const float* __restrict__ E, long long M, int dim, const float* __restrict__ w,
                                  const float* __restrict__ b, float* __restrict__ att) {
+  ek_pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -206,6 +218,7 @@ __global__ void att_score_kernel(const float* __restrict__ E, long long M, int d
 // attended[g, c] = sum_n att[g*N + n] * Xc[g*N + n, c]
 __global__ void att_pool_kernel(const float* __restrict__ att, const float* __restrict__ Xc, int N, int D,
                                 float* __restrict__ attended) {
+  ek_pdl_prologue();
   const int g = blockIdx.x;
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= D) return;
@@ -221,6 +234,7 @@ __global__ void att_pool_bwd_kernel(const float* __restrict__ dA, const float* _
                                     const float* __restrict__ E, const float* __restrict__ w, long long M, int N, int D,
                                     int dim, float* __restrict__ dXc, T* __restrict__ dE, float* __restrict__ dpre_out,
                                     float escale) {
+  ek_pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -245,6 +259,7 @@ __global__ void att_pool_bwd_kernel(const float* __restrict__ dA, const float* _
 // labels: float64 [B, S, S]; out fp32 [B, N, N, L]: plane c = (label == c+1)
 __global__ void onehot_adj_kernel(const double* __restrict__ labels, int S, int N, int L, long long total,
                                   float* __restrict__ out) {
+  ek_pdl_prologue();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const long long b = e / ((long long)N * N);
@@ -260,6 +275,7 @@ __global__ void onehot_adj_kernel(const double* __restrict__ labels, int S, int 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
                             const float* __restrict__ pow_state) {
+  ek_pdl_prologue();
   // pow_state = {b1^t, b2^t} lives in device memory so a captured CUDA graph stays valid across steps
   const float bc1 = 1.f - pow_state[0], bc2 = 1.f - pow_state[1];
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -276,6 +292,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 
 __global__ void adam_advance_kernel(float* pow_state, float b1, float b2) {
+  ek_pdl_prologue();
   pow_state[0] *= b1;
   pow_state[1] *= b2;
 }
@@ -287,6 +304,7 @@ template <typename T>
 __global__ void build_vq_kernel(const float* __restrict__ X, const float* __restrict__ qv,
                                 const uint8_t* __restrict__ flags, long long M, int N, int B, int D, int Dq,
                                 T* __restrict__ VQ, EkDrop dr) {
+  ek_pdl_prologue();
   // 8 consecutive columns per thread (D, Dq multiples of 8): one row lookup, 2 x 16-byte loads, one 16-byte store
   const int W = D + Dq;
   const int W8 = W / 8;
@@ -322,6 +340,7 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
                                     const TI* __restrict__ in2, long long ldi, EkDrop d0, EkDrop d1, EkDrop d2,
                                     long long M, int C, float* __restrict__ outf, long long ldf, int accumulate,
                                     TO* __restrict__ outT, long long ldo) {
+  ek_pdl_prologue();
   // V consecutive columns per thread (V = 4 needs C, pitches % 4 == 0; the compiler merges the accesses)
   const int CV = C / V;
   const long long total = M * CV;
@@ -356,7 +375,8 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
 // w = v * g / ||v||_F.  Two launches forward (partials; scale) and two backward, all deterministic.
 constexpr int WN_BLOCKS = 128;
 __global__ void wn_partial_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
-                                  float* __restrict__ part) {     // part[blk] = sum a*b over the block's slice
+                                  float* __restrict__ part) {
+  ek_pdl_prologue();     // part[blk] = sum a*b over the block's slice
   __shared__ float red[32];
   float s = 0.f;
   const long long n4 = ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) ? n / 4 : 0;
@@ -375,6 +395,7 @@ __device__ __forceinline__ float wn_total(const float* __restrict__ part, float*
 }
 __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ part,
                                 long long n, float* __restrict__ w, float* __restrict__ norm_out) {
+  ek_pdl_prologue();
   __shared__ float red[32];
   const float nrm = sqrtf(wn_total(part, red));
   const float sc = g[0] / nrm;
@@ -386,6 +407,7 @@ __global__ void wn_scale_kernel(const float* __restrict__ v, const float* __rest
 __global__ void wn_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v, const float* __restrict__ g,
                               const float* __restrict__ norm, const float* __restrict__ part, long long n,
                               float* __restrict__ dv, float* __restrict__ dg) {
+  ek_pdl_prologue();
   __shared__ float red[32];
   const float dot = wn_total(part, red);
   const float nrm = norm[0], gv = g[0];
@@ -395,7 +417,8 @@ __global__ void wn_bwd_kernel(const float* __restrict__ dw, const float* __restr
     dv[e] = c1 * dw[e] - c2 * v[e];
 }
 
-__global__ void rng_advance_kernel(unsigned long long* seed) { *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
+__global__ void rng_advance_kernel(unsigned long long* seed) {
+  ek_pdl_prologue(); *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
 
 inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
@@ -410,7 +433,7 @@ int ek_cast_f32_bf16_launch(const float* src, long long lds, bf16* dst, long lon
   EK_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0,
              EK_ERR_ALIGN, "cast_f32_bf16: cols/pitch must be multiples of 4 and pointers aligned");
   if (rows * cols == 0) return EK_OK;
-  cast_f32_bf16_kernel<<<grid_for(rows * cols / 4), 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+  ek_launch(cast_f32_bf16_kernel, grid_for(rows * cols / 4), 256, 0, st, src, lds, dst, ldd, rows, cols);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -419,14 +442,14 @@ int ek_copy_f32_launch(const float* src, long long lds, float* dst, long long ld
   EK_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0,
              EK_ERR_ALIGN, "copy_f32: cols/pitch must be multiples of 4 and pointers aligned");
   if (rows * cols == 0) return EK_OK;
-  copy_f32_kernel<<<grid_for(rows * cols / 4), 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+  ek_launch(copy_f32_kernel, grid_for(rows * cols / 4), 256, 0, st, src, lds, dst, ldd, rows, cols);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_cast_bf16_f32_launch(const bf16* src, long long lds, float* dst, long long ldd, long long rows, int cols,
                             cudaStream_t st) {
   if (rows * cols == 0) return EK_OK;
-  cast_bf16_f32_kernel<<<grid_for(rows * cols), 256, 0, st>>>(src, lds, dst, ldd, rows, cols);
+  ek_launch(cast_bf16_f32_kernel, grid_for(rows * cols), 256, 0, st, src, lds, dst, ldd, rows, cols);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -439,17 +462,17 @@ int ek_colsum_launch(int is_bf16, const void* src, long long ld, long long M, in
   if (nparts < 1) nparts = 1;
   dim3 grid(ek_div_up(N, 32), nparts);
   if (is_bf16)
-    colsum_part_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, ld, M, N, rowscale, workspace, nparts);
+    ek_launch(colsum_part_kernel<bf16>, grid, 256, 0, st, (const bf16*)src, ld, M, N, rowscale, workspace, nparts);
   else
-    colsum_part_kernel<float><<<grid, 256, 0, st>>>((const float*)src, ld, M, N, rowscale, workspace, nparts);
+    ek_launch(colsum_part_kernel<float>, grid, 256, 0, st, (const float*)src, ld, M, N, rowscale, workspace, nparts);
   EK_CHECK_LAUNCH();
-  colsum_final_kernel<<<ek_div_up(N, 128), 128, 0, st>>>(workspace, nparts, N, out);
+  ek_launch(colsum_final_kernel, ek_div_up(N, 128), 128, 0, st, workspace, nparts, N, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 
 int ek_row_zero_flags_launch(const float* X, long long M, int D, uint8_t* flags, cudaStream_t st) {
-  row_zero_flags_kernel<<<ek_div_up(M, 8), 256, 0, st>>>(X, M, D, flags);
+  ek_launch(row_zero_flags_kernel, ek_div_up(M, 8), 256, 0, st, X, M, D, flags);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -457,8 +480,8 @@ int ek_row_zero_flags_launch(const float* X, long long M, int D, uint8_t* flags,
 int ek_group_rowsum_launch(int is_bf16, const void* src, long long ld, int N, int B, int S, int D, const uint8_t* flags,
                            float* out, cudaStream_t st) {
   dim3 grid(B, ek_div_up(D, 128));
-  if (is_bf16) group_rowsum_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)src, ld, N, B, S, D, flags, out);
-  else group_rowsum_kernel<float><<<grid, 128, 0, st>>>((const float*)src, ld, N, B, S, D, flags, out);
+  if (is_bf16) ek_launch(group_rowsum_kernel<bf16>, grid, 128, 0, st, (const bf16*)src, ld, N, B, S, D, flags, out);
+  else ek_launch(group_rowsum_kernel<float>, grid, 128, 0, st, (const float*)src, ld, N, B, S, D, flags, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -466,15 +489,15 @@ int ek_group_rowsum_launch(int is_bf16, const void* src, long long ld, int N, in
 int ek_combine_diff_fwd_launch(int is_bf16, const float* X3, long long BN, int D, int mode, float c1, float c2,
                                float c3, float* Xc, void* CAT, cudaStream_t st) {
   if (is_bf16)
-    combine_diff_fwd_kernel<bf16><<<grid_for(BN * D), 256, 0, st>>>(X3, BN, D, mode, c1, c2, c3, Xc, (bf16*)CAT);
+    ek_launch(combine_diff_fwd_kernel<bf16>, grid_for(BN * D), 256, 0, st, X3, BN, D, mode, c1, c2, c3, Xc, (bf16*)CAT);
   else
-    combine_diff_fwd_kernel<float><<<grid_for(BN * D), 256, 0, st>>>(X3, BN, D, mode, c1, c2, c3, Xc, (float*)CAT);
+    ek_launch(combine_diff_fwd_kernel<float>, grid_for(BN * D), 256, 0, st, X3, BN, D, mode, c1, c2, c3, Xc, (float*)CAT);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_combine_diff_bwd_launch(const float* dXc, const float* dCAT, long long BN, int D, int mode, float c1, float c2,
                                float c3, float* dX3, cudaStream_t st) {
-  combine_diff_bwd_kernel<<<grid_for(BN * D), 256, 0, st>>>(dXc, dCAT, BN, D, mode, c1, c2, c3, dX3);
+  ek_launch(combine_diff_bwd_kernel, grid_for(BN * D), 256, 0, st, dXc, dCAT, BN, D, mode, c1, c2, c3, dX3);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -482,19 +505,19 @@ int ek_combine_diff_bwd_launch(const float* dXc, const float* dCAT, long long BN
 int ek_gate_fwd_launch(int is_bf16, const float* pre, long long M, int D, void* ctx, void* gate, void* CAT, EkDrop dc,
                        EkDrop dg, cudaStream_t st) {
   if (is_bf16)
-    gate_fwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT, dc, dg);
+    ek_launch(gate_fwd_kernel<bf16>, grid_for(M * D), 256, 0, st, pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT, dc, dg);
   else
-    gate_fwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(pre, M, D, (float*)ctx, (float*)gate, (float*)CAT, dc, dg);
+    ek_launch(gate_fwd_kernel<float>, grid_for(M * D), 256, 0, st, pre, M, D, (float*)ctx, (float*)gate, (float*)CAT, dc, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_gate_bwd_launch(int is_bf16, const float* dCAT, const void* ctx, const void* gate, long long M, int D,
                        void* dpre, EkDrop dc, EkDrop dg, cudaStream_t st) {
   if (is_bf16)
-    gate_bwd_kernel<bf16><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre,
+    ek_launch(gate_bwd_kernel<bf16>, grid_for(M * D), 256, 0, st, dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre,
                                                            dc, dg);
   else
-    gate_bwd_kernel<float><<<grid_for(M * D), 256, 0, st>>>(dCAT, (const float*)ctx, (const float*)gate, M, D,
+    ek_launch(gate_bwd_kernel<float>, grid_for(M * D), 256, 0, st, dCAT, (const float*)ctx, (const float*)gate, M, D,
                                                             (float*)dpre, dc, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -502,9 +525,9 @@ int ek_gate_bwd_launch(int is_bf16, const float* dCAT, const void* ctx, const vo
 
 int ek_att_pool_fwd_launch(const float* E, long long M, int N, int D, int dim, const float* w, const float* b,
                            const float* Xc, float* att, float* attended, cudaStream_t st) {
-  att_score_kernel<<<ek_div_up(M, 8), 256, 0, st>>>(E, M, dim, w, b, att);
+  ek_launch(att_score_kernel, ek_div_up(M, 8), 256, 0, st, E, M, dim, w, b, att);
   EK_CHECK_LAUNCH();
-  att_pool_kernel<<<dim3((unsigned)(M / N), ek_div_up(D, 128)), 128, 0, st>>>(att, Xc, N, D, attended);
+  ek_launch(att_pool_kernel, dim3((unsigned)(M / N), ek_div_up(D, 128)), 128, 0, st, att, Xc, N, D, attended);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -512,10 +535,10 @@ int ek_att_pool_bwd_launch(int is_bf16, const float* dA, const float* dattw, con
                            const float* E, const float* w, long long M, int N, int D, int dim, float* dXc, void* dE,
                            float* dpre, float escale, cudaStream_t st) {
   if (is_bf16)
-    att_pool_bwd_kernel<bf16><<<ek_div_up(M, 8), 256, 0, st>>>(dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, (bf16*)dE,
+    ek_launch(att_pool_bwd_kernel<bf16>, ek_div_up(M, 8), 256, 0, st, dA, dattw, att, Xc, E, w, M, N, D, dim, dXc, (bf16*)dE,
                                                                 dpre, escale);
   else
-    att_pool_bwd_kernel<float><<<ek_div_up(M, 8), 256, 0, st>>>(dA, dattw, att, Xc, E, w, M, N, D, dim, dXc,
+    ek_launch(att_pool_bwd_kernel<float>, ek_div_up(M, 8), 256, 0, st, dA, dattw, att, Xc, E, w, M, N, D, dim, dXc,
                                                                  (float*)dE, dpre, escale);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -524,7 +547,7 @@ int ek_att_pool_bwd_launch(int is_bf16, const float* dA, const float* dattw, con
 int ek_onehot_adj_launch(const double* labels, int B, int S, int N, int L, float* out, cudaStream_t st) {
   const long long total = (long long)B * N * N;
   if (total == 0) return EK_OK;
-  onehot_adj_kernel<<<grid_for(total), 256, 0, st>>>(labels, S, N, L, total, out);
+  ek_launch(onehot_adj_kernel, grid_for(total), 256, 0, st, labels, S, N, L, total, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -532,13 +555,13 @@ int ek_onehot_adj_launch(const double* labels, int B, int S, int N, int L, float
 int ek_adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                    float wd, const float* pow_state, cudaStream_t st) {
   if (n == 0) return EK_OK;
-  adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, wd, pow_state);
+  ek_launch(adam_kernel, grid_for(n), 256, 0, st, p, g, m, v, n, lr, b1, b2, eps, wd, pow_state);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 
 int ek_adam_advance_launch(float* pow_state, float b1, float b2, cudaStream_t st) {
-  adam_advance_kernel<<<1, 1, 0, st>>>(pow_state, b1, b2);
+  ek_launch(adam_advance_kernel, 1, 1, 0, st, pow_state, b1, b2);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -547,8 +570,8 @@ int ek_build_vq_launch(int is_bf16, const float* X, const float* qv, const uint8
                        int D, int Dq, void* VQ, EkDrop dr, cudaStream_t st) {
   EK_REQUIRE(D % 8 == 0 && Dq % 8 == 0, EK_ERR_SHAPE, "build_vq: D=%d Dq=%d must be multiples of 8", D, Dq);
   const int g = grid_for(M * ((D + Dq) / 8));
-  if (is_bf16) build_vq_kernel<bf16><<<g, 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
-  else build_vq_kernel<float><<<g, 256, 0, st>>>(X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
+  if (is_bf16) ek_launch(build_vq_kernel<bf16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
+  else ek_launch(build_vq_kernel<float>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -558,16 +581,16 @@ static void drop_combine_dispatch(int in_bf16, int out_bf16, int nin, const void
                                   long long ldf, int accumulate, void* outT, long long ldo, cudaStream_t st) {
   const int g = grid_for(M * (C / V));
   if (in_bf16 && out_bf16)
-    drop_combine_kernel<bf16, bf16, V><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
+    ek_launch(drop_combine_kernel<bf16, bf16, V>, g, 256, 0, st, nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
                                                          d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
   else if (in_bf16)
-    drop_combine_kernel<bf16, float, V><<<g, 256, 0, st>>>(nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
+    ek_launch(drop_combine_kernel<bf16, float, V>, g, 256, 0, st, nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
                                                           d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
   else if (out_bf16)
-    drop_combine_kernel<float, bf16, V><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1, (const float*)in2,
+    ek_launch(drop_combine_kernel<float, bf16, V>, g, 256, 0, st, nin, (const float*)in0, (const float*)in1, (const float*)in2,
                                                           ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
   else
-    drop_combine_kernel<float, float, V><<<g, 256, 0, st>>>(nin, (const float*)in0, (const float*)in1,
+    ek_launch(drop_combine_kernel<float, float, V>, g, 256, 0, st, nin, (const float*)in0, (const float*)in1,
                                                            (const float*)in2, ldi, d0, d1, d2, M, C, outf, ldf,
                                                            accumulate, (float*)outT, ldo);
 }
@@ -581,7 +604,7 @@ int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, 
   return EK_OK;
 }
 int ek_rng_advance_launch(unsigned long long* seed, cudaStream_t st) {
-  rng_advance_kernel<<<1, 1, 0, st>>>(seed);
+  ek_launch(rng_advance_kernel, 1, 1, 0, st, seed);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -589,17 +612,17 @@ int ek_rng_advance_launch(unsigned long long* seed, cudaStream_t st) {
 // workspace: WN_BLOCKS (128) floats
 int ek_wn_fwd_launch(const float* v, const float* g, long long n, float* w, float* norm_out, float* workspace,
                      cudaStream_t st) {
-  wn_partial_kernel<<<WN_BLOCKS, 256, 0, st>>>(v, v, n, workspace);
+  ek_launch(wn_partial_kernel, WN_BLOCKS, 256, 0, st, v, v, n, workspace);
   EK_CHECK_LAUNCH();
-  wn_scale_kernel<<<grid_for(n), 256, 0, st>>>(v, g, workspace, n, w, norm_out);
+  ek_launch(wn_scale_kernel, grid_for(n), 256, 0, st, v, g, workspace, n, w, norm_out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_wn_bwd_launch(const float* dw, const float* v, const float* g, const float* norm, long long n, float* dv,
                      float* dg, float* workspace, cudaStream_t st) {
-  wn_partial_kernel<<<WN_BLOCKS, 256, 0, st>>>(dw, v, n, workspace);
+  ek_launch(wn_partial_kernel, WN_BLOCKS, 256, 0, st, dw, v, n, workspace);
   EK_CHECK_LAUNCH();
-  wn_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dw, v, g, norm, workspace, n, dv, dg);
+  ek_launch(wn_bwd_kernel, grid_for(n), 256, 0, st, dw, v, g, norm, workspace, n, dv, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -12,6 +12,7 @@ template <int TM>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long long sam, long long sak,
                 const float* __restrict__ B, long long sbk, long long sbn, EkEpilogue ep) {
+  ek_pdl_prologue();
   constexpr int BT = 16 * TM;   // block tile (square)
   constexpr int BK = 16;
   constexpr int PER = BT * BK / 256;   // elements per thread per operand per slab
@@ -98,10 +99,10 @@ int ek_gemm_f32_launch(int M, int N, int K, const float* A, long long sam, long 
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_f32: bad shape M=%d N=%d K=%d", M, N, K);
   if ((long long)M * N >= 128 * 128 * 64) {
     dim3 grid(ek_div_up(N, 128), ek_div_up(M, 128));
-    gemm_f32_kernel<8><<<grid, 256, 0, stream>>>(M, N, K, A, sam, sak, B, sbk, sbn, ep);
+    ek_launch(gemm_f32_kernel<8>, grid, 256, 0, stream, M, N, K, A, sam, sak, B, sbk, sbn, ep);
   } else {
     dim3 grid(ek_div_up(N, 64), ek_div_up(M, 64));
-    gemm_f32_kernel<4><<<grid, 256, 0, stream>>>(M, N, K, A, sam, sak, B, sbk, sbn, ep);
+    ek_launch(gemm_f32_kernel<4>, grid, 256, 0, stream, M, N, K, A, sam, sak, B, sbk, sbn, ep);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;

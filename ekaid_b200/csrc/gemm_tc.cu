@@ -282,6 +282,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CL > 1) cluster_sync_all();        // peer barriers initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ek_pdl_wait();     // barriers, TMEM and tensor maps are set up; from here on we touch the previous kernel's data
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -604,7 +605,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
   const int slots = num_sms() / CL;
   const int grid = CL * (units < slots ? units : slots);
   if (CL == 1) {
-    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep, vec_ok, splits);
+    ek_launch(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, M, N, K, ep, vec_ok, splits);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

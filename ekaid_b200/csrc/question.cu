@@ -8,6 +8,7 @@ namespace {
 template <typename T>
 __global__ void embed_gather_kernel(const long long* __restrict__ q, const float* __restrict__ emb,
                                     const float* __restrict__ emb2, int B, int L, int ed, T* __restrict__ E) {
+  ek_pdl_prologue();
   const int row = blockIdx.x;                 // l*B + b
   const int l = row / B, b = row % B;
   const long long tok = q[(size_t)b * L + l];
@@ -23,6 +24,7 @@ __global__ void embed_gather_kernel(const long long* __restrict__ q, const float
 __global__ void __launch_bounds__(128)
 embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict__ dE, long long ldde, int B, int L,
                         int ed, float* __restrict__ demb) {
+  ek_pdl_prologue();
   extern __shared__ int rows[];        // up to B*L matching rows
   __shared__ int count;
   __shared__ float part[4][32];
@@ -62,6 +64,7 @@ template <typename T>
 __global__ void gru_cell_fwd_kernel(const float* __restrict__ gi, float* __restrict__ gh,
                                     const float* __restrict__ hprev, int B, int H, float* __restrict__ h,
                                     T* __restrict__ hT, float* __restrict__ gates, const float* __restrict__ gh_reset) {
+  ek_pdl_prologue();
   const int total = B * H;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int b = e / H, c = e % H;
@@ -91,6 +94,7 @@ __global__ void gru_cell_bwd_kernel(const float* __restrict__ dh, const float* _
                                     const float* __restrict__ hprev, int B, int H, float* __restrict__ dgi,
                                     float* __restrict__ dgh, T* __restrict__ dgiT, T* __restrict__ dghT,
                                     float* __restrict__ dhprev) {
+  ek_pdl_prologue();
   const int total = B * H;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int b = e / H, c = e % H;
@@ -116,6 +120,7 @@ __global__ void gru_cell_bwd_kernel(const float* __restrict__ dh, const float* _
 template <typename T>
 __global__ void rowdot_kernel(const T* __restrict__ A, long long lda, long long M, int K, const float* __restrict__ w,
                               const float* __restrict__ b, float* __restrict__ out) {
+  ek_pdl_prologue();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -130,6 +135,7 @@ __global__ void rowdot_kernel(const T* __restrict__ A, long long lda, long long 
 // re-views the contiguous [L,B] buffer as [B,1,L]:  Wt[b, l] = S_flat[b*L + l].
 // qv[b, :] = sum_l Wt[b,l] * Hs[l*B + b, :]
 __global__ void qpool_softmax_kernel(const float* __restrict__ a, int B, int L, float* __restrict__ S) {
+  ek_pdl_prologue();
   __shared__ float red[32];
   const int l = blockIdx.x;
   float mx = -INFINITY;
@@ -148,6 +154,7 @@ __global__ void qpool_softmax_kernel(const float* __restrict__ a, int B, int L, 
 }
 __global__ void qpool_sum_kernel(const float* __restrict__ S, const float* __restrict__ Hs, int B, int L, int H,
                                  float* __restrict__ qv) {
+  ek_pdl_prologue();
   const int b = blockIdx.x;
   for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < H; c += gridDim.y * blockDim.x) {
     float s = 0.f;
@@ -160,6 +167,7 @@ __global__ void qpool_sum_kernel(const float* __restrict__ S, const float* __res
 __global__ void qpool_bwd1_kernel(const float* __restrict__ dqv, const float* __restrict__ S,
                                   const float* __restrict__ Hs, int B, int L, int H, float* __restrict__ dS,
                                   float* __restrict__ dHs) {
+  ek_pdl_prologue();
   __shared__ float red[32];
   const int b = blockIdx.x;
   for (int l = 0; l < L; ++l) {
@@ -177,6 +185,7 @@ __global__ void qpool_bwd1_kernel(const float* __restrict__ dqv, const float* __
 // backward part 2 (one CTA per l): softmax over b:  da[l,b] = S * (dS - sum_b S dS)
 __global__ void qpool_bwd2_kernel(const float* __restrict__ S, const float* __restrict__ dS, int B, int L,
                                   float* __restrict__ da) {
+  ek_pdl_prologue();
   __shared__ float red[32];
   const int l = blockIdx.x;
   float s = 0.f;
@@ -189,6 +198,7 @@ __global__ void qpool_bwd2_kernel(const float* __restrict__ S, const float* __re
 template <typename T>
 __global__ void qatt_tanh_bwd_kernel(const float* __restrict__ da, const float* __restrict__ w2,
                                      const T* __restrict__ a1, long long M, int H, T* __restrict__ dpre) {
+  ek_pdl_prologue();
   const long long total = M * H;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -200,6 +210,7 @@ __global__ void qatt_tanh_bwd_kernel(const float* __restrict__ da, const float* 
 }
 // y += x  (fp32), used to accumulate gradient streams
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  ek_pdl_prologue();
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
     y[e] += x[e];
 }
@@ -214,14 +225,14 @@ inline int grid_for(long long total, int block = 256) {
 
 int ek_embed_gather_launch(int is_bf16, const long long* q, const float* emb, const float* emb2, int B, int L, int ed,
                            void* E, cudaStream_t st) {
-  if (is_bf16) embed_gather_kernel<bf16><<<B * L, 128, 0, st>>>(q, emb, emb2, B, L, ed, (bf16*)E);
-  else embed_gather_kernel<float><<<B * L, 128, 0, st>>>(q, emb, emb2, B, L, ed, (float*)E);
+  if (is_bf16) ek_launch(embed_gather_kernel<bf16>, B * L, 128, 0, st, q, emb, emb2, B, L, ed, (bf16*)E);
+  else ek_launch(embed_gather_kernel<float>, B * L, 128, 0, st, q, emb, emb2, B, L, ed, (float*)E);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ldde, int B, int L, int ed, int V,
                                float* demb, cudaStream_t st) {
-  embed_gather_bwd_kernel<<<dim3(V, ek_div_up(ed, 32)), 128, (size_t)B * L * sizeof(int), st>>>(q, dE, ldde, B, L, ed,
+  ek_launch(embed_gather_bwd_kernel, dim3(V, ek_div_up(ed, 32)), 128, (size_t)B * L * sizeof(int), st, q, dE, ldde, B, L, ed,
                                                                                                   demb);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -229,10 +240,10 @@ int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ld
 int ek_gru_cell_fwd_launch(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h,
                            void* hT, float* gates, const float* gh_reset, cudaStream_t st) {
   if (is_bf16)
-    gru_cell_fwd_kernel<bf16><<<grid_for((long long)B * H), 256, 0, st>>>(gi, gh, hprev, B, H, h, (bf16*)hT, gates,
+    ek_launch(gru_cell_fwd_kernel<bf16>, grid_for((long long)B * H), 256, 0, st, gi, gh, hprev, B, H, h, (bf16*)hT, gates,
                                                                            gh_reset);
   else
-    gru_cell_fwd_kernel<float><<<grid_for((long long)B * H), 256, 0, st>>>(gi, gh, hprev, B, H, h, (float*)hT, gates,
+    ek_launch(gru_cell_fwd_kernel<float>, grid_for((long long)B * H), 256, 0, st, gi, gh, hprev, B, H, h, (float*)hT, gates,
                                                                             gh_reset);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -240,46 +251,46 @@ int ek_gru_cell_fwd_launch(int is_bf16, const float* gi, float* gh, const float*
 int ek_gru_cell_bwd_launch(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H,
                            float* dgi, float* dgh, void* dgiT, void* dghT, float* dhprev, cudaStream_t st) {
   if (is_bf16)
-    gru_cell_bwd_kernel<bf16><<<grid_for((long long)B * H), 256, 0, st>>>(dh, gates, hprev, B, H, dgi, dgh, (bf16*)dgiT,
+    ek_launch(gru_cell_bwd_kernel<bf16>, grid_for((long long)B * H), 256, 0, st, dh, gates, hprev, B, H, dgi, dgh, (bf16*)dgiT,
                                                                            (bf16*)dghT, dhprev);
   else
-    gru_cell_bwd_kernel<float><<<grid_for((long long)B * H), 256, 0, st>>>(dh, gates, hprev, B, H, dgi, dgh,
+    ek_launch(gru_cell_bwd_kernel<float>, grid_for((long long)B * H), 256, 0, st, dh, gates, hprev, B, H, dgi, dgh,
                                                                             (float*)dgiT, (float*)dghT, dhprev);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_rowdot_launch(int is_bf16, const void* A, long long lda, long long M, int K, const float* w, const float* b,
                      float* out, cudaStream_t st) {
-  if (is_bf16) rowdot_kernel<bf16><<<ek_div_up(M, 8), 256, 0, st>>>((const bf16*)A, lda, M, K, w, b, out);
-  else rowdot_kernel<float><<<ek_div_up(M, 8), 256, 0, st>>>((const float*)A, lda, M, K, w, b, out);
+  if (is_bf16) ek_launch(rowdot_kernel<bf16>, ek_div_up(M, 8), 256, 0, st, (const bf16*)A, lda, M, K, w, b, out);
+  else ek_launch(rowdot_kernel<float>, ek_div_up(M, 8), 256, 0, st, (const float*)A, lda, M, K, w, b, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_qpool_fwd_launch(const float* a, const float* Hs, int B, int L, int H, float* S, float* qv, cudaStream_t st) {
-  qpool_softmax_kernel<<<L, 256, 0, st>>>(a, B, L, S);
+  ek_launch(qpool_softmax_kernel, L, 256, 0, st, a, B, L, S);
   EK_CHECK_LAUNCH();
-  qpool_sum_kernel<<<dim3(B, ek_div_up(H, 256)), 256, 0, st>>>(S, Hs, B, L, H, qv);
+  ek_launch(qpool_sum_kernel, dim3(B, ek_div_up(H, 256)), 256, 0, st, S, Hs, B, L, H, qv);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_qpool_bwd_launch(const float* dqv, const float* S, const float* Hs, int B, int L, int H, float* dS, float* da,
                         float* dHs, cudaStream_t st) {
-  qpool_bwd1_kernel<<<B, 256, 0, st>>>(dqv, S, Hs, B, L, H, dS, dHs);
+  ek_launch(qpool_bwd1_kernel, B, 256, 0, st, dqv, S, Hs, B, L, H, dS, dHs);
   EK_CHECK_LAUNCH();
-  qpool_bwd2_kernel<<<L, 256, 0, st>>>(S, dS, B, L, da);
+  ek_launch(qpool_bwd2_kernel, L, 256, 0, st, S, dS, B, L, da);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_qatt_tanh_bwd_launch(int is_bf16, const float* da, const float* w2, const void* a1, long long M, int H,
                             void* dpre, cudaStream_t st) {
-  if (is_bf16) qatt_tanh_bwd_kernel<bf16><<<grid_for(M * H), 256, 0, st>>>(da, w2, (const bf16*)a1, M, H, (bf16*)dpre);
-  else qatt_tanh_bwd_kernel<float><<<grid_for(M * H), 256, 0, st>>>(da, w2, (const float*)a1, M, H, (float*)dpre);
+  if (is_bf16) ek_launch(qatt_tanh_bwd_kernel<bf16>, grid_for(M * H), 256, 0, st, da, w2, (const bf16*)a1, M, H, (bf16*)dpre);
+  else ek_launch(qatt_tanh_bwd_kernel<float>, grid_for(M * H), 256, 0, st, da, w2, (const float*)a1, M, H, (float*)dpre);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_add_inplace_launch(float* y, const float* x, long long n, cudaStream_t st) {
   if (n == 0) return EK_OK;
-  add_inplace_kernel<<<grid_for(n), 256, 0, st>>>(y, x, n);
+  ek_launch(add_inplace_kernel, grid_for(n), 256, 0, st, y, x, n);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -76,6 +76,9 @@ int ekaid_abi_version(void);
 const char* ekaid_last_error(void);
 /* 0 if the current device is sm_100 (B200), EKAID_ERR_ARCH otherwise */
 int ekaid_check_device(void);
+/* Programmatic dependent launch between consecutive kernels of a stream (default on; EKAID_B200_PDL=0 disables).
+ * Returns the previous setting.  Ordering and results are identical either way; only launch latency overlaps. */
+int ekaid_set_pdl(int on);
 
 /* ---- dense contractions ---------------------------------------------------------------------------------
  * C[M,N] = op(A) op(B):  transA = 0: A is [M,K] (lda), 1: A is [K,M];  transB = 0: B is [N,K] (ldb) i.e. an
