@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--graph", default="all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--qlen", type=int, default=20, help="question length (20 = the reference's; other values are experiments)")
     ap.add_argument("--no-pdl", action="store_true", help="turn programmatic dependent launch between kernels off")
     ap.add_argument("--cpu-sample-batch", type=int, default=16)
     ap.add_argument("--no-dropout", action="store_true", help="train step with modules in eval mode (no dropout)")
@@ -247,7 +248,7 @@ def main():
     # synthetic loader: 4 distinct host batches (pinned), per-rank seeds
     host = []
     for i in range(4):
-        b = synthetic_batch(B, N, seed=1234 + 17 * rank + i)
+        b = synthetic_batch(B, N, seed=1234 + 17 * rank + i, q_len=args.qlen)
         host.append(tuple(t.contiguous().pin_memory() for t in select_fields(b)))
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     torch.cuda.synchronize()

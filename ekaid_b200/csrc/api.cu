@@ -74,6 +74,10 @@ int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
 int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
+int ek_gru_seq_fwd_launch(const float*, const bf16*, const float*, int, int, int, float*, bf16*, float*, unsigned int*,
+                          cudaStream_t);
+int ek_gru_seq_bwd_launch(const float*, const float*, const float*, const bf16*, int, int, int, float*, float*, bf16*,
+                          bf16*, unsigned int*, cudaStream_t);
 int ek_gru_cell_fwd_launch(int, const float*, float*, const float*, int, int, float*, void*, float*, const float*,
                            cudaStream_t);
 int ek_gru_cell_bwd_launch(int, const float*, const float*, const float*, int, int, float*, float*, void*, void*,
@@ -288,6 +292,15 @@ int ekaid_gru_cell_fwd(int is_bf16, const float* gi, float* gh, const float* hpr
 int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H, float* dgi,
                        float* dgh, void* dgiT, void* dghT, float* dhprev, void* stream) {
   return ek_gru_cell_bwd_launch(is_bf16, dh, gates, hprev, B, H, dgi, dgh, dgiT, dghT, dhprev, ST);
+}
+int ekaid_gru_seq_fwd(const float* gi, const void* Whh, const float* bhh, int B, int H, int L, float* Hs, void* HsT,
+                      float* gates, void* barrier_ws, void* stream) {
+  return ek_gru_seq_fwd_launch(gi, (const bf16*)Whh, bhh, B, H, L, Hs, (bf16*)HsT, gates, (unsigned int*)barrier_ws, ST);
+}
+int ekaid_gru_seq_bwd(const float* dHs, const float* gates, const float* Hs, const void* Whh, int B, int H, int L,
+                      float* dgi, float* dgh, void* dgiT, void* dghT, void* barrier_ws, void* stream) {
+  return ek_gru_seq_bwd_launch(dHs, gates, Hs, (const bf16*)Whh, B, H, L, dgi, dgh, (bf16*)dgiT, (bf16*)dghT,
+                               (unsigned int*)barrier_ws, ST);
 }
 int ekaid_rowdot(int is_bf16, const void* A, int64_t lda, int64_t M, int K, const float* w, const float* b, float* out,
                  void* stream) {

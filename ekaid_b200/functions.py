@@ -15,6 +15,7 @@ Tensors that feed GEMMs are kept in the operand type T of the precision mode: bf
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -300,6 +301,29 @@ class LinearFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # question path
 # ------------------------------------------------------------------------------------------------
+GRU_SEQ = os.environ.get("EKAID_B200_GRU_SEQ", "1") != "0"     # 0: per-step GEMM + cell kernels on the bf16 path too
+GRU_SEQ_MAX_BATCH = 64
+_barrier_bufs = {}
+
+
+def _barrier_ws(dev):
+    """4 bytes of device memory per (device, stream) for the persistent GRU kernels' grid barrier."""
+    key = (str(dev), torch.cuda.current_stream().cuda_stream)
+    if key not in _barrier_bufs:
+        _barrier_bufs[key] = torch.zeros(4, dtype=torch.int32, device=dev)
+    return _barrier_bufs[key]
+
+
+def _gru_seq_ok(pc, dev, B, H):
+    """The one-launch recurrence covers the bf16 path when all H/8 CTAs are co-resident (see gru_seq.cu).  Every CTA
+    streams the whole [B, H] / [B, 3H] operand each step, so beyond one 64-row pass the per-step tcgen05 GEMMs win
+    (measured at B = 256: 397 vs 312 us forward)."""
+    if not (GRU_SEQ and pc.bf16 and H % 512 == 0 and B <= GRU_SEQ_MAX_BATCH):
+        return False
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    return H // 8 <= sms
+
+
 class QuestionFn(torch.autograd.Function):
     """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156)."""
 
@@ -321,16 +345,21 @@ class QuestionFn(torch.autograd.Function):
         # operand-type copy with one leading zero block: HsT[t] = h_{t-1}, so "previous h of every step" is a view
         HsT = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev)
         gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
-        # gh accumulator: armed with b_hh (broadcast copy), "gh += h W_hh^T" as a split-K GEMM (M = B is tiny, so the
-        # K loop is what can be spread over the SMs), re-armed by the cell kernel
-        gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
-        call("copy_f32", bhhc.data_ptr(), 0, gh.data_ptr(), 3 * H, B, 3 * H)
-        for t in range(L):
-            gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, addend=gh, C=gh)
-            hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
-            call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
-                 Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr(),
-                 bhhc.data_ptr())
+        if _gru_seq_ok(pc, dev, B, H):
+            # the whole recurrence in one persistent launch (gru_seq.cu)
+            call("gru_seq_fwd", gi.data_ptr(), WhhT.data_ptr(), bhhc.data_ptr(), B, H, L, Hs.data_ptr(), HsT.data_ptr(),
+                 gates.data_ptr(), _barrier_ws(dev).data_ptr())
+        else:
+            # gh accumulator: armed with b_hh (broadcast copy), "gh += h W_hh^T" as a split-K GEMM (M = B is tiny, so
+            # the K loop is what can be spread over the SMs), re-armed by the cell kernel
+            gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
+            call("copy_f32", bhhc.data_ptr(), 0, gh.data_ptr(), 3 * H, B, 3 * H)
+            for t in range(L):
+                gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, addend=gh, C=gh)
+                hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+                call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
+                     Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr(),
+                     bhhc.data_ptr())
         HsT_cur = HsT[B:]
         if drop is not None and drop.on:          # Dropout(0.2) on the input of W1 (language_model.py:123-124)
             Hd = torch.empty(L * B, H, dtype=pc.T, device=dev)
@@ -387,18 +416,22 @@ class QuestionFn(torch.autograd.Function):
         dgh = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
         dgiT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgi
         dghT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgh
-        carry = torch.empty(B, H, dtype=torch.float32, device=dev)
-        for t in range(L - 1, -1, -1):
-            sl = slice(t * B, (t + 1) * B)
-            if t < L - 1:
-                call("add_inplace", dHs[sl].data_ptr(), carry.data_ptr(), B * H)
-            hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
-            # the cell kernel writes dh*z into `carry`; the split-K GEMM then adds dgh W_hh onto it
-            call("gru_cell_bwd", pc.f, dHs[sl].data_ptr(), gates[t].data_ptr(), ptr(hprev), B, H, dgi[sl].data_ptr(),
-                 dgh[sl].data_ptr(), dgiT[sl].data_ptr() if pc.bf16 else None,
-                 dghT[sl].data_ptr() if pc.bf16 else None, carry.data_ptr())
-            if t > 0:
-                gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=carry, C=carry)   # carry = dh*z + dgh W_hh
+        if _gru_seq_ok(pc, dev, B, H):
+            call("gru_seq_bwd", dHs.data_ptr(), gates.data_ptr(), Hs.data_ptr(), WhhT.data_ptr(), B, H, L, dgi.data_ptr(),
+                 dgh.data_ptr(), dgiT.data_ptr(), dghT.data_ptr(), _barrier_ws(dev).data_ptr())
+        else:
+            carry = torch.empty(B, H, dtype=torch.float32, device=dev)
+            for t in range(L - 1, -1, -1):
+                sl = slice(t * B, (t + 1) * B)
+                if t < L - 1:
+                    call("add_inplace", dHs[sl].data_ptr(), carry.data_ptr(), B * H)
+                hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+                # the cell kernel writes dh*z into `carry`; the split-K GEMM then adds dgh W_hh onto it
+                call("gru_cell_bwd", pc.f, dHs[sl].data_ptr(), gates[t].data_ptr(), ptr(hprev), B, H, dgi[sl].data_ptr(),
+                     dgh[sl].data_ptr(), dgiT[sl].data_ptr() if pc.bf16 else None,
+                     dghT[sl].data_ptr() if pc.bf16 else None, carry.data_ptr())
+                if t > 0:
+                    gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=carry, C=carry)   # carry = dh*z + dgh W_hh
         dWih = gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=_dst(kk["Wih"], (3 * H, 2 * ed), dev))
         dbih = colsum(dgi, L * B, 3 * H, out=_dst(kk["bih"], (3 * H,), dev))
         dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1, out=_dst(kk["Whh"], (3 * H, H), dev))

@@ -187,6 +187,16 @@ int ekaid_gru_cell_fwd(int is_bf16, const float* gi, float* gh, const float* hpr
                        float* gates, const float* gh_reset, void* stream);
 int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const float* hprev, int B, int H, float* dgi,
                        float* dgh, void* dgiT, void* dghT, float* dhprev, void* stream);
+/* The whole recurrence of forward_all (:106-115) / its BPTT in ONE persistent launch (bf16 tensor-core path): CTA c owns
+ * hidden units 8c..8c+7, keeps its slice of W_hh in shared memory, and a grid-wide barrier separates the time steps.
+ * Rows are time-major (t*B + b).  gi [L*B,3H] = x W_ih^T + b_ih; Whh [3H,H] bf16; Hs [L*B,H] fp32; HsT [(L+1)*B,H] bf16
+ * whose block 0 (h_{-1} = 0) the caller zeroes; gates [L,B,4H] saves (r,z,n,gh_n); dHs [L*B,H] = gradient reaching h_t from
+ * outside the recurrence; dgi/dgh [L*B,3H] fp32 with bf16 copies dgiT/dghT.  barrier_ws: 4 bytes of device memory.
+ * Requires H % 512 == 0 and H/8 <= number of SMs (EKAID_ERR_UNSUPPORTED otherwise: use the per-step entry points). */
+int ekaid_gru_seq_fwd(const float* gi, const void* Whh, const float* bhh, int B, int H, int L, float* Hs, void* HsT,
+                      float* gates, void* barrier_ws, void* stream);
+int ekaid_gru_seq_bwd(const float* dHs, const float* gates, const float* Hs, const void* Whh, int B, int H, int L,
+                      float* dgi, float* dgh, void* dgiT, void* dghT, void* barrier_ws, void* stream);
 /* out[m] = A[m,:] . w + b[0]   (W2_self_att_q, :142) */
 int ekaid_rowdot(int is_bf16, const void* A, int64_t lda, int64_t M, int K, const float* w, const float* b, float* out,
                  void* stream);

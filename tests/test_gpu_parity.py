@@ -364,3 +364,36 @@ def test_full_size_batch64_forward_and_consistency():
         full, _ = enc(v.clone(), adj, q)
         part, _ = enc(v[:8].clone(), adj[:8], q[:8])
     assert torch.equal(full[:8], part)
+
+
+@pytest.mark.parametrize("B", [1, 3, 64, 130])
+def test_gru_one_launch_recurrence_matches_step_kernels(B):
+    """gru_seq.cu (all 20 steps in one persistent launch, grid barrier between steps) against the per-step GEMM + cell
+    kernels it replaces on the bf16 path, forward and BPTT, including ragged and multi-pass batch sizes."""
+    from ekaid_b200 import functions as F
+    from ekaid_b200.functions import PC
+    dev = _dev()
+    z, meta = load_case("c1_b3_n52_all_grads")
+    sd, inp, _ = case_inputs(meta)
+    g = torch.Generator().manual_seed(11 + B)
+    question = torch.randint(0, 100, (B, 20), generator=g).to(dev)
+    w = torch.randn(B, 1024, generator=g).to(dev)
+    res = {}
+    old = (F.GRU_SEQ, F.GRU_SEQ_MAX_BATCH)
+    F.GRU_SEQ_MAX_BATCH = 1 << 20          # exercise the multi-pass code too, whatever the dispatch heuristic says
+    try:
+        for mode in (True, False):
+            F.GRU_SEQ = mode
+            m = build_model(meta, sd, "bf16", dev)
+            qv = m.question_vector(PC("bf16"), question)
+            (qv * w).sum().backward()
+            res[mode] = (qv.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    finally:
+        F.GRU_SEQ, F.GRU_SEQ_MAX_BATCH = old
+    assert rel_err(res[True][0], res[False][0]) < 2e-3, rel_err(res[True][0], res[False][0])
+    assert set(res[True][1]) == set(res[False][1])
+    for k, gseq in res[True][1].items():
+        gstep = res[False][1][k]
+        if float(gstep.abs().max()) > 1e-6:
+            e = float((gseq - gstep).norm() / gstep.norm())
+            assert e < 2e-2, (k, e)
