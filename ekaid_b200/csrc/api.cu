@@ -74,6 +74,13 @@ int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
 int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
+int ek_small_linear_launch(const float*, long long, int, int, const float*, const float*, int, float*, cudaStream_t);
+int ek_weighted_sums_launch(int, const float* const*, const float* const*, const long long*, const float*, float*,
+                            cudaStream_t);
+int ek_wn_fwd_many_launch(int, const float* const*, const float* const*, const long long*, float* const*, float*, float*,
+                          cudaStream_t);
+int ek_wn_bwd_many_launch(int, const float* const*, const float* const*, const float* const*, const float*,
+                          const long long*, float* const*, float* const*, float*, cudaStream_t);
 int ek_gru_seq_fwd_launch(const float*, const bf16*, const float*, int, int, int, float*, bf16*, float*, unsigned int*,
                           cudaStream_t);
 int ek_gru_seq_bwd_launch(const float*, const float*, const float*, const bf16*, int, int, int, float*, float*, bf16*,
@@ -248,6 +255,23 @@ int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* 
 }
 int ekaid_wn_fwd(const float* v, const float* g, int64_t n, float* w, float* norm_out, float* workspace, void* stream) {
   return ek_wn_fwd_launch(v, g, n, w, norm_out, workspace, ST);
+}
+int ekaid_small_linear(const float* x, int64_t ldx, int M, int K, const float* W, const float* b, int N, float* y,
+                       void* stream) {
+  return ek_small_linear_launch(x, ldx, M, K, W, b, N, y, ST);
+}
+int ekaid_weighted_sums(int count, const float* const* a, const float* const* w, const int64_t* n, const float* coef,
+                        float* out, void* stream) {
+  return ek_weighted_sums_launch(count, a, w, (const long long*)n, coef, out, ST);
+}
+int ekaid_wn_fwd_many(int count, const float* const* v, const float* const* g, const int64_t* n, float* const* w,
+                      float* norms, float* workspace, void* stream) {
+  return ek_wn_fwd_many_launch(count, v, g, (const long long*)n, w, norms, workspace, ST);
+}
+int ekaid_wn_bwd_many(int count, const float* const* dw, const float* const* v, const float* const* g,
+                      const float* norms, const int64_t* n, float* const* dv, float* const* dg, float* workspace,
+                      void* stream) {
+  return ek_wn_bwd_many_launch(count, dw, v, g, norms, (const long long*)n, dv, dg, workspace, ST);
 }
 int ekaid_wn_bwd(const float* dw, const float* v, const float* g, const float* norm, int64_t n, float* dv, float* dg,
                  float* workspace, void* stream) {

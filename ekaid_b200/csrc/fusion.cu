@@ -44,13 +44,16 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds
   }
 }
 
-// ---------------------------------------------------------------- column sums (bias gradients), two deterministic passes
-// part[p, n] = sum_{m in chunk p} scale[m] * src[m, n]
+// ---------------------------------------------------------------- column sums (bias gradients), deterministic, one launch
+// part[p, n] = sum_{m in chunk p} scale[m] * src[m, n]; the last CTA of a column block to finish (ticket counter) adds the
+// partials in fixed order p = 0..nparts-1 and leaves the counter at zero for the next call.
 template <typename T>
-__global__ void colsum_part_kernel(const T* __restrict__ src, long long ld, long long M, int N,
-                                   const float* __restrict__ rowscale, float* __restrict__ part, int nparts) {
+__global__ void colsum_kernel(const T* __restrict__ src, long long ld, long long M, int N,
+                              const float* __restrict__ rowscale, float* part, int nparts, unsigned int* tickets,
+                              float* __restrict__ out) {
   ek_pdl_prologue();
   __shared__ float red[8][33];
+  __shared__ int is_last;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   const long long rows_per = (M + nparts - 1) / nparts;
@@ -70,14 +73,20 @@ __global__ void colsum_part_kernel(const T* __restrict__ src, long long ld, long
     for (int k = 0; k < 8; ++k) t += red[k][tx];
     part[(size_t)blockIdx.y * N + n] = t;
   }
-}
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ out) {
-  ek_pdl_prologue();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * N + n];
-  out[n] = s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(tickets + blockIdx.x, 1u);
+    is_last = (ticket == (unsigned int)nparts - 1u);
+    if (is_last) tickets[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (is_last && ty == 0 && n < N) {
+    __threadfence();
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += __ldcg(part + (size_t)p * N + n);
+    out[n] = t;
+  }
 }
 
 // ---------------------------------------------------------------- row flags for quirk Q10
@@ -417,6 +426,115 @@ __global__ void wn_bwd_kernel(const float* __restrict__ dw, const float* __restr
     dv[e] = c1 * dw[e] - c2 * v[e];
 }
 
+// Batched form: the same arithmetic for up to WN_MANY tensors in two launches (blockIdx.y = tensor).  All
+// weight-normalised matrices of the relation encoders are independent of the activations, so the step normalises them
+// together up front and differentiates them together at the end.
+constexpr int WN_MANY = 16;
+struct WnMany {
+  const float* a[WN_MANY];      // forward: v            backward: dw
+  const float* b[WN_MANY];      // forward: v            backward: v
+  const float* g[WN_MANY];
+  float* out[WN_MANY];          // forward: w            backward: dv
+  float* out1[WN_MANY];         // forward: unused       backward: dg (1 element)
+  long long n[WN_MANY];
+};
+__global__ void wn_many_partial_kernel(WnMany t, float* __restrict__ part) {
+  ek_pdl_prologue();
+  __shared__ float red[32];
+  const int i = blockIdx.y;
+  const float* __restrict__ a = t.a[i];
+  const float* __restrict__ b = t.b[i];
+  const long long n = t.n[i];
+  float s = 0.f;
+  const long long n4 = ((((uintptr_t)a | (uintptr_t)b) & 15) == 0) ? n / 4 : 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 x = ((const float4*)a)[e], y = ((const float4*)b)[e];
+    s = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, s))));
+  }
+  for (long long e = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    s = fmaf(a[e], b[e], s);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) part[(size_t)i * WN_BLOCKS + blockIdx.x] = s;
+}
+__global__ void wn_many_scale_kernel(WnMany t, const float* __restrict__ part, float* __restrict__ norms) {
+  ek_pdl_prologue();
+  __shared__ float red[32];
+  const int i = blockIdx.y;
+  const long long n = t.n[i];
+  if ((long long)blockIdx.x * blockDim.x * 4 >= n && blockIdx.x != 0) return;      // nothing to do for this block
+  const float nrm = sqrtf(wn_total(part + (size_t)i * WN_BLOCKS, red));
+  const float sc = t.g[i][0] / nrm;
+  if (blockIdx.x == 0 && threadIdx.x == 0) norms[i] = nrm;
+  const float* __restrict__ v = t.b[i];
+  float* __restrict__ w = t.out[i];
+  const long long n4 = ((((uintptr_t)v | (uintptr_t)w) & 15) == 0) ? n / 4 : 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 x = ((const float4*)v)[e];
+    ((float4*)w)[e] = make_float4(x.x * sc, x.y * sc, x.z * sc, x.w * sc);
+  }
+  for (long long e = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    w[e] = v[e] * sc;
+}
+__global__ void wn_many_bwd_kernel(WnMany t, const float* __restrict__ part, const float* __restrict__ norms) {
+  ek_pdl_prologue();
+  __shared__ float red[32];
+  const int i = blockIdx.y;
+  const long long n = t.n[i];
+  if ((long long)blockIdx.x * blockDim.x * 4 >= n && blockIdx.x != 0) return;
+  const float dot = wn_total(part + (size_t)i * WN_BLOCKS, red);
+  const float nrm = norms[i], gv = t.g[i][0];
+  const float c1 = gv / nrm, c2 = gv * dot / (nrm * nrm * nrm);
+  if (blockIdx.x == 0 && threadIdx.x == 0) t.out1[i][0] = dot / nrm;
+  const float* __restrict__ dw = t.a[i];
+  const float* __restrict__ v = t.b[i];
+  float* __restrict__ dv = t.out[i];
+  const long long n4 = ((((uintptr_t)dw | (uintptr_t)v | (uintptr_t)dv) & 15) == 0) ? n / 4 : 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 x = ((const float4*)dw)[e], y = ((const float4*)v)[e];
+    ((float4*)dv)[e] = make_float4(c1 * x.x - c2 * y.x, c1 * x.y - c2 * y.y, c1 * x.z - c2 * y.z, c1 * x.w - c2 * y.w);
+  }
+  for (long long e = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    dv[e] = c1 * dw[e] - c2 * v[e];
+}
+
+// y[m, n] = x[m, :] . W[n, :] + b[n]  for a handful of outputs (fc1: 6 change classes, modules.py:312) -- one warp per (m, n)
+__global__ void small_linear_kernel(const float* __restrict__ x, long long ldx, int M, int K, const float* __restrict__ W,
+                                    const float* __restrict__ b, int N, float* __restrict__ y) {
+  ek_pdl_prologue();
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= M * N) return;
+  const int m = pair / N, n = pair % N, lane = threadIdx.x & 31;
+  const float* xr = x + (size_t)m * ldx;
+  const float* wr = W + (size_t)n * K;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(xr[k], __ldg(wr + k), s);
+  s = warp_sum(s);
+  if (lane == 0) y[(size_t)m * N + n] = s + (b ? b[n] : 0.f);
+}
+
+// out[0] = sum_k coef[k] * <a_k, w_k>  (w_k = NULL: plain sum of a_k); k < 5.  The training objective of
+// train_mimic.py:246-247 with the decoder's gradient given as fixed cotangents: one CTA, fixed summation order.
+struct WsumArgs {
+  const float* a[5];
+  const float* w[5];
+  long long n[5];
+  float coef[5];
+};
+__global__ void weighted_sums_kernel(WsumArgs t, int count, float* __restrict__ out) {
+  ek_pdl_prologue();
+  __shared__ float red[32];
+  float total = 0.f;
+  for (int k = 0; k < count; ++k) {
+    const float* __restrict__ a = t.a[k];
+    const float* __restrict__ w = t.w[k];
+    float s = 0.f;
+    for (long long e = threadIdx.x; e < t.n[k]; e += blockDim.x) s = w ? fmaf(a[e], w[e], s) : s + a[e];
+    total = fmaf(t.coef[k], s, total);
+  }
+  total = block_sum(total, red);
+  if (threadIdx.x == 0) out[0] = total;
+}
+
 __global__ void rng_advance_kernel(unsigned long long* seed) {
   ek_pdl_prologue(); *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
 
@@ -461,12 +579,15 @@ int ek_colsum_launch(int is_bf16, const void* src, long long ld, long long M, in
   if (nparts > 64) nparts = 64;
   if (nparts < 1) nparts = 1;
   dim3 grid(ek_div_up(N, 32), nparts);
+  // workspace: [1024 ticket counters, one per 32-column block, zero between calls] [64 * N partial sums].  The split is
+  // the same for every N so that calls with different N can share one workspace.
+  EK_REQUIRE(N <= 32 * 1024, EK_ERR_SHAPE, "colsum: N=%d > 32768", N);
+  unsigned int* tickets = (unsigned int*)workspace;
+  float* part = workspace + 1024;
   if (is_bf16)
-    ek_launch(colsum_part_kernel<bf16>, grid, 256, 0, st, (const bf16*)src, ld, M, N, rowscale, workspace, nparts);
+    ek_launch(colsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)src, ld, M, N, rowscale, part, nparts, tickets, out);
   else
-    ek_launch(colsum_part_kernel<float>, grid, 256, 0, st, (const float*)src, ld, M, N, rowscale, workspace, nparts);
-  EK_CHECK_LAUNCH();
-  ek_launch(colsum_final_kernel, ek_div_up(N, 128), 128, 0, st, workspace, nparts, N, out);
+    ek_launch(colsum_kernel<float>, grid, 256, 0, st, (const float*)src, ld, M, N, rowscale, part, nparts, tickets, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -615,6 +736,48 @@ int ek_wn_fwd_launch(const float* v, const float* g, long long n, float* w, floa
   ek_launch(wn_partial_kernel, WN_BLOCKS, 256, 0, st, v, v, n, workspace);
   EK_CHECK_LAUNCH();
   ek_launch(wn_scale_kernel, grid_for(n), 256, 0, st, v, g, workspace, n, w, norm_out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_small_linear_launch(const float* x, long long ldx, int M, int K, const float* W, const float* b, int N, float* y,
+                           cudaStream_t st) {
+  EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "small_linear: bad shape M=%d N=%d K=%d", M, N, K);
+  ek_launch(small_linear_kernel, ek_div_up((long long)M * N, 8), 256, 0, st, x, ldx, M, K, W, b, N, y);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_weighted_sums_launch(int count, const float* const* a, const float* const* w, const long long* n,
+                            const float* coef, float* out, cudaStream_t st) {
+  EK_REQUIRE(count >= 1 && count <= 5, EK_ERR_SHAPE, "weighted_sums: count=%d not in [1,5]", count);
+  WsumArgs t = {};
+  for (int k = 0; k < count; ++k) { t.a[k] = a[k]; t.w[k] = w[k]; t.n[k] = n[k]; t.coef[k] = coef[k]; }
+  ek_launch(weighted_sums_kernel, 1, 1024, 0, st, t, count, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+// norms: [count] floats kept for the backward; workspace: count * 128 floats
+int ek_wn_fwd_many_launch(int count, const float* const* v, const float* const* g, const long long* n, float* const* w,
+                          float* norms, float* workspace, cudaStream_t st) {
+  EK_REQUIRE(count >= 1 && count <= WN_MANY, EK_ERR_SHAPE, "wn_fwd_many: count=%d not in [1,%d]", count, WN_MANY);
+  WnMany t = {};
+  for (int i = 0; i < count; ++i) { t.a[i] = v[i]; t.b[i] = v[i]; t.g[i] = g[i]; t.out[i] = w[i]; t.n[i] = n[i]; }
+  ek_launch(wn_many_partial_kernel, dim3(WN_BLOCKS, count), 256, 0, st, t, workspace);
+  EK_CHECK_LAUNCH();
+  ek_launch(wn_many_scale_kernel, dim3(296, count), 256, 0, st, t, workspace, norms);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_wn_bwd_many_launch(int count, const float* const* dw, const float* const* v, const float* const* g,
+                          const float* norms, const long long* n, float* const* dv, float* const* dg, float* workspace,
+                          cudaStream_t st) {
+  EK_REQUIRE(count >= 1 && count <= WN_MANY, EK_ERR_SHAPE, "wn_bwd_many: count=%d not in [1,%d]", count, WN_MANY);
+  WnMany t = {};
+  for (int i = 0; i < count; ++i) {
+    t.a[i] = dw[i]; t.b[i] = v[i]; t.g[i] = g[i]; t.out[i] = dv[i]; t.out1[i] = dg[i]; t.n[i] = n[i];
+  }
+  ek_launch(wn_many_partial_kernel, dim3(WN_BLOCKS, count), 256, 0, st, t, workspace);
+  EK_CHECK_LAUNCH();
+  ek_launch(wn_many_bwd_kernel, dim3(296, count), 256, 0, st, t, workspace, norms);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -162,25 +162,24 @@ __global__ void qpool_sum_kernel(const float* __restrict__ S, const float* __res
     qv[(size_t)b * H + c] = s;
   }
 }
-// backward part 1 (one CTA per b): dWt[b,l] = dqv[b,:] . Hs[l*B+b,:]  -> dS_flat[b*L + l];
-//                                   dHs[l*B+b, :] (+)= Wt[b,l] * dqv[b,:]
+// backward part 1 (one CTA per (b, l)): dWt[b,l] = dqv[b,:] . Hs[l*B+b,:]  -> dS_flat[b*L + l];
+//                                        dHs[l*B+b, :] = Wt[b,l] * dqv[b,:]
 __global__ void qpool_bwd1_kernel(const float* __restrict__ dqv, const float* __restrict__ S,
                                   const float* __restrict__ Hs, int B, int L, int H, float* __restrict__ dS,
                                   float* __restrict__ dHs) {
   ek_pdl_prologue();
   __shared__ float red[32];
-  const int b = blockIdx.x;
-  for (int l = 0; l < L; ++l) {
-    const float wt = S[(size_t)b * L + l];
-    float s = 0.f;
-    for (int c = threadIdx.x; c < H; c += blockDim.x) {
-      const float d = dqv[(size_t)b * H + c];
-      s = fmaf(d, Hs[((size_t)l * B + b) * H + c], s);
-      dHs[((size_t)l * B + b) * H + c] = wt * d;
-    }
-    s = block_sum(s, red);
-    if (threadIdx.x == 0) dS[(size_t)b * L + l] = s;
+  const int b = blockIdx.x, l = blockIdx.y;
+  const float wt = S[(size_t)b * L + l];
+  const size_t row = ((size_t)l * B + b) * H;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float d = dqv[(size_t)b * H + c];
+    s = fmaf(d, Hs[row + c], s);
+    dHs[row + c] = wt * d;
   }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) dS[(size_t)b * L + l] = s;
 }
 // backward part 2 (one CTA per l): softmax over b:  da[l,b] = S * (dS - sum_b S dS)
 __global__ void qpool_bwd2_kernel(const float* __restrict__ S, const float* __restrict__ dS, int B, int L,
@@ -275,7 +274,7 @@ int ek_qpool_fwd_launch(const float* a, const float* Hs, int B, int L, int H, fl
 }
 int ek_qpool_bwd_launch(const float* dqv, const float* S, const float* Hs, int B, int L, int H, float* dS, float* da,
                         float* dHs, cudaStream_t st) {
-  ek_launch(qpool_bwd1_kernel, B, 256, 0, st, dqv, S, Hs, B, L, H, dS, dHs);
+  ek_launch(qpool_bwd1_kernel, dim3(B, L), 256, 0, st, dqv, S, Hs, B, L, H, dS, dHs);
   EK_CHECK_LAUNCH();
   ek_launch(qpool_bwd2_kernel, L, 256, 0, st, S, dS, B, L, da);
   EK_CHECK_LAUNCH();

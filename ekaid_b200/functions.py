@@ -181,11 +181,27 @@ def _workspace(dev, n):
     return ws
 
 
+_colsum_bufs = {}
+
+
+def _colsum_ws(dev, N):
+    """Workspace of ekaid_colsum per (device, stream): ticket counters (zero between calls) + partial sums."""
+    key = (str(dev), torch.cuda.current_stream().cuda_stream)
+    need = 1024 + 64 * N
+    ws = _colsum_bufs.get(key)
+    if ws is None or ws.numel() < need:
+        if ws is not None:
+            _colsum_bufs.setdefault("retired", []).append(ws)     # a captured CUDA graph may still point at it
+        ws = torch.zeros(max(need, 1024 + 64 * 6144), dtype=torch.float32, device=dev)
+        _colsum_bufs[key] = ws
+    return ws
+
+
 def colsum(src, M, N, rowscale=None, out=None):
     """out[n] = sum_m rowscale[m] * src[m, n]  (fp32 result)."""
     if out is None:
         out = torch.empty(N, dtype=torch.float32, device=src.device)
-    ws = torch.empty(64 * N, dtype=torch.float32, device=src.device)
+    ws = _colsum_ws(src.device, N)
     call("colsum", 1 if src.dtype == torch.bfloat16 else 0, src.data_ptr(), src.stride(0) if src.dim() == 2 else 1,
          M, N, ptr(rowscale), out.data_ptr(), ws.data_ptr())
     return out
@@ -228,6 +244,103 @@ class WNormFn(torch.autograd.Function):
         call("wn_bwd", dwc.data_ptr(), vc.data_ptr(), gc.data_ptr(), norm.data_ptr(), vc.numel(), dv.data_ptr(),
              dg.data_ptr(), ws.data_ptr())
         return dv, dg
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+class WNormManyFn(torch.autograd.Function):
+    """WNormFn for up to 16 (v, g) pairs at once: two launches forward and two backward for all of them (the
+    weight-normalised matrices of the relation encoders do not depend on the activations, so the step normalises them
+    together up front and autograd differentiates them together once every dw has arrived).
+    Arguments: v0, g0, v1, g1, ...; returns (w0, w1, ...)."""
+
+    @staticmethod
+    def forward(ctx, *vg):
+        lib.require_device()
+        vs = [_f32c(t) for t in vg[0::2]]
+        gs = [_f32c(t).reshape(1) for t in vg[1::2]]
+        cnt = len(vs)
+        dev = vs[0].device
+        ws_out = [torch.empty_like(v) for v in vs]
+        norms = torch.empty(cnt, dtype=torch.float32, device=dev)
+        work = torch.empty(cnt * 128, dtype=torch.float32, device=dev)
+        ns = (ctypes.c_int64 * cnt)(*[v.numel() for v in vs])
+        pv, pg, pw = _ptr_array(vs), _ptr_array(gs), _ptr_array(ws_out)      # host arrays, read during the call
+        call("wn_fwd_many", cnt, ctypes.addressof(pv), ctypes.addressof(pg), ctypes.addressof(ns), ctypes.addressof(pw),
+             norms.data_ptr(), work.data_ptr())
+        ctx.saved = (vs, gs, norms)
+        ctx.gshapes = [t.shape for t in vg[1::2]]
+        ctx.keys = [(v.data_ptr(), g.data_ptr()) for v, g in zip(vg[0::2], vg[1::2])]
+        return tuple(ws_out)
+
+    @staticmethod
+    def backward(ctx, *dws):
+        vs, gs, norms = ctx.saved
+        cnt = len(vs)
+        dev = vs[0].device
+        dwc = [_f32c(d) if d is not None else torch.zeros_like(v) for d, v in zip(dws, vs)]
+        dvs = [_dst(k[0], v.shape, dev) for k, v in zip(ctx.keys, vs)]
+        dgs = [_dst(k[1], sh, dev) for k, sh in zip(ctx.keys, ctx.gshapes)]
+        work = torch.empty(cnt * 128, dtype=torch.float32, device=dev)
+        ns = (ctypes.c_int64 * cnt)(*[v.numel() for v in vs])
+        pdw, pv, pg, pdv, pdg = (_ptr_array(x) for x in (dwc, vs, gs, dvs, dgs))
+        call("wn_bwd_many", cnt, ctypes.addressof(pdw), ctypes.addressof(pv), ctypes.addressof(pg), norms.data_ptr(),
+             ctypes.addressof(ns), ctypes.addressof(pdv), ctypes.addressof(pdg), work.data_ptr())
+        out = []
+        for dv, dg in zip(dvs, dgs):
+            out += [dv, dg]
+        return tuple(out)
+
+
+class SmallLinearFn(torch.autograd.Function):
+    """nn.Linear with a handful of outputs (fc1, modules.py:312): one warp per output element instead of a GEMM
+    launch.  The reference never uses `pred` in the loss (Q11); the backward is plain torch for whoever does."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        lib.require_device()
+        xc, Wc = _f32c(x), _f32c(W)
+        y = torch.empty(xc.shape[0], Wc.shape[0], dtype=torch.float32, device=xc.device)
+        call("small_linear", xc.data_ptr(), xc.stride(0), xc.shape[0], xc.shape[1], Wc.data_ptr(),
+             _f32c(b).data_ptr() if b is not None else None, Wc.shape[0], y.data_ptr())
+        ctx.save_for_backward(xc, Wc)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, Wc = ctx.saved_tensors
+        return dy @ Wc, dy.t() @ xc, dy.sum(0) if ctx.has_bias else None
+
+
+class WeightedSumsFn(torch.autograd.Function):
+    """loss = sum_k coef_k <a_k, w_k>  (w_k None: sum of a_k) in one launch; the gradient of a_k is coef_k * w_k."""
+
+    @staticmethod
+    def forward(ctx, coefs, weights, *tensors):
+        lib.require_device()
+        ts = [_f32c(t) for t in tensors]
+        dev = ts[0].device
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        cnt = len(ts)
+        pa = _ptr_array(ts)
+        pw = (ctypes.c_void_p * cnt)(*[w.data_ptr() if w is not None else None for w in weights])
+        ns = (ctypes.c_int64 * cnt)(*[t.numel() for t in ts])
+        cf = (ctypes.c_float * cnt)(*[float(c) for c in coefs])
+        call("weighted_sums", cnt, ctypes.addressof(pa), ctypes.addressof(pw), ctypes.addressof(ns),
+             ctypes.addressof(cf), out.data_ptr())
+        ctx.coefs, ctx.weights = coefs, weights
+        ctx.shapes = [t.shape for t in tensors]
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = []
+        for c, w, sh in zip(ctx.coefs, ctx.weights, ctx.shapes):
+            grads.append((g * c) * w.view(sh) if w is not None else (g * c).expand(sh))
+        return (None, None, *grads)
 
 
 def cast_into(pc: PC, src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -458,6 +571,54 @@ def _dim_t(dev, feat_dim=64, wave_length=1000.0):
     return _dim_t_cache[key]
 
 
+def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split):
+    """Everything of a relation step that does not depend on the activations or the question vector: operand-type
+    copies of the weights ([Wq; Wk; Z-blocks] stacked for the single QKZ GEMM), the adjacency condition / label bias
+    (explicit) or the geometry bias (implicit).  ChangeDetector runs this for all encoders while the question path is
+    still busy on its own stream; RelationFn.forward falls back to it when no `prep` is handed in."""
+    G, B, N, Kn, D, H = dims
+    dev = Wsw.device
+    don = drop is not None and drop.on
+    WswT = to_T(pc, Wsw)
+    Wsw32 = _f32c(Wsw)
+    # [Wq ; Wk ; Z-blocks] operand: ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T (Q3)
+    WqkzT = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
+    cast_into(pc, Wq, WqkzT[0:D])
+    cast_into(pc, Wk, WqkzT[D:2 * D])
+    Wo2c = _f32c(Wo2)
+    for h in range(H):
+        cast_into(pc, Wo2c[:, h * D:(h + 1) * D], WqkzT[(2 + h) * D:(3 + h) * D])
+    bqkzc = torch.zeros((2 + H) * D, dtype=torch.float32, device=dev)
+    call("copy_f32", _f32c(bq).data_ptr(), D, bqkzc.data_ptr(), D, 1, D)
+    call("copy_f32", _f32c(bk).data_ptr(), D, bqkzc[D:].data_ptr(), D, 1, D)
+    cond = lbias = gbias = None
+    if kind == "explicit":
+        a0 = _f32c(adj0)
+        a1 = _f32c(adj1) if adj1 is not None else None
+        Lb = a0.shape[-1]
+        if a0.shape[1] != N or a0.shape[2] != N or (a1 is not None and a1.shape[1:] != a0.shape[1:]):
+            raise ValueError("adjacency must be [*, %d, %d, labels], got %s" % (N, N, tuple(a0.shape)))
+        wb = _f32c(p0).view(-1)
+        cond = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
+        lbias = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
+        call("adj_prep_fwd", a0.data_ptr(), ptr(a1), g_split, wb.data_ptr(), G, N, Kn, Lb, cond.data_ptr(),
+             lbias.data_ptr())
+        geo = (a0, a1, Lb)
+    else:
+        a0 = adj0.detach().to(device=dev, dtype=torch.float64).contiguous()
+        a1 = adj1.detach().to(device=dev, dtype=torch.float64).contiguous() if adj1 is not None else None
+        Wp, bp = _f32c(p0), _f32c(p1)
+        gbias = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
+        dgeo = drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)
+        need_bwd = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (p0, p1))
+        emb_cache = torch.empty(G, N * Kn, 64, dtype=torch.float32, device=dev) if need_bwd else None
+        call("geom_bias_fwd", a0.data_ptr(), ptr(a1), g_split, Wp.data_ptr(), bp.data_ptr(),
+             _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr(), *dgeo, ptr(emb_cache), pc.f)
+        geo = (a0, a1, Wp, bp, emb_cache)
+    return {"WswT": WswT, "Wsw32": Wsw32, "WqkzT": WqkzT, "bqkzc": bqkzc, "cond": cond, "lbias": lbias,
+            "gbias": gbias, "geo": geo}
+
+
 class RelationFn(torch.autograd.Function):
     """X <- X + relu(2 * GAT_dir1(cat(X, q)))  for G stacked images (G = S*B; image g uses question g % B).
 
@@ -467,7 +628,7 @@ class RelationFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, pc: PC, drop, site0, kind: str, dims, X, XT, qv, Wsw, bsw, Wq, bq, Wk, bk, Wo2, bout, p0, p1,
-                adj0, adj1, g_split):
+                adj0, adj1, g_split, prep=None):
         lib.require_device()
         G, B, N, Kn, D, H = dims
         dev = X.device
@@ -475,18 +636,9 @@ class RelationFn(torch.autograd.Function):
         X = _f32c(X).view(M, D)
         qv = _f32c(qv)
         don = drop is not None and drop.on
-        WswT = to_T(pc, Wsw)
-        Wsw32 = _f32c(Wsw)
-        # [Wq ; Wk ; Z-blocks] operand: ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T (Q3)
-        WqkzT = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
-        cast_into(pc, Wq, WqkzT[0:D])
-        cast_into(pc, Wk, WqkzT[D:2 * D])
-        Wo2c = _f32c(Wo2)
-        for h in range(H):
-            cast_into(pc, Wo2c[:, h * D:(h + 1) * D], WqkzT[(2 + h) * D:(3 + h) * D])
-        bqkzc = torch.zeros((2 + H) * D, dtype=torch.float32, device=dev)
-        call("copy_f32", _f32c(bq).data_ptr(), D, bqkzc.data_ptr(), D, 1, D)
-        call("copy_f32", _f32c(bk).data_ptr(), D, bqkzc[D:].data_ptr(), D, 1, D)
+        if prep is None:
+            prep = relation_prepare(pc, drop, site0, kind, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split)
+        WswT, Wsw32, WqkzT, bqkzc = prep["WswT"], prep["Wsw32"], prep["WqkzT"], prep["bqkzc"]
         bswc, boutc = _f32c(bsw), _f32c(bout)
         flags = torch.empty(M, dtype=torch.uint8, device=dev)
         call("row_zero_flags", X.data_ptr(), M, D, flags.data_ptr())
@@ -518,30 +670,8 @@ class RelationFn(torch.autograd.Function):
                 out = QKZ[:, lo:hi]
                 gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=None if pc.bf16 else out,
                      Cb=out if pc.bf16 else None)
-        cond = lbias = gbias = None
-        if kind == "explicit":
-            a0 = _f32c(adj0)
-            a1 = _f32c(adj1) if adj1 is not None else None
-            Lb = a0.shape[-1]
-            if a0.shape[1] != N or a0.shape[2] != N or (a1 is not None and a1.shape[1:] != a0.shape[1:]):
-                raise ValueError("adjacency must be [*, %d, %d, labels], got %s" % (N, N, tuple(a0.shape)))
-            wb = _f32c(p0).view(-1)
-            cond = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
-            lbias = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
-            call("adj_prep_fwd", a0.data_ptr(), ptr(a1), g_split, wb.data_ptr(), G, N, Kn, Lb, cond.data_ptr(),
-                 lbias.data_ptr())
-            ctx.geo = (a0, a1, Lb)
-        else:
-            a0 = adj0.detach().to(device=dev, dtype=torch.float64).contiguous()
-            a1 = adj1.detach().to(device=dev, dtype=torch.float64).contiguous() if adj1 is not None else None
-            Wp, bp = _f32c(p0), _f32c(p1)
-            gbias = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev)
-            dgeo = drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)
-            need_bwd = any(t is not None and t.requires_grad for t in (p0, p1))
-            emb_cache = torch.empty(G, N * Kn, 64, dtype=torch.float32, device=dev) if need_bwd else None
-            call("geom_bias_fwd", a0.data_ptr(), ptr(a1), g_split, Wp.data_ptr(), bp.data_ptr(),
-                 _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr(), *dgeo, ptr(emb_cache), pc.f)
-            ctx.geo = (a0, a1, Wp, bp, emb_cache)
+        cond, lbias, gbias = prep["cond"], prep["lbias"], prep["gbias"]
+        ctx.geo = prep["geo"]
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
         es = 2 if pc.bf16 else 4
         # bf16 path: P also as bf16 hi/lo planes, staged by the aggregation kernels with async 16-byte copies
@@ -665,7 +795,7 @@ class RelationFn(torch.autograd.Function):
             dqv = torch.empty(B, Dq, dtype=torch.float32, device=dev)
             call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(), dqv.data_ptr())
         return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWq, dbq, dWk, dbk, dWo2, dbout, dp0, dp1,
-                None, None, None)
+                None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------

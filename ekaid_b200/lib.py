@@ -94,7 +94,8 @@ def ptr(t) -> int | None:
 
 
 # kernels launched per C-ABI call (for the bench's `gpu_launches` count)
-KERNELS_PER_CALL = {"colsum": 2, "att_pool_fwd": 2, "qpool_fwd": 2, "qpool_bwd": 2}
+KERNELS_PER_CALL = {"att_pool_fwd": 2, "qpool_fwd": 2, "qpool_bwd": 2, "wn_fwd": 2, "wn_bwd": 2, "wn_fwd_many": 2,
+                    "wn_bwd_many": 2}
 LAUNCHES = 0
 # bench only: when a list, every call is bracketed by CUDA events on the launching stream:
 # (name, start_event, end_event, info)

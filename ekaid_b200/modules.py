@@ -34,7 +34,7 @@ with warnings.catch_warnings():
     from torch.nn.utils import weight_norm as _weight_norm
 
 from . import lib as _lib
-from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn, WNormFn
+from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn, WNormManyFn
 
 
 def _default_precision() -> str:
@@ -169,33 +169,49 @@ class GAttNet(nn.Module):
         the question GRU runs on its own stream)."""
         if self.dir_num != 2:
             raise NotImplementedError("only dir_num == 2 (the reference configuration) is implemented")
-        layer = self.live_layer()
-        w = {"sw": wn_weight(self.self_weights.linear()), "q": wn_weight(layer.query.linear()),
-             "k": wn_weight(layer.key.linear())}
-        if self.pos_emb_dim > 0:
-            w["p0"] = wn_weight(layer.pair_pos_fc1.linear())
-        else:
-            w["p0"] = wn_weight(self.bias.linear())
-        return w
+        return dict(zip(("sw", "q", "k", "p0"), (wn_weight(lin) for lin in self.wn_linears())))
 
-    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N, drop=None, site0=100, weights=None):
-        """X [G*N, D] -> X + relu(2 * attention output).  geo*: adjacency (explicit) or fp64 boxes (implicit)."""
-        if drop is None:
-            drop = self.make_drop(X.device)
-        D = self.out_feat_dim
+    def wn_linears(self):
+        """The four weight-normalised layers of the live branch, in the order (sw, q, k, p0)."""
+        if self.dir_num != 2:
+            raise NotImplementedError("only dir_num == 2 (the reference configuration) is implemented")
         layer = self.live_layer()
-        H = layer.num_heads
-        Kn = min(self.nongt_dim, N)
+        p0 = layer.pair_pos_fc1.linear() if self.pos_emb_dim > 0 else self.bias.linear()
+        return [self.self_weights.linear(), layer.query.linear(), layer.key.linear(), p0]
+
+    def _step_args(self, N, weights):
+        layer = self.live_layer()
         w = weights if weights is not None else self.effective_weights()
-        sw = self.self_weights.linear()
-        ql, kl = layer.query.linear(), layer.key.linear()
         if self.pos_emb_dim > 0:
             kind, p1 = "implicit", layer.pair_pos_fc1.linear().bias
         else:
             kind, p1 = "explicit", None
+        return layer, w, kind, p1, layer.num_heads, min(self.nongt_dim, N)
+
+    def prepare_step(self, pc, geo0, geo1, g_split, G, B, N, drop=None, site0=100, weights=None):
+        """The activation-independent part of relation_step (functions.relation_prepare); hand the result back through
+        relation_step(prep=...)."""
+        from .functions import relation_prepare
+        layer, w, kind, p1, H, Kn = self._step_args(N, weights)
+        dev = w["sw"].device
+        if drop is None:
+            drop = self.make_drop(dev)
+        dims = (G, B, N, Kn, self.out_feat_dim, H)
+        return relation_prepare(pc, drop, site0, kind, dims, w["sw"], w["q"], layer.query.linear().bias, w["k"],
+                                layer.key.linear().bias, layer.linear_out_2.weight, w["p0"], p1, geo0, geo1, g_split)
+
+    def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N, drop=None, site0=100, weights=None, prep=None):
+        """X [G*N, D] -> X + relu(2 * attention output).  geo*: adjacency (explicit) or fp64 boxes (implicit)."""
+        if drop is None:
+            drop = self.make_drop(X.device)
+        D = self.out_feat_dim
+        layer, w, kind, p1, H, Kn = self._step_args(N, weights)
+        sw = self.self_weights.linear()
+        ql, kl = layer.query.linear(), layer.key.linear()
         dims = (G, B, N, Kn, D, H)
         return RelationFn.apply(pc, drop, site0, kind, dims, X, XT, q, w["sw"], sw.bias, w["q"], ql.bias, w["k"], kl.bias,
-                                layer.linear_out_2.weight, layer.linear_out_2.bias, w["p0"], p1, geo0, geo1, g_split)
+                                layer.linear_out_2.weight, layer.linear_out_2.bias, w["p0"], p1, geo0, geo1, g_split,
+                                prep)
 
     def forward(self, v_feat, adj_matrix, pos_emb=None):
         if self.pos_emb_dim > 0 and pos_emb is None:
@@ -474,20 +490,22 @@ class ChangeDetector(nn.Module):
             gats['spa'] = self.spatial_relation.explicit_relation
         if graph in ('implicit', 'all', 'i+s'):
             gats['imp'] = self.imp_relation.implicit_relation
-        eff = {k: g.effective_weights() for k, g in gats.items()}
+        # every weight-normalised matrix of the selected encoders in two launches (and two more in backward)
+        lins = [lin for g in gats.values() for lin in g.wn_linears()]
+        ws = WNormManyFn.apply(*[t for lin in lins for t in (lin.weight_v, lin.weight_g)])
+        eff = {k: dict(zip(("sw", "q", "k", "p0"), ws[4 * i:4 * i + 4])) for i, k in enumerate(gats)}
+        # ... and everything else that needs neither the activations nor the question vector: operand-type weight
+        # copies, adjacency condition / label bias, geometry bias.  All of it overlaps the question path.
+        geos = {'sem': (d_sem_adj_matrix, q_sem_adj_matrix, 100), 'spa': (d_adj_matrix, q_adj_matrix, 200),
+                'imp': (d_bb, q_bb, 300)}
+        drops = {k: g.make_drop(dev, ov) for k, g in gats.items()}
+        preps = {k: g.prepare_step(pc, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k], site0=geos[k][2],
+                                   weights=eff[k]) for k, g in gats.items()}
         cur.wait_stream(side)
-        if 'sem' in gats:
-            gat = gats['sem']
-            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_sem_adj_matrix, q_sem_adj_matrix, B, G, B, N,
-                                         drop=gat.make_drop(dev, ov), site0=100, weights=eff['sem'])
-        if 'spa' in gats:
-            gat = gats['spa']
-            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_adj_matrix, q_adj_matrix, B, G, B, N,
-                                         drop=gat.make_drop(dev, ov), site0=200, weights=eff['spa'])
-        if 'imp' in gats:
-            gat = gats['imp']
-            X, XT, _ = gat.relation_step(pc, X, XT, qv, d_bb, q_bb, B, G, B, N,
-                                         drop=gat.make_drop(dev, ov), site0=300, weights=eff['imp'])
+        for k in ('sem', 'spa', 'imp'):
+            if k in gats:
+                X, XT, _ = gats[k].relation_step(pc, X, XT, qv, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k],
+                                                 site0=geos[k][2], weights=eff[k], prep=preps[k])
         mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
         coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
         fdrop = Drop(dev, self.training, p_fuse=self.dropout.p if ov is None else ov,
@@ -501,5 +519,5 @@ class ChangeDetector(nn.Module):
         att_weight_after = att[BN:].view(B, 1, N)
         attended_1, attended_2 = attended[:B], attended[B:]
         input_attended = attended_2 - attended_1
-        pred = F.linear(input_attended, self.fc1.weight, self.fc1.bias)      # [B,6], unused by the loss (Q11)
+        pred = SmallLinearFn.apply(input_attended, self.fc1.weight, self.fc1.bias)      # [B,6], unused by the loss (Q11)
         return pred, att_weight_before, att_weight_after, attended_1, attended_2, input_attended

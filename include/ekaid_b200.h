@@ -98,7 +98,8 @@ int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, 
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
-/* out[n] = sum_m rowscale[m] * src[m,n]  (bias gradients); workspace >= 64*N floats */
+/* out[n] = sum_m rowscale[m] * src[m,n]  (bias gradients), deterministic, one launch, N <= 32768.  workspace >= 1024 +
+ * 64*N floats; the first 1024 words are ticket counters: zero them once, every call leaves them zero again */
 int ekaid_colsum(int is_bf16, const void* src, int64_t ld, int64_t M, int N, const float* rowscale, float* out,
                  float* workspace, void* stream);
 int ekaid_add_inplace(float* y, const float* x, int64_t n, void* stream);
@@ -207,12 +208,28 @@ int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, in
 int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
                         void* stream);
 
+/* y[m,n] = x[m,:] . W[n,:] + b[n] for a handful of outputs (fc1, the 6-way change classifier, modules.py:312) */
+int ekaid_small_linear(const float* x, int64_t ldx, int M, int K, const float* W, const float* b, int N, float* y,
+                       void* stream);
+/* out[0] = sum_k coef[k] * <a_k, w_k> (w_k NULL: plain sum), k < count <= 5; a, w, n, coef are HOST arrays.  The step
+ * objective of train_mimic.py:246-247 when the decoder's gradient arrives as cotangents; deterministic (one CTA). */
+int ekaid_weighted_sums(int count, const float* const* a, const float* const* w, const int64_t* n, const float* coef,
+                        float* out, void* stream);
+
 /* ---- legacy weight_norm(dim=None) (models/fc.py:33-34): w = v * g / ||v||_F over the whole tensor -------------- */
 /* workspace: 128 floats; norm_out: 1 float kept for the backward */
 int ekaid_wn_fwd(const float* v, const float* g, int64_t n, float* w, float* norm_out, float* workspace, void* stream);
 /* dv = (g/n) dw - (g <dw,v> / n^3) v ; dg = <dw,v> / n */
 int ekaid_wn_bwd(const float* dw, const float* v, const float* g, const float* norm, int64_t n, float* dv, float* dg,
                  float* workspace, void* stream);
+
+/* the same for `count` <= 16 tensors in two launches: v, g, w, dw, dv, dg are HOST arrays of `count` device pointers, n a
+ * host array of element counts (all read at call time); norms [count] and workspace [count*128] are device memory */
+int ekaid_wn_fwd_many(int count, const float* const* v, const float* const* g, const int64_t* n, float* const* w,
+                      float* norms, float* workspace, void* stream);
+int ekaid_wn_bwd_many(int count, const float* const* dw, const float* const* v, const float* const* g,
+                      const float* norms, const int64_t* n, float* const* dv, float* const* dg, float* workspace,
+                      void* stream);
 
 /* ---- train-mode dropout helpers -------------------------------------------------------------------------- */
 int ekaid_rng_advance(uint64_t* seed, void* stream);

@@ -102,6 +102,10 @@ def test_colsum_rowflags_onehot():
     assert float((colsum(x, 777, 130, rowscale=sc) - (x * sc[:, None]).sum(0)).abs().max()) < 1e-3
     xb = x.to(torch.bfloat16)
     assert float((colsum(xb, 777, 130) - xb.float().sum(0)).abs().max()) < 1e-3
+    # calls with different widths share one workspace (ticket counters must survive the partial sums of other widths)
+    for n in (1024, 3072, 1, 6144, 33, 3072):
+        y = torch.randn(60, n, device=dev)
+        assert float((colsum(y, 60, n) - y.sum(0)).abs().max()) < 1e-4, n
     X = _mk((100, 256), dev, 13, torch.float32)
     X[3] = 0
     X[17] = 0

@@ -394,6 +394,6 @@ def test_gru_one_launch_recurrence_matches_step_kernels(B):
     assert set(res[True][1]) == set(res[False][1])
     for k, gseq in res[True][1].items():
         gstep = res[False][1][k]
-        if float(gstep.abs().max()) > 1e-6:
-            e = float((gseq - gstep).norm() / gstep.norm())
-            assert e < 2e-2, (k, e)
+        # (the attention bias b2 has an analytically zero gradient -- softmax shift invariance -- hence the atol)
+        e = float((gseq - gstep).abs().max())
+        assert e < 2e-2 * float(gstep.abs().max()) + 1e-4, (k, e, float(gstep.abs().max()))
