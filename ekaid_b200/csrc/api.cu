@@ -74,6 +74,7 @@ int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
 int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
+int ek_geom_bias_bwd_parts();
 int ek_small_linear_launch(const float*, long long, int, int, const float*, const float*, int, float*, cudaStream_t);
 int ek_weighted_sums_launch(int, const float* const*, const float* const*, const long long*, const float*, float*,
                             cudaStream_t);
@@ -202,6 +203,7 @@ int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const
   return ek_geom_bias_fwd_launch(bb0, bb1, g_split, Wp, bp, dim_t, G, N, Kn, H, gbias, mk_drop(seed, site, p),
                                  emb_cache, fast_trig, ST);
 }
+int ekaid_geom_bias_bwd_parts(void) { return ek_geom_bias_bwd_parts(); }
 int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
                         const uint64_t* seed, uint32_t site, float p, const float* emb_cache, int fast_trig,

@@ -181,10 +181,87 @@ __global__ void geom_bias_fwd_kernel(const double* __restrict__ bb0, const doubl
   }
 }
 
-// part[g, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h].
+// bf16-path forward: box differences and ratios in fp64 (they cancel), everything after that in fp32 -- logf, the
+// wave-length division as a multiplication by 100/dim_t, sin/cos as a two-term Cody-Waite reduction to [-pi, pi] + the
+// SFU intrinsic (abs error 4e-7 there).  ~3x fewer instructions than the fp64 formulation the fp32 parity path keeps.
+__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831855f, x);
+  r = fmaf(-k, -1.7484555e-7f, r);
+  __sincosf(r, s, c);
+}
+__global__ void __launch_bounds__(128)
+geom_bias_fwd_fast_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
+                          const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ dim_t,
+                          int N, int Kn, int H, float* __restrict__ gbias, EkDrop dr, float* __restrict__ emb_cache) {
+  ek_pdl_prologue();
+  extern __shared__ float sW[];      // H*64 weights, H biases, then 8 x (100 / wave length)
+  float* sK = sW + H * 65;
+  for (int e = threadIdx.x; e < H * 64; e += blockDim.x) sW[e] = Wp[e];
+  for (int e = threadIdx.x; e < H; e += blockDim.x) sW[H * 64 + e] = bp[e];
+  if (threadIdx.x < 8) sK[threadIdx.x] = (float)(100.0 / (double)dim_t[threadIdx.x]);
+  __syncthreads();
+  const int g = blockIdx.x;
+  const double* bb = (g < g_split) ? bb0 + (size_t)g * N * 4 : bb1 + (size_t)(g - g_split) * N * 4;
+  const unsigned long long seedv = ek_seed(dr);
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < N * Kn; e += gridDim.y * blockDim.x) {
+    const int r = e / N, c = e % N;        // flat index i*Kn + j reinterpreted over [Kn, N] (Q13)
+    float gq[4];
+    {
+      const double x0r = bb[r * 4 + 0], y0r = bb[r * 4 + 1], x1r = bb[r * 4 + 2], y1r = bb[r * 4 + 3];
+      const double x0c = bb[c * 4 + 0], y0c = bb[c * 4 + 1], x1c = bb[c * 4 + 2], y1c = bb[c * 4 + 3];
+      const double wr = x1r - x0r + 1.0, hr = y1r - y0r + 1.0;
+      const double wc = x1c - x0c + 1.0, hc = y1c - y0c + 1.0;
+      const float iwr = 1.f / (float)wr, ihr = 1.f / (float)hr;
+      const float dx = fmaxf(fabsf((float)(0.5 * (x0r + x1r) - 0.5 * (x0c + x1c)) * iwr), 1e-3f);
+      const float dy = fmaxf(fabsf((float)(0.5 * (y0r + y1r) - 0.5 * (y0c + y1c)) * ihr), 1e-3f);
+      gq[0] = logf(dx);
+      gq[1] = logf(dy);
+      gq[2] = logf((float)wr / (float)wc);
+      gq[3] = logf((float)hr / (float)hc);
+    }
+    const unsigned long long pair_idx = (unsigned long long)g * N * Kn + e;
+    float f[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) f[h] = (h < H) ? sW[H * 64 + h] : 0.f;
+    float4* dst = emb_cache ? (float4*)(emb_cache + pair_idx * 64) : nullptr;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float ms[8], mc[8];
+      ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 0, ms);
+      ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 1, ms + 4);
+      ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 2, mc);
+      ek_drop_mult4(dr, seedv, pair_idx * 16 + q * 4 + 3, mc + 4);
+      float es[8], ec[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        float sv, cv;
+        fast_sincos(gq[q] * sK[t], &sv, &cv);
+        es[t] = sv * ms[t];
+        ec[t] = cv * mc[t];
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          if (h < H) f[h] = fmaf(sW[h * 64 + q * 16 + t], es[t], fmaf(sW[h * 64 + q * 16 + 8 + t], ec[t], f[h]));
+      }
+      if (dst) {
+        dst[q * 4 + 0] = make_float4(es[0], es[1], es[2], es[3]);
+        dst[q * 4 + 1] = make_float4(es[4], es[5], es[6], es[7]);
+        dst[q * 4 + 2] = make_float4(ec[0], ec[1], ec[2], ec[3]);
+        dst[q * 4 + 3] = make_float4(ec[4], ec[5], ec[6], ec[7]);
+      }
+    }
+    for (int h = 0; h < H; ++h) {
+      const float v = fmaxf(fmaxf(f[h], 0.f), 1e-6f);
+      gbias[pair_idx * H + h] = logf(v);
+    }
+  }
+}
+
+// part[g * GB_SPLIT + y, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h]   (blockIdx.y = y takes every GB_SPLIT-th tile).
 // Two phases per tile of 128 pairs: (1) one thread per pair recomputes the embedding and df = dgbias / f (f > 1e-6),
 // parks both in shared memory; (2) one thread per (h,k) output accumulates over the tile.  No shuffles, no atomics.
 constexpr int GB_TILE = 128;
+constexpr int GB_SPLIT = 4;
 __global__ void __launch_bounds__(GB_TILE)
 geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ bb1, int g_split,
                      const float* __restrict__ Wp, const float* __restrict__ bp, const float* __restrict__ dim_t, int N,
@@ -206,30 +283,51 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
   const int nout = H * 65;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};         // outputs tid, tid+128, ... (H <= 8 -> <= 520 outputs)
   __syncthreads();
-  for (int t0 = 0; t0 < total; t0 += GB_TILE) {
+  for (int t0 = blockIdx.y * GB_TILE; t0 < total; t0 += gridDim.y * GB_TILE) {
     const int e = t0 + tid;
-    float emb[64];
     float df[8];
 #pragma unroll
     for (int h = 0; h < 8; ++h) df[h] = 0.f;
+    if (emb_cache) {
+      // the tile's cached embeddings are one contiguous [<=128 x 64] block: coalesced 16-byte loads into sE
+      const int rows = min(GB_TILE, total - t0);
+      const float4* src = (const float4*)(emb_cache + ((size_t)g * total + t0) * 64);
+      for (int i = tid; i < GB_TILE * 16; i += GB_TILE) {
+        const int row = i >> 4, c4 = (i & 15) * 4;
+        const float4 v = (row < rows) ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* d = sE + row * 65 + c4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+      sE[tid * 65 + 64] = 1.f;                         // bias column
+      __syncthreads();
+      if (e < total) {
+        for (int h = 0; h < H; ++h) {
+          float a = sW[H * 64 + h];
+#pragma unroll 16
+          for (int k = 0; k < 64; ++k) a = fmaf(sW[h * 64 + k], sE[tid * 65 + k], a);
+          df[h] = (a > 1e-6f) ? dgbias[((size_t)g * total + e) * H + h] / a : 0.f;
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 8; ++h) sDf[tid * 8 + h] = df[h];
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        const int o = tid + a * GB_TILE;
+        if (o < nout) {
+          const int h = o / 65, k = o % 65;
+          float s2 = acc[a];
+          for (int p = 0; p < GB_TILE; ++p) s2 = fmaf(sDf[p * 8 + h], sE[p * 65 + k], s2);
+          acc[a] = s2;
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    float emb[64];
     if (e < total) {
       float f[8];
-      if (emb_cache) {
-        const float4* src = (const float4*)(emb_cache + ((size_t)g * total + e) * 64);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const float4 v = src[k];
-          emb[4 * k] = v.x; emb[4 * k + 1] = v.y; emb[4 * k + 2] = v.z; emb[4 * k + 3] = v.w;
-        }
-#pragma unroll
-        for (int h = 0; h < 8; ++h) {
-          float a = (h < H) ? sW[H * 64 + h] : 0.f;
-          if (h < H)
-#pragma unroll
-            for (int k = 0; k < 64; ++k) a = fmaf(sW[h * 64 + k], emb[k], a);
-          f[h] = a;
-        }
-      } else {
+      {
         const int r = e / N, c = e % N;
         double gq[4];
         pos_feats(bb, r, c, gq);
@@ -263,7 +361,7 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
 #pragma unroll
   for (int a = 0; a < 5; ++a) {
     const int o = tid + a * GB_TILE;
-    if (o < nout) part[(size_t)g * nout + o] = acc[a];
+    if (o < nout) part[((size_t)g * gridDim.y + blockIdx.y) * nout + o] = acc[a];
   }
 }
 
@@ -592,18 +690,23 @@ int ek_geom_bias_fwd_launch(const double* bb0, const double* bb1, int g_split, c
                             int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   dim3 grid(G, ek_div_up(N * Kn, 128 * 4));
-  ek_launch(geom_bias_fwd_kernel, grid, 128, (H * 65 + 8) * sizeof(float), st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
-                                                                         gbias, dr, emb_cache, fast_trig);
+  if (fast_trig)
+    ek_launch(geom_bias_fwd_fast_kernel, grid, 128, (H * 65 + 8) * sizeof(float), st, bb0, bb1, g_split, Wp, bp, dim_t, N,
+              Kn, H, gbias, dr, emb_cache);
+  else
+    ek_launch(geom_bias_fwd_kernel, grid, 128, (H * 65 + 8) * sizeof(float), st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H,
+              gbias, dr, emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
+int ek_geom_bias_bwd_parts() { return GB_SPLIT; }
 int ek_geom_bias_bwd_launch(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                             const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
                             EkDrop dr, const float* emb_cache, int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
   const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float);
-  ek_launch(geom_bias_bwd_kernel, G, GB_TILE, smem, st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias, part, dr,
-                                                 emb_cache, fast_trig);
+  ek_launch(geom_bias_bwd_kernel, dim3(G, GB_SPLIT), GB_TILE, smem, st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias,
+            part, dr, emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -739,11 +739,12 @@ class RelationFn(torch.autograd.Function):
             dp0 = colsum(part, G, Lb).view(1, Lb)
         else:
             a0, a1, Wp, bp, emb_cache = ctx.geo
-            part = torch.empty(G, H * 65, dtype=torch.float32, device=dev)
+            nparts = G * lib.load().ekaid_geom_bias_bwd_parts()
+            part = torch.empty(nparts, H * 65, dtype=torch.float32, device=dev)
             call("geom_bias_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, Wp.data_ptr(), bp.data_ptr(),
                  _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr(),
                  *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)), ptr(emb_cache), pc.f)
-            tot = colsum(part, G, H * 65).view(H, 65)
+            tot = colsum(part, nparts, H * 65).view(H, 65)
             dp0 = tot[:, :64].contiguous()
             dp1 = _dst(kk["p1"], (H,), dev)
             dp1.copy_(tot[:, 64])

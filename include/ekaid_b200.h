@@ -126,7 +126,9 @@ int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const 
 int ekaid_geom_bias_fwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, float* gbias, const uint64_t* seed,
                         uint32_t site, float p, float* emb_cache, int fast_trig, void* stream);
-/* part[g, h*65 + k]: k < 64 -> dWp[h,k], k = 64 -> dbp[h] */
+/* part[r, h*65 + k], r < G * ekaid_geom_bias_bwd_parts(): partial sums, k < 64 -> dWp[h,k], k = 64 -> dbp[h]; the caller
+ * adds the rows (ekaid_colsum) */
+int ekaid_geom_bias_bwd_parts(void);
 int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const float* Wp, const float* bp,
                         const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
                         const uint64_t* seed, uint32_t site, float p, const float* emb_cache, int fast_trig,
