@@ -54,7 +54,7 @@ int ek_att_pool_bwd_launch(int, const float*, const float*, const float*, const 
                            long long, int, int, int, float*, void*, float*, float, cudaStream_t);
 int ek_onehot_adj_launch(const double*, int, int, int, int, float*, cudaStream_t);
 int ek_adam_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, const float*,
-                   cudaStream_t);
+                   int, cudaStream_t);
 int ek_adam_advance_launch(float*, float, float, cudaStream_t);
 int ek_adj_prep_fwd_launch(const float*, const float*, int, const float*, int, int, int, int, float*, float*,
                            cudaStream_t);
@@ -77,7 +77,7 @@ int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, i
 int ek_geom_bias_bwd_parts();
 int ek_small_linear_launch(const float*, long long, int, int, const float*, const float*, int, float*, cudaStream_t);
 int ek_weighted_sums_launch(int, const float* const*, const float* const*, const long long*, const float*, float*,
-                            cudaStream_t);
+                            float*, cudaStream_t);
 int ek_wn_fwd_many_launch(int, const float* const*, const float* const*, const long long*, float* const*, float*, float*,
                           cudaStream_t);
 int ek_wn_bwd_many_launch(int, const float* const*, const float* const*, const float* const*, const float*,
@@ -263,8 +263,8 @@ int ekaid_small_linear(const float* x, int64_t ldx, int M, int K, const float* W
   return ek_small_linear_launch(x, ldx, M, K, W, b, N, y, ST);
 }
 int ekaid_weighted_sums(int count, const float* const* a, const float* const* w, const int64_t* n, const float* coef,
-                        float* out, void* stream) {
-  return ek_weighted_sums_launch(count, a, w, (const long long*)n, coef, out, ST);
+                        float* out, float* workspace, void* stream) {
+  return ek_weighted_sums_launch(count, a, w, (const long long*)n, coef, out, workspace, ST);
 }
 int ekaid_wn_fwd_many(int count, const float* const* v, const float* const* g, const int64_t* n, float* const* w,
                       float* norms, float* workspace, void* stream) {
@@ -347,8 +347,8 @@ int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream) {
   return ek_adam_advance_launch(pow_state, b1, b2, ST);
 }
 int ekaid_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-                    float wd, const float* pow_state, void* stream) {
-  return ek_adam_launch(p, g, m, v, n, lr, b1, b2, eps, wd, pow_state, ST);
+                    float wd, const float* pow_state, int max_ctas, void* stream) {
+  return ek_adam_launch(p, g, m, v, n, lr, b1, b2, eps, wd, pow_state, max_ctas, ST);
 }
 
 }  // extern "C"

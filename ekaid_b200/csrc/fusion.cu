@@ -47,31 +47,51 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds
 // ---------------------------------------------------------------- column sums (bias gradients), deterministic, one launch
 // part[p, n] = sum_{m in chunk p} scale[m] * src[m, n]; the last CTA of a column block to finish (ticket counter) adds the
 // partials in fixed order p = 0..nparts-1 and leaves the counter at zero for the next call.
-template <typename T>
-__global__ void colsum_kernel(const T* __restrict__ src, long long ld, long long M, int N,
-                              const float* __restrict__ rowscale, float* part, int nparts, unsigned int* tickets,
-                              float* __restrict__ out) {
+// Block = 8 warps; a warp reads one row segment of VEC*32 consecutive columns with 16-byte loads (VEC = 8 bf16 / 4 fp32),
+// the 8 warps take 8 different rows per iteration.  grid = (column blocks, row chunks).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ src, long long ld, long long M, int N, const float* __restrict__ rowscale,
+              float* part, int nparts, unsigned int* tickets, float* __restrict__ out, int vec_ok) {
   ek_pdl_prologue();
-  __shared__ float red[8][33];
+  constexpr int CB = VEC * 32;             // columns per block
+  __shared__ float red[8][CB + 1];
   __shared__ int is_last;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int n = blockIdx.x * 32 + tx;
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * CB + lane * VEC;
   const long long rows_per = (M + nparts - 1) / nparts;
   const long long r0 = (long long)blockIdx.y * rows_per;
   const long long r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
-  float s = 0.f;
-  if (n < N)
-    for (long long m = r0 + ty; m < r1; m += 8) {
-      const float v = to_f32<T>(src[m * ld + n]);
-      s += rowscale ? v * rowscale[m] : v;
-    }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && n < N) {
-    float t = 0.f;
+  float s[VEC];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][tx];
-    part[(size_t)blockIdx.y * N + n] = t;
+  for (int v = 0; v < VEC; ++v) s[v] = 0.f;
+  if (vec_ok && n0 + VEC <= N) {
+    for (long long m = r0 + ty; m < r1; m += 8) {
+      const float sc = rowscale ? rowscale[m] : 1.f;
+      const uint4 raw = *(const uint4*)(src + m * ld + n0);
+      const T* pv = (const T*)&raw;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s[v] = fmaf(to_f32<T>(pv[v]), sc, s[v]);
+    }
+  } else {
+    for (long long m = r0 + ty; m < r1; m += 8) {
+      const float sc = rowscale ? rowscale[m] : 1.f;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (n0 + v < N) s[v] = fmaf(to_f32<T>(src[m * ld + n0 + v]), sc, s[v]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[ty][lane * VEC + v] = s[v];
+  __syncthreads();
+  for (int c = threadIdx.x; c < CB; c += 256) {
+    const int n = blockIdx.x * CB + c;
+    if (n < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k][c];
+      part[(size_t)blockIdx.y * N + n] = t;
+    }
   }
   __threadfence();
   __syncthreads();
@@ -81,11 +101,16 @@ __global__ void colsum_kernel(const T* __restrict__ src, long long ld, long long
     if (is_last) tickets[blockIdx.x] = 0u;
   }
   __syncthreads();
-  if (is_last && ty == 0 && n < N) {
+  if (is_last) {
     __threadfence();
-    float t = 0.f;
-    for (int p = 0; p < nparts; ++p) t += __ldcg(part + (size_t)p * N + n);
-    out[n] = t;
+    for (int c = threadIdx.x; c < CB; c += 256) {
+      const int n = blockIdx.x * CB + c;
+      if (n < N) {
+        float t = 0.f;
+        for (int p = 0; p < nparts; ++p) t += __ldcg(part + (size_t)p * N + n);
+        out[n] = t;
+      }
+    }
   }
 }
 
@@ -281,22 +306,40 @@ __global__ void onehot_adj_kernel(const double* __restrict__ labels, int S, int 
 }
 
 // ---------------------------------------------------------------- Adam (utils/utils.py:96-99 -> torch.optim.Adam)
+__device__ __forceinline__ void adam_one(float& pv, float gr, float& mv, float& vv, float lr_bc1, float rs_bc2, float b1,
+                                         float b2, float eps, float wd) {
+  if (wd != 0.f) gr = fmaf(wd, pv, gr);
+  mv = b1 * mv + (1.f - b1) * gr;
+  vv = b2 * vv + (1.f - b2) * gr * gr;
+  const float denom = sqrtf(vv) * rs_bc2 + eps;
+  pv = pv - lr_bc1 * (mv / denom);
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
                             const float* __restrict__ pow_state) {
   ek_pdl_prologue();
   // pow_state = {b1^t, b2^t} lives in device memory so a captured CUDA graph stays valid across steps
   const float bc1 = 1.f - pow_state[0], bc2 = 1.f - pow_state[1];
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    float gr = g[e];
-    const float pv = p[e];
-    if (wd != 0.f) gr = fmaf(wd, pv, gr);
-    const float mv = b1 * m[e] + (1.f - b1) * gr;
-    const float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+  const float lr_bc1 = lr / bc1, rs_bc2 = 1.f / sqrtf(bc2);
+  const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    float4 pv = ((float4*)p)[e], mv = ((float4*)m)[e], vv = ((float4*)v)[e];
+    const float4 gr = ((const float4*)g)[e];
+    adam_one(pv.x, gr.x, mv.x, vv.x, lr_bc1, rs_bc2, b1, b2, eps, wd);
+    adam_one(pv.y, gr.y, mv.y, vv.y, lr_bc1, rs_bc2, b1, b2, eps, wd);
+    adam_one(pv.z, gr.z, mv.z, vv.z, lr_bc1, rs_bc2, b1, b2, eps, wd);
+    adam_one(pv.w, gr.w, mv.w, vv.w, lr_bc1, rs_bc2, b1, b2, eps, wd);
+    ((float4*)m)[e] = mv;
+    ((float4*)v)[e] = vv;
+    ((float4*)p)[e] = pv;
+  }
+  for (long long e = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float pv = p[e], mv = m[e], vv = v[e];
+    adam_one(pv, g[e], mv, vv, lr_bc1, rs_bc2, b1, b2, eps, wd);
     m[e] = mv;
     v[e] = vv;
-    const float denom = sqrtf(vv) / sqrtf(bc2) + eps;
-    p[e] = pv - (lr / bc1) * (mv / denom);
+    p[e] = pv;
   }
 }
 
@@ -520,19 +563,35 @@ struct WsumArgs {
   long long n[5];
   float coef[5];
 };
-__global__ void weighted_sums_kernel(WsumArgs t, int count, float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+weighted_sums_kernel(WsumArgs t, int count, float* part, unsigned int* ticket, float* __restrict__ out) {
   ek_pdl_prologue();
   __shared__ float red[32];
+  __shared__ int is_last;
   float total = 0.f;
   for (int k = 0; k < count; ++k) {
     const float* __restrict__ a = t.a[k];
     const float* __restrict__ w = t.w[k];
     float s = 0.f;
-    for (long long e = threadIdx.x; e < t.n[k]; e += blockDim.x) s = w ? fmaf(a[e], w[e], s) : s + a[e];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < t.n[k]; e += (long long)gridDim.x * blockDim.x)
+      s = w ? fmaf(a[e], w[e], s) : s + a[e];
     total = fmaf(t.coef[k], s, total);
   }
   total = block_sum(total, red);
-  if (threadIdx.x == 0) out[0] = total;
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = total;
+    __threadfence();
+    const unsigned int tk = atomicAdd(ticket, 1u);
+    is_last = (tk == gridDim.x - 1);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {       // fixed summation order: deterministic
+    __threadfence();
+    float s = 0.f;
+    for (unsigned int p = 0; p < gridDim.x; ++p) s += __ldcg(part + p);
+    out[0] = s;
+  }
 }
 
 __global__ void rng_advance_kernel(unsigned long long* seed) {
@@ -578,16 +637,19 @@ int ek_colsum_launch(int is_bf16, const void* src, long long ld, long long M, in
   int nparts = (int)((M + 255) / 256);
   if (nparts > 64) nparts = 64;
   if (nparts < 1) nparts = 1;
-  dim3 grid(ek_div_up(N, 32), nparts);
   // workspace: [1024 ticket counters, one per 32-column block, zero between calls] [64 * N partial sums].  The split is
   // the same for every N so that calls with different N can share one workspace.
   EK_REQUIRE(N <= 32 * 1024, EK_ERR_SHAPE, "colsum: N=%d > 32768", N);
   unsigned int* tickets = (unsigned int*)workspace;
   float* part = workspace + 1024;
+  const int es = is_bf16 ? 2 : 4;
+  const int vec_ok = (((uintptr_t)src & 15) == 0 && (ld * es) % 16 == 0) ? 1 : 0;
   if (is_bf16)
-    ek_launch(colsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)src, ld, M, N, rowscale, part, nparts, tickets, out);
+    ek_launch(colsum_kernel<bf16, 8>, dim3(ek_div_up(N, 256), nparts), 256, 0, st, (const bf16*)src, ld, M, N, rowscale, part,
+              nparts, tickets, out, vec_ok);
   else
-    ek_launch(colsum_kernel<float>, grid, 256, 0, st, (const float*)src, ld, M, N, rowscale, part, nparts, tickets, out);
+    ek_launch(colsum_kernel<float, 4>, dim3(ek_div_up(N, 128), nparts), 256, 0, st, (const float*)src, ld, M, N, rowscale,
+              part, nparts, tickets, out, vec_ok);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -674,9 +736,19 @@ int ek_onehot_adj_launch(const double* labels, int B, int S, int N, int L, float
 }
 
 int ek_adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                   float wd, const float* pow_state, cudaStream_t st) {
+                   float wd, const float* pow_state, int max_ctas, cudaStream_t st) {
   if (n == 0) return EK_OK;
-  ek_launch(adam_kernel, grid_for(n), 256, 0, st, p, g, m, v, n, lr, b1, b2, eps, wd, pow_state);
+  int grid = grid_for(n / 4 + 1);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;      // background mode: leave SM slots to concurrent kernels
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // An SM cannot change its L1 / shared-memory split while CTAs are resident.  This kernel needs no shared memory, but
+    // it runs next to kernels that need almost all of it (the GRU recurrence, the GEMMs): ask for the maximum carve-out
+    // so their CTAs can join an SM that already hosts ours.
+    cudaFuncSetAttribute(adam_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
+  }
+  ek_launch(adam_kernel, grid, 256, 0, st, p, g, m, v, n, lr, b1, b2, eps, wd, pow_state);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -746,12 +818,13 @@ int ek_small_linear_launch(const float* x, long long ldx, int M, int K, const fl
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
+// workspace: 1 ticket word (zero between calls) + 64 partial sums
 int ek_weighted_sums_launch(int count, const float* const* a, const float* const* w, const long long* n,
-                            const float* coef, float* out, cudaStream_t st) {
+                            const float* coef, float* out, float* workspace, cudaStream_t st) {
   EK_REQUIRE(count >= 1 && count <= 5, EK_ERR_SHAPE, "weighted_sums: count=%d not in [1,5]", count);
   WsumArgs t = {};
   for (int k = 0; k < count; ++k) { t.a[k] = a[k]; t.w[k] = w[k]; t.n[k] = n[k]; t.coef[k] = coef[k]; }
-  ek_launch(weighted_sums_kernel, 1, 1024, 0, st, t, count, out);
+  ek_launch(weighted_sums_kernel, 64, 256, 0, st, t, count, workspace + 1, (unsigned int*)workspace, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -1,29 +1,33 @@
 // Persistent GRU recurrence of the question path (language_model.py:106-115 forward_all, and its BPTT) on the bf16
 // tensor-core path.  One launch runs all L time steps instead of L x (GEMM + cell kernel):
 //
-//   * the hidden state is split over the grid: CTA c owns GU = 8 hidden units j0..j0+7 and keeps the matching slice
-//     of W_hh resident in shared memory for the whole sequence (forward: the 3 x 8 gate rows, 48 KB; backward: the
-//     8 columns, as 8 K-major rows of W_hh^T, 48 KB);
-//   * per step every CTA streams the full broadcast operand (h_{t-1} [B,H] forward, dgh_{t+1} [B,3H] backward; bf16,
-//     L2 resident) through a double-buffered cp.async ring, multiplies it with its weight slice on warp-level
-//     mma.sync m16n8k16 (fp32 accumulate; M = batch is tiny, so this is a skinny GEMM and tcgen05's 128-row tile
-//     would be 50 % empty), applies the GRU cell (or its derivative) to its own units and writes its slice of the
-//     outputs;
-//   * a grid-wide barrier (one atomic counter in global memory, release/acquire) separates the steps.  The grid is
-//     H / 8 = 128 CTAs of one CTA per SM, so all CTAs are co-resident on a B200; a barrier wait is bounded and traps
-//     instead of hanging.
+//   * the hidden state is split over the grid: CTA c owns GU = 16 hidden units; four neighbouring CTAs form a
+//     thread-block cluster that owns 64 units together.  Inside a cluster the reduction dimension of the per-step
+//     product is split four ways: CTA r multiplies ITS quarter of the broadcast operand (h_{t-1} [B,H] forward,
+//     dgh_{t+1} [B,3H] backward; bf16, L2 resident) with the matching quarter of the cluster's W_hh slice, which stays
+//     in its shared memory for the whole sequence (~100 KB), on warp-level mma.sync m16n8k16 (fp32 accumulate; M =
+//     batch is tiny, a tcgen05 128-row tile would be half empty).  So each SM pulls only a quarter of the operand per
+//     step, and the grid is 64 CTAs: 84 SMs stay free for whatever runs next to the recurrence.
+//   * the partial sums are pushed into the owner CTA's shared memory through distributed shared memory
+//     (st.shared::cluster), one cluster barrier later the owner applies the GRU cell (or its derivative) to its 16 units
+//     and writes its slice of the outputs;
+//   * a grid-wide barrier (one atomic counter in global memory, release/acquire) separates the steps.  All 64 CTAs are
+//     co-resident (checked with cudaOccupancyMaxActiveClusters); a barrier wait is bounded and traps instead of hanging.
 //
 // Arithmetic is that of gru_cell_fwd/bwd_kernel + the bf16 GEMMs they were paired with (question.cu), so the two
 // formulations agree to fp32 summation order.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
 
-constexpr int GU = 8;             // hidden units per CTA
-constexpr int KC = 512;           // k elements of the broadcast operand per staged chunk
+// Template parameters of the kernels: GU = hidden units per CTA, CS = CTAs per cluster (= split of the reduction
+// dimension).  <16, 4>: 64 CTAs, least L2 traffic, leaves 84 SMs free (backward, which runs next to the optimizer).
+// <8, 2>: 128 CTAs, half the mma.sync work per SM (forward, which is on the critical path of the step).
+constexpr int KC = 256;           // k elements of the broadcast operand per staged chunk
 constexpr int RB = 64;            // batch rows per pass (4 MMA row tiles)
-constexpr int AP = KC + 8;        // chunk row pitch in elements (1040 B: ldmatrix rows land in distinct 16-byte slots)
-constexpr int THREADS = 256;      // 8 warps = 4 row tiles x 2 k halves
+constexpr int AP = KC + 8;        // chunk row pitch in elements (528 B: ldmatrix rows land in distinct 16-byte slots)
+constexpr int THREADS = 256;      // 8 warps = 4 row tiles x 2 column halves
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
@@ -42,6 +46,24 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory location of this CTA) in the shared memory of CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(const void* p, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(s_u32(p)), "r"(rank));
+  return a;
+}
+__device__ __forceinline__ void dsmem_st2(uint32_t addr, float x, float y) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
@@ -66,113 +88,113 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
   __syncthreads();
 }
 
-// stage rows [rb0, rb0+RB) x columns [k0, k0+KC) of the row-major bf16 matrix Ag [rows, K] into buf [RB][AP]
-__device__ __forceinline__ void load_chunk(bf16* buf, const bf16* Ag, int rows, int K, int rb0, int k0) {
+// stage rows [rb0, rb0+RB) x columns [k0, k0+KC) of the row-major bf16 matrix Ag [rows, ld] into buf [RB][AP]
+__device__ __forceinline__ void load_chunk(bf16* buf, const bf16* Ag, int rows, int ld, int rb0, int k0) {
   constexpr int CPR = KC / 8;              // 16-byte pieces per row
   for (int e = threadIdx.x; e < RB * CPR; e += THREADS) {
     const int r = e / CPR, ch = e % CPR;
     const int row = rb0 + r;
     const bool ok = row < rows;
-    const bf16* src = Ag + (size_t)(ok ? row : 0) * K + k0 + ch * 8;
+    const bf16* src = Ag + (size_t)(ok ? row : 0) * ld + k0 + ch * 8;
     cp_async16_zfill(buf + r * AP + ch * 8, src, ok ? 16 : 0);
   }
 }
 
-// acc[nt][:] += A[rb0 + 16*mt .. +16, :] . Ws[nt*8 .. +8, :]^T  for this warp's k half of every chunk.
-// Ws is [NT*8][wp] bf16, K-major (row n = output column n).  All threads of the CTA must call.
-template <int NT>
-__device__ __forceinline__ void skinny_gemm(const bf16* Ag, int rows, int K, int rb0, bf16* As, const bf16* Ws, int wp,
-                                            float (&acc)[NT][4]) {
+// acc[j][:] += A[rb0 + 16*mt .. +16, kbeg .. kbeg + nchunks*KC) . Ws[(nh*NTW + j)*8 .. +8, 0 .. nchunks*KC)^T
+// warp = (mt = warp & 3, nh = warp >> 2).  Ws is [2*NTW*8][wp] bf16, K-major.  All threads of the CTA must call.
+template <int NTW>
+__device__ __forceinline__ void skinny_gemm(const bf16* Ag, int rows, int ld, int rb0, int kbeg, int nchunks, bf16* As,
+                                            const bf16* Ws, int wp, float (&acc)[NTW][4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = warp & 3, kh = warp >> 2;
-  const int nchunks = K / KC;
-  load_chunk(As, Ag, rows, K, rb0, 0);
+  const int mt = warp & 3, nh = warp >> 2;
+  load_chunk(As, Ag, rows, ld, rb0, kbeg);
   cp_async_commit();
   for (int c = 0; c < nchunks; ++c) {
     if (c + 1 < nchunks) {
-      load_chunk(As + ((c + 1) & 1) * (RB * AP), Ag, rows, K, rb0, (c + 1) * KC);
+      load_chunk(As + ((c + 1) & 1) * (RB * AP), Ag, rows, ld, rb0, kbeg + (c + 1) * KC);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const bf16* a_base = As + (c & 1) * (RB * AP) + (mt * 16 + (lane & 15)) * AP + kh * (KC / 2) + (lane >> 4) * 8;
-    const bf16* w_base = Ws + (size_t)(lane >> 2) * wp + c * KC + kh * (KC / 2) + (lane & 3) * 2;
+    const bf16* a_base = As + (c & 1) * (RB * AP) + (mt * 16 + (lane & 15)) * AP + (lane >> 4) * 8;
+    const bf16* w_base = Ws + (size_t)(nh * NTW * 8 + (lane >> 2)) * wp + c * KC + (lane & 3) * 2;
 #pragma unroll 4
-    for (int ks = 0; ks < KC / 2 / 16; ++ks) {
+    for (int ks = 0; ks < KC / 16; ++ks) {
       uint32_t a[4];
       ldsm_x4(a, a_base + ks * 16);
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        const bf16* w = w_base + (size_t)nt * 8 * wp + ks * 16;
-        mma_bf16_16816(acc[nt], a, *(const uint32_t*)w, *(const uint32_t*)(w + 8));
+      for (int j = 0; j < NTW; ++j) {
+        const bf16* w = w_base + (size_t)j * 8 * wp + ks * 16;
+        mma_bf16_16816(acc[j], a, *(const uint32_t*)w, *(const uint32_t*)(w + 8));
       }
     }
     __syncthreads();                       // the buffer may be refilled by the next iteration's prefetch
   }
 }
 
-// sum the two k halves and lay the [RB x NT*8] result out in shared memory (row pitch NT*8+1 floats)
-template <int NT>
-__device__ __forceinline__ void reduce_to_smem(float (&acc)[NT][4], float* out) {
+// Push this warp's partial sums to the owners: cluster column n (0 .. CS*OW) belongs to CTA n / OW, local column
+// n % OW; the owner keeps one [RB][OW + 1] fp32 slab per source rank in `recv`.
+template <int NTW, int OW>
+__device__ __forceinline__ void push_partials(float (&acc)[NTW][4], float* recv, uint32_t my_rank) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = warp & 3, kh = warp >> 2;
-  constexpr int OP = NT * 8 + 1;
-  const int r0 = mt * 16 + (lane >> 2), c0 = (lane & 3) * 2;
-  if (kh == 0) {
+  const int mt = warp & 3, nh = warp >> 2;
+  constexpr int RP = OW + 2;               // slab row pitch (even: 8-byte aligned pairs)
+  const int r0 = mt * 16 + (lane >> 2);
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      out[r0 * OP + nt * 8 + c0] = acc[nt][0];
-      out[r0 * OP + nt * 8 + c0 + 1] = acc[nt][1];
-      out[(r0 + 8) * OP + nt * 8 + c0] = acc[nt][2];
-      out[(r0 + 8) * OP + nt * 8 + c0 + 1] = acc[nt][3];
-    }
+  for (int j = 0; j < NTW; ++j) {
+    const int n = (nh * NTW + j) * 8 + (lane & 3) * 2;       // cluster column of acc[j][0]
+    const uint32_t owner = n / OW;
+    const int cl = n % OW;
+    float* slot = recv + ((size_t)my_rank * RB + r0) * RP + cl;
+    const uint32_t a0 = dsmem_addr(slot, owner);
+    dsmem_st2(a0, acc[j][0], acc[j][1]);
+    dsmem_st2(a0 + 8 * RP * 4, acc[j][2], acc[j][3]);
   }
-  __syncthreads();
-  if (kh == 1) {
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-      out[r0 * OP + nt * 8 + c0] += acc[nt][0];
-      out[r0 * OP + nt * 8 + c0 + 1] += acc[nt][1];
-      out[(r0 + 8) * OP + nt * 8 + c0] += acc[nt][2];
-      out[(r0 + 8) * OP + nt * 8 + c0 + 1] += acc[nt][3];
-    }
-  }
-  __syncthreads();
 }
-
-constexpr int EPT = RB * GU / THREADS;     // (row, unit) elements per thread per pass = 2
 
 // ------------------------------------------------------------------------------------------------ forward
 // gi [L*B, 3H] fp32 (= x W_ih^T + b_ih, time-major rows t*B + b), Whh [3H, H] bf16, bhh [3H].
 // Hs [L*B, H] fp32, HsT [(L+1)*B, H] bf16 with block 0 = h_{-1} = 0 (written by the caller), gates [L, B, 4H] = (r, z, n, gh_n).
+template <int GU, int CS>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_seq_fwd_kernel(const float* __restrict__ gi, const bf16* __restrict__ Whh, const float* __restrict__ bhh, int B,
                    int H, int L, float* __restrict__ Hs, bf16* HsT, float* __restrict__ gates, unsigned int* bar) {
   ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
-  constexpr int NT = 3 * GU / 8;
-  constexpr int OP = NT * 8 + 1;
-  const int wp = H + 8;
-  bf16* Ws = (bf16*)smraw;                                  // [3*GU][wp]   row g*GU + u = W_hh[g*H + j0 + u, :]
-  bf16* As = Ws + (size_t)3 * GU * wp;                      // 2 x [RB][AP]
-  float* ghs = (float*)(As + 2 * RB * AP);                  // [RB][OP]
-  float* hprev = ghs + RB * OP;                             // [B][GU] this CTA's slice of h_{t-1} (fp32)
-  const int j0 = blockIdx.x * GU;
+  constexpr int CU = GU * CS;              // hidden units per cluster
+  constexpr int EPT = RB * GU / THREADS;   // (row, unit) elements per thread per pass
+  constexpr int OW = 3 * GU;               // columns owned per CTA: (gate, unit)
+  constexpr int NTW = CS * OW / 8 / 2;     // n-tiles per warp (two column halves)
+  static_assert((CS * OW / 8) % 2 == 0, "the cluster's columns split into two warp halves");
+  constexpr int RP = OW + 2;
+  const int KS = H / CS;                   // this CTA's slice of the reduction dimension
+  const int wp = KS + 8;
+  bf16* Ws = (bf16*)smraw;                                  // [CS*OW][wp]: row = owner*OW + g*GU + u
+  const int nbuf = (KS / KC > 1) ? 2 : 1;
+  bf16* As = Ws + (size_t)CS * OW * wp;                     // nbuf x [RB][AP]
+  float* recv = (float*)(As + nbuf * RB * AP);              // [CS][RB][RP] partial sums pushed by the cluster
+  float* hprev = recv + CS * RB * RP;                       // [B][GU] this CTA's slice of h_{t-1} (fp32)
+  const uint32_t rank = cluster_rank();
+  const int jc0 = (blockIdx.x / CS) * CU;                   // first unit of the cluster
+  const int j0 = jc0 + (int)rank * GU;                      // first unit of this CTA
   const int tid = threadIdx.x;
   {
-    const int cpr = H / 8;
-    for (int e = tid; e < 3 * GU * cpr; e += THREADS) {
+    const int cpr = KS / 8;
+    for (int e = tid; e < CS * OW * cpr; e += THREADS) {
       const int n = e / cpr, ch = e % cpr;
-      const int g = n / GU, u = n % GU;
-      cp_async16_zfill(Ws + (size_t)n * wp + ch * 8, Whh + ((size_t)g * H + j0 + u) * H + ch * 8, 16);
+      const int owner = n / OW, g = (n % OW) / GU, u = n % GU;
+      cp_async16_zfill(Ws + (size_t)n * wp + ch * 8,
+                       Whh + ((size_t)g * H + jc0 + owner * GU + u) * H + (size_t)rank * KS + ch * 8, 16);
     }
     cp_async_commit();
     cp_async_wait<0>();
     for (int e = tid; e < B * GU; e += THREADS) hprev[e] = 0.f;
+    for (int e = tid; e < CS * RB * RP; e += THREADS) recv[e] = 0.f;
     __syncthreads();
   }
+  cluster_sync();                          // every CTA of the cluster is running before anyone pushes into it
   unsigned int arrivals = 0;
   for (int t = 0; t < L; ++t) {
     for (int rb0 = 0; rb0 < B; rb0 += RB) {
@@ -189,20 +211,26 @@ gru_seq_fwd_kernel(const float* __restrict__ gi, const bf16* __restrict__ Whh, c
           gir[i] = giz[i] = gin[i] = 0.f;
         }
       }
-      float acc[NT][4];
+      if (t > 0) {                         // h_{-1} = 0: the first step has no recurrent term (recv stays zero)
+        float acc[NTW][4];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      if (t > 0) skinny_gemm<NT>(HsT + (size_t)t * B * H, B, H, rb0, As, Ws, wp, acc);     // h_{t-1} W_hh^T (h_{-1} = 0)
-      reduce_to_smem<NT>(acc, ghs);
+        for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        skinny_gemm<NTW>(HsT + (size_t)t * B * H, B, H, rb0, (int)rank * KS, KS / KC, As, Ws, wp, acc);
+        push_partials<NTW, OW>(acc, recv, rank);
+        cluster_sync();
+      }
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
         const int e = tid + i * THREADS;
         const int bl = e / GU, u = e % GU;
         const int b = rb0 + bl, j = j0 + u;
         if (b < B) {
-          const float ghr = ghs[bl * OP + u] + __ldg(bhh + j);
-          const float ghz = ghs[bl * OP + GU + u] + __ldg(bhh + H + j);
-          const float ghn = ghs[bl * OP + 2 * GU + u] + __ldg(bhh + 2 * H + j);
+          float ghr = __ldg(bhh + j), ghz = __ldg(bhh + H + j), ghn = __ldg(bhh + 2 * H + j);
+#pragma unroll
+          for (int s = 0; s < CS; ++s) {
+            const float* rs = recv + ((size_t)s * RB + bl) * RP;
+            ghr += rs[u]; ghz += rs[GU + u]; ghn += rs[2 * GU + u];
+          }
           const float r = sigmoidf_(gir[i] + ghr);
           const float z = sigmoidf_(giz[i] + ghz);
           const float n = tanhf(gin[i] + r * ghn);
@@ -216,42 +244,54 @@ gru_seq_fwd_kernel(const float* __restrict__ gi, const bf16* __restrict__ Whh, c
           gs[0] = r; gs[H] = z; gs[2 * H] = n; gs[3 * H] = ghn;
         }
       }
-      __syncthreads();                     // ghs is rewritten by the next pass
+      if (B > RB) cluster_sync();          // recv is rewritten by the next pass of this step
     }
     if (t + 1 < L) {
       arrivals += gridDim.x;
       grid_barrier(bar, arrivals);         // every CTA's slice of h_t is in HsT before anyone starts step t+1
     }
   }
+  cluster_sync();                          // no CTA leaves while a peer may still push into it
 }
 
 // ------------------------------------------------------------------------------------------------ backward (BPTT)
 // dHs [L*B, H]: gradient reaching h_t from outside the recurrence.  Per step (t = L-1 .. 0), for the CTA's units k:
 //   dh = dHs[t] + dh_{t+1} * z_{t+1} + dgh_{t+1} . W_hh[:, k];   cell derivative -> dgi[t], dgh[t] (fp32 and bf16 copies).
+template <int GU, int CS>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_seq_bwd_kernel(const float* __restrict__ dHs, const float* __restrict__ gates, const float* __restrict__ Hs,
                    const bf16* __restrict__ Whh, int B, int H, int L, float* __restrict__ dgi, float* __restrict__ dgh,
                    bf16* __restrict__ dgiT, bf16* dghT, unsigned int* bar) {
   ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
-  constexpr int NT = GU / 8;
-  constexpr int OP = NT * 8 + 1;
+  constexpr int CU = GU * CS;
+  constexpr int EPT = RB * GU / THREADS;
+  constexpr int OW = GU;
+  constexpr int NTW = CS * OW / 8 / 2;
+  static_assert((CS * OW / 8) % 2 == 0, "the cluster's columns split into two warp halves");
+  constexpr int RP = OW + 2;
   const int K = 3 * H;
-  const int wp = K + 8;
-  bf16* Ws = (bf16*)smraw;                                  // [GU][wp]   row u = W_hh[:, j0 + u]
-  bf16* As = Ws + (size_t)GU * wp;                          // 2 x [RB][AP]
-  float* cs = (float*)(As + 2 * RB * AP);                   // [RB][OP]   dgh_{t+1} W_hh for this CTA's units
-  float* dhz = cs + RB * OP;                                // [B][GU]    dh_{t+1} * z_{t+1}
-  const int j0 = blockIdx.x * GU;
+  const int KS = K / CS;
+  const int wp = KS + 8;
+  bf16* Ws = (bf16*)smraw;                                  // [CU][wp]: row n = W_hh[rank*KS .. +KS, jc0 + n]
+  bf16* As = Ws + (size_t)CU * wp;                          // 2 x [RB][AP]
+  float* recv = (float*)(As + 2 * RB * AP);                 // [CS][RB][RP]
+  float* dhz = recv + CS * RB * RP;                         // [B][GU]    dh_{t+1} * z_{t+1}
+  const uint32_t rank = cluster_rank();
+  const int jc0 = (blockIdx.x / CS) * CU;
+  const int j0 = jc0 + (int)rank * GU;
   const int tid = threadIdx.x;
-  for (int c = tid; c < K; c += THREADS) {
-    const uint4 v = *(const uint4*)(Whh + (size_t)c * H + j0);       // 8 consecutive columns of row c
+  for (int e = tid; e < KS * (CU / 8); e += THREADS) {
+    const int cl = e / (CU / 8), c8 = e % (CU / 8);
+    const uint4 v = *(const uint4*)(Whh + ((size_t)rank * KS + cl) * H + jc0 + c8 * 8);      // 8 consecutive columns
     const bf16* pv = (const bf16*)&v;
 #pragma unroll
-    for (int u = 0; u < GU; ++u) Ws[(size_t)u * wp + c] = pv[u];
+    for (int u = 0; u < 8; ++u) Ws[(size_t)(c8 * 8 + u) * wp + cl] = pv[u];
   }
   for (int e = tid; e < B * GU; e += THREADS) dhz[e] = 0.f;
+  for (int e = tid; e < CS * RB * RP; e += THREADS) recv[e] = 0.f;
   __syncthreads();
+  cluster_sync();
   unsigned int arrivals = 0;
   for (int t = L - 1; t >= 0; --t) {
     for (int rb0 = 0; rb0 < B; rb0 += RB) {
@@ -270,11 +310,14 @@ gru_seq_bwd_kernel(const float* __restrict__ dHs, const float* __restrict__ gate
           gr[i] = gz[i] = gn[i] = gg[i] = dd[i] = hp[i] = 0.f;
         }
       }
-      float acc[NT][4];
+      if (t < L - 1) {
+        float acc[NTW][4];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-      if (t < L - 1) skinny_gemm<NT>(dghT + (size_t)(t + 1) * B * K, B, K, rb0, As, Ws, wp, acc);
-      reduce_to_smem<NT>(acc, cs);
+        for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        skinny_gemm<NTW>(dghT + (size_t)(t + 1) * B * K, B, K, rb0, (int)rank * KS, KS / KC, As, Ws, wp, acc);
+        push_partials<NTW, OW>(acc, recv, rank);
+        cluster_sync();
+      }
 #pragma unroll
       for (int i = 0; i < EPT; ++i) {
         const int e = tid + i * THREADS;
@@ -282,7 +325,9 @@ gru_seq_bwd_kernel(const float* __restrict__ dHs, const float* __restrict__ gate
         const int b = rb0 + bl, j = j0 + u;
         if (b < B) {
           const float r = gr[i], z = gz[i], n = gn[i], ghn = gg[i];
-          const float d = dd[i] + dhz[b * GU + u] + cs[bl * OP + u];
+          float d = dd[i] + dhz[b * GU + u];
+#pragma unroll
+          for (int s = 0; s < CS; ++s) d += recv[((size_t)s * RB + bl) * RP + u];
           const float dn = d * (1.f - z);
           const float dz = d * (hp[i] - n);
           const float dnp = dn * (1.f - n * n);
@@ -298,51 +343,93 @@ gru_seq_bwd_kernel(const float* __restrict__ dHs, const float* __restrict__ gate
           dghT[o + 2 * H] = __float2bfloat16_rn(dnp * r);
         }
       }
-      __syncthreads();
+      if (B > RB) cluster_sync();
     }
     if (t > 0) {
       arrivals += gridDim.x;
       grid_barrier(bar, arrivals);         // dgh_t of every unit is in dghT before anyone starts step t-1
     }
   }
-}
-
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+  cluster_sync();
 }
 
 int check_shape(const char* who, int B, int H, int L) {
   EK_REQUIRE(B > 0 && L > 0 && H > 0, EK_ERR_SHAPE, "%s: bad shape B=%d H=%d L=%d", who, B, H, L);
-  EK_REQUIRE(H % KC == 0, EK_ERR_UNSUPPORTED, "%s: H=%d must be a multiple of %d", who, H, KC);
-  EK_REQUIRE(H / GU <= sm_count(), EK_ERR_UNSUPPORTED,
-             "%s: H/%d = %d CTAs must be co-resident (one per SM, %d SMs)", who, GU, H / GU, sm_count());
+  EK_REQUIRE(H % 1024 == 0, EK_ERR_UNSUPPORTED, "%s: H=%d must be a multiple of 1024", who, H);
   return EK_OK;
 }
 
+template <int CS, typename Kern, typename... Args>
+int launch_clustered(const char* who, Kern kern, int grid, size_t smem, cudaStream_t st, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "%s: cannot set smem attr (%zu bytes): %s", who, smem, cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = ek_pdl_enabled();
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  // the grid barrier needs every cluster resident at the same time
+  int max_clusters = 0;
+  e = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+  EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "%s: cudaOccupancyMaxActiveClusters: %s", who, cudaGetErrorString(e));
+  EK_REQUIRE(max_clusters >= grid / CS, EK_ERR_UNSUPPORTED, "%s: %d clusters of %d CTAs needed, %d fit on this device", who,
+             grid / CS, CS, max_clusters);
+  cfg.numAttrs = 2;
+  e = cudaLaunchKernelEx(&cfg, kern, args...);
+  EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
+  return EK_OK;
+}
+
+template <int GU, int CS>
+int fwd_launch(const float* gi, const bf16* Whh, const float* bhh, int B, int H, int L, float* Hs, bf16* HsT, float* gates,
+               unsigned int* bar, cudaStream_t st) {
+  const size_t nbuf = (H / CS / KC > 1) ? 2 : 1;
+  const size_t smem = (size_t)CS * 3 * GU * (H / CS + 8) * 2 + nbuf * RB * AP * 2 +
+                      (size_t)CS * RB * (3 * GU + 2) * 4 + (size_t)B * GU * 4;
+  EK_REQUIRE(smem <= 227 * 1024, EK_ERR_UNSUPPORTED, "gru_seq_fwd: B=%d H=%d needs %zu bytes of shared memory", B, H, smem);
+  cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
+  return launch_clustered<CS>("gru_seq_fwd", gru_seq_fwd_kernel<GU, CS>, H / GU, smem, st, gi, Whh, bhh, B, H, L, Hs, HsT,
+                              gates, bar);
+}
+template <int GU, int CS>
+int bwd_launch(const float* dHs, const float* gates, const float* Hs, const bf16* Whh, int B, int H, int L, float* dgi,
+               float* dgh, bf16* dgiT, bf16* dghT, unsigned int* bar, cudaStream_t st) {
+  const size_t smem = (size_t)GU * CS * (3 * H / CS + 8) * 2 + (size_t)2 * RB * AP * 2 + (size_t)CS * RB * (GU + 2) * 4 +
+                      (size_t)B * GU * 4;
+  EK_REQUIRE(smem <= 227 * 1024, EK_ERR_UNSUPPORTED, "gru_seq_bwd: B=%d H=%d needs %zu bytes of shared memory", B, H, smem);
+  cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
+  return launch_clustered<CS>("gru_seq_bwd", gru_seq_bwd_kernel<GU, CS>, H / GU, smem, st, dHs, gates, Hs, Whh, B, H, L,
+                              dgi, dgh, dgiT, dghT, bar);
+}
+
 }  // namespace
+
+// variant: 0 = default (forward <8,2>, backward <16,4>), 1 = <8,2>, 2 = <16,4>   (EKAID_B200_GRU_VARIANT, for measurements)
+static int gru_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EKAID_B200_GRU_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 int ek_gru_seq_fwd_launch(const float* gi, const bf16* Whh, const float* bhh, int B, int H, int L, float* Hs, bf16* HsT,
                           float* gates, unsigned int* bar, cudaStream_t st) {
   int rc = check_shape("gru_seq_fwd", B, H, L);
   if (rc) return rc;
-  const size_t smem = (size_t)3 * GU * (H + 8) * 2 + (size_t)2 * RB * AP * 2 + (size_t)RB * (3 * GU + 1) * 4 +
-                      (size_t)B * GU * 4;
-  EK_REQUIRE(smem <= 227 * 1024, EK_ERR_UNSUPPORTED, "gru_seq_fwd: B=%d H=%d needs %zu bytes of shared memory", B, H, smem);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gru_seq_fwd: cannot set smem attr: %s", cudaGetErrorString(e));
-    attr = smem;
-  }
-  cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
-  ek_launch(gru_seq_fwd_kernel, H / GU, THREADS, smem, st, gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar);
+  if (gru_variant() == 2) rc = fwd_launch<16, 4>(gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar, st);
+  else rc = fwd_launch<8, 2>(gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar, st);
+  if (rc) return rc;
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -351,17 +438,9 @@ int ek_gru_seq_bwd_launch(const float* dHs, const float* gates, const float* Hs,
                           float* dgi, float* dgh, bf16* dgiT, bf16* dghT, unsigned int* bar, cudaStream_t st) {
   int rc = check_shape("gru_seq_bwd", B, H, L);
   if (rc) return rc;
-  const size_t smem = (size_t)GU * (3 * H + 8) * 2 + (size_t)2 * RB * AP * 2 + (size_t)RB * (GU + 1) * 4 +
-                      (size_t)B * GU * 4;
-  EK_REQUIRE(smem <= 227 * 1024, EK_ERR_UNSUPPORTED, "gru_seq_bwd: B=%d H=%d needs %zu bytes of shared memory", B, H, smem);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gru_seq_bwd: cannot set smem attr: %s", cudaGetErrorString(e));
-    attr = smem;
-  }
-  cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
-  ek_launch(gru_seq_bwd_kernel, H / GU, THREADS, smem, st, dHs, gates, Hs, Whh, B, H, L, dgi, dgh, dgiT, dghT, bar);
+  if (gru_variant() == 1) rc = bwd_launch<8, 2>(dHs, gates, Hs, Whh, B, H, L, dgi, dgh, dgiT, dghT, bar, st);
+  else rc = bwd_launch<16, 4>(dHs, gates, Hs, Whh, B, H, L, dgi, dgh, dgiT, dghT, bar, st);
+  if (rc) return rc;
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

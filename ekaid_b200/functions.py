@@ -329,8 +329,11 @@ class WeightedSumsFn(torch.autograd.Function):
         pw = (ctypes.c_void_p * cnt)(*[w.data_ptr() if w is not None else None for w in weights])
         ns = (ctypes.c_int64 * cnt)(*[t.numel() for t in ts])
         cf = (ctypes.c_float * cnt)(*[float(c) for c in coefs])
+        key = ("wsum", str(dev), torch.cuda.current_stream().cuda_stream)
+        if key not in _colsum_bufs:
+            _colsum_bufs[key] = torch.zeros(128, dtype=torch.float32, device=dev)
         call("weighted_sums", cnt, ctypes.addressof(pa), ctypes.addressof(pw), ctypes.addressof(ns),
-             ctypes.addressof(cf), out.data_ptr())
+             ctypes.addressof(cf), out.data_ptr(), _colsum_bufs[key].data_ptr())
         ctx.coefs, ctx.weights = coefs, weights
         ctx.shapes = [t.shape for t in tensors]
         return out.view(())
@@ -414,6 +417,10 @@ class LinearFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # question path
 # ------------------------------------------------------------------------------------------------
+# step.GraphFusionStep sets this: called (no arguments) right before the BPTT recurrence is launched, i.e. when the
+# question path starts its longest serial stretch -- the moment to put independent work next to it (the optimizer update
+# of the image-path parameters, whose gradients are all enqueued by then).
+BPTT_HOOK = None
 GRU_SEQ = os.environ.get("EKAID_B200_GRU_SEQ", "1") != "0"     # 0: per-step GEMM + cell kernels on the bf16 path too
 GRU_SEQ_MAX_BATCH = 64
 _barrier_bufs = {}
@@ -428,13 +435,12 @@ def _barrier_ws(dev):
 
 
 def _gru_seq_ok(pc, dev, B, H):
-    """The one-launch recurrence covers the bf16 path when all H/8 CTAs are co-resident (see gru_seq.cu).  Every CTA
-    streams the whole [B, H] / [B, 3H] operand each step, so beyond one 64-row pass the per-step tcgen05 GEMMs win
-    (measured at B = 256: 397 vs 312 us forward)."""
-    if not (GRU_SEQ and pc.bf16 and H % 512 == 0 and B <= GRU_SEQ_MAX_BATCH):
+    """The one-launch recurrence covers the bf16 path when all H/16 CTAs are co-resident (see gru_seq.cu).  It works
+    in passes of 64 batch rows, so for large batches the per-step tcgen05 GEMMs win."""
+    if not (GRU_SEQ and pc.bf16 and H % 1024 == 0 and B <= GRU_SEQ_MAX_BATCH):
         return False
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    return H // 8 <= sms
+    return H // 8 <= sms and B * 64 + 192 * 1024 <= 227 * 1024
 
 
 class QuestionFn(torch.autograd.Function):
@@ -529,6 +535,8 @@ class QuestionFn(torch.autograd.Function):
         dgh = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
         dgiT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgi
         dghT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgh
+        if BPTT_HOOK is not None:
+            BPTT_HOOK()
         if _gru_seq_ok(pc, dev, B, H):
             call("gru_seq_bwd", dHs.data_ptr(), gates.data_ptr(), Hs.data_ptr(), WhhT.data_ptr(), B, H, L, dgi.data_ptr(),
                  dgh.data_ptr(), dgiT.data_ptr(), dghT.data_ptr(), _barrier_ws(dev).data_ptr())

@@ -413,6 +413,10 @@ class ChangeDetector(nn.Module):
         """Parameters that can receive a gradient in setting='mode2'.  The rest exist only so reference checkpoints
         load (quirk Q11): SSRE.*, direction-0 attention layers (Q2), the never-called grouped conv linear_out_ (Q3)
         and the frozen embedding table.  torch.optim.Adam skips them too (their .grad stays None)."""
+        return [p for _, p in self.live_named_parameters()]
+
+    def live_named_parameters(self):
+        """(name, parameter) pairs of live_parameters()."""
         out = []
         for name, p in self.named_parameters():
             if not p.requires_grad or name.startswith("SSRE."):
@@ -424,7 +428,7 @@ class ChangeDetector(nn.Module):
                 owner = self.get_submodule(".".join(parts[:parts.index("neighbor_net")]))
                 if int(parts[parts.index("neighbor_net") + 1]) != owner.dir_num - 1:
                     continue
-            out.append(p)
+            out.append((name, p))
         return out
 
     def set_precision(self, precision: str) -> "ChangeDetector":
@@ -476,7 +480,7 @@ class ChangeDetector(nn.Module):
         # the same split in backward (BPTT next to the weight-norm / img gradients); a captured CUDA graph keeps it.
         cur = torch.cuda.current_stream(dev)
         if self._side is None:
-            self._side = torch.cuda.Stream(dev)
+            self._side = torch.cuda.Stream(dev, priority=-1)    # its small kernels go first when SM slots free up
         side = self._side
         side.wait_stream(cur)
         with torch.cuda.stream(side):

@@ -10,6 +10,7 @@ do in the reference; without one, a fixed cotangent stands in for the decoder gr
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -36,6 +37,7 @@ class FlatAdam:
         self.pow_state = torch.ones(2, dtype=torch.float32, device=dev)
         off = 0
         self.slots = []
+        self.offsets = [0]            # start of every parameter in the flat buffers (+ the total at the end)
         for p in params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
@@ -46,6 +48,7 @@ class FlatAdam:
             # the backward kernels write this parameter's gradient straight into its slot (functions.GRAD_SLOTS)
             functions.GRAD_SLOTS[p.data_ptr()] = slot
             off += (k + al - 1) // al * al
+            self.offsets.append(off)
         self.params = params
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self._checked = 0
@@ -62,10 +65,21 @@ class FlatAdam:
             if p.grad is not None and p.grad.data_ptr() != slot.data_ptr():
                 raise RuntimeError("gradient of a parameter of shape %s did not land in its flat slot" % (tuple(p.shape),))
 
-    def step(self):
+    def advance(self):
+        """beta^t bookkeeping of the step about to be applied (once per step, before the first update_range)."""
         lib.call("adam_advance", self.pow_state.data_ptr(), self.betas[0], self.betas[1])
-        lib.call("adam_step", self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
-                 self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.pow_state.data_ptr())
+
+    def update_range(self, lo: int, hi: int, max_ctas: int = 0):
+        """Adam update of flat elements [lo, hi) (a whole number of parameters)."""
+        if hi <= lo:
+            return
+        f, g, m, v = (t[lo:hi] for t in (self.flat, self.grad, self.m, self.v))
+        lib.call("adam_step", f.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), hi - lo, self.lr, self.betas[0],
+                 self.betas[1], self.eps, self.wd, self.pow_state.data_ptr(), max_ctas)
+
+    def step(self):
+        self.advance()
+        self.update_range(0, self.flat.numel())
 
 
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
@@ -125,9 +139,50 @@ class GraphFusionStep:
         self.graph = graph
         self.decoder_loss = decoder_loss
         self.pg = process_group
-        self.opt = FlatAdam(change_detector.live_parameters(), lr=lr)
+        # Flat parameter order: image path first, question path (embedding, GRU, question attention) last.  The
+        # question-path gradients are the last to be finished in backward (BPTT starts only when every relation encoder
+        # has contributed to d(question vector)), so the optimizer update -- and, data-parallel, the all-reduce -- of
+        # the image-path segment is issued from an autograd hook as soon as that segment is complete and overlaps BPTT.
+        named = change_detector.live_named_parameters()
+        qpath = ("w_emb.", "q_emb.", "q_att.")
+        head = [p for n, p in named if not n.startswith(qpath)]
+        tail = [p for n, p in named if n.startswith(qpath)]
+        self.opt = FlatAdam(head + tail, lr=lr)
+        self._split = self.opt.offsets[len(head)]
+        self._armed = False
+        self._fired = 0
+        self._expected = None      # how many image-path parameters receive a gradient (learned on the first step:
+        self._early = False        # e.g. fc1 never does, its output is not part of the reference's loss -- Q11)
+        self._opt_stream = None
+        self._hooked = bool(head and tail and head[0].is_cuda and os.environ.get("EKAID_B200_EARLY_ADAM", "1") != "0")
+        if self._hooked:
+            for p in head:
+                p.register_post_accumulate_grad_hook(self._head_grad_ready)
         self._cot = None
         self._graph = None
+
+    def _head_grad_ready(self, _param):
+        """autograd hook: counts the image-path gradients of the running train_step."""
+        self._fired += 1
+
+    def _bptt_starts(self):
+        """functions.BPTT_HOOK: the question path is about to run its recurrence backwards (one long, register-light
+        kernel).  If every image-path gradient has been enqueued by now, their all-reduce and Adam update go out on the
+        optimizer stream and run next to it."""
+        if not self._armed or self._expected is None or self._fired != self._expected or self._early:
+            return
+        dev = self.opt.flat.device
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(dev)
+        st = self._opt_stream
+        st.wait_stream(self._main)                          # every image-path gradient
+        st.wait_stream(torch.cuda.current_stream(dev))      # ... and not before the GPU reaches the recurrence: the
+        with torch.cuda.stream(st):                         # GEMMs ahead of it need whole SMs, the recurrence does not
+            if self.pg is not None:
+                allreduce_mean_(self.opt.grad[:self._split], self.pg)
+            self.opt.advance()
+            self.opt.update_range(0, self._split, max_ctas=2 * 148)
+        self._early = True
 
     def _cotangents(self, bef):
         # stand in for d(decoder NLL)/d(bef, aft, diff): fixed unit-scale cotangents
@@ -163,13 +218,39 @@ class GraphFusionStep:
         if self.cd.training:
             rng_advance(self.opt.flat.device)      # fresh dropout masks (a kernel: replays draw new masks too)
         total = self.loss(inputs, labels, masks)
-        total.backward()
-        if self.opt._checked < 2 and not torch.cuda.is_current_stream_capturing():
+        self._early = False
+        self._fired = 0
+        self._main = torch.cuda.current_stream() if total.is_cuda else None
+        self._armed = self._hooked
+        if self._hooked:
+            functions.BPTT_HOOK = self._bptt_starts
+        try:
+            total.backward()
+        finally:
+            self._armed = False
+            if self._hooked:
+                functions.BPTT_HOOK = None
+        if self._hooked:
+            if self._expected is None:
+                self._expected = self._fired
+            elif self._fired != self._expected:
+                raise RuntimeError("the set of parameters receiving gradients changed between steps (%d -> %d): the "
+                                   "early optimizer update of the image-path segment is no longer valid"
+                                   % (self._expected, self._fired))
+        if total.is_cuda and self.opt._checked < 2 and not torch.cuda.is_current_stream_capturing():
             self.opt.check_slots()
             self.opt._checked += 1
-        if self.pg is not None:
-            allreduce_mean_(self.opt.grad, self.pg)
-        self.opt.step()
+        n = self.opt.flat.numel()
+        if self._early:
+            # the image-path segment is already being updated on the optimizer stream; finish with the question path
+            if self.pg is not None:
+                allreduce_mean_(self.opt.grad[self._split:], self.pg)
+            self.opt.update_range(self._split, n)
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
+        else:
+            if self.pg is not None:
+                allreduce_mean_(self.opt.grad, self.pg)
+            self.opt.step()
         return total.detach()
 
     # -- CUDA-graph replay of the whole step ------------------------------------------------------------------

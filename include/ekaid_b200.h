@@ -214,9 +214,10 @@ int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const voi
 int ekaid_small_linear(const float* x, int64_t ldx, int M, int K, const float* W, const float* b, int N, float* y,
                        void* stream);
 /* out[0] = sum_k coef[k] * <a_k, w_k> (w_k NULL: plain sum), k < count <= 5; a, w, n, coef are HOST arrays.  The step
- * objective of train_mimic.py:246-247 when the decoder's gradient arrives as cotangents; deterministic (one CTA). */
+ * objective of train_mimic.py:246-247 when the decoder's gradient arrives as cotangents; deterministic.  workspace: 65
+ * floats, word 0 a ticket counter (zero it once; every call leaves it zero). */
 int ekaid_weighted_sums(int count, const float* const* a, const float* const* w, const int64_t* n, const float* coef,
-                        float* out, void* stream);
+                        float* out, float* workspace, void* stream);
 
 /* ---- legacy weight_norm(dim=None) (models/fc.py:33-34): w = v * g / ||v||_F over the whole tensor -------------- */
 /* workspace: 128 floats; norm_out: 1 float kept for the backward */
@@ -249,8 +250,9 @@ int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, cons
 /* ---- optimizer (utils/utils.py:96-99 -> torch.optim.Adam semantics) -------------------------------------- */
 /* pow_state: device float[2] = {beta1^t, beta2^t}; call ekaid_adam_advance once per step before the updates */
 int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream);
+/* max_ctas > 0 caps the grid (an update running next to other kernels should not take every SM slot); 0 = full grid */
 int ekaid_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-                    float wd, const float* pow_state, void* stream);
+                    float wd, const float* pow_state, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

