@@ -115,11 +115,46 @@ __device__ __forceinline__ unsigned int ek_rand32(unsigned long long seed, unsig
   z ^= z >> 31;
   return (unsigned int)(z >> 32);
 }
+// One 64-bit draw decides four consecutive elements (16 bits each, p resolved to 2^-16): element idx of a site uses
+// lane idx & 3 of the draw of group idx >> 2.  Kernels that own aligned runs of elements hash once per group.
+__device__ __forceinline__ unsigned long long ek_draw64(unsigned long long seedv, unsigned int site, unsigned long long grp) {
+  unsigned long long z = seedv + (unsigned long long)site * 0x9E3779B97F4A7C15ull + grp * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 // multiplier of element idx: 0 (dropped) or 1/(1-p) (kept); 1 when dropout is off
 __device__ __forceinline__ float ek_drop_mult(const EkDrop& d, unsigned long long seedv, unsigned long long idx) {
   if (d.seed == nullptr || d.p <= 0.f) return 1.f;
-  const unsigned int thr = (unsigned int)(d.p * 4294967296.0f);
-  return ek_rand32(seedv, d.site, idx) >= thr ? 1.f / (1.f - d.p) : 0.f;
+  const unsigned int thr = (unsigned int)(d.p * 65536.0f);
+  const unsigned long long z = ek_draw64(seedv, d.site, idx >> 2);
+  return ((unsigned int)(z >> (16 * (idx & 3))) & 0xFFFFu) >= thr ? 1.f / (1.f - d.p) : 0.f;
+}
+// multipliers of the V consecutive elements e0 .. e0+V-1 (V = 2: e0 even; V % 4 == 0: one draw per aligned group of four)
+template <int V>
+__device__ __forceinline__ void ek_drop_multv(const EkDrop& d, unsigned long long seedv, unsigned long long e0, float* out) {
+  if (d.seed == nullptr || d.p <= 0.f) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = 1.f;
+    return;
+  }
+  const unsigned int thr = (unsigned int)(d.p * 65536.0f);
+  const float keep = 1.f / (1.f - d.p);
+  if (V == 2 && (e0 & 1) == 0) {
+    const unsigned long long z = ek_draw64(seedv, d.site, e0 >> 2) >> (16 * (e0 & 3));
+    out[0] = ((unsigned int)z & 0xFFFFu) >= thr ? keep : 0.f;
+    out[1] = ((unsigned int)(z >> 16) & 0xFFFFu) >= thr ? keep : 0.f;
+  } else if (V % 4 == 0 && (e0 & 3) == 0) {
+#pragma unroll
+    for (int g = 0; g < V / 4; ++g) {
+      const unsigned long long z = ek_draw64(seedv, d.site, (e0 >> 2) + g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) out[4 * g + k] = ((unsigned int)(z >> (16 * k)) & 0xFFFFu) >= thr ? keep : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; ++k) out[k] = ek_drop_mult(d, seedv, e0 + k);
+  }
 }
 __device__ __forceinline__ unsigned long long ek_seed(const EkDrop& d) { return d.seed ? *d.seed : 0ull; }
 // four independent 16-bit lanes from one 64-bit draw: multipliers of elements 4*group .. 4*group+3 (p resolved to 2^-16)

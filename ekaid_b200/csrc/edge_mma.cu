@@ -157,8 +157,10 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
           const float o0 = acc[it][nt][2 * hh] + bo.x, o1 = acc[it][nt][2 * hh + 1] + bo.y;
           const float2 xi = *(const float2*)(Xin + row * D + col);
           // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
-          const float p0 = (o0 + o0) * ek_drop_mult(dr, sd, row * D + col);
-          const float p1 = (o1 + o1) * ek_drop_mult(dr, sd, row * D + col + 1);
+          float dm[2];
+          ek_drop_multv<2>(dr, sd, row * D + col, dm);          // col is even: both lanes come from one draw
+          const float p0 = (o0 + o0) * dm[0];
+          const float p1 = (o1 + o1) * dm[1];
           const float x0 = xi.x + fmaxf(p0, 0.f), x1 = xi.y + fmaxf(p1, 0.f);
           *(float2*)(Xout + row * D + col) = make_float2(x0, x1);
           if (XoutT) *(__nv_bfloat162*)(XoutT + row * ldt + col) = __floats2bfloat162_rn(x0, x1);

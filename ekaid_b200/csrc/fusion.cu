@@ -204,18 +204,27 @@ template <typename T>
 __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int D, T* __restrict__ ctx,
                                 T* __restrict__ gate, T* __restrict__ CAT, EkDrop dc, EkDrop dg) {
   ek_pdl_prologue();
-  const long long total = M * D;
+  // four consecutive columns per thread (D % 4 == 0, checked by the launcher)
+  const long long total = M * D / 4;
   const unsigned long long sc = ek_seed(dc), sg = ek_seed(dg);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t * 4;
     const long long r = e / D;
     const int c = (int)(e % D);
-    const float cv = tanhf(pre[r * 2 * D + c]);
-    const float gv = sigmoidf_(pre[r * 2 * D + D + c]);
-    ctx[e] = from_f32<T>(cv);
-    gate[e] = from_f32<T>(gv);
+    const float4 pc = *(const float4*)(pre + r * 2 * D + c);
+    const float4 pg = *(const float4*)(pre + r * 2 * D + D + c);
+    const float cv[4] = {tanhf(pc.x), tanhf(pc.y), tanhf(pc.z), tanhf(pc.w)};
+    const float gv[4] = {sigmoidf_(pg.x), sigmoidf_(pg.y), sigmoidf_(pg.z), sigmoidf_(pg.w)};
     // train mode: Dropout(0.5) on the tanh output and, independently, on the sigmoid output (modules.py:279,281)
-    CAT[r * 3 * D + 2 * D + c] = from_f32<T>((gv * ek_drop_mult(dg, sg, e)) * (cv * ek_drop_mult(dc, sc, e)));
+    float mc[4], mg[4];
+    ek_drop_multv<4>(dc, sc, (unsigned long long)e, mc);
+    ek_drop_multv<4>(dg, sg, (unsigned long long)e, mg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ctx[e + k] = from_f32<T>(cv[k]);
+      gate[e + k] = from_f32<T>(gv[k]);
+      CAT[r * 3 * D + 2 * D + c + k] = from_f32<T>((gv[k] * mg[k]) * (cv[k] * mc[k]));
+    }
   }
 }
 // dXs = dCAT[:, 2D:3D] (fp32) -> dpre [M, 2D] (T)
@@ -223,16 +232,24 @@ template <typename T>
 __global__ void gate_bwd_kernel(const float* __restrict__ dCAT, const T* __restrict__ ctx, const T* __restrict__ gate,
                                 long long M, int D, T* __restrict__ dpre, EkDrop dc, EkDrop dg) {
   ek_pdl_prologue();
-  const long long total = M * D;
+  const long long total = M * D / 4;
   const unsigned long long sc = ek_seed(dc), sg = ek_seed(dg);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long e = t * 4;
     const long long r = e / D;
     const int c = (int)(e % D);
-    const float d = dCAT[r * 3 * D + 2 * D + c] * ek_drop_mult(dc, sc, e) * ek_drop_mult(dg, sg, e);
-    const float cv = to_f32<T>(ctx[e]), gv = to_f32<T>(gate[e]);
-    dpre[r * 2 * D + c] = from_f32<T>(d * gv * (1.f - cv * cv));
-    dpre[r * 2 * D + D + c] = from_f32<T>(d * cv * gv * (1.f - gv));
+    const float4 dv = *(const float4*)(dCAT + r * 3 * D + 2 * D + c);
+    const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
+    float mc[4], mg[4];
+    ek_drop_multv<4>(dc, sc, (unsigned long long)e, mc);
+    ek_drop_multv<4>(dg, sg, (unsigned long long)e, mg);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = dd[k] * mc[k] * mg[k];
+      const float cv = to_f32<T>(ctx[e + k]), gv = to_f32<T>(gate[e + k]);
+      dpre[r * 2 * D + c + k] = from_f32<T>(d * gv * (1.f - cv * cv));
+      dpre[r * 2 * D + D + c + k] = from_f32<T>(d * cv * gv * (1.f - gv));
+    }
   }
 }
 
@@ -378,8 +395,10 @@ __global__ void build_vq_kernel(const float* __restrict__ X, const float* __rest
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
     const unsigned long long e0 = (unsigned long long)m * W + c;
+    float mk[8];
+    ek_drop_multv<8>(dr, sd, e0, mk);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] *= ek_drop_mult(dr, sd, e0 + k);
+    for (int k = 0; k < 8; ++k) v[k] *= mk[k];
     T* dst = VQ + m * W + c;
 #pragma unroll
     for (int k = 0; k < 8; ++k) dst[k] = from_f32<T>(v[k]);
@@ -401,15 +420,20 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
     const long long m = t / CV;
     const int c = (int)(t % CV) * V;
     const unsigned long long e0 = (unsigned long long)m * C + c;
-    float v[V];
+    float v[V], mk[V];
+    ek_drop_multv<V>(d0, s0, e0, mk);
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = to_f32<TI>(in0[m * ldi + c + k]) * ek_drop_mult(d0, s0, e0 + k);
-    if (nin > 1)
+    for (int k = 0; k < V; ++k) v[k] = to_f32<TI>(in0[m * ldi + c + k]) * mk[k];
+    if (nin > 1) {
+      ek_drop_multv<V>(d1, s1, e0, mk);
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in1[m * ldi + c + k]) * ek_drop_mult(d1, s1, e0 + k);
-    if (nin > 2)
+      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in1[m * ldi + c + k]) * mk[k];
+    }
+    if (nin > 2) {
+      ek_drop_multv<V>(d2, s2, e0, mk);
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in2[m * ldi + c + k]) * ek_drop_mult(d2, s2, e0 + k);
+      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in2[m * ldi + c + k]) * mk[k];
+    }
     if (outf) {
 #pragma unroll
       for (int k = 0; k < V; ++k) {
@@ -687,20 +711,22 @@ int ek_combine_diff_bwd_launch(const float* dXc, const float* dCAT, long long BN
 
 int ek_gate_fwd_launch(int is_bf16, const float* pre, long long M, int D, void* ctx, void* gate, void* CAT, EkDrop dc,
                        EkDrop dg, cudaStream_t st) {
+  EK_REQUIRE(D % 4 == 0 && ((uintptr_t)pre & 15) == 0, EK_ERR_ALIGN, "gate_fwd: D=%d must be a multiple of 4, pre 16-byte aligned", D);
   if (is_bf16)
-    ek_launch(gate_fwd_kernel<bf16>, grid_for(M * D), 256, 0, st, pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT, dc, dg);
+    ek_launch(gate_fwd_kernel<bf16>, grid_for(M * D / 4), 256, 0, st, pre, M, D, (bf16*)ctx, (bf16*)gate, (bf16*)CAT, dc, dg);
   else
-    ek_launch(gate_fwd_kernel<float>, grid_for(M * D), 256, 0, st, pre, M, D, (float*)ctx, (float*)gate, (float*)CAT, dc, dg);
+    ek_launch(gate_fwd_kernel<float>, grid_for(M * D / 4), 256, 0, st, pre, M, D, (float*)ctx, (float*)gate, (float*)CAT, dc, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
 int ek_gate_bwd_launch(int is_bf16, const float* dCAT, const void* ctx, const void* gate, long long M, int D,
                        void* dpre, EkDrop dc, EkDrop dg, cudaStream_t st) {
+  EK_REQUIRE(D % 4 == 0 && ((uintptr_t)dCAT & 15) == 0, EK_ERR_ALIGN, "gate_bwd: D=%d must be a multiple of 4, dCAT 16-byte aligned", D);
   if (is_bf16)
-    ek_launch(gate_bwd_kernel<bf16>, grid_for(M * D), 256, 0, st, dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre,
+    ek_launch(gate_bwd_kernel<bf16>, grid_for(M * D / 4), 256, 0, st, dCAT, (const bf16*)ctx, (const bf16*)gate, M, D, (bf16*)dpre,
                                                            dc, dg);
   else
-    ek_launch(gate_bwd_kernel<float>, grid_for(M * D), 256, 0, st, dCAT, (const float*)ctx, (const float*)gate, M, D,
+    ek_launch(gate_bwd_kernel<float>, grid_for(M * D / 4), 256, 0, st, dCAT, (const float*)ctx, (const float*)gate, M, D,
                                                             (float*)dpre, dc, dg);
   EK_CHECK_LAUNCH();
   return EK_OK;

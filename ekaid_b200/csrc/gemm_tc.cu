@@ -166,10 +166,10 @@ __device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uin
               }
             }
             if (ep.drop.seed) {
-              const unsigned long long sd = ek_seed(ep.drop);
+              float mk[32];
+              ek_drop_multv<32>(ep.drop, ek_seed(ep.drop), (unsigned long long)m * ep.dropN + ep.dropOff + nb, mk);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                v[j] *= ek_drop_mult(ep.drop, sd, (unsigned long long)m * ep.dropN + ep.dropOff + nb + j);
+              for (int j = 0; j < 32; ++j) v[j] *= mk[j];
             }
             if (ep.addend) {
               const float* ap = ep.addend + m * ep.ldadd + nb;
@@ -434,8 +434,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                   if (ep.drop.seed) {
                     const unsigned long long e0 = (unsigned long long)mm * ep.dropN + ep.dropOff + n;
-                    v.x *= ek_drop_mult(ep.drop, dseed, e0);     v.y *= ek_drop_mult(ep.drop, dseed, e0 + 1);
-                    v.z *= ek_drop_mult(ep.drop, dseed, e0 + 2); v.w *= ek_drop_mult(ep.drop, dseed, e0 + 3);
+                    float mk[4];
+                    ek_drop_multv<4>(ep.drop, dseed, e0, mk);
+                    v.x *= mk[0]; v.y *= mk[1]; v.z *= mk[2]; v.w *= mk[3];
                   }
                   if (ep.addend) {
                     const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + n);

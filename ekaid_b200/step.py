@@ -181,7 +181,7 @@ class GraphFusionStep:
             if self.pg is not None:
                 allreduce_mean_(self.opt.grad[:self._split], self.pg)
             self.opt.advance()
-            self.opt.update_range(0, self._split, max_ctas=2 * 148)
+            self.opt.update_range(0, self._split, max_ctas=int(os.environ.get("EKAID_B200_BG_CTAS", "148")))
         self._early = True
 
     def _cotangents(self, bef):
