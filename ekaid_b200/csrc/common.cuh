@@ -99,6 +99,39 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
+// V consecutive elements <-> registers with explicit 8/16-byte accesses (pointers aligned to V * sizeof(T); V in {4, 8})
+template <typename T, int V> __device__ __forceinline__ void store_vec(T* dst, const float* v);
+template <> __device__ __forceinline__ void store_vec<float, 4>(float* dst, const float* v) {
+  *(float4*)dst = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store_vec<float, 8>(float* dst, const float* v) {
+  *(float4*)dst = make_float4(v[0], v[1], v[2], v[3]);
+  *(float4*)(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store_vec<bf16, 4>(bf16* dst, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 pk;
+  pk.x = *(uint32_t*)&a; pk.y = *(uint32_t*)&b;
+  *(uint2*)dst = pk;
+}
+template <> __device__ __forceinline__ void store_vec<bf16, 8>(bf16* dst, const float* v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+  uint4 pk;
+  pk.x = *(uint32_t*)&a; pk.y = *(uint32_t*)&b; pk.z = *(uint32_t*)&c; pk.w = *(uint32_t*)&d;
+  *(uint4*)dst = pk;
+}
+template <typename T, int V> __device__ __forceinline__ void load_vec(const T* src, float* v);
+template <> __device__ __forceinline__ void load_vec<float, 4>(const float* src, float* v) {
+  const float4 a = *(const float4*)src;
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <> __device__ __forceinline__ void load_vec<bf16, 4>(const bf16* src, float* v) {
+  const uint2 raw = *(const uint2*)src;
+  const float2 a = __bfloat1622float2(*(const __nv_bfloat162*)&raw.x), b = __bfloat1622float2(*(const __nv_bfloat162*)&raw.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // Counter-based dropout RNG (splitmix64 finaliser): the mask of element `idx` at dropout site `site` for the step

@@ -219,12 +219,12 @@ __global__ void gate_fwd_kernel(const float* __restrict__ pre, long long M, int 
     float mc[4], mg[4];
     ek_drop_multv<4>(dc, sc, (unsigned long long)e, mc);
     ek_drop_multv<4>(dg, sg, (unsigned long long)e, mg);
+    float xs[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      ctx[e + k] = from_f32<T>(cv[k]);
-      gate[e + k] = from_f32<T>(gv[k]);
-      CAT[r * 3 * D + 2 * D + c + k] = from_f32<T>((gv[k] * mg[k]) * (cv[k] * mc[k]));
-    }
+    for (int k = 0; k < 4; ++k) xs[k] = (gv[k] * mg[k]) * (cv[k] * mc[k]);
+    store_vec<T, 4>(ctx + e, cv);
+    store_vec<T, 4>(gate + e, gv);
+    store_vec<T, 4>(CAT + r * 3 * D + 2 * D + c, xs);
   }
 }
 // dXs = dCAT[:, 2D:3D] (fp32) -> dpre [M, 2D] (T)
@@ -243,13 +243,17 @@ __global__ void gate_bwd_kernel(const float* __restrict__ dCAT, const T* __restr
     float mc[4], mg[4];
     ek_drop_multv<4>(dc, sc, (unsigned long long)e, mc);
     ek_drop_multv<4>(dg, sg, (unsigned long long)e, mg);
+    float cv[4], gv[4], dc4[4], dg4[4];
+    load_vec<T, 4>(ctx + e, cv);
+    load_vec<T, 4>(gate + e, gv);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float d = dd[k] * mc[k] * mg[k];
-      const float cv = to_f32<T>(ctx[e + k]), gv = to_f32<T>(gate[e + k]);
-      dpre[r * 2 * D + c + k] = from_f32<T>(d * gv * (1.f - cv * cv));
-      dpre[r * 2 * D + D + c + k] = from_f32<T>(d * cv * gv * (1.f - gv));
+      dc4[k] = d * gv[k] * (1.f - cv[k] * cv[k]);
+      dg4[k] = d * cv[k] * gv[k] * (1.f - gv[k]);
     }
+    store_vec<T, 4>(dpre + r * 2 * D + c, dc4);
+    store_vec<T, 4>(dpre + r * 2 * D + D + c, dg4);
   }
 }
 
@@ -399,9 +403,7 @@ __global__ void build_vq_kernel(const float* __restrict__ X, const float* __rest
     ek_drop_multv<8>(dr, sd, e0, mk);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] *= mk[k];
-    T* dst = VQ + m * W + c;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) dst[k] = from_f32<T>(v[k]);
+    store_vec<T, 8>(VQ + m * W + c, v);
   }
 }
 // out = sum_k mult_k(idx) * in_k   (k < nin <= 3; mult_k = 1 when site k has p = 0);  idx = m*C + c
@@ -420,30 +422,39 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
     const long long m = t / CV;
     const int c = (int)(t % CV) * V;
     const unsigned long long e0 = (unsigned long long)m * C + c;
-    float v[V], mk[V];
+    float v[V], mk[V], x[V];
     ek_drop_multv<V>(d0, s0, e0, mk);
+    if constexpr (V == 4) load_vec<TI, 4>(in0 + m * ldi + c, x);
+    else x[0] = to_f32<TI>(in0[m * ldi + c]);
 #pragma unroll
-    for (int k = 0; k < V; ++k) v[k] = to_f32<TI>(in0[m * ldi + c + k]) * mk[k];
+    for (int k = 0; k < V; ++k) v[k] = x[k] * mk[k];
     if (nin > 1) {
       ek_drop_multv<V>(d1, s1, e0, mk);
+      if constexpr (V == 4) load_vec<TI, 4>(in1 + m * ldi + c, x);
+      else x[0] = to_f32<TI>(in1[m * ldi + c]);
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in1[m * ldi + c + k]) * mk[k];
+      for (int k = 0; k < V; ++k) v[k] += x[k] * mk[k];
     }
     if (nin > 2) {
       ek_drop_multv<V>(d2, s2, e0, mk);
+      if constexpr (V == 4) load_vec<TI, 4>(in2 + m * ldi + c, x);
+      else x[0] = to_f32<TI>(in2[m * ldi + c]);
 #pragma unroll
-      for (int k = 0; k < V; ++k) v[k] += to_f32<TI>(in2[m * ldi + c + k]) * mk[k];
+      for (int k = 0; k < V; ++k) v[k] += x[k] * mk[k];
     }
     if (outf) {
+      if (accumulate) {
+        if constexpr (V == 4) load_vec<float, 4>(outf + m * ldf + c, x);
+        else x[0] = outf[m * ldf + c];
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        if (accumulate) v[k] += outf[m * ldf + c + k];
-        outf[m * ldf + c + k] = v[k];
+        for (int k = 0; k < V; ++k) v[k] += x[k];
       }
+      if constexpr (V == 4) store_vec<float, 4>(outf + m * ldf + c, v);
+      else outf[m * ldf + c] = v[0];
     }
     if (outT) {
-#pragma unroll
-      for (int k = 0; k < V; ++k) outT[m * ldo + c + k] = from_f32<TO>(v[k]);
+      if constexpr (V == 4) store_vec<TO, 4>(outT + m * ldo + c, v);
+      else outT[m * ldo + c] = from_f32<TO>(v[0]);
     }
   }
 }
@@ -816,7 +827,8 @@ static void drop_combine_dispatch(int in_bf16, int out_bf16, int nin, const void
 int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
                            long long ldi, EkDrop d0, EkDrop d1, EkDrop d2, long long M, int C, float* outf,
                            long long ldf, int accumulate, void* outT, long long ldo, cudaStream_t st) {
-  const bool v4 = (C % 4 == 0) && (ldi % 4 == 0) && (!outf || ldf % 4 == 0) && (!outT || ldo % 4 == 0);
+  const uintptr_t ptrs = (uintptr_t)in0 | (uintptr_t)in1 | (uintptr_t)in2 | (uintptr_t)outf | (uintptr_t)outT;
+  const bool v4 = (C % 4 == 0) && (ldi % 4 == 0) && (!outf || ldf % 4 == 0) && (!outT || ldo % 4 == 0) && (ptrs & 15) == 0;
   if (v4) drop_combine_dispatch<4>(in_bf16, out_bf16, nin, in0, in1, in2, ldi, d0, d1, d2, M, C, outf, ldf, accumulate, outT, ldo, st);
   else drop_combine_dispatch<1>(in_bf16, out_bf16, nin, in0, in1, in2, ldi, d0, d1, d2, M, C, outf, ldf, accumulate, outT, ldo, st);
   EK_CHECK_LAUNCH();
