@@ -68,6 +68,7 @@ int ek_edge_softmax_fwd_launch(int, const void*, long long, int, const float*, c
 int ek_edge_aggregate_fwd_launch(int, const float*, const void*, long long, int, const float*, const float*, int, int,
                                  int, int, float*, void*, long long, uint8_t*, EkDrop, const void*, cudaStream_t);
 int ek_edge_num_slices(int D);
+int ek_edge_bwd_slices(int, int, int, int, int, int);
 int ek_edge_aggregate_bwd_launch(int, const float*, const uint8_t*, const float*, const void*, long long, int, int, int,
                                  int, int, void*, float*, float*, float, const void*, cudaStream_t);
 int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*, long long, int, const float*, int,
@@ -225,6 +226,9 @@ int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64
                                       mk_drop(seed, site, p), Phl, ST);
 }
 int ekaid_edge_num_slices(int D) { return ek_edge_num_slices(D); }
+int ekaid_edge_bwd_slices(int is_bf16, int D, int N, int Kn, int H, int have_phl) {
+  return ek_edge_bwd_slices(is_bf16, D, N, Kn, H, have_phl);
+}
 int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                              int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
                              float gscale, const void* Phl, void* stream) {

@@ -785,6 +785,12 @@ int ek_edge_aggregate_fwd_launch(int is_bf16, const float* P, const void* QKZ, l
 }
 
 int ek_edge_num_slices(int D) { return ek_div_up(D, AG_COLS); }
+int ek_agg_bwd_img_ok(int D, int N, int Kn, int H, int have_phl);
+// number of dP partial slices ekaid_edge_aggregate_bwd writes (and ekaid_edge_softmax_bwd has to add up) for this call
+int ek_edge_bwd_slices(int is_bf16, int D, int N, int Kn, int H, int have_phl) {
+  if (is_bf16 && ek_agg_bwd_img_ok(D, N, Kn, H, have_phl)) return 1;
+  return ek_edge_num_slices(D);
+}
 
 template <typename T>
 static int edge_aggregate_bwd_t(const float* dXout, const uint8_t* mask, const float* P, const T* QKZ, long long ld,

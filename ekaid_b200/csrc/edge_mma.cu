@@ -327,6 +327,163 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
 
 
 // ------------------------------------------------------------------------------------------------
+// aggregate backward, one CTA per image (N <= 64, all (h,j) rows in one chunk, D % 128 == 0, P available as bf16).
+// The CTA walks the D/128 column slices itself: P is staged once, Z slices are double-buffered with cp.async (the next
+// slice streams in while this one is multiplied), and dP = sum_c dout[i,c] Z[(h,j),c] stays in registers across the
+// slices -- no [slices, G, N, H*K] partial tensor, no re-reading of P, and loads overlap the MMAs.
+__global__ void __launch_bounds__(256, 1)
+agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ mask, const bf16* __restrict__ QKZ,
+                   long long ld, int D, int N, int Kn, int H, bf16* __restrict__ dQKZ, float* __restrict__ dOut,
+                   float* __restrict__ dP, float gscale, const bf16* __restrict__ Phl) {
+  ek_pdl_prologue();
+  constexpr int MR = 64;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  const int HK = H * Kn;
+  const int HKP = (HK + 15) & ~15;
+  const int PS = HKP + 8;
+  bf16* Ps = (bf16*)smraw;                          // [MR][PS]      P (i, (h,j)), staged once
+  bf16* Zs0 = Ps + (size_t)MR * PS;                 // 2 x [HKP][ZS] Z slice, double-buffered
+  float* raw = (float*)(Zs0 + (size_t)2 * HKP * ZS);   // [MR][NC]   dX slice as it comes from memory
+  uint8_t* mk = (uint8_t*)(raw + MR * NC);          // [MR][NC]      ReLU mask slice
+  bf16* dOs = (bf16*)(mk + MR * NC);                // [MR][ZS]      dout slice (bf16 operand)
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = D / NC;
+
+  auto issue_slice = [&](int s) {
+    const int c0 = s * NC;
+    load_z_chunk(Zs0 + (size_t)(s & 1) * HKP * ZS, QKZ, ld, D, g, N, Kn, HK, 0, HKP, c0);
+    for (int e = tid; e < MR * (NC / 4); e += 256) {           // 16-byte pieces of the fp32 rows
+      const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
+      float* dst = raw + i * NC + c;
+      if (i < N) cp_async16(dst, dXout + ((size_t)g * N + i) * D + c0 + c);
+      else *(float4*)dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int e = tid; e < MR * (NC / 16); e += 256) {
+      const int i = e / (NC / 16), c = (e % (NC / 16)) * 16;
+      uint8_t* dst = mk + i * NC + c;
+      if (i < N) cp_async16(dst, mask + ((size_t)g * N + i) * D + c0 + c);
+      else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+    }
+  };
+
+  {
+    const int cpr = HKP / 8;
+    for (int e = tid; e < MR * cpr; e += 256) {
+      const int i = e / cpr, ch = e % cpr;
+      bf16* dst = Ps + i * PS + ch * 8;
+      if (i < N && ch * 8 < HK) cp_async16(dst, Phl + ((size_t)g * N + i) * HK + ch * 8);
+      else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+    }
+  }
+  issue_slice(0);
+
+  // this warp's share of dP: 16 query rows x half of the (h,j) tiles, accumulated over all slices
+  const int ntiles = HKP / 8;
+  const int nhalf = (ntiles + 1) / 2;               // <= 16
+  const int pmt = warp >> 1, pnb = (warp & 1) * nhalf;
+  const int pcnt = min(nhalf, ntiles - pnb);
+  float accp[16][4];
+#pragma unroll
+  for (int a = 0; a < 16; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) accp[a][c] = 0.f;
+
+  for (int s = 0; s < S; ++s) {
+    const int c0 = s * NC;
+    const bf16* Zs = Zs0 + (size_t)(s & 1) * HKP * ZS;
+    cp_async_wait_all();
+    __syncthreads();                                 // slice s has landed; everybody is done with slice s-1
+    // dout = gscale * mask * dX  -> global (fp32, for the b_out column sum) and shared (bf16 operand)
+    for (int e = tid; e < MR * (NC / 4); e += 256) {
+      const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
+      const float4 d = *(const float4*)(raw + i * NC + c);
+      const uchar4 m = *(const uchar4*)(mk + i * NC + c);
+      const float4 v = make_float4(m.x ? gscale * d.x : 0.f, m.y ? gscale * d.y : 0.f, m.z ? gscale * d.z : 0.f,
+                                   m.w ? gscale * d.w : 0.f);
+      if (i < N) *(float4*)(dOut + ((size_t)g * N + i) * D + c0 + c) = v;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *(uint32_t*)&a;
+      pk.y = *(uint32_t*)&b;
+      *(uint2*)(dOs + i * ZS + c) = pk;
+    }
+    __syncthreads();
+    if (s + 1 < S) issue_slice(s + 1);               // streams in while this slice is multiplied
+    // ---- dZ[(h,j), c] = sum_i P[i,(h,j)] dout[i,c]
+    for (int mt = warp; mt < HKP / 16; mt += 8) {
+      float acc[16][4];
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < MR / 16; ++kt) {
+        uint32_t af[4];
+        const int arow = kt * 16 + (lane >> 4) * 8 + (lane & 7);
+        const int acol = mt * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4_t(af, Ps + arow * PS + acol);
+#pragma unroll
+        for (int np = 0; np < 8; ++np) {
+          uint32_t bfr[4];
+          const int brow = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+          const int bcol = np * 16 + (lane >> 4) * 8;
+          ldsm_x4_t(bfr, dOs + brow * ZS + bcol);
+          mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
+          mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 16; ++nt) {
+        const int col = c0 + nt * 8 + 2 * (lane & 3);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int k = mt * 16 + (lane >> 2) + hh * 8;
+          if (k >= HK) continue;
+          const int h = k / Kn, j = k % Kn;
+          *(__nv_bfloat162*)(dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + col) =
+              __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
+        }
+      }
+    }
+    // ---- dP[i, (h,j)] += sum_{c in slice} dout[i,c] Z[(h,j),c]
+#pragma unroll
+    for (int kt = 0; kt < NC / 16; ++kt) {
+      uint32_t af[4];
+      const int arow = pmt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const int acol = kt * 16 + (lane >> 4) * 8;
+      ldsm_x4(af, dOs + arow * ZS + acol);
+#pragma unroll
+      for (int np = 0; np < 8; ++np) {
+        if (2 * np < pcnt) {
+          uint32_t bfr[4];
+          int nrow = (pnb + 2 * np) * 8 + (lane >> 4) * 8 + (lane & 7);
+          if (nrow >= HKP) nrow = HKP - 1;           // odd tile count: second tile unused
+          const int kcol = kt * 16 + ((lane >> 3) & 1) * 8;
+          ldsm_x4(bfr, Zs + nrow * ZS + kcol);
+          mma_bf16_16816(accp[2 * np], af, bfr[0], bfr[1]);
+          if (2 * np + 1 < pcnt) mma_bf16_16816(accp[2 * np + 1], af, bfr[2], bfr[3]);
+        }
+      }
+    }
+  }
+  float* dPg = dP + (size_t)g * N * HK;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    if (nt >= pcnt) continue;
+    const int kk = (pnb + nt) * 8 + 2 * (lane & 3);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = pmt * 16 + (lane >> 2) + hh * 8;
+      if (i >= N) continue;
+      float* dst = dPg + (size_t)i * HK + kk;
+      if (kk < HK) dst[0] = accp[nt][2 * hh];
+      if (kk + 1 < HK) dst[1] = accp[nt][2 * hh + 1];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // scores + mask/bias + softmax on tensor cores: one CTA per (image, head), one warp per 16 query rows
 // ------------------------------------------------------------------------------------------------
 constexpr float NEG_MASK_MMA = -9e15f;
@@ -601,11 +758,30 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
   return EK_OK;
 }
 
+// one CTA per image with dP kept in registers (a single dP slice) when the shape allows it
+static size_t agg_bwd_img_smem(int N, int Kn, int H) {
+  const int HKP = (H * Kn + 15) & ~15;
+  return ((size_t)64 * (HKP + 8) + (size_t)2 * HKP * ZS + (size_t)64 * ZS) * sizeof(bf16) + (size_t)64 * NC * 5;
+}
+int ek_agg_bwd_img_ok(int D, int N, int Kn, int H, int have_phl) {
+  return have_phl && N <= 64 && D % NC == 0 && D / NC >= 2 && (H * Kn) % 8 == 0 && (D % 16) == 0 &&
+         agg_bwd_img_smem(N, Kn, H) <= 227 * 1024;
+}
+
 int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
                           int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, float gscale,
                           const bf16* Phl, cudaStream_t st) {
   if ((D % 8) || (ld % 8) || ((uintptr_t)QKZ & 15) || ((uintptr_t)dQKZ & 3) || N > 128) return EK_ERR_UNSUPPORTED;
   if (Phl && (((H * Kn) % 8) || ((uintptr_t)Phl & 15))) Phl = nullptr;
+  if (ek_agg_bwd_img_ok(D, N, Kn, H, Phl != nullptr) && !((uintptr_t)dXout & 15) && !((uintptr_t)mask & 15)) {
+    const size_t smem = agg_bwd_img_smem(N, Kn, H);
+    static size_t cimg = 0;
+    int rc = set_smem(agg_bwd_img_kernel, smem, cimg, "agg_bwd_img");
+    if (rc) return rc;
+    ek_launch(agg_bwd_img_kernel, G, 256, smem, st, dXout, mask, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, gscale, Phl);
+    EK_CHECK_LAUNCH();
+    return EK_OK;
+  }
   const int HK = H * Kn;
   const int HKp = (HK + 15) & ~15;
   const int kchunk = HKp < MAXCH ? HKp : MAXCH;

@@ -66,6 +66,7 @@ colsum_kernel(const T* __restrict__ src, long long ld, long long M, int N, const
 #pragma unroll
   for (int v = 0; v < VEC; ++v) s[v] = 0.f;
   if (vec_ok && n0 + VEC <= N) {
+#pragma unroll 4
     for (long long m = r0 + ty; m < r1; m += 8) {
       const float sc = rowscale ? rowscale[m] : 1.f;
       const uint4 raw = *(const uint4*)(src + m * ld + n0);
@@ -669,7 +670,7 @@ int ek_cast_bf16_f32_launch(const bf16* src, long long lds, float* dst, long lon
 // workspace: >= 64 * N floats
 int ek_colsum_launch(int is_bf16, const void* src, long long ld, long long M, int N, const float* rowscale, float* out,
                      float* workspace, cudaStream_t st) {
-  int nparts = (int)((M + 255) / 256);
+  int nparts = (int)((M + 31) / 32);       // enough CTAs to cover the machine even for the narrow (N = 1024) case
   if (nparts > 64) nparts = 64;
   if (nparts < 1) nparts = 1;
   // workspace: [1024 ticket counters, one per 32-column block, zero between calls] [64 * N partial sums].  The split is

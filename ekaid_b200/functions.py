@@ -719,7 +719,7 @@ class RelationFn(torch.autograd.Function):
         M = G * N
         W = (2 + H) * D
         dXn = _f32c(dXn).view(M, D)
-        ns = lib.load().ekaid_edge_num_slices(D)
+        ns = lib.load().ekaid_edge_bwd_slices(pc.f, D, N, Kn, H, 1 if Phl is not None else 0)
         alloc = torch.zeros if N > Kn else torch.empty
         dQKZ = alloc(M, W, dtype=pc.T, device=dev)
         dOut = torch.empty(M, D, dtype=torch.float32, device=dev)

@@ -149,6 +149,9 @@ int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
                              uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl, void* stream);
 int ekaid_edge_num_slices(int D);
+/* number of dP partial slices ekaid_edge_aggregate_bwd will write for these arguments (1 when the per-image tensor-core
+ * kernel applies: bf16, Phl given, N <= 64, D % 128 == 0; else ekaid_edge_num_slices(D)) */
+int ekaid_edge_bwd_slices(int is_bf16, int D, int N, int Kn, int H, int have_phl);
 /* dOut [G*N, D] = gscale*mask*dXout (gscale = 2/(1-p)); dQKZ[:, 2D:] = dZ; dPpart [slices, G,N,H,Kn] */
 int ekaid_edge_aggregate_bwd(int is_bf16, const float* dXout, const uint8_t* mask, const float* P, const void* QKZ,
                              int64_t ld, int D, int G, int N, int Kn, int H, void* dQKZ, float* dOut, float* dPpart,
