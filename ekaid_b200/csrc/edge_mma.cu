@@ -264,17 +264,15 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
         }
       }
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt) {
-        const int col = c0 + nt * 8 + 2 * (lane & 3);
-        if (col >= D) continue;
+      for (int hh = 0; hh < 2; ++hh) {
+        const int kk = mt * 16 + (lane >> 2) + hh * 8;
+        if (kk >= kc) continue;
+        const int k = k0 + kk, h = k / Kn, j = k - h * Kn;
+        bf16* rowp = dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + 2 * (lane & 3);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int kk = mt * 16 + (lane >> 2) + hh * 8;
-          if (kk >= kc) continue;
-          const int k = k0 + kk, h = k / Kn, j = k % Kn;
-          *(__nv_bfloat162*)(dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + col) =
-              __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
-        }
+        for (int nt = 0; nt < 16; ++nt)
+          if (c0 + nt * 8 + 2 * (lane & 3) < D)
+            *(__nv_bfloat162*)(rowp + nt * 8) = __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
       }
     }
     // ---- dPpart[i, (h,j)] = sum_c dout[i,c] Z[(h,j),c] : items = (16-row tile of i, half of the (h,j) tiles)
@@ -433,17 +431,21 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
           mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
         }
       }
+      // the two (h,j) rows this thread owns in the tile: one division each, outside the column loop
+      bf16* rowp[2];
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt) {
-        const int col = c0 + nt * 8 + 2 * (lane & 3);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int k = mt * 16 + (lane >> 2) + hh * 8;
+        const int h = k / Kn, j = k - h * Kn;
+        rowp[hh] = (k < HK) ? dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + 2 * (lane & 3)
+                            : nullptr;
+      }
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int k = mt * 16 + (lane >> 2) + hh * 8;
-          if (k >= HK) continue;
-          const int h = k / Kn, j = k % Kn;
-          *(__nv_bfloat162*)(dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + col) =
-              __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
-        }
+      for (int hh = 0; hh < 2; ++hh) {
+        if (rowp[hh] == nullptr) continue;
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt)
+          *(__nv_bfloat162*)(rowp[hh] + nt * 8) = __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
       }
     }
     // ---- dP[i, (h,j)] += sum_{c in slice} dout[i,c] Z[(h,j),c]
