@@ -16,6 +16,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "epilogue.cuh"
 
@@ -233,7 +234,7 @@ __device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uin
 template <int BN, int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, EkEpilogue ep, int vec_ok, int splits) {
+                    int K, EkEpilogue ep, int vec_ok, int splits, int tail_from) {
   using C = Cfg<BN, A_MN, B_MN>;
   static_assert(CL == 1 || BN >= 128, "the shared B tile must split into two TMA boxes");
   extern __shared__ uint8_t smem_raw[];
@@ -253,7 +254,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_tiles = num_mg * num_n;
   const int num_kb = (K + BK - 1) / BK;
   const int kb_per = (num_kb + splits - 1) / splits;
-  const int num_units = num_tiles * splits;
+  // Work units [0, tail_from) are whole tiles.  When the last wave of tiles would leave most SMs idle, the launcher sets
+  // tail_from < num_tiles and the remaining tiles are issued as half-width units (BN/2 columns each): the last wave
+  // then costs about half a tile time on twice as many SMs.  (splits == 1 and CL == 1 in that mode.)
+  const int num_units = (tail_from < num_tiles) ? tail_from + 2 * (num_tiles - tail_from) : num_tiles * splits;
+  auto decode = [&](int unit, int& tile, int& ncol0, int& bn_eff) {
+    if (unit < tail_from || tail_from >= num_tiles) {
+      tile = unit % num_tiles;
+      ncol0 = (tile / num_mg) * BN;
+      bn_eff = BN;
+    } else {
+      const int hidx = unit - tail_from;
+      tile = tail_from + (hidx >> 1);
+      ncol0 = (tile / num_mg) * BN + (hidx & 1) * (BN / 2);
+      bn_eff = BN / 2;
+    }
+  };
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   const int unit0 = blockIdx.x / CL;
   const int unit_stride = gridDim.x / CL;
@@ -290,16 +306,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
-        const int tile = unit % num_tiles;
-        const int kb0 = (unit / num_tiles) * kb_per;
+        int tile, n0, bn_eff;
+        decode(unit, tile, n0, bn_eff);
+        const int kb0 = (tail_from < num_tiles) ? 0 : (unit / num_tiles) * kb_per;
         const int kb1 = min(kb0 + kb_per, num_kb);
         const int m0 = ((tile % num_mg) * CL + (int)crank) * BM;
-        const int n0 = (tile / num_mg) * BN;
+        const bool half_w = bn_eff != BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], half_w ? C::A_BYTES + C::B_BYTES / 2 : C::STAGE_BYTES);
           const int k0 = kb * BK;
           if (A_MN == 0) {
             tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                 // box {64 k, 128 m}
@@ -310,11 +327,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (CL == 1) {
             if (B_MN == 0) {
-              tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);               // box {64 k, BN n}
+              if (BN == 256) {                                                  // two boxes {64 k, 128 n}
+                tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+                if (!half_w) tma_load_2d(&tmB, &full_bar[stage], sb + (BN / 2) * BK * 2, k0, n0 + BN / 2);
+              } else {
+                tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);             // box {64 k, BN n}
+              }
             } else {
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)                                 // box {64 n, 64 k}
-                tma_load_2d(&tmB, &full_bar[stage], sb + i * (64 * BK * 2), n0 + 64 * i, k0);
+                if (!half_w || i < BN / 128)
+                  tma_load_2d(&tmB, &full_bar[stage], sb + i * (64 * BK * 2), n0 + 64 * i, k0);
             }
           } else {
             // this CTA fetches half of the shared B tile and multicasts it to both CTAs of the pair
@@ -341,9 +364,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t idesc_half = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(BN >> 4) << 17);      // N = BN / 2
       for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
-        const int kb0 = (unit / num_tiles) * kb_per;
+        const int kb0 = (tail_from < num_tiles) ? 0 : (unit / num_tiles) * kb_per;
         const int kb1 = min(kb0 + kb_per, num_kb);
+        const uint32_t idesc_u = (tail_from < num_tiles && unit >= tail_from) ? idesc_half : idesc;
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
@@ -363,7 +388,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                         : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024)
                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, ((kb - kb0) | k) ? 1u : 0u);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc_u, ((kb - kb0) | k) ? 1u : 0u);
           }
           // frees the smem slot when these MMAs retire (in both CTAs of a pair: the peer multicasts into it too)
           if (CL == 1) tc_commit(&empty_bar[stage]);
@@ -380,11 +405,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp & 3) * (32 * 36);   // split-K path, half 0 only
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
-      const int tile = unit % num_tiles;
+      int tile, n0, bn_eff;
+      decode(unit, tile, n0, bn_eff);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m0 = ((tile % num_mg) * CL + (int)crank) * BM;
-      const int n0 = (tile / num_mg) * BN;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
       const long long mlane0 = (long long)m0 + q * 32;
@@ -487,7 +512,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else rowb_ptr = ep.rowb + (long long)((m / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
         }
         int nch = (N - n0 + 31) / 32;
-        nch = nch > BN / 32 ? BN / 32 : nch;
+        nch = nch > bn_eff / 32 ? bn_eff / 32 : nch;
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
         uint32_t ra[32], rb[32];
         int c = half;
@@ -596,7 +621,7 @@ int num_sms() {
 
 template <int BN, int A_MN, int B_MN, int CL>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep, int vec_ok,
-               int splits, cudaStream_t stream) {
+               int splits, int tail_halving, cudaStream_t stream) {
   using C = Cfg<BN, A_MN, B_MN>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN, CL>;
@@ -605,11 +630,19 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cannot set smem attr: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int units = ek_div_up(ek_div_up(M, BM), CL) * ek_div_up(N, BN) * splits;
+  const int tiles = ek_div_up(ek_div_up(M, BM), CL) * ek_div_up(N, BN);
+  const int units = tiles * splits;
   const int slots = num_sms() / CL;
   const int grid = CL * (units < slots ? units : slots);
+  // Tail halving: a last wave of R <= slots/2 whole tiles would keep most SMs idle for a full tile time; issue those
+  // tiles as 2R half-width units instead (kernel: decode()).  Only for the 256-wide single-CTA configuration.
+  int tail_from = tiles;
+  if (tail_halving && CL == 1 && BN == 256 && splits == 1 && tiles > slots) {
+    const int rem = tiles % slots;
+    if (rem > 0 && 2 * rem <= slots) tail_from = tiles - rem;
+  }
   if (CL == 1) {
-    ek_launch(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, M, N, K, ep, vec_ok, splits);
+    ek_launch(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, M, N, K, ep, vec_ok, splits, tail_from);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -623,7 +656,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, vec_ok, splits);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, vec_ok, splits, tail_from);
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
   }
   EK_CHECK_LAUNCH();
@@ -632,15 +665,15 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
 
 template <int A_MN, int B_MN>
 int launch_bn(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep,
-              int vec_ok, int splits, cudaStream_t stream) {
+              int vec_ok, int splits, int th, cudaStream_t stream) {
   if (cl == 2) {
-    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
-    return launch_cfg<256, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    return launch_cfg<256, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
   }
   switch (bn) {
-    case 64: return launch_cfg<64, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
-    case 128: return launch_cfg<128, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
-    default: return launch_cfg<256, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, stream);
+    case 64: return launch_cfg<64, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    case 128: return launch_cfg<128, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    default: return launch_cfg<256, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
   }
 }
 
@@ -680,10 +713,12 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
     for (int i = 0; i < 3; ++i) {
       const int c = cand[i];
       const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, c);
-      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      double waves = (double)((tiles + num_sms() - 1) / num_sms());
+      const long long rem = tiles % num_sms();
+      if (c == 256 && tiles > num_sms() && rem > 0 && 2 * rem <= num_sms()) waves -= 0.44;   // tail halving (launch_cfg)
       // useful fraction of issued MMA work: (real N columns / padded) * (tiles / slots); wide tiles are
       // ~10% more efficient per flop (fewer A re-reads, shorter epilogue share)
-      const double useful = (double)N / ((double)ek_div_up(N, c) * c) * (double)tiles / (double)(waves * num_sms());
+      const double useful = (double)N / ((double)ek_div_up(N, c) * c) * (double)tiles / (waves * num_sms());
       const double score = useful * (c == 256 ? 1.0 : (c == 128 ? 0.72 : 0.5));   // measured: scripts/gemm_bench.py
       if (score > best) { best = score; bn = c; }
     }
@@ -695,7 +730,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);                 // [M rows, K cols], box {64, 128}
   else rc = make_tmap(&ta, A, K, M, lda, BK);                         // [K rows, M cols], box {64, 64}
   if (rc) return rc;
-  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, cl == 2 ? bn / 2 : bn);   // [N rows, K cols], box {64, bn or bn/2}
+  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, (cl == 2 || bn == 256) ? bn / 2 : bn);   // [N rows, K cols], box {64, bn or bn/2}
   else rc = make_tmap(&tb, B, K, N, ldb, BK);                         // [K rows, N cols], box {64, 64}
   if (rc) return rc;
   // bit 0: 16-byte vector stores possible; bits 1..3: vector loads of bias / addend / row-broadcast operands
@@ -716,6 +751,11 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       if (splits < 1) splits = 1;
     }
   }
+  static int th = -1;
+  if (th < 0) {
+    const char* e = getenv("EKAID_B200_TAIL_HALVING");
+    th = (e && e[0] == '0') ? 0 : 1;
+  }
   EkEpilogue epk = ep;
   if (splits > 1) {
     EK_REQUIRE(plain_out, EK_ERR_UNSUPPORTED, "gemm_tc: split-K needs a plain fp32 (or C += AB) epilogue");
@@ -729,8 +769,8 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       epk.addend = nullptr;                    // partial sums are atomically added onto C (zeroed or pre-existing)
     }
   }
-  if (!transA && !transB) return launch_bn<0, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
-  if (!transA && transB) return launch_bn<0, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
-  if (transA && !transB) return launch_bn<1, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
-  return launch_bn<1, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, stream);
+  if (!transA && !transB) return launch_bn<0, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
+  if (!transA && transB) return launch_bn<0, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
+  if (transA && !transB) return launch_bn<1, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
+  return launch_bn<1, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
 }
