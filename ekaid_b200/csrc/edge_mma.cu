@@ -139,35 +139,54 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
         }
       }
     }
-    // epilogue: + b_out, doubled ReLU, residual
+    // epilogue: + b_out, doubled ReLU, residual.  Row bases are computed once per thread row, and all Xin / bias loads
+    // of an item are issued before the first use (they were the kernel's main stall).
 #pragma unroll
     for (int it = 0; it < IPW; ++it) {
       const int item = warp + it * 8;
       const int mt = item >> 1, nh = item & 1;
+      const int colb = c0 + nh * 64 + 2 * (lane & 3);          // column of nt = 0
+      float2 bo[8], xi[2][8];
+      size_t rbase[2];
+      bool rok[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int i = r0 + mt * 16 + (lane >> 2) + hh * 8;
+        rok[hh] = i < N;
+        rbase[hh] = ((size_t)g * N + (rok[hh] ? i : 0)) * D + colb;
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const int col = c0 + nh * 64 + nt * 8 + 2 * (lane & 3);
-        if (col >= D) continue;
-        const float2 bo = *(const float2*)(b_out + col);
+        const bool cok = colb + nt * 8 < D;
+        bo[nt] = cok ? *(const float2*)(b_out + colb + nt * 8) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          xi[hh][nt] = (cok && rok[hh]) ? *(const float2*)(Xin + rbase[hh] + nt * 8) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        if (colb + nt * 8 >= D) continue;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int i = r0 + mt * 16 + (lane >> 2) + hh * 8;
-          if (i >= N) continue;
-          const size_t row = (size_t)g * N + i;
-          const float o0 = acc[it][nt][2 * hh] + bo.x, o1 = acc[it][nt][2 * hh + 1] + bo.y;
-          const float2 xi = *(const float2*)(Xin + row * D + col);
+          if (!rok[hh]) continue;
+          const size_t idx = rbase[hh] + nt * 8;
+          const float o0 = acc[it][nt][2 * hh] + bo[nt].x, o1 = acc[it][nt][2 * hh + 1] + bo[nt].y;
           // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
           float dm[2];
-          ek_drop_multv<2>(dr, sd, row * D + col, dm);          // col is even: both lanes come from one draw
+          ek_drop_multv<2>(dr, sd, idx, dm);                   // even column: both lanes come from one draw
           const float p0 = (o0 + o0) * dm[0];
           const float p1 = (o1 + o1) * dm[1];
-          const float x0 = xi.x + fmaxf(p0, 0.f), x1 = xi.y + fmaxf(p1, 0.f);
-          *(float2*)(Xout + row * D + col) = make_float2(x0, x1);
-          if (XoutT) *(__nv_bfloat162*)(XoutT + row * ldt + col) = __floats2bfloat162_rn(x0, x1);
+          const float x0 = xi[hh][nt].x + fmaxf(p0, 0.f), x1 = xi[hh][nt].y + fmaxf(p1, 0.f);
+          *(float2*)(Xout + idx) = make_float2(x0, x1);
+          if (XoutT) {
+            const size_t row = idx / D;                         // only when the operand copy has its own pitch
+            const size_t tix = (ldt == D) ? idx : row * ldt + (idx - row * D);
+            *(__nv_bfloat162*)(XoutT + tix) = __floats2bfloat162_rn(x0, x1);
+          }
           uchar2 mk;
           mk.x = p0 > 0.f ? 1 : 0;
           mk.y = p1 > 0.f ? 1 : 0;
-          *(uchar2*)(mask + row * D + col) = mk;
+          *(uchar2*)(mask + idx) = mk;
         }
       }
     }
@@ -514,9 +533,34 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
     if (ok) cp_async16(dst, QKZ + ((size_t)g * N + row) * ld + (isq ? 0 : D) + h * dh + ch * 8);
     else *(uint4*)dst = make_uint4(0, 0, 0, 0);
   }
+  // additive terms of this thread's score elements, fetched while the Q / K tiles are still in flight:
+  // score = cond > 0 ? scale * qk + pre + post : -9e15 + post   (pre = geometry bias, post = label bias; masked: pre = -inf)
+  const int mt = warp;
+  const size_t total = (size_t)N * Kn;
+  float pre[NT][4], post[NT][4];
+  if (mt * 16 < N) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = mt * 16 + (lane >> 2) + hh * 8;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = nt * 8 + 2 * (lane & 3) + c;
+          float a = 0.f, b = 0.f;
+          if (i < N && j < Kn) {
+            const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
+            if (gbias) a = gbias[ge * H + h];
+            if (cond && !(cond[ge] > 0.f)) a = -INFINITY;
+            if (lbias) b = lbias[ge];
+          }
+          pre[nt][2 * hh + c] = a;
+          post[nt][2 * hh + c] = b;
+        }
+    }
+  }
   cp_async_wait_all();
   __syncthreads();
-  const int mt = warp;
   if (mt * 16 >= N) return;
   float acc[NT][4];
 #pragma unroll
@@ -536,7 +580,6 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
     }
   }
   const float scale = 1.0f / sqrtf((float)dh);
-  const size_t total = (size_t)N * Kn;
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int i = mt * 16 + (lane >> 2) + hh * 8;
@@ -549,11 +592,9 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
         const int j = nt * 8 + 2 * (lane & 3) + c;
         float sv = -INFINITY;
         if (rok && j < Kn) {
-          sv = scale * acc[nt][2 * hh + c];
-          const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
-          if (gbias) sv += gbias[ge * H + h];
-          if (cond) sv = (cond[ge] > 0.f) ? sv : NEG_MASK_MMA;
-          if (lbias) sv += lbias[ge];
+          const float a = pre[nt][2 * hh + c];
+          sv = (a == -INFINITY) ? NEG_MASK_MMA : scale * acc[nt][2 * hh + c] + a;
+          sv += post[nt][2 * hh + c];
         }
         acc[nt][2 * hh + c] = sv;
         mx = fmaxf(mx, sv);
@@ -625,41 +666,52 @@ softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dP
     else *(uint4*)dst = make_uint4(0, 0, 0, 0);
   }
   const size_t total = (size_t)N * Kn;
-  for (int i = warp; i < MR; i += 8) {
-    if (i < N) {
-      const float* Pr = P + (((size_t)g * N + i) * H + h) * Kn;
-      float dot = 0.f;
-      float dpv[(MR + 31) / 32];
+  {
+    // ds = P * (dP - <P, dP>) per query row; a warp owns rows warp, warp+8, ...  All global operands of the warp's rows
+    // are fetched before the first reduction (the per-row load -> shuffle chains were the kernel's main stall).
+    constexpr int RPW = MR / 8;                // rows per warp
+    constexpr int NR = (MR + 31) / 32;         // key columns per lane
+    float pv[RPW][NR], dpv[RPW][NR], cv[RPW][NR];
 #pragma unroll
-      for (int r = 0; r < (MR + 31) / 32; ++r) {
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int i = warp + 8 * rr;
+      const float* Pr = P + (((size_t)g * N + (i < N ? i : 0)) * H + h) * Kn;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
         const int j = lane + 32 * r;
-        float dp = 0.f;
-        if (j < Kn) {
+        float pj = 0.f, dp = 0.f, cj = 1.f;
+        if (i < N && j < Kn) {
+          pj = Pr[j];
           for (int sidx = 0; sidx < nslices; ++sidx) dp += dPpart[(((size_t)sidx * G + g) * N + i) * HK + h * Kn + j];
-          dot = fmaf(Pr[j], dp, dot);
+          if (cond) cj = cond[(size_t)g * total + (size_t)i * Kn + j];
         }
-        dpv[r] = dp;
+        pv[rr][r] = pj; dpv[rr][r] = dp; cv[rr][r] = cj;
       }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int i = warp + 8 * rr;
+      float dot = 0.f;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) dot = fmaf(pv[rr][r], dpv[rr][r], dot);
       dot = warp_sum(dot);
 #pragma unroll
-      for (int r = 0; r < (MR + 31) / 32; ++r) {
+      for (int r = 0; r < NR; ++r) {
         const int j = lane + 32 * r;
         if (j < MR) {
           float ds = 0.f;
-          if (j < Kn) {
-            ds = Pr[j] * (dpv[r] - dot);
+          if (i < N && j < Kn) {
+            ds = pv[rr][r] * (dpv[rr][r] - dot);
             const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
             if (dgbias) dgbias[ge * H + h] = ds;
             if (dlbias_part) dlbias_part[(size_t)h * G * total + ge] = ds;
-            if (cond && !(cond[ge] > 0.f)) ds = 0.f;
+            if (cond && !(cv[rr][r] > 0.f)) ds = 0.f;
           }
           const bf16 hi = __float2bfloat16_rn(ds);
           Shi[i * SS + j] = hi;
           Slo[i * SS + j] = __float2bfloat16_rn(ds - __bfloat162float(hi));
         }
       }
-    } else {
-      for (int j = lane; j < MR; j += 32) { Shi[i * SS + j] = __float2bfloat16_rn(0.f); Slo[i * SS + j] = __float2bfloat16_rn(0.f); }
     }
   }
   cp_async_wait_all();
