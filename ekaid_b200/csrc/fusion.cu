@@ -103,13 +103,29 @@ colsum_kernel(const T* __restrict__ src, long long ld, long long M, int N, const
   }
   __syncthreads();
   if (is_last) {
+    // final pass, all 8 warps: warp ty adds partials ty, ty+8, ... for its lane's VEC columns (independent loads, one
+    // L2 round trip), then the 8 sub-sums are added in fixed order through shared memory -> still deterministic
     __threadfence();
+    float t[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) t[v] = 0.f;
+#pragma unroll 8
+    for (int p = ty; p < nparts; p += 8) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (n0 + v < N) t[v] += __ldcg(part + (size_t)p * N + n0 + v);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) red[ty][lane * VEC + v] = t[v];
+    __syncthreads();
     for (int c = threadIdx.x; c < CB; c += 256) {
       const int n = blockIdx.x * CB + c;
       if (n < N) {
-        float t = 0.f;
-        for (int p = 0; p < nparts; ++p) t += __ldcg(part + (size_t)p * N + n);
-        out[n] = t;
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += red[k][c];
+        out[n] = a;
       }
     }
   }

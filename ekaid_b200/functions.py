@@ -434,6 +434,20 @@ def _barrier_ws(dev):
     return _barrier_bufs[key]
 
 
+_branch = {}
+
+
+def _branch_streams(dev):
+    """Two extra streams per device for independent gradient groups of the question path."""
+    if os.environ.get("EKAID_B200_QBRANCH", "1") == "0":
+        cur = torch.cuda.current_stream(dev)
+        return cur, cur
+    key = str(dev)
+    if key not in _branch:
+        _branch[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _branch[key]
+
+
 def _gru_seq_ok(pc, dev, B, H):
     """The one-launch recurrence covers the bf16 path when all H/16 CTAs are co-resident (see gru_seq.cu).  It works
     in passes of 64 batch rows, so for large batches the per-step tcgen05 GEMMs win."""
@@ -521,10 +535,22 @@ class QuestionFn(torch.autograd.Function):
         dpre = torch.empty(L * B, H, dtype=pc.T, device=dev)
         call("qatt_tanh_bwd", pc.f, da.data_ptr(), w2c.data_ptr(), a1.data_ptr(), L * B, H, dpre.data_ptr())
         kk = ctx.keys
-        dw2 = colsum(a1, L * B, H, rowscale=da).view(1, H)
-        db2 = colsum(da.view(-1, 1), L * B, 1, out=_dst(kk["b2"], (1,), dev))
-        dW1 = gemm_f32out(dpre, Hd, H, H, L * B, transA=1, transB=1)
-        db1 = colsum(dpre, L * B, H, out=_dst(kk["b1"], (H,), dev))
+        # Everything below that does not feed BPTT (weight / bias gradients of the attention MLP) goes to a branch stream
+        # and runs next to the recurrence; the serial chain of this stream is only dHs -> BPTT.  Temporaries are
+        # allocated here, on this stream, so the caching allocator's stream bookkeeping stays simple.
+        cur = torch.cuda.current_stream(dev)
+        br1, br2 = _branch_streams(dev)
+        dw2 = torch.empty(H, dtype=torch.float32, device=dev)
+        dW1 = torch.empty(H, H, dtype=torch.float32, device=dev)
+        db2 = _dst(kk["b2"], (1,), dev)
+        db1 = _dst(kk["b1"], (H,), dev)
+        br1.wait_stream(cur)
+        with torch.cuda.stream(br1):
+            colsum(a1, L * B, H, rowscale=da, out=dw2)
+            colsum(da.view(-1, 1), L * B, 1, out=db2)
+            gemm_f32out(dpre, Hd, H, H, L * B, transA=1, transB=1, out=dW1)
+            colsum(dpre, L * B, H, out=db1)
+        dw2 = dw2.view(1, H)
         if don:
             tmp = gemm_f32out(dpre, W1T, L * B, H, H, transB=1)
             drop_combine([tmp], [drop.a(10, drop.p_fc)], L * B, H, outf=dHs, accumulate=1)
@@ -553,13 +579,25 @@ class QuestionFn(torch.autograd.Function):
                      dghT[sl].data_ptr() if pc.bf16 else None, carry.data_ptr())
                 if t > 0:
                     gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=carry, C=carry)   # carry = dh*z + dgh W_hh
-        dWih = gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=_dst(kk["Wih"], (3 * H, 2 * ed), dev))
-        dbih = colsum(dgi, L * B, 3 * H, out=_dst(kk["bih"], (3 * H,), dev))
-        dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1, out=_dst(kk["Whh"], (3 * H, H), dev))
-        dbhh = colsum(dgh, L * B, 3 * H, out=_dst(kk["bhh"], (3 * H,), dev))
-        dE = gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1)           # only the trainable table's columns
+        # three independent groups of parameter gradients: this stream and the two branches take one each
+        dWih = _dst(kk["Wih"], (3 * H, 2 * ed), dev)
+        dbih = _dst(kk["bih"], (3 * H,), dev)
+        dWhh = _dst(kk["Whh"], (3 * H, H), dev)
+        dbhh = _dst(kk["bhh"], (3 * H,), dev)
         demb = _dst(kk["emb"], (V, ed), dev)
-        call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr())
+        dE = torch.empty(L * B, ed, dtype=torch.float32, device=dev)
+        br1.wait_stream(cur)
+        br2.wait_stream(cur)
+        with torch.cuda.stream(br1):
+            gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1, out=dWhh)
+            colsum(dgh, L * B, 3 * H, out=dbhh)
+        with torch.cuda.stream(br2):
+            gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1, out=dE)       # only the trainable table's columns
+            call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr())
+        gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=dWih)
+        colsum(dgi, L * B, 3 * H, out=dbih)
+        cur.wait_stream(br1)
+        cur.wait_stream(br2)
         return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
 
 
