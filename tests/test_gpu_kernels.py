@@ -135,3 +135,65 @@ def test_adam_matches_torch():
         call("adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-3, 0.9, 0.999, 1e-8,
              0.0, pw.data_ptr(), 0 if step else 7)      # step 0 with a capped grid (background mode)
     assert float((p - ref.detach()).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("transA,transB", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(6656, 1024, 192), (6656, 1000, 200), (4992, 1024, 128), (6656, 768, 64)])
+def test_gemm_tail_halving(transA, transB, M, N, K):
+    """Shapes whose last wave of 256-wide tiles is at most half full: those tiles run as half-width units
+    (gemm_tc.cu decode()).  Bias + bf16/fp32 outputs so the whole epilogue is exercised on both unit kinds."""
+    from ekaid_b200.functions import gemm
+    dev = _dev()
+    A = _mk((K, M) if transA else (M, K), dev, 31, torch.bfloat16)
+    B = _mk((K, N) if transB else (N, K), dev, 32, torch.bfloat16)
+    bias = _mk((N,), dev, 33, torch.float32)
+    C = torch.full((M, N), float("nan"), device=dev)
+    Cb = torch.full((M, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    gemm(A, B, M, N, K, transA, transB, bias=bias, C=C, Cb=Cb, force_bn=256)
+    Af = A.float().t() if transA else A.float()
+    Bf = B.float() if transB else B.float().t()
+    ref = Af.double() @ Bf.double() + bias.double()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((Cb.double() - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+def test_small_linear_weighted_sums_wn_many():
+    """The small fused entry points against their torch expressions."""
+    import ctypes
+    from ekaid_b200.functions import SmallLinearFn, WeightedSumsFn, WNormFn, WNormManyFn
+    dev = _dev()
+    x = _mk((64, 1024), dev, 41, torch.float32).requires_grad_(True)
+    W = _mk((6, 1024), dev, 42, torch.float32).requires_grad_(True)
+    b = _mk((6,), dev, 43, torch.float32).requires_grad_(True)
+    y = SmallLinearFn.apply(x, W, b)
+    ref = torch.nn.functional.linear(x.detach(), W.detach(), b.detach())
+    assert float((y - ref).abs().max()) < 1e-4
+    y.sum().backward()
+    assert float((W.grad - x.detach().sum(0).expand(6, -1)).abs().max()) < 1e-3 and float((b.grad - 64).abs().max()) < 1e-4
+
+    ts = [_mk((64, 1024), dev, 50 + k, torch.float32).requires_grad_(True) for k in range(3)]
+    ts += [_mk((3328,), dev, 60 + k, torch.float32).requires_grad_(True) for k in range(2)]
+    ws = [_mk((64, 1024), dev, 70 + k, torch.float32) for k in range(3)] + [None, None]
+    coefs = (1.0, 1.0, 0.5, 2.5e-3, -1.25e-3)
+    loss = WeightedSumsFn.apply(coefs, ws, *ts)
+    ref = sum(c * ((t.detach().double() * w.double()).sum() if w is not None else t.detach().double().sum()) for c, w, t in zip(coefs, ws, ts))
+    assert abs(float(loss) - float(ref)) < 1e-3 * (1 + abs(float(ref)))
+    loss.backward()
+    assert float((ts[2].grad - 0.5 * ws[2]).abs().max()) < 1e-6 and float((ts[4].grad + 1.25e-3).abs().max()) < 1e-8
+    l2 = WeightedSumsFn.apply(coefs, ws, *ts)          # deterministic: bitwise equal on a second call
+    assert float(l2) == float(loss)
+
+    vs = [_mk(s, dev, 80 + i, torch.float32).requires_grad_(True) for i, s in enumerate([(1024, 2048), (1024, 1024), (4, 64), (1, 11)])]
+    gs = [torch.tensor(1.5 + i, device=dev).requires_grad_(True) for i in range(4)]
+    outs = WNormManyFn.apply(*[t for v, g in zip(vs, gs) for t in (v, g)])
+    cot = [_mk(v.shape, dev, 90 + i, torch.float32) for i, v in enumerate(vs)]
+    sum((o * c).sum() for o, c in zip(outs, cot)).backward()
+    for v, g, o, c in zip(vs, gs, outs, cot):
+        v2, g2 = v.detach().clone().requires_grad_(True), g.detach().clone().requires_grad_(True)
+        o2 = WNormFn.apply(v2, g2)
+        (o2 * c).sum().backward()
+        refw = v.detach() * (g.detach() / v.detach().norm())
+        assert float((o - refw).abs().max()) < 1e-5 * float(refw.abs().max()) + 1e-7
+        assert float((o - o2).abs().max()) == 0.0
+        assert float((v.grad - v2.grad).abs().max()) <= 1e-6 * float(v2.grad.abs().max()) + 1e-9
+        assert abs(float(g.grad) - float(g2.grad)) <= 1e-5 * abs(float(g2.grad)) + 1e-7
