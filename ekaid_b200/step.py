@@ -59,6 +59,18 @@ class FlatAdam:
         for p in self.params:
             p.grad = None
 
+    def sync_slots(self, first: int = 0, last: Optional[int] = None, dry_run: bool = False) -> int:
+        """Gradients that autograd did NOT adopt as their slot view (it clones a gradient whenever somebody else still
+        references it -- seen e.g. under compute-sanitizer) are copied into the flat buffer so that the update and the
+        all-reduce see them.  Returns how many needed that (dry_run: only counts)."""
+        n = 0
+        for p, slot in list(zip(self.params, self.slots))[first:last]:
+            if p.grad is not None and p.grad.data_ptr() != slot.data_ptr():
+                n += 1
+                if not dry_run:
+                    slot.copy_(p.grad)
+        return n
+
     def check_slots(self):
         """After a backward: every gradient autograd holds must BE its slot (otherwise Adam would miss it)."""
         for p, slot in zip(self.params, self.slots):
@@ -150,6 +162,7 @@ class GraphFusionStep:
         self.opt = FlatAdam(head + tail, lr=lr)
         self._split = self.opt.offsets[len(head)]
         self._armed = False
+        self._n_head = len(head)
         self._fired = 0
         self._expected = None      # how many image-path parameters receive a gradient (learned on the first step:
         self._early = False        # e.g. fc1 never does, its output is not part of the reference's loss -- Q11)
@@ -171,6 +184,8 @@ class GraphFusionStep:
         optimizer stream and run next to it."""
         if not self._armed or self._expected is None or self._fired != self._expected or self._early:
             return
+        if self.opt.sync_slots(0, self._n_head, dry_run=True):
+            return                                          # some gradient is not in its slot: take the late path
         dev = self.opt.flat.device
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(dev)
@@ -237,9 +252,8 @@ class GraphFusionStep:
                 raise RuntimeError("the set of parameters receiving gradients changed between steps (%d -> %d): the "
                                    "early optimizer update of the image-path segment is no longer valid"
                                    % (self._expected, self._fired))
-        if total.is_cuda and self.opt._checked < 2 and not torch.cuda.is_current_stream_capturing():
-            self.opt.check_slots()
-            self.opt._checked += 1
+        # gradients autograd cloned instead of adopting go into their slots now (normally none)
+        self.opt.sync_slots(self._n_head if self._early else 0)
         n = self.opt.flat.numel()
         if self._early:
             # the image-path segment is already being updated on the optimizer stream; finish with the question path

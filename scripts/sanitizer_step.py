@@ -1,6 +1,6 @@
 """Two eager training steps at a small batch, for `compute-sanitizer --tool memcheck python scripts/sanitizer_step.py 4`.
 The slot check of FlatAdam is skipped and reported instead: under the sanitizer autograd does not adopt the gradient
-views (it clones them), which is harmless for a memory check but would trip `check_slots`."""
+views (it clones them); GraphFusionStep.train_step copies such gradients into their slots, this script reports them."""
 import contextlib, io, sys, torch
 sys.path.insert(0, ".")
 from ekaid_b200 import lib
