@@ -151,53 +151,114 @@ class GraphFusionStep:
         self.graph = graph
         self.decoder_loss = decoder_loss
         self.pg = process_group
-        # Flat parameter order: image path first, question path (embedding, GRU, question attention) last.  The
-        # question-path gradients are the last to be finished in backward (BPTT starts only when every relation encoder
-        # has contributed to d(question vector)), so the optimizer update -- and, data-parallel, the all-reduce -- of
-        # the image-path segment is issued from an autograd hook as soon as that segment is complete and overlaps BPTT.
+        # Flat parameter order = the order in which backward FINISHES the gradients, in contiguous segments:
+        #   0 fusion stage | 1 implicit encoder | 2 spatial encoder | 3 semantic encoder   (parameters whose gradient
+        #     is written by the stage's own backward; done as soon as that stage's backward has run)
+        #   4 everything else on the image path (weight-normalised v/g: their batched backward runs last; img)
+        #   5 question path (embedding, GRU, question attention): BPTT is the serial tail of the step
+        # As soon as a segment is complete (autograd hooks count its gradients) its all-reduce (N > 1) and Adam update
+        # go out on the optimizer stream and overlap the rest of backward; segment 4 goes out when BPTT is launched
+        # and runs next to the recurrence; only segment 5 is left for the end.
         named = change_detector.live_named_parameters()
-        qpath = ("w_emb.", "q_emb.", "q_att.")
-        head = [p for n, p in named if not n.startswith(qpath)]
-        tail = [p for n, p in named if n.startswith(qpath)]
-        self.opt = FlatAdam(head + tail, lr=lr)
-        self._split = self.opt.offsets[len(head)]
+
+        def segment_of(name: str) -> int:
+            if name.startswith(("w_emb.", "q_emb.", "q_att.")):
+                return 5
+            if "weight_v" in name or "weight_g" in name:
+                return 4
+            if name.startswith(("context1.", "context2.", "gate1.", "gate2.", "embed.", "att.", "fc1.")):
+                return 0
+            if name.startswith("imp_relation."):
+                return 1
+            if name.startswith("spatial_relation."):
+                return 2
+            if name.startswith("semantic_relation."):
+                return 3
+            return 4
+
+        seg = [segment_of(n) for n, _ in named]
+        order = sorted(range(len(named)), key=lambda i: (seg[i], i))
+        params = [named[i][1] for i in order]
+        self.opt = FlatAdam(params, lr=lr)
+        self._seg_of_param = [seg[i] for i in order]
+        self._nseg = 6
+        # [first, last) parameter index and [lo, hi) flat offsets of every segment
+        self._seg_pidx, self._seg_range = [], []
+        for k in range(self._nseg):
+            idx = [j for j, sk in enumerate(self._seg_of_param) if sk == k]
+            first, last = (idx[0], idx[-1] + 1) if idx else (0, 0)
+            self._seg_pidx.append((first, last))
+            self._seg_range.append((self.opt.offsets[first], self.opt.offsets[last]) if idx else (0, 0))
         self._armed = False
-        self._n_head = len(head)
-        self._fired = 0
-        self._expected = None      # how many image-path parameters receive a gradient (learned on the first step:
-        self._early = False        # e.g. fc1 never does, its output is not part of the reference's loss -- Q11)
+        self._fired = [0] * self._nseg
+        self._expected = None      # per segment: how many parameters receive a gradient (learned on the first step:
+        self._done = [False] * self._nseg      # e.g. fc1 never does, its output is not in the reference's loss -- Q11)
+        self._advanced = False
         self._opt_stream = None
-        self._hooked = bool(head and tail and head[0].is_cuda and os.environ.get("EKAID_B200_EARLY_ADAM", "1") != "0")
+        self._hooked = bool(params and params[0].is_cuda and os.environ.get("EKAID_B200_EARLY_ADAM", "1") != "0")
+        # EKAID_B200_EARLY_SEGMENTS=1: segments 0-3 go out right when they complete instead of at the BPTT launch.
+        # Measured (B200, 1 and 2 GPUs over NVLink): no gain -- 4.19 vs 4.15 ms and 4.52 vs 4.48 ms; the all-reduce is
+        # cheap and the extra Adam launches compete with the GEMMs -- so it is off by default.
+        self._early_segments = os.environ.get("EKAID_B200_EARLY_SEGMENTS", "0") == "1"
         if self._hooked:
-            for p in head:
-                p.register_post_accumulate_grad_hook(self._head_grad_ready)
+            for p, k in zip(params, self._seg_of_param):
+                if k < 5:
+                    p.register_post_accumulate_grad_hook(lambda _p, k=k: self._grad_ready(k))
         self._cot = None
         self._graph = None
 
-    def _head_grad_ready(self, _param):
-        """autograd hook: counts the image-path gradients of the running train_step."""
-        self._fired += 1
-
-    def _bptt_starts(self):
-        """functions.BPTT_HOOK: the question path is about to run its recurrence backwards (one long, register-light
-        kernel).  If every image-path gradient has been enqueued by now, their all-reduce and Adam update go out on the
-        optimizer stream and run next to it."""
-        if not self._armed or self._expected is None or self._fired != self._expected or self._early:
-            return
-        if self.opt.sync_slots(0, self._n_head, dry_run=True):
-            return                                          # some gradient is not in its slot: take the late path
+    def _launch_run(self, k0: int, k1: int, wait_current: bool) -> bool:
+        """All-reduce + Adam of the contiguous segments k0 .. k1-1 on the optimizer stream (after everything enqueued so
+        far on the main stream and, if asked, on the calling stream)."""
+        first, last = self._seg_pidx[k0][0], self._seg_pidx[k1 - 1][1]
+        lo, hi = self._seg_range[k0][0], self._seg_range[k1 - 1][1]
+        if hi <= lo:
+            return False
+        if self.opt.sync_slots(first, last, dry_run=True):
+            return False                                    # some gradient is not in its slot: take the late path
         dev = self.opt.flat.device
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(dev)
         st = self._opt_stream
-        st.wait_stream(self._main)                          # every image-path gradient
-        st.wait_stream(torch.cuda.current_stream(dev))      # ... and not before the GPU reaches the recurrence: the
-        with torch.cuda.stream(st):                         # GEMMs ahead of it need whole SMs, the recurrence does not
+        st.wait_stream(self._main)
+        if wait_current:
+            st.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(st):
             if self.pg is not None:
-                allreduce_mean_(self.opt.grad[:self._split], self.pg)
-            self.opt.advance()
-            self.opt.update_range(0, self._split, max_ctas=int(os.environ.get("EKAID_B200_BG_CTAS", "148")))
-        self._early = True
+                allreduce_mean_(self.opt.grad[lo:hi], self.pg)
+            if not self._advanced:
+                self.opt.advance()
+                self._advanced = True
+            self.opt.update_range(lo, hi, max_ctas=int(os.environ.get("EKAID_B200_BG_CTAS", "148")))
+        for k in range(k0, k1):
+            self._done[k] = True
+        return True
+
+    def _nonempty(self, k: int) -> bool:
+        return self._seg_range[k][1] > self._seg_range[k][0]
+
+    def _grad_ready(self, k: int):
+        """autograd hook: one more gradient of segment k has been accumulated."""
+        self._fired[k] += 1
+        if (self._armed and k < 4 and self._expected is not None and self._fired[k] == self._expected[k]
+                and not self._done[k] and self._nonempty(k) and self._early_segments):
+            self._launch_run(k, k + 1, wait_current=True)
+
+    def _bptt_starts(self):
+        """functions.BPTT_HOOK: the question path is about to run its recurrence backwards (one long kernel on 64 SMs).
+        By now every image-path gradient has been enqueued: what is still pending of segments 0-4 goes out (contiguous
+        segments together) and runs next to the recurrence -- and not before the GPU reaches it: the GEMMs ahead of it
+        need whole SMs."""
+        if not self._armed or self._expected is None:
+            return
+        ready = [k for k in range(5) if not self._done[k] and self._nonempty(k) and self._fired[k] == self._expected[k]]
+        i = 0
+        while i < len(ready):
+            j = i
+            while j + 1 < len(ready) and ready[j + 1] == ready[j] + 1:
+                j += 1
+            self._launch_run(ready[i], ready[j] + 1, wait_current=True)
+            i = j + 1
 
     def _cotangents(self, bef):
         # stand in for d(decoder NLL)/d(bef, aft, diff): fixed unit-scale cotangents
@@ -233,8 +294,9 @@ class GraphFusionStep:
         if self.cd.training:
             rng_advance(self.opt.flat.device)      # fresh dropout masks (a kernel: replays draw new masks too)
         total = self.loss(inputs, labels, masks)
-        self._early = False
-        self._fired = 0
+        self._fired = [0] * self._nseg
+        self._done = [False] * self._nseg
+        self._advanced = False
         self._main = torch.cuda.current_stream() if total.is_cuda else None
         self._armed = self._hooked
         if self._hooked:
@@ -247,24 +309,33 @@ class GraphFusionStep:
                 functions.BPTT_HOOK = None
         if self._hooked:
             if self._expected is None:
-                self._expected = self._fired
+                self._expected = list(self._fired)
             elif self._fired != self._expected:
-                raise RuntimeError("the set of parameters receiving gradients changed between steps (%d -> %d): the "
-                                   "early optimizer update of the image-path segment is no longer valid"
-                                   % (self._expected, self._fired))
-        # gradients autograd cloned instead of adopting go into their slots now (normally none)
-        self.opt.sync_slots(self._n_head if self._early else 0)
-        n = self.opt.flat.numel()
-        if self._early:
-            # the image-path segment is already being updated on the optimizer stream; finish with the question path
-            if self.pg is not None:
-                allreduce_mean_(self.opt.grad[self._split:], self.pg)
-            self.opt.update_range(self._split, n)
+                raise RuntimeError("the set of parameters receiving gradients changed between steps (%s -> %s): the "
+                                   "early optimizer updates are no longer valid" % (self._expected, self._fired))
+        # whatever was not updated early: (clone-instead-of-adopt gradients go into their slots first; normally none)
+        pending = [k for k in range(self._nseg) if not self._done[k] and self._seg_range[k][1] > self._seg_range[k][0]]
+        if pending:
+            for k in pending:
+                self.opt.sync_slots(*self._seg_pidx[k])
+            if not self._advanced:
+                self.opt.advance()
+                self._advanced = True
+            # contiguous runs of pending segments share one all-reduce / one launch
+            runs, cur = [], None
+            for k in pending:
+                lo, hi = self._seg_range[k]
+                if cur is not None and cur[1] == lo:
+                    cur[1] = hi
+                else:
+                    cur = [lo, hi]
+                    runs.append(cur)
+            for lo, hi in runs:
+                if self.pg is not None:
+                    allreduce_mean_(self.opt.grad[lo:hi], self.pg)
+                self.opt.update_range(lo, hi)
+        if self._opt_stream is not None and any(self._done):
             torch.cuda.current_stream().wait_stream(self._opt_stream)
-        else:
-            if self.pg is not None:
-                allreduce_mean_(self.opt.grad, self.pg)
-            self.opt.step()
         return total.detach()
 
     # -- CUDA-graph replay of the whole step ------------------------------------------------------------------
