@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_set>
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "../../include/ekaid_b200.h"
@@ -13,6 +15,20 @@ void ek_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+static int g_carveout = -1;
+void ek_prepare_kernel(const void* fn) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  if (g_carveout < 0) {
+    const char* e = getenv("EKAID_B200_MAX_CARVEOUT");      // measured: 4.22 vs 4.15 ms/step with it on -> opt-in
+    g_carveout = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!g_carveout) return;
+  std::lock_guard<std::mutex> lk(mu);
+  if (seen.insert(fn).second)
+    cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 static int g_pdl = -1;
