@@ -85,6 +85,37 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
                ::"r"(smem_u32(bar)), "h"(mask)
                : "memory");
 }
+// ---- cta_group::2 (CTA pair): one MMA of M = 256 spans both CTAs; each CTA stages its 128 rows of A and HALF of B
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// TMA load whose completion is signalled on `bar_cluster_addr`, an mbarrier of either CTA of the pair
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* tmap, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -136,12 +167,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-template <int BN, int A_MN, int B_MN>
+template <int BN, int A_MN, int B_MN, int CG = 1>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;      // cta_group::2: each CTA stages half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
   static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;                     // transposition buffers of the 4 epilogue warps
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
@@ -231,12 +262,13 @@ __device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uin
 // CL = 1: independent CTAs.  CL = 2: thread-block cluster of two CTAs on neighbouring M tiles of the SAME N tile; each
 // loads its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory -> 1.5x fewer bytes pulled
 // from L2 per flop (the single-CTA 128x256 tile is L2-bandwidth bound at ~85 flop/B).
-template <int BN, int A_MN, int B_MN, int CL>
+template <int BN, int A_MN, int B_MN, int CL, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                     int K, EkEpilogue ep, int vec_ok, int splits, int tail_from) {
-  using C = Cfg<BN, A_MN, B_MN>;
+  using C = Cfg<BN, A_MN, B_MN, CG>;
   static_assert(CL == 1 || BN >= 128, "the shared B tile must split into two TMA boxes");
+  static_assert(CG == 1 || CL == 2, "cta_group::2 needs a cluster of two CTAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
@@ -279,19 +311,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CL);      // one commit-arrive per CTA whose MMAs read this slot
+      mbar_init(&empty_bar[s], CG == 2 ? 1 : CL);   // one commit-arrive per MMA issuer that reads this slot
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 8);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], CG == 2 ? 16 : 8);   // one arrive per epilogue warp (of both CTAs under cta_group::2)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -316,8 +355,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], half_w ? C::A_BYTES + C::B_BYTES / 2 : C::STAGE_BYTES);
           const int k0 = kb * BK;
+          if constexpr (CG == 2) {
+            // cta_group::2: both CTAs' boxes complete on the LEADER's barrier (it alone waits, its MMA spans both CTAs)
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            if (A_MN == 0) {
+              tma_load_2d_cg2(&tmA, lbar, sa, k0, m0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d_cg2(&tmA, lbar, sa + i * (64 * BK * 2), m0 + 64 * i, k0);
+            }
+            const int nh0 = n0 + (int)crank * (BN / 2);          // this CTA's half of the B tile
+            if (B_MN == 0) {
+              tma_load_2d_cg2(&tmB, lbar, sb, k0, nh0);          // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 128; ++i) tma_load_2d_cg2(&tmB, lbar, sb + i * (64 * BK * 2), nh0 + 64 * i, k0);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], half_w ? C::A_BYTES + C::B_BYTES / 2 : C::STAGE_BYTES);
           if (A_MN == 0) {
             tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);                 // box {64 k, 128 m}
           } else {
@@ -357,10 +416,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && (CG == 1 || crank == 0)) {
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accum, bf16 x bf16
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -388,14 +447,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                         : make_smem_desc(sa + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024)
                                         : make_smem_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, idesc_u, ((kb - kb0) | k) ? 1u : 0u);
+            if constexpr (CG == 2) tc_mma_bf16_cg2(tmem_d, adesc, bdesc, idesc_u, ((kb - kb0) | k) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, adesc, bdesc, idesc_u, ((kb - kb0) | k) ? 1u : 0u);
           }
           // frees the smem slot when these MMAs retire (in both CTAs of a pair: the peer multicasts into it too)
-          if (CL == 1) tc_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) tc_commit_cg2(&empty_bar[stage], 3);
+          else if (CL == 1) tc_commit(&empty_bar[stage]);
           else tc_commit_mc(&empty_bar[stage], 3);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[buf]);              // accumulator complete -> epilogue
+        if constexpr (CG == 2) tc_commit_cg2(&tfull_bar[buf], 3);   // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&tfull_bar[buf]);         // accumulator complete -> epilogue
       }
     }
   } else {
@@ -531,7 +593,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader issues the MMAs
+        else mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
   tc_fence_before();
@@ -539,9 +604,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CL > 1) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it / arrive on it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)C::TMEM_COLS)
-                 : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -619,12 +687,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int A_MN, int B_MN, int CL>
+template <int BN, int A_MN, int B_MN, int CL, int CG = 1>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep, int vec_ok,
                int splits, int tail_halving, cudaStream_t stream) {
-  using C = Cfg<BN, A_MN, B_MN>;
+  using C = Cfg<BN, A_MN, B_MN, CG>;
   static bool attr_set = false;
-  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN, CL>;
+  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN, CL, CG>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cannot set smem attr: %s", cudaGetErrorString(e));
@@ -666,6 +734,10 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
 template <int A_MN, int B_MN>
 int launch_bn(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep,
               int vec_ok, int splits, int th, cudaStream_t stream) {
+  if (cl == 3) {     // cta_group::2 pair
+    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    return launch_cfg<256, A_MN, B_MN, 2, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+  }
   if (cl == 2) {
     if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
     return launch_cfg<256, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
@@ -686,8 +758,9 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   // force_bn = 1000 + width selects the CTA-pair (cluster of 2, multicast B) variant of that width.  It is NOT the
   // default: measured on B200 it is no faster than independent CTAs (L2 already merges the two CTAs' requests for the
   // same B tile), and the lock-step coupling costs ~10-40 % on some shapes (profiles/r01_notes.md).
-  bool want_cluster = false;
-  if (force_bn > 1000) { want_cluster = true; force_bn -= 1000; }
+  bool want_cluster = false, want_cg2 = false;
+  if (force_bn > 2000) { want_cg2 = true; force_bn -= 2000; }          // 2000 + width: cta_group::2 pair
+  else if (force_bn > 1000) { want_cluster = true; force_bn -= 1000; }
   // Split-K candidates: plain fp32 outputs, or "C += A B" (addend aliases C, nothing else in the epilogue) where the
   // partial sums are reduced straight onto the existing values.
   const bool acc_alias = ep.addend && ep.addend == ep.C && ep.ldadd == ep.ldc;
@@ -724,13 +797,14 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
     }
   }
   // CTA pairs (cluster of 2 along M sharing the B tile): opt-in, needs two M tiles and a >= 128 wide tile
-  const int cl = (want_cluster && bn >= 128 && ek_div_up(M, BM) >= 2) ? 2 : 1;
+  int cl = (want_cluster && bn >= 128 && ek_div_up(M, BM) >= 2) ? 2 : 1;
+  if (want_cg2 && bn >= 128 && ek_div_up(M, BM) >= 2) cl = 3;
   CUtensorMap ta, tb;
   int rc;
   if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);                 // [M rows, K cols], box {64, 128}
   else rc = make_tmap(&ta, A, K, M, lda, BK);                         // [K rows, M cols], box {64, 64}
   if (rc) return rc;
-  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, (cl == 2 || bn == 256) ? bn / 2 : bn);   // [N rows, K cols], box {64, bn or bn/2}
+  if (!transB) rc = make_tmap(&tb, B, N, K, ldb, (cl >= 2 || bn == 256) ? bn / 2 : bn);   // [N rows, K cols], box {64, bn or bn/2}
   else rc = make_tmap(&tb, B, K, N, ldb, BK);                         // [K rows, N cols], box {64, 64}
   if (rc) return rc;
   // bit 0: 16-byte vector stores possible; bits 1..3: vector loads of bias / addend / row-broadcast operands

@@ -37,7 +37,7 @@ for (M, N, K, ta, tb, out) in SHAPES:
         sets.append((A, B, C))
     flops = 2.0 * M * N * K
     res = {"shape": (M, N, K, ta, tb, out)}
-    for name, bn in (("auto", 0), ("bn64", 64), ("bn128", 128), ("bn256", 256), ("cl256", 1256)):
+    for name, bn in (("auto", 0), ("bn64", 64), ("bn128", 128), ("bn256", 256), ("cl256", 1256), ("cg256", 2256), ("cg128", 2128)):
         def run(i, bn=bn):
             A, B, C = sets[i % 4]
             if out == "f32":

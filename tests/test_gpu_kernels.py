@@ -36,7 +36,7 @@ def test_gemm_layouts(dtype, transA, transB, M, N, K):
     assert err < (2e-5 if dtype == torch.float32 else 1e-5), err      # operands identical -> only fp32 accumulation order
 
 
-@pytest.mark.parametrize("bn", [64, 128, 256, 1128, 1256])     # 1000 + width: CTA-pair (cluster) multicast variant
+@pytest.mark.parametrize("bn", [64, 128, 256, 1128, 1256, 2128, 2256])     # 1000 + width: CTA-pair multicast; 2000 + width: cta_group::2
 def test_gemm_tc_tile_widths_and_splitk(bn):
     from ekaid_b200.functions import gemm
     dev = _dev()
