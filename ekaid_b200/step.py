@@ -374,7 +374,64 @@ class GraphFusionStep:
         lib.LAUNCHES += self.launches_per_replay
         return self._static_out
 
+    def pipeline(self) -> "StepPipeline":
+        """Input pipeline for the captured step (see StepPipeline)."""
+        return StepPipeline(self)
+
     @torch.no_grad()
     def infer_step(self, inputs):
         """test_mimic.py:116-117: the three vectors the decoder consumes, plus the attention maps."""
         return self.cd(*inputs, setting="mode2", graph=self.graph)
+
+
+class StepPipeline:
+    """What a data loader does around the captured step: while step i computes, the host->device copies of batch i+1
+    run on a copy stream into one of two staging sets, and the scalar result of every step comes back through a pinned
+    host buffer, read one step late.  Every batch still crosses PCIe and every result is still read on the host; they
+    just no longer serialise with the compute.
+
+        pipe = step.pipeline(); pipe.prefetch(host_batch_0)
+        for i in ...: pipe.prefetch(host_batch_{i+1}); k = pipe.run(); ...; value = pipe.result(k)
+    """
+
+    def __init__(self, step: GraphFusionStep):
+        if step._graph is None:
+            raise RuntimeError("StepPipeline needs a captured step (GraphFusionStep.capture)")
+        self.step = step
+        dev = step._static[0].device
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.stage = [[torch.empty_like(t) for t in step._static] for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]       # staging set filled
+        self.consumed = [torch.cuda.Event() for _ in range(2)]    # staging set copied into the captured buffers
+        self.host_out = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.out_done = [torch.cuda.Event() for _ in range(2)]
+        self._filled = []          # staging sets that hold a prefetched batch, oldest first
+        self._next = 0
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in step._static)
+
+    def prefetch(self, host_batch) -> None:
+        k = self._next
+        self._next ^= 1
+        self.copy_stream.wait_event(self.consumed[k])
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self.stage[k], host_batch):
+                dst.copy_(src, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self._filled.append(k)
+
+    def run(self) -> int:
+        """Run the step on the oldest prefetched batch; returns the slot to pass to result()."""
+        k = self._filled.pop(0)
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self.ready[k])
+        out = self.step.replay(self.stage[k])
+        self.consumed[k].record(cur)
+        val = out if self.step._train else out[5].sum()
+        self.host_out[k:k + 1].copy_(val.reshape(1), non_blocking=True)
+        self.out_done[k].record(cur)
+        return k
+
+    def result(self, k: int) -> float:
+        self.out_done[k].synchronize()
+        return float(self.host_out[k])

@@ -98,3 +98,52 @@ def test_graph_replay_matches_eager_step():
     assert losses["eager"][0] != losses["eager"][1]
     for k in params["eager"]:
         assert float((params["eager"][k] - params["graph"][k]).abs().max()) < 1e-6, k
+
+
+def test_step_pipeline_matches_plain_replay():
+    """StepPipeline (prefetch of the next host batch on a copy stream, results read one step late) must give the same
+    sequence of losses and the same parameters as replaying the same host batches one after the other."""
+    from ekaid_b200 import functions
+    from ekaid_b200.step import GraphFusionStep, select_fields
+    from ekaid_b200.synthetic import synthetic_batch
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, _, _ = case_inputs(meta)
+    host = [tuple(t.contiguous().pin_memory() for t in select_fields(synthetic_batch(2, 52, seed=s))) for s in (1, 2, 3, 4, 5)]
+    losses, params = {}, {}
+    try:
+        for mode in ("plain", "pipeline"):
+            functions.GRAD_SLOTS.clear()
+            m = build_model(meta, sd, "fp32", dev)            # eval mode: no dropout, so both runs are comparable
+            step = GraphFusionStep(m, m.cfg, lr=1e-3)
+            step.capture(tuple(t.to(dev) for t in host[0]), train=True, warmup=2)
+            with torch.no_grad():
+                m.load_state_dict(sd)
+            step.opt.m.zero_()
+            step.opt.v.zero_()
+            step.opt.pow_state.fill_(1.0)
+            out = []
+            if mode == "plain":
+                for b in host:
+                    out.append(float(step.replay(b)))
+            else:
+                pipe = step.pipeline()
+                pipe.prefetch(host[0])
+                pending = None
+                for i in range(len(host)):
+                    if i + 1 < len(host):
+                        pipe.prefetch(host[i + 1])
+                    k = pipe.run()
+                    if pending is not None:
+                        out.append(pipe.result(pending))
+                    pending = k
+                out.append(pipe.result(pending))
+            torch.cuda.synchronize()
+            losses[mode] = out
+            params[mode] = {k: p.detach().clone() for k, p in m.named_parameters()}
+    finally:
+        functions.GRAD_SLOTS.clear()
+    assert losses["plain"] == pytest.approx(losses["pipeline"], rel=1e-6)
+    assert len(set(losses["plain"])) == len(host)
+    for k in params["plain"]:
+        assert float((params["plain"][k] - params["pipeline"][k]).abs().max()) < 1e-6, k
