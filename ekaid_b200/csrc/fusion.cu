@@ -21,6 +21,51 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
     *(uint2*)(dst + r * ldd + c) = pk;
   }
 }
+// Up to CM_MAX strided 2-D blocks in one launch (blockIdx.y = block): fp32 -> bf16 casts (mode 0), fp32 -> fp32 copies
+// (mode 1) or raw 16-byte copies of `cols` BYTES per row (mode 2: the captured step's input staging).
+constexpr int CM_MAX = 16;
+struct CastMany {
+  const void* src[CM_MAX];
+  void* dst[CM_MAX];
+  long long lds[CM_MAX], ldd[CM_MAX], rows[CM_MAX];
+  int cols[CM_MAX];
+  int mode[CM_MAX];
+};
+__global__ void cast_many_kernel(CastMany t) {
+  ek_pdl_prologue();
+  const int i = blockIdx.y;
+  const long long rows = t.rows[i];
+  const int cols = t.cols[i], mode = t.mode[i];
+  if (mode == 2) {
+    const int c16 = cols / 16;
+    const long long total = rows * c16;
+    const uint8_t* src = (const uint8_t*)t.src[i];
+    uint8_t* dst = (uint8_t*)t.dst[i];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const long long r = e / c16;
+      const int c = (int)(e % c16) * 16;
+      *(uint4*)(dst + r * t.ldd[i] + c) = *(const uint4*)(src + r * t.lds[i] + c);
+    }
+    return;
+  }
+  const int c4n = cols / 4;
+  const long long total = rows * c4n;
+  const float* src = (const float*)t.src[i];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / c4n;
+    const int c = (int)(e % c4n) * 4;
+    const float4 v = *(const float4*)(src + r * t.lds[i] + c);
+    if (mode == 0) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *(uint32_t*)&a;
+      pk.y = *(uint32_t*)&b;
+      *(uint2*)((bf16*)t.dst[i] + r * t.ldd[i] + c) = pk;
+    } else {
+      *(float4*)((float*)t.dst[i] + r * t.ldd[i] + c) = v;
+    }
+  }
+}
 __global__ void copy_f32_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
                                 long long rows, int cols) {
   ek_pdl_prologue();
@@ -663,6 +708,30 @@ int ek_cast_f32_bf16_launch(const float* src, long long lds, bf16* dst, long lon
              EK_ERR_ALIGN, "cast_f32_bf16: cols/pitch must be multiples of 4 and pointers aligned");
   if (rows * cols == 0) return EK_OK;
   ek_launch(cast_f32_bf16_kernel, grid_for(rows * cols / 4), 256, 0, st, src, lds, dst, ldd, rows, cols);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+// count <= 16 blocks; all arrays are host arrays read at call time.  mode: 0 fp32->bf16, 1 fp32->fp32, 2 bytes (cols = bytes
+// per row, multiple of 16; pitches in bytes).  Modes 0/1: cols and pitches (elements) multiples of 4, 16-byte aligned.
+int ek_cast_many_launch(int count, const void* const* src, const long long* lds, void* const* dst, const long long* ldd,
+                        const long long* rows, const int* cols, const int* mode, cudaStream_t st) {
+  EK_REQUIRE(count >= 1 && count <= CM_MAX, EK_ERR_SHAPE, "cast_many: count=%d not in [1,%d]", count, CM_MAX);
+  CastMany t = {};
+  long long most = 0;
+  for (int i = 0; i < count; ++i) {
+    const int unit = mode[i] == 2 ? 16 : 4;
+    EK_REQUIRE(mode[i] >= 0 && mode[i] <= 2 && cols[i] % unit == 0 && lds[i] % unit == 0 && ldd[i] % unit == 0 &&
+                   ((uintptr_t)src[i] & 15) == 0 && ((uintptr_t)dst[i] & (mode[i] == 0 ? 7 : 15)) == 0,
+               EK_ERR_ALIGN, "cast_many: block %d: cols/pitches must be multiples of %d and pointers aligned", i, unit);
+    t.src[i] = src[i]; t.dst[i] = dst[i]; t.lds[i] = lds[i]; t.ldd[i] = ldd[i]; t.rows[i] = rows[i]; t.cols[i] = cols[i];
+    t.mode[i] = mode[i];
+    const long long work = rows[i] * (cols[i] / unit);
+    if (work > most) most = work;
+  }
+  if (most == 0) return EK_OK;
+  int gx = (int)((most + 255) / 256);
+  if (gx > 148 * 4) gx = 148 * 4;
+  ek_launch(cast_many_kernel, dim3(gx, count), 256, 0, st, t);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

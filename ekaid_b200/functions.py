@@ -169,6 +169,44 @@ def to_T(pc: PC, w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def cast_many(pc: PC, pairs) -> None:
+    """[(src fp32 2-D view, dst view)] -> ONE launch: dst in the operand type (bf16: cast, fp32: copy) or, for an fp32
+    dst on the bf16 path, a copy.  Views may have any row pitch."""
+    pairs = [(s_.detach(), d) for s_, d in pairs]
+    for lo in range(0, len(pairs), 16):
+        chunk = pairs[lo:lo + 16]
+        n = len(chunk)
+        srcs = [(s_ if s_.dim() == 2 else s_.view(1, -1)) for s_, _ in chunk]
+        dsts = [(d if d.dim() == 2 else d.view(1, -1)) for _, d in chunk]
+        for a, b in zip(srcs, dsts):
+            assert a.dtype == torch.float32 and a.stride(-1) == 1 and b.stride(-1) == 1 and a.shape == b.shape
+        ps = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+        pd = (ctypes.c_void_p * n)(*[t.data_ptr() for t in dsts])
+        ls = (ctypes.c_int64 * n)(*[t.stride(0) for t in srcs])
+        ld = (ctypes.c_int64 * n)(*[t.stride(0) for t in dsts])
+        rows = (ctypes.c_int64 * n)(*[t.shape[0] for t in srcs])
+        cols = (ctypes.c_int32 * n)(*[t.shape[1] for t in srcs])
+        mode = (ctypes.c_int32 * n)(*[0 if t.dtype == torch.bfloat16 else 1 for t in dsts])
+        call("cast_many", n, ctypes.addressof(ps), ctypes.addressof(ls), ctypes.addressof(pd), ctypes.addressof(ld),
+             ctypes.addressof(rows), ctypes.addressof(cols), ctypes.addressof(mode))
+
+
+def copy_many_bytes(pairs) -> None:
+    """[(src, dst)] contiguous device tensors of equal byte size (multiples of 16) -> one launch of raw copies."""
+    for lo in range(0, len(pairs), 16):
+        chunk = pairs[lo:lo + 16]
+        n = len(chunk)
+        nb = [s_.numel() * s_.element_size() for s_, _ in chunk]
+        ps = (ctypes.c_void_p * n)(*[s_.data_ptr() for s_, _ in chunk])
+        pd = (ctypes.c_void_p * n)(*[d.data_ptr() for _, d in chunk])
+        ls = (ctypes.c_int64 * n)(*nb)
+        rows = (ctypes.c_int64 * n)(*([1] * n))
+        cols = (ctypes.c_int32 * n)(*nb)
+        mode = (ctypes.c_int32 * n)(*([2] * n))
+        call("cast_many", n, ctypes.addressof(ps), ctypes.addressof(ls), ctypes.addressof(pd), ctypes.addressof(ls),
+             ctypes.addressof(rows), ctypes.addressof(cols), ctypes.addressof(mode))
+
+
 _ws_cache = {}
 
 
@@ -471,7 +509,12 @@ class QuestionFn(torch.autograd.Function):
         embc, emb2c = _f32c(emb), _f32c(emb2)
         E = torch.empty(L * B, 2 * ed, dtype=pc.T, device=dev)
         call("embed_gather", pc.f, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
-        WihT, WhhT, W1T = to_T(pc, Wih), to_T(pc, Whh), to_T(pc, W1)
+        if pc.bf16:
+            srcs = [_f32c(Wih), _f32c(Whh), _f32c(W1)]
+            WihT, WhhT, W1T = (torch.empty(t.shape, dtype=pc.T, device=dev) for t in srcs)
+            cast_many(pc, list(zip(srcs, (WihT, WhhT, W1T))))
+        else:
+            WihT, WhhT, W1T = to_T(pc, Wih), to_T(pc, Whh), to_T(pc, W1)
         bihc, bhhc, b1c, w2c, b2c = _f32c(bih), _f32c(bhh), _f32c(b1), _f32c(w2).view(-1), _f32c(b2).view(-1)
         gi = gemm_f32out(E, WihT, L * B, 3 * H, 2 * ed, bias=bihc)
         Hs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
@@ -625,18 +668,18 @@ def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, 
     G, B, N, Kn, D, H = dims
     dev = Wsw.device
     don = drop is not None and drop.on
-    WswT = to_T(pc, Wsw)
     Wsw32 = _f32c(Wsw)
+    WswT = torch.empty(Wsw32.shape, dtype=pc.T, device=dev) if pc.bf16 else Wsw32
     # [Wq ; Wk ; Z-blocks] operand: ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T (Q3)
     WqkzT = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
-    cast_into(pc, Wq, WqkzT[0:D])
-    cast_into(pc, Wk, WqkzT[D:2 * D])
     Wo2c = _f32c(Wo2)
-    for h in range(H):
-        cast_into(pc, Wo2c[:, h * D:(h + 1) * D], WqkzT[(2 + h) * D:(3 + h) * D])
     bqkzc = torch.zeros((2 + H) * D, dtype=torch.float32, device=dev)
-    call("copy_f32", _f32c(bq).data_ptr(), D, bqkzc.data_ptr(), D, 1, D)
-    call("copy_f32", _f32c(bk).data_ptr(), D, bqkzc[D:].data_ptr(), D, 1, D)
+    jobs = [(_f32c(Wq), WqkzT[0:D]), (_f32c(Wk), WqkzT[D:2 * D])]
+    jobs += [(Wo2c[:, h * D:(h + 1) * D], WqkzT[(2 + h) * D:(3 + h) * D]) for h in range(H)]
+    jobs += [(_f32c(bq).view(1, D), bqkzc[0:D].view(1, D)), (_f32c(bk).view(1, D), bqkzc[D:2 * D].view(1, D))]
+    if pc.bf16:
+        jobs.append((Wsw32, WswT))
+    cast_many(pc, jobs)          # one launch instead of nine
     cond = lbias = gbias = None
     if kind == "explicit":
         a0 = _f32c(adj0)
@@ -868,14 +911,14 @@ class FusionFn(torch.autograd.Function):
         call("combine_diff_fwd", pc.f, X3.data_ptr(), BN, D, mode, c1, c2, c3, Xc.data_ptr(), CAT.data_ptr())
         # [[context2 | context1], [gate2 | gate1]]: one GEMM over CAT[:, :2D] = [X | diff] gives both pre-activations
         WcgT = torch.empty(2 * D, 2 * D, dtype=pc.T, device=dev)
-        cast_into(pc, C2, WcgT[:D, :D])
-        cast_into(pc, C1, WcgT[:D, D:])
-        cast_into(pc, G2, WcgT[D:, :D])
-        cast_into(pc, G1, WcgT[D:, D:])
         bcgc = torch.empty(2 * D, dtype=torch.float32, device=dev)
-        call("copy_f32", _f32c(bC2).data_ptr(), D, bcgc.data_ptr(), D, 1, D)
-        call("copy_f32", _f32c(bG2).data_ptr(), D, bcgc[D:].data_ptr(), D, 1, D)
-        WeT = to_T(pc, We)
+        We32 = _f32c(We)
+        WeT = torch.empty(We32.shape, dtype=pc.T, device=dev) if pc.bf16 else We32
+        jobs = [(_f32c(C2), WcgT[:D, :D]), (_f32c(C1), WcgT[:D, D:]), (_f32c(G2), WcgT[D:, :D]), (_f32c(G1), WcgT[D:, D:]),
+                (_f32c(bC2).view(1, D), bcgc[:D].view(1, D)), (_f32c(bG2).view(1, D), bcgc[D:].view(1, D))]
+        if pc.bf16:
+            jobs.append((We32, WeT))
+        cast_many(pc, jobs)      # one launch instead of seven
         bec, wac, bac = _f32c(be), _f32c(wa).view(-1), _f32c(ba).view(-1)
         pre = gemm_f32out(CAT[:, :2 * D], WcgT, M, 2 * D, 2 * D, bias=bcgc)
         cx = torch.empty(M, D, dtype=pc.T, device=dev)

@@ -368,8 +368,12 @@ class GraphFusionStep:
 
     def replay(self, raw):
         """Copy a new raw device (or pinned host) batch into the captured buffers and replay the step."""
-        for dst, src in zip(self._static, raw):
-            dst.copy_(src, non_blocking=True)
+        if all(s_.is_cuda and s_.is_contiguous() and s_.dtype == d.dtype and s_.shape == d.shape
+               and (s_.numel() * s_.element_size()) % 16 == 0 and s_.data_ptr() % 16 == 0 for d, s_ in zip(self._static, raw)):
+            functions.copy_many_bytes(list(zip(raw, self._static)))          # one launch instead of 11 memcpy nodes
+        else:
+            for dst, src in zip(self._static, raw):
+                dst.copy_(src, non_blocking=True)
         self._graph.replay()
         lib.LAUNCHES += self.launches_per_replay
         return self._static_out

@@ -97,6 +97,11 @@ int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, 
 /* ---- casts / reductions / glue -------------------------------------------------------------------------- */
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+/* the same for up to 16 strided 2-D blocks in ONE launch.  src, lds, dst, ldd, rows, cols, mode are HOST arrays read at
+ * call time; mode[i]: 0 = fp32 -> bf16, 1 = fp32 -> fp32, 2 = raw bytes (cols = bytes per row, multiple of 16, pitches in
+ * bytes).  Used for the operand-type copies of a relation encoder's weights and for staging the step's inputs. */
+int ekaid_cast_many(int count, const void* const* src, const int64_t* lds, void* const* dst, const int64_t* ldd,
+                    const int64_t* rows, const int32_t* cols, const int32_t* mode, void* stream);
 int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 /* out[n] = sum_m rowscale[m] * src[m,n]  (bias gradients), deterministic, one launch, N <= 32768.  workspace >= 1024 +
  * 64*N floats; the first 1024 words are ticket counters: zero them once, every call leaves them zero again */
