@@ -272,7 +272,7 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
   float* sW = sm;
   float* sDim = sm + H * 65;
   float* sE = sDim + 8;
-  float* sDf = sE + GB_TILE * 65;
+  float* sDf = (float*)(((uintptr_t)(sE + GB_TILE * 65) + 15) & ~(uintptr_t)15);      // 16-byte aligned rows of 8
   const int tid = threadIdx.x;
   if (tid < 8) sDim[tid] = dim_t[tid];
   for (int e = tid; e < H * 64; e += GB_TILE) sW[e] = Wp[e];
@@ -282,6 +282,8 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
   const int total = N * Kn;
   const int nout = H * 65;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};         // outputs tid, tid+128, ... (H <= 8 -> <= 520 outputs)
+  float kacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // cached path: column tid % 64 of every head
+  float bacc = 0.f;                                  // cached path: bias gradient of head tid (threads 0..7)
   __syncthreads();
   for (int t0 = blockIdx.y * GB_TILE; t0 < total; t0 += gridDim.y * GB_TILE) {
     const int e = t0 + tid;
@@ -311,14 +313,23 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
 #pragma unroll
       for (int h = 0; h < 8; ++h) sDf[tid * 8 + h] = df[h];
       __syncthreads();
-#pragma unroll
-      for (int a = 0; a < 5; ++a) {
-        const int o = tid + a * GB_TILE;
-        if (o < nout) {
-          const int h = o / 65, k = o % 65;
-          float s2 = acc[a];
-          for (int p = 0; p < GB_TILE; ++p) s2 = fmaf(sDf[p * 8 + h], sE[p * 65 + k], s2);
-          acc[a] = s2;
+      // thread (k = tid % 64, hf = tid / 64) owns column k of every head over every second pair: one E load and two
+      // 16-byte df loads per 8 FMAs (the old (h,k)-per-thread form needed two loads per FMA); bias column: threads 0..7
+      {
+        const int k = tid & 63, hf = tid >> 6;
+#pragma unroll 4
+        for (int p = hf; p < GB_TILE; p += 2) {
+          const float ev = sE[p * 65 + k];
+          const float4 d0 = *(const float4*)(sDf + p * 8), d1 = *(const float4*)(sDf + p * 8 + 4);
+          kacc[0] = fmaf(d0.x, ev, kacc[0]); kacc[1] = fmaf(d0.y, ev, kacc[1]);
+          kacc[2] = fmaf(d0.z, ev, kacc[2]); kacc[3] = fmaf(d0.w, ev, kacc[3]);
+          kacc[4] = fmaf(d1.x, ev, kacc[4]); kacc[5] = fmaf(d1.y, ev, kacc[5]);
+          kacc[6] = fmaf(d1.z, ev, kacc[6]); kacc[7] = fmaf(d1.w, ev, kacc[7]);
+        }
+        if (tid < 8) {
+          float bs = bacc;
+          for (int p = 0; p < GB_TILE; ++p) bs += sDf[p * 8 + tid];
+          bacc = bs;
         }
       }
       __syncthreads();
@@ -358,10 +369,25 @@ geom_bias_bwd_kernel(const double* __restrict__ bb0, const double* __restrict__ 
     }
     __syncthreads();
   }
+  float* pout = part + ((size_t)g * gridDim.y + blockIdx.y) * nout;
+  if (emb_cache) {
+    // combine the two pair-halves through shared memory (sE is free now), then write [h][65]
+    __syncthreads();
+    float* sK = sE;                                   // [2][64][8]
+#pragma unroll
+    for (int h = 0; h < 8; ++h) sK[((tid >> 6) * 64 + (tid & 63)) * 8 + h] = kacc[h];
+    __syncthreads();
+    for (int o = tid; o < H * 64; o += GB_TILE) {
+      const int h = o / 64, k = o % 64;
+      pout[h * 65 + k] = sK[k * 8 + h] + sK[(64 + k) * 8 + h];
+    }
+    if (tid < H) pout[tid * 65 + 64] = bacc;
+    return;
+  }
 #pragma unroll
   for (int a = 0; a < 5; ++a) {
     const int o = tid + a * GB_TILE;
-    if (o < nout) part[((size_t)g * gridDim.y + blockIdx.y) * nout + o] = acc[a];
+    if (o < nout) pout[o] = acc[a];
   }
 }
 
@@ -704,7 +730,7 @@ int ek_geom_bias_bwd_launch(const double* bb0, const double* bb1, int g_split, c
                             const float* dim_t, int G, int N, int Kn, int H, const float* dgbias, float* part,
                             EkDrop dr, const float* emb_cache, int fast_trig, cudaStream_t st) {
   EK_REQUIRE(H <= 8, EK_ERR_UNSUPPORTED, "geom_bias: H=%d > 8", H);
-  const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float);
+  const size_t smem = (H * 65 + 8 + GB_TILE * 65 + GB_TILE * 8) * sizeof(float) + 16;
   ek_launch(geom_bias_bwd_kernel, dim3(G, GB_SPLIT), GB_TILE, smem, st, bb0, bb1, g_split, Wp, bp, dim_t, N, Kn, H, dgbias,
             part, dr, emb_cache, fast_trig);
   EK_CHECK_LAUNCH();
