@@ -531,12 +531,18 @@ edge_aggregate_fwd_kernel(const float* __restrict__ P, const T* __restrict__ QKZ
         if (i < rows) {
           const size_t row = (size_t)g * N + i0 + i;
           const float o = acc[r] + bo;
-          // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
-          const float o2 = (o + o) * ek_drop_mult(dr, sd, row * D + c0 + cl);
-          const float xn = Xin[row * D + c0 + cl] + fmaxf(o2, 0.f);
+          float xn;
+          if (mask == nullptr) {
+            // plain attention output of GraphSelfAttentionLayer.forward (graph_att_layer.py:164-178): no doubling / ReLU
+            xn = o + (Xin ? Xin[row * D + c0 + cl] : 0.f);
+          } else {
+            // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
+            const float o2 = (o + o) * ek_drop_mult(dr, sd, row * D + c0 + cl);
+            xn = (Xin ? Xin[row * D + c0 + cl] : 0.f) + fmaxf(o2, 0.f);
+            mask[row * D + c0 + cl] = o2 > 0.f ? 1 : 0;
+          }
           Xout[row * D + c0 + cl] = xn;
           if (XoutT) XoutT[row * ldt + c0 + cl] = from_f32<T>(xn);
-          mask[row * D + c0 + cl] = o2 > 0.f ? 1 : 0;
         }
       }
     }

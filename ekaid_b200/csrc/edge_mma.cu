@@ -161,7 +161,7 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
         bo[nt] = cok ? *(const float2*)(b_out + colb + nt * 8) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh)
-          xi[hh][nt] = (cok && rok[hh]) ? *(const float2*)(Xin + rbase[hh] + nt * 8) : make_float2(0.f, 0.f);
+          xi[hh][nt] = (cok && rok[hh] && Xin) ? *(const float2*)(Xin + rbase[hh] + nt * 8) : make_float2(0.f, 0.f);
       }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -171,22 +171,32 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
           if (!rok[hh]) continue;
           const size_t idx = rbase[hh] + nt * 8;
           const float o0 = acc[it][nt][2 * hh] + bo[nt].x, o1 = acc[it][nt][2 * hh + 1] + bo[nt].y;
-          // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
-          float dm[2];
-          ek_drop_multv<2>(dr, sd, idx, dm);                   // even column: both lanes come from one draw
-          const float p0 = (o0 + o0) * dm[0];
-          const float p1 = (o1 + o1) * dm[1];
-          const float x0 = xi[hh][nt].x + fmaxf(p0, 0.f), x1 = xi[hh][nt].y + fmaxf(p1, 0.f);
+          float x0, x1, p0 = 0.f, p1 = 0.f;
+          if (mask == nullptr) {
+            // plain attention output of GraphSelfAttentionLayer.forward: no doubling, dropout or ReLU
+            x0 = xi[hh][nt].x + o0;
+            x1 = xi[hh][nt].y + o1;
+          } else {
+            // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
+            float dm[2];
+            ek_drop_multv<2>(dr, sd, idx, dm);                 // even column: both lanes come from one draw
+            p0 = (o0 + o0) * dm[0];
+            p1 = (o1 + o1) * dm[1];
+            x0 = xi[hh][nt].x + fmaxf(p0, 0.f);
+            x1 = xi[hh][nt].y + fmaxf(p1, 0.f);
+          }
           *(float2*)(Xout + idx) = make_float2(x0, x1);
           if (XoutT) {
             const size_t row = idx / D;                         // only when the operand copy has its own pitch
             const size_t tix = (ldt == D) ? idx : row * ldt + (idx - row * D);
             *(__nv_bfloat162*)(XoutT + tix) = __floats2bfloat162_rn(x0, x1);
           }
-          uchar2 mk;
-          mk.x = p0 > 0.f ? 1 : 0;
-          mk.y = p1 > 0.f ? 1 : 0;
-          *(uchar2*)(mask + idx) = mk;
+          if (mask) {
+            uchar2 mk;
+            mk.x = p0 > 0.f ? 1 : 0;
+            mk.y = p1 > 0.f ? 1 : 0;
+            *(uchar2*)(mask + idx) = mk;
+          }
         }
       }
     }

@@ -495,6 +495,74 @@ def _gru_seq_ok(pc, dev, B, H):
     return H // 8 <= sms and B * 64 + 192 * 1024 <= 227 * 1024
 
 
+class GRUFn(torch.autograd.Function):
+    """nn.GRU(batch_first, 1 layer, unidirectional, h0 = 0) on x [B,L,in] -> all outputs [B,L,H]
+    (QuestionEmbedding.forward_all stand-alone, language_model.py:106-115).  Same kernels as QuestionFn's middle part."""
+
+    @staticmethod
+    def forward(ctx, pc: PC, x, Wih, Whh, bih, bhh):
+        lib.require_device()
+        dev = x.device
+        B, L, I = x.shape
+        H = Whh.shape[1]
+        # time-major rows t*B + b, in the operand type
+        E = to_T(pc, _f32c(x).transpose(0, 1).reshape(L * B, I))
+        WihT, WhhT = to_T(pc, Wih), to_T(pc, Whh)
+        bihc, bhhc = _f32c(bih), _f32c(bhh)
+        gi = gemm_f32out(E, WihT, L * B, 3 * H, I, bias=bihc)
+        Hs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
+        HsT = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev)
+        gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
+        if _gru_seq_ok(pc, dev, B, H):
+            call("gru_seq_fwd", gi.data_ptr(), WhhT.data_ptr(), bhhc.data_ptr(), B, H, L, Hs.data_ptr(), HsT.data_ptr(),
+                 gates.data_ptr(), _barrier_ws(dev).data_ptr())
+        else:
+            gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
+            call("copy_f32", bhhc.data_ptr(), 0, gh.data_ptr(), 3 * H, B, 3 * H)
+            for t in range(L):
+                gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, addend=gh, C=gh)
+                hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+                call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
+                     Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr(),
+                     bhhc.data_ptr())
+        ctx.pc, ctx.dims = pc, (B, L, I, H)
+        ctx.saved = (E, WihT, WhhT, Hs, HsT, gates)
+        return Hs.view(L, B, H).transpose(0, 1).contiguous()
+
+    @staticmethod
+    def backward(ctx, dout):
+        pc = ctx.pc
+        B, L, I, H = ctx.dims
+        E, WihT, WhhT, Hs, HsT, gates = ctx.saved
+        dev = Hs.device
+        dHs = _f32c(dout).transpose(0, 1).reshape(L * B, H).contiguous()
+        dgi = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
+        dgh = torch.empty(L * B, 3 * H, dtype=torch.float32, device=dev)
+        dgiT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgi
+        dghT = torch.empty(L * B, 3 * H, dtype=pc.T, device=dev) if pc.bf16 else dgh
+        if _gru_seq_ok(pc, dev, B, H):
+            call("gru_seq_bwd", dHs.data_ptr(), gates.data_ptr(), Hs.data_ptr(), WhhT.data_ptr(), B, H, L, dgi.data_ptr(),
+                 dgh.data_ptr(), dgiT.data_ptr(), dghT.data_ptr(), _barrier_ws(dev).data_ptr())
+        else:
+            carry = torch.empty(B, H, dtype=torch.float32, device=dev)
+            for t in range(L - 1, -1, -1):
+                sl = slice(t * B, (t + 1) * B)
+                if t < L - 1:
+                    call("add_inplace", dHs[sl].data_ptr(), carry.data_ptr(), B * H)
+                hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
+                call("gru_cell_bwd", pc.f, dHs[sl].data_ptr(), gates[t].data_ptr(), ptr(hprev), B, H, dgi[sl].data_ptr(),
+                     dgh[sl].data_ptr(), dgiT[sl].data_ptr() if pc.bf16 else None,
+                     dghT[sl].data_ptr() if pc.bf16 else None, carry.data_ptr())
+                if t > 0:
+                    gemm(dghT[sl], WhhT, B, H, 3 * H, transB=1, addend=carry, C=carry)
+        dWih = gemm_f32out(dgiT, E, 3 * H, I, L * B, transA=1, transB=1)
+        dbih = colsum(dgi, L * B, 3 * H)
+        dWhh = gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1)
+        dbhh = colsum(dgh, L * B, 3 * H)
+        dx = gemm_f32out(dgiT, WihT, L * B, I, 3 * H, transB=1)
+        return None, dx.view(L, B, I).transpose(0, 1).contiguous(), dWih, dWhh, dbih, dbhh
+
+
 class QuestionFn(torch.autograd.Function):
     """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156)."""
 
@@ -642,6 +710,64 @@ class QuestionFn(torch.autograd.Function):
         cur.wait_stream(br1)
         cur.wait_stream(br2)
         return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
+
+
+# ------------------------------------------------------------------------------------------------
+# the edge part alone (stand-alone GraphSelfAttentionLayer / GAttNet forward)
+# ------------------------------------------------------------------------------------------------
+class EdgeAttentionFn(torch.autograd.Function):
+    """out = sum_h softmax(mask(Q_h K_h^T / sqrt(d_h) + gbias_h) + lbias) Z_h + b_out   (graph_att_layer.py:105-178 with
+    the out-projection re-associated per Q3).  QKZ32 [G*N, (2+H)*D] fp32 = [query | key | Z_0..Z_{H-1}] (rows j >= Kn of
+    the key / Z parts are never read).  cond / lbias [G,N,Kn], gbias [G,N,Kn,H] may be None.  Returns (out, P)."""
+
+    @staticmethod
+    def forward(ctx, pc: PC, dims, QKZ32, cond, lbias, gbias, bout):
+        lib.require_device()
+        G, N, Kn, D, H = dims
+        dev = QKZ32.device
+        M, W = G * N, (2 + H) * D
+        q32 = _f32c(QKZ32).view(M, W)
+        QKZ = to_T(pc, q32)
+        condc = _f32c(cond).contiguous() if cond is not None else None
+        lbc = _f32c(lbias).contiguous() if lbias is not None else None
+        gbc = _f32c(gbias).contiguous() if gbias is not None else None
+        P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
+        Phl = None
+        if pc.bf16 and (H * Kn) % 8 == 0 and N <= 128 and (D // H) % 16 == 0:
+            Phl = torch.empty(2, G, N, H * Kn, dtype=torch.bfloat16, device=dev)
+        call("edge_softmax_fwd", pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(condc), ptr(lbc), ptr(gbc), G, N, Kn, H,
+             P.data_ptr(), ptr(Phl))
+        out = torch.empty(M, D, dtype=torch.float32, device=dev)
+        call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, _f32c(bout).data_ptr(), None,
+             G, N, Kn, H, out.data_ptr(), None, D, None, None, 0, 0.0, ptr(Phl))
+        ctx.pc, ctx.dims = pc, dims
+        ctx.flags = (lbias is not None, gbias is not None)
+        ctx.saved = (QKZ, condc, P, Phl)
+        ctx.mark_non_differentiable(P)
+        return out, P
+
+    @staticmethod
+    def backward(ctx, dout, _dP):
+        pc = ctx.pc
+        G, N, Kn, D, H = ctx.dims
+        QKZ, cond, P, Phl = ctx.saved
+        dev = P.device
+        M, W = G * N, (2 + H) * D
+        dout = _f32c(dout).view(M, D)
+        ns = lib.load().ekaid_edge_bwd_slices(pc.f, D, N, Kn, H, 1 if Phl is not None else 0)
+        dQKZ = torch.zeros(M, W, dtype=pc.T, device=dev)
+        dOut = torch.empty(M, D, dtype=torch.float32, device=dev)
+        dPpart = torch.empty(ns, G, N, H, Kn, dtype=torch.float32, device=dev)
+        ones = torch.ones(M, D, dtype=torch.uint8, device=dev)          # plain output: no ReLU mask, gradient scale 1
+        call("edge_aggregate_bwd", pc.f, dout.data_ptr(), ones.data_ptr(), P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D,
+             G, N, Kn, H, dQKZ.data_ptr(), dOut.data_ptr(), dPpart.data_ptr(), 1.0, ptr(Phl))
+        dbout = colsum(dOut, M, D)
+        has_lb, has_gb = ctx.flags
+        dlb = torch.empty(H, G, N, Kn, dtype=torch.float32, device=dev) if has_lb else None
+        dgb = torch.empty(G, N, Kn, H, dtype=torch.float32, device=dev) if has_gb else None
+        call("edge_softmax_bwd", pc.f, P.data_ptr(), dPpart.data_ptr(), ns, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond),
+             G, N, Kn, H, dQKZ.data_ptr(), ptr(dlb), ptr(dgb))
+        return None, None, dQKZ.float(), None, (dlb.sum(0) if has_lb else None), dgb, dbout
 
 
 # ------------------------------------------------------------------------------------------------

@@ -34,7 +34,8 @@ with warnings.catch_warnings():
     from torch.nn.utils import weight_norm as _weight_norm
 
 from . import lib as _lib
-from .functions import PC, Drop, FusionFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn, WNormManyFn
+from .functions import (PC, Drop, EdgeAttentionFn, FusionFn, GRUFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn,
+                        WNormManyFn)
 
 
 def _default_precision() -> str:
@@ -85,7 +86,11 @@ class FCNet(nn.Module):
         for m in self.main:
             if isinstance(m, nn.Linear):
                 shp = out.shape
-                y, _ = LinearFn.apply(pc, out.reshape(-1, shp[-1]), None, wn_weight(m), m.bias)
+                if m.in_features % 8 or m.out_features % 8:
+                    # a handful of inputs / outputs (label bias 3|11 -> 1, pair_pos_fc1 64 -> 4): one warp per output
+                    y = SmallLinearFn.apply(out.reshape(-1, shp[-1]).float(), wn_weight(m), m.bias)
+                else:
+                    y, _ = LinearFn.apply(pc, out.reshape(-1, shp[-1]), None, wn_weight(m), m.bias)
                 out = y.view(*shp[:-1], y.shape[-1])
             else:
                 out = m(out)
@@ -122,12 +127,41 @@ class GraphSelfAttentionLayer(nn.Module):
         self.linear_out_ = _wn(nn.Conv2d(in_channels=self.fc_dim * feat_dim, out_channels=self.dim[2],
                                          kernel_size=(1, 1), groups=self.fc_dim))
         self.linear_out_2 = nn.Linear(self.fc_dim * feat_dim, self.dim[2])
-
+        self.precision = _default_precision()
 
     def forward(self, roi_feat, adj_matrix, position_embedding, label_biases_att):
-        raise NotImplementedError(
-            "GraphSelfAttentionLayer is executed inside the fused relation kernels; call the owning "
-            "ExplicitRelationEncoder / ImplicitRelationEncoder (or ChangeDetector) instead")
+        """Stand-alone form of models/graph_att_layer.py:60-178: (output [B,N,D], aff_softmax [B,N,H,K]).  Projections
+        go through the GEMM kernels (FCNet / LinearFn), scores + mask + biases + softmax and the aggregation through the
+        edge kernels (EdgeAttentionFn); the few reshapes in between are torch ops.  The relation encoders and
+        ChangeDetector do not come through here: they run the fused RelationFn."""
+        pc = PC(getattr(self, "precision", _default_precision()))
+        B, N, D = roi_feat.shape
+        H = self.num_heads
+        Kn = self.nongt_dim if self.nongt_dim < N else N
+        nongt = roi_feat[:, :Kn, :]
+        q = self.query(roi_feat)                                        # [B,N,D]
+        k = self.key(nongt)                                             # [B,Kn,D]
+        # Z_h = v_data W_out2[:, hD:(h+1)D]^T: the out-projection applied before the aggregation (Q3 re-association)
+        Wz = self.linear_out_2.weight.view(D, H, D).permute(1, 0, 2).reshape(H * D, D)
+        z, _ = LinearFn.apply(pc, nongt.reshape(B * Kn, D), None, Wz, None)
+        z = z.view(B, Kn, H * D)
+        if Kn < N:
+            k = F.pad(k, (0, 0, 0, N - Kn))
+            z = F.pad(z, (0, 0, 0, N - Kn))
+        qkz = torch.cat((q, k, z), dim=-1).reshape(B * N, (2 + H) * D)
+        gbias = None
+        if position_embedding is not None and self.pos_emb_dim > 0:
+            pe = position_embedding.float().reshape(B, -1, self.pos_emb_dim)
+            feat = F.relu(self.pair_pos_fc1(pe)).view(B, -1, Kn, self.fc_dim)          # :113-127
+            if feat.shape[1] != N:
+                raise ValueError("position_embedding must hold N x K pairs per image, got %s" % (tuple(position_embedding.shape),))
+            gbias = torch.log(torch.clamp(feat, min=1e-6))                               # :131-135
+        cond = lbias = None
+        if adj_matrix is not None:
+            cond = adj_matrix.float().reshape(B, N, Kn)
+            lbias = label_biases_att.float().reshape(B, N, Kn)
+        out, P = EdgeAttentionFn.apply(pc, (B, N, Kn, D, H), qkz, cond, lbias, gbias, self.linear_out_2.bias)
+        return out.view(B, N, D), P
 
 
 class GAttNet(nn.Module):
@@ -218,9 +252,31 @@ class GAttNet(nn.Module):
             raise ValueError(f"position embedding is set to None with pos_emb_dim {self.pos_emb_dim}")
         elif self.pos_emb_dim < 0 and pos_emb is not None:
             raise ValueError("position embedding is NOT None with pos_emb_dim < 0")
-        raise NotImplementedError(
-            "GAttNet consumes the concatenated [v | q] tensor in the reference; the CUDA path never builds it. "
-            "Call ExplicitRelationEncoder / ImplicitRelationEncoder.forward(v, adj_or_boxes, q)")
+        # Stand-alone form of models/graph_att.py:71-106 on a materialised [v | q] tensor (the relation encoders and
+        # ChangeDetector never build it: they run the fused RelationFn).  Returns (output, [aff_d0, aff_d1]).
+        B, N, _ = v_feat.shape
+        nongt = self.nongt_dim
+        adj = adj_matrix.float()
+        adj_list = [adj, adj.transpose(1, 2)]
+        self_feat = self.self_weights(v_feat)                           # [B,N,out]
+        output = self_feat
+        aff = []
+        for d in range(self.dir_num):
+            a = adj_list[d][:, :, :nongt, :]
+            cond = a.sum(-1)                                            # :88
+            lbias = self.bias(a).squeeze(-1)                            # :92
+            layer = self.neighbor_net[d]
+            if d < self.dir_num - 1:
+                # quirk Q2: this direction's output is overwritten below; only its attention map is returned
+                with torch.no_grad():
+                    _, p = layer(self_feat, cond, pos_emb, lbias)
+                aff.append(p)
+                continue
+            out, p = layer(self_feat, cond, pos_emb, lbias)
+            aff.append(p)
+            output = out + out                                          # :99-101 (neighbor_emb[d] is `output` itself)
+        output = F.relu(self.dropout(output))
+        return output, aff
 
 
 def _maybe_inplace(v: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
@@ -250,11 +306,19 @@ class ImplicitRelationEncoder(nn.Module):
         self.precision = _default_precision()
 
     def forward(self, v, position_embedding, q):
-        if position_embedding.dim() != 3 or position_embedding.shape[-1] != 4:
-            raise ValueError("the CUDA implicit encoder takes the boxes [B, N, 4]; the 64-d position embedding is "
-                             "computed inside the kernel (got shape %s)" % (tuple(position_embedding.shape),))
         if self.v_transform is not None or not self.residual_connection or self.num_steps != 1:
             raise NotImplementedError("only v_dim == out_dim, residual_connection=True, num_steps=1 (reference config)")
+        if position_embedding.dim() == 4:
+            # the reference's materialised [B,N,K,pos_emb_dim] embedding: the stand-alone GAttNet path
+            # (relation_encoder.py:68-84); the fused path below takes the boxes and never builds it
+            B, N, _ = v.shape
+            ones = torch.ones(B, N, N, 1, device=v.device)
+            rel, affs = self.implicit_relation(q_expand_v_cat(q, v, mask=True), ones, position_embedding)
+            return _maybe_inplace(v, v + rel), affs
+        if position_embedding.dim() != 3 or position_embedding.shape[-1] != 4:
+            raise ValueError("the implicit encoder takes the boxes [B, N, 4] (geometry computed inside the kernel) or "
+                             "the reference's [B, N, K, %d] position embedding (got shape %s)"
+                             % (self.implicit_relation.pos_emb_dim, tuple(position_embedding.shape)))
         pc = PC(self.precision)
         B, N, D = v.shape
         out, _, P = self.implicit_relation.relation_step(pc, v.reshape(B * N, D), None, q, position_embedding, None,
@@ -323,6 +387,19 @@ class QuestionEmbedding(nn.Module):
         self.nlayers = nlayers
         self.rnn_type = rnn_type
         self.ndirections = 1 + int(bidirect)
+        self.precision = _default_precision()
+
+    def forward_all(self, x):
+        """All GRU outputs [B,L,H] for x [B,L,in] (language_model.py:106-115), stand-alone; inside ChangeDetector the
+        recurrence is part of QuestionFn."""
+        if self.rnn_type != 'GRU' or self.nlayers != 1 or self.ndirections != 1:
+            raise NotImplementedError("only the reference configuration (1-layer unidirectional GRU) is implemented")
+        rnn = self.rnn
+        return GRUFn.apply(PC(self.precision), x, rnn.weight_ih_l0, rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0)
+
+    def forward(self, x):
+        """Last GRU output [B,H] (language_model.py:87-98)."""
+        return self.forward_all(x)[:, -1]
 
 
 class QuestionSelfAttention(nn.Module):
@@ -334,6 +411,17 @@ class QuestionSelfAttention(nn.Module):
         self.drop = nn.Dropout(dropout)
         self.W1_self_att_q = FCNet(dims=[num_hid, num_hid], dropout=dropout, act=None)
         self.W2_self_att_q = FCNet(dims=[num_hid, 1], act=None)
+
+    def forward(self, ques_feat):
+        """[B,L,H] -> [B,H] (language_model.py:127-156), stand-alone: the two projections run through the GEMM kernels,
+        the batch-axis softmax and its reinterpretation (quirk Q4) are written with the same tensor ops as the
+        reference so that the quirk is reproduced exactly."""
+        B, L = ques_feat.shape[0], ques_feat.shape[1]
+        flat = ques_feat.contiguous().view(-1, self.num_hid)
+        atten = self.W2_self_att_q(torch.tanh(self.W1_self_att_q(flat))).view(B, L)
+        weight = F.softmax(atten.t(), dim=1).view(-1, 1, L)             # Q4: softmax over the batch axis, then reinterpreted
+        out = torch.bmm(weight, ques_feat).view(-1, self.num_hid)
+        return self.drop(out)
 
 
 class SelfAttention(nn.Module):

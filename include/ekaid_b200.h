@@ -149,7 +149,9 @@ int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, cons
  * aggregation kernels stage with 16-byte async copies (pass the same pointer to edge_aggregate_fwd/bwd, or NULL). */
 /* out = sum_h P_h Z_h + b_out;  Xout = Xin + relu(2 out);  mask = (out > 0)
  * (graph_att_layer.py:164-176 re-associated per Q3, graph_att.py:95-104 (Q2), relation_encoder.py:81,129 (Q1)).
- * XoutT: optional copy of Xout in the operand type with pitch ldt (may be NULL). */
+ * XoutT: optional copy of Xout in the operand type with pitch ldt (may be NULL).
+ * Xin NULL: no residual.  mask NULL: plain attention output Xout = (Xin +) out, without doubling, dropout or ReLU
+ * (GraphSelfAttentionLayer.forward stand-alone, graph_att_layer.py:164-178). */
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
                              uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl, void* stream);

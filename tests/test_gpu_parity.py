@@ -397,3 +397,92 @@ def test_gru_one_launch_recurrence_matches_step_kernels(B):
         # (the attention bias b2 has an analytically zero gradient -- softmax shift invariance -- hence the atol)
         e = float((gseq - gstep).norm() / (gstep.norm() + 1e-3 * gstep.numel() ** 0.5))
         assert e < 3e-2, (k, e, float(gstep.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gattnet_and_attention_layer_standalone(precision):
+    """GAttNet.forward(v_feat = [v | q], adj, pos_emb) and, through it, GraphSelfAttentionLayer.forward -- the inner
+    signatures of SURVEY.md section 8(b) -- against the oracle: output = relu(2 out) = X_new - X, aff[1] = P."""
+    from ekaid_b200.modules import ExplicitRelationEncoder, ImplicitRelationEncoder, q_expand_v_cat
+    from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B, N, D = 2, 52, 1024
+    full = synthetic_state_dict(spec_for("all"), 1238)
+    batch = synthetic_batch(B, N, seed=23)
+    g = torch.Generator().manual_seed(9)
+    v = torch.randn(B, N, D, generator=g)
+    v[1, 5] = 0
+    q = torch.randn(B, D, generator=g)
+    adj = O.process_matrix(batch[6], N, 11)
+    tol = TOL[precision]
+    for kind in ("explicit", "implicit"):
+        with contextlib.redirect_stdout(io.StringIO()):
+            if kind == "explicit":
+                enc = ExplicitRelationEncoder(D, D, D, 2, 11, num_heads=4, nongt_dim=52, label_bias=False)
+                prefix, R, gat = "spatial_relation.", O.REL_SPA, None
+            else:
+                enc = ImplicitRelationEncoder(D, D, D, 2, 64, 52, num_heads=4, label_bias=False)
+                prefix, R = "imp_relation.", O.REL_IMP
+        enc.load_state_dict({k[len(prefix):]: t for k, t in full.items() if k.startswith(prefix)})
+        enc.to(dev).eval()
+        for m in enc.modules():
+            if hasattr(m, "precision"):
+                m.precision = precision
+        gat = enc.explicit_relation if kind == "explicit" else enc.implicit_relation
+        vq = q_expand_v_cat(q, v).to(dev).requires_grad_(True)
+        if kind == "explicit":
+            out, aff = gat(vq, adj.to(dev))
+            pos = None
+        else:
+            pos = O.position_embedding(O.position_matrix(batch[10], 52), 64)          # [B,N,K,64] fp64, as the reference
+            out, aff = gat(vq, torch.ones(B, N, N, 1, device=dev), pos.to(dev))
+        sdg = {k: t.clone().requires_grad_(True) for k, t in full.items() if k.startswith(prefix)}
+        vr = v.clone().requires_grad_(True)
+        Xn, aux = O.gat_relation(sdg, R, vr, q, adj if kind == "explicit" else None, pos, 4, 52, return_aux=True)
+        ref = (Xn - vr).detach()
+        assert rel_err(out, ref) < tol, (kind, precision, rel_err(out, ref))
+        assert len(aff) == 2 and tuple(aff[1].shape) == (B, N, 4, 52)
+        assert float((aff[1].cpu() - aux["P"].detach()).abs().max()) < (1e-4 if precision == "fp32" else 2e-2)
+        # gradients through the stand-alone path: d/d(v half of the input) and a weight
+        w = torch.randn(out.shape, generator=torch.Generator().manual_seed(10))
+        (out * w.to(dev)).sum().backward()
+        ((Xn - vr) * w).sum().backward()
+        gv = vq.grad[..., :D].cpu()
+        # the oracle's vr.grad also contains the residual-free path only (Xn - vr removes the identity)
+        e = float((gv - vr.grad).norm() / vr.grad.norm())
+        assert e < (5e-3 if precision == "fp32" else 6e-2), (kind, precision, "d v", e)
+        pname = "neighbor_net.1.linear_out_2.weight"
+        pg = dict(gat.named_parameters())[pname].grad.cpu()
+        rg = sdg[prefix + ("explicit_relation." if kind == "explicit" else "implicit_relation.") + pname].grad
+        e = float((pg - rg).norm() / rg.norm())
+        assert e < (5e-3 if precision == "fp32" else 6e-2), (kind, precision, pname, e)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_question_modules_standalone(precision):
+    """WordEmbedding -> QuestionEmbedding.forward_all -> QuestionSelfAttention.forward called one by one (the inner
+    signatures of SURVEY.md section 8(b)) must reproduce the oracle's question vector and its gradients."""
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z, meta = load_case("c1_b3_n52_all_grads")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    question = inp[8].to(dev)
+    w_emb = m.w_emb(question)                                       # [B,L,600]
+    hs = m.q_emb.forward_all(w_emb)                                 # [B,L,1024]
+    qv = m.q_att(hs)                                                # [B,1024]
+    assert tuple(hs.shape) == (question.shape[0], question.shape[1], 1024)
+    assert float((m.q_emb(w_emb) - hs[:, -1]).abs().max()) < (1e-5 if precision == "fp32" else 2e-2)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()
+           if k.startswith(("w_emb", "q_emb", "q_att"))}
+    ref = O.question_vector(sdg, inp[8])
+    assert rel_err(qv, ref) < TOL[precision], rel_err(qv, ref)
+    w = torch.randn(qv.shape, generator=torch.Generator().manual_seed(3))
+    (qv * w.to(dev)).sum().backward()
+    (ref * w).sum().backward()
+    for k in ("q_emb.rnn.weight_hh_l0", "q_emb.rnn.weight_ih_l0", "q_att.W1_self_att_q.main.1.weight_v", "w_emb.emb.weight"):
+        g = dict(m.named_parameters())[k].grad
+        assert g is not None, k
+        e = grad_err(g, sdg[k].grad, precision)
+        assert e < gtol(precision, k, sdg[k].grad), (precision, k, e)
