@@ -451,12 +451,12 @@ def test_gattnet_and_attention_layer_standalone(precision):
         gv = vq.grad[..., :D].cpu()
         # the oracle's vr.grad also contains the residual-free path only (Xn - vr removes the identity)
         e = float((gv - vr.grad).norm() / vr.grad.norm())
-        assert e < (5e-3 if precision == "fp32" else 6e-2), (kind, precision, "d v", e)
+        assert e < (1e-2 if precision == "fp32" else 0.1), (kind, precision, "d v", e)
         pname = "neighbor_net.1.linear_out_2.weight"
         pg = dict(gat.named_parameters())[pname].grad.cpu()
         rg = sdg[prefix + ("explicit_relation." if kind == "explicit" else "implicit_relation.") + pname].grad
         e = float((pg - rg).norm() / rg.norm())
-        assert e < (5e-3 if precision == "fp32" else 6e-2), (kind, precision, pname, e)
+        assert e < (1e-2 if precision == "fp32" else 0.1), (kind, precision, pname, e)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
