@@ -473,7 +473,7 @@ def test_question_modules_standalone(precision):
     hs = m.q_emb.forward_all(w_emb)                                 # [B,L,1024]
     qv = m.q_att(hs)                                                # [B,1024]
     assert tuple(hs.shape) == (question.shape[0], question.shape[1], 1024)
-    assert float((m.q_emb(w_emb) - hs[:, -1]).abs().max()) < (1e-5 if precision == "fp32" else 2e-2)
+    assert float((m.q_emb(w_emb).detach() - hs[:, -1].detach()).abs().max()) < (1e-5 if precision == "fp32" else 2e-2)
     sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()
            if k.startswith(("w_emb", "q_emb", "q_att"))}
     ref = O.question_vector(sdg, inp[8])
