@@ -991,16 +991,19 @@ class RelationFn(torch.autograd.Function):
             dqv = gemm_f32out(dqpT, WswT[:, D:], B, Dq, D, transB=1)
             gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
         else:
-            parts = []
             dWz = torch.empty(H * D, D, dtype=torch.float32, device=dev)
             for src, lo, hi, dst in ((Sq, 0, D, dWq), (Sk, D, 2 * D, dWk), (Sf, 2 * D, W, dWz)):
                 gemm(dQKZ[:, lo:hi], src, hi - lo, D, M, transA=1, transB=1, C=dst)
-                parts.append(gemm_f32out(dQKZ[:, lo:hi], WqkzT[lo:hi], M, D, hi - lo, transB=1))
             for h in range(H):
                 call("copy_f32", dWz[h * D:(h + 1) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(), H * D, D, D)
+            # dSf = mask_q * (dQ Wq) + mask_k * (dK Wk) + dZ Wz: the three products are chained through the GEMM epilogue
+            # (dropout mask of the forward's query / key inputs, then "+ addend"), the last one writes the operand type
+            acc = torch.empty(M, D, dtype=torch.float32, device=dev)
             dSf = torch.empty(M, D, dtype=pc.T, device=dev)
-            drop_combine(parts, [drop.a(site0 + 2, drop.p_fc), drop.a(site0 + 3, drop.p_fc), (None, 0, 0.0)], M, D,
-                         outT=dSf)
+            gemm(dQKZ[:, 0:D], WqkzT[0:D], M, D, D, transB=1, C=acc, drop=drop.a(site0 + 2, drop.p_fc))
+            gemm(dQKZ[:, D:2 * D], WqkzT[D:2 * D], M, D, D, transB=1, addend=acc, C=acc, drop=drop.a(site0 + 3, drop.p_fc))
+            gemm(dQKZ[:, 2 * D:W], WqkzT[2 * D:W], M, D, W - 2 * D, transB=1, addend=acc,
+                 C=None if pc.bf16 else dSf, Cb=dSf if pc.bf16 else None)
             gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
             dbsw = colsum(dSf, M, D, out=_dst(kk["bsw"], (D,), dev))
             # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
