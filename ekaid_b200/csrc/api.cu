@@ -58,6 +58,8 @@ int ek_gate_fwd_launch(int, const float*, long long, int, void*, void*, void*, E
 int ek_gate_bwd_launch(int, const float*, const void*, const void*, long long, int, void*, EkDrop, EkDrop, cudaStream_t);
 int ek_build_vq_launch(int, const float*, const float*, const uint8_t*, long long, int, int, int, int, void*, EkDrop,
                        cudaStream_t);
+int ek_drop_fanout_launch(int, const void*, long long, EkDrop, EkDrop, long long, int, void*, void*, long long,
+                          cudaStream_t);
 int ek_drop_combine_launch(int, int, int, const void*, const void*, const void*, long long, EkDrop, EkDrop, EkDrop,
                            long long, int, float*, long long, int, void*, long long, cudaStream_t);
 int ek_rng_advance_launch(unsigned long long*, cudaStream_t);
@@ -319,6 +321,11 @@ int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, cons
   return ek_drop_combine_launch(in_bf16, out_bf16, nin, in0, in1, in2, ldi, mk_drop(seed, site0, p0),
                                 mk_drop(seed, site1, p1), mk_drop(seed, site2, p2), M, C, outf, ldf, accumulate, outT,
                                 ldo, ST);
+}
+int ekaid_drop_fanout(int is_bf16, const void* in, int64_t ldi, const uint64_t* seed, uint32_t site0, float p0,
+                      uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* stream) {
+  return ek_drop_fanout_launch(is_bf16, in, ldi, mk_drop(seed, site0, p0), mk_drop(seed, site1, p1), M, C, out0, out1, ldo,
+                               ST);
 }
 int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const float* w, const float* b,
                        const float* Xc, float* att, float* attended, void* stream) {

@@ -520,6 +520,30 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
     }
   }
 }
+// out0 = mult_0 * in, out1 = mult_1 * in (two independent dropout sites on the same tensor: the query and key inputs of
+// a relation layer, graph_att_layer.py:77,89 through fc.py:25-32); index m*C + c; 4 columns per thread.
+template <typename T>
+__global__ void drop_fanout_kernel(const T* __restrict__ in, long long ldi, EkDrop d0, EkDrop d1, long long M, int C,
+                                   T* __restrict__ out0, T* __restrict__ out1, long long ldo) {
+  ek_pdl_prologue();
+  const int CV = C / 4;
+  const long long total = M * CV;
+  const unsigned long long s0 = ek_seed(d0), s1 = ek_seed(d1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long m = t / CV;
+    const int c = (int)(t % CV) * 4;
+    const unsigned long long e0 = (unsigned long long)m * C + c;
+    float x[4], m0[4], m1[4], a[4], b[4];
+    load_vec<T, 4>(in + m * ldi + c, x);
+    ek_drop_multv<4>(d0, s0, e0, m0);
+    ek_drop_multv<4>(d1, s1, e0, m1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[k] = x[k] * m0[k]; b[k] = x[k] * m1[k]; }
+    store_vec<T, 4>(out0 + m * ldo + c, a);
+    store_vec<T, 4>(out1 + m * ldo + c, b);
+  }
+}
+
 // ---------------------------------------------------------------- legacy weight_norm(dim=None) (fc.py:33-34)
 // w = v * g / ||v||_F.  Two launches forward (partials; scale) and two backward, all deterministic.
 constexpr int WN_BLOCKS = 128;
@@ -917,6 +941,19 @@ int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, 
   const bool v4 = (C % 4 == 0) && (ldi % 4 == 0) && (!outf || ldf % 4 == 0) && (!outT || ldo % 4 == 0) && (ptrs & 15) == 0;
   if (v4) drop_combine_dispatch<4>(in_bf16, out_bf16, nin, in0, in1, in2, ldi, d0, d1, d2, M, C, outf, ldf, accumulate, outT, ldo, st);
   else drop_combine_dispatch<1>(in_bf16, out_bf16, nin, in0, in1, in2, ldi, d0, d1, d2, M, C, outf, ldf, accumulate, outT, ldo, st);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_drop_fanout_launch(int is_bf16, const void* in, long long ldi, EkDrop d0, EkDrop d1, long long M, int C, void* out0,
+                          void* out1, long long ldo, cudaStream_t st) {
+  const uintptr_t ptrs = (uintptr_t)in | (uintptr_t)out0 | (uintptr_t)out1;
+  EK_REQUIRE(C % 4 == 0 && ldi % 4 == 0 && ldo % 4 == 0 && (ptrs & 15) == 0, EK_ERR_ALIGN,
+             "drop_fanout: C=%d and the pitches must be multiples of 4, pointers 16-byte aligned", C);
+  const int g = grid_for(M * (C / 4));
+  if (is_bf16)
+    ek_launch(drop_fanout_kernel<bf16>, g, 256, 0, st, (const bf16*)in, ldi, d0, d1, M, C, (bf16*)out0, (bf16*)out1, ldo);
+  else
+    ek_launch(drop_fanout_kernel<float>, g, 256, 0, st, (const float*)in, ldi, d0, d1, M, C, (float*)out0, (float*)out1, ldo);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

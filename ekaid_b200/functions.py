@@ -663,8 +663,8 @@ class QuestionFn(torch.autograd.Function):
             colsum(dpre, L * B, H, out=db1)
         dw2 = dw2.view(1, H)
         if don:
-            tmp = gemm_f32out(dpre, W1T, L * B, H, H, transB=1)
-            drop_combine([tmp], [drop.a(10, drop.p_fc)], L * B, H, outf=dHs, accumulate=1)
+            # dHs += mask * (dpre W1): dropout mask of W1's input and the accumulation, both in the GEMM epilogue
+            gemm(dpre, W1T, L * B, H, H, transB=1, addend=dHs, C=dHs, drop=drop.a(10, drop.p_fc))
         else:
             gemm(dpre, W1T, L * B, H, H, transB=1, addend=dHs, C=dHs)     # dHs += dpre W1
         # BPTT
@@ -878,8 +878,8 @@ class RelationFn(torch.autograd.Function):
             Sf, _ = gemm_T(pc, XT, WswT, M, D, D + Dq, bias=bswc)
             Sq = torch.empty(M, D, dtype=pc.T, device=dev)
             Sk = torch.empty(M, D, dtype=pc.T, device=dev)
-            drop_combine([Sf], [drop.a(site0 + 2, drop.p_fc)], M, D, outT=Sq)
-            drop_combine([Sf], [drop.a(site0 + 3, drop.p_fc)], M, D, outT=Sk)
+            call("drop_fanout", pc.f, Sf.data_ptr(), Sf.stride(0), drop.seed, site0 + 2, float(drop.p_fc), site0 + 3,
+                 float(drop.p_fc), M, D, Sq.data_ptr(), Sk.data_ptr(), D)
             QKZ = torch.empty(M, W, dtype=pc.T, device=dev)
             for src, lo, hi in ((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W)):
                 out = QKZ[:, lo:hi]

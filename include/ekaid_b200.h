@@ -256,6 +256,10 @@ int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, cons
                        int64_t ldi, const uint64_t* seed, uint32_t site0, float p0, uint32_t site1, float p1,
                        uint32_t site2, float p2, int64_t M, int C, float* outf, int64_t ldf, int accumulate,
                        void* outT, int64_t ldo, void* stream);
+/* out0 = mult(site0) * in, out1 = mult(site1) * in: two independent dropout sites on one tensor in the operand type (the
+ * query and key inputs of a relation layer in train mode); index m*C + c */
+int ekaid_drop_fanout(int is_bf16, const void* in, int64_t ldi, const uint64_t* seed, uint32_t site0, float p0,
+                      uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* stream);
 
 /* ---- optimizer (utils/utils.py:96-99 -> torch.optim.Adam semantics) -------------------------------------- */
 /* pow_state: device float[2] = {beta1^t, beta2^t}; call ekaid_adam_advance once per step before the updates */
