@@ -94,6 +94,8 @@ int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
 int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
 int ek_geom_bias_bwd_parts();
+int ek_colsum_many_launch(int, const int*, const void* const*, const long long*, long long, const int*, float* const*, float*,
+                          cudaStream_t);
 int ek_cast_many_launch(int, const void* const*, const long long*, void* const*, const long long*, const long long*,
                         const int*, const int*, cudaStream_t);
 int ek_small_linear_launch(const float*, long long, int, int, const float*, const float*, int, float*, cudaStream_t);
@@ -281,6 +283,10 @@ int ekaid_gate_bwd(int is_bf16, const float* dCAT, const void* ctx, const void* 
 }
 int ekaid_wn_fwd(const float* v, const float* g, int64_t n, float* w, float* norm_out, float* workspace, void* stream) {
   return ek_wn_fwd_launch(v, g, n, w, norm_out, workspace, ST);
+}
+int ekaid_colsum_many(int count, const int32_t* is_bf16, const void* const* src, const int64_t* ld, int64_t M,
+                      const int32_t* N, float* const* out, float* workspace, void* stream) {
+  return ek_colsum_many_launch(count, is_bf16, src, (const long long*)ld, M, N, out, workspace, ST);
 }
 int ekaid_cast_many(int count, const void* const* src, const int64_t* lds, void* const* dst, const int64_t* ldd,
                     const int64_t* rows, const int32_t* cols, const int32_t* mode, void* stream) {

@@ -176,6 +176,112 @@ colsum_kernel(const T* __restrict__ src, long long ld, long long M, int N, const
   }
 }
 
+// Several column sums over the same number of rows in ONE launch (blockIdx.z = job): the bias gradients of a relation
+// layer (query, key, self_weights, out-projection).  Same scheme as colsum_kernel with 128 columns per block for both
+// operand types; job j uses tickets [j*1024, (j+1)*1024) and partials [(CSM_MAX + j*64*... see launcher].
+constexpr int CSM_MAX = 8;
+struct ColsumMany {
+  const void* src[CSM_MAX];
+  float* out[CSM_MAX];
+  long long ld[CSM_MAX];
+  int N[CSM_MAX];
+  int is_bf16[CSM_MAX];
+  int vec_ok[CSM_MAX];
+  long long part_off[CSM_MAX];     // float offset of the job's partial sums in the workspace
+};
+__global__ void __launch_bounds__(256)
+colsum_many_kernel(ColsumMany t, long long M, int nparts, float* workspace) {
+  ek_pdl_prologue();
+  constexpr int VEC = 4, CB = 128;
+  __shared__ float red[8][CB + 1];
+  __shared__ int is_last;
+  const int j = blockIdx.z;
+  const int N = t.N[j];
+  if (blockIdx.x * CB >= N) return;                    // this job has fewer column blocks than the widest one
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * CB + lane * VEC;
+  const long long ld = t.ld[j];
+  unsigned int* tickets = (unsigned int*)workspace + (size_t)j * 1024;
+  float* part = workspace + t.part_off[j];
+  const long long rows_per = (M + nparts - 1) / nparts;
+  const long long r0 = (long long)blockIdx.y * rows_per;
+  const long long r1 = (r0 + rows_per < M) ? r0 + rows_per : M;
+  float s[VEC] = {0.f, 0.f, 0.f, 0.f};
+  if (t.is_bf16[j]) {
+    const bf16* src = (const bf16*)t.src[j];
+    if (t.vec_ok[j] && n0 + VEC <= N) {
+#pragma unroll 4
+      for (long long m = r0 + ty; m < r1; m += 8) {
+        float x[4];
+        load_vec<bf16, 4>(src + m * ld + n0, x);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] += x[v];
+      }
+    } else {
+      for (long long m = r0 + ty; m < r1; m += 8)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if (n0 + v < N) s[v] += __bfloat162float(src[m * ld + n0 + v]);
+    }
+  } else {
+    const float* src = (const float*)t.src[j];
+    if (t.vec_ok[j] && n0 + VEC <= N) {
+#pragma unroll 4
+      for (long long m = r0 + ty; m < r1; m += 8) {
+        const float4 x = *(const float4*)(src + m * ld + n0);
+        s[0] += x.x; s[1] += x.y; s[2] += x.z; s[3] += x.w;
+      }
+    } else {
+      for (long long m = r0 + ty; m < r1; m += 8)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if (n0 + v < N) s[v] += src[m * ld + n0 + v];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[ty][lane * VEC + v] = s[v];
+  __syncthreads();
+  for (int c = threadIdx.x; c < CB; c += 256) {
+    const int n = blockIdx.x * CB + c;
+    if (n < N) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a += red[k][c];
+      part[(size_t)blockIdx.y * N + n] = a;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(tickets + blockIdx.x, 1u);
+    is_last = (ticket == (unsigned int)nparts - 1u);
+    if (is_last) tickets[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    float a[VEC] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int p = ty; p < nparts; p += 8)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (n0 + v < N) a[v] += __ldcg(part + (size_t)p * N + n0 + v);
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) red[ty][lane * VEC + v] = a[v];
+    __syncthreads();
+    for (int c = threadIdx.x; c < CB; c += 256) {
+      const int n = blockIdx.x * CB + c;
+      if (n < N) {
+        float b = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b += red[k][c];
+        t.out[j][n] = b;
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- row flags for quirk Q10
 __global__ void row_zero_flags_kernel(const float* __restrict__ X, long long M, int D, uint8_t* __restrict__ flags) {
   ek_pdl_prologue();
@@ -795,6 +901,31 @@ int ek_colsum_launch(int is_bf16, const void* src, long long ld, long long M, in
   else
     ek_launch(colsum_kernel<float, 4>, dim3(ek_div_up(N, 128), nparts), 256, 0, st, (const float*)src, ld, M, N, rowscale,
               part, nparts, tickets, out, vec_ok);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+// workspace >= count * (1024 + 64 * Nmax) floats (Nmax = widest job); the first count*1024 words are ticket counters
+// (zero between calls).  All jobs sum over the same M rows.
+int ek_colsum_many_launch(int count, const int* is_bf16, const void* const* src, const long long* ld, long long M,
+                          const int* N, float* const* out, float* workspace, cudaStream_t st) {
+  EK_REQUIRE(count >= 1 && count <= CSM_MAX, EK_ERR_SHAPE, "colsum_many: count=%d not in [1,%d]", count, CSM_MAX);
+  ColsumMany t = {};
+  int nmax = 0;
+  for (int j = 0; j < count; ++j) {
+    EK_REQUIRE(N[j] > 0 && N[j] <= 32 * 1024, EK_ERR_SHAPE, "colsum_many: N[%d]=%d", j, N[j]);
+    if (N[j] > nmax) nmax = N[j];
+  }
+  int nparts = (int)((M + 31) / 32);
+  if (nparts > 64) nparts = 64;
+  if (nparts < 1) nparts = 1;
+  for (int j = 0; j < count; ++j) {
+    const int es = is_bf16[j] ? 2 : 4;
+    t.src[j] = src[j]; t.out[j] = out[j]; t.ld[j] = ld[j]; t.N[j] = N[j]; t.is_bf16[j] = is_bf16[j];
+    t.vec_ok[j] = (((uintptr_t)src[j] & 15) == 0 && (ld[j] * es) % 16 == 0) ? 1 : 0;
+    t.part_off[j] = (long long)count * 1024 + (long long)j * 64 * nmax;
+  }
+  ek_launch(colsum_many_kernel, dim3(ek_div_up(nmax, 128), nparts, count), 256, 0, st, t, M, nparts, workspace);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

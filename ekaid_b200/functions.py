@@ -235,6 +235,28 @@ def _colsum_ws(dev, N):
     return ws
 
 
+def colsum_many(jobs, M) -> None:
+    """[(src 2-D view [M, N_j], out fp32 [N_j])]: all column sums in ONE launch (deterministic)."""
+    n = len(jobs)
+    dev = jobs[0][0].device
+    nmax = max(s_.shape[1] for s_, _ in jobs)
+    key = ("many", str(dev), torch.cuda.current_stream().cuda_stream)
+    need = n * (1024 + 64 * nmax)
+    ws = _colsum_bufs.get(key)
+    if ws is None or ws.numel() < need:
+        if ws is not None:
+            _colsum_bufs.setdefault("retired", []).append(ws)
+        ws = torch.zeros(max(need, 8 * (1024 + 64 * 6144)), dtype=torch.float32, device=dev)
+        _colsum_bufs[key] = ws
+    isb = (ctypes.c_int32 * n)(*[1 if s_.dtype == torch.bfloat16 else 0 for s_, _ in jobs])
+    ps = (ctypes.c_void_p * n)(*[s_.data_ptr() for s_, _ in jobs])
+    ld = (ctypes.c_int64 * n)(*[s_.stride(0) for s_, _ in jobs])
+    ns = (ctypes.c_int32 * n)(*[s_.shape[1] for s_, _ in jobs])
+    po = (ctypes.c_void_p * n)(*[o.data_ptr() for _, o in jobs])
+    call("colsum_many", n, ctypes.addressof(isb), ctypes.addressof(ps), ctypes.addressof(ld), M, ctypes.addressof(ns),
+         ctypes.addressof(po), ws.data_ptr())
+
+
 def colsum(src, M, N, rowscale=None, out=None):
     """out[n] = sum_m rowscale[m] * src[m, n]  (fp32 result)."""
     if out is None:
@@ -937,7 +959,7 @@ class RelationFn(torch.autograd.Function):
              2.0 / (1.0 - drop.p_gat) if don else 2.0, ptr(Phl),
              info={"bytes": G * (N * D * (4 + 1 + 4) + N * H * Kn * 4 * (1 + ns) + 2 * Kn * H * D * es)})
         kk = ctx.keys
-        dbout = colsum(dOut, M, D, out=_dst(kk["bout"], (D,), dev))
+        dbout = _dst(kk["bout"], (D,), dev)          # filled with the other bias gradients of the layer (colsum_many)
         dlb = dgb = None
         if kind == "explicit":
             dlb = torch.empty(H, G, N, Kn, dtype=torch.float32, device=dev)
@@ -964,8 +986,9 @@ class RelationFn(torch.autograd.Function):
             dp1 = _dst(kk["p1"], (H,), dev)
             dp1.copy_(tot[:, 64])
         Dq = qvT.shape[1]
-        dbq = colsum(dQKZ[:, :D], M, D, out=_dst(kk["bq"], (D,), dev))
-        dbk = colsum(dQKZ[:, D:2 * D], M, D, out=_dst(kk["bk"], (D,), dev))
+        dbq = _dst(kk["bq"], (D,), dev)
+        dbk = _dst(kk["bk"], (D,), dev)
+        dbsw = _dst(kk["bsw"], (D,), dev)
         dWo2 = _dst(kk["Wo2"], (D, H * D), dev)
         if don:
             dWq = torch.empty(D, D, dtype=torch.float32, device=dev)
@@ -982,7 +1005,7 @@ class RelationFn(torch.autograd.Function):
             dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
             # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
             gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
-            dbsw = colsum(dSf, M, D, out=_dst(kk["bsw"], (D,), dev))
+            colsum_many([(dOut, dbout), (dQKZ[:, :D], dbq), (dQKZ[:, D:2 * D], dbk), (dSf, dbsw)], M)   # one launch
             dqpart = torch.empty(B, D, dtype=torch.float32, device=dev)
             call("group_rowsum", pc.f, dSf.data_ptr(), dSf.stride(0), N, B, G // B, D, flags.data_ptr(),
                  dqpart.data_ptr())
@@ -1005,7 +1028,7 @@ class RelationFn(torch.autograd.Function):
             gemm(dQKZ[:, 2 * D:W], WqkzT[2 * D:W], M, D, W - 2 * D, transB=1, addend=acc,
                  C=None if pc.bf16 else dSf, Cb=dSf if pc.bf16 else None)
             gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
-            dbsw = colsum(dSf, M, D, out=_dst(kk["bsw"], (D,), dev))
+            colsum_many([(dOut, dbout), (dQKZ[:, :D], dbq), (dQKZ[:, D:2 * D], dbk), (dSf, dbsw)], M)   # one launch
             # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
             # (index = row * (D + Dq) + column); the node half also adds the residual gradient
             s1 = drop.a(site0 + 1, drop.p_fc)

@@ -107,6 +107,10 @@ int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64
  * 64*N floats; the first 1024 words are ticket counters: zero them once, every call leaves them zero again */
 int ekaid_colsum(int is_bf16, const void* src, int64_t ld, int64_t M, int N, const float* rowscale, float* out,
                  float* workspace, void* stream);
+/* up to 8 column sums over the same M rows in ONE launch.  is_bf16, src, ld, N, out are HOST arrays read at call time.
+ * workspace >= count * (1024 + 64 * max N) floats; its first count*1024 words are ticket counters (zero them once). */
+int ekaid_colsum_many(int count, const int32_t* is_bf16, const void* const* src, const int64_t* ld, int64_t M,
+                      const int32_t* N, float* const* out, float* workspace, void* stream);
 int ekaid_add_inplace(float* y, const float* x, int64_t n, void* stream);
 /* flags[m] = (sum_c X[m,c] == 0): the mask of q_expand_v_cat (relation_encoder.py:23-27) */
 int ekaid_row_zero_flags(const float* X, int64_t M, int D, uint8_t* flags, void* stream);

@@ -102,6 +102,18 @@ def test_colsum_rowflags_onehot():
     assert float((colsum(x, 777, 130, rowscale=sc) - (x * sc[:, None]).sum(0)).abs().max()) < 1e-3
     xb = x.to(torch.bfloat16)
     assert float((colsum(xb, 777, 130) - xb.float().sum(0)).abs().max()) < 1e-3
+    # several sums of different widths / operand types in one launch
+    from ekaid_b200.functions import colsum_many
+    a = torch.randn(700, 1024, device=dev)
+    b = torch.randn(700, 2048, device=dev).to(torch.bfloat16)
+    c = torch.randn(700, 130, device=dev)
+    outs = [torch.empty(1024, device=dev), torch.empty(1024, device=dev), torch.empty(1024, device=dev), torch.empty(130, device=dev)]
+    for _ in range(2):          # twice: the ticket counters must be back at zero
+        colsum_many([(a, outs[0]), (b[:, :1024], outs[1]), (b[:, 1024:], outs[2]), (c, outs[3])], 700)
+        assert float((outs[0] - a.sum(0)).abs().max()) < 1e-3
+        assert float((outs[1] - b[:, :1024].float().sum(0)).abs().max()) < 1e-3
+        assert float((outs[2] - b[:, 1024:].float().sum(0)).abs().max()) < 1e-3
+        assert float((outs[3] - c.sum(0)).abs().max()) < 1e-3
     # calls with different widths share one workspace (ticket counters must survive the partial sums of other widths)
     for n in (1024, 3072, 1, 6144, 33, 3072):
         y = torch.randn(60, n, device=dev)
