@@ -110,3 +110,34 @@ def test_golden_manifest_complete():
         assert os.path.exists(os.path.join(GOLDEN, c + ".npz")), c
     assert os.path.exists(os.path.join(GOLDEN, "make_golden.py"))
     json.load(open(os.path.join(GOLDEN, "state_dict_spec.json")))
+
+
+def test_checkpoint_layout_round_trip(tmp_path):
+    """train_mimic.py:283-287 checkpoint dict: written by the drop-in, read back strictly; a reference-shaped
+    state dict (golden spec) loads strictly too; a foreign file is refused."""
+    from ekaid_b200 import checkpoint as C
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    from ekaid_b200.synthetic import synthetic_state_dict
+    cfg = default_cfg("all")
+    with contextlib.redirect_stdout(io.StringIO()):
+        a = ChangeDetector(cfg, WORD_TO_IDX)
+        b = ChangeDetector(cfg, WORD_TO_IDX)
+    a.load_state_dict(synthetic_state_dict(spec_for("all"), 7), strict=True)
+    path = str(tmp_path / "checkpoint_10000.pt")
+    C.save_checkpoint(path, a, speaker=None, cfg=cfg)
+    ckpt = C.load_checkpoint(path)
+    assert set(C.KEYS) <= set(ckpt)
+    assert list(ckpt["change_detector_state"].keys()) == list(spec_for("all").keys())
+    C.restore(b, ckpt)
+    for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    assert ckpt["model_cfg"].model.change_detector.att_head == cfg.model.change_detector.att_head
+    with contextlib.redirect_stdout(io.StringIO()):
+        c = ChangeDetector(default_cfg("semantic"), WORD_TO_IDX)
+    with pytest.raises(RuntimeError):
+        C.restore(c, ckpt)                                  # graph='semantic' has no spatial/implicit encoders
+    other = str(tmp_path / "other.pt")
+    torch.save({"weights": 1}, other)
+    with pytest.raises(KeyError):
+        C.load_checkpoint(other)
