@@ -59,6 +59,20 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def gemm_traffic_profile(args):
+    """DRAM bytes per tcgen05 GEMM launch of the default workload, from the committed ncu capture of this command
+    (profiles/r01_v14_gemm_traffic.json, made by scripts/gemm_traffic.py); None for any other workload."""
+    p = os.path.join(ROOT, "profiles", "r01_v14_gemm_traffic.json")
+    default = (args.batch, args.nodes, args.mode, args.precision, args.graph, args.qlen) == (64, 52, "train", "bf16", "all", 20)
+    if not default or args.no_dropout or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    d["note"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d GEMM launches (%d per step) of "
+                 "`bench.py --steps 1 --warmup 1 --no-graph`: profiles/r01_v14_gemm_traffic.json"
+                 % (d["launches"], d["launches_per_step"]))
+    return d
+
+
 class ClockSampler:
     """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled in-process through NVML
     every 50 ms (an external `nvidia-smi -lms` loop was measured to slow a launch-heavy step several-fold)."""
@@ -381,6 +395,11 @@ def main():
         roof = {"kernel": "gemm_bf16_tc_kernel (tcgen05)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops_sustained"],
                 "traffic": None, "peak_kind": pk_kind + " sustained (kernel timed inside a long step)"}
+        roof["algorithmic_bytes"] = td["bytes"] / td["n"] if td["n"] else None
+        tr = gemm_traffic_profile(args)
+        if tr is not None:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["note"]
     else:
         ach = td["bytes"] / (td["ms"] * 1e-3) / 1e9 if td["bytes"] else 0.0
         roof = {"kernel": tname, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -71,6 +71,7 @@ int ek_att_pool_fwd_launch(const float*, long long, int, int, int, const float*,
 int ek_att_pool_bwd_launch(int, const float*, const float*, const float*, const float*, const float*, const float*,
                            long long, int, int, int, float*, void*, float*, float, cudaStream_t);
 int ek_onehot_adj_launch(const double*, int, int, int, int, float*, cudaStream_t);
+int ek_spatial_labels_launch(const double*, int, int, int, double, double, double*, cudaStream_t);
 int ek_adam_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, const float*,
                    int, cudaStream_t);
 int ek_adam_advance_launch(float*, float, float, cudaStream_t);
@@ -210,6 +211,11 @@ int ekaid_group_rowsum(int is_bf16, const void* src, int64_t ld, int N, int B, i
 int ekaid_onehot_adj(const double* labels, int B, int S, int N, int L, float* out, void* stream) {
   EK_REQUIRE(N <= S && L >= 1, EK_ERR_SHAPE, "onehot_adj: N=%d > S=%d", N, S);
   return ek_onehot_adj_launch(labels, B, S, N, L, out, ST);
+}
+int ekaid_spatial_labels(const double* boxes, int B, int N, int S, double lx, double ly, double* labels, void* stream) {
+  EK_REQUIRE(B >= 0 && N >= 0 && N <= S, EK_ERR_SHAPE, "spatial_labels: N=%d > S=%d", N, S);
+  EK_REQUIRE(lx + ly > 0, EK_ERR_SHAPE, "spatial_labels: image extent %g x %g", lx, ly);
+  return ek_spatial_labels_launch(boxes, B, N, S, lx, ly, labels, ST);
 }
 int ekaid_adj_prep_fwd(const float* adj0, const float* adj1, int g_split, const float* w, int G, int N, int Kn, int L,
                        float* cond, float* lbias, void* stream) {

@@ -494,6 +494,47 @@ __global__ void onehot_adj_kernel(const double* __restrict__ labels, int S, int 
   }
 }
 
+// ---------------------------------------------------------------- spatial adjacency labels from ROI boxes
+// bbox_relation_type / reverse_type / get_adj_matrix ("feature extraction/ana_bbox_generator.py":213-259,266-302,
+// 320-335): boxes f64 [B, N, 4] (xmin, ymin, xmax, ymax) -> labels f64 [B, S, S] (the HDF5 `image_adj_matrix` layout the
+// loader hands to process_matrix; rows / columns >= N are 0).  The reference evaluates the pair (i, j) for i <= j and
+// stores reverse_type at (j, i); one thread per entry does the same on its own pair, in double like the reference.
+__device__ __forceinline__ int box_relation_type(const double* a, const double* b, double far) {
+  if (a[0] < b[0] && a[1] < b[1] && a[2] > b[2] && a[3] > b[3]) return 1;
+  if (a[0] > b[0] && a[1] > b[1] && a[2] < b[2] && a[3] < b[3]) return 2;
+  const double iw = fmax(fmin(a[2], b[2]) - fmax(a[0], b[0]) + 1., 0.);
+  const double ih = fmax(fmin(a[3], b[3]) - fmax(a[1], b[1]) + 1., 0.);
+  const double inter = iw * ih;
+  const double uni = (a[2] - a[0] + 1.) * (a[3] - a[1] + 1.) + (b[2] - b[0] + 1.) * (b[3] - b[1] + 1.) - inter;
+  if (inter / uni >= 0.5) return 3;
+  const double dx = (b[2] + b[0]) / 2 - (a[2] + a[0]) / 2, dy = (b[3] + b[1]) / 2 - (a[3] + a[1]) / 2;
+  if (sqrt(dx * dx + dy * dy) >= far) return 0;
+  double ang = atan2(dy, dx) / 3.141592653589793 * 180.;
+  if (ang < 0) ang += 360.;
+  return (int)ceil(ang / 45.) + 3;
+}
+__global__ void spatial_labels_kernel(const double* __restrict__ boxes, int N, int S, double far, long long total,
+                                      double* __restrict__ labels) {
+  ek_pdl_prologue();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / ((long long)S * S);
+    const int ij = (int)(e % ((long long)S * S));
+    const int i = ij / S, j = ij % S;
+    int t = 0;
+    if (i < N && j < N) {
+      const double* bb = boxes + b * N * 4;
+      double lo[4], hi[4];
+      const int a = min(i, j), c = max(i, j);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { lo[q] = bb[a * 4 + q]; hi[q] = bb[c * 4 + q]; }
+      t = box_relation_type(lo, hi, far);
+      if (i > j) t = (t == 1) ? 2 : (t == 2) ? 1 : (t >= 8) ? t - 4 : (t >= 4) ? t + 4 : t;   // reverse_type
+    }
+    labels[e] = (double)t;
+  }
+}
+
 // ---------------------------------------------------------------- Adam (utils/utils.py:96-99 -> torch.optim.Adam)
 __device__ __forceinline__ void adam_one(float& pv, float gr, float& mv, float& vv, float lr_bc1, float rs_bc2, float b1,
                                          float b2, float eps, float wd) {
@@ -1001,6 +1042,15 @@ int ek_att_pool_bwd_launch(int is_bf16, const float* dA, const float* dattw, con
   else
     ek_launch(att_pool_bwd_kernel<float>, ek_div_up(M, 8), 256, 0, st, dA, dattw, att, Xc, E, w, M, N, D, dim, dXc,
                                                                  (float*)dE, dpre, escale);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_spatial_labels_launch(const double* boxes, int B, int N, int S, double lx, double ly, double* labels,
+                             cudaStream_t st) {
+  const long long total = (long long)B * S * S;
+  if (total == 0) return EK_OK;
+  ek_launch(spatial_labels_kernel, grid_for(total), 256, 0, st, boxes, N, S, (lx + ly) / 3., total, labels);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -126,7 +126,10 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
     ep.Cb = ptr(Cb)
     ep.ldcb = Cb.stride(0) if Cb is not None else 0
     assert A.dtype == B.dtype and A.stride(-1) == 1 and B.stride(-1) == 1
-    info = {"flops": 2.0 * M * N * K, "shape": (M, N, K, transA, transB)}
+    # algorithmic bytes: both operands once, every output once, the epilogue addend once
+    nbytes = A.element_size() * (M * K + K * N) + M * N * ((4 if C is not None else 0) + (2 if Cb is not None else 0) +
+                                                          (addend.element_size() if addend is not None else 0))
+    info = {"flops": 2.0 * M * N * K, "bytes": float(nbytes), "shape": (M, N, K, transA, transB)}
     if A.dtype == torch.bfloat16:
         call("gemm_bf16", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
              ctypes.addressof(ep), force_bn, splits, info=info)
@@ -1142,6 +1145,24 @@ class FusionFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # step glue
 # ------------------------------------------------------------------------------------------------
+def spatial_labels(boxes: torch.Tensor, size: int = 100, lx: float = 1024.0, ly: float = 1024.0) -> torch.Tensor:
+    """get_adj_matrix / bbox_relation_type ("feature extraction/ana_bbox_generator.py":266-302,320-335) as one kernel:
+    boxes [B,N,4] (xmin,ymin,xmax,ymax, any real dtype) on the device -> float64 labels [B,S,S], S = max(size, N),
+    the layout the loader hands to process_matrix / `onehot_adj`."""
+    lib.require_device()
+    if boxes.dim() != 3 or boxes.shape[-1] != 4:
+        raise ValueError("spatial_labels: boxes must be [B, N, 4], got %s" % (tuple(boxes.shape),))
+    bb = boxes.detach()
+    if bb.dtype != torch.float64:
+        bb = bb.double()
+    bb = bb.contiguous()
+    Bn, N = bb.shape[0], bb.shape[1]
+    S = max(int(size), N)
+    out = torch.empty(Bn, S, S, dtype=torch.float64, device=bb.device)
+    call("spatial_labels", bb.data_ptr(), Bn, N, S, float(lx), float(ly), out.data_ptr())
+    return out
+
+
 def onehot_adj(labels: torch.Tensor, num_objects: int, label_num: int) -> torch.Tensor:
     """process_matrix (utils/mimic_utils.py:141-149) as one kernel: labels [B,S,S] (any real dtype) on the device
     -> fp32 one-hot [B,N,N,L]."""

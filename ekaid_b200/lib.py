@@ -50,7 +50,7 @@ def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[str]]]:
 
 
 _CT = {"int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint32_t": ctypes.c_uint32,
-       "float": ctypes.c_float,
+       "float": ctypes.c_float, "double": ctypes.c_double,
        "ptr": ctypes.c_void_p}
 
 _lib = None

@@ -121,6 +121,11 @@ int ekaid_group_rowsum(int is_bf16, const void* src, int64_t ld, int N, int B, i
 /* process_matrix / torch_broadcast_adj_matrix (utils/mimic_utils.py:119-149): float64 labels [B,S,S] ->
  * one-hot fp32 [B,N,N,L] in ONE launch (the reference loops over labels with a host sync each) */
 int ekaid_onehot_adj(const double* labels, int B, int S, int N, int L, float* out, void* stream);
+/* bbox_relation_type / reverse_type / get_adj_matrix ("feature extraction/ana_bbox_generator.py":266-302,320-335):
+ * boxes f64 [B,N,4] (xmin,ymin,xmax,ymax) -> spatial labels f64 [B,S,S] in the HDF5 `image_adj_matrix` layout
+ * (0 = far, 1 inside, 2 cover, 3 IoU >= 0.5, 4..11 = 45-degree sector; entry (j,i), j > i, = reverse_type of (i,j);
+ * rows / columns >= N are 0).  lx, ly: image extent (1024 x 1024 in the reference); "far" = (lx+ly)/3 */
+int ekaid_spatial_labels(const double* boxes, int B, int N, int S, double lx, double ly, double* labels, void* stream);
 
 /* ---- relation-aware graph attention (models/graph_att.py:53-106, models/graph_att_layer.py:60-178) ------- */
 /* cond[g,i,j] = sum_c adj[g,j,i,c], lbias[g,i,j] = sum_c adj[g,j,i,c] w[c]   (graph_att.py:76,88-92; Q2,Q5) */

@@ -249,6 +249,46 @@ def process_matrix(adj: Tensor, num_objects: int, label_num: int) -> Tensor:
     return torch.stack([(a == i).to(torch.float32) for i in range(1, label_num + 1)], 3)
 
 
+def spatial_adj_matrix(boxes, size: int = 100, lx: float = 1024.0, ly: float = 1024.0) -> Tensor:
+    """get_adj_matrix with bbox_relation_type / reverse_type ("feature extraction/ana_bbox_generator.py":213-259,
+    266-302,320-335), scalar double arithmetic pair by pair like the reference: boxes [B,N,4] -> int64 [B,S,S],
+    S = max(size, N).  Pinned by tests/golden/spatial_labels.npz (made by the reference's own functions)."""
+    import math
+    bb = torch.as_tensor(boxes, dtype=torch.float64).tolist()
+    n = len(bb[0]) if bb else 0
+    S = max(size, n)
+    out = torch.zeros(len(bb), S, S, dtype=torch.int64)
+    rev = (0, 2, 1, 3, 8, 9, 10, 11, 4, 5, 6, 7)
+
+    def rel(a, b):
+        if a[0] < b[0] and a[1] < b[1] and a[2] > b[2] and a[3] > b[3]:
+            return 1
+        if a[0] > b[0] and a[1] > b[1] and a[2] < b[2] and a[3] < b[3]:
+            return 2
+        iw = max(min(a[2], b[2]) - max(a[0], b[0]) + 1.0, 0.0)
+        ih = max(min(a[3], b[3]) - max(a[1], b[1]) + 1.0, 0.0)
+        inter = iw * ih
+        uni = (a[2] - a[0] + 1.0) * (a[3] - a[1] + 1.0) + (b[2] - b[0] + 1.0) * (b[3] - b[1] + 1.0) - inter
+        if inter / uni >= 0.5:
+            return 3
+        dx = (b[2] + b[0]) / 2 - (a[2] + a[0]) / 2
+        dy = (b[3] + b[1]) / 2 - (a[3] + a[1]) / 2
+        if math.sqrt(dx * dx + dy * dy) >= (lx + ly) / 3:
+            return 0
+        ang = math.atan2(dy, dx) / math.pi * 180
+        if ang < 0:
+            ang += 360
+        return math.ceil(ang / 45) + 3
+
+    for k, boxes_k in enumerate(bb):
+        for i in range(n):
+            for j in range(i, n):
+                t = rel(boxes_k[i], boxes_k[j])
+                out[k, i, j] = t
+                out[k, j, i] = rev[t]
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # answer decoder (boundary consumer) -- greedy decode used for the arg-max token parity check
 # ----------------------------------------------------------------------------------------------

@@ -130,6 +130,32 @@ def test_colsum_rowflags_onehot():
         assert torch.equal(got.cpu(), O.process_matrix(b[idx], 52, L))
 
 
+def test_spatial_labels_from_boxes_golden_and_oracle():
+    """ekaid_spatial_labels == the reference's get_adj_matrix (golden fixture, decision-boundary boxes included) and ==
+    the oracle on seeded loader boxes; padding rows / columns are zero; feeds onehot_adj directly."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from ekaid_b200.functions import onehot_adj, spatial_labels
+    from ekaid_b200.synthetic import synthetic_batch
+    dev = _dev()
+    z = np.load(os.path.join(GOLDEN, "spatial_labels.npz"))
+    for k in range(5):
+        bb = torch.from_numpy(z["boxes%d" % k])
+        want = torch.from_numpy(z["labels%d" % k].astype(np.int64))
+        got = spatial_labels(bb.to(dev))
+        assert got.dtype == torch.float64 and got.shape == want.shape
+        assert torch.equal(got.cpu().long(), want), k
+    b = synthetic_batch(2, 60, seed=21)
+    got = spatial_labels(b[10].to(dev), size=100)
+    assert torch.equal(got.cpu().long(), O.spatial_adj_matrix(b[10]))
+    assert torch.equal(got.cpu(), b[6])                      # the loader's own labels for these boxes
+    assert torch.equal(onehot_adj(got, 60, 11).cpu(), O.process_matrix(b[6], 60, 11))
+    assert spatial_labels(torch.zeros(0, 52, 4, device=dev)).shape == (0, 100, 100)
+    with pytest.raises(ValueError):
+        spatial_labels(torch.zeros(2, 52, 3, device=dev))
+
+
 def test_adam_matches_torch():
     from ekaid_b200.lib import call
     dev = _dev()

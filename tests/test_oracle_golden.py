@@ -1,12 +1,14 @@
 """The CPU oracle (oracle/ekaid_oracle.py) against golden vectors produced by the reference itself
 (tests/golden/make_golden.py).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import ekaid_oracle as O
 from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
-from helpers import (CASES, OUT_NAMES, case_inputs, check_fixture_inputs, grad_summary, load_case, loss_weights,
+from helpers import (CASES, GOLDEN, OUT_NAMES, case_inputs, check_fixture_inputs, grad_summary, load_case, loss_weights,
                      oracle_forward, rel_err, speaker_spec, checksum)
 
 
@@ -75,3 +77,18 @@ def test_process_matrix_fixture():
     assert np.array_equal(ps.sum((0, 3)).numpy(), z["sem_sum"])
     np.testing.assert_allclose(checksum(pm), z["spa_chk"])
     np.testing.assert_allclose(checksum(ps), z["sem_chk"])
+
+
+def test_spatial_labels_fixture():
+    """Spatial adjacency labels from boxes: the oracle's scalar restatement and the loader's vectorised rule against
+    labels produced by the reference's own get_adj_matrix (tests/golden/make_spatial_golden.py)."""
+    from ekaid_b200.synthetic import spatial_labels_from_boxes
+    z = np.load(os.path.join(GOLDEN, "spatial_labels.npz"))
+    for k in range(5):
+        bb = torch.from_numpy(z["boxes%d" % k])
+        want = torch.from_numpy(z["labels%d" % k].astype(np.int64))
+        n = bb.shape[1]
+        assert want.shape[1] == max(100, n) and int(want[:, n:].abs().sum()) == 0 and int(want[:, :, n:].abs().sum()) == 0
+        assert torch.equal(O.spatial_adj_matrix(bb), want), k
+        assert torch.equal(spatial_labels_from_boxes(bb), want[:, :n, :n]), k
+    assert O.spatial_adj_matrix(torch.zeros(0, 5, 4)).shape == (0, 100, 100)
