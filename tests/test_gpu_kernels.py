@@ -136,6 +136,7 @@ def test_spatial_labels_from_boxes_golden_and_oracle():
     import os
     import numpy as np
     from helpers import GOLDEN
+    from oracle import ekaid_oracle as O
     from ekaid_b200.functions import onehot_adj, spatial_labels
     from ekaid_b200.synthetic import synthetic_batch
     dev = _dev()
