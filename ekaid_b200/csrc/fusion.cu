@@ -504,11 +504,14 @@ __device__ __forceinline__ int box_relation_type(const double* a, const double* 
   if (a[0] > b[0] && a[1] > b[1] && a[2] < b[2] && a[3] < b[3]) return 2;
   const double iw = fmax(fmin(a[2], b[2]) - fmax(a[0], b[0]) + 1., 0.);
   const double ih = fmax(fmin(a[3], b[3]) - fmax(a[1], b[1]) + 1., 0.);
-  const double inter = iw * ih;
-  const double uni = (a[2] - a[0] + 1.) * (a[3] - a[1] + 1.) + (b[2] - b[0] + 1.) * (b[3] - b[1] + 1.) - inter;
+  // __dmul_rn / __dadd_rn: products and sums rounded separately like the reference's Python floats (no FMA contraction),
+  // so the IoU >= 0.5 and distance >= far decisions see the same doubles
+  const double inter = __dmul_rn(iw, ih);
+  const double uni = __dadd_rn(__dadd_rn(__dmul_rn(a[2] - a[0] + 1., a[3] - a[1] + 1.),
+                                         __dmul_rn(b[2] - b[0] + 1., b[3] - b[1] + 1.)), -inter);
   if (inter / uni >= 0.5) return 3;
   const double dx = (b[2] + b[0]) / 2 - (a[2] + a[0]) / 2, dy = (b[3] + b[1]) / 2 - (a[3] + a[1]) / 2;
-  if (sqrt(dx * dx + dy * dy) >= far) return 0;
+  if (sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) >= far) return 0;
   double ang = atan2(dy, dx) / 3.141592653589793 * 180.;
   if (ang < 0) ang += 360.;
   return (int)ceil(ang / 45.) + 3;

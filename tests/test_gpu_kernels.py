@@ -157,6 +157,27 @@ def test_spatial_labels_from_boxes_golden_and_oracle():
         spatial_labels(torch.zeros(2, 52, 3, device=dev))
 
 
+def test_spatial_labels_full_size_properties():
+    """Inference-config size (512 pairs) and the stress graph (126 nodes): the kernel against the loader's vectorised
+    rule, plus the size-independent properties of get_adj_matrix: self edges are label 3 (IoU = 1), entry (j,i) is
+    reverse_type of (i,j), containment is antisymmetric (1 <-> 2), padding is zero."""
+    from ekaid_b200.functions import spatial_labels
+    from ekaid_b200.synthetic import _REVERSE, spatial_labels_from_boxes, synthetic_batch
+    dev = _dev()
+    for B, N in ((512, 52), (64, 126)):
+        bb = synthetic_batch(B, N, seed=77)[10]
+        got = spatial_labels(bb.to(dev)).cpu().long()
+        S = max(100, N)
+        assert got.shape == (B, S, S)
+        lab = got[:, :N, :N]
+        assert torch.equal(lab, spatial_labels_from_boxes(bb))
+        assert int(got[:, N:].abs().sum()) == 0 and int(got[:, :, N:].abs().sum()) == 0
+        assert bool((lab.diagonal(dim1=1, dim2=2) == 3).all())
+        upper = torch.triu(torch.ones(N, N, dtype=torch.bool), 1)
+        assert torch.equal(lab.transpose(1, 2)[:, upper], _REVERSE[lab[:, upper]])
+        assert int(lab.min()) >= 0 and int(lab.max()) <= 11
+
+
 def test_adam_matches_torch():
     from ekaid_b200.lib import call
     dev = _dev()
