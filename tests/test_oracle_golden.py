@@ -92,3 +92,25 @@ def test_spatial_labels_fixture():
         assert torch.equal(O.spatial_adj_matrix(bb), want), k
         assert torch.equal(spatial_labels_from_boxes(bb), want[:, :n, :n]), k
     assert O.spatial_adj_matrix(torch.zeros(0, 5, 4)).shape == (0, 100, 100)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_spatial_labels_scalar_vs_vectorised_on_integer_boxes(seed):
+    """Integer box coordinates put many pairs exactly on the decision boundaries (shared edges, equal centres, exact
+    45-degree diagonals): the scalar restatement of get_adj_matrix and the loader's vectorised rule must agree there
+    too, and the reverse_type / self-edge properties hold."""
+    from ekaid_b200.synthetic import _REVERSE, spatial_labels_from_boxes
+    g = torch.Generator().manual_seed(seed)
+    lo = torch.randint(0, 40, (2, 24, 2), generator=g) * 16
+    wh = torch.randint(0, 12, (2, 24, 2), generator=g) * 16
+    bb = torch.cat([lo, lo + wh], 2).double()
+    bb[0, 3] = bb[0, 2]                                   # identical boxes
+    bb[1, 5] = 0                                          # a missing detection (all-zero box)
+    want = O.spatial_adj_matrix(bb, size=30)
+    assert want.shape == (2, 30, 30)
+    lab = spatial_labels_from_boxes(bb)
+    assert torch.equal(lab, want[:, :24, :24])
+    assert bool((lab.diagonal(dim1=1, dim2=2) == 3).all())
+    upper = torch.triu(torch.ones(24, 24, dtype=torch.bool), 1)
+    assert torch.equal(lab.transpose(1, 2)[:, upper], _REVERSE[lab[:, upper]])
+    assert len(torch.unique(lab)) >= 8                    # the draw exercises most label values
