@@ -141,3 +141,35 @@ def test_checkpoint_layout_round_trip(tmp_path):
     torch.save({"weights": 1}, other)
     with pytest.raises(KeyError):
         C.load_checkpoint(other)
+
+
+def test_product_never_imports_the_oracle_or_reads_the_reference():
+    """The oracle is test infrastructure: nothing under ekaid_b200/ may import it, and nothing the GPU box runs
+    (package, bench.py, __graft_entry__.py, GPU tests) may read /root/reference at run time."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ekaid_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (fn, names)
+    runtime = [os.path.join(pkg, f) for f in os.listdir(pkg) if f.endswith(".py")]
+    runtime += [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    runtime += [os.path.join(root, "tests", f) for f in os.listdir(os.path.join(root, "tests")) if f.startswith("test_gpu")]
+    for path in runtime:
+        tree = ast.parse(open(path).read())
+        docs = set()
+        for node in ast.walk(tree):
+            if isinstance(node, (ast.Module, ast.ClassDef, ast.FunctionDef, ast.AsyncFunctionDef)) and node.body and \
+                    isinstance(node.body[0], ast.Expr) and isinstance(node.body[0].value, ast.Constant):
+                docs.add(id(node.body[0].value))              # docstrings may cite reference paths
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Constant) and isinstance(node.value, str) and id(node) not in docs:
+                assert "/root/reference" not in node.value, (path, node.lineno)
