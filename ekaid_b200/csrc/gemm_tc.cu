@@ -127,6 +127,18 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
 }
+// One lane of a converged warp, chosen by the hardware.  Unlike `lane == 0`, ptxas knows that exactly one lane runs the
+// guarded region, so the uniform-datapath instructions inside it (UTMALDG, UTCHMMA, UTCBAR) are emitted directly instead
+// of inside an ELECT / R2UR.BROADCAST / BRA.U.ANY loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -341,7 +353,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = unit0; unit < num_units; unit += unit_stride) {
@@ -416,7 +428,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (CG == 1 || crank == 0)) {
+    if ((CG == 1 || crank == 0) && elect_one()) {
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accum, bf16 x bf16
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
