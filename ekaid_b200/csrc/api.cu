@@ -44,7 +44,8 @@ int ek_pdl_enabled() {
 int ek_gemm_f32_launch(int M, int N, int K, const float* A, long long sam, long long sak, const float* B,
                        long long sbk, long long sbn, const EkEpilogue& ep, cudaStream_t stream);
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
-                           long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream);
+                           long long ldb, const EkEpilogue& ep, int force_bn, int splits, int fmt, cudaStream_t stream);
+void ek_gemm_debug(int flags, unsigned long long* ts);
 int ek_cast_f32_bf16_launch(const float*, long long, bf16*, long long, long long, int, cudaStream_t);
 int ek_cast_bf16_f32_launch(const bf16*, long long, float*, long long, long long, int, cudaStream_t);
 int ek_copy_f32_launch(const float*, long long, float*, long long, long long, int, cudaStream_t);
@@ -141,6 +142,12 @@ static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
   r.ldc = e->ldc;
   r.Cb = (bf16*)e->Cb;
   r.ldcb = e->ldcb;
+  r.cb_fmt = e->cb_fmt;
+  r.cb_n1 = e->cb_n1;
+  r.Cb2 = (bf16*)e->Cb2;
+  r.ldcb2 = e->ldcb2;
+  r.cb2_fmt = e->cb2_fmt;
+  r.cb2_n0 = e->cb2_n0;
   return r;
 }
 
@@ -183,9 +190,19 @@ int ekaid_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, 
 }
 int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
                     int64_t ldb, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream) {
-  EK_REQUIRE(ep && (ep->C || ep->Cb), EK_ERR_SHAPE, "gemm_bf16: no output");
+  return ekaid_gemm_tc(transA, transB, M, N, K, A, lda, 0, B, ldb, 0, ep, force_bn, splits, stream);
+}
+int ekaid_gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, int a_fp16, const void* B,
+                  int64_t ldb, int b_fp16, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream) {
+  EK_REQUIRE(ep && (ep->C || ep->Cb || ep->Cb2), EK_ERR_SHAPE, "gemm_tc: no output");
+  EK_REQUIRE((ep->cb_n1 % 32) == 0 && (ep->cb2_n0 % 32) == 0 && ep->cb_n1 >= 0 && ep->cb2_n0 >= 0, EK_ERR_SHAPE,
+             "gemm_tc: cb_n1 / cb2_n0 must be non-negative multiples of 32");
   return ek_gemm_bf16_tc_launch(transA, transB, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, to_ep(ep), force_bn,
-                                splits, ST);
+                                splits, (a_fp16 ? 1 : 0) | (b_fp16 ? 2 : 0), ST);
+}
+int ekaid_gemm_debug(int flags, void* ts) {
+  ek_gemm_debug(flags, (unsigned long long*)ts);
+  return EK_OK;
 }
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
   return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, ST);

@@ -2,10 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 
 typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // Error codes returned through the C ABI (0 = ok); see include/ekaid_b200.h
 #define EK_OK 0
@@ -100,7 +102,27 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<f16>(f16 v) { return __half2float(v); }
+// fp32 pair -> packed fp16x2, round to nearest, saturating to +-65504 instead of overflowing to infinity
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *(uint32_t*)&t;
+}
+// 16-bit storage format chosen at run time: 0 = bf16, 1 = fp16 (saturating)
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi, int fmt) { return fmt ? pack_f16x2_sat(lo, hi) : pack_bf16x2(lo, hi); }
+__device__ __forceinline__ void ek_store16(bf16* dst, float v, int fmt) {
+  *(unsigned short*)dst = (unsigned short)(pack16x2(v, 0.f, fmt) & 0xFFFFu);
+}
 template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ f16 from_f32<f16>(float v) {
+  const unsigned short b = (unsigned short)(pack_f16x2_sat(v, 0.f) & 0xFFFFu);
+  return *(const f16*)&b;
+}
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -126,7 +148,23 @@ template <> __device__ __forceinline__ void store_vec<bf16, 8>(bf16* dst, const 
   pk.x = *(uint32_t*)&a; pk.y = *(uint32_t*)&b; pk.z = *(uint32_t*)&c; pk.w = *(uint32_t*)&d;
   *(uint4*)dst = pk;
 }
+template <> __device__ __forceinline__ void store_vec<f16, 4>(f16* dst, const float* v) {
+  uint2 pk;
+  pk.x = pack_f16x2_sat(v[0], v[1]); pk.y = pack_f16x2_sat(v[2], v[3]);
+  *(uint2*)dst = pk;
+}
+template <> __device__ __forceinline__ void store_vec<f16, 8>(f16* dst, const float* v) {
+  uint4 pk;
+  pk.x = pack_f16x2_sat(v[0], v[1]); pk.y = pack_f16x2_sat(v[2], v[3]);
+  pk.z = pack_f16x2_sat(v[4], v[5]); pk.w = pack_f16x2_sat(v[6], v[7]);
+  *(uint4*)dst = pk;
+}
 template <typename T, int V> __device__ __forceinline__ void load_vec(const T* src, float* v);
+template <> __device__ __forceinline__ void load_vec<f16, 4>(const f16* src, float* v) {
+  const uint2 raw = *(const uint2*)src;
+  const float2 a = __half22float2(*(const __half2*)&raw.x), b = __half22float2(*(const __half2*)&raw.y);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 template <> __device__ __forceinline__ void load_vec<float, 4>(const float* src, float* v) {
   const float4 a = *(const float4*)src;
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;

@@ -22,8 +22,14 @@ struct EkEpilogue {
   int dropOff;
   float* C;
   long long ldc;
-  bf16* Cb;
+  bf16* Cb;           // 16-bit output #1 (bf16, or fp16 when cb_fmt = 1), columns n < cb_n1 (0 = all)
   long long ldcb;
+  int cb_fmt;
+  int cb_n1;
+  bf16* Cb2;          // optional 16-bit output #2 (own format), columns n >= cb2_n0, stored at column n - cb2_n0
+  long long ldcb2;
+  int cb2_fmt;
+  int cb2_n0;
 };
 
 __device__ __forceinline__ float ek_act(float v, int act) {
@@ -47,5 +53,6 @@ __device__ __forceinline__ void ek_epilogue_store(const EkEpilogue& e, long long
   }
   v = ek_act(v, e.act);
   if (e.C) e.C[m * e.ldc + n] = v;
-  if (e.Cb) e.Cb[m * e.ldcb + n] = __float2bfloat16_rn(v);
+  if (e.Cb && (e.cb_n1 == 0 || n < e.cb_n1)) ek_store16(e.Cb + m * e.ldcb + n, v, e.cb_fmt);
+  if (e.Cb2 && n >= e.cb2_n0) ek_store16(e.Cb2 + m * e.ldcb2 + (n - e.cb2_n0), v, e.cb2_fmt);
 }

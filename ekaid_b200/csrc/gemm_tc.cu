@@ -27,6 +27,23 @@ constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 
+// kernel `flags` argument
+constexpr int GF_A_F16 = 1;        // A operand holds IEEE fp16 (default bf16); kind::f16 takes either format per operand
+constexpr int GF_B_F16 = 2;        // B operand holds IEEE fp16
+// measurement-only ablations (ekaid_gemm_debug): results are garbage, timings isolate one pipeline role
+constexpr int GF_NOSTORE = 16;     // epilogue drains TMEM but skips the fused epilogue (no global loads / stores)
+constexpr int GF_NOTMA = 32;       // producer arrives on the full barriers without loading
+constexpr int GF_NOMMA = 64;       // issuer commits without issuing MMAs
+constexpr int GF_NOEPI = 256;      // epilogue does not even read TMEM
+constexpr int GF_EARLY = 128;      // griddepcontrol.launch_dependents once this CTA has set up (experiment)
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GSTAMP(slot) do { if (dbg) dbg[(size_t)blockIdx.x * 32 + (slot)] = gtime_ns(); } while (0)
+
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -249,16 +266,25 @@ __device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uin
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
-            if (ep.Cb) {
+            // 16-bit outputs: bf16 or saturating fp16 per output, each limited to its column range (warp-uniform tests:
+            // cb_n1 and cb2_n0 are multiples of the 32-column chunk)
+            if (ep.Cb && (ep.cb_n1 == 0 || nb < ep.cb_n1)) {
               bf16* cp = ep.Cb + m * ep.ldcb + nb;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                pk.x = *(uint32_t*)&t0; pk.y = *(uint32_t*)&t1; pk.z = *(uint32_t*)&t2; pk.w = *(uint32_t*)&t3;
+                pk.x = pack16x2(v[j], v[j + 1], ep.cb_fmt); pk.y = pack16x2(v[j + 2], v[j + 3], ep.cb_fmt);
+                pk.z = pack16x2(v[j + 4], v[j + 5], ep.cb_fmt); pk.w = pack16x2(v[j + 6], v[j + 7], ep.cb_fmt);
+                *(uint4*)(cp + j) = pk;
+              }
+            }
+            if (ep.Cb2 && nb >= ep.cb2_n0) {
+              bf16* cp = ep.Cb2 + m * ep.ldcb2 + (nb - ep.cb2_n0);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 pk;
+                pk.x = pack16x2(v[j], v[j + 1], ep.cb2_fmt); pk.y = pack16x2(v[j + 2], v[j + 3], ep.cb2_fmt);
+                pk.z = pack16x2(v[j + 4], v[j + 5], ep.cb2_fmt); pk.w = pack16x2(v[j + 6], v[j + 7], ep.cb2_fmt);
                 *(uint4*)(cp + j) = pk;
               }
             }
@@ -277,7 +303,7 @@ __device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uin
 template <int BN, int A_MN, int B_MN, int CL, int CG = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
-                    int K, EkEpilogue ep, int vec_ok, int splits, int tail_from) {
+                    int K, EkEpilogue ep, int vec_ok, int splits, int tail_from, int flags, unsigned long long* dbg) {
   using C = Cfg<BN, A_MN, B_MN, CG>;
   static_assert(CL == 1 || BN >= 128, "the shared B tile must split into two TMA boxes");
   static_assert(CG == 1 || CL == 2, "cta_group::2 needs a cluster of two CTAs");
@@ -349,7 +375,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (CL > 1) cluster_sync_all();        // peer barriers initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) GSTAMP(0);
   ek_pdl_wait();     // barriers, TMEM and tensor maps are set up; from here on we touch the previous kernel's data
+  if (threadIdx.x == 0) GSTAMP(1);
+  if (flags & GF_EARLY) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -368,6 +397,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const int k0 = kb * BK;
+          if (flags & GF_NOTMA) {
+            if (CG == 1 || crank == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if (unit == unit0 && kb == kb0) GSTAMP(2);
           if constexpr (CG == 2) {
             // cta_group::2: both CTAs' boxes complete on the LEADER's barrier (it alone waits, its MMA spans both CTAs)
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -430,7 +465,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ MMA issuer
     if ((CG == 1 || crank == 0) && elect_one()) {
       // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accum, bf16 x bf16
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
+      // a_format / b_format (bits 7-9 / 10-12): 0 = fp16, 1 = bf16 -- chosen per operand, so a bf16 gradient can meet an
+      // fp16 activation or weight in one MMA
+      const uint32_t idesc = (1u << 4) | ((flags & GF_A_F16) ? 0u : (1u << 7)) | ((flags & GF_B_F16) ? 0u : (1u << 10)) |
+                             ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -448,6 +486,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0 && kb == kb0) GSTAMP(3);
+          if (flags & GF_NOMMA) {
+            if constexpr (CG == 2) tc_commit_cg2(&empty_bar[stage], 3);
+            else if (CL == 1) tc_commit(&empty_bar[stage]);
+            else tc_commit_mc(&empty_bar[stage], 3);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t sb = sa + C::A_BYTES;
 #pragma unroll
@@ -470,6 +516,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if constexpr (CG == 2) tc_commit_cg2(&tfull_bar[buf], 3);   // accumulator complete -> both CTAs' epilogues
         else tc_commit(&tfull_bar[buf]);         // accumulator complete -> epilogue
+        if (it < 6) GSTAMP(4 + 2 * it);          // all MMAs of work unit `it` issued
       }
     }
   } else {
@@ -486,8 +533,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int m0 = ((tile % num_mg) * CL + (int)crank) * BM;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && it < 6) GSTAMP(16 + it);     // accumulator of work unit `it` complete
       const long long mlane0 = (long long)m0 + q * 32;
-      if (splits > 1 && half == 1) {
+      if (flags & GF_NOEPI) {
+      } else if (splits > 1 && half == 1) {
         // split-K partial sums are reduced by the first warp of each quarter (one staging buffer per quarter)
       } else if (splits > 1) {
         // Each lane owns accumulator row (q*32 + lane) in TMEM.  A 32x32 chunk is transposed through shared memory (16-byte
@@ -552,12 +601,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     v.x = ek_act(v.x, ep.act); v.y = ek_act(v.y, ep.act); v.z = ek_act(v.z, ep.act); v.w = ek_act(v.w, ep.act);
                   }
                   if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
-                  if (ep.Cb) {
-                    __nv_bfloat162 t0 = __floats2bfloat162_rn(v.x, v.y), t1 = __floats2bfloat162_rn(v.z, v.w);
+                  if (ep.Cb && (ep.cb_n1 == 0 || n < ep.cb_n1)) {
                     uint2 pk;
-                    pk.x = *(uint32_t*)&t0;
-                    pk.y = *(uint32_t*)&t1;
+                    pk.x = pack16x2(v.x, v.y, ep.cb_fmt);
+                    pk.y = pack16x2(v.z, v.w, ep.cb_fmt);
                     *(uint2*)(ep.Cb + mm * ep.ldcb + n) = pk;
+                  }
+                  if (ep.Cb2 && n >= ep.cb2_n0) {
+                    uint2 pk;
+                    pk.x = pack16x2(v.x, v.y, ep.cb2_fmt);
+                    pk.y = pack16x2(v.z, v.w, ep.cb2_fmt);
+                    *(uint2*)(ep.Cb2 + mm * ep.ldcb2 + (n - ep.cb2_n0)) = pk;
                   }
                 }
               }
@@ -595,11 +649,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (; c < nch; c += 4) {
           tc_wait_ld();
           if (c + 2 < nch) tc_ld32(tbase + (c + 2) * 32, rb);
-          if (row_ok) epi_direct_chunk(ep, ra, m, n0 + c * 32, N, vec_ok, rowb_ptr);
+          if (row_ok && !(flags & GF_NOSTORE)) epi_direct_chunk(ep, ra, m, n0 + c * 32, N, vec_ok, rowb_ptr);
           if (c + 2 < nch) {
             tc_wait_ld();
             if (c + 4 < nch) tc_ld32(tbase + (c + 4) * 32, ra);
-            if (row_ok) epi_direct_chunk(ep, rb, m, n0 + (c + 2) * 32, N, vec_ok, rowb_ptr);
+            if (row_ok && !(flags & GF_NOSTORE)) epi_direct_chunk(ep, rb, m, n0 + (c + 2) * 32, N, vec_ok, rowb_ptr);
           }
         }
       }
@@ -609,10 +663,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader issues the MMAs
         else mbar_arrive(&tempty_bar[buf]);
       }
+      if (warp == 2 && lane == 0 && it < 6) GSTAMP(5 + 2 * it);  // epilogue of work unit `it` done (this warp)
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GSTAMP(31);
   if (CL > 1) cluster_sync_all();        // no CTA leaves while its peer may still multicast into it / arrive on it
   if (warp == 1) {
     tc_fence_after();
@@ -699,9 +755,14 @@ int num_sms() {
   return n;
 }
 
+int g_dbg_flags = 0;                       // ekaid_gemm_debug: measurement-only ablation flags (GF_NO*) / experiments
+unsigned long long* g_dbg_ts = nullptr;    // device buffer [grid][32] of globaltimer stamps, or null
+
 template <int BN, int A_MN, int B_MN, int CL, int CG = 1>
 int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep, int vec_ok,
-               int splits, int tail_halving, cudaStream_t stream) {
+               int splits, int tail_halving, int flags, cudaStream_t stream) {
+  flags |= g_dbg_flags;
+  unsigned long long* dbg = g_dbg_ts;
   using C = Cfg<BN, A_MN, B_MN, CG>;
   static bool attr_set = false;
   auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN, CL, CG>;
@@ -722,7 +783,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
     if (rem > 0 && 2 * rem <= slots) tail_from = tiles - rem;
   }
   if (CL == 1) {
-    ek_launch(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, M, N, K, ep, vec_ok, splits, tail_from);
+    ek_launch(kern, grid, NUM_THREADS, C::SMEM_BYTES, stream, ta, tb, M, N, K, ep, vec_ok, splits, tail_from, flags, dbg);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -736,7 +797,7 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, vec_ok, splits, tail_from);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, ep, vec_ok, splits, tail_from, flags, dbg);
     EK_REQUIRE(e == cudaSuccess, EK_ERR_CUDA, "gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
   }
   EK_CHECK_LAUNCH();
@@ -745,27 +806,34 @@ int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K
 
 template <int A_MN, int B_MN>
 int launch_bn(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EkEpilogue& ep,
-              int vec_ok, int splits, int th, cudaStream_t stream) {
+              int vec_ok, int splits, int th, int flags, cudaStream_t stream) {
   if (cl == 3) {     // cta_group::2 pair
-    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
-    return launch_cfg<256, A_MN, B_MN, 2, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
+    return launch_cfg<256, A_MN, B_MN, 2, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
   }
   if (cl == 2) {
-    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
-    return launch_cfg<256, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    if (bn == 128) return launch_cfg<128, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
+    return launch_cfg<256, A_MN, B_MN, 2>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
   }
   switch (bn) {
-    case 64: return launch_cfg<64, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
-    case 128: return launch_cfg<128, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
-    default: return launch_cfg<256, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, stream);
+    case 64: return launch_cfg<64, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
+    case 128: return launch_cfg<128, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
+    default: return launch_cfg<256, A_MN, B_MN, 1>(ta, tb, M, N, K, ep, vec_ok, splits, th, flags, stream);
   }
 }
 
 }  // namespace
 
 // transA: A stored [K, M];  transB: B stored [K, N]  (see file header)
+void ek_gemm_debug(int flags, unsigned long long* ts) {
+  g_dbg_flags = flags;
+  g_dbg_ts = ts;
+}
+
+// fmt: bit 0 = A holds fp16 (else bf16), bit 1 = B holds fp16
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
-                           long long ldb, const EkEpilogue& ep, int force_bn, int splits, cudaStream_t stream) {
+                           long long ldb, const EkEpilogue& ep, int force_bn, int splits, int fmt, cudaStream_t stream) {
+  const int flags = fmt & (GF_A_F16 | GF_B_F16);
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
   // force_bn = 1000 + width selects the CTA-pair (cluster of 2, multicast B) variant of that width.  It is NOT the
   // default: measured on B200 it is no faster than independent CTAs (L2 already merges the two CTAs' requests for the
@@ -776,7 +844,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   // Split-K candidates: plain fp32 outputs, or "C += A B" (addend aliases C, nothing else in the epilogue) where the
   // partial sums are reduced straight onto the existing values.
   const bool acc_alias = ep.addend && ep.addend == ep.C && ep.ldadd == ep.ldc;
-  const bool plain_out = ep.C && !ep.Cb && !ep.bias && (!ep.addend || acc_alias) && !ep.rowb &&
+  const bool plain_out = ep.C && !ep.Cb && !ep.Cb2 && !ep.bias && (!ep.addend || acc_alias) && !ep.rowb &&
                          ep.act == EK_ACT_NONE && !ep.drop.seed;
   const int nkb = ek_div_up(K, BK);
   int bn = 256;
@@ -823,6 +891,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   int vec_ok = 15;
   if (ep.C && (((uintptr_t)ep.C & 15) || (ep.ldc & 3))) vec_ok &= ~1;
   if (ep.Cb && (((uintptr_t)ep.Cb & 15) || (ep.ldcb & 7))) vec_ok &= ~1;
+  if (ep.Cb2 && (((uintptr_t)ep.Cb2 & 15) || (ep.ldcb2 & 7))) vec_ok &= ~1;
   if (ep.bias && ((uintptr_t)ep.bias & 15)) vec_ok &= ~2;
   if (ep.addend && (((uintptr_t)ep.addend & 15) || (ep.ldadd & 3))) vec_ok &= ~4;
   if (ep.rowb && (((uintptr_t)ep.rowb & 15) || (ep.ldrowb & 3) || ((uintptr_t)ep.rowb_alt & 15))) vec_ok &= ~8;
@@ -855,8 +924,8 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
       epk.addend = nullptr;                    // partial sums are atomically added onto C (zeroed or pre-existing)
     }
   }
-  if (!transA && !transB) return launch_bn<0, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
-  if (!transA && transB) return launch_bn<0, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
-  if (transA && !transB) return launch_bn<1, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
-  return launch_bn<1, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, stream);
+  if (!transA && !transB) return launch_bn<0, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, flags, stream);
+  if (!transA && transB) return launch_bn<0, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, flags, stream);
+  if (transA && !transB) return launch_bn<1, 0>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, flags, stream);
+  return launch_bn<1, 1>(bn, cl, ta, tb, M, N, K, epk, vec_ok, splits, th, flags, stream);
 }

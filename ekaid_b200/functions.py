@@ -104,8 +104,11 @@ class PC:
 # thin wrappers
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None, rowb_div=1, rowb_mod=1,
-         rowflag=None, rowb_alt=None, act=ACT_NONE, C=None, Cb=None, splits=0, force_bn=0, drop=None):
-    """C[M,N] = op(A) op(B) with the fused epilogue; dtype of A selects tcgen05 (bf16) or SIMT (fp32)."""
+         rowflag=None, rowb_alt=None, act=ACT_NONE, C=None, Cb=None, splits=0, force_bn=0, drop=None,
+         Cb2=None, cb_n1=0, cb2_n0=0):
+    """C[M,N] = op(A) op(B) with the fused epilogue; dtype of A selects tcgen05 (16-bit operands: bf16 or fp16, chosen
+    per operand) or SIMT (fp32).  Cb / Cb2: 16-bit outputs (bf16 or fp16 by their dtype): Cb takes columns < cb_n1
+    (0 = all), Cb2 columns >= cb2_n0."""
     ep = Epilogue()
     ep.bias = ptr(bias)
     ep.addend = ptr(addend)
@@ -125,16 +128,26 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
     ep.ldc = C.stride(0) if C is not None else 0
     ep.Cb = ptr(Cb)
     ep.ldcb = Cb.stride(0) if Cb is not None else 0
-    assert A.dtype == B.dtype and A.stride(-1) == 1 and B.stride(-1) == 1
+    ep.cb_fmt = 1 if (Cb is not None and Cb.dtype == torch.float16) else 0
+    ep.cb_n1 = cb_n1
+    ep.Cb2 = ptr(Cb2)
+    ep.ldcb2 = Cb2.stride(0) if Cb2 is not None else 0
+    ep.cb2_fmt = 1 if (Cb2 is not None and Cb2.dtype == torch.float16) else 0
+    ep.cb2_n0 = cb2_n0
+    assert A.stride(-1) == 1 and B.stride(-1) == 1
     # algorithmic bytes: both operands once, every output once, the epilogue addend once
     nbytes = A.element_size() * (M * K + K * N) + M * N * ((4 if C is not None else 0) + (2 if Cb is not None else 0) +
                                                           (addend.element_size() if addend is not None else 0))
+    if Cb2 is not None:
+        nbytes += M * (N - cb2_n0) * 2 - (M * (N - cb_n1) * 2 if cb_n1 else 0)
     info = {"flops": 2.0 * M * N * K, "bytes": float(nbytes), "shape": (M, N, K, transA, transB)}
-    if A.dtype == torch.bfloat16:
-        call("gemm_bf16", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
-             ctypes.addressof(ep), force_bn, splits, info=info)
+    if A.dtype in (torch.bfloat16, torch.float16):
+        assert B.dtype in (torch.bfloat16, torch.float16)
+        call("gemm_tc", transA, transB, M, N, K, A.data_ptr(), A.stride(0), 1 if A.dtype == torch.float16 else 0,
+             B.data_ptr(), B.stride(0), 1 if B.dtype == torch.float16 else 0, ctypes.addressof(ep), force_bn, splits,
+             info=info)
     else:
-        assert A.dtype == torch.float32 and Cb is None
+        assert A.dtype == torch.float32 and B.dtype == torch.float32 and Cb is None and Cb2 is None
         call("gemm_f32", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
              ctypes.addressof(ep), info=info)
 

@@ -27,6 +27,9 @@ class Epilogue(ctypes.Structure):
         ("drop_p", ctypes.c_float), ("drop_n", ctypes.c_int32), ("drop_off", ctypes.c_int32),
         ("C", ctypes.c_void_p), ("ldc", ctypes.c_int64),
         ("Cb", ctypes.c_void_p), ("ldcb", ctypes.c_int64),
+        ("cb_fmt", ctypes.c_int32), ("cb_n1", ctypes.c_int32),
+        ("Cb2", ctypes.c_void_p), ("ldcb2", ctypes.c_int64),
+        ("cb2_fmt", ctypes.c_int32), ("cb2_n0", ctypes.c_int32),
     ]
 
 
@@ -100,6 +103,7 @@ LAUNCHES = 0
 # bench only: when a list, every call is bracketed by CUDA events on the launching stream:
 # (name, start_event, end_event, info)
 PROFILE = None
+PROFILE_EXTERNAL = False      # events that may be recorded inside a CUDA-graph capture (event-record nodes)
 
 
 def call(name: str, *args, info=None) -> None:
@@ -110,8 +114,8 @@ def call(name: str, *args, info=None) -> None:
     if PROFILE is None:
         rc = fn(*args, stream_ptr())
     else:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+        e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e1 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
         e0.record()
         rc = fn(*args, stream_ptr())
         e1.record()

@@ -339,7 +339,7 @@ class GraphFusionStep:
         return total.detach()
 
     # -- CUDA-graph replay of the whole step ------------------------------------------------------------------
-    def capture(self, raw_example, train: bool = True, warmup: int = 3):
+    def capture(self, raw_example, train: bool = True, warmup: int = 3, profile: bool = False):
         """Capture  process_matrix x4 -> forward -> backward -> [all-reduce] -> Adam  (or the inference forward) into
         one CUDA graph.  `raw_example` fixes the shapes: the device tuple `to_device` returns.  The step is ~600 small
         launches at batch 64; replaying a graph removes the Python/launch overhead between them."""
@@ -361,8 +361,17 @@ class GraphFusionStep:
         torch.cuda.synchronize()
         before = lib.LAUNCHES
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_out = body()
+        self.profile_events = None
+        if profile:
+            # measurement build of the graph: every C-ABI call is bracketed by event-record nodes (external events), so
+            # after a replay each kernel's duration inside the replayed step can be read with cudaEventElapsedTime
+            lib.PROFILE, lib.PROFILE_EXTERNAL = [], True
+        try:
+            with torch.cuda.graph(self._graph):
+                self._static_out = body()
+        finally:
+            if profile:
+                self.profile_events, lib.PROFILE, lib.PROFILE_EXTERNAL = lib.PROFILE, None, False
         self.launches_per_replay = lib.LAUNCHES - before
         return self
 

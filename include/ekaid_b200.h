@@ -63,8 +63,18 @@ typedef struct ekaid_epilogue {
   int32_t drop_off;
   float* C;
   int64_t ldc;
-  void* Cb; /* __nv_bfloat16* */
+  void* Cb; /* 16-bit output #1: __nv_bfloat16* (cb_fmt 0) or __half* (cb_fmt 1, saturating conversion) */
   int64_t ldcb;
+  /* 16-bit outputs may be split by column: Cb receives columns n < cb_n1 (0 = all); Cb2 (optional second 16-bit
+   * output, own format) receives columns n >= cb2_n0 at Cb2[m * ldcb2 + n - cb2_n0].  cb_n1 and cb2_n0 are multiples
+   * of 32.  Used to keep one tensor in two formats (e.g. Z as bf16 for the backward kernels and as fp16 for the
+   * forward aggregation) or to route [query | key] and Z to different buffers from ONE GEMM. */
+  int32_t cb_fmt;
+  int32_t cb_n1;
+  void* Cb2;
+  int64_t ldcb2;
+  int32_t cb2_fmt;
+  int32_t cb2_n0;
 } ekaid_epilogue_t;
 
 /* Dropout convention (train mode; eval / p = 0 passes seed = NULL): masks are never stored.  Every dropout site of the
@@ -93,6 +103,15 @@ int ekaid_gemm_f32(int transA, int transB, int M, int N, int K, const float* A, 
  * splits: 0 = auto split-K (plain fp32 C only), 1 = off. Operands 16-byte aligned, pitches multiples of 8. */
 int ekaid_gemm_bf16(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, const void* B,
                     int64_t ldb, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream);
+/* The same kernel with the 16-bit format chosen per operand (tcgen05 kind::f16 takes fp16 or bf16 for A and for B
+ * independently): a_fp16 / b_fp16 = 1 when that operand holds IEEE fp16.  The forward pass keeps weights and bounded
+ * activations in fp16 (11 significant bits), gradients stay bf16 (range); wgrad / dgrad GEMMs mix the two. */
+int ekaid_gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int64_t lda, int a_fp16, const void* B,
+                  int64_t ldb, int b_fp16, const ekaid_epilogue_t* ep, int force_bn, int splits, void* stream);
+/* Measurement hook (scripts/gemm_probe.py): flags isolate one pipeline role of the GEMM kernel (16 = no fused epilogue,
+ * 32 = no TMA loads, 64 = no MMAs, 256 = no TMEM drain; results are then garbage), 128 = early programmatic-launch
+ * trigger; ts = device buffer of grid x 32 uint64 globaltimer stamps or NULL.  0 / NULL restores normal operation. */
+int ekaid_gemm_debug(int flags, void* ts);
 
 /* ---- casts / reductions / glue -------------------------------------------------------------------------- */
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);

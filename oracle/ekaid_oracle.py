@@ -107,6 +107,7 @@ def position_embedding(pos_mat: Tensor, feat_dim: int = 64, wave_length: float =
     promoted to the dtype of pos_mat (fp64 when the boxes arrive as .double())."""
     feat_range = torch.arange(0, feat_dim / 8)
     dim_mat = torch.pow(torch.ones((1,)) * wave_length, (8.0 / feat_dim) * feat_range).view(1, 1, 1, -1)
+    dim_mat = dim_mat.to(pos_mat.device)      # (bench.py's GPU-eager comparator runs this restatement on cuda:0)
     div = (100.0 * pos_mat).unsqueeze(4) / dim_mat
     emb = torch.cat([torch.sin(div), torch.cos(div)], -1)
     return emb.view(emb.shape[0], emb.shape[1], emb.shape[2], feat_dim)
