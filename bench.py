@@ -464,7 +464,11 @@ def main():
     # Fallback (--no-graph or if external events cannot be captured): eager launches bracketed the same way.
     nprof = min(args.steps, 5)
     prof = None
-    timing_mode = "in-graph event nodes"
+    timing_mode = ("in-graph event nodes; for this pass the independent GEMMs that the timed step runs on parallel "
+                   "streams are serialised, so every duration is the kernel alone on the GPU")
+    from ekaid_b200 import functions as _fn
+    fork_was = _fn.FORK_ENABLED
+    _fn.FORK_ENABLED = False       # per-kernel durations are only meaningful when the kernel has the GPU to itself
     if use_graph:
         try:
             step.capture(resident[0], train=train, warmup=1, profile=True)
@@ -492,6 +496,7 @@ def main():
         torch.cuda.synchronize()
         raw_prof, lib.PROFILE = lib.PROFILE, None
         prof = [(name, a.elapsed_time(b_), info) for name, a, b_, info in raw_prof]
+    _fn.FORK_ENABLED = fork_was
     agg = {}
     for name, ms_, info in prof:
         key = "gemm_bf16" if name == "gemm_tc" else name

@@ -94,7 +94,7 @@ int ek_edge_aggregate_bwd_launch(int, const float*, const uint8_t*, const float*
 int ek_edge_softmax_bwd_launch(int, const float*, const float*, int, const void*, long long, int, const float*, int,
                                int, int, int, void*, float*, float*, cudaStream_t);
 int ek_embed_gather_launch(int, const long long*, const float*, const float*, int, int, int, void*, cudaStream_t);
-int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, cudaStream_t);
+int ek_embed_gather_bwd_launch(const long long*, const float*, long long, int, int, int, int, float*, int, cudaStream_t);
 int ek_geom_bias_bwd_parts();
 int ek_colsum_many_launch(int, const int*, const void* const*, const long long*, long long, const int*, float* const*, float*,
                           cudaStream_t);
@@ -371,8 +371,8 @@ int ekaid_embed_gather(int is_bf16, const int64_t* q, const float* emb, const fl
   return ek_embed_gather_launch(is_bf16, (const long long*)q, emb, emb2, B, L, ed, E, ST);
 }
 int ekaid_embed_gather_bwd(const int64_t* q, const float* dE, int64_t ldde, int B, int L, int ed, int V, float* demb,
-                           void* stream) {
-  return ek_embed_gather_bwd_launch((const long long*)q, dE, ldde, B, L, ed, V, demb, ST);
+                           int padding_idx, void* stream) {
+  return ek_embed_gather_bwd_launch((const long long*)q, dE, ldde, B, L, ed, V, demb, padding_idx, ST);
 }
 int ekaid_gru_cell_fwd(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h, void* hT,
                        float* gates, const float* gh_reset, void* stream) {

@@ -35,6 +35,8 @@ constexpr int GF_NOSTORE = 16;     // epilogue drains TMEM but skips the fused e
 constexpr int GF_NOTMA = 32;       // producer arrives on the full barriers without loading
 constexpr int GF_NOMMA = 64;       // issuer commits without issuing MMAs
 constexpr int GF_NOEPI = 256;      // epilogue does not even read TMEM
+constexpr int GF_NOGST = 512;      // fused epilogue runs but its global stores are skipped
+constexpr int GF_NOSTAGE = 1024;   // no shared-memory staging round trip (stores garbage)
 constexpr int GF_EARLY = 128;      // griddepcontrol.launch_dependents once this CTA has set up (experiment)
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -183,6 +185,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// explicit shared-space 16-byte accesses (the staging pointer is derived from an aligned-up generic pointer, for which
+// the compiler would otherwise emit generic ST.E / LD.E -- measured 2x slower than the uncoalesced epilogue it replaced)
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 
 // Shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version field = 1
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
@@ -203,96 +215,136 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (CG == 2) ? (BN == 256 ? 6 : 8) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;   // two accumulator buffers
-  static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;                     // transposition buffers of the 4 epilogue warps
+  static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;                     // one swizzled 32x32 fp32 staging tile per epilogue warp
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
 };
 
-// Direct epilogue of one 32-column chunk: this lane owns one accumulator row and stores 32 consecutive columns.
-__device__ __forceinline__ void epi_direct_chunk(const EkEpilogue& ep, const uint32_t* r, long long m, int nb, int N,
-                                                 int vec_ok, const float* rowb_ptr) {
-  if ((vec_ok & 1) && nb + 32 <= N) {
-            float v[32];
+// ---- the fused epilogue on one staged 32x32 chunk, in the transposed layout (this lane: rows i*4 + rg, cols n..n+3) ----
+// The epilogue is ISSUE bound: a 128x256 tile is 8192 float4 row pieces, and every instruction spent per piece costs
+// ~0.15 us per tile.  A loop that tests run-time feature flags and nullable pointers per piece compiled to ~90
+// instructions (7 us per tile, as long as the K = 1024 main loop).  So the common combinations are compiled separately
+// (OUT: bit 0 = fp32 C, bit 1 = Cb, bit 2 = Cb2; ADD = addend) with pointers resolved once per chunk and bumped
+// unconditionally; everything else takes the general forms below.
+struct EpiChunk {
+  uint32_t stg;           // this warp's staging tile (shared-space address)
+  int rg, cg;             // row group / 16-byte column group of this lane
+  int nvalid;             // row groups of this lane inside the matrix
+  long long row0;         // first row of this lane
+  int n, nb;              // this lane's first column, the chunk's first column
+};
+
+__device__ __forceinline__ void epi_load8(const EpiChunk& k, float4* vt) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (ep.bias) {
-              if (vec_ok & 2) {
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + k.rg;
+    vt[i] = lds128(k.stg + (uint32_t)(rr * 128 + ((k.cg ^ (rr & 7)) << 4)));
+  }
+}
+
+template <int OUT, bool ADD, bool DROP = false, bool ROWB = false>
+__device__ __forceinline__ void epi_rows_fast(const EkEpilogue& ep, const EpiChunk& k, float4 bv, const float4* add4,
+                                              unsigned long long dseed = 0ull, const float* rowb_lane = nullptr) {
+  float4 vt[8];
+  epi_load8(k, vt);
+  float* pc = ep.C + k.row0 * ep.ldc + k.n;
+  bf16* pb = ep.Cb + k.row0 * ep.ldcb + k.n;
+  bf16* pb2 = ep.Cb2 + k.row0 * ep.ldcb2 + (k.n - ep.cb2_n0);
+  const long long sc = 4 * ep.ldc, sb = 4 * ep.ldcb, sb2 = 4 * ep.ldcb2;
+  const int fb = ep.cb_fmt, fb2 = ep.cb2_fmt;
+  // dropout counter of this lane's first element; one 64-bit draw covers the four columns (n is a multiple of 4)
+  unsigned long long e0 = DROP ? (unsigned long long)k.row0 * ep.dropN + ep.dropOff + k.n : 0ull;
+  const unsigned long long es = DROP ? 4ull * (unsigned long long)ep.dropN : 0ull;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b4 = __ldg((const float4*)(ep.bias + nb + j));
-                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                }
-              } else {
+  for (int i = 0; i < 8; ++i) {
+    unsigned long long pr = 0ull;
+    if (ROWB) pr = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, i * 4 + k.rg);
+    if (i < k.nvalid) {
+      float4 v = vt[i];
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (DROP) {
+        float mk[4];
+        ek_drop_multv<4>(ep.drop, dseed, e0, mk);
+        v.x *= mk[0]; v.y *= mk[1]; v.z *= mk[2]; v.w *= mk[3];
+      }
+      if (ADD) { v.x += add4[i].x; v.y += add4[i].y; v.z += add4[i].z; v.w += add4[i].w; }
+      if (ROWB) {
+        const float4 a4 = __ldg((const float4*)((const float*)(uintptr_t)pr + k.n));
+        v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+      }
+      if (OUT & 1) *(float4*)pc = v;
+      if (OUT & 2) *(uint2*)pb = make_uint2(pack16x2(v.x, v.y, fb), pack16x2(v.z, v.w, fb));
+      if (OUT & 4) *(uint2*)pb2 = make_uint2(pack16x2(v.x, v.y, fb2), pack16x2(v.z, v.w, fb2));
+    }
+    if (OUT & 1) pc += sc;
+    if (OUT & 2) pb += sb;
+    if (OUT & 4) pb2 += sb2;
+    if (DROP) e0 += es;
+  }
+}
+
+// split-K partial sums: fp32 reduction in L2, one 16-byte reduction per four columns
+__device__ __forceinline__ void epi_rows_red(const EkEpilogue& ep, const EpiChunk& k) {
+  float4 vt[8];
+  epi_load8(k, vt);
+  float* pc = ep.C + k.row0 * ep.ldc + k.n;
+  const long long sc = 4 * ep.ldc;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(ep.bias + nb + j);
-              }
-            }
-            if (ep.drop.seed) {
-              float mk[32];
-              ek_drop_multv<32>(ep.drop, ek_seed(ep.drop), (unsigned long long)m * ep.dropN + ep.dropOff + nb, mk);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] *= mk[j];
-            }
-            if (ep.addend) {
-              const float* ap = ep.addend + m * ep.ldadd + nb;
-              if (vec_ok & 4) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 a4 = *(const float4*)(ap + j);
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += ap[j];
-              }
-            }
-            if (rowb_ptr) {
-              if (vec_ok & 8) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 a4 = __ldg((const float4*)(rowb_ptr + nb + j));
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += __ldg(rowb_ptr + nb + j);
-              }
-            }
-            if (ep.act != EK_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = ek_act(v[j], ep.act);
-            }
-            if (ep.C) {
-              float* cp = ep.C + m * ep.ldc + nb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *(float4*)(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            // 16-bit outputs: bf16 or saturating fp16 per output, each limited to its column range (warp-uniform tests:
-            // cb_n1 and cb2_n0 are multiples of the 32-column chunk)
-            if (ep.Cb && (ep.cb_n1 == 0 || nb < ep.cb_n1)) {
-              bf16* cp = ep.Cb + m * ep.ldcb + nb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                pk.x = pack16x2(v[j], v[j + 1], ep.cb_fmt); pk.y = pack16x2(v[j + 2], v[j + 3], ep.cb_fmt);
-                pk.z = pack16x2(v[j + 4], v[j + 5], ep.cb_fmt); pk.w = pack16x2(v[j + 6], v[j + 7], ep.cb_fmt);
-                *(uint4*)(cp + j) = pk;
-              }
-            }
-            if (ep.Cb2 && nb >= ep.cb2_n0) {
-              bf16* cp = ep.Cb2 + m * ep.ldcb2 + (nb - ep.cb2_n0);
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                pk.x = pack16x2(v[j], v[j + 1], ep.cb2_fmt); pk.y = pack16x2(v[j + 2], v[j + 3], ep.cb2_fmt);
-                pk.z = pack16x2(v[j + 4], v[j + 5], ep.cb2_fmt); pk.w = pack16x2(v[j + 6], v[j + 7], ep.cb2_fmt);
-                *(uint4*)(cp + j) = pk;
-              }
-            }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {         // cold path (static indexing keeps r[] in registers)
-      const int n = nb + j;
-      if (n < N) ek_epilogue_store(ep, m, n, __uint_as_float(r[j]));
+  for (int i = 0; i < 8; ++i) {
+    if (i < k.nvalid)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pc), "f"(vt[i].x), "f"(vt[i].y), "f"(vt[i].z),
+                   "f"(vt[i].w)
+                   : "memory");
+    pc += sc;
+  }
+}
+
+// four consecutive columns of one row -> C (fp32) / Cb / Cb2 (16-bit, per-output format and column range)
+__device__ __forceinline__ void epi_store4(const EkEpilogue& ep, long long mm, int n, int nb, float4 v) {
+  if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
+  if (ep.Cb && (ep.cb_n1 == 0 || nb < ep.cb_n1)) {
+    uint2 pk;
+    pk.x = pack16x2(v.x, v.y, ep.cb_fmt);
+    pk.y = pack16x2(v.z, v.w, ep.cb_fmt);
+    *(uint2*)(ep.Cb + mm * ep.ldcb + n) = pk;
+  }
+  if (ep.Cb2 && nb >= ep.cb2_n0) {
+    uint2 pk;
+    pk.x = pack16x2(v.x, v.y, ep.cb2_fmt);
+    pk.y = pack16x2(v.z, v.w, ep.cb2_fmt);
+    *(uint2*)(ep.Cb2 + mm * ep.ldcb2 + (n - ep.cb2_n0)) = pk;
+  }
+}
+
+// general form: every epilogue feature, one row group per iteration of a ROLLED loop (one copy of the dropout hash and
+// of the transcendental activations in the instruction stream)
+__device__ __forceinline__ void epi_rows_general(const EkEpilogue& ep, const EpiChunk& k, float4 bv, const float* rowb_lane,
+                                              unsigned long long dseed) {
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + k.rg;
+    const unsigned long long pr =
+        ep.rowb ? __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr) : 0ull;
+    if (i < k.nvalid) {
+      const long long mm = k.row0 + 4 * i;
+      float4 v = lds128(k.stg + (uint32_t)(rr * 128 + ((k.cg ^ (rr & 7)) << 4)));
+      v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      if (ep.drop.seed) {
+        float mk[4];
+        ek_drop_multv<4>(ep.drop, dseed, (unsigned long long)mm * ep.dropN + ep.dropOff + k.n, mk);
+        v.x *= mk[0]; v.y *= mk[1]; v.z *= mk[2]; v.w *= mk[3];
+      }
+      if (ep.addend) {
+        const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + k.n);
+        v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+      }
+      if (ep.rowb) {
+        const float4 a4 = __ldg((const float4*)((const float*)(uintptr_t)pr + k.n));
+        v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+      }
+      if (ep.act != EK_ACT_NONE) {
+        v.x = ek_act(v.x, ep.act); v.y = ek_act(v.y, ep.act); v.z = ek_act(v.z, ep.act); v.w = ek_act(v.w, ep.act);
+      }
+      epi_store4(ep, mm, k.n, k.nb, v);
     }
   }
 }
@@ -521,9 +573,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps (2..9)
+    // TMEM -> registers (tcgen05.ld 32x32b: lane = accumulator row) -> per-warp 4 KB staging tile in shared memory
+    // (16-byte chunks XOR-swizzled by row: conflict-free both ways) -> read back TRANSPOSED, so that one warp
+    // instruction touches 4 rows x 128 contiguous bytes.  The fused epilogue runs in that layout: bias / addend /
+    // row-broadcast loads and the C / Cb / Cb2 stores are all fully coalesced (a row-per-lane store of the same data
+    // costs 32 cache-line transactions per instruction and made the epilogue -- 6 us per 128x256 bf16 tile, 13 us per
+    // fp32 tile -- as long as the whole K = 1024 main loop: profiles/r02_gemm_probe.json).  Two warps share each TMEM
+    // lane quarter and take alternate 32-column chunks; the next chunk's TMEM load is in flight while this one is stored.
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;            // which of the two warps of this quarter
-    float* stg = (float*)(smem + C::STAGES * C::STAGE_BYTES + 256) + (warp & 3) * (32 * 36);   // split-K path, half 0 only
+    const uint32_t stg = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256) + (uint32_t)(warp - 2) * 4096u;
+    const int rg = lane >> 3, cg = lane & 7;     // transposed layout: row group / 4-column group of this lane
     int it = 0;
     for (int unit = unit0; unit < num_units; unit += unit_stride, ++it) {
       int tile, n0, bn_eff;
@@ -534,134 +594,132 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
       if (warp == 2 && lane == 0 && it < 6) GSTAMP(16 + it);     // accumulator of work unit `it` complete
-      const long long mlane0 = (long long)m0 + q * 32;
-      if (flags & GF_NOEPI) {
-      } else if (splits > 1 && half == 1) {
-        // split-K partial sums are reduced by the first warp of each quarter (one staging buffer per quarter)
-      } else if (splits > 1) {
-        // Each lane owns accumulator row (q*32 + lane) in TMEM.  A 32x32 chunk is transposed through shared memory (16-byte
-        // accesses, pitch 36 floats: conflict-free both ways) so that one warp instruction stores 4 rows x 128 contiguous
-        // bytes instead of 32 scattered 16-byte pieces.
-        const long long mlane = (long long)m0 + q * 32 + lane;
-        const float* rowb_lane = nullptr;
-        if (ep.rowb && mlane < M) {
-          if (ep.rowflag && ep.rowflag[mlane]) rowb_lane = ep.rowb_alt;
-          else rowb_lane = ep.rowb + (long long)((mlane / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
+      const long long mrow0 = (long long)m0 + q * 32;            // first accumulator row of this warp's quarter
+      const long long mlane = mrow0 + lane;
+      // row-broadcast operand: pointer of this lane's OWN row; the transposed loop fetches it by shuffle
+      const float* rowb_lane = nullptr;
+      if (ep.rowb && mlane < M) {
+        if (ep.rowflag && ep.rowflag[mlane]) rowb_lane = ep.rowb_alt;
+        else rowb_lane = ep.rowb + (long long)((mlane / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
+      }
+      const unsigned long long dseed = ep.drop.seed ? ek_seed(ep.drop) : 0ull;
+      // compiled-in fast forms cover: bias, addend, dropout, row broadcast, the common output sets; no activation
+      const int fastmask = (ep.act == EK_ACT_NONE) ? 1 : 0;
+      const bool lean = fastmask != 0;
+      int rows_here = (int)((long long)M - mrow0);
+      rows_here = rows_here < 0 ? 0 : (rows_here > 32 ? 32 : rows_here);
+      int nch = (N - n0 + 31) / 32;
+      nch = nch > bn_eff / 32 ? bn_eff / 32 : nch;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
+      auto release_acc = [&]() {                 // this warp has read everything it needs from the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader issues the MMAs
+          else mbar_arrive(&tempty_bar[buf]);
         }
-        const unsigned long long dseed = ep.drop.seed ? ek_seed(ep.drop) : 0ull;
-        int rows_here = (int)((long long)M - ((long long)m0 + q * 32));
-        rows_here = rows_here < 0 ? 0 : (rows_here > 32 ? 32 : rows_here);
-        const int rg = lane >> 3, c4 = (lane & 7) * 4;        // this lane's row group / 4-column group after transposition
-  #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+      };
+      uint32_t r[32];
+      int c = half;
+      if ((flags & GF_NOEPI) || c >= nch) {
+        release_acc();
+      } else {
+        tc_ld32(tbase + c * 32, r);
+#pragma unroll 1
+        for (; c < nch; c += 2) {
           const int nb = n0 + c * 32;
-          if (nb >= N) break;                      // warp-uniform
-          uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), r);
+          const bool fast = (vec_ok == 15) && nb + 32 <= N && !(flags & GF_NOSTORE);
+          const int n = nb + cg * 4;
+          // operand prefetch in the transposed layout, before waiting for the accumulator chunk
+          float4 add4[8];
+          if (fast && lean && ep.addend && splits == 1) {
+            const float* pa = ep.addend + (mrow0 + rg) * ep.ldadd + n;
+            const long long sa = 4 * ep.ldadd;
+            const int nvalid = (rows_here - rg + 3) >> 2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              add4[i] = (i < nvalid) ? *(const float4*)pa : make_float4(0.f, 0.f, 0.f, 0.f);
+              pa += sa;
+            }
+          }
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (fast && ep.bias && splits == 1) bv = __ldg((const float4*)(ep.bias + n));
+          const bool st_on = dbg && warp == 2 && lane == 0 && it == 0 && c < 4;
+          const int sb = 22 + (c >> 1) * 4;           // slots 22..25 (chunk 0), 26..29 (chunk 2)
+          if (st_on) dbg[(size_t)blockIdx.x * 32 + sb] = gtime_ns();
           tc_wait_ld();
-          if ((vec_ok == 15) && nb + 32 <= N) {
-  #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *(float4*)(stg + lane * 36 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                            __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (st_on) dbg[(size_t)blockIdx.x * 32 + sb + 1] = gtime_ns();
+          if (fast) {
+            if (!(flags & GF_NOSTAGE))
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(stg + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), __uint_as_float(r[4 * j]),
+                     __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
             __syncwarp();
-            const int n = nb + c4;
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ep.bias) bv = __ldg((const float4*)(ep.bias + n));
-  #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + rg;
-              const unsigned long long pr = ep.rowb ? __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rowb_lane, rr) : 0ull;
-              if (rr < rows_here) {
-                const long long mm = (long long)m0 + q * 32 + rr;
-                float4 v = *(const float4*)(stg + rr * 36 + c4);
-                if (splits > 1) {                  // split-K partial sums: fp32 reduction in L2
-                  float* cp = ep.C + mm * ep.ldc + n;
-                  // one 16-byte reduction instead of four 4-byte ones: the L2 atomic units are the bottleneck of split-K
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(v.x), "f"(v.y), "f"(v.z),
-                               "f"(v.w)
+            if (c + 2 < nch) tc_ld32(tbase + (c + 2) * 32, r);      // next chunk's TMEM load overlaps the stores below
+            else release_acc();
+            if (st_on) dbg[(size_t)blockIdx.x * 32 + sb + 2] = gtime_ns();
+            {
+              EpiChunk k;
+              k.stg = stg; k.rg = rg; k.cg = cg; k.nvalid = (rows_here - rg + 3) >> 2; k.row0 = mrow0 + rg; k.n = n; k.nb = nb;
+              if (flags & GF_NOGST) {
+              } else if (splits > 1) {
+                epi_rows_red(ep, k);
+              } else {
+                // outputs this chunk really writes (Cb / Cb2 may be limited to a column range)
+                const int om = fastmask == 0 ? 0
+                             : ((ep.C ? 1 : 0) | ((ep.Cb && (ep.cb_n1 == 0 || nb < ep.cb_n1)) ? 2 : 0) |
+                                ((ep.Cb2 && nb >= ep.cb2_n0) ? 4 : 0));
+                const int feat = (ep.addend ? 1 : 0) | (ep.drop.seed ? 2 : 0) | (ep.rowb ? 4 : 0);
+                switch (om * 8 + feat) {
+                  case 8: epi_rows_fast<1, false>(ep, k, bv, add4); break;
+                  case 9: epi_rows_fast<1, true>(ep, k, bv, add4); break;
+                  case 10: epi_rows_fast<1, false, true>(ep, k, bv, add4, dseed); break;
+                  case 11: epi_rows_fast<1, true, true>(ep, k, bv, add4, dseed); break;
+                  case 16: epi_rows_fast<2, false>(ep, k, bv, add4); break;
+                  case 17: epi_rows_fast<2, true>(ep, k, bv, add4); break;
+                  case 20: epi_rows_fast<2, false, false, true>(ep, k, bv, add4, 0ull, rowb_lane); break;
+                  case 24: epi_rows_fast<3, false>(ep, k, bv, add4); break;
+                  case 25: epi_rows_fast<3, true>(ep, k, bv, add4); break;
+                  case 28: epi_rows_fast<3, false, false, true>(ep, k, bv, add4, 0ull, rowb_lane); break;
+                  case 32: epi_rows_fast<4, false>(ep, k, bv, add4); break;
+                  case 48: epi_rows_fast<6, false>(ep, k, bv, add4); break;
+                  case 52: epi_rows_fast<6, false, false, true>(ep, k, bv, add4, 0ull, rowb_lane); break;
+                  default: epi_rows_general(ep, k, bv, rowb_lane, dseed); break;
+                }
+              }
+            }
+            if (st_on) dbg[(size_t)blockIdx.x * 32 + sb + 3] = gtime_ns();
+            __syncwarp();                          // staging tile is rewritten by the next chunk
+          } else {
+            // cold path (unaligned operands / partial last chunk): staged like the fast path so that the registers are
+            // free again, then this lane walks its own row element by element in a ROLLED loop (one copy of the scalar
+            // epilogue in the instruction stream instead of 32)
+            if (!(flags & GF_NOSTORE)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                sts128(stg + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), __uint_as_float(r[4 * j]),
+                       __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              __syncwarp();
+              if (mlane < M) {
+#pragma unroll 1
+                for (int j = 0; j < 32; ++j) {
+                  const int nn = nb + j;
+                  if (nn >= N) break;
+                  float a;
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a)
+                               : "r"(stg + (uint32_t)(lane * 128 + (((j >> 2) ^ (lane & 7)) << 4) + ((j & 3) << 2)))
                                : "memory");
-                } else {
-                  v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                  if (ep.drop.seed) {
-                    const unsigned long long e0 = (unsigned long long)mm * ep.dropN + ep.dropOff + n;
-                    float mk[4];
-                    ek_drop_multv<4>(ep.drop, dseed, e0, mk);
-                    v.x *= mk[0]; v.y *= mk[1]; v.z *= mk[2]; v.w *= mk[3];
-                  }
-                  if (ep.addend) {
-                    const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + n);
-                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
-                  }
-                  if (ep.rowb) {
-                    const float4 a4 = __ldg((const float4*)((const float*)(uintptr_t)pr + n));
-                    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
-                  }
-                  if (ep.act != EK_ACT_NONE) {
-                    v.x = ek_act(v.x, ep.act); v.y = ek_act(v.y, ep.act); v.z = ek_act(v.z, ep.act); v.w = ek_act(v.w, ep.act);
-                  }
-                  if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
-                  if (ep.Cb && (ep.cb_n1 == 0 || n < ep.cb_n1)) {
-                    uint2 pk;
-                    pk.x = pack16x2(v.x, v.y, ep.cb_fmt);
-                    pk.y = pack16x2(v.z, v.w, ep.cb_fmt);
-                    *(uint2*)(ep.Cb + mm * ep.ldcb + n) = pk;
-                  }
-                  if (ep.Cb2 && n >= ep.cb2_n0) {
-                    uint2 pk;
-                    pk.x = pack16x2(v.x, v.y, ep.cb2_fmt);
-                    pk.y = pack16x2(v.z, v.w, ep.cb2_fmt);
-                    *(uint2*)(ep.Cb2 + mm * ep.ldcb2 + (n - ep.cb2_n0)) = pk;
-                  }
+                  if (splits > 1) atomicAdd(ep.C + mlane * ep.ldc + nn, a);
+                  else ek_epilogue_store(ep, mlane, nn, a);
                 }
               }
             }
             __syncwarp();
-          } else if (mlane < M) {
-            // cold path (unaligned operands / partial last chunk): this lane's row, element by element
-  #pragma unroll 1
-            for (int j = 0; j < 32; ++j) {
-              const int n = nb + j;
-              if (n < N) {
-                if (splits > 1) atomicAdd(ep.C + mlane * ep.ldc + n, __uint_as_float(r[j]));
-                else ek_epilogue_store(ep, mlane, n, __uint_as_float(r[j]));
-              }
-            }
+            if (c + 2 < nch) tc_ld32(tbase + (c + 2) * 32, r);
+            else release_acc();
           }
         }
-      } else {
-        // direct path, software-pipelined: the TMEM load of the next chunk is in flight while this one is stored.
-        // Two warps share each TMEM lane quarter and take alternate 32-column chunks.
-        const long long m = mlane0 + lane;
-        const bool row_ok = m < M;
-        const float* rowb_ptr = nullptr;
-        if (ep.rowb && row_ok) {
-          if (ep.rowflag && ep.rowflag[m]) rowb_ptr = ep.rowb_alt;
-          else rowb_ptr = ep.rowb + (long long)((m / ep.rowb_div) % ep.rowb_mod) * ep.ldrowb;
-        }
-        int nch = (N - n0 + 31) / 32;
-        nch = nch > bn_eff / 32 ? bn_eff / 32 : nch;
-        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN);
-        uint32_t ra[32], rb[32];
-        int c = half;
-        if (c < nch) tc_ld32(tbase + c * 32, ra);
-#pragma unroll 1
-        for (; c < nch; c += 4) {
-          tc_wait_ld();
-          if (c + 2 < nch) tc_ld32(tbase + (c + 2) * 32, rb);
-          if (row_ok && !(flags & GF_NOSTORE)) epi_direct_chunk(ep, ra, m, n0 + c * 32, N, vec_ok, rowb_ptr);
-          if (c + 2 < nch) {
-            tc_wait_ld();
-            if (c + 4 < nch) tc_ld32(tbase + (c + 4) * 32, ra);
-            if (row_ok && !(flags & GF_NOSTORE)) epi_direct_chunk(ep, rb, m, n0 + (c + 2) * 32, N, vec_ok, rowb_ptr);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[buf]), 0));   // the leader issues the MMAs
-        else mbar_arrive(&tempty_bar[buf]);
       }
       if (warp == 2 && lane == 0 && it < 6) GSTAMP(5 + 2 * it);  // epilogue of work unit `it` done (this warp)
     }
@@ -879,6 +937,18 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   // CTA pairs (cluster of 2 along M sharing the B tile): opt-in, needs two M tiles and a >= 128 wide tile
   int cl = (want_cluster && bn >= 128 && ek_div_up(M, BM) >= 2) ? 2 : 1;
   if (want_cg2 && bn >= 128 && ek_div_up(M, BM) >= 2) cl = 3;
+  // CTA pairs (cta_group::2, 256 x 256 per pair, each CTA stages half of B) by default where they measured faster with
+  // the coalesced epilogue (profiles/r02_gemm_probe.json): long K loops or very many tiles; an even number of M tiles
+  // keeps every pair full.  EKAID_B200_CG2=0 turns the rule off.
+  static int cg2_auto = -1;
+  if (cg2_auto < 0) {
+    const char* e = getenv("EKAID_B200_CG2");
+    cg2_auto = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (cg2_auto && force_bn == 0 && cl == 1 && bn == 256 && N >= 256 && (ek_div_up(M, BM) % 2) == 0) {
+    const long long tiles = (long long)ek_div_up(M, BM) * ek_div_up(N, 256);
+    if ((K >= 2048 && tiles >= 100) || tiles >= 12LL * num_sms()) cl = 3;
+  }
   CUtensorMap ta, tb;
   int rc;
   if (!transA) rc = make_tmap(&ta, A, M, K, lda, BM);                 // [M rows, K cols], box {64, 128}

@@ -23,8 +23,14 @@ __global__ void embed_gather_kernel(const long long* __restrict__ q, const float
 // positions) is spread over ed/32 CTAs instead of serialising one.
 __global__ void __launch_bounds__(128)
 embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict__ dE, long long ldde, int B, int L,
-                        int ed, float* __restrict__ demb) {
+                        int ed, float* __restrict__ demb, int padding_idx) {
   ek_pdl_prologue();
+  if ((int)blockIdx.x == padding_idx) {
+    // nn.Embedding(padding_idx=ntoken) (language_model.py:26): that row never receives a gradient, whatever the batch holds
+    const int c = blockIdx.y * 32 + (threadIdx.x & 31);
+    if (threadIdx.x < 32 && c < ed) demb[(size_t)blockIdx.x * ed + c] = 0.f;
+    return;
+  }
   extern __shared__ int rows[];        // up to B*L matching rows
   __shared__ int count;
   __shared__ float part[4][32];
@@ -230,9 +236,9 @@ int ek_embed_gather_launch(int is_bf16, const long long* q, const float* emb, co
   return EK_OK;
 }
 int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ldde, int B, int L, int ed, int V,
-                               float* demb, cudaStream_t st) {
+                               float* demb, int padding_idx, cudaStream_t st) {
   ek_launch(embed_gather_bwd_kernel, dim3(V, ek_div_up(ed, 32)), 128, (size_t)B * L * sizeof(int), st, q, dE, ldde, B, L, ed,
-                                                                                                  demb);
+                                                                                                  demb, padding_idx);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -14,6 +14,7 @@ Tensors that feed GEMMs are kept in the operand type T of the precision mode: bf
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from typing import Optional
@@ -46,19 +47,43 @@ def _dst(key_ptr, shape, dev):
     return torch.empty(shape, dtype=torch.float32, device=dev)
 
 
-_rng_state = {}
+_rng_state = {}      # {device: [seed tensor, torch seed it was derived from]}
+
+
+def _mix64(x: int) -> int:
+    """splitmix64 finaliser (host side): decorrelates (torch seed, rank, device) into the 63-bit device seed."""
+    x &= 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return (x ^ (x >> 31)) & 0x7FFFFFFFFFFFFFFF
 
 
 def rng_state(dev) -> torch.Tensor:
-    """Device-resident 64-bit seed of the dropout masks (one per device), initialised from torch's seed."""
+    """Device-resident 64-bit seed of the dropout masks (one per device).  Derived from torch's seed, the data-parallel
+    rank and the device index, so ranks draw different masks; re-derived when `torch.manual_seed` has been called since
+    (never during a CUDA-graph capture: the tensor's address is what captured kernels read)."""
+    dev = torch.device(dev)
     key = str(dev)
-    if key not in _rng_state:
-        _rng_state[key] = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=dev)
-    return _rng_state[key]
+    seed_now = torch.initial_seed()
+    st = _rng_state.get(key)
+    if st is not None and (st[1] == seed_now or torch.cuda.is_current_stream_capturing()):
+        return st[0]
+    rank = int(os.environ.get("RANK", "0"))
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    val = _mix64(seed_now + 0x9E3779B97F4A7C15 * (rank + 1) + 0xD1B54A32D192ED03 * (idx + 1))
+    if st is None:
+        st = [torch.tensor([val], dtype=torch.int64, device=dev), seed_now]
+        _rng_state[key] = st
+    else:
+        st[0].copy_(torch.tensor([val], dtype=torch.int64))
+        st[1] = seed_now
+    return st[0]
 
 
 def rng_advance(dev) -> None:
-    """Draw fresh dropout masks for the next step (a kernel: stays valid inside a captured CUDA graph)."""
+    """Draw fresh dropout masks for the next forward (a kernel: stays valid inside a captured CUDA graph).  Called by
+    every train-mode forward entry point (ChangeDetector.forward, the stand-alone relation encoders), like nn.Dropout
+    draws fresh masks on every call."""
     call("rng_advance", rng_state(dev).data_ptr())
 
 
@@ -497,6 +522,7 @@ class LinearFn(torch.autograd.Function):
 # question path starts its longest serial stretch -- the moment to put independent work next to it (the optimizer update
 # of the image-path parameters, whose gradients are all enqueued by then).
 BPTT_HOOK = None
+CHECK_TOKEN_RANGE = os.environ.get("EKAID_B200_CHECK_TOKENS", "1") != "0"
 GRU_SEQ = os.environ.get("EKAID_B200_GRU_SEQ", "1") != "0"     # 0: per-step GEMM + cell kernels on the bf16 path too
 GRU_SEQ_MAX_BATCH = 64
 _barrier_bufs = {}
@@ -531,6 +557,41 @@ def _gru_seq_ok(pc, dev, B, H):
         return False
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     return H // 8 <= sms and B * 64 + 192 * 1024 <= 227 * 1024
+
+
+_fork_pool = {}
+FORK_ENABLED = os.environ.get("EKAID_B200_FORK", "1") != "0"      # bench.py serialises the branches for per-kernel timing
+
+
+class Fork:
+    """Run independent kernels of one stage on parallel streams.  The GEMM kernels are persistent (one CTA per SM): when
+    two independent ones are in flight, the second one's CTAs move onto SMs as the first one's CTAs retire, so the
+    tail of one launch (last-tile epilogue, idle SMs of a partial wave) overlaps the head of the next.  Inside a captured
+    CUDA graph this becomes parallel branches.  All tensors are allocated on the calling stream BEFORE the fork and the
+    caller joins before using any result, which keeps the caching allocator's stream bookkeeping trivial.
+
+        f = Fork(dev, 2); with f.branch(0): ...; with f.branch(1): ...; (work on the calling stream); f.join()
+    """
+
+    def __init__(self, dev, n: int):
+        key = str(dev)
+        pool = _fork_pool.setdefault(key, [])
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(dev))
+        self.cur = torch.cuda.current_stream(dev)
+        self.on = FORK_ENABLED
+        self.streams = pool[:n] if self.on else [self.cur] * n
+        if self.on:
+            for st in self.streams:
+                st.wait_stream(self.cur)
+
+    def branch(self, i: int):
+        return torch.cuda.stream(self.streams[i])
+
+    def join(self):
+        if self.on:
+            for st in self.streams:
+                self.cur.wait_stream(st)
 
 
 class GRUFn(torch.autograd.Function):
@@ -605,13 +666,18 @@ class QuestionFn(torch.autograd.Function):
     """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156)."""
 
     @staticmethod
-    def forward(ctx, pc: PC, drop, question, emb, emb2, Wih, Whh, bih, bhh, W1, b1, w2, b2):
+    def forward(ctx, pc: PC, drop, question, emb, emb2, Wih, Whh, bih, bhh, W1, b1, w2, b2, padding_idx=-1):
         lib.require_device()
         dev = emb.device
         B, L = question.shape
         ed = emb.shape[1]
         H = Whh.shape[1]
         q = question.detach().to(torch.int64).contiguous()
+        if CHECK_TOKEN_RANGE and not torch.cuda.is_current_stream_capturing():
+            # nn.Embedding raises on ids outside the table; the gather kernel would read out of bounds (one host sync,
+            # skipped inside a CUDA-graph capture; EKAID_B200_CHECK_TOKENS=0 turns it off)
+            if bool(((q < 0) | (q >= emb.shape[0])).any()):
+                raise IndexError("question holds token ids outside [0, %d)" % emb.shape[0])
         embc, emb2c = _f32c(emb), _f32c(emb2)
         E = torch.empty(L * B, 2 * ed, dtype=pc.T, device=dev)
         call("embed_gather", pc.f, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
@@ -660,6 +726,7 @@ class QuestionFn(torch.autograd.Function):
         ctx.keys = {k: t.data_ptr() for k, t in (("emb", emb), ("Wih", Wih), ("Whh", Whh), ("bih", bih), ("bhh", bhh),
                                                  ("b1", b1), ("b2", b2))}
         ctx.dims = (B, L, ed, H, emb.shape[0])
+        ctx.padding_idx = int(padding_idx)
         ctx.saved = (q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd)
         return qv
 
@@ -742,12 +809,13 @@ class QuestionFn(torch.autograd.Function):
             colsum(dgh, L * B, 3 * H, out=dbhh)
         with torch.cuda.stream(br2):
             gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1, out=dE)       # only the trainable table's columns
-            call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr())
+            call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr(),
+                 ctx.padding_idx)
         gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=dWih)
         colsum(dgi, L * B, 3 * H, out=dbih)
         cur.wait_stream(br1)
         cur.wait_stream(br2)
-        return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2
+        return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -919,10 +987,14 @@ class RelationFn(torch.autograd.Function):
             call("drop_fanout", pc.f, Sf.data_ptr(), Sf.stride(0), drop.seed, site0 + 2, float(drop.p_fc), site0 + 3,
                  float(drop.p_fc), M, D, Sq.data_ptr(), Sk.data_ptr(), D)
             QKZ = torch.empty(M, W, dtype=pc.T, device=dev)
-            for src, lo, hi in ((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W)):
+            # three independent projections: the big Z GEMM on this stream, query / key next to it
+            fk = Fork(dev, 2)
+            for bi, (src, lo, hi) in enumerate(((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W))):
                 out = QKZ[:, lo:hi]
-                gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=None if pc.bf16 else out,
-                     Cb=out if pc.bf16 else None)
+                with (fk.branch(bi) if bi < 2 else contextlib.nullcontext()):
+                    gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=None if pc.bf16 else out,
+                         Cb=out if pc.bf16 else None)
+            fk.join()
         cond, lbias, gbias = prep["cond"], prep["lbias"], prep["gbias"]
         ctx.geo = prep["geo"]
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
@@ -1031,27 +1103,40 @@ class RelationFn(torch.autograd.Function):
             gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX)         # residual + dSf Wv
         else:
             dWz = torch.empty(H * D, D, dtype=torch.float32, device=dev)
-            for src, lo, hi, dst in ((Sq, 0, D, dWq), (Sk, D, 2 * D, dWk), (Sf, 2 * D, W, dWz)):
-                gemm(dQKZ[:, lo:hi], src, hi - lo, D, M, transA=1, transB=1, C=dst)
-            for h in range(H):
-                call("copy_f32", dWz[h * D:(h + 1) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(), H * D, D, D)
-            # dSf = mask_q * (dQ Wq) + mask_k * (dK Wk) + dZ Wz: the three products are chained through the GEMM epilogue
-            # (dropout mask of the forward's query / key inputs, then "+ addend"), the last one writes the operand type
             acc = torch.empty(M, D, dtype=torch.float32, device=dev)
             dSf = torch.empty(M, D, dtype=pc.T, device=dev)
+            dVq = torch.empty(M, Dq, dtype=torch.float32, device=dev)
+            dqv = torch.empty(B, Dq, dtype=torch.float32, device=dev)
+            # the weight gradients are leaves of the backward graph: they run on two side streams next to the dgrad chain
+            fk = Fork(dev, 2)
+            with fk.branch(0):
+                gemm(dQKZ[:, 2 * D:W], Sf, W - 2 * D, D, M, transA=1, transB=1, C=dWz)
+                for h in range(H):
+                    call("copy_f32", dWz[h * D:(h + 1) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(), H * D, D, D)
+            with fk.branch(1):
+                gemm(dQKZ[:, 0:D], Sq, D, D, M, transA=1, transB=1, C=dWq)
+                gemm(dQKZ[:, D:2 * D], Sk, D, D, M, transA=1, transB=1, C=dWk)
+            # dSf = mask_q * (dQ Wq) + mask_k * (dK Wk) + dZ Wz: the three products are chained through the GEMM epilogue
+            # (dropout mask of the forward's query / key inputs, then "+ addend"), the last one writes the operand type
             gemm(dQKZ[:, 0:D], WqkzT[0:D], M, D, D, transB=1, C=acc, drop=drop.a(site0 + 2, drop.p_fc))
             gemm(dQKZ[:, D:2 * D], WqkzT[D:2 * D], M, D, D, transB=1, addend=acc, C=acc, drop=drop.a(site0 + 3, drop.p_fc))
             gemm(dQKZ[:, 2 * D:W], WqkzT[2 * D:W], M, D, W - 2 * D, transB=1, addend=acc,
                  C=None if pc.bf16 else dSf, Cb=dSf if pc.bf16 else None)
-            gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
-            colsum_many([(dOut, dbout), (dQKZ[:, :D], dbq), (dQKZ[:, D:2 * D], dbk), (dSf, dbsw)], M)   # one launch
-            # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
-            # (index = row * (D + Dq) + column); the node half also adds the residual gradient
+            fk.join()
+            # everything below needs dSf: wgrad of self_weights + the bias sums on one side stream, the question half of
+            # the input gradient on the other, the node half (+ residual) here
             s1 = drop.a(site0 + 1, drop.p_fc)
-            gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX, drop=s1 + (D + Dq, 0))
-            dVq = gemm_f32out(dSf, WswT[:, D:], M, Dq, D, transB=1, drop=s1 + (D + Dq, D))
-            dqv = torch.empty(B, Dq, dtype=torch.float32, device=dev)
-            call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(), dqv.data_ptr())
+            fk = Fork(dev, 2)
+            with fk.branch(0):
+                gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
+                colsum_many([(dOut, dbout), (dQKZ[:, :D], dbq), (dQKZ[:, D:2 * D], dbk), (dSf, dbsw)], M)   # one launch
+            with fk.branch(1):
+                # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
+                # (index = row * (D + Dq) + column)
+                gemm(dSf, WswT[:, D:], M, Dq, D, transB=1, C=dVq, drop=s1 + (D + Dq, D))
+                call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(), dqv.data_ptr())
+            gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX, drop=s1 + (D + Dq, 0))   # + residual gradient
+            fk.join()
         return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWq, dbq, dWk, dbk, dWo2, dbout, dp0, dp1,
                 None, None, None, None)
 

@@ -35,7 +35,7 @@ with warnings.catch_warnings():
 
 from . import lib as _lib
 from .functions import (PC, Drop, EdgeAttentionFn, FusionFn, GRUFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn,
-                        WNormManyFn)
+                        WNormManyFn, rng_advance)
 
 
 def _default_precision() -> str:
@@ -321,6 +321,8 @@ class ImplicitRelationEncoder(nn.Module):
                              % (self.implicit_relation.pos_emb_dim, tuple(position_embedding.shape)))
         pc = PC(self.precision)
         B, N, D = v.shape
+        if self.training:
+            rng_advance(v.device)        # fresh dropout masks per forward, like nn.Dropout
         out, _, P = self.implicit_relation.relation_step(pc, v.reshape(B * N, D), None, q, position_embedding, None,
                                                          B, B, B, N)
         return _maybe_inplace(v, out), [None, P]
@@ -347,6 +349,8 @@ class ExplicitRelationEncoder(nn.Module):
             raise NotImplementedError("only v_dim == out_dim, residual_connection=True, num_steps=1 (reference config)")
         pc = PC(self.precision)
         B, N, D = v.shape
+        if self.training:
+            rng_advance(v.device)        # fresh dropout masks per forward, like nn.Dropout
         out, _, P = self.explicit_relation.relation_step(pc, v.reshape(B * N, D), None, q, exp_adj_matrix, None,
                                                          B, B, B, N)
         return _maybe_inplace(v, out), [None, P]
@@ -494,6 +498,8 @@ class ChangeDetector(nn.Module):
         self.precision = _default_precision()
         # tests only: force every dropout probability (0.0 runs the train-mode code path without masks)
         self.dropout_override = None
+        # tests only: keep the dropout seed where it is (finite-difference checks need the SAME masks in every forward)
+        self.freeze_dropout_seed = False
         self._side = None
         self._qv_keepalive = None
 
@@ -537,7 +543,8 @@ class ChangeDetector(nn.Module):
                     p_qv=self.q_att.drop.p if ov is None else ov)
         return QuestionFn.apply(pc, drop, question, self.w_emb.emb.weight, self.w_emb.emb_.weight, rnn.weight_ih_l0,
                                 rnn.weight_hh_l0, rnn.bias_ih_l0, rnn.bias_hh_l0, wn_weight(w1), w1.bias,
-                                wn_weight(w2), w2.bias)
+                                wn_weight(w2), w2.bias,
+                                self.w_emb.emb.padding_idx if self.w_emb.emb.padding_idx is not None else -1)
 
     def position_emb(self, bb):
         """The reference materialises a [B,N,K,64] fp64 embedding here (modules.py:162-166); the CUDA path
@@ -563,6 +570,10 @@ class ChangeDetector(nn.Module):
         G = 2 * B
         _lib.require_device()            # no CPU / PyTorch fallback: fail loudly without an sm_100 device
         dev = input_1.device
+        if self.training and not self.freeze_dropout_seed:
+            # every train-mode forward draws fresh dropout masks (the reference's nn.Dropout modules do): the device-side
+            # seed is advanced by a kernel, so this also holds for replays of a captured CUDA graph
+            rng_advance(dev)
         # The question path is a chain of 20 small, latency-bound GRU steps: it runs on its own stream while this
         # stream does the work that does not depend on it (ROI projection, weight normalisation).  Autograd replays
         # the same split in backward (BPTT next to the weight-norm / img gradients); a captured CUDA graph keeps it.

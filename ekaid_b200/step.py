@@ -16,7 +16,7 @@ from typing import Callable, Optional, Sequence
 import torch
 
 from . import functions, lib
-from .functions import onehot_adj, rng_advance
+from .functions import onehot_adj
 from .modules import ChangeDetector
 
 
@@ -291,8 +291,8 @@ class GraphFusionStep:
         """optimizer.zero_grad -> forward -> backward -> [all-reduce(mean)] -> Adam  (train_mimic.py:220-269).
         Returns the (device) loss tensor; no host sync happens here."""
         self.opt.zero_grad()
-        if self.cd.training:
-            rng_advance(self.opt.flat.device)      # fresh dropout masks (a kernel: replays draw new masks too)
+        # (fresh dropout masks: ChangeDetector.forward advances the device-side seed itself in train mode -- a kernel, so
+        # replays of the captured step draw new masks too)
         total = self.loss(inputs, labels, masks)
         self._fired = [0] * self._nseg
         self._done = [False] * self._nseg

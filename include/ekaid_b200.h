@@ -220,8 +220,10 @@ int ekaid_att_pool_bwd(int is_bf16, const float* dA, const float* dattw, const f
 /* E[l*B+b,:] = [emb[q[b,l]] | emb_[q[b,l]]]   (:48-53) */
 int ekaid_embed_gather(int is_bf16, const int64_t* q, const float* emb, const float* emb2, int B, int L, int ed,
                        void* E, void* stream);
+/* demb[v,:] = sum of dE rows whose token is v; row padding_idx gets zeros (nn.Embedding(padding_idx=ntoken),
+ * language_model.py:26: that row is never trained), -1 = no padding row.  Token ids must lie in [0, V). */
 int ekaid_embed_gather_bwd(const int64_t* q, const float* dE, int64_t ldde, int B, int L, int ed, int V, float* demb,
-                           void* stream);
+                           int padding_idx, void* stream);
 /* one GRU step (:106-115): gi, gh [B,3H] incl. biases; gates [B,4H] saves (r,z,n,gh_n).  gh_reset (optional, [3H]):
  * after use gh is overwritten with it, so the next step's split-K "gh += h W_hh^T" GEMM starts from the bias */
 int ekaid_gru_cell_fwd(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h, void* hT,

@@ -39,8 +39,11 @@ def wn(sd: Dict[str, Tensor], prefix: str) -> Tensor:
 # question path
 # ----------------------------------------------------------------------------------------------
 def word_embedding(sd, question: Tensor) -> Tensor:
-    """models/language_model.py:48-53  (two tables, concatenated; dropout p=0)."""
-    return torch.cat((sd["w_emb.emb.weight"][question], sd["w_emb.emb_.weight"][question]), 2)
+    """models/language_model.py:48-53  (two tables, concatenated; dropout p=0).  Both tables are
+    nn.Embedding(ntoken + 1, 300, padding_idx=ntoken) (:26-29): row ntoken never receives a gradient."""
+    w, w_ = sd["w_emb.emb.weight"], sd["w_emb.emb_.weight"]
+    return torch.cat((F.embedding(question, w, padding_idx=w.shape[0] - 1),
+                      F.embedding(question, w_, padding_idx=w_.shape[0] - 1)), 2)
 
 
 def gru_all(sd, x: Tensor) -> Tensor:

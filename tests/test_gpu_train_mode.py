@@ -99,6 +99,7 @@ def test_train_mode_gradients_match_finite_differences():
     sd, inp, _ = case_inputs(meta)
     m = build_model(meta, sd, "fp32", dev)
     m.train()
+    m.freeze_dropout_seed = True
     dinp = to_dev(inp, dev)
     gw = torch.Generator().manual_seed(7)
     cot = None
@@ -145,3 +146,37 @@ def test_train_mode_gradients_match_finite_differences():
         tol = 6e-2 if ("pair_pos" in k or ".bias.main" in k) else 3e-2      # tiny, kink-rich parameters
         assert abs(fd - analytic) < tol * abs(analytic) + 1e-3, (k, analytic, fd, eps)
     print("finite-difference check:", [(k.split(".")[-3:], round(a, 4), round(f, 4)) for k, a, f in report])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_every_train_forward_draws_fresh_masks(precision):
+    """The reference's nn.Dropout modules draw new masks on every forward; so must the drop-in when it is used in the
+    reference's own loop (no GraphFusionStep): two consecutive train-mode forwards differ, a frozen seed repeats, and
+    torch.manual_seed re-derives the device seed."""
+    from ekaid_b200.functions import rng_state
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    m.train()
+    dinp = to_dev(inp, dev)
+    with torch.no_grad():
+        a = m(*dinp)[3].clone()
+        b = m(*dinp)[3].clone()
+        assert rel_err(a, b) > 1e-3, "two train-mode forwards reused the same dropout masks"
+        m.freeze_dropout_seed = True
+        c = m(*dinp)[3].clone()
+        d = m(*dinp)[3].clone()
+        assert torch.equal(c, d)
+        m.freeze_dropout_seed = False
+        # stand-alone encoder entry point advances too
+        enc = m.spatial_relation.train()
+        v = torch.randn(2, 52, 1024, device=dev)
+        q = torch.randn(2, 1024, device=dev)
+        o1 = enc(v.clone(), dinp[2], q)[0].clone()
+        o2 = enc(v.clone(), dinp[2], q)[0].clone()
+        assert rel_err(o1, o2) > 1e-3
+        s0 = int(rng_state(dev).item())
+        torch.manual_seed(torch.initial_seed() + 1)
+        s1 = int(rng_state(dev).item())
+        assert s0 != s1, "torch.manual_seed did not re-derive the device-side dropout seed"
