@@ -31,19 +31,31 @@ ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
 DEBUG_SINK = None
 
 
-# Gradient slots (step.FlatAdam): {parameter data_ptr: preallocated fp32 gradient view in the flat gradient buffer}.
-# When a parameter has a slot, the backward kernels write its gradient straight into the slot and hand that tensor to
-# autograd, whose AccumulateGrad adopts it without a copy (the parameter's .grad must be None at backward time) -- no
-# per-parameter "grad += new" kernels and no gradient memset.  Empty dict = plain autograd behaviour.
+# Gradient slots (step.FlatAdam): {parameter data_ptr: (preallocated fp32 gradient view in the flat gradient buffer,
+# weak reference to the parameter)}.  When a parameter has a slot, the backward kernels write its gradient straight into
+# the slot and hand that tensor to autograd, whose AccumulateGrad adopts it without a copy -- no per-parameter
+# "grad += new" kernels and no gradient memset.  That is only valid for the FIRST gradient a parameter receives after
+# its .grad was reset: a second contribution (gradient accumulation without zero_grad, or a module applied twice in one
+# graph, like the reference's `semantic_relation.forward(bef)` then `.forward(aft)`) gets a fresh tensor, which autograd
+# adds onto the first one.  Empty dict = plain autograd behaviour.
 GRAD_SLOTS = {}
+_SLOTS_WRITTEN = set()      # slots handed out since the owner's last zero_grad (FlatAdam.zero_grad clears it)
+
+
+def slots_reset() -> None:
+    _SLOTS_WRITTEN.clear()
 
 
 def _dst(key_ptr, shape, dev):
-    """Destination of a parameter gradient: its slot when registered, else a fresh tensor."""
-    slot = GRAD_SLOTS.get(key_ptr) if GRAD_SLOTS else None
-    if slot is not None and tuple(slot.shape) == tuple(shape):
-        # a FRESH view object: AccumulateGrad only adopts a gradient nobody else references (use_count == 1)
-        return slot.view(slot.shape)
+    """Destination of a parameter gradient: its slot on first use after a gradient reset, else a fresh tensor."""
+    ent = GRAD_SLOTS.get(key_ptr) if GRAD_SLOTS else None
+    if ent is not None:
+        slot, ref = ent
+        p = ref()
+        if (p is not None and p.grad is None and key_ptr not in _SLOTS_WRITTEN and tuple(slot.shape) == tuple(shape)):
+            _SLOTS_WRITTEN.add(key_ptr)
+            # a FRESH view object: AccumulateGrad only adopts a gradient nobody else references (use_count == 1)
+            return slot.view(slot.shape)
     return torch.empty(shape, dtype=torch.float32, device=dev)
 
 
@@ -502,11 +514,20 @@ class LinearFn(torch.autograd.Function):
         M, N = dy2.shape
         K = ctx.xT.shape[1]
         dyT = to_T(pc, dy2)
-        dW = gemm_f32out(dyT, ctx.xT, N, K, M, transA=1, transB=1, out=_dst(ctx.keys[0], (N, K), dy2.device))
-        db = colsum(dy2, M, N, out=_dst(ctx.keys[1], (N,), dy2.device)) if ctx.has_b else None
+        dW = _dst(ctx.keys[0], (N, K), dy2.device)
+        db = _dst(ctx.keys[1], (N,), dy2.device) if ctx.has_b else None
         dx = dx2 = None
-        if ctx.need[0] or ctx.need[1]:
-            dfull = gemm_f32out(dyT, ctx.WT, M, K, N, transB=1)
+        need_dx = ctx.need[0] or ctx.need[1]
+        dfull = torch.empty(M, K, dtype=torch.float32, device=dy2.device) if need_dx else None
+        fk = Fork(dy2.device, 1)
+        with fk.branch(0) if need_dx else contextlib.nullcontext():
+            gemm_f32out(dyT, ctx.xT, N, K, M, transA=1, transB=1, out=dW)
+            if ctx.has_b:
+                colsum(dy2, M, N, out=db)
+        if need_dx:
+            gemm_f32out(dyT, ctx.WT, M, K, N, transB=1, out=dfull)
+        fk.join()
+        if need_dx:
             sa, sb, Ma = ctx.shapes
             if ctx.need[0]:
                 dx = dfull[:Ma].view(sa)
@@ -585,7 +606,10 @@ class Fork:
             for st in self.streams:
                 st.wait_stream(self.cur)
 
-    def branch(self, i: int):
+    def branch(self, i: int, resync: bool = False):
+        """Context of branch i; resync=True makes the branch wait for what the calling stream has enqueued since the fork."""
+        if resync and self.on:
+            self.streams[i].wait_stream(self.cur)
         return torch.cuda.stream(self.streams[i])
 
     def join(self):
@@ -1215,27 +1239,38 @@ class FusionFn(torch.autograd.Function):
              M, N, D, dim, dXc.data_ptr(), dE.data_ptr(), dpa.data_ptr(),
              1.0 / (1.0 - drop.p_embed) if don else 1.0)
         kk = ctx.keys
+        # every buffer first (on this stream), then the weight / bias gradients -- leaves of the backward graph -- go to
+        # side streams and run next to the dgrad chain
         dwa = _dst(kk["wa"], (1, dim), dev)
-        colsum(E, M, dim, rowscale=dpa, out=dwa.view(dim))
-        dba = colsum(dpa.view(-1, 1), M, 1, out=_dst(kk["ba"], (1,), dev))
-        dWe = gemm_f32out(dE, CAT, dim, 3 * D, M, transA=1, transB=1, out=_dst(kk["We"], (dim, 3 * D), dev))
-        dbe = colsum(dE, M, dim, out=_dst(kk["be"], (dim,), dev))
-        dCAT = gemm_f32out(dE, WeT, M, 3 * D, dim, transB=1)
+        dba = _dst(kk["ba"], (1,), dev)
+        dWe = _dst(kk["We"], (dim, 3 * D), dev)
+        dbe = _dst(kk["be"], (dim,), dev)
+        dCAT = torch.empty(M, 3 * D, dtype=torch.float32, device=dev)
         dpre = torch.empty(M, 2 * D, dtype=pc.T, device=dev)
+        dWcg = torch.empty(2 * D, 2 * D, dtype=torch.float32, device=dev)
+        blocks = {name: _dst(kk[name], (D, D), dev) for name in ("C2", "C1", "G2", "G1")}
+        dbC2 = _dst(kk["bC2"], (D,), dev)
+        dbG2 = _dst(kk["bG2"], (D,), dev)
+        dX3 = torch.empty(M, D, dtype=torch.float32, device=dev)
+        fk = Fork(dev, 2)
+        with fk.branch(0):
+            colsum(E, M, dim, rowscale=dpa, out=dwa.view(dim))
+            colsum(dpa.view(-1, 1), M, 1, out=dba)
+            gemm_f32out(dE, CAT, dim, 3 * D, M, transA=1, transB=1, out=dWe)
+            colsum(dE, M, dim, out=dbe)
+        gemm_f32out(dE, WeT, M, 3 * D, dim, transB=1, out=dCAT)
         call("gate_bwd", pc.f, dCAT.data_ptr(), cx.data_ptr(), gt.data_ptr(), M, D, dpre.data_ptr(),
              drop.seed if don else None, 20, 21, drop.p_fuse if don else 0.0)
-        dWcg = gemm_f32out(dpre, CAT[:, :2 * D], 2 * D, 2 * D, M, transA=1, transB=1)
-        # blocks of the fused [[context2 | context1], [gate2 | gate1]] gradient -> parameter-shaped (contiguous) tensors
-        blocks = {}
-        for name, r0, c0 in (("C2", 0, 0), ("C1", 0, D), ("G2", D, 0), ("G1", D, D)):
-            dstb = _dst(kk[name], (D, D), dev)
-            call("copy_f32", dWcg[r0:r0 + D, c0:c0 + D].data_ptr(), 2 * D, dstb.data_ptr(), D, D, D)
-            blocks[name] = dstb
-        dbC2 = colsum(dpre[:, :D], M, D, out=_dst(kk["bC2"], (D,), dev))
-        dbG2 = colsum(dpre[:, D:], M, D, out=_dst(kk["bG2"], (D,), dev))
+        with fk.branch(1, resync=True):
+            gemm_f32out(dpre, CAT[:, :2 * D], 2 * D, 2 * D, M, transA=1, transB=1, out=dWcg)
+            # blocks of the fused [[context2 | context1], [gate2 | gate1]] gradient -> parameter-shaped (contiguous) tensors
+            for name, r0, c0 in (("C2", 0, 0), ("C1", 0, D), ("G2", D, 0), ("G1", D, D)):
+                call("copy_f32", dWcg[r0:r0 + D, c0:c0 + D].data_ptr(), 2 * D, blocks[name].data_ptr(), D, D, D)
+            colsum(dpre[:, :D], M, D, out=dbC2)
+            colsum(dpre[:, D:], M, D, out=dbG2)
         gemm(dpre, WcgT, M, 2 * D, 2 * D, transB=1, addend=dCAT[:, :2 * D], C=dCAT[:, :2 * D])
-        dX3 = torch.empty(M, D, dtype=torch.float32, device=dev)
         call("combine_diff_bwd", dXc.data_ptr(), dCAT.data_ptr(), BN, D, ctx.mode, c1, c2, c3, dX3.data_ptr())
+        fk.join()
         return (None, None, None, None, None, dX3, blocks["C1"], blocks["C2"], dbC2, blocks["G1"], blocks["G2"], dbG2, dWe,
                 dbe, dwa, dba)
 

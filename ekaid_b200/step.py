@@ -11,6 +11,7 @@ do in the reference; without one, a fixed cotangent stands in for the decoder gr
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -46,7 +47,7 @@ class FlatAdam:
             self.slots.append(slot)
             p.grad = None
             # the backward kernels write this parameter's gradient straight into its slot (functions.GRAD_SLOTS)
-            functions.GRAD_SLOTS[p.data_ptr()] = slot
+            functions.GRAD_SLOTS[p.data_ptr()] = (slot, weakref.ref(p))
             off += (k + al - 1) // al * al
             self.offsets.append(off)
         self.params = params
@@ -58,6 +59,18 @@ class FlatAdam:
         autograd adopts the slot tensors instead of launching one `grad += new` kernel per parameter."""
         for p in self.params:
             p.grad = None
+        functions.slots_reset()
+
+    def close(self):
+        """Unregister the gradient slots (the parameters keep their storage in the flat buffer)."""
+        for p in self.params:
+            functions.GRAD_SLOTS.pop(p.data_ptr(), None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def sync_slots(self, first: int = 0, last: Optional[int] = None, dry_run: bool = False) -> int:
         """Gradients that autograd did NOT adopt as their slot view (it clones a gradient whenever somebody else still

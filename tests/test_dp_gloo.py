@@ -60,7 +60,7 @@ def _worker(rank, world, port, outfile):
     for p, slot in zip(opt.params, opt.slots):
         k = names[id(p)]
         assert slot.data_ptr() >= opt.grad.data_ptr() and p.data_ptr() % 256 == opt.flat.data_ptr() % 256
-        assert functions.GRAD_SLOTS[p.data_ptr()] is slot and slot.shape == p.shape
+        assert functions.GRAD_SLOTS[p.data_ptr()][0] is slot and slot.shape == p.shape
         if k in grads:
             slot.copy_(grads[k])
     allreduce_mean_(opt.grad)

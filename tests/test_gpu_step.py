@@ -147,3 +147,58 @@ def test_step_pipeline_matches_plain_replay():
     assert len(set(losses["plain"])) == len(host)
     for k in params["plain"]:
         assert float((params["plain"][k] - params["pipeline"][k]).abs().max()) < 1e-6, k
+
+
+def test_second_gradient_contribution_accumulates_instead_of_overwriting():
+    """A parameter that receives two gradient contributions before its .grad is reset -- a second backward without
+    zero_grad (gradient accumulation), or one module applied twice in a graph -- must end up with the SUM: only the
+    first contribution may be written into the flat slot, later ones are added by autograd."""
+    from ekaid_b200 import functions
+    from ekaid_b200.step import FlatAdam
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, _ = case_inputs(meta)
+    dinp = to_dev(inp, dev)
+    ref = build_model(meta, sd, "fp32", dev)
+    _loss(ref(*dinp)).backward()
+    g1 = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+    m = build_model(meta, sd, "fp32", dev)
+    try:
+        opt = FlatAdam(m.live_parameters(), lr=1e-3)
+        opt.zero_grad()
+        _loss(m(*dinp)).backward()
+        _loss(m(*dinp)).backward()            # no zero_grad in between
+        torch.cuda.synchronize()
+        n = 0
+        for k, p in m.named_parameters():
+            if k in g1 and p.grad is not None:
+                err = float((p.grad - 2 * g1[k]).abs().max() / (2 * g1[k].abs().max() + 1e-30))
+                assert err < 1e-5, (k, err)
+                n += 1
+        assert n > 60
+        # the encoder applied twice in ONE graph (reference style: forward(bef) then forward(aft))
+        opt.zero_grad()
+        enc = m.spatial_relation
+        v1 = torch.randn(2, 52, 1024, device=dev)
+        v2 = torch.randn(2, 52, 1024, device=dev)
+        q = torch.randn(2, 1024, device=dev)
+        o1, _ = enc(v1.clone().requires_grad_(True), dinp[2], q)
+        o2, _ = enc(v2.clone().requires_grad_(True), dinp[3], q)
+        (o1.sum() + o2.sum()).backward()
+        w = enc.explicit_relation.neighbor_net[1].linear_out_2.weight
+        both = w.grad.clone()
+        opt.zero_grad()
+        o1, _ = enc(v1.clone().requires_grad_(True), dinp[2], q)
+        o1.sum().backward()
+        first = w.grad.clone()
+        opt.zero_grad()
+        o2, _ = enc(v2.clone().requires_grad_(True), dinp[3], q)
+        o2.sum().backward()
+        second = w.grad.clone()
+        err = float((both - (first + second)).abs().max() / (both.abs().max() + 1e-30))
+        assert err < 1e-5, err
+        opt.close()
+        assert not functions.GRAD_SLOTS
+    finally:
+        functions.GRAD_SLOTS.clear()
+        functions.slots_reset()
