@@ -46,7 +46,7 @@ int ek_gemm_f32_launch(int M, int N, int K, const float* A, long long sam, long 
 int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B,
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, int fmt, cudaStream_t stream);
 void ek_gemm_debug(int flags, unsigned long long* ts);
-int ek_cast_f32_bf16_launch(const float*, long long, bf16*, long long, long long, int, cudaStream_t);
+int ek_cast_f32_bf16_launch(const float*, long long, bf16*, long long, long long, int, int, cudaStream_t);
 int ek_cast_bf16_f32_launch(const bf16*, long long, float*, long long, long long, int, cudaStream_t);
 int ek_copy_f32_launch(const float*, long long, float*, long long, long long, int, cudaStream_t);
 int ek_colsum_launch(int, const void*, long long, long long, int, const float*, float*, float*, cudaStream_t);
@@ -86,7 +86,8 @@ int ek_geom_bias_bwd_launch(const double*, const double*, int, const float*, con
 int ek_edge_softmax_fwd_launch(int, const void*, long long, int, const float*, const float*, const float*, int, int,
                                int, int, float*, void*, cudaStream_t);
 int ek_edge_aggregate_fwd_launch(int, const float*, const void*, long long, int, const float*, const float*, int, int,
-                                 int, int, float*, void*, long long, uint8_t*, EkDrop, const void*, cudaStream_t);
+                                 int, int, float*, void*, long long, uint8_t*, EkDrop, const void*, const void*, long long,
+                                 cudaStream_t);
 int ek_edge_num_slices(int D);
 int ek_edge_bwd_slices(int, int, int, int, int, int);
 int ek_edge_aggregate_bwd_launch(int, const float*, const uint8_t*, const float*, const void*, long long, int, int, int,
@@ -108,7 +109,7 @@ int ek_wn_fwd_many_launch(int, const float* const*, const float* const*, const l
 int ek_wn_bwd_many_launch(int, const float* const*, const float* const*, const float* const*, const float*,
                           const long long*, float* const*, float* const*, float*, cudaStream_t);
 int ek_gru_seq_fwd_launch(const float*, const bf16*, const float*, int, int, int, float*, bf16*, float*, unsigned int*,
-                          cudaStream_t);
+                          int, bf16*, cudaStream_t);
 int ek_gru_seq_bwd_launch(const float*, const float*, const float*, const bf16*, int, int, int, float*, float*, bf16*,
                           bf16*, unsigned int*, cudaStream_t);
 int ek_gru_cell_fwd_launch(int, const float*, float*, const float*, int, int, float*, void*, float*, const float*,
@@ -118,7 +119,7 @@ int ek_gru_cell_bwd_launch(int, const float*, const float*, const float*, int, i
 int ek_rowdot_launch(int, const void*, long long, long long, int, const float*, const float*, float*, cudaStream_t);
 int ek_qpool_fwd_launch(const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 int ek_qpool_bwd_launch(const float*, const float*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
-int ek_qatt_tanh_bwd_launch(int, const float*, const float*, const void*, long long, int, void*, cudaStream_t);
+int ek_qatt_tanh_bwd_launch(int, const float*, const float*, const void*, long long, int, void*, float*, cudaStream_t);
 int ek_add_inplace_launch(float*, const float*, long long, cudaStream_t);
 
 static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
@@ -205,7 +206,10 @@ int ekaid_gemm_debug(int flags, void* ts) {
   return EK_OK;
 }
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
-  return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, ST);
+  return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, 0, ST);
+}
+int ekaid_cast_f32_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
+  return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, 1, ST);
 }
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
   return ek_cast_bf16_f32_launch((const bf16*)src, lds, dst, ldd, rows, cols, ST);
@@ -266,9 +270,9 @@ int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, cons
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
                              uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl,
-                             void* stream) {
+                             const void* Z16, int64_t ldz16, void* stream) {
   return ek_edge_aggregate_fwd_launch(is_bf16, P, QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, XoutT, ldt, mask,
-                                      mk_drop(seed, site, p), Phl, ST);
+                                      mk_drop(seed, site, p), Phl, Z16, ldz16, ST);
 }
 int ekaid_edge_num_slices(int D) { return ek_edge_num_slices(D); }
 int ekaid_edge_bwd_slices(int is_bf16, int D, int N, int Kn, int H, int have_phl) {
@@ -383,8 +387,9 @@ int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const f
   return ek_gru_cell_bwd_launch(is_bf16, dh, gates, hprev, B, H, dgi, dgh, dgiT, dghT, dhprev, ST);
 }
 int ekaid_gru_seq_fwd(const float* gi, const void* Whh, const float* bhh, int B, int H, int L, float* Hs, void* HsT,
-                      float* gates, void* barrier_ws, void* stream) {
-  return ek_gru_seq_fwd_launch(gi, (const bf16*)Whh, bhh, B, H, L, Hs, (bf16*)HsT, gates, (unsigned int*)barrier_ws, ST);
+                      float* gates, void* barrier_ws, int fp16_ops, void* HsB, void* stream) {
+  return ek_gru_seq_fwd_launch(gi, (const bf16*)Whh, bhh, B, H, L, Hs, (bf16*)HsT, gates, (unsigned int*)barrier_ws,
+                               fp16_ops, (bf16*)HsB, ST);
 }
 int ekaid_gru_seq_bwd(const float* dHs, const float* gates, const float* Hs, const void* Whh, int B, int H, int L,
                       float* dgi, float* dgh, void* dgiT, void* dghT, void* barrier_ws, void* stream) {
@@ -403,8 +408,8 @@ int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, in
   return ek_qpool_bwd_launch(dqv, S, Hs, B, L, H, dS, da, dHs, ST);
 }
 int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
-                        void* stream) {
-  return ek_qatt_tanh_bwd_launch(is_bf16, da, w2, a1, M, H, dpre, ST);
+                        float* dpre32, void* stream) {
+  return ek_qatt_tanh_bwd_launch(is_bf16, da, w2, a1, M, H, dpre, dpre32, ST);
 }
 int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream) {
   return ek_adam_advance_launch(pow_state, b1, b2, ST);

@@ -760,7 +760,8 @@ static int edge_softmax_fwd_t(const T* QKZ, long long ld, int D, const float* co
   return EK_OK;
 }
 int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float* cond, const float* lbias,
-                              const float* gbias, int G, int N, int Kn, int H, float* P, bf16* Phl, cudaStream_t st);
+                              const float* gbias, int G, int N, int Kn, int H, float* P, bf16* Phl, int p16,
+                              cudaStream_t st);
 int ek_softmax_bwd_mma_launch(const float* P, const float* dPpart, int nslices, const bf16* QKZ, long long ld, int D,
                               const float* cond, int G, int N, int Kn, int H, bf16* dQKZ, float* dlbias_part,
                               float* dgbias, cudaStream_t st);
@@ -769,8 +770,9 @@ int ek_edge_softmax_fwd_launch(int is_bf16, const void* QKZ, long long ld, int D
                                const float* lbias, const float* gbias, int G, int N, int Kn, int H, float* P,
                                void* Phl, cudaStream_t st) {
   if (is_bf16) {
+    // is_bf16 == 3: Phl has a third plane that receives the attention weights as IEEE fp16
     const int rc = ek_softmax_fwd_mma_launch((const bf16*)QKZ, ld, D, cond, lbias, gbias, G, N, Kn, H, P, (bf16*)Phl,
-                                             st);
+                                             is_bf16 == 3 ? 1 : 0, st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
     if (Phl) { ek_set_error("edge_softmax: bf16 planes requested but the tensor-core kernel does not take this shape"); return EK_ERR_UNSUPPORTED; }
   }
@@ -797,18 +799,20 @@ static int edge_aggregate_fwd_t(const float* P, const T* QKZ, long long ld, int 
 }
 int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
                           int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
-                          EkDrop dr, const bf16* Phl, cudaStream_t st);
+                          EkDrop dr, const bf16* Phl, const bf16* Z16, long long ldz16, cudaStream_t st);
 int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* P, const bf16* QKZ, long long ld, int D,
                           int G, int N, int Kn, int H, bf16* dQKZ, float* dOut, float* dPpart, float gscale,
                           const bf16* Phl, cudaStream_t st);
 
 int ek_edge_aggregate_fwd_launch(int is_bf16, const float* P, const void* QKZ, long long ld, int D, const float* b_out,
                                  const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT,
-                                 long long ldt, uint8_t* mask, EkDrop dr, const void* Phl, cudaStream_t st) {
+                                 long long ldt, uint8_t* mask, EkDrop dr, const void* Phl, const void* Z16,
+                                 long long ldz16, cudaStream_t st) {
   if (is_bf16) {   // tensor-core kernel (edge_mma.cu); SIMT template only for shapes it does not take
     const int rc = ek_agg_fwd_mma_launch(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT, ldt,
-                                         mask, dr, (const bf16*)Phl, st);
+                                         mask, dr, (const bf16*)Phl, (const bf16*)Z16, ldz16, st);
     if (rc != EK_ERR_UNSUPPORTED) return rc;
+    if (Z16) { ek_set_error("edge_aggregate_fwd: fp16 Z requested but the tensor-core kernel does not take this shape"); return EK_ERR_UNSUPPORTED; }
   }
   return is_bf16 ? edge_aggregate_fwd_t<bf16>(P, (const bf16*)QKZ, ld, D, b_out, Xin, G, N, Kn, H, Xout, (bf16*)XoutT,
                                               ldt, mask, dr, st)

@@ -29,6 +29,11 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_u32(dst)), "l"(src) : "memory");
 }
@@ -36,7 +41,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 
 // stage rows k0..k0+kc of the (h,j)-indexed Z matrix, columns [c0, c0+NC), into Zs[kc_pad][ZS]
 __device__ __forceinline__ void load_z_chunk(bf16* Zs, const bf16* __restrict__ QKZ, long long ld, int D, int g, int N,
-                                             int Kn, int HK, int k0, int kc_pad, int c0) {
+                                             int Kn, int HK, int k0, int kc_pad, int c0, int zoff) {
   const int tid = threadIdx.x;
   for (int e = tid; e < kc_pad * (NC / 8); e += blockDim.x) {
     const int kk = e / (NC / 8), ch = e % (NC / 8);
@@ -44,7 +49,7 @@ __device__ __forceinline__ void load_z_chunk(bf16* Zs, const bf16* __restrict__ 
     bf16* dst = Zs + kk * ZS + ch * 8;
     if (k < HK && c0 + ch * 8 < D) {
       const int h = k / Kn, j = k % Kn;
-      cp_async16(dst, QKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + ch * 8);
+      cp_async16(dst, QKZ + ((size_t)g * N + j) * ld + (size_t)zoff + (size_t)h * D + c0 + ch * 8);
     } else {
       *(uint4*)dst = make_uint4(0, 0, 0, 0);
     }
@@ -54,12 +59,14 @@ __device__ __forceinline__ void load_z_chunk(bf16* Zs, const bf16* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int MR>   // padded query rows per CTA pass: 64 or 128
+// F16: Z (at Zsrc, pitch ldz, head 0 at column zoff) and the attention weights (plane 2 of Phl) hold IEEE fp16 -- one
+// MMA per product instead of the bf16 path's hi + lo pair, and 11 significant bits in Z; XoutT is then written as fp16 too.
+template <int MR, bool F16>   // padded query rows per CTA pass: 64 or 128
 __global__ void __launch_bounds__(256)
 agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, long long ld, int D,
                    const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                    float* __restrict__ Xout, bf16* __restrict__ XoutT, long long ldt, uint8_t* __restrict__ mask,
-                   int kchunk, EkDrop dr, const bf16* __restrict__ Phl, long long plane) {
+                   int kchunk, EkDrop dr, const bf16* __restrict__ Phl, long long plane, int zoff) {
   ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const unsigned long long sd = ek_seed(dr);
@@ -84,8 +91,19 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
       const int kc = min(kchunk, HK - k0);
       const int kc_pad = (kc + 15) & ~15;
       __syncthreads();
-      load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0);
-      if (Phl) {
+      load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0, zoff);
+      if (F16) {
+        // fp16 attention weights (plane 2 of the softmax kernel's 16-bit planes): one plane, pure async copies
+        const int cpr = kc_pad / 8;
+        for (int e = tid; e < MR * cpr; e += 256) {
+          const int i = e / cpr, ch = e % cpr;
+          bf16* dst = Phi + i * PS + ch * 8;
+          if (r0 + i < N && ch * 8 < kc)
+            cp_async16(dst, Phl + 2 * plane + ((size_t)g * N + r0 + i) * HK + k0 + ch * 8);
+          else
+            *(uint4*)dst = make_uint4(0, 0, 0, 0);
+        }
+      } else if (Phl) {
         // attention weights pre-split into bf16 hi/lo planes by the softmax kernel: pure async copies
         const int cpr = kc_pad / 8;                  // 16-byte chunks per row
         for (int e = tid; e < 2 * MR * cpr; e += 256) {
@@ -124,17 +142,22 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
           const int arow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           const int acol = kt * 16 + (lane >> 4) * 8;
           ldsm_x4(ah, Phi + arow * PS + acol);
-          ldsm_x4(al, Plo + arow * PS + acol);
+          if (!F16) ldsm_x4(al, Plo + arow * PS + acol);
 #pragma unroll
           for (int np = 0; np < 4; ++np) {           // pairs of 8-column tiles
             uint32_t bfr[4];
             const int brow = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
             const int bcol = nh * 64 + np * 16 + (lane >> 4) * 8;
             ldsm_x4_t(bfr, Zs + brow * ZS + bcol);
-            mma_bf16_16816(acc[it][2 * np], ah, bfr[0], bfr[1]);
-            mma_bf16_16816(acc[it][2 * np], al, bfr[0], bfr[1]);
-            mma_bf16_16816(acc[it][2 * np + 1], ah, bfr[2], bfr[3]);
-            mma_bf16_16816(acc[it][2 * np + 1], al, bfr[2], bfr[3]);
+            if (F16) {
+              mma_f16_16816(acc[it][2 * np], ah, bfr[0], bfr[1]);
+              mma_f16_16816(acc[it][2 * np + 1], ah, bfr[2], bfr[3]);
+            } else {
+              mma_bf16_16816(acc[it][2 * np], ah, bfr[0], bfr[1]);
+              mma_bf16_16816(acc[it][2 * np], al, bfr[0], bfr[1]);
+              mma_bf16_16816(acc[it][2 * np + 1], ah, bfr[2], bfr[3]);
+              mma_bf16_16816(acc[it][2 * np + 1], al, bfr[2], bfr[3]);
+            }
           }
         }
       }
@@ -189,7 +212,7 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
           if (XoutT) {
             const size_t row = idx / D;                         // only when the operand copy has its own pitch
             const size_t tix = (ldt == D) ? idx : row * ldt + (idx - row * D);
-            *(__nv_bfloat162*)(XoutT + tix) = __floats2bfloat162_rn(x0, x1);
+            *(uint32_t*)(XoutT + tix) = F16 ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
           }
           if (mask) {
             uchar2 mk;
@@ -246,7 +269,7 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
     const int kc = min(kchunk, HK - k0);
     const int kc_pad = (kc + 15) & ~15;
     __syncthreads();
-    load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0);
+    load_z_chunk(Zs, QKZ, ld, D, g, N, Kn, HK, k0, kc_pad, c0, 2 * D);
     if (Phl) {
       const int cpr = kc_pad / 8;
       for (int e = tid; e < MR * cpr; e += 256) {
@@ -379,7 +402,7 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
 
   auto issue_slice = [&](int s) {
     const int c0 = s * NC;
-    load_z_chunk(Zs0 + (size_t)(s & 1) * HKP * ZS, QKZ, ld, D, g, N, Kn, HK, 0, HKP, c0);
+    load_z_chunk(Zs0 + (size_t)(s & 1) * HKP * ZS, QKZ, ld, D, g, N, Kn, HK, 0, HKP, c0, 2 * D);
     for (int e = tid; e < MR * (NC / 4); e += 256) {           // 16-byte pieces of the fp32 rows
       const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
       float* dst = raw + i * NC + c;
@@ -523,7 +546,7 @@ template <int NT>   // 8-column key tiles held per warp: 8 (Kn <= 64) or 16 (Kn 
 __global__ void __launch_bounds__(256)
 softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond,
                        const float* __restrict__ lbias, const float* __restrict__ gbias, int N, int Kn, int H,
-                       float* __restrict__ P, int MR, bf16* __restrict__ Phl, long long plane) {
+                       float* __restrict__ P, int MR, bf16* __restrict__ Phl, long long plane, int p16) {
   ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const int g = blockIdx.x, h = blockIdx.y;
@@ -639,6 +662,7 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
               const size_t o = (((size_t)g * N + i) * H + h) * Kn + j;
               Phl[o] = hi;
               Phl[plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+              if (p16) ((f16*)Phl)[2 * plane + o] = from_f32<f16>(pv);     // fp16 plane for the fp16 forward aggregation
             }
           }
         }
@@ -794,10 +818,12 @@ int set_smem(K kern, size_t smem, size_t& configured, const char* what) {
 }  // namespace
 
 // returns EK_ERR_UNSUPPORTED when the shape does not fit (caller falls back to the SIMT template)
+// Z16 (optional): the Z blocks as IEEE fp16, [G*N, H*D] with pitch ldz16; needs the fp16 plane of Phl (3 planes)
 int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, const float* b_out, const float* Xin,
                           int G, int N, int Kn, int H, float* Xout, bf16* XoutT, long long ldt, uint8_t* mask,
-                          EkDrop dr, const bf16* Phl, cudaStream_t st) {
+                          EkDrop dr, const bf16* Phl, const bf16* Z16, long long ldz16, cudaStream_t st) {
   if ((D % 8) || (ld % 8) || (ldt % 2) || ((uintptr_t)QKZ & 15)) return EK_ERR_UNSUPPORTED;
+  if (Z16 && ((ldz16 % 8) || ((uintptr_t)Z16 & 15) || !Phl || (H * Kn) % 8 || ((uintptr_t)Phl & 15))) return EK_ERR_UNSUPPORTED;
   const int HK = H * Kn;
   const int HKp = (HK + 15) & ~15;
   const int kchunk = HKp < MAXCH ? HKp : MAXCH;
@@ -807,16 +833,27 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
   const size_t smem = ((size_t)kchunk * ZS + 2 * (size_t)MR * (kchunk + 8)) * sizeof(bf16);
   dim3 grid(G, ek_div_up(D, NC));
   static size_t c64 = 0, c128 = 0;
-  if (MR == 64) {
-    int rc = set_smem(agg_fwd_mma_kernel<64>, smem, c64, "agg_fwd_mma");
+  static size_t h64 = 0, h128 = 0;
+  if (Z16 && MR == 64) {
+    int rc = set_smem(agg_fwd_mma_kernel<64, true>, smem, h64, "agg_fwd_mma");
     if (rc) return rc;
-    ek_launch(agg_fwd_mma_kernel<64>, grid, 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
-                                                    dr, Phl, plane);
+    ek_launch(agg_fwd_mma_kernel<64, true>, grid, 256, smem, st, P, Z16, ldz16, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
+                                                          kchunk, dr, Phl, plane, 0);
+  } else if (Z16) {
+    int rc = set_smem(agg_fwd_mma_kernel<128, true>, smem, h128, "agg_fwd_mma");
+    if (rc) return rc;
+    ek_launch(agg_fwd_mma_kernel<128, true>, grid, 256, smem, st, P, Z16, ldz16, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
+                                                           kchunk, dr, Phl, plane, 0);
+  } else if (MR == 64) {
+    int rc = set_smem(agg_fwd_mma_kernel<64, false>, smem, c64, "agg_fwd_mma");
+    if (rc) return rc;
+    ek_launch(agg_fwd_mma_kernel<64, false>, grid, 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
+                                                           kchunk, dr, Phl, plane, 2 * D);
   } else {
-    int rc = set_smem(agg_fwd_mma_kernel<128>, smem, c128, "agg_fwd_mma");
+    int rc = set_smem(agg_fwd_mma_kernel<128, false>, smem, c128, "agg_fwd_mma");
     if (rc) return rc;
-    ek_launch(agg_fwd_mma_kernel<128>, grid, 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask, kchunk,
-                                                     dr, Phl, plane);
+    ek_launch(agg_fwd_mma_kernel<128, false>, grid, 256, smem, st, P, QKZ, ld, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
+                                                            kchunk, dr, Phl, plane, 2 * D);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -869,7 +906,8 @@ int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* 
 }
 
 int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float* cond, const float* lbias,
-                              const float* gbias, int G, int N, int Kn, int H, float* P, bf16* Phl, cudaStream_t st) {
+                              const float* gbias, int G, int N, int Kn, int H, float* P, bf16* Phl, int p16,
+                              cudaStream_t st) {
   const long long plane = (long long)G * N * H * Kn;
   if ((D % H) || ((D / H) % 16) || (ld % 8) || ((uintptr_t)QKZ & 15) || N > 128 || Kn > 128) return EK_ERR_UNSUPPORTED;
   const int dh = D / H;
@@ -881,11 +919,11 @@ int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float*
   if (NT == 8) {
     int rc = set_smem(softmax_fwd_mma_kernel<8>, smem, c8, "softmax_fwd_mma");
     if (rc) return rc;
-    ek_launch(softmax_fwd_mma_kernel<8>, grid, 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
+    ek_launch(softmax_fwd_mma_kernel<8>, grid, 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane, p16);
   } else {
     int rc = set_smem(softmax_fwd_mma_kernel<16>, smem, c16, "softmax_fwd_mma");
     if (rc) return rc;
-    ek_launch(softmax_fwd_mma_kernel<16>, grid, 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane);
+    ek_launch(softmax_fwd_mma_kernel<16>, grid, 256, smem, st, QKZ, ld, D, cond, lbias, gbias, N, Kn, H, P, MR, Phl, plane, p16);
   }
   EK_CHECK_LAUNCH();
   return EK_OK;

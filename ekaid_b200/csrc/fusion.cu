@@ -6,7 +6,7 @@ namespace {
 
 // ---------------------------------------------------------------- casts / copies
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst,
-                                     long long ldd, long long rows, int cols) {
+                                     long long ldd, long long rows, int cols, int fmt) {
   ek_pdl_prologue();
   const long long total = rows * (cols / 4);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -14,15 +14,15 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
     const long long r = e / (cols / 4);
     const int c = (int)(e % (cols / 4)) * 4;
     const float4 v = *(const float4*)(src + r * lds + c);
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
     uint2 pk;
-    pk.x = *(uint32_t*)&a;
-    pk.y = *(uint32_t*)&b;
+    pk.x = pack16x2(v.x, v.y, fmt);
+    pk.y = pack16x2(v.z, v.w, fmt);
     *(uint2*)(dst + r * ldd + c) = pk;
   }
 }
 // Up to CM_MAX strided 2-D blocks in one launch (blockIdx.y = block): fp32 -> bf16 casts (mode 0), fp32 -> fp32 copies
-// (mode 1) or raw 16-byte copies of `cols` BYTES per row (mode 2: the captured step's input staging).
+// (mode 1), raw 16-byte copies of `cols` BYTES per row (mode 2: the captured step's input staging), fp32 -> fp16 casts
+// (mode 3, saturating) or fp16 -> bf16 conversions (mode 4: the backward's copy of a forward activation).
 constexpr int CM_MAX = 16;
 struct CastMany {
   const void* src[CM_MAX];
@@ -48,6 +48,22 @@ __global__ void cast_many_kernel(CastMany t) {
     }
     return;
   }
+  if (mode == 4) {
+    const int c8n = cols / 8;
+    const long long total = rows * c8n;
+    const f16* src = (const f16*)t.src[i];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+      const long long r = e / c8n;
+      const int c = (int)(e % c8n) * 8;
+      const uint4 raw = *(const uint4*)(src + r * t.lds[i] + c);
+      const float2 a = __half22float2(*(const __half2*)&raw.x), b = __half22float2(*(const __half2*)&raw.y);
+      const float2 cc = __half22float2(*(const __half2*)&raw.z), d = __half22float2(*(const __half2*)&raw.w);
+      uint4 pk;
+      pk.x = pack_bf16x2(a.x, a.y); pk.y = pack_bf16x2(b.x, b.y); pk.z = pack_bf16x2(cc.x, cc.y); pk.w = pack_bf16x2(d.x, d.y);
+      *(uint4*)((bf16*)t.dst[i] + r * t.ldd[i] + c) = pk;
+    }
+    return;
+  }
   const int c4n = cols / 4;
   const long long total = rows * c4n;
   const float* src = (const float*)t.src[i];
@@ -55,11 +71,10 @@ __global__ void cast_many_kernel(CastMany t) {
     const long long r = e / c4n;
     const int c = (int)(e % c4n) * 4;
     const float4 v = *(const float4*)(src + r * t.lds[i] + c);
-    if (mode == 0) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    if (mode == 0 || mode == 3) {
       uint2 pk;
-      pk.x = *(uint32_t*)&a;
-      pk.y = *(uint32_t*)&b;
+      pk.x = pack16x2(v.x, v.y, mode == 3);
+      pk.y = pack16x2(v.z, v.w, mode == 3);
       *(uint2*)((bf16*)t.dst[i] + r * t.ldd[i] + c) = pk;
     } else {
       *(float4*)((float*)t.dst[i] + r * t.ldd[i] + c) = v;
@@ -877,11 +892,11 @@ inline int grid_for(long long total, int block = 256) {
 }  // namespace
 
 int ek_cast_f32_bf16_launch(const float* src, long long lds, bf16* dst, long long ldd, long long rows, int cols,
-                            cudaStream_t st) {
+                            int fmt, cudaStream_t st) {
   EK_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0,
              EK_ERR_ALIGN, "cast_f32_bf16: cols/pitch must be multiples of 4 and pointers aligned");
   if (rows * cols == 0) return EK_OK;
-  ek_launch(cast_f32_bf16_kernel, grid_for(rows * cols / 4), 256, 0, st, src, lds, dst, ldd, rows, cols);
+  ek_launch(cast_f32_bf16_kernel, grid_for(rows * cols / 4), 256, 0, st, src, lds, dst, ldd, rows, cols, fmt);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -893,9 +908,9 @@ int ek_cast_many_launch(int count, const void* const* src, const long long* lds,
   CastMany t = {};
   long long most = 0;
   for (int i = 0; i < count; ++i) {
-    const int unit = mode[i] == 2 ? 16 : 4;
-    EK_REQUIRE(mode[i] >= 0 && mode[i] <= 2 && cols[i] % unit == 0 && lds[i] % unit == 0 && ldd[i] % unit == 0 &&
-                   ((uintptr_t)src[i] & 15) == 0 && ((uintptr_t)dst[i] & (mode[i] == 0 ? 7 : 15)) == 0,
+    const int unit = mode[i] == 2 ? 16 : (mode[i] == 4 ? 8 : 4);
+    EK_REQUIRE(mode[i] >= 0 && mode[i] <= 4 && cols[i] % unit == 0 && lds[i] % unit == 0 && ldd[i] % unit == 0 &&
+                   ((uintptr_t)src[i] & 15) == 0 && ((uintptr_t)dst[i] & ((mode[i] == 0 || mode[i] == 3) ? 7 : 15)) == 0,
                EK_ERR_ALIGN, "cast_many: block %d: cols/pitches must be multiples of %d and pointers aligned", i, unit);
     t.src[i] = src[i]; t.dst[i] = dst[i]; t.lds[i] = lds[i]; t.ldd[i] = ldd[i]; t.rows[i] = rows[i]; t.cols[i] = cols[i];
     t.mode[i] = mode[i];
@@ -1094,7 +1109,8 @@ int ek_build_vq_launch(int is_bf16, const float* X, const float* qv, const uint8
                        int D, int Dq, void* VQ, EkDrop dr, cudaStream_t st) {
   EK_REQUIRE(D % 8 == 0 && Dq % 8 == 0, EK_ERR_SHAPE, "build_vq: D=%d Dq=%d must be multiples of 8", D, Dq);
   const int g = grid_for(M * ((D + Dq) / 8));
-  if (is_bf16) ek_launch(build_vq_kernel<bf16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
+  if (is_bf16 == 2) ek_launch(build_vq_kernel<f16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (f16*)VQ, dr);
+  else if (is_bf16) ek_launch(build_vq_kernel<bf16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
   else ek_launch(build_vq_kernel<float>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -1104,7 +1120,16 @@ static void drop_combine_dispatch(int in_bf16, int out_bf16, int nin, const void
                                   long long ldi, EkDrop d0, EkDrop d1, EkDrop d2, long long M, int C, float* outf,
                                   long long ldf, int accumulate, void* outT, long long ldo, cudaStream_t st) {
   const int g = grid_for(M * (C / V));
-  if (in_bf16 && out_bf16)
+  if (in_bf16 == 2 && out_bf16 == 2)
+    ek_launch(drop_combine_kernel<f16, f16, V>, g, 256, 0, st, nin, (const f16*)in0, (const f16*)in1, (const f16*)in2, ldi,
+                                                       d0, d1, d2, M, C, outf, ldf, accumulate, (f16*)outT, ldo);
+  else if (in_bf16 == 2 && out_bf16 == 0)
+    ek_launch(drop_combine_kernel<f16, float, V>, g, 256, 0, st, nin, (const f16*)in0, (const f16*)in1, (const f16*)in2, ldi,
+                                                         d0, d1, d2, M, C, outf, ldf, accumulate, (float*)outT, ldo);
+  else if (in_bf16 == 0 && out_bf16 == 2)
+    ek_launch(drop_combine_kernel<float, f16, V>, g, 256, 0, st, nin, (const float*)in0, (const float*)in1, (const float*)in2,
+                                                         ldi, d0, d1, d2, M, C, outf, ldf, accumulate, (f16*)outT, ldo);
+  else if (in_bf16 && out_bf16)
     ek_launch(drop_combine_kernel<bf16, bf16, V>, g, 256, 0, st, nin, (const bf16*)in0, (const bf16*)in1, (const bf16*)in2, ldi,
                                                          d0, d1, d2, M, C, outf, ldf, accumulate, (bf16*)outT, ldo);
   else if (in_bf16)
@@ -1134,7 +1159,9 @@ int ek_drop_fanout_launch(int is_bf16, const void* in, long long ldi, EkDrop d0,
   EK_REQUIRE(C % 4 == 0 && ldi % 4 == 0 && ldo % 4 == 0 && (ptrs & 15) == 0, EK_ERR_ALIGN,
              "drop_fanout: C=%d and the pitches must be multiples of 4, pointers 16-byte aligned", C);
   const int g = grid_for(M * (C / 4));
-  if (is_bf16)
+  if (is_bf16 == 2)
+    ek_launch(drop_fanout_kernel<f16>, g, 256, 0, st, (const f16*)in, ldi, d0, d1, M, C, (f16*)out0, (f16*)out1, ldo);
+  else if (is_bf16)
     ek_launch(drop_fanout_kernel<bf16>, g, 256, 0, st, (const bf16*)in, ldi, d0, d1, M, C, (bf16*)out0, (bf16*)out1, ldo);
   else
     ek_launch(drop_fanout_kernel<float>, g, 256, 0, st, (const float*)in, ldi, d0, d1, M, C, (float*)out0, (float*)out1, ldo);

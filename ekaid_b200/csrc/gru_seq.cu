@@ -39,6 +39,11 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 // 16-byte async copy through L2 only (the source was written by other CTAs earlier in this kernel); nbytes = 0 zero-fills
 __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, int nbytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s_u32(dst)), "l"(src), "r"(nbytes) : "memory");
@@ -102,7 +107,7 @@ __device__ __forceinline__ void load_chunk(bf16* buf, const bf16* Ag, int rows, 
 
 // acc[j][:] += A[rb0 + 16*mt .. +16, kbeg .. kbeg + nchunks*KC) . Ws[(nh*NTW + j)*8 .. +8, 0 .. nchunks*KC)^T
 // warp = (mt = warp & 3, nh = warp >> 2).  Ws is [2*NTW*8][wp] bf16, K-major.  All threads of the CTA must call.
-template <int NTW>
+template <int NTW, bool F16 = false>     // F16: both operands hold IEEE fp16 (forward: h in [-1, 1], weights), else bf16
 __device__ __forceinline__ void skinny_gemm(const bf16* Ag, int rows, int ld, int rb0, int kbeg, int nchunks, bf16* As,
                                             const bf16* Ws, int wp, float (&acc)[NTW][4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,7 +132,8 @@ __device__ __forceinline__ void skinny_gemm(const bf16* Ag, int rows, int ld, in
 #pragma unroll
       for (int j = 0; j < NTW; ++j) {
         const bf16* w = w_base + (size_t)j * 8 * wp + ks * 16;
-        mma_bf16_16816(acc[j], a, *(const uint32_t*)w, *(const uint32_t*)(w + 8));
+        if (F16) mma_f16_16816(acc[j], a, *(const uint32_t*)w, *(const uint32_t*)(w + 8));
+        else mma_bf16_16816(acc[j], a, *(const uint32_t*)w, *(const uint32_t*)(w + 8));
       }
     }
     __syncthreads();                       // the buffer may be refilled by the next iteration's prefetch
@@ -157,10 +163,13 @@ __device__ __forceinline__ void push_partials(float (&acc)[NTW][4], float* recv,
 // ------------------------------------------------------------------------------------------------ forward
 // gi [L*B, 3H] fp32 (= x W_ih^T + b_ih, time-major rows t*B + b), Whh [3H, H] bf16, bhh [3H].
 // Hs [L*B, H] fp32, HsT [(L+1)*B, H] bf16 with block 0 = h_{-1} = 0 (written by the caller), gates [L, B, 4H] = (r, z, n, gh_n).
-template <int GU, int CS>
+// F16: Whh and HsT hold IEEE fp16 (h is bounded by 1, so fp16 only adds mantissa bits); HsB (optional): a bf16 copy of
+// HsT for the backward pass, whose wgrad pairs it with bf16 gradients (one MMA takes one 16-bit format for both operands)
+template <int GU, int CS, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_seq_fwd_kernel(const float* __restrict__ gi, const bf16* __restrict__ Whh, const float* __restrict__ bhh, int B,
-                   int H, int L, float* __restrict__ Hs, bf16* HsT, float* __restrict__ gates, unsigned int* bar) {
+                   int H, int L, float* __restrict__ Hs, bf16* HsT, float* __restrict__ gates, unsigned int* bar,
+                   bf16* __restrict__ HsB) {
   ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   constexpr int CU = GU * CS;              // hidden units per cluster
@@ -215,7 +224,7 @@ gru_seq_fwd_kernel(const float* __restrict__ gi, const bf16* __restrict__ Whh, c
         float acc[NTW][4];
 #pragma unroll
         for (int j = 0; j < NTW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        skinny_gemm<NTW>(HsT + (size_t)t * B * H, B, H, rb0, (int)rank * KS, KS / KC, As, Ws, wp, acc);
+        skinny_gemm<NTW, F16>(HsT + (size_t)t * B * H, B, H, rb0, (int)rank * KS, KS / KC, As, Ws, wp, acc);
         push_partials<NTW, OW>(acc, recv, rank);
         cluster_sync();
       }
@@ -239,7 +248,9 @@ gru_seq_fwd_kernel(const float* __restrict__ gi, const bf16* __restrict__ Whh, c
           hprev[b * GU + u] = hv;
           const size_t row = (size_t)t * B + b;
           Hs[row * H + j] = hv;
-          HsT[(row + B) * H + j] = __float2bfloat16_rn(hv);
+          if (F16) ((f16*)HsT)[(row + B) * H + j] = from_f32<f16>(hv);
+          else HsT[(row + B) * H + j] = __float2bfloat16_rn(hv);
+          if (HsB) HsB[(row + B) * H + j] = __float2bfloat16_rn(hv);
           float* gs = gates + row * 4 * H + j;
           gs[0] = r; gs[H] = z; gs[2 * H] = n; gs[3 * H] = ghn;
         }
@@ -391,14 +402,17 @@ int launch_clustered(const char* who, Kern kern, int grid, size_t smem, cudaStre
 
 template <int GU, int CS>
 int fwd_launch(const float* gi, const bf16* Whh, const float* bhh, int B, int H, int L, float* Hs, bf16* HsT, float* gates,
-               unsigned int* bar, cudaStream_t st) {
+               unsigned int* bar, int f16_ops, bf16* HsB, cudaStream_t st) {
   const size_t nbuf = (H / CS / KC > 1) ? 2 : 1;
   const size_t smem = (size_t)CS * 3 * GU * (H / CS + 8) * 2 + nbuf * RB * AP * 2 +
                       (size_t)CS * RB * (3 * GU + 2) * 4 + (size_t)B * GU * 4;
   EK_REQUIRE(smem <= 227 * 1024, EK_ERR_UNSUPPORTED, "gru_seq_fwd: B=%d H=%d needs %zu bytes of shared memory", B, H, smem);
   cudaMemsetAsync(bar, 0, sizeof(unsigned int), st);
-  return launch_clustered<CS>("gru_seq_fwd", gru_seq_fwd_kernel<GU, CS>, H / GU, smem, st, gi, Whh, bhh, B, H, L, Hs, HsT,
-                              gates, bar);
+  if (f16_ops)
+    return launch_clustered<CS>("gru_seq_fwd", gru_seq_fwd_kernel<GU, CS, true>, H / GU, smem, st, gi, Whh, bhh, B, H, L, Hs,
+                                HsT, gates, bar, HsB);
+  return launch_clustered<CS>("gru_seq_fwd", gru_seq_fwd_kernel<GU, CS, false>, H / GU, smem, st, gi, Whh, bhh, B, H, L, Hs,
+                              HsT, gates, bar, HsB);
 }
 template <int GU, int CS>
 int bwd_launch(const float* dHs, const float* gates, const float* Hs, const bf16* Whh, int B, int H, int L, float* dgi,
@@ -424,11 +438,11 @@ static int gru_variant() {
 }
 
 int ek_gru_seq_fwd_launch(const float* gi, const bf16* Whh, const float* bhh, int B, int H, int L, float* Hs, bf16* HsT,
-                          float* gates, unsigned int* bar, cudaStream_t st) {
+                          float* gates, unsigned int* bar, int f16_ops, bf16* HsB, cudaStream_t st) {
   int rc = check_shape("gru_seq_fwd", B, H, L);
   if (rc) return rc;
-  if (gru_variant() == 2) rc = fwd_launch<16, 4>(gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar, st);
-  else rc = fwd_launch<8, 2>(gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar, st);
+  if (gru_variant() == 2) rc = fwd_launch<16, 4>(gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar, f16_ops, HsB, st);
+  else rc = fwd_launch<8, 2>(gi, Whh, bhh, B, H, L, Hs, HsT, gates, bar, f16_ops, HsB, st);
   if (rc) return rc;
   EK_CHECK_LAUNCH();
   return EK_OK;

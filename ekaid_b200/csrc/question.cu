@@ -200,17 +200,20 @@ __global__ void qpool_bwd2_kernel(const float* __restrict__ S, const float* __re
     da[(size_t)l * B + b] = S[(size_t)l * B + b] * (dS[(size_t)l * B + b] - s);
 }
 // dpre[row, c] = da[row] * w2[c] * (1 - a1[row,c]^2)     (tanh + W2 backward, output in GEMM operand type)
-template <typename T>
+template <typename TA, typename T>     // TA: storage of the saved tanh output (fp32 keeps 1 - t^2 exact near saturation)
 __global__ void qatt_tanh_bwd_kernel(const float* __restrict__ da, const float* __restrict__ w2,
-                                     const T* __restrict__ a1, long long M, int H, T* __restrict__ dpre) {
+                                     const TA* __restrict__ a1, long long M, int H, T* __restrict__ dpre,
+                                     float* __restrict__ dpre32) {
   ek_pdl_prologue();
   const long long total = M * H;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / H;
     const int c = (int)(e % H);
-    const float t = to_f32<T>(a1[e]);
-    dpre[e] = from_f32<T>(da[r] * w2[c] * (1.f - t * t));
+    const float t = to_f32<TA>(a1[e]);
+    const float v = da[r] * w2[c] * (1.f - t * t);
+    dpre[e] = from_f32<T>(v);
+    if (dpre32) dpre32[e] = v;       // unrounded copy: the bias gradient is a cancelling column sum of these
   }
 }
 // y += x  (fp32), used to accumulate gradient streams
@@ -230,7 +233,8 @@ inline int grid_for(long long total, int block = 256) {
 
 int ek_embed_gather_launch(int is_bf16, const long long* q, const float* emb, const float* emb2, int B, int L, int ed,
                            void* E, cudaStream_t st) {
-  if (is_bf16) ek_launch(embed_gather_kernel<bf16>, B * L, 128, 0, st, q, emb, emb2, B, L, ed, (bf16*)E);
+  if (is_bf16 == 2) ek_launch(embed_gather_kernel<f16>, B * L, 128, 0, st, q, emb, emb2, B, L, ed, (f16*)E);
+  else if (is_bf16) ek_launch(embed_gather_kernel<bf16>, B * L, 128, 0, st, q, emb, emb2, B, L, ed, (bf16*)E);
   else ek_launch(embed_gather_kernel<float>, B * L, 128, 0, st, q, emb, emb2, B, L, ed, (float*)E);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -244,7 +248,10 @@ int ek_embed_gather_bwd_launch(const long long* q, const float* dE, long long ld
 }
 int ek_gru_cell_fwd_launch(int is_bf16, const float* gi, float* gh, const float* hprev, int B, int H, float* h,
                            void* hT, float* gates, const float* gh_reset, cudaStream_t st) {
-  if (is_bf16)
+  if (is_bf16 == 2)
+    ek_launch(gru_cell_fwd_kernel<f16>, grid_for((long long)B * H), 256, 0, st, gi, gh, hprev, B, H, h, (f16*)hT, gates,
+                                                                          gh_reset);
+  else if (is_bf16)
     ek_launch(gru_cell_fwd_kernel<bf16>, grid_for((long long)B * H), 256, 0, st, gi, gh, hprev, B, H, h, (bf16*)hT, gates,
                                                                            gh_reset);
   else
@@ -266,7 +273,8 @@ int ek_gru_cell_bwd_launch(int is_bf16, const float* dh, const float* gates, con
 }
 int ek_rowdot_launch(int is_bf16, const void* A, long long lda, long long M, int K, const float* w, const float* b,
                      float* out, cudaStream_t st) {
-  if (is_bf16) ek_launch(rowdot_kernel<bf16>, ek_div_up(M, 8), 256, 0, st, (const bf16*)A, lda, M, K, w, b, out);
+  if (is_bf16 == 2) ek_launch(rowdot_kernel<f16>, ek_div_up(M, 8), 256, 0, st, (const f16*)A, lda, M, K, w, b, out);
+  else if (is_bf16) ek_launch(rowdot_kernel<bf16>, ek_div_up(M, 8), 256, 0, st, (const bf16*)A, lda, M, K, w, b, out);
   else ek_launch(rowdot_kernel<float>, ek_div_up(M, 8), 256, 0, st, (const float*)A, lda, M, K, w, b, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
@@ -287,9 +295,11 @@ int ek_qpool_bwd_launch(const float* dqv, const float* S, const float* Hs, int B
   return EK_OK;
 }
 int ek_qatt_tanh_bwd_launch(int is_bf16, const float* da, const float* w2, const void* a1, long long M, int H,
-                            void* dpre, cudaStream_t st) {
-  if (is_bf16) ek_launch(qatt_tanh_bwd_kernel<bf16>, grid_for(M * H), 256, 0, st, da, w2, (const bf16*)a1, M, H, (bf16*)dpre);
-  else ek_launch(qatt_tanh_bwd_kernel<float>, grid_for(M * H), 256, 0, st, da, w2, (const float*)a1, M, H, (float*)dpre);
+                            void* dpre, float* dpre32, cudaStream_t st) {
+  // is_bf16: 0 = fp32 a1 and dpre, 1 = bf16 both, 3 = fp32 a1 with a bf16 dpre (the 16-bit path keeps tanh outputs in fp32)
+  if (is_bf16 == 3) ek_launch(qatt_tanh_bwd_kernel<float, bf16>, grid_for(M * H), 256, 0, st, da, w2, (const float*)a1, M, H, (bf16*)dpre, dpre32);
+  else if (is_bf16) ek_launch(qatt_tanh_bwd_kernel<bf16, bf16>, grid_for(M * H), 256, 0, st, da, w2, (const bf16*)a1, M, H, (bf16*)dpre, dpre32);
+  else ek_launch(qatt_tanh_bwd_kernel<float, float>, grid_for(M * H), 256, 0, st, da, w2, (const float*)a1, M, H, (float*)dpre, dpre32);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -120,14 +120,31 @@ def drop_combine(ins, sites, M, C, outf=None, accumulate=0, outT=None):
     ptrs = [t.data_ptr() for t in ins] + pad
     sp = list(sites) + [(None, 0, 0.0)] * (3 - nin)
     seed = next((x[0] for x in sp if x[0] is not None and x[2] > 0), None)
-    call("drop_combine", 1 if i0.dtype == torch.bfloat16 else 0, 1 if (outT is not None and outT.dtype == torch.bfloat16) else 0,
+    call("drop_combine", _fmt(i0), _fmt(outT) if outT is not None else 0,
          nin, ptrs[0], ptrs[1], ptrs[2], i0.stride(0), seed, sp[0][1], sp[0][2], sp[1][1], sp[1][2], sp[2][1], sp[2][2],
          M, C, ptr(outf), outf.stride(0) if outf is not None else 0, accumulate, ptr(outT),
          outT.stride(0) if outT is not None else 0)
 
 
+FWD16 = os.environ.get("EKAID_B200_FWD16", "fp16")     # "bf16": pure-bf16 forward (the round-1 numerics)
+
+
+def _fmt(t) -> int:
+    """format code of a tensor for the C ABI: 0 = fp32, 1 = bf16, 2 = fp16"""
+    return {torch.bfloat16: 1, torch.float16: 2}.get(t.dtype, 0)
+
+
 class PC:
-    """precision config: 'bf16' (tensor cores) or 'fp32' (SIMT, 1e-4 parity mode)."""
+    """precision config: 'bf16' (16-bit tensor-core path) or 'fp32' (SIMT, 1e-4 parity mode).
+
+    On the tensor-core path two 16-bit formats are in use, both with fp32 accumulation in TMEM:
+      T  = bf16: gradients (range matters) and the fusion stage;
+      TF = fp16: weights and activations of the question path and the relation encoders in the FORWARD pass.  They are
+           range-bounded here (GRU state and attention weights in [0, 1], weights O(0.1), node features O(10)) and the
+           conversion saturates; the three extra mantissa bits are what brings `input_attended` -- a 40x cancelling
+           difference -- inside the 2e-2 bar (scripts/bf16_error_budget.py).  One MMA takes ONE format for both
+           operands (a mixed pair raises an illegal-instruction error on the B200), so the backward pass, whose other
+           operand is always a bf16 gradient, reads bf16 copies of the tensors it needs (`dual`)."""
 
     def __init__(self, precision: str):
         if precision not in ("bf16", "fp32"):
@@ -135,6 +152,9 @@ class PC:
         self.bf16 = precision == "bf16"
         self.T = torch.bfloat16 if self.bf16 else torch.float32
         self.f = 1 if self.bf16 else 0
+        self.TF = torch.float16 if (self.bf16 and FWD16 == "fp16") else self.T
+        self.ff = 2 if self.TF == torch.float16 else self.f      # format code of forward tensors for the C ABI
+        self.dual = self.TF != self.T
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,23 +228,53 @@ def gemm_f32out(A, B, M, N, K, transA=0, transB=0, out=None, **kw):
     return C
 
 
-def to_T(pc: PC, w: torch.Tensor) -> torch.Tensor:
-    """fp32 2-D tensor -> operand type (own cast kernel for bf16; identity for fp32)."""
+def _to16(w: torch.Tensor, dtype) -> torch.Tensor:
     w = w.detach()
     if w.dim() == 1:
         w = w.view(1, -1)
     if not w.is_contiguous():
         w = w.contiguous()
-    if not pc.bf16:
+    if dtype == torch.float32:
         return w
-    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-    call("cast_f32_bf16", w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0), w.shape[0], w.shape[1])
+    out = torch.empty(w.shape, dtype=dtype, device=w.device)
+    call("cast_f32_f16" if dtype == torch.float16 else "cast_f32_bf16", w.data_ptr(), w.stride(0), out.data_ptr(),
+         out.stride(0), w.shape[0], w.shape[1])
     return out
 
 
+def to_T(pc: PC, w: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor -> gradient-side operand type (own cast kernel for bf16; identity for fp32)."""
+    return _to16(w, pc.T)
+
+
+def to_TF(pc: PC, w: torch.Tensor) -> torch.Tensor:
+    """fp32 2-D tensor -> forward operand type (fp16 on the tensor-core path unless EKAID_B200_FWD16=bf16)."""
+    return _to16(w, pc.TF)
+
+
+def bcopy(pairs) -> None:
+    """[(src fp16 2-D view, dst bf16 view)]: the backward pass's bf16 copies of forward tensors, ONE launch."""
+    for lo in range(0, len(pairs), 16):
+        chunk = pairs[lo:lo + 16]
+        n = len(chunk)
+        srcs = [(a if a.dim() == 2 else a.view(1, -1)) for a, _ in chunk]
+        dsts = [(b if b.dim() == 2 else b.view(1, -1)) for _, b in chunk]
+        for a, b in zip(srcs, dsts):
+            assert a.dtype == torch.float16 and b.dtype == torch.bfloat16 and a.shape == b.shape
+        ps = (ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs])
+        pd = (ctypes.c_void_p * n)(*[t.data_ptr() for t in dsts])
+        ls = (ctypes.c_int64 * n)(*[t.stride(0) for t in srcs])
+        ld = (ctypes.c_int64 * n)(*[t.stride(0) for t in dsts])
+        rows = (ctypes.c_int64 * n)(*[t.shape[0] for t in srcs])
+        cols = (ctypes.c_int32 * n)(*[t.shape[1] for t in srcs])
+        mode = (ctypes.c_int32 * n)(*([4] * n))
+        call("cast_many", n, ctypes.addressof(ps), ctypes.addressof(ls), ctypes.addressof(pd), ctypes.addressof(ld),
+             ctypes.addressof(rows), ctypes.addressof(cols), ctypes.addressof(mode))
+
+
 def cast_many(pc: PC, pairs) -> None:
-    """[(src fp32 2-D view, dst view)] -> ONE launch: dst in the operand type (bf16: cast, fp32: copy) or, for an fp32
-    dst on the bf16 path, a copy.  Views may have any row pitch."""
+    """[(src fp32 2-D view, dst view)] -> ONE launch: each dst receives a cast to ITS dtype (bf16 / fp16) or, for an fp32
+    dst, a copy.  Views may have any row pitch."""
     pairs = [(s_.detach(), d) for s_, d in pairs]
     for lo in range(0, len(pairs), 16):
         chunk = pairs[lo:lo + 16]
@@ -239,7 +289,7 @@ def cast_many(pc: PC, pairs) -> None:
         ld = (ctypes.c_int64 * n)(*[t.stride(0) for t in dsts])
         rows = (ctypes.c_int64 * n)(*[t.shape[0] for t in srcs])
         cols = (ctypes.c_int32 * n)(*[t.shape[1] for t in srcs])
-        mode = (ctypes.c_int32 * n)(*[0 if t.dtype == torch.bfloat16 else 1 for t in dsts])
+        mode = (ctypes.c_int32 * n)(*[{torch.bfloat16: 0, torch.float16: 3}.get(t.dtype, 1) for t in dsts])
         call("cast_many", n, ctypes.addressof(ps), ctypes.addressof(ls), ctypes.addressof(pd), ctypes.addressof(ld),
              ctypes.addressof(rows), ctypes.addressof(cols), ctypes.addressof(mode))
 
@@ -497,7 +547,7 @@ class LinearFn(torch.autograd.Function):
         WT = to_T(pc, W)
         bb = _f32c(b) if b is not None else None
         y = torch.empty(M, N, dtype=torch.float32, device=dev)
-        yT = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if pc.bf16 else None
+        yT = torch.empty(M, N, dtype=pc.TF, device=dev) if pc.bf16 else None      # operand copy for the next stage's GEMM
         gemm(xT, WT, M, N, K, bias=bb, C=y, Cb=yT)
         ctx.pc, ctx.xT, ctx.WT, ctx.has_b = pc, xT, WT, b is not None
         ctx.keys = (W.data_ptr(), b.data_ptr() if b is not None else 0)
@@ -638,7 +688,7 @@ class GRUFn(torch.autograd.Function):
         gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
         if _gru_seq_ok(pc, dev, B, H):
             call("gru_seq_fwd", gi.data_ptr(), WhhT.data_ptr(), bhhc.data_ptr(), B, H, L, Hs.data_ptr(), HsT.data_ptr(),
-                 gates.data_ptr(), _barrier_ws(dev).data_ptr())
+                 gates.data_ptr(), _barrier_ws(dev).data_ptr(), 0, None)
         else:
             gh = torch.empty(B, 3 * H, dtype=torch.float32, device=dev)
             call("copy_f32", bhhc.data_ptr(), 0, gh.data_ptr(), 3 * H, B, 3 * H)
@@ -687,7 +737,10 @@ class GRUFn(torch.autograd.Function):
 
 
 class QuestionFn(torch.autograd.Function):
-    """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156)."""
+    """w_emb -> q_emb.forward_all -> q_att   (modules.py:200-206; language_model.py:48-53,106-115,127-156).
+
+    Forward operands are in pc.TF (fp16 on the tensor-core path: embeddings, GRU state and tanh outputs are bounded);
+    the backward pairs bf16 gradients with bf16 copies of the weights / saved activations (suffix B below)."""
 
     @staticmethod
     def forward(ctx, pc: PC, drop, question, emb, emb2, Wih, Whh, bih, bhh, W1, b1, w2, b2, padding_idx=-1):
@@ -702,25 +755,35 @@ class QuestionFn(torch.autograd.Function):
             # skipped inside a CUDA-graph capture; EKAID_B200_CHECK_TOKENS=0 turns it off)
             if bool(((q < 0) | (q >= emb.shape[0])).any()):
                 raise IndexError("question holds token ids outside [0, %d)" % emb.shape[0])
+        need_bwd = any(ctx.needs_input_grad)
+        dual = pc.dual and need_bwd
         embc, emb2c = _f32c(emb), _f32c(emb2)
-        E = torch.empty(L * B, 2 * ed, dtype=pc.T, device=dev)
-        call("embed_gather", pc.f, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
+        E = torch.empty(L * B, 2 * ed, dtype=pc.TF, device=dev)
+        call("embed_gather", pc.ff, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
+        srcs = [_f32c(Wih), _f32c(Whh), _f32c(W1)]
         if pc.bf16:
-            srcs = [_f32c(Wih), _f32c(Whh), _f32c(W1)]
-            WihT, WhhT, W1T = (torch.empty(t.shape, dtype=pc.T, device=dev) for t in srcs)
-            cast_many(pc, list(zip(srcs, (WihT, WhhT, W1T))))
+            WihT, WhhT, W1T = (torch.empty(t.shape, dtype=pc.TF, device=dev) for t in srcs)
+            jobs = list(zip(srcs, (WihT, WhhT, W1T)))
+            if dual:
+                WihB, WhhB, W1B = (torch.empty(t.shape, dtype=pc.T, device=dev) for t in srcs)
+                jobs += list(zip(srcs, (WihB, WhhB, W1B)))
+            else:
+                WihB, WhhB, W1B = WihT, WhhT, W1T
+            cast_many(pc, jobs)
         else:
-            WihT, WhhT, W1T = to_T(pc, Wih), to_T(pc, Whh), to_T(pc, W1)
+            WihT, WhhT, W1T = srcs
+            WihB, WhhB, W1B = srcs
         bihc, bhhc, b1c, w2c, b2c = _f32c(bih), _f32c(bhh), _f32c(b1), _f32c(w2).view(-1), _f32c(b2).view(-1)
         gi = gemm_f32out(E, WihT, L * B, 3 * H, 2 * ed, bias=bihc)
         Hs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
         # operand-type copy with one leading zero block: HsT[t] = h_{t-1}, so "previous h of every step" is a view
-        HsT = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev)
+        HsT = torch.zeros((L + 1) * B, H, dtype=pc.TF, device=dev)
+        HsB = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev) if dual else HsT
         gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
         if _gru_seq_ok(pc, dev, B, H):
             # the whole recurrence in one persistent launch (gru_seq.cu)
             call("gru_seq_fwd", gi.data_ptr(), WhhT.data_ptr(), bhhc.data_ptr(), B, H, L, Hs.data_ptr(), HsT.data_ptr(),
-                 gates.data_ptr(), _barrier_ws(dev).data_ptr())
+                 gates.data_ptr(), _barrier_ws(dev).data_ptr(), 1 if pc.ff == 2 else 0, HsB.data_ptr() if dual else None)
         else:
             # gh accumulator: armed with b_hh (broadcast copy), "gh += h W_hh^T" as a split-K GEMM (M = B is tiny, so
             # the K loop is what can be spread over the SMs), re-armed by the cell kernel
@@ -729,18 +792,29 @@ class QuestionFn(torch.autograd.Function):
             for t in range(L):
                 gemm(HsT[t * B:(t + 1) * B], WhhT, B, 3 * H, H, addend=gh, C=gh)
                 hprev = Hs[(t - 1) * B:t * B] if t > 0 else None
-                call("gru_cell_fwd", pc.f, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
+                call("gru_cell_fwd", pc.ff, gi[t * B:(t + 1) * B].data_ptr(), gh.data_ptr(), ptr(hprev), B, H,
                      Hs[t * B:(t + 1) * B].data_ptr(), HsT[(t + 1) * B:(t + 2) * B].data_ptr(), gates[t].data_ptr(),
                      bhhc.data_ptr())
+            if dual:
+                bcopy([(HsT[B:], HsB[B:])])
         HsT_cur = HsT[B:]
         if drop is not None and drop.on:          # Dropout(0.2) on the input of W1 (language_model.py:123-124)
-            Hd = torch.empty(L * B, H, dtype=pc.T, device=dev)
+            Hd = torch.empty(L * B, H, dtype=pc.TF, device=dev)
             drop_combine([HsT_cur], [drop.a(10, drop.p_fc)], L * B, H, outT=Hd)
+            if dual:
+                HdB = torch.empty(L * B, H, dtype=pc.T, device=dev)
+                bcopy([(Hd, HdB)])
+            else:
+                HdB = Hd
         else:
-            Hd = HsT_cur
-        a1, _ = gemm_T(pc, Hd, W1T, L * B, H, H, bias=b1c, act=ACT_TANH)
+            Hd, HdB = HsT_cur, HsB[B:]
+        # a1 = tanh(Hd W1^T + b1) stays in fp32 (5 MB): it is no GEMM operand, and its backward factor 1 - a1^2 is
+        # ill-conditioned under 16-bit storage wherever the tanh saturates
+        a1 = torch.empty(L * B, H, dtype=torch.float32, device=dev)
+        gemm(Hd, W1T, L * B, H, H, bias=b1c, act=ACT_TANH, C=a1)
+        a1B = a1
         a = torch.empty(L * B, dtype=torch.float32, device=dev)
-        call("rowdot", pc.f, a1.data_ptr(), a1.stride(0), L * B, H, w2c.data_ptr(), b2c.data_ptr(), a.data_ptr())
+        call("rowdot", 0, a1.data_ptr(), a1.stride(0), L * B, H, w2c.data_ptr(), b2c.data_ptr(), a.data_ptr())
         S = torch.empty(L * B, dtype=torch.float32, device=dev)
         qv = torch.empty(B, H, dtype=torch.float32, device=dev)
         call("qpool_fwd", a.data_ptr(), Hs.data_ptr(), B, L, H, S.data_ptr(), qv.data_ptr())
@@ -751,14 +825,20 @@ class QuestionFn(torch.autograd.Function):
                                                  ("b1", b1), ("b2", b2))}
         ctx.dims = (B, L, ed, H, emb.shape[0])
         ctx.padding_idx = int(padding_idx)
-        ctx.saved = (q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd)
+        if need_bwd:
+            if dual:
+                EB = torch.empty(L * B, 2 * ed, dtype=pc.T, device=dev)
+                bcopy([(E, EB)])
+            else:
+                EB = E
+            ctx.saved = (q, EB, WihB, WhhB, W1B, w2c, Hs, HsB, gates, a1B, S, HdB)
         return qv
 
     @staticmethod
     def backward(ctx, dqv):
         pc = ctx.pc
         B, L, ed, H, V = ctx.dims
-        q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd = ctx.saved
+        q, E, WihT, WhhT, W1T, w2c, Hs, HsT, gates, a1, S, Hd = ctx.saved      # all 16-bit tensors here are in pc.T
         drop = ctx.drop
         don = drop is not None and drop.on
         dev = Hs.device
@@ -773,7 +853,11 @@ class QuestionFn(torch.autograd.Function):
         call("qpool_bwd", dqv.data_ptr(), S.data_ptr(), Hs.data_ptr(), B, L, H, dS.data_ptr(), da.data_ptr(),
              dHs.data_ptr())
         dpre = torch.empty(L * B, H, dtype=pc.T, device=dev)
-        call("qatt_tanh_bwd", pc.f, da.data_ptr(), w2c.data_ptr(), a1.data_ptr(), L * B, H, dpre.data_ptr())
+        # (unrounded fp32 copy of dpre for the bias gradient: a column sum that cancels -- sum_b da[l, b] = 0 under the
+        # batch-axis softmax -- so bf16 rounding noise of the terms would dominate it)
+        dpre32 = torch.empty(L * B, H, dtype=torch.float32, device=dev) if pc.bf16 else None
+        call("qatt_tanh_bwd", 3 if pc.bf16 else 0, da.data_ptr(), w2c.data_ptr(), a1.data_ptr(), L * B, H, dpre.data_ptr(),
+             ptr(dpre32))
         kk = ctx.keys
         # Everything below that does not feed BPTT (weight / bias gradients of the attention MLP) goes to a branch stream
         # and runs next to the recurrence; the serial chain of this stream is only dHs -> BPTT.  Temporaries are
@@ -789,7 +873,7 @@ class QuestionFn(torch.autograd.Function):
             colsum(a1, L * B, H, rowscale=da, out=dw2)
             colsum(da.view(-1, 1), L * B, 1, out=db2)
             gemm_f32out(dpre, Hd, H, H, L * B, transA=1, transB=1, out=dW1)
-            colsum(dpre, L * B, H, out=db1)
+            colsum(dpre32 if dpre32 is not None else dpre, L * B, H, out=db1)
         dw2 = dw2.view(1, H)
         if don:
             # dHs += mask * (dpre W1): dropout mask of W1's input and the accumulation, both in the GEMM epilogue
@@ -869,7 +953,7 @@ class EdgeAttentionFn(torch.autograd.Function):
              P.data_ptr(), ptr(Phl))
         out = torch.empty(M, D, dtype=torch.float32, device=dev)
         call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, _f32c(bout).data_ptr(), None,
-             G, N, Kn, H, out.data_ptr(), None, D, None, None, 0, 0.0, ptr(Phl))
+             G, N, Kn, H, out.data_ptr(), None, D, None, None, 0, 0.0, ptr(Phl), None, 0)
         ctx.pc, ctx.dims = pc, dims
         ctx.flags = (lbias is not None, gbias is not None)
         ctx.saved = (QKZ, condc, P, Phl)
@@ -916,7 +1000,8 @@ def _dim_t(dev, feat_dim=64, wave_length=1000.0):
     return _dim_t_cache[key]
 
 
-def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split):
+def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split,
+                     need_bwd: bool = True):
     """Everything of a relation step that does not depend on the activations or the question vector: operand-type
     copies of the weights ([Wq; Wk; Z-blocks] stacked for the single QKZ GEMM), the adjacency condition / label bias
     (explicit) or the geometry bias (implicit).  ChangeDetector runs this for all encoders while the question path is
@@ -925,17 +1010,30 @@ def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, 
     dev = Wsw.device
     don = drop is not None and drop.on
     Wsw32 = _f32c(Wsw)
-    WswT = torch.empty(Wsw32.shape, dtype=pc.T, device=dev) if pc.bf16 else Wsw32
+    dual = pc.dual and need_bwd
+    WswT = torch.empty(Wsw32.shape, dtype=pc.TF, device=dev) if pc.bf16 else Wsw32
     # [Wq ; Wk ; Z-blocks] operand: ONE GEMM yields query, key and Z_h = self_feat W_out2[:, hD:(h+1)D]^T (Q3)
-    WqkzT = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
+    WqkzT = torch.empty((2 + H) * D, D, dtype=pc.TF, device=dev)
     Wo2c = _f32c(Wo2)
     bqkzc = torch.zeros((2 + H) * D, dtype=torch.float32, device=dev)
-    jobs = [(_f32c(Wq), WqkzT[0:D]), (_f32c(Wk), WqkzT[D:2 * D])]
-    jobs += [(Wo2c[:, h * D:(h + 1) * D], WqkzT[(2 + h) * D:(3 + h) * D]) for h in range(H)]
+
+    def wjobs(Wq_dst, Wsw_dst):
+        j = [(_f32c(Wq), Wq_dst[0:D]), (_f32c(Wk), Wq_dst[D:2 * D])]
+        j += [(Wo2c[:, h * D:(h + 1) * D], Wq_dst[(2 + h) * D:(3 + h) * D]) for h in range(H)]
+        if pc.bf16:
+            j.append((Wsw32, Wsw_dst))
+        return j
+
+    jobs = wjobs(WqkzT, WswT)
     jobs += [(_f32c(bq).view(1, D), bqkzc[0:D].view(1, D)), (_f32c(bk).view(1, D), bqkzc[D:2 * D].view(1, D))]
-    if pc.bf16:
-        jobs.append((Wsw32, WswT))
     cast_many(pc, jobs)          # one launch instead of nine
+    if dual:
+        # bf16 copies for the backward's dgrad GEMMs (their other operand is a bf16 gradient)
+        WswB = torch.empty(Wsw32.shape, dtype=pc.T, device=dev)
+        WqkzB = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
+        cast_many(pc, wjobs(WqkzB, WswB))
+    else:
+        WswB, WqkzB = WswT, WqkzT
     cond = lbias = gbias = None
     if kind == "explicit":
         a0 = _f32c(adj0)
@@ -960,8 +1058,8 @@ def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, 
         call("geom_bias_fwd", a0.data_ptr(), ptr(a1), g_split, Wp.data_ptr(), bp.data_ptr(),
              _dim_t(dev).data_ptr(), G, N, Kn, H, gbias.data_ptr(), *dgeo, ptr(emb_cache), pc.f)
         geo = (a0, a1, Wp, bp, emb_cache)
-    return {"WswT": WswT, "Wsw32": Wsw32, "WqkzT": WqkzT, "bqkzc": bqkzc, "cond": cond, "lbias": lbias,
-            "gbias": gbias, "geo": geo}
+    return {"WswT": WswT, "Wsw32": Wsw32, "WqkzT": WqkzT, "WswB": WswB, "WqkzB": WqkzB, "bqkzc": bqkzc, "cond": cond,
+            "lbias": lbias, "gbias": gbias, "geo": geo, "dual": dual}
 
 
 class RelationFn(torch.autograd.Function):
@@ -981,66 +1079,119 @@ class RelationFn(torch.autograd.Function):
         X = _f32c(X).view(M, D)
         qv = _f32c(qv)
         don = drop is not None and drop.on
-        if prep is None:
-            prep = relation_prepare(pc, drop, site0, kind, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split)
+        need_bwd = any(ctx.needs_input_grad)
+        if prep is None or (need_bwd and pc.dual and not prep["dual"]):
+            prep = relation_prepare(pc, drop, site0, kind, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split,
+                                    need_bwd=need_bwd)
+        dual = pc.dual and need_bwd       # bf16 copies of what the backward's GEMMs / edge kernels read (suffix B)
         WswT, Wsw32, WqkzT, bqkzc = prep["WswT"], prep["Wsw32"], prep["WqkzT"], prep["bqkzc"]
         bswc, boutc = _f32c(bsw), _f32c(bout)
         flags = torch.empty(M, dtype=torch.uint8, device=dev)
         call("row_zero_flags", X.data_ptr(), M, D, flags.data_ptr())
         W = (2 + H) * D
         Dq = qv.shape[1]
-        qvT = to_T(pc, qv)
+        qvT = to_TF(pc, qv)
+        qvB = to_T(pc, qv) if dual else qvT
+        # Z in the forward format for the aggregation (fp16: 11 significant bits, one MMA per product); Q, K -- and, when
+        # a backward follows, Z -- in bf16 for the score kernels and the backward edge kernels
+        Z16 = torch.empty(M, H * D, dtype=pc.TF, device=dev) if pc.dual else None
+        wq = W if (need_bwd or not pc.dual) else 2 * D        # inference: no bf16 Z at all
+        QKZ = torch.empty(M, wq, dtype=pc.T, device=dev)
+        SfB = SqB = SkB = XB = None
         if not don:
-            if XT is None or XT.dtype != pc.T:
-                XT = to_T(pc, X)
+            if XT is None or XT.dtype != pc.TF:
+                XT = to_TF(pc, X)
             # question half of self_weights, once per sample (M = B rows), broadcast per row in the GEMM epilogue
             qpart = gemm_f32out(qvT, WswT[:, D:], B, D, Dq, bias=bswc)
-            Sf, _ = gemm_T(pc, XT, WswT[:, :D], M, D, D, rowb=qpart, rowb_div=N, rowb_mod=B, rowflag=flags,
-                           rowb_alt=bswc)
-            QKZ, _ = gemm_T(pc, Sf, WqkzT, M, W, D, bias=bqkzc)
+            Sf = torch.empty(M, D, dtype=pc.TF, device=dev)
+            if dual:
+                SfB = torch.empty(M, D, dtype=pc.T, device=dev)
+                XB = torch.empty(M, D, dtype=pc.T, device=dev)
+            kw = dict(rowb=qpart, rowb_div=N, rowb_mod=B, rowflag=flags, rowb_alt=bswc)
+            if pc.bf16:
+                gemm(XT, WswT[:, :D], M, D, D, Cb=Sf, Cb2=SfB, **kw)
+                if pc.dual:
+                    gemm(Sf, WqkzT, M, W, D, bias=bqkzc, Cb=QKZ, cb_n1=wq if wq < W else 0, Cb2=Z16, cb2_n0=2 * D)
+                else:
+                    gemm(Sf, WqkzT, M, W, D, bias=bqkzc, Cb=QKZ)
+                if dual:
+                    bcopy([(XT, XB)])
+            else:
+                gemm(XT, WswT[:, :D], M, D, D, C=Sf, **kw)
+                gemm(Sf, WqkzT, M, W, D, bias=bqkzc, C=QKZ)
             Sq = Sk = Sf
+            if not dual:
+                SfB, XB = Sf, XT
+            SqB = SkB = SfB
         else:
             # train mode: Dropout(0.2) hits the concatenated [v | q] element-wise, so the question half is no longer
             # the same for every node -> K = D + Dq GEMM on the dropped concat; query / key see two more masks
-            XT = torch.empty(M, D + Dq, dtype=pc.T, device=dev)          # the dropped [v | q] operand
-            call("build_vq", pc.f, X.data_ptr(), qv.data_ptr(), flags.data_ptr(), M, N, B, D, Dq, XT.data_ptr(),
+            XT = torch.empty(M, D + Dq, dtype=pc.TF, device=dev)          # the dropped [v | q] operand
+            call("build_vq", pc.ff, X.data_ptr(), qv.data_ptr(), flags.data_ptr(), M, N, B, D, Dq, XT.data_ptr(),
                  *drop.a(site0 + 1, drop.p_fc))
-            Sf, _ = gemm_T(pc, XT, WswT, M, D, D + Dq, bias=bswc)
-            Sq = torch.empty(M, D, dtype=pc.T, device=dev)
-            Sk = torch.empty(M, D, dtype=pc.T, device=dev)
-            call("drop_fanout", pc.f, Sf.data_ptr(), Sf.stride(0), drop.seed, site0 + 2, float(drop.p_fc), site0 + 3,
+            Sf = torch.empty(M, D, dtype=pc.TF, device=dev)
+            Sq = torch.empty(M, D, dtype=pc.TF, device=dev)
+            Sk = torch.empty(M, D, dtype=pc.TF, device=dev)
+            if dual:
+                SfB = torch.empty(M, D, dtype=pc.T, device=dev)
+                SqB = torch.empty(M, D, dtype=pc.T, device=dev)
+                SkB = torch.empty(M, D, dtype=pc.T, device=dev)
+                XB = torch.empty(M, D + Dq, dtype=pc.T, device=dev)
+            if pc.bf16:
+                gemm(XT, WswT, M, D, D + Dq, bias=bswc, Cb=Sf, Cb2=SfB)
+            else:
+                gemm(XT, WswT, M, D, D + Dq, bias=bswc, C=Sf)
+            call("drop_fanout", pc.ff, Sf.data_ptr(), Sf.stride(0), drop.seed, site0 + 2, float(drop.p_fc), site0 + 3,
                  float(drop.p_fc), M, D, Sq.data_ptr(), Sk.data_ptr(), D)
-            QKZ = torch.empty(M, W, dtype=pc.T, device=dev)
-            # three independent projections: the big Z GEMM on this stream, query / key next to it
+            # three independent projections: the big Z GEMM on this stream, query / key next to it; the backward's bf16
+            # copies of the dropped operands ride on the side streams too
             fk = Fork(dev, 2)
             for bi, (src, lo, hi) in enumerate(((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W))):
                 out = QKZ[:, lo:hi]
                 with (fk.branch(bi) if bi < 2 else contextlib.nullcontext()):
-                    gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=None if pc.bf16 else out,
-                         Cb=out if pc.bf16 else None)
+                    if not pc.bf16:
+                        gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=out)
+                    elif bi < 2:
+                        gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], Cb=out)
+                        if dual:
+                            bcopy([(Sq, SqB), (XT, XB)] if bi == 0 else [(Sk, SkB)])
+                    elif pc.dual:
+                        gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], Cb=out if need_bwd else None, Cb2=Z16)
+                    else:
+                        gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], Cb=out)
             fk.join()
+            if not dual:
+                SfB, SqB, SkB, XB = Sf, Sq, Sk, XT
         cond, lbias, gbias = prep["cond"], prep["lbias"], prep["gbias"]
         ctx.geo = prep["geo"]
         P = torch.empty(G, N, H, Kn, dtype=torch.float32, device=dev)
         es = 2 if pc.bf16 else 4
-        # bf16 path: P also as bf16 hi/lo planes, staged by the aggregation kernels with async 16-byte copies
+        # bf16 path: P also as 16-bit planes, staged by the aggregation kernels with async 16-byte copies: bf16 hi + lo
+        # (backward) and, on the dual-format path, fp16 (forward)
         Phl = None
         if pc.bf16 and (H * Kn) % 8 == 0 and N <= 128 and (D // H) % 16 == 0:
-            Phl = torch.empty(2, G, N, H * Kn, dtype=torch.bfloat16, device=dev)
-        call("edge_softmax_fwd", pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond), ptr(lbias), ptr(gbias), G, N, Kn, H,
-             P.data_ptr(), ptr(Phl), info={"bytes": G * ((N + Kn) * D * es + N * H * Kn * 4 + N * Kn * 4 * (2 if cond is not None else H))})
+            Phl = torch.empty(3 if pc.dual else 2, G, N, H * Kn, dtype=torch.bfloat16, device=dev)
+        use16 = pc.dual and Phl is not None
+        if pc.dual and not use16:
+            raise lib.EkaidError("the fp16 forward aggregation needs H*K % 8 == 0, N <= 128, head dim % 16 == 0 "
+                                 "(set EKAID_B200_FWD16=bf16 for other shapes)")
+        call("edge_softmax_fwd", 3 if use16 else pc.f, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond), ptr(lbias), ptr(gbias),
+             G, N, Kn, H, P.data_ptr(), ptr(Phl),
+             info={"bytes": G * ((N + Kn) * D * es + N * H * Kn * 4 + N * Kn * 4 * (2 if cond is not None else H))})
         Xn = torch.empty(M, D, dtype=torch.float32, device=dev)
-        XnT = torch.empty(M, D, dtype=pc.T, device=dev) if pc.bf16 else None
+        XnT = torch.empty(M, D, dtype=pc.TF, device=dev) if pc.bf16 else None
         mask = torch.empty(M, D, dtype=torch.uint8, device=dev)
         call("edge_aggregate_fwd", pc.f, P.data_ptr(), QKZ.data_ptr(), QKZ.stride(0), D, boutc.data_ptr(), X.data_ptr(),
              G, N, Kn, H, Xn.data_ptr(), ptr(XnT), D, mask.data_ptr(),
              *(drop.a(site0 + 5, drop.p_gat) if don else (None, 0, 0.0)), ptr(Phl),
-             info={"bytes": G * (N * H * Kn * 4 + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
+             Z16.data_ptr() if use16 else None, Z16.stride(0) if use16 else 0,
+             info={"bytes": G * (N * H * Kn * (2 if use16 else 4) + Kn * H * D * es + N * D * (4 + 4 + 1 + (2 if pc.bf16 else 0)))})
         ctx.pc, ctx.kind, ctx.dims, ctx.g_split = pc, kind, dims, g_split
         ctx.drop, ctx.site0 = drop, site0
         ctx.keys = {k: (t.data_ptr() if t is not None else 0) for k, t in (("bsw", bsw), ("bq", bq), ("bk", bk),
                                                                           ("Wo2", Wo2), ("bout", bout), ("p1", p1))}
-        ctx.saved = (XT, qvT, WswT, Wsw32, WqkzT, flags, Sf, Sq, Sk, QKZ, cond, P, mask, Phl)
+        if need_bwd:
+            ctx.saved = (XB, qvB, prep["WswB"], Wsw32, prep["WqkzB"], flags, SfB, SqB, SkB, QKZ, cond, P, mask, Phl)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append(mask.bool().cpu())
         if XnT is not None:

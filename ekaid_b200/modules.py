@@ -232,7 +232,8 @@ class GAttNet(nn.Module):
             drop = self.make_drop(dev)
         dims = (G, B, N, Kn, self.out_feat_dim, H)
         return relation_prepare(pc, drop, site0, kind, dims, w["sw"], w["q"], layer.query.linear().bias, w["k"],
-                                layer.key.linear().bias, layer.linear_out_2.weight, w["p0"], p1, geo0, geo1, g_split)
+                                layer.key.linear().bias, layer.linear_out_2.weight, w["p0"], p1, geo0, geo1, g_split,
+                                need_bwd=torch.is_grad_enabled())
 
     def relation_step(self, pc, X, XT, q, geo0, geo1, g_split, G, B, N, drop=None, site0=100, weights=None, prep=None):
         """X [G*N, D] -> X + relu(2 * attention output).  geo*: adjacency (explicit) or fp64 boxes (implicit)."""

@@ -116,9 +116,12 @@ int ekaid_gemm_debug(int flags, void* ts);
 /* ---- casts / reductions / glue -------------------------------------------------------------------------- */
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+/* fp32 -> IEEE fp16, round to nearest, saturating at +-65504 (forward operands of the 16-bit path: weights, bounded
+ * activations) */
+int ekaid_cast_f32_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 /* the same for up to 16 strided 2-D blocks in ONE launch.  src, lds, dst, ldd, rows, cols, mode are HOST arrays read at
  * call time; mode[i]: 0 = fp32 -> bf16, 1 = fp32 -> fp32, 2 = raw bytes (cols = bytes per row, multiple of 16, pitches in
- * bytes).  Used for the operand-type copies of a relation encoder's weights and for staging the step's inputs. */
+ * bytes), 3 = fp32 -> fp16, 4 = fp16 -> bf16 (cols multiple of 8; the backward's bf16 copy of a forward activation).  Used for the operand-type copies of a relation encoder's weights and for staging the step's inputs. */
 int ekaid_cast_many(int count, const void* const* src, const int64_t* lds, void* const* dst, const int64_t* ldd,
                     const int64_t* rows, const int32_t* cols, const int32_t* mode, void* stream);
 int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
@@ -174,15 +177,19 @@ int ekaid_geom_bias_bwd(const double* bb0, const double* bb1, int g_split, const
 int ekaid_edge_softmax_fwd(int is_bf16, const void* QKZ, int64_t ld, int D, const float* cond, const float* lbias,
                            const float* gbias, int G, int N, int Kn, int H, float* P, void* Phl, void* stream);
 /* Phl (optional, bf16 path only, needs H*Kn % 8 == 0): [2, G, N, H*Kn] bf16 = P split into hi and lo planes, which the
- * aggregation kernels stage with 16-byte async copies (pass the same pointer to edge_aggregate_fwd/bwd, or NULL). */
+ * aggregation kernels stage with 16-byte async copies (pass the same pointer to edge_aggregate_fwd/bwd, or NULL).
+ * is_bf16 = 3: Phl is [3, G, N, H*Kn] and plane 2 additionally receives P as IEEE fp16 (for the fp16 forward aggregation). */
 /* out = sum_h P_h Z_h + b_out;  Xout = Xin + relu(2 out);  mask = (out > 0)
  * (graph_att_layer.py:164-176 re-associated per Q3, graph_att.py:95-104 (Q2), relation_encoder.py:81,129 (Q1)).
  * XoutT: optional copy of Xout in the operand type with pitch ldt (may be NULL).
  * Xin NULL: no residual.  mask NULL: plain attention output Xout = (Xin +) out, without doubling, dropout or ReLU
- * (GraphSelfAttentionLayer.forward stand-alone, graph_att_layer.py:164-178). */
+ * (GraphSelfAttentionLayer.forward stand-alone, graph_att_layer.py:164-178).
+ * Z16 (optional): the Z blocks as IEEE fp16, [G*N, H*D] with pitch ldz16 -- the forward then multiplies fp16 P (plane 2 of
+ * a 3-plane Phl) with fp16 Z (11 significant bits each, one MMA per product) and writes XoutT as fp16; QKZ is not read. */
 int ekaid_edge_aggregate_fwd(int is_bf16, const float* P, const void* QKZ, int64_t ld, int D, const float* b_out,
                              const float* Xin, int G, int N, int Kn, int H, float* Xout, void* XoutT, int64_t ldt,
-                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl, void* stream);
+                             uint8_t* mask, const uint64_t* seed, uint32_t site, float p, const void* Phl,
+                             const void* Z16, int64_t ldz16, void* stream);
 int ekaid_edge_num_slices(int D);
 /* number of dP partial slices ekaid_edge_aggregate_bwd will write for these arguments (1 when the per-image tensor-core
  * kernel applies: bf16, Phl given, N <= 64, D % 128 == 0; else ekaid_edge_num_slices(D)) */
@@ -235,9 +242,11 @@ int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const f
  * Rows are time-major (t*B + b).  gi [L*B,3H] = x W_ih^T + b_ih; Whh [3H,H] bf16; Hs [L*B,H] fp32; HsT [(L+1)*B,H] bf16
  * whose block 0 (h_{-1} = 0) the caller zeroes; gates [L,B,4H] saves (r,z,n,gh_n); dHs [L*B,H] = gradient reaching h_t from
  * outside the recurrence; dgi/dgh [L*B,3H] fp32 with bf16 copies dgiT/dghT.  barrier_ws: 4 bytes of device memory.
- * Requires H % 512 == 0 and H/8 <= number of SMs (EKAID_ERR_UNSUPPORTED otherwise: use the per-step entry points). */
+ * Requires H % 512 == 0 and H/8 <= number of SMs (EKAID_ERR_UNSUPPORTED otherwise: use the per-step entry points).
+ * fp16_ops = 1: Whh and HsT hold IEEE fp16 (the forward operand format of the 16-bit path; h is bounded by 1); HsB
+ * (optional): bf16 copy of HsT for the backward wgrad, whose other operand is a bf16 gradient. */
 int ekaid_gru_seq_fwd(const float* gi, const void* Whh, const float* bhh, int B, int H, int L, float* Hs, void* HsT,
-                      float* gates, void* barrier_ws, void* stream);
+                      float* gates, void* barrier_ws, int fp16_ops, void* HsB, void* stream);
 int ekaid_gru_seq_bwd(const float* dHs, const float* gates, const float* Hs, const void* Whh, int B, int H, int L,
                       float* dgi, float* dgh, void* dgiT, void* dghT, void* barrier_ws, void* stream);
 /* out[m] = A[m,:] . w + b[0]   (W2_self_att_q, :142) */
@@ -247,8 +256,10 @@ int ekaid_rowdot(int is_bf16, const void* A, int64_t lda, int64_t M, int K, cons
 int ekaid_qpool_fwd(const float* a, const float* Hs, int B, int L, int H, float* S, float* qv, void* stream);
 int ekaid_qpool_bwd(const float* dqv, const float* S, const float* Hs, int B, int L, int H, float* dS, float* da,
                     float* dHs, void* stream);
+/* dpre = da[r] w2[c] (1 - a1^2)  (backward of tanh(W1 h) . w2).  is_bf16: 0 = fp32 a1 and dpre, 1 = bf16 both, 3 = fp32
+ * a1 with a bf16 dpre.  dpre32 (optional): unrounded fp32 copy for the bias gradient's cancelling column sum. */
 int ekaid_qatt_tanh_bwd(int is_bf16, const float* da, const float* w2, const void* a1, int64_t M, int H, void* dpre,
-                        void* stream);
+                        float* dpre32, void* stream);
 
 /* y[m,n] = x[m,:] . W[n,:] + b[n] for a handful of outputs (fc1, the 6-way change classifier, modules.py:312) */
 int ekaid_small_linear(const float* x, int64_t ldx, int M, int K, const float* W, const float* b, int N, float* y,

@@ -43,7 +43,7 @@ def main():
 
         def fwd():
             call("gru_seq_fwd", gi.data_ptr(), Whh.data_ptr(), bhh.data_ptr(), B, H, L, Hs.data_ptr(), HsT.data_ptr(),
-                 gates.data_ptr(), bar.data_ptr())
+                 gates.data_ptr(), bar.data_ptr(), 0, None)
 
         def bwd():
             call("gru_seq_bwd", dHs.data_ptr(), gates.data_ptr(), Hs.data_ptr(), Whh.data_ptr(), B, H, L, dgi.data_ptr(),

@@ -21,22 +21,35 @@ TOL = {"fp32": 1e-4, "bf16": 2e-2}
 GTOL = {"fp32": 5e-4, "bf16": 5e-2}
 
 
-def gtol(precision, k, g_ref):
-    """bf16 path: scalar gains (weight_g) and the W1 bias are sums of ~1e6 cancelling terms that each carry bf16
-    rounding noise; they get a wider band (documented in DESIGN.md 'bf16 numerics')."""
-    if precision == "bf16" and (g_ref.numel() <= 16 or k.endswith("W1_self_att_q.main.1.bias")):
-        return 0.35
-    return GTOL[precision]
-
-
 def grad_err(g, ref, precision):
-    """fp32 path: max-abs error / max-abs.  bf16 path: relative L2 error (activation gradients are stored in bf16,
+    """fp32 path: max-abs error / max-abs.  16-bit path: relative L2 error (activation gradients are stored in bf16,
     so single entries of cancelling sums carry ~2^-9 of the TERM size; the L2 norm is the meaningful scale)."""
     g = g.detach().double().cpu()
     ref = ref.detach().double().cpu()
     if precision == "fp32":
         return float((g - ref).abs().max() / (ref.abs().max() + 1e-30))
     return float((g - ref).norm() / (ref.norm() + 1e-30))
+
+
+def gain_err(g, k, ref_grads, sd):
+    """Scalar gain of a legacy weight_norm layer (w = g v / ||v||): its gradient dg = <dW, v> / ||v|| is the projection
+    of the effective-weight gradient dW onto one direction -- a cancelling inner product of ~1e6 terms for the big
+    layers.  The 16-bit path bounds the error of dW in relative L2 (GTOL); the consistent bound for its projection is
+    the same fraction of ||dW||_F, which follows from the two reference gradients:
+    ||dW||^2 = dg^2 + (||v|| / g)^2 ||dv||^2."""
+    kv = k[:-len("weight_g")] + "weight_v"
+    dg_ref = float(ref_grads[k].double())
+    v, gval = sd[kv].double(), float(sd[k].double())
+    dv_ref = ref_grads[kv].double()
+    dW = (dg_ref ** 2 + (float(v.norm()) / gval) ** 2 * float(dv_ref.norm()) ** 2) ** 0.5
+    return abs(float(g.detach().double().cpu()) - dg_ref) / (dW + 1e-30)
+
+
+def param_err(precision, k, g, ref_grads, values):
+    """Error of one parameter gradient in the metric of its kind (k = full reference name)."""
+    if precision == "bf16" and k.endswith("weight_g") and (k[:-len("weight_g")] + "weight_v") in ref_grads:
+        return gain_err(g, k, ref_grads, values)
+    return grad_err(g, ref_grads[k], precision)
 
 
 def _dev():
@@ -78,20 +91,12 @@ def test_forward_matches_golden_and_oracle(name, precision):
         assert tuple(o.shape) == z[k].shape, k
         errs[k] = (rel_err(o, z[k]), rel_err(o, r))
     print(name, precision, {k: "%.1e/%.1e" % v for k, v in errs.items()})
-    scale = max(float(np.abs(z["attended_1"]).max()), float(np.abs(z["attended_2"]).max()))
+    # every output -- including the 40x cancelling difference `input_attended` and the fc1 head `pred` -- at the
+    # north-star tolerance relative to ITS OWN maximum, against the reference's golden vectors and against the oracle
     for k, (eg, eo) in errs.items():
-        if k == "pred":
-            continue        # fc1 head of the (cancelling) difference vector; not consumed by anything (Q11)
         tol = TOL[precision]
-        if k == "input_attended" and precision == "bf16":
-            # input_attended = attended_2 - attended_1 is an exact fp32 subtraction of two outputs that each pass;
-            # it cancels ~40x (|attended| ~ 250, |difference| ~ 6), so its error is bounded relative to its
-            # OPERANDS (2e-2 of max|attended|); relative to its own maximum the bf16 path measures 2-4e-2
-            # (DESIGN.md "bf16 numerics") and is guarded at 8e-2 here.
-            own = float(np.abs(z[k]).max())
-            assert eg * own / scale < tol, (name, k, "vs golden, operand scale", eg * own / scale)
-            assert eg < 8e-2 and eo < 8e-2, (name, k, eg, eo)
-            continue
+        if k in ("pred", "input_attended") and float(np.abs(z[k]).max()) == 0.0:
+            continue        # empty_image: both images identical, the difference is exactly zero on both sides
         assert eg < tol, (name, precision, k, "vs golden", eg)
         assert eo < tol, (name, precision, k, "vs oracle", eo)
 
@@ -134,9 +139,9 @@ def test_gradients_match_oracle(name, precision):
                 assert float(p.grad.abs().max()) < (1e-3 if precision == "fp32" else 0.5), (k, float(p.grad.abs().max()))
             continue
         assert p.grad is not None, k
-        e = grad_err(p.grad, g_ref, precision)
+        e = param_err(precision, k, p.grad, {n: t.grad for n, t in sdg.items() if t.grad is not None}, sd)
         table.append((e, k))
-        if e > gtol(precision, k, g_ref):
+        if e > GTOL[precision]:
             bad.append((k, e))
     table.sort(reverse=True)
     print(name, precision, "worst grads:", [("%.1e" % e, k) for e, k in table[:6]])
@@ -258,7 +263,8 @@ def test_relation_encoders_standalone(precision):
             gr = sdg[prefix + k].grad
             if gr is None or float(gr.abs().max()) < 1e-4:
                 continue
-            assert grad_err(p.grad, gr, precision) < gtol(precision, k, gr), (kind, k, grad_err(p.grad, gr, precision))
+            e = param_err(precision, prefix + k, p.grad, {n: t.grad for n, t in sdg.items() if t.grad is not None}, full)
+            assert e < GTOL[precision], (kind, k, e)
         # outside autograd the encoder mutates and returns its first argument (quirk Q1)
         with torch.no_grad():
             v2 = v.clone().to(dev)
@@ -284,8 +290,8 @@ def test_question_path_matches_oracle():
         assert rel_err(qv, ref) < TOL[precision], rel_err(qv, ref)
         for k, p in m.named_parameters():
             if k in sdg and sdg[k].grad is not None and float(sdg[k].grad.abs().max()) > 1e-4:
-                e = grad_err(p.grad, sdg[k].grad, precision)
-                assert e < gtol(precision, k, sdg[k].grad), (precision, k, e)
+                e = param_err(precision, k, p.grad, {n: t.grad for n, t in sdg.items() if t.grad is not None}, sd)
+                assert e < GTOL[precision], (precision, k, e)
 
 
 def test_batch_coupling_q4_and_local_batch_contract():
@@ -485,4 +491,4 @@ def test_question_modules_standalone(precision):
         g = dict(m.named_parameters())[k].grad
         assert g is not None, k
         e = grad_err(g, sdg[k].grad, precision)
-        assert e < gtol(precision, k, sdg[k].grad), (precision, k, e)
+        assert e < GTOL[precision], (precision, k, e)

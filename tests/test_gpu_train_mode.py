@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from helpers import OUT_NAMES, case_inputs, load_case, loss_weights, oracle_forward, rel_err
-from test_gpu_parity import build_model, to_dev, grad_err, gtol, TOL
+from test_gpu_parity import build_model, to_dev, grad_err, param_err, GTOL, TOL
 
 pytestmark = pytest.mark.gpu
 
@@ -86,8 +86,8 @@ def test_train_path_with_p0_matches_oracle(precision):
         g_ref = sdg[k].grad
         if g_ref is None or float(g_ref.abs().max()) < 1e-4:
             continue
-        e = grad_err(p.grad, g_ref, precision)
-        if e > gtol(precision, k, g_ref):
+        e = param_err(precision, k, p.grad, {n: t.grad for n, t in sdg.items() if t.grad is not None}, sd)
+        if e > GTOL[precision]:
             bad.append((k, e))
     assert not bad, bad
 
