@@ -58,9 +58,9 @@ int ek_combine_diff_bwd_launch(const float*, const float*, long long, int, int, 
 int ek_gate_fwd_launch(int, const float*, long long, int, void*, void*, void*, EkDrop, EkDrop, cudaStream_t);
 int ek_gate_bwd_launch(int, const float*, const void*, const void*, long long, int, void*, EkDrop, EkDrop, cudaStream_t);
 int ek_build_vq_launch(int, const float*, const float*, const uint8_t*, long long, int, int, int, int, void*, EkDrop,
-                       cudaStream_t);
+                       void*, cudaStream_t);
 int ek_drop_fanout_launch(int, const void*, long long, EkDrop, EkDrop, long long, int, void*, void*, long long,
-                          cudaStream_t);
+                          void*, void*, cudaStream_t);
 int ek_drop_combine_launch(int, int, int, const void*, const void*, const void*, long long, EkDrop, EkDrop, EkDrop,
                            long long, int, float*, long long, int, void*, long long, cudaStream_t);
 int ek_rng_advance_launch(unsigned long long*, cudaStream_t);
@@ -343,8 +343,8 @@ int ekaid_wn_bwd(const float* dw, const float* v, const float* g, const float* n
 }
 int ekaid_rng_advance(uint64_t* seed, void* stream) { return ek_rng_advance_launch((unsigned long long*)seed, ST); }
 int ekaid_build_vq(int is_bf16, const float* X, const float* qv, const uint8_t* flags, int64_t M, int N, int B, int D,
-                   int Dq, void* VQ, const uint64_t* seed, uint32_t site, float p, void* stream) {
-  return ek_build_vq_launch(is_bf16, X, qv, flags, M, N, B, D, Dq, VQ, mk_drop(seed, site, p), ST);
+                   int Dq, void* VQ, const uint64_t* seed, uint32_t site, float p, void* VQB, void* stream) {
+  return ek_build_vq_launch(is_bf16, X, qv, flags, M, N, B, D, Dq, VQ, mk_drop(seed, site, p), VQB, ST);
 }
 int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
                        int64_t ldi, const uint64_t* seed, uint32_t site0, float p0, uint32_t site1, float p1,
@@ -356,9 +356,10 @@ int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, cons
                                 ldo, ST);
 }
 int ekaid_drop_fanout(int is_bf16, const void* in, int64_t ldi, const uint64_t* seed, uint32_t site0, float p0,
-                      uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* stream) {
+                      uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* out0B,
+                      void* out1B, void* stream) {
   return ek_drop_fanout_launch(is_bf16, in, ldi, mk_drop(seed, site0, p0), mk_drop(seed, site1, p1), M, C, out0, out1, ldo,
-                               ST);
+                               out0B, out1B, ST);
 }
 int ekaid_att_pool_fwd(const float* E, int64_t M, int N, int D, int dim, const float* w, const float* b,
                        const float* Xc, float* att, float* attended, void* stream) {

@@ -603,7 +603,7 @@ __global__ void adam_advance_kernel(float* pow_state, float b1, float b2) {
 template <typename T>
 __global__ void build_vq_kernel(const float* __restrict__ X, const float* __restrict__ qv,
                                 const uint8_t* __restrict__ flags, long long M, int N, int B, int D, int Dq,
-                                T* __restrict__ VQ, EkDrop dr) {
+                                T* __restrict__ VQ, EkDrop dr, bf16* __restrict__ VQB) {
   ek_pdl_prologue();
   // 8 consecutive columns per thread (D, Dq multiples of 8): one row lookup, 2 x 16-byte loads, one 16-byte store
   const int W = D + Dq;
@@ -631,6 +631,7 @@ __global__ void build_vq_kernel(const float* __restrict__ X, const float* __rest
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] *= mk[k];
     store_vec<T, 8>(VQ + m * W + c, v);
+    if (VQB) store_vec<bf16, 8>(VQB + m * W + c, v);      // the backward's bf16 copy (wgrad operand), same values
   }
 }
 // out = sum_k mult_k(idx) * in_k   (k < nin <= 3; mult_k = 1 when site k has p = 0);  idx = m*C + c
@@ -689,7 +690,8 @@ __global__ void drop_combine_kernel(int nin, const TI* __restrict__ in0, const T
 // a relation layer, graph_att_layer.py:77,89 through fc.py:25-32); index m*C + c; 4 columns per thread.
 template <typename T>
 __global__ void drop_fanout_kernel(const T* __restrict__ in, long long ldi, EkDrop d0, EkDrop d1, long long M, int C,
-                                   T* __restrict__ out0, T* __restrict__ out1, long long ldo) {
+                                   T* __restrict__ out0, T* __restrict__ out1, long long ldo, bf16* __restrict__ out0B,
+                                   bf16* __restrict__ out1B) {
   ek_pdl_prologue();
   const int CV = C / 4;
   const long long total = M * CV;
@@ -706,6 +708,10 @@ __global__ void drop_fanout_kernel(const T* __restrict__ in, long long ldi, EkDr
     for (int k = 0; k < 4; ++k) { a[k] = x[k] * m0[k]; b[k] = x[k] * m1[k]; }
     store_vec<T, 4>(out0 + m * ldo + c, a);
     store_vec<T, 4>(out1 + m * ldo + c, b);
+    if (out0B) {                                         // the backward's bf16 copies (wgrad operands)
+      store_vec<bf16, 4>(out0B + m * ldo + c, a);
+      store_vec<bf16, 4>(out1B + m * ldo + c, b);
+    }
   }
 }
 
@@ -1106,12 +1112,12 @@ int ek_adam_advance_launch(float* pow_state, float b1, float b2, cudaStream_t st
 }
 
 int ek_build_vq_launch(int is_bf16, const float* X, const float* qv, const uint8_t* flags, long long M, int N, int B,
-                       int D, int Dq, void* VQ, EkDrop dr, cudaStream_t st) {
+                       int D, int Dq, void* VQ, EkDrop dr, void* VQB, cudaStream_t st) {
   EK_REQUIRE(D % 8 == 0 && Dq % 8 == 0, EK_ERR_SHAPE, "build_vq: D=%d Dq=%d must be multiples of 8", D, Dq);
   const int g = grid_for(M * ((D + Dq) / 8));
-  if (is_bf16 == 2) ek_launch(build_vq_kernel<f16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (f16*)VQ, dr);
-  else if (is_bf16) ek_launch(build_vq_kernel<bf16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr);
-  else ek_launch(build_vq_kernel<float>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr);
+  if (is_bf16 == 2) ek_launch(build_vq_kernel<f16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (f16*)VQ, dr, (bf16*)VQB);
+  else if (is_bf16) ek_launch(build_vq_kernel<bf16>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (bf16*)VQ, dr, (bf16*)VQB);
+  else ek_launch(build_vq_kernel<float>, g, 256, 0, st, X, qv, flags, M, N, B, D, Dq, (float*)VQ, dr, (bf16*)nullptr);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -1154,17 +1160,20 @@ int ek_drop_combine_launch(int in_bf16, int out_bf16, int nin, const void* in0, 
   return EK_OK;
 }
 int ek_drop_fanout_launch(int is_bf16, const void* in, long long ldi, EkDrop d0, EkDrop d1, long long M, int C, void* out0,
-                          void* out1, long long ldo, cudaStream_t st) {
+                          void* out1, long long ldo, void* out0B, void* out1B, cudaStream_t st) {
   const uintptr_t ptrs = (uintptr_t)in | (uintptr_t)out0 | (uintptr_t)out1;
   EK_REQUIRE(C % 4 == 0 && ldi % 4 == 0 && ldo % 4 == 0 && (ptrs & 15) == 0, EK_ERR_ALIGN,
              "drop_fanout: C=%d and the pitches must be multiples of 4, pointers 16-byte aligned", C);
   const int g = grid_for(M * (C / 4));
   if (is_bf16 == 2)
-    ek_launch(drop_fanout_kernel<f16>, g, 256, 0, st, (const f16*)in, ldi, d0, d1, M, C, (f16*)out0, (f16*)out1, ldo);
+    ek_launch(drop_fanout_kernel<f16>, g, 256, 0, st, (const f16*)in, ldi, d0, d1, M, C, (f16*)out0, (f16*)out1, ldo,
+                                                    (bf16*)out0B, (bf16*)out1B);
   else if (is_bf16)
-    ek_launch(drop_fanout_kernel<bf16>, g, 256, 0, st, (const bf16*)in, ldi, d0, d1, M, C, (bf16*)out0, (bf16*)out1, ldo);
+    ek_launch(drop_fanout_kernel<bf16>, g, 256, 0, st, (const bf16*)in, ldi, d0, d1, M, C, (bf16*)out0, (bf16*)out1, ldo,
+                                                     (bf16*)out0B, (bf16*)out1B);
   else
-    ek_launch(drop_fanout_kernel<float>, g, 256, 0, st, (const float*)in, ldi, d0, d1, M, C, (float*)out0, (float*)out1, ldo);
+    ek_launch(drop_fanout_kernel<float>, g, 256, 0, st, (const float*)in, ldi, d0, d1, M, C, (float*)out0, (float*)out1, ldo,
+                                                      (bf16*)nullptr, (bf16*)nullptr);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

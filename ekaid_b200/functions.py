@@ -1026,14 +1026,14 @@ def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, 
 
     jobs = wjobs(WqkzT, WswT)
     jobs += [(_f32c(bq).view(1, D), bqkzc[0:D].view(1, D)), (_f32c(bk).view(1, D), bqkzc[D:2 * D].view(1, D))]
-    cast_many(pc, jobs)          # one launch instead of nine
     if dual:
-        # bf16 copies for the backward's dgrad GEMMs (their other operand is a bf16 gradient)
+        # bf16 copies for the backward's dgrad GEMMs (their other operand is a bf16 gradient), same launch
         WswB = torch.empty(Wsw32.shape, dtype=pc.T, device=dev)
         WqkzB = torch.empty((2 + H) * D, D, dtype=pc.T, device=dev)
-        cast_many(pc, wjobs(WqkzB, WswB))
+        jobs += wjobs(WqkzB, WswB)
     else:
         WswB, WqkzB = WswT, WqkzT
+    cast_many(pc, jobs)          # one launch instead of up to sixteen
     cond = lbias = gbias = None
     if kind == "explicit":
         a0 = _f32c(adj0)
@@ -1127,24 +1127,24 @@ class RelationFn(torch.autograd.Function):
             # train mode: Dropout(0.2) hits the concatenated [v | q] element-wise, so the question half is no longer
             # the same for every node -> K = D + Dq GEMM on the dropped concat; query / key see two more masks
             XT = torch.empty(M, D + Dq, dtype=pc.TF, device=dev)          # the dropped [v | q] operand
-            call("build_vq", pc.ff, X.data_ptr(), qv.data_ptr(), flags.data_ptr(), M, N, B, D, Dq, XT.data_ptr(),
-                 *drop.a(site0 + 1, drop.p_fc))
             Sf = torch.empty(M, D, dtype=pc.TF, device=dev)
             Sq = torch.empty(M, D, dtype=pc.TF, device=dev)
             Sk = torch.empty(M, D, dtype=pc.TF, device=dev)
             if dual:
+                # bf16 copies for the backward's wgrad GEMMs, written by the same kernels that produce the fp16 ones
                 SfB = torch.empty(M, D, dtype=pc.T, device=dev)
                 SqB = torch.empty(M, D, dtype=pc.T, device=dev)
                 SkB = torch.empty(M, D, dtype=pc.T, device=dev)
                 XB = torch.empty(M, D + Dq, dtype=pc.T, device=dev)
+            call("build_vq", pc.ff, X.data_ptr(), qv.data_ptr(), flags.data_ptr(), M, N, B, D, Dq, XT.data_ptr(),
+                 *drop.a(site0 + 1, drop.p_fc), ptr(XB))
             if pc.bf16:
                 gemm(XT, WswT, M, D, D + Dq, bias=bswc, Cb=Sf, Cb2=SfB)
             else:
                 gemm(XT, WswT, M, D, D + Dq, bias=bswc, C=Sf)
             call("drop_fanout", pc.ff, Sf.data_ptr(), Sf.stride(0), drop.seed, site0 + 2, float(drop.p_fc), site0 + 3,
-                 float(drop.p_fc), M, D, Sq.data_ptr(), Sk.data_ptr(), D)
-            # three independent projections: the big Z GEMM on this stream, query / key next to it; the backward's bf16
-            # copies of the dropped operands ride on the side streams too
+                 float(drop.p_fc), M, D, Sq.data_ptr(), Sk.data_ptr(), D, ptr(SqB), ptr(SkB))
+            # three independent projections: the big Z GEMM on this stream, query / key next to it
             fk = Fork(dev, 2)
             for bi, (src, lo, hi) in enumerate(((Sq, 0, D), (Sk, D, 2 * D), (Sf, 2 * D, W))):
                 out = QKZ[:, lo:hi]
@@ -1153,8 +1153,6 @@ class RelationFn(torch.autograd.Function):
                         gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], C=out)
                     elif bi < 2:
                         gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], Cb=out)
-                        if dual:
-                            bcopy([(Sq, SqB), (XT, XB)] if bi == 0 else [(Sk, SkB)])
                     elif pc.dual:
                         gemm(src, WqkzT[lo:hi], M, hi - lo, D, bias=bqkzc[lo:hi], Cb=out if need_bwd else None, Cb2=Z16)
                     else:

@@ -288,9 +288,10 @@ int ekaid_wn_bwd_many(int count, const float* const* dw, const float* const* v, 
 /* ---- train-mode dropout helpers -------------------------------------------------------------------------- */
 int ekaid_rng_advance(uint64_t* seed, void* stream);
 /* VQ [M, D+Dq] = Dropout(cat(X, flag ? 0 : q))  -- the input of self_weights in train mode (relation_encoder.py:19-29,
- * fc.py:25-32; graph_att.py:80), operand type */
+ * fc.py:25-32; graph_att.py:80), operand type (is_bf16: 0 fp32, 1 bf16, 2 fp16).  VQB (optional): the same values as
+ * bf16, the backward's copy (its wgrad pairs this operand with a bf16 gradient). */
 int ekaid_build_vq(int is_bf16, const float* X, const float* qv, const uint8_t* flags, int64_t M, int N, int B, int D,
-                   int Dq, void* VQ, const uint64_t* seed, uint32_t site, float p, void* stream);
+                   int Dq, void* VQ, const uint64_t* seed, uint32_t site, float p, void* VQB, void* stream);
 /* out = sum_{k<nin} mult_k * in_k  (mult_k = dropout multiplier of site k, 1 when p_k = 0); index m*C + c.
  * outf (fp32, optional, accumulate != 0 adds to its old value) and/or outT (operand type, optional). */
 int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, const void* in1, const void* in2,
@@ -298,9 +299,11 @@ int ekaid_drop_combine(int in_bf16, int out_bf16, int nin, const void* in0, cons
                        uint32_t site2, float p2, int64_t M, int C, float* outf, int64_t ldf, int accumulate,
                        void* outT, int64_t ldo, void* stream);
 /* out0 = mult(site0) * in, out1 = mult(site1) * in: two independent dropout sites on one tensor in the operand type (the
- * query and key inputs of a relation layer in train mode); index m*C + c */
+ * query and key inputs of a relation layer in train mode); index m*C + c.  out0B / out1B (optional, both or none): bf16
+ * copies for the backward. */
 int ekaid_drop_fanout(int is_bf16, const void* in, int64_t ldi, const uint64_t* seed, uint32_t site0, float p0,
-                      uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* stream);
+                      uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* out0B,
+                      void* out1B, void* stream);
 
 /* ---- optimizer (utils/utils.py:96-99 -> torch.optim.Adam semantics) -------------------------------------- */
 /* pow_state: device float[2] = {beta1^t, beta2^t}; call ekaid_adam_advance once per step before the updates */

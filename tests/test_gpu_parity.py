@@ -159,7 +159,7 @@ def test_argmax_answer_tokens(name, precision):
     greedy decoding feeds every flip back into the recurrence.  The check is therefore made step-wise along the
     REFERENCE token path (teacher forcing on the golden tokens): at every step where the reference's top-2 logit
     margin exceeds `tau`, the arg-max computed from the CUDA path's (bef, aft, diff) must be the reference token.
-    tau: 1e-3 nat for the fp32 path, 0.03 nat for the bf16 path; the free-running greedy decode must additionally
+    tau: 1e-3 nat for the fp32 path, 0.01 nat for the 16-bit path (twice its largest log-probability deviation); the free-running greedy decode must additionally
     agree on the whole prefix before the first sub-margin step."""
     from ekaid_b200.synthetic import synthetic_state_dict
     from oracle import ekaid_oracle as O
@@ -167,7 +167,7 @@ def test_argmax_answer_tokens(name, precision):
     z, meta = load_case(name)
     sd, inp, _ = case_inputs(meta)
     m = build_model(meta, sd, precision, dev)
-    tau = 1e-3 if precision == "fp32" else 0.03
+    tau = 1e-3 if precision == "fp32" else 0.01      # 16-bit path: measured max |dlogp| 4-5e-3 nat
     with torch.no_grad():
         outs = m(*to_dev(inp, dev), setting="mode2", graph=meta["graph"])
         ssd = synthetic_state_dict(speaker_spec(), 4321)
@@ -200,7 +200,8 @@ def test_argmax_answer_tokens(name, precision):
         print("   margin quantiles (5/25/50/75%%): %s; max |dlogp| %.3g" % (
             [round(float(q), 4) for q in torch.quantile(margin.flatten(), torch.tensor([.05, .25, .5, .75]))],
             float((lm - lr)[:, 1:].abs().max())))
-        assert frac > (0.5 if precision == "fp32" else 0.1)
+        assert frac > (0.5 if precision == "fp32" else 0.3)
+        assert float((lm - lr)[:, 1:].abs().max()) < (1e-3 if precision == "fp32" else 1e-2)
         assert bool(agree[solid].all()), "arg-max token differs at a step with a solid reference margin"
         seq = O.speaker_greedy(ssd, *my_feats, 90, 512)
         for b in range(B):
