@@ -121,6 +121,11 @@ int ek_qpool_fwd_launch(const float*, const float*, int, int, int, float*, float
 int ek_qpool_bwd_launch(const float*, const float*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
 int ek_qatt_tanh_bwd_launch(int, const float*, const float*, const void*, long long, int, void*, float*, cudaStream_t);
 int ek_add_inplace_launch(float*, const float*, long long, cudaStream_t);
+int ek_weighted_sums_bwd_launch(int, float* const*, const float* const*, const long long*, const float*, const float*,
+                                cudaStream_t);
+int ek_head_fwd_launch(const float*, long long, float*, cudaStream_t);
+int ek_head_bwd_launch(const float*, const float*, const float*, const float*, const float*, long long, long long, float*,
+                       float*, cudaStream_t);
 
 static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
   EkEpilogue r;
@@ -421,3 +426,15 @@ int ekaid_adam_step(float* p, const float* g, float* m, float* v, int64_t n, flo
 }
 
 }  // extern "C"
+
+int ekaid_weighted_sums_bwd(int count, float* const* out, const float* const* w, const int64_t* n, const float* coef,
+                            const float* g, void* stream) {
+  return ek_weighted_sums_bwd_launch(count, out, w, (const long long*)n, coef, g, ST);
+}
+int ekaid_head_fwd(const float* attended, int64_t BD, float* input_attended, void* stream) {
+  return ek_head_fwd_launch(attended, BD, input_attended, ST);
+}
+int ekaid_head_bwd(const float* d_att_bef, const float* d_att_aft, const float* d_a1, const float* d_a2, const float* d_ia,
+                   int64_t BN, int64_t BD, float* d_att, float* d_attended, void* stream) {
+  return ek_head_bwd_launch(d_att_bef, d_att_aft, d_a1, d_a2, d_ia, BN, BD, d_att, d_attended, ST);
+}

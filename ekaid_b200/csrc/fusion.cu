@@ -312,19 +312,29 @@ __global__ void row_zero_flags_kernel(const float* __restrict__ X, long long M, 
 // ---------------------------------------------------------------- per-sample row sums (backward of the q broadcast)
 // out[b, c] = sum_{s < S} sum_{n < N} (flags[row] ? 0 : src[row, c]),  row = (s*B + b)*N + n
 template <typename T>
-__global__ void group_rowsum_kernel(const T* __restrict__ src, long long ld, int N, int B, int S, int D,
-                                    const uint8_t* __restrict__ flags, float* __restrict__ out) {
+__global__ void __launch_bounds__(256)
+group_rowsum_kernel(const T* __restrict__ src, long long ld, int N, int B, int S, int D,
+                    const uint8_t* __restrict__ flags, float* __restrict__ out) {
   ek_pdl_prologue();
+  // 64 columns x 4 row lanes per CTA: every lane sums every fourth row of the sample (independent loads in flight
+  // instead of one serial chain of S*N dependent ones), fixed-order combine -> deterministic
+  __shared__ float part[4][64];
   const int b = blockIdx.x;
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= D) return;
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.y * 64 + cl;
+  const int R = S * N;
   float acc = 0.f;
-  for (int s = 0; s < S; ++s)
-    for (int n = 0; n < N; ++n) {
-      const long long row = ((long long)s * B + b) * N + n;
+  if (c < D) {
+#pragma unroll 4
+    for (int i = rl; i < R; i += 4) {
+      const int s_ = i / N, n = i - s_ * N;
+      const long long row = ((long long)s_ * B + b) * N + n;
       if (!(flags && flags[row])) acc += to_f32<T>(src[row * ld + c]);
     }
-  out[(size_t)b * D + c] = acc;
+  }
+  part[rl][cl] = acc;
+  __syncthreads();
+  if (rl == 0 && c < D) out[(size_t)b * D + c] = ((part[0][cl] + part[1][cl]) + part[2][cl]) + part[3][cl];
 }
 
 // ---------------------------------------------------------------- graph combine + difference (modules.py:233-250)
@@ -886,6 +896,43 @@ weighted_sums_kernel(WsumArgs t, int count, float* part, unsigned int* ticket, f
   }
 }
 
+// backward of weighted_sums: grad_k[e] = g * coef_k * (w_k ? w_k[e] : 1), all k in one launch (blockIdx.y = k)
+__global__ void weighted_sums_bwd_kernel(WsumArgs t, const float* __restrict__ g) {
+  ek_pdl_prologue();
+  const int k = blockIdx.y;
+  const float s = g[0] * t.coef[k];
+  float* __restrict__ o = const_cast<float*>(t.a[k]);
+  const float* __restrict__ w = t.w[k];
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < t.n[k]; e += (long long)gridDim.x * blockDim.x)
+    o[e] = w ? s * w[e] : s;
+}
+// input_attended = attended_2 - attended_1 (modules.py:309): attended [2B, D] (main rows, then reference rows) -> ia [B, D]
+__global__ void head_fwd_kernel(const float* __restrict__ attended, long long BD, float* __restrict__ ia) {
+  ek_pdl_prologue();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < BD; e += (long long)gridDim.x * blockDim.x)
+    ia[e] = attended[BD + e] - attended[e];
+}
+// gradients reaching the five views the module returns -> the two tensors the fusion stage produced, in ONE launch:
+// d_att = [d_att_bef ; d_att_aft],  d_attended = [d_a1 - d_ia ; d_a2 + d_ia]   (any input may be NULL = zero)
+__global__ void head_bwd_kernel(const float* __restrict__ d_att_bef, const float* __restrict__ d_att_aft,
+                                const float* __restrict__ d_a1, const float* __restrict__ d_a2,
+                                const float* __restrict__ d_ia, long long BN, long long BD, float* __restrict__ d_att,
+                                float* __restrict__ d_attended) {
+  ek_pdl_prologue();
+  const long long total = 2 * BN + 2 * BD;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    if (e < BN) d_att[e] = d_att_bef ? d_att_bef[e] : 0.f;
+    else if (e < 2 * BN) d_att[e] = d_att_aft ? d_att_aft[e - BN] : 0.f;
+    else if (e < 2 * BN + BD) {
+      const long long i = e - 2 * BN;
+      d_attended[i] = (d_a1 ? d_a1[i] : 0.f) - (d_ia ? d_ia[i] : 0.f);
+    } else {
+      const long long i = e - 2 * BN - BD;
+      d_attended[BD + i] = (d_a2 ? d_a2[i] : 0.f) + (d_ia ? d_ia[i] : 0.f);
+    }
+  }
+}
+
 __global__ void rng_advance_kernel(unsigned long long* seed) {
   ek_pdl_prologue(); *seed = *seed * 6364136223846793005ull + 1442695040888963407ull; }
 
@@ -1003,9 +1050,9 @@ int ek_row_zero_flags_launch(const float* X, long long M, int D, uint8_t* flags,
 
 int ek_group_rowsum_launch(int is_bf16, const void* src, long long ld, int N, int B, int S, int D, const uint8_t* flags,
                            float* out, cudaStream_t st) {
-  dim3 grid(B, ek_div_up(D, 128));
-  if (is_bf16) ek_launch(group_rowsum_kernel<bf16>, grid, 128, 0, st, (const bf16*)src, ld, N, B, S, D, flags, out);
-  else ek_launch(group_rowsum_kernel<float>, grid, 128, 0, st, (const float*)src, ld, N, B, S, D, flags, out);
+  dim3 grid(B, ek_div_up(D, 64));
+  if (is_bf16) ek_launch(group_rowsum_kernel<bf16>, grid, 256, 0, st, (const bf16*)src, ld, N, B, S, D, flags, out);
+  else ek_launch(group_rowsum_kernel<float>, grid, 256, 0, st, (const float*)src, ld, N, B, S, D, flags, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
@@ -1206,6 +1253,27 @@ int ek_weighted_sums_launch(int count, const float* const* a, const float* const
   WsumArgs t = {};
   for (int k = 0; k < count; ++k) { t.a[k] = a[k]; t.w[k] = w[k]; t.n[k] = n[k]; t.coef[k] = coef[k]; }
   ek_launch(weighted_sums_kernel, 64, 256, 0, st, t, count, workspace + 1, (unsigned int*)workspace, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_weighted_sums_bwd_launch(int count, float* const* out, const float* const* w, const long long* n, const float* coef,
+                                const float* g, cudaStream_t st) {
+  EK_REQUIRE(count >= 1 && count <= 5, EK_ERR_SHAPE, "weighted_sums_bwd: count=%d not in [1,5]", count);
+  WsumArgs t = {};
+  for (int k = 0; k < count; ++k) { t.a[k] = out[k]; t.w[k] = w[k]; t.n[k] = n[k]; t.coef[k] = coef[k]; }
+  ek_launch(weighted_sums_bwd_kernel, dim3(32, count), 256, 0, st, t, g);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_head_fwd_launch(const float* attended, long long BD, float* ia, cudaStream_t st) {
+  ek_launch(head_fwd_kernel, grid_for(BD), 256, 0, st, attended, BD, ia);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_head_bwd_launch(const float* d_att_bef, const float* d_att_aft, const float* d_a1, const float* d_a2,
+                       const float* d_ia, long long BN, long long BD, float* d_att, float* d_attended, cudaStream_t st) {
+  ek_launch(head_bwd_kernel, grid_for(2 * BN + 2 * BD), 256, 0, st, d_att_bef, d_att_aft, d_a1, d_a2, d_ia, BN, BD, d_att,
+                                              d_attended);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

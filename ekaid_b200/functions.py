@@ -503,10 +503,19 @@ class WeightedSumsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        grads = []
-        for c, w, sh in zip(ctx.coefs, ctx.weights, ctx.shapes):
-            grads.append((g * c) * w.view(sh) if w is not None else (g * c).expand(sh))
-        return (None, None, *grads)
+        # the gradient of every term is a constant times g: all of them in ONE launch (the composite form is ~25 tiny
+        # ATen kernels, 50 us of launch latency in the captured step)
+        cnt = len(ctx.shapes)
+        dev = g.device
+        gc = _f32c(g).reshape(1)
+        outs = [torch.empty(sh, dtype=torch.float32, device=dev) for sh in ctx.shapes]
+        po = _ptr_array(outs)
+        pw = (ctypes.c_void_p * cnt)(*[w.data_ptr() if w is not None else None for w in ctx.weights])
+        ns = (ctypes.c_int64 * cnt)(*[o.numel() for o in outs])
+        cf = (ctypes.c_float * cnt)(*[float(c) for c in ctx.coefs])
+        call("weighted_sums_bwd", cnt, ctypes.addressof(po), ctypes.addressof(pw), ctypes.addressof(ns),
+             ctypes.addressof(cf), gc.data_ptr())
+        return (None, None, *outs)
 
 
 def cast_into(pc: PC, src: torch.Tensor, dst: torch.Tensor) -> None:
@@ -644,8 +653,8 @@ class Fork:
         f = Fork(dev, 2); with f.branch(0): ...; with f.branch(1): ...; (work on the calling stream); f.join()
     """
 
-    def __init__(self, dev, n: int):
-        key = str(dev)
+    def __init__(self, dev, n: int, pool: str = "stage"):
+        key = (str(dev), pool)          # separate pools: work queued on one pool never sits behind another pool's work
         pool = _fork_pool.setdefault(key, [])
         while len(pool) < n:
             pool.append(torch.cuda.Stream(dev))
@@ -1260,9 +1269,7 @@ class RelationFn(torch.autograd.Function):
             # [query | key | Z] projection: ONE wgrad GEMM, then the Z blocks are copied into linear_out_2's layout
             dWqkz = gemm_f32out(dQKZ, Sf, W, D, M, transA=1, transB=1)
             dWq, dWk = dWqkz[:D], dWqkz[D:2 * D]
-            for h in range(H):
-                call("copy_f32", dWqkz[(2 + h) * D:(3 + h) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(),
-                     H * D, D, D)
+            cast_many(pc, [(dWqkz[(2 + h) * D:(3 + h) * D], dWo2[:, h * D:(h + 1) * D]) for h in range(H)])
             dSf, _ = gemm_T(pc, dQKZ, WqkzT, M, D, W, transB=1)
             # self_feat = X Wv^T + (flag ? b_sw : q Wq^T + b_sw)
             gemm(dSf, XT, D, D, M, transA=1, transB=1, C=dWsw[:, :D])
@@ -1284,8 +1291,7 @@ class RelationFn(torch.autograd.Function):
             fk = Fork(dev, 2)
             with fk.branch(0):
                 gemm(dQKZ[:, 2 * D:W], Sf, W - 2 * D, D, M, transA=1, transB=1, C=dWz)
-                for h in range(H):
-                    call("copy_f32", dWz[h * D:(h + 1) * D].data_ptr(), D, dWo2[:, h * D:(h + 1) * D].data_ptr(), H * D, D, D)
+                cast_many(pc, [(dWz[h * D:(h + 1) * D], dWo2[:, h * D:(h + 1) * D]) for h in range(H)])   # one launch
             with fk.branch(1):
                 gemm(dQKZ[:, 0:D], Sq, D, D, M, transA=1, transB=1, C=dWq)
                 gemm(dQKZ[:, D:2 * D], Sk, D, D, M, transA=1, transB=1, C=dWk)
@@ -1366,10 +1372,14 @@ class FusionFn(torch.autograd.Function):
         ctx.saved = (Xc, CAT, WcgT, WeT, wac, cx, gt, E, att)
         if DEBUG_SINK is not None:
             DEBUG_SINK.append((E > 0).cpu())
-        return att, attended
+        # the module's outputs (modules.py:305-313) as views of the two buffers + the difference vector: their five
+        # gradients come back together and are folded into (d_att, d_attended) by one kernel
+        ia = torch.empty(B, D, dtype=torch.float32, device=dev)
+        call("head_fwd", attended.data_ptr(), B * D, ia.data_ptr())
+        return att[:BN].view(B, 1, N), att[BN:].view(B, 1, N), attended[:B], attended[B:], ia
 
     @staticmethod
-    def backward(ctx, datt, dattended):
+    def backward(ctx, d_att_bef, d_att_aft, d_a1, d_a2, d_ia):
         pc = ctx.pc
         B, N, D, dim = ctx.dims
         Xc, CAT, WcgT, WeT, wac, cx, gt, E, att = ctx.saved
@@ -1379,8 +1389,10 @@ class FusionFn(torch.autograd.Function):
         BN = B * N
         M = 2 * BN
         c1, c2, c3 = ctx.coefs
-        dA = _f32c(dattended) if dattended is not None else torch.zeros(2 * B, D, dtype=torch.float32, device=dev)
-        dw_ = _f32c(datt).view(-1) if datt is not None else None
+        gs = [(_f32c(t) if t is not None else None) for t in (d_att_bef, d_att_aft, d_a1, d_a2, d_ia)]
+        dA = torch.empty(2 * B, D, dtype=torch.float32, device=dev)
+        dw_ = torch.empty(M, dtype=torch.float32, device=dev)
+        call("head_bwd", ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]), ptr(gs[4]), BN, B * D, dw_.data_ptr(), dA.data_ptr())
         dXc = torch.empty(M, D, dtype=torch.float32, device=dev)
         dE = torch.empty(M, dim, dtype=pc.T, device=dev)
         dpa = torch.empty(M, dtype=torch.float32, device=dev)
@@ -1413,8 +1425,8 @@ class FusionFn(torch.autograd.Function):
         with fk.branch(1, resync=True):
             gemm_f32out(dpre, CAT[:, :2 * D], 2 * D, 2 * D, M, transA=1, transB=1, out=dWcg)
             # blocks of the fused [[context2 | context1], [gate2 | gate1]] gradient -> parameter-shaped (contiguous) tensors
-            for name, r0, c0 in (("C2", 0, 0), ("C1", 0, D), ("G2", D, 0), ("G1", D, D)):
-                call("copy_f32", dWcg[r0:r0 + D, c0:c0 + D].data_ptr(), 2 * D, blocks[name].data_ptr(), D, D, D)
+            cast_many(pc, [(dWcg[r0:r0 + D, c0:c0 + D], blocks[name])
+                           for name, r0, c0 in (("C2", 0, 0), ("C1", 0, D), ("G2", D, 0), ("G1", D, D))])     # one launch
             colsum(dpre[:, :D], M, D, out=dbC2)
             colsum(dpre[:, D:], M, D, out=dbG2)
         gemm(dpre, WcgT, M, 2 * D, 2 * D, transB=1, addend=dCAT[:, :2 * D], C=dCAT[:, :2 * D])

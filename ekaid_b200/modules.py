@@ -34,7 +34,7 @@ with warnings.catch_warnings():
     from torch.nn.utils import weight_norm as _weight_norm
 
 from . import lib as _lib
-from .functions import (PC, Drop, EdgeAttentionFn, FusionFn, GRUFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn,
+from .functions import (PC, Drop, EdgeAttentionFn, Fork, FusionFn, GRUFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn,
                         WNormManyFn, rng_advance)
 
 
@@ -603,25 +603,27 @@ class ChangeDetector(nn.Module):
         geos = {'sem': (d_sem_adj_matrix, q_sem_adj_matrix, 100), 'spa': (d_adj_matrix, q_adj_matrix, 200),
                 'imp': (d_bb, q_bb, 300)}
         drops = {k: g.make_drop(dev, ov) for k, g in gats.items()}
-        preps = {k: g.prepare_step(pc, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k], site0=geos[k][2],
-                                   weights=eff[k]) for k, g in gats.items()}
+        # one stream per encoder: the preparation of the second / third encoder (its weight casts, adjacency bias or
+        # geometry bias) must not delay the first encoder's GEMMs -- each is joined right before the step that needs it
+        fkp = Fork(dev, len(gats), pool="prep")
+        preps = {}
+        for i, (k, g) in enumerate(gats.items()):
+            with fkp.branch(i):
+                preps[k] = g.prepare_step(pc, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k], site0=geos[k][2],
+                                          weights=eff[k])
         cur.wait_stream(side)
-        for k in ('sem', 'spa', 'imp'):
-            if k in gats:
-                X, XT, _ = gats[k].relation_step(pc, X, XT, qv, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k],
-                                                 site0=geos[k][2], weights=eff[k], prep=preps[k])
+        for i, k in enumerate(gats):
+            if fkp.on:
+                cur.wait_stream(fkp.streams[i])
+            X, XT, _ = gats[k].relation_step(pc, X, XT, qv, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k],
+                                             site0=geos[k][2], weights=eff[k], prep=preps[k])
         mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
         coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
         fdrop = Drop(dev, self.training, p_fuse=self.dropout.p if ov is None else ov,
                      p_embed=self.embed[1].p if ov is None else ov)
-        att, attended = FusionFn.apply(pc, fdrop, (B, N, D, self.dim), mode, coefs, X, self.context1.weight,
-                                       self.context2.weight, self.context2.bias, self.gate1.weight, self.gate2.weight,
-                                       self.gate2.bias, self.embed[0].weight, self.embed[0].bias, self.att.weight,
-                                       self.att.bias)
-        BN = B * N
-        att_weight_before = att[:BN].view(B, 1, N)
-        att_weight_after = att[BN:].view(B, 1, N)
-        attended_1, attended_2 = attended[:B], attended[B:]
-        input_attended = attended_2 - attended_1
+        att_weight_before, att_weight_after, attended_1, attended_2, input_attended = FusionFn.apply(
+            pc, fdrop, (B, N, D, self.dim), mode, coefs, X, self.context1.weight, self.context2.weight, self.context2.bias,
+            self.gate1.weight, self.gate2.weight, self.gate2.bias, self.embed[0].weight, self.embed[0].bias,
+            self.att.weight, self.att.bias)
         pred = SmallLinearFn.apply(input_attended, self.fc1.weight, self.fc1.bias)      # [B,6], unused by the loss (Q11)
         return pred, att_weight_before, att_weight_after, attended_1, attended_2, input_attended

@@ -269,6 +269,15 @@ int ekaid_small_linear(const float* x, int64_t ldx, int M, int K, const float* W
  * floats, word 0 a ticket counter (zero it once; every call leaves it zero). */
 int ekaid_weighted_sums(int count, const float* const* a, const float* const* w, const int64_t* n, const float* coef,
                         float* out, float* workspace, void* stream);
+/* backward of ekaid_weighted_sums in one launch: out_k[e] = g[0] * coef_k * (w_k ? w_k[e] : 1); g is a device scalar */
+int ekaid_weighted_sums_bwd(int count, float* const* out, const float* const* w, const int64_t* n, const float* coef,
+                            const float* g, void* stream);
+/* input_attended = attended_2 - attended_1 (modules.py:309) from the stacked attended [2B, D]; BD = B*D */
+int ekaid_head_fwd(const float* attended, int64_t BD, float* input_attended, void* stream);
+/* gradients of the module's five outputs (att_bef, att_aft, attended_1, attended_2, input_attended; each may be NULL = zero)
+ * -> d_att [2*B*N] and d_attended [2B, D] of the fusion stage, one launch; BN = B*N, BD = B*D */
+int ekaid_head_bwd(const float* d_att_bef, const float* d_att_aft, const float* d_a1, const float* d_a2, const float* d_ia,
+                   int64_t BN, int64_t BD, float* d_att, float* d_attended, void* stream);
 
 /* ---- legacy weight_norm(dim=None) (models/fc.py:33-34): w = v * g / ||v||_F over the whole tensor -------------- */
 /* workspace: 128 floats; norm_out: 1 float kept for the backward */
