@@ -413,30 +413,40 @@ def _ptr_array(tensors):
     return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
+def wn_many_compute(vg):
+    """The kernels of WNormManyFn.forward without autograd: (v0, g0, v1, g1, ...) -> (vs, gs, [w0, w1, ...], norms)."""
+    lib.require_device()
+    vs = [_f32c(t) for t in vg[0::2]]
+    gs = [_f32c(t).reshape(1) for t in vg[1::2]]
+    cnt = len(vs)
+    dev = vs[0].device
+    ws_out = [torch.empty_like(v) for v in vs]
+    norms = torch.empty(cnt, dtype=torch.float32, device=dev)
+    work = torch.empty(cnt * 128, dtype=torch.float32, device=dev)
+    ns = (ctypes.c_int64 * cnt)(*[v.numel() for v in vs])
+    pv, pg, pw = _ptr_array(vs), _ptr_array(gs), _ptr_array(ws_out)      # host arrays, read during the call
+    call("wn_fwd_many", cnt, ctypes.addressof(pv), ctypes.addressof(pg), ctypes.addressof(ns), ctypes.addressof(pw),
+         norms.data_ptr(), work.data_ptr())
+    return vs, gs, ws_out, norms
+
+
 class WNormManyFn(torch.autograd.Function):
-    """WNormFn for up to 16 (v, g) pairs at once: two launches forward and two backward for all of them (the
-    weight-normalised matrices of the relation encoders do not depend on the activations, so the step normalises them
-    together up front and autograd differentiates them together once every dw has arrived).
-    Arguments: v0, g0, v1, g1, ...; returns (w0, w1, ...)."""
+    """WNormFn for up to 16 (v, g) pairs at once: two launches forward and two backward for all of them.
+    Arguments: pre, v0, g0, v1, g1, ...; returns (w0, w1, ...).
+
+    `pre` = wn_many_compute(...) of the same arguments, or None.  ChangeDetector computes the effective weights early
+    (they feed the activation-independent preparation that overlaps the question path) but creates THIS autograd node
+    only right before the encoder runs: autograd executes backward nodes newest-first, so the weight-norm backward of an
+    encoder then runs right after that encoder's backward -- its v / g gradients are complete early and can be
+    exchanged between ranks while the rest of backward is still running."""
 
     @staticmethod
-    def forward(ctx, *vg):
-        lib.require_device()
-        vs = [_f32c(t) for t in vg[0::2]]
-        gs = [_f32c(t).reshape(1) for t in vg[1::2]]
-        cnt = len(vs)
-        dev = vs[0].device
-        ws_out = [torch.empty_like(v) for v in vs]
-        norms = torch.empty(cnt, dtype=torch.float32, device=dev)
-        work = torch.empty(cnt * 128, dtype=torch.float32, device=dev)
-        ns = (ctypes.c_int64 * cnt)(*[v.numel() for v in vs])
-        pv, pg, pw = _ptr_array(vs), _ptr_array(gs), _ptr_array(ws_out)      # host arrays, read during the call
-        call("wn_fwd_many", cnt, ctypes.addressof(pv), ctypes.addressof(pg), ctypes.addressof(ns), ctypes.addressof(pw),
-             norms.data_ptr(), work.data_ptr())
+    def forward(ctx, pre, *vg):
+        vs, gs, ws_out, norms = pre if pre is not None else wn_many_compute(vg)
         ctx.saved = (vs, gs, norms)
         ctx.gshapes = [t.shape for t in vg[1::2]]
         ctx.keys = [(v.data_ptr(), g.data_ptr()) for v, g in zip(vg[0::2], vg[1::2])]
-        return tuple(ws_out)
+        return tuple(w.view(w.shape) for w in ws_out) if pre is not None else tuple(ws_out)
 
     @staticmethod
     def backward(ctx, *dws):
@@ -451,7 +461,7 @@ class WNormManyFn(torch.autograd.Function):
         pdw, pv, pg, pdv, pdg = (_ptr_array(x) for x in (dwc, vs, gs, dvs, dgs))
         call("wn_bwd_many", cnt, ctypes.addressof(pdw), ctypes.addressof(pv), ctypes.addressof(pg), norms.data_ptr(),
              ctypes.addressof(ns), ctypes.addressof(pdv), ctypes.addressof(pdg), work.data_ptr())
-        out = []
+        out = [None]
         for dv, dg in zip(dvs, dgs):
             out += [dv, dg]
         return tuple(out)

@@ -35,7 +35,7 @@ with warnings.catch_warnings():
 
 from . import lib as _lib
 from .functions import (PC, Drop, EdgeAttentionFn, Fork, FusionFn, GRUFn, LinearFn, QuestionFn, RelationFn, SmallLinearFn, WNormFn,
-                        WNormManyFn, rng_advance)
+                        WNormManyFn, rng_advance, wn_many_compute)
 
 
 def _default_precision() -> str:
@@ -594,10 +594,13 @@ class ChangeDetector(nn.Module):
             gats['spa'] = self.spatial_relation.explicit_relation
         if graph in ('implicit', 'all', 'i+s'):
             gats['imp'] = self.imp_relation.implicit_relation
-        # every weight-normalised matrix of the selected encoders in two launches (and two more in backward)
-        lins = [lin for g in gats.values() for lin in g.wn_linears()]
-        ws = WNormManyFn.apply(*[t for lin in lins for t in (lin.weight_v, lin.weight_g)])
-        eff = {k: dict(zip(("sw", "q", "k", "p0"), ws[4 * i:4 * i + 4])) for i, k in enumerate(gats)}
+        # the four weight-normalised matrices of each encoder in two launches (and two more in backward).  One call per
+        # encoder, not one for all: its backward then runs as soon as THAT encoder's weight gradients exist, so the
+        # gradients of the encoders that finish first can be exchanged between ranks long before backward ends
+        wn_args = {k: [t for lin in g.wn_linears() for t in (lin.weight_v, lin.weight_g)] for k, g in gats.items()}
+        with torch.no_grad():
+            wn_pre = {k: wn_many_compute(wn_args[k]) for k in gats}
+        pre_w = {k: dict(zip(("sw", "q", "k", "p0"), wn_pre[k][2])) for k in gats}
         # ... and everything else that needs neither the activations nor the question vector: operand-type weight
         # copies, adjacency condition / label bias, geometry bias.  All of it overlaps the question path.
         geos = {'sem': (d_sem_adj_matrix, q_sem_adj_matrix, 100), 'spa': (d_adj_matrix, q_adj_matrix, 200),
@@ -610,13 +613,15 @@ class ChangeDetector(nn.Module):
         for i, (k, g) in enumerate(gats.items()):
             with fkp.branch(i):
                 preps[k] = g.prepare_step(pc, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k], site0=geos[k][2],
-                                          weights=eff[k])
+                                          weights=pre_w[k])
         cur.wait_stream(side)
         for i, k in enumerate(gats):
             if fkp.on:
                 cur.wait_stream(fkp.streams[i])
+            # the autograd node of this encoder's weight normalisation is created HERE (see WNormManyFn)
+            eff = dict(zip(("sw", "q", "k", "p0"), WNormManyFn.apply(wn_pre[k], *wn_args[k])))
             X, XT, _ = gats[k].relation_step(pc, X, XT, qv, geos[k][0], geos[k][1], B, G, B, N, drop=drops[k],
-                                             site0=geos[k][2], weights=eff[k], prep=preps[k])
+                                             site0=geos[k][2], weights=eff, prep=preps[k])
         mode = 1 if graph == 'all' else (2 if graph == 'i+s' else 0)
         coefs = (float(self.coef_sem), float(self.coef_spa), float(1 - self.coef_sem - self.coef_spa))
         fdrop = Drop(dev, self.training, p_fuse=self.dropout.p if ov is None else ov,

@@ -107,12 +107,21 @@ class FlatAdam:
         self.update_range(0, self.flat.numel())
 
 
-def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
-    """Data-parallel gradient exchange: ONE all-reduce over the flat gradient buffer, mean over ranks
-    (NCCL: ReduceOp.AVG over NVLink; gloo, used by the CPU tests, has no AVG -> SUM then scale)."""
+def allreduce_mean_(flat: torch.Tensor, group=None, wire_bf16: bool = False) -> torch.Tensor:
+    """Data-parallel gradient exchange: ONE all-reduce over a slice of the flat gradient buffer, mean over ranks
+    (NCCL: ReduceOp.AVG over NVLink; gloo, used by the CPU tests, has no AVG -> SUM then scale).
+    wire_bf16: the slice crosses NVLink as bf16 (half the bytes; own cast kernels on both sides) -- the 16-bit path's
+    gradients carry bf16 operand noise anyway; the fp32 path always exchanges fp32."""
     import torch.distributed as dist
     if dist.get_backend(group) == "nccl":
-        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+        n = flat.numel()
+        if wire_bf16 and flat.is_cuda and n % 64 == 0 and flat.data_ptr() % 16 == 0:
+            wire = torch.empty(n, dtype=torch.bfloat16, device=flat.device)
+            lib.call("cast_f32_bf16", flat.data_ptr(), 64, wire.data_ptr(), 64, n // 64, 64)
+            dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=group)
+            lib.call("cast_bf16_f32", wire.data_ptr(), 64, flat.data_ptr(), 64, n // 64, 64)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
     else:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         flat.div_(dist.get_world_size(group))
@@ -165,9 +174,9 @@ class GraphFusionStep:
         self.decoder_loss = decoder_loss
         self.pg = process_group
         # Flat parameter order = the order in which backward FINISHES the gradients, in contiguous segments:
-        #   0 fusion stage | 1 implicit encoder | 2 spatial encoder | 3 semantic encoder   (parameters whose gradient
-        #     is written by the stage's own backward; done as soon as that stage's backward has run)
-        #   4 everything else on the image path (weight-normalised v/g: their batched backward runs last; img)
+        #   0 fusion stage | 1 implicit encoder | 2 spatial encoder | 3 semantic encoder   (every parameter of the stage,
+        #     incl. its weight-normalised v / g pairs: each encoder's weight-norm backward runs right after the encoder's)
+        #   4 the ROI projection `img` (its gradient is the last one of the image path)
         #   5 question path (embedding, GRU, question attention): BPTT is the serial tail of the step
         # As soon as a segment is complete (autograd hooks count its gradients) its all-reduce (N > 1) and Adam update
         # go out on the optimizer stream and overlap the rest of backward; segment 4 goes out when BPTT is launched
@@ -177,8 +186,6 @@ class GraphFusionStep:
         def segment_of(name: str) -> int:
             if name.startswith(("w_emb.", "q_emb.", "q_att.")):
                 return 5
-            if "weight_v" in name or "weight_g" in name:
-                return 4
             if name.startswith(("context1.", "context2.", "gate1.", "gate2.", "embed.", "att.", "fc1.")):
                 return 0
             if name.startswith("imp_relation."):
@@ -187,7 +194,7 @@ class GraphFusionStep:
                 return 2
             if name.startswith("semantic_relation."):
                 return 3
-            return 4
+            return 4                      # img: its gradient is the last one of the image path
 
         seg = [segment_of(n) for n, _ in named]
         order = sorted(range(len(named)), key=lambda i: (seg[i], i))
@@ -213,6 +220,13 @@ class GraphFusionStep:
         # Measured (B200, 1 and 2 GPUs over NVLink): no gain -- 4.19 vs 4.15 ms and 4.52 vs 4.48 ms; the all-reduce is
         # cheap and the extra Adam launches compete with the GEMMs -- so it is off by default.
         self._early_segments = os.environ.get("EKAID_B200_EARLY_SEGMENTS", "0") == "1"
+        # Data parallel: the gradient all-reduce of a segment goes out the moment the segment is complete (NCCL kernels
+        # on the optimizer stream, next to the rest of backward); the Adam update of segments 0-4 still waits for the
+        # BPTT launch.  EKAID_B200_EARLY_REDUCE=0: one all-reduce at the BPTT launch (the round-1 behaviour).
+        self._early_reduce = os.environ.get("EKAID_B200_EARLY_REDUCE", "1") != "0"
+        self._reduced = [False] * self._nseg
+        wb = os.environ.get("EKAID_B200_AR_BF16", "auto")
+        self._wire_bf16 = (change_detector.precision == "bf16") if wb == "auto" else (wb == "1")
         if self._hooked:
             for p, k in zip(params, self._seg_of_param):
                 if k < 5:
@@ -220,15 +234,7 @@ class GraphFusionStep:
         self._cot = None
         self._graph = None
 
-    def _launch_run(self, k0: int, k1: int, wait_current: bool) -> bool:
-        """All-reduce + Adam of the contiguous segments k0 .. k1-1 on the optimizer stream (after everything enqueued so
-        far on the main stream and, if asked, on the calling stream)."""
-        first, last = self._seg_pidx[k0][0], self._seg_pidx[k1 - 1][1]
-        lo, hi = self._seg_range[k0][0], self._seg_range[k1 - 1][1]
-        if hi <= lo:
-            return False
-        if self.opt.sync_slots(first, last, dry_run=True):
-            return False                                    # some gradient is not in its slot: take the late path
+    def _opt(self, wait_current: bool):
         dev = self.opt.flat.device
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(dev)
@@ -236,9 +242,45 @@ class GraphFusionStep:
         st.wait_stream(self._main)
         if wait_current:
             st.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(st):
+        return st
+
+    def _reduce_run(self, k0: int, k1: int) -> None:
+        """All-reduce the not yet reduced parts of segments k0 .. k1-1 (contiguous runs together); caller is on the
+        optimizer stream."""
+        k = k0
+        while k < k1:
+            if self._reduced[k] or not self._nonempty(k):
+                k += 1
+                continue
+            j = k
+            while j + 1 < k1 and not self._reduced[j + 1] and self._nonempty(j + 1):
+                j += 1
+            allreduce_mean_(self.opt.grad[self._seg_range[k][0]:self._seg_range[j][1]], self.pg, self._wire_bf16)
+            for i in range(k, j + 1):
+                self._reduced[i] = True
+            k = j + 1
+
+    def _launch_reduce(self, k: int) -> bool:
+        """Early gradient exchange of one complete segment (no update yet)."""
+        first, last = self._seg_pidx[k]
+        if self.opt.sync_slots(first, last, dry_run=True):
+            return False
+        with torch.cuda.stream(self._opt(wait_current=True)):
+            self._reduce_run(k, k + 1)
+        return True
+
+    def _launch_run(self, k0: int, k1: int, wait_current: bool) -> bool:
+        """All-reduce (what has not been exchanged yet) + Adam of the contiguous segments k0 .. k1-1 on the optimizer
+        stream (after everything enqueued so far on the main stream and, if asked, on the calling stream)."""
+        first, last = self._seg_pidx[k0][0], self._seg_pidx[k1 - 1][1]
+        lo, hi = self._seg_range[k0][0], self._seg_range[k1 - 1][1]
+        if hi <= lo:
+            return False
+        if self.opt.sync_slots(first, last, dry_run=True):
+            return False                                    # some gradient is not in its slot: take the late path
+        with torch.cuda.stream(self._opt(wait_current)):
             if self.pg is not None:
-                allreduce_mean_(self.opt.grad[lo:hi], self.pg)
+                self._reduce_run(k0, k1)
             if not self._advanced:
                 self.opt.advance()
                 self._advanced = True
@@ -253,9 +295,13 @@ class GraphFusionStep:
     def _grad_ready(self, k: int):
         """autograd hook: one more gradient of segment k has been accumulated."""
         self._fired[k] += 1
-        if (self._armed and k < 4 and self._expected is not None and self._fired[k] == self._expected[k]
-                and not self._done[k] and self._nonempty(k) and self._early_segments):
+        if not (self._armed and k < 5 and self._expected is not None and self._fired[k] == self._expected[k]
+                and not self._done[k] and self._nonempty(k)):
+            return
+        if k < 4 and self._early_segments:
             self._launch_run(k, k + 1, wait_current=True)
+        elif self.pg is not None and self._early_reduce and not self._reduced[k]:
+            self._launch_reduce(k)
 
     def _bptt_starts(self):
         """functions.BPTT_HOOK: the question path is about to run its recurrence backwards (one long kernel on 64 SMs).
@@ -309,6 +355,7 @@ class GraphFusionStep:
         total = self.loss(inputs, labels, masks)
         self._fired = [0] * self._nseg
         self._done = [False] * self._nseg
+        self._reduced = [False] * self._nseg
         self._advanced = False
         self._main = torch.cuda.current_stream() if total.is_cuda else None
         self._armed = self._hooked
@@ -329,6 +376,8 @@ class GraphFusionStep:
         # whatever was not updated early: (clone-instead-of-adopt gradients go into their slots first; normally none)
         pending = [k for k in range(self._nseg) if not self._done[k] and self._seg_range[k][1] > self._seg_range[k][0]]
         if pending:
+            if self._opt_stream is not None and any(self._reduced):
+                torch.cuda.current_stream().wait_stream(self._opt_stream)      # early exchanges of pending segments
             for k in pending:
                 self.opt.sync_slots(*self._seg_pidx[k])
             if not self._advanced:
@@ -345,7 +394,12 @@ class GraphFusionStep:
                     runs.append(cur)
             for lo, hi in runs:
                 if self.pg is not None:
-                    allreduce_mean_(self.opt.grad[lo:hi], self.pg)
+                    # (segments exchanged early keep their flag; a run may mix both, so go segment by segment)
+                    for k in pending:
+                        slo, shi = self._seg_range[k]
+                        if lo <= slo and shi <= hi and not self._reduced[k]:
+                            allreduce_mean_(self.opt.grad[slo:shi], self.pg, self._wire_bf16)
+                            self._reduced[k] = True
                 self.opt.update_range(lo, hi)
         if self._opt_stream is not None and any(self._done):
             torch.cuda.current_stream().wait_stream(self._opt_stream)

@@ -245,7 +245,7 @@ def test_small_linear_weighted_sums_wn_many():
 
     vs = [_mk(s, dev, 80 + i, torch.float32).requires_grad_(True) for i, s in enumerate([(1024, 2048), (1024, 1024), (4, 64), (1, 11)])]
     gs = [torch.tensor(1.5 + i, device=dev).requires_grad_(True) for i in range(4)]
-    outs = WNormManyFn.apply(*[t for v, g in zip(vs, gs) for t in (v, g)])
+    outs = WNormManyFn.apply(None, *[t for v, g in zip(vs, gs) for t in (v, g)])
     cot = [_mk(v.shape, dev, 90 + i, torch.float32) for i, v in enumerate(vs)]
     sum((o * c).sum() for o, c in zip(outs, cot)).backward()
     for v, g, o, c in zip(vs, gs, outs, cot):
