@@ -47,7 +47,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, int fmt, cudaStream_t stream);
 void ek_gemm_debug(int flags, unsigned long long* ts);
 int ek_cast_f32_bf16_launch(const float*, long long, bf16*, long long, long long, int, int, cudaStream_t);
-int ek_cast_bf16_f32_launch(const bf16*, long long, float*, long long, long long, int, cudaStream_t);
+int ek_cast_bf16_f32_launch(const bf16*, long long, float*, long long, long long, int, float, cudaStream_t);
 int ek_copy_f32_launch(const float*, long long, float*, long long, long long, int, cudaStream_t);
 int ek_colsum_launch(int, const void*, long long, long long, int, const float*, float*, float*, cudaStream_t);
 int ek_row_zero_flags_launch(const float*, long long, int, uint8_t*, cudaStream_t);
@@ -217,7 +217,11 @@ int ekaid_cast_f32_f16(const float* src, int64_t lds, void* dst, int64_t ldd, in
   return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, 1, ST);
 }
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
-  return ek_cast_bf16_f32_launch((const bf16*)src, lds, dst, ldd, rows, cols, ST);
+  return ek_cast_bf16_f32_launch((const bf16*)src, lds, dst, ldd, rows, cols, 1.0f, ST);
+}
+int ekaid_cast_bf16_f32_scaled(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, float scale,
+                               void* stream) {
+  return ek_cast_bf16_f32_launch((const bf16*)src, lds, dst, ldd, rows, cols, scale, ST);
 }
 int ekaid_copy_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
   return ek_copy_f32_launch(src, lds, dst, ldd, rows, cols, ST);

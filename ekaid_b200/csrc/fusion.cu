@@ -93,14 +93,14 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, long long lds, fl
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, long long lds, float* __restrict__ dst,
-                                     long long ldd, long long rows, int cols) {
+                                     long long ldd, long long rows, int cols, float scale) {
   ek_pdl_prologue();
   const long long total = rows * cols;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const long long r = e / cols;
     const int c = (int)(e % cols);
-    dst[r * ldd + c] = __bfloat162float(src[r * lds + c]);
+    dst[r * ldd + c] = scale * __bfloat162float(src[r * lds + c]);
   }
 }
 
@@ -987,9 +987,9 @@ int ek_copy_f32_launch(const float* src, long long lds, float* dst, long long ld
   return EK_OK;
 }
 int ek_cast_bf16_f32_launch(const bf16* src, long long lds, float* dst, long long ldd, long long rows, int cols,
-                            cudaStream_t st) {
+                            float scale, cudaStream_t st) {
   if (rows * cols == 0) return EK_OK;
-  ek_launch(cast_bf16_f32_kernel, grid_for(rows * cols), 256, 0, st, src, lds, dst, ldd, rows, cols);
+  ek_launch(cast_bf16_f32_kernel, grid_for(rows * cols), 256, 0, st, src, lds, dst, ldd, rows, cols, scale);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

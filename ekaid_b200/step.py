@@ -115,11 +115,14 @@ def allreduce_mean_(flat: torch.Tensor, group=None, wire_bf16: bool = False) -> 
     import torch.distributed as dist
     if dist.get_backend(group) == "nccl":
         n = flat.numel()
+        world = dist.get_world_size(group)
         if wire_bf16 and flat.is_cuda and n % 64 == 0 and flat.data_ptr() % 16 == 0:
+            # SUM, not AVG: NCCL implements AVG as a pre-multiplied sum, which rules out the in-switch (NVLS) reduction;
+            # the 1 / world factor is applied by the cast back to fp32
             wire = torch.empty(n, dtype=torch.bfloat16, device=flat.device)
             lib.call("cast_f32_bf16", flat.data_ptr(), 64, wire.data_ptr(), 64, n // 64, 64)
-            dist.all_reduce(wire, op=dist.ReduceOp.AVG, group=group)
-            lib.call("cast_bf16_f32", wire.data_ptr(), 64, flat.data_ptr(), 64, n // 64, 64)
+            dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=group)
+            lib.call("cast_bf16_f32_scaled", wire.data_ptr(), 64, flat.data_ptr(), 64, n // 64, 64, 1.0 / world)
         else:
             dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
     else:
@@ -223,7 +226,14 @@ class GraphFusionStep:
         # Data parallel: the gradient all-reduce of a segment goes out the moment the segment is complete (NCCL kernels
         # on the optimizer stream, next to the rest of backward); the Adam update of segments 0-4 still waits for the
         # BPTT launch.  EKAID_B200_EARLY_REDUCE=0: one all-reduce at the BPTT launch (the round-1 behaviour).
-        self._early_reduce = os.environ.get("EKAID_B200_EARLY_REDUCE", "1") != "0"
+        er = os.environ.get("EKAID_B200_EARLY_REDUCE", "auto")
+        if er == "auto":
+            # measured (profiles/r02_notes.md): with 2 ranks the early exchanges hide behind backward (3.95 vs 4.15 ms);
+            # with 8 the ranks drift apart during backward and every early ring stalls the faster ones (4.34 vs 4.12 ms)
+            import torch.distributed as dist
+            self._early_reduce = process_group is not None and dist.get_world_size(process_group) <= 2
+        else:
+            self._early_reduce = er != "0"
         self._reduced = [False] * self._nseg
         wb = os.environ.get("EKAID_B200_AR_BF16", "auto")
         self._wire_bf16 = (change_detector.precision == "bf16") if wb == "auto" else (wb == "1")

@@ -116,6 +116,10 @@ int ekaid_gemm_debug(int flags, void* ts);
 /* ---- casts / reductions / glue -------------------------------------------------------------------------- */
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+/* dst = scale * float(src): the receiving side of the bf16 gradient exchange (scale = 1 / world size after a SUM
+ * all-reduce, which -- unlike AVG -- NCCL can run inside the NVSwitch) */
+int ekaid_cast_bf16_f32_scaled(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, float scale,
+                               void* stream);
 /* fp32 -> IEEE fp16, round to nearest, saturating at +-65504 (forward operands of the 16-bit path: weights, bounded
  * activations) */
 int ekaid_cast_f32_f16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
