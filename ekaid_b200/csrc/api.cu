@@ -79,6 +79,11 @@ int ek_adam_advance_launch(float*, float, float, cudaStream_t);
 int ek_adj_prep_fwd_launch(const float*, const float*, int, const float*, int, int, int, int, float*, float*,
                            cudaStream_t);
 int ek_adj_prep_bwd_launch(const float*, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
+int ek_adj_labels_fwd_launch(const int8_t*, const int8_t*, int, int, const float*, int, int, int, int, float*, float*,
+                             cudaStream_t);
+int ek_adj_labels_bwd_launch(const int8_t*, const int8_t*, int, int, const float*, int, int, int, int, int, float*,
+                             cudaStream_t);
+int ek_onehot_adj_i8_launch(const int8_t*, int, int, int, int, float*, cudaStream_t);
 int ek_geom_bias_fwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
                             int, float*, EkDrop, float*, int, cudaStream_t);
 int ek_geom_bias_bwd_launch(const double*, const double*, int, const float*, const float*, const float*, int, int, int,
@@ -441,4 +446,17 @@ int ekaid_head_fwd(const float* attended, int64_t BD, float* input_attended, voi
 int ekaid_head_bwd(const float* d_att_bef, const float* d_att_aft, const float* d_a1, const float* d_a2, const float* d_ia,
                    int64_t BN, int64_t BD, float* d_att, float* d_attended, void* stream) {
   return ek_head_bwd_launch(d_att_bef, d_att_aft, d_a1, d_a2, d_ia, BN, BD, d_att, d_attended, ST);
+}
+
+int ekaid_adj_labels_fwd(const int8_t* lab0, const int8_t* lab1, int g_split, int S, const float* w, int G, int N, int Kn,
+                         int L, float* cond, float* lbias, void* stream) {
+  return ek_adj_labels_fwd_launch(lab0, lab1, g_split, S, w, G, N, Kn, L, cond, lbias, ST);
+}
+int ekaid_adj_labels_bwd(const int8_t* lab0, const int8_t* lab1, int g_split, int S, const float* dlbias_part, int nparts,
+                         int G, int N, int Kn, int L, float* dw_part, void* stream) {
+  return ek_adj_labels_bwd_launch(lab0, lab1, g_split, S, dlbias_part, nparts, G, N, Kn, L, dw_part, ST);
+}
+int ekaid_onehot_adj_i8(const int8_t* labels, int B, int S, int N, int L, float* out, void* stream) {
+  EK_REQUIRE(N <= S && L >= 1, EK_ERR_SHAPE, "onehot_adj_i8: N=%d > S=%d", N, S);
+  return ek_onehot_adj_i8_launch(labels, B, S, N, L, out, ST);
 }

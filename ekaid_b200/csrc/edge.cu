@@ -80,6 +80,61 @@ __global__ void adj_prep_bwd_kernel(const float* __restrict__ adj0, const float*
   }
 }
 
+// The same two kernels on the loader's INTEGER label matrices (int8 [*, S, S], label 0 = no edge, c+1 = plane c of
+// process_matrix, utils/mimic_utils.py:119-149): a one-hot row sums to (1 <= label <= L) and its dot product with the
+// bias table is w[label - 1], so the fp32 one-hot planes (4 * L bytes per edge) never have to exist.
+__global__ void adj_labels_fwd_kernel(const int8_t* __restrict__ lab0, const int8_t* __restrict__ lab1, int g_split, int S,
+                                      const float* __restrict__ w, int N, int Kn, int L, float* __restrict__ cond,
+                                      float* __restrict__ lbias) {
+  ek_pdl_prologue();
+  const int g = blockIdx.x;
+  const int8_t* lab = (g < g_split) ? lab0 + (size_t)g * S * S : lab1 + (size_t)(g - g_split) * S * S;
+  for (int e = threadIdx.x; e < N * Kn; e += blockDim.x) {
+    const int i = e / Kn, j = e % Kn;
+    const int l = lab[(size_t)j * S + i];               // transposed: adjacency entry (j, i)   (graph_att.py:76, Q2)
+    const bool on = l >= 1 && l <= L;
+    cond[(size_t)g * N * Kn + e] = on ? 1.f : 0.f;
+    lbias[(size_t)g * N * Kn + e] = on ? __ldg(w + l - 1) : 0.f;
+  }
+}
+// dw_part[g, c] = sum over the edges of image g with label c+1 of sum_p dlbias_part[p, g, i, j]
+__global__ void adj_labels_bwd_kernel(const int8_t* __restrict__ lab0, const int8_t* __restrict__ lab1, int g_split, int S,
+                                      const float* __restrict__ dlbias_part, int nparts, int N, int Kn, int L,
+                                      float* __restrict__ dw_part) {
+  ek_pdl_prologue();
+  constexpr int LC = 16;
+  __shared__ float red[8][LC];
+  const int g = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int8_t* lab = (g < g_split) ? lab0 + (size_t)g * S * S : lab1 + (size_t)(g - g_split) * S * S;
+  for (int c0 = 0; c0 < L; c0 += LC) {
+    const int lc = min(LC, L - c0);
+    float acc[LC];
+#pragma unroll
+    for (int c = 0; c < LC; ++c) acc[c] = 0.f;
+    for (int e = threadIdx.x; e < N * Kn; e += blockDim.x) {
+      const int i = e / Kn, j = e % Kn;
+      float dl = 0.f;
+      for (int p = 0; p < nparts; ++p) dl += dlbias_part[((size_t)p * gridDim.x + g) * N * Kn + e];
+      const int l = (int)lab[(size_t)j * S + i] - 1 - c0;
+#pragma unroll
+      for (int c = 0; c < LC; ++c) acc[c] += (c == l) ? dl : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < LC; ++c) {
+      const float v = warp_sum(acc[c]);
+      if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < lc) {
+      float t = 0.f;
+      for (int w_ = 0; w_ < (int)(blockDim.x >> 5); ++w_) t += red[w_][threadIdx.x];
+      dw_part[(size_t)g * L + c0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // geometry bias (implicit relation)
 // ------------------------------------------------------------------------------------------------
@@ -713,6 +768,21 @@ int ek_adj_prep_fwd_launch(const float* adj0, const float* adj1, int g_split, co
 int ek_adj_prep_bwd_launch(const float* adj0, const float* adj1, int g_split, const float* dlbias_part, int nparts,
                            int G, int N, int Kn, int L, float* dw_part, cudaStream_t st) {
   ek_launch(adj_prep_bwd_kernel, G, 256, 0, st, adj0, adj1, g_split, dlbias_part, nparts, N, Kn, L, dw_part);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_adj_labels_fwd_launch(const int8_t* lab0, const int8_t* lab1, int g_split, int S, const float* w, int G, int N,
+                             int Kn, int L, float* cond, float* lbias, cudaStream_t st) {
+  EK_REQUIRE(N <= S && Kn <= N, EK_ERR_SHAPE, "adj_labels: N=%d Kn=%d S=%d", N, Kn, S);
+  ek_launch(adj_labels_fwd_kernel, G, 256, 0, st, lab0, lab1, g_split, S, w, N, Kn, L, cond, lbias);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+int ek_adj_labels_bwd_launch(const int8_t* lab0, const int8_t* lab1, int g_split, int S, const float* dlbias_part,
+                             int nparts, int G, int N, int Kn, int L, float* dw_part, cudaStream_t st) {
+  EK_REQUIRE(N <= S && Kn <= N, EK_ERR_SHAPE, "adj_labels: N=%d Kn=%d S=%d", N, Kn, S);
+  ek_launch(adj_labels_bwd_kernel, G, 256, 0, st, lab0, lab1, g_split, S, dlbias_part, nparts, N, Kn, L, dw_part);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

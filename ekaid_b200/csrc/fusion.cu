@@ -519,6 +519,21 @@ __global__ void onehot_adj_kernel(const double* __restrict__ labels, int S, int 
   }
 }
 
+// the same from the loader's compact int8 label matrices
+__global__ void onehot_adj_i8_kernel(const int8_t* __restrict__ labels, int S, int N, int L, long long total,
+                                     float* __restrict__ out) {
+  ek_pdl_prologue();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / ((long long)N * N);
+    const int ij = (int)(e % ((long long)N * N));
+    const int i = ij / N, j = ij % N;
+    const int v = labels[(b * S + i) * S + j];
+    float* o = out + e * L;
+    for (int c = 0; c < L; ++c) o[c] = (v == c + 1) ? 1.f : 0.f;
+  }
+}
+
 // ---------------------------------------------------------------- spatial adjacency labels from ROI boxes
 // bbox_relation_type / reverse_type / get_adj_matrix ("feature extraction/ana_bbox_generator.py":213-259,266-302,
 // 320-335): boxes f64 [B, N, 4] (xmin, ymin, xmax, ymax) -> labels f64 [B, S, S] (the HDF5 `image_adj_matrix` layout the
@@ -1130,6 +1145,14 @@ int ek_onehot_adj_launch(const double* labels, int B, int S, int N, int L, float
   const long long total = (long long)B * N * N;
   if (total == 0) return EK_OK;
   ek_launch(onehot_adj_kernel, grid_for(total), 256, 0, st, labels, S, N, L, total, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_onehot_adj_i8_launch(const int8_t* labels, int B, int S, int N, int L, float* out, cudaStream_t st) {
+  const long long total = (long long)B * N * N;
+  if (total == 0) return EK_OK;
+  ek_launch(onehot_adj_i8_kernel, grid_for(total), 256, 0, st, labels, S, N, L, total, out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

@@ -1019,6 +1019,13 @@ def _dim_t(dev, feat_dim=64, wave_length=1000.0):
     return _dim_t_cache[key]
 
 
+def _labels_i8(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.int8:
+        t = t.to(torch.int8)
+    return t.contiguous()
+
+
 def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, Wo2, p0, p1, adj0, adj1, g_split,
                      need_bwd: bool = True):
     """Everything of a relation step that does not depend on the activations or the question vector: operand-type
@@ -1055,17 +1062,29 @@ def relation_prepare(pc: PC, drop, site0, kind: str, dims, Wsw, Wq, bq, Wk, bk, 
     cast_many(pc, jobs)          # one launch instead of up to sixteen
     cond = lbias = gbias = None
     if kind == "explicit":
-        a0 = _f32c(adj0)
-        a1 = _f32c(adj1) if adj1 is not None else None
-        Lb = a0.shape[-1]
-        if a0.shape[1] != N or a0.shape[2] != N or (a1 is not None and a1.shape[1:] != a0.shape[1:]):
-            raise ValueError("adjacency must be [*, %d, %d, labels], got %s" % (N, N, tuple(a0.shape)))
         wb = _f32c(p0).view(-1)
         cond = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
         lbias = torch.empty(G, N, Kn, dtype=torch.float32, device=dev)
-        call("adj_prep_fwd", a0.data_ptr(), ptr(a1), g_split, wb.data_ptr(), G, N, Kn, Lb, cond.data_ptr(),
-             lbias.data_ptr())
-        geo = (a0, a1, Lb)
+        if adj0.dim() == 3:
+            # the loader's integer label matrices [*, S, S] (0 = no edge, c + 1 = plane c of process_matrix): consumed
+            # as they are, the fp32 one-hot planes are never built
+            a0 = _labels_i8(adj0)
+            a1 = _labels_i8(adj1) if adj1 is not None else None
+            Lb, S = wb.numel(), a0.shape[1]
+            if a0.shape[2] != S or S < N or (a1 is not None and a1.shape[1:] != a0.shape[1:]):
+                raise ValueError("label matrices must be [*, S, S] with S >= %d, got %s" % (N, tuple(a0.shape)))
+            call("adj_labels_fwd", a0.data_ptr(), ptr(a1), g_split, S, wb.data_ptr(), G, N, Kn, Lb, cond.data_ptr(),
+                 lbias.data_ptr())
+            geo = (a0, a1, Lb, S)
+        else:
+            a0 = _f32c(adj0)
+            a1 = _f32c(adj1) if adj1 is not None else None
+            Lb = a0.shape[-1]
+            if a0.shape[1] != N or a0.shape[2] != N or (a1 is not None and a1.shape[1:] != a0.shape[1:]):
+                raise ValueError("adjacency must be [*, %d, %d, labels], got %s" % (N, N, tuple(a0.shape)))
+            call("adj_prep_fwd", a0.data_ptr(), ptr(a1), g_split, wb.data_ptr(), G, N, Kn, Lb, cond.data_ptr(),
+                 lbias.data_ptr())
+            geo = (a0, a1, Lb, 0)
     else:
         a0 = adj0.detach().to(device=dev, dtype=torch.float64).contiguous()
         a1 = adj1.detach().to(device=dev, dtype=torch.float64).contiguous() if adj1 is not None else None
@@ -1248,23 +1267,38 @@ class RelationFn(torch.autograd.Function):
         call("edge_softmax_bwd", pc.f, P.data_ptr(), dPpart.data_ptr(), ns, QKZ.data_ptr(), QKZ.stride(0), D, ptr(cond),
              G, N, Kn, H, dQKZ.data_ptr(), ptr(dlb), ptr(dgb),
              info={"bytes": G * (N * H * Kn * 4 * (2 + ns) + 2 * (N + Kn) * D * es)})
+        # gradient of the label-bias table / the geometry FC: leaves of the backward graph (they feed no other gradient),
+        # so they run on a side stream next to the dgrad / wgrad GEMMs below instead of in front of them
         dp0 = dp1 = None
+        fkp = Fork(dev, 1, pool="leaf")
         if kind == "explicit":
-            a0, a1, Lb = ctx.geo
+            a0, a1, Lb, S = ctx.geo
             part = torch.empty(G, Lb, dtype=torch.float32, device=dev)
-            call("adj_prep_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, dlb.data_ptr(), H, G, N, Kn, Lb, part.data_ptr())
-            dp0 = colsum(part, G, Lb).view(1, Lb)
+            dp0 = torch.empty(Lb, dtype=torch.float32, device=dev)
+            with fkp.branch(0):
+                if S:
+                    call("adj_labels_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, S, dlb.data_ptr(), H, G, N, Kn, Lb,
+                         part.data_ptr())
+                else:
+                    call("adj_prep_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, dlb.data_ptr(), H, G, N, Kn, Lb,
+                         part.data_ptr())
+                colsum(part, G, Lb, out=dp0)
+            dp0 = dp0.view(1, Lb)
         else:
             a0, a1, Wp, bp, emb_cache = ctx.geo
             nparts = G * lib.load().ekaid_geom_bias_bwd_parts()
             part = torch.empty(nparts, H * 65, dtype=torch.float32, device=dev)
-            call("geom_bias_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, Wp.data_ptr(), bp.data_ptr(),
-                 _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr(),
-                 *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)), ptr(emb_cache), pc.f)
-            tot = colsum(part, nparts, H * 65).view(H, 65)
-            dp0 = tot[:, :64].contiguous()
+            tot = torch.empty(H * 65, dtype=torch.float32, device=dev)
+            dp0 = torch.empty(H, 64, dtype=torch.float32, device=dev)
             dp1 = _dst(kk["p1"], (H,), dev)
-            dp1.copy_(tot[:, 64])
+            with fkp.branch(0):
+                call("geom_bias_bwd", a0.data_ptr(), ptr(a1), ctx.g_split, Wp.data_ptr(), bp.data_ptr(),
+                     _dim_t(dev).data_ptr(), G, N, Kn, H, dgb.data_ptr(), part.data_ptr(),
+                     *(drop.a(site0 + 4, drop.p_fc) if don else (None, 0, 0.0)), ptr(emb_cache), pc.f)
+                colsum(part, nparts, H * 65, out=tot)
+                t2 = tot.view(H, 65)
+                dp0.copy_(t2[:, :64])
+                dp1.copy_(t2[:, 64])
         Dq = qvT.shape[1]
         dbq = _dst(kk["bq"], (D,), dev)
         dbk = _dst(kk["bk"], (D,), dev)
@@ -1326,6 +1360,7 @@ class RelationFn(torch.autograd.Function):
                 call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(), dqv.data_ptr())
             gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX, drop=s1 + (D + Dq, 0))   # + residual gradient
             fk.join()
+        fkp.join()
         return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWq, dbq, dWk, dbk, dWo2, dbout, dp0, dp1,
                 None, None, None, None)
 
@@ -1472,6 +1507,12 @@ def onehot_adj(labels: torch.Tensor, num_objects: int, label_num: int) -> torch.
     -> fp32 one-hot [B,N,N,L]."""
     lib.require_device()
     lab = labels.detach()
+    if lab.dtype == torch.int8:
+        lab = lab.contiguous()
+        Bn, S = lab.shape[0], lab.shape[1]
+        out = torch.empty(Bn, num_objects, num_objects, label_num, dtype=torch.float32, device=lab.device)
+        call("onehot_adj_i8", lab.data_ptr(), Bn, S, num_objects, label_num, out.data_ptr())
+        return out
     if lab.dtype != torch.float64:
         lab = lab.double()
     lab = lab.contiguous()

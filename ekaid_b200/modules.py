@@ -556,6 +556,11 @@ class ChangeDetector(nn.Module):
                 question, setting='mode2', graph='all'):
         if self.cfg.data.train.empty_image == True:  # noqa: E712  (modules.py:170-178)
             input_1, input_2 = torch.ones_like(input_1), torch.ones_like(input_2)
+            if d_adj_matrix.dim() == 3:        # label matrices: the reference sees all-ones ONE-HOT tensors here
+                n_ = input_1.shape[1]
+                ones = lambda L: torch.ones(input_1.shape[0], n_, n_, L, device=input_1.device)  # noqa: E731
+                d_adj_matrix, q_adj_matrix = ones(self.cfg.model.change_detector.spa_label_num), ones(self.cfg.model.change_detector.spa_label_num)
+                d_sem_adj_matrix, q_sem_adj_matrix = ones(self.cfg.model.change_detector.sem_label_num), ones(self.cfg.model.change_detector.sem_label_num)
             d_adj_matrix, q_adj_matrix = torch.ones_like(d_adj_matrix), torch.ones_like(q_adj_matrix)
             d_sem_adj_matrix, q_sem_adj_matrix = torch.ones_like(d_sem_adj_matrix), torch.ones_like(q_sem_adj_matrix)
             d_bb, q_bb = torch.ones_like(d_bb), torch.ones_like(q_bb)

@@ -138,31 +138,43 @@ def shard_batch(batch, rank: int, world: int):
     return tuple(t[rank * per:(rank + 1) * per] for t in batch)
 
 
-def select_fields(batch):
+def select_fields(batch, compact: bool = True):
     """The 11 tensors of the loader's 13-tuple that the step consumes (train_mimic.py:206-218), in step order:
     (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question, labels, masks); adjacency still as integer
-    label matrices [B,S,S]."""
+    label matrices [B,S,S].  compact: the four label matrices (values 0..11, stored as float64 by the reference's
+    collate) are narrowed to int8 on the host -- the collate-side half of SURVEY.md section 8f row 2: 20 MB -> 2.5 MB
+    of the 48 MB a batch of 64 moves over PCIe -- and the relation encoders read them as they are."""
     (d_feats, sc_feats, labels, sc_pos_labels, masks, pair_index, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb,
      question) = batch
+    if compact:
+        d_adj, q_adj, d_sem, q_sem = (t if t.dtype == torch.int8 else t.to(torch.int8)
+                                      for t in (d_adj, q_adj, d_sem, q_sem))
     return (d_feats, sc_feats, d_adj, q_adj, d_sem, q_sem, d_bb, q_bb, question, labels.squeeze(1), masks.squeeze(1))
 
 
-def to_device(batch, device):
+def to_device(batch, device, compact: bool = True):
     """Host 13-tuple -> device tensors (pinned host memory makes the copies asynchronous)."""
-    return tuple(t.to(device, non_blocking=True) for t in select_fields(batch))
+    return tuple(t.to(device, non_blocking=True) for t in select_fields(batch, compact))
 
 
-def expand_adjacency(raw, cfg):
-    """train_mimic.py:223-227 (process_matrix x4), one kernel per matrix.  -> the 9 ChangeDetector inputs."""
+def expand_adjacency(raw, cfg, onehot: bool = None):
+    """train_mimic.py:223-227.  -> the 9 ChangeDetector inputs.  int8 label matrices (select_fields(compact=True)) are
+    handed to ChangeDetector as they are: its relation encoders take the label of an edge straight from the matrix
+    (`adj_labels_fwd/bwd`), so the fp32 one-hot tensors of process_matrix never exist.  onehot=True (default for any
+    other dtype) runs process_matrix x4, one kernel per matrix, and yields the reference's [B,N,N,L] tensors."""
     cd = cfg.model.change_detector
     n = raw[0].shape[1]
+    if onehot is None:
+        onehot = raw[2].dtype != torch.int8
+    if not onehot:
+        return tuple(raw[:9])
     return (raw[0], raw[1], onehot_adj(raw[2], n, cd.spa_label_num), onehot_adj(raw[3], n, cd.spa_label_num),
             onehot_adj(raw[4], n, cd.sem_label_num), onehot_adj(raw[5], n, cd.sem_label_num), raw[6], raw[7], raw[8])
 
 
-def process_batch(batch, cfg, device):
+def process_batch(batch, cfg, device, compact: bool = True):
     """to_device + expand_adjacency.  Returns (inputs, labels, masks)."""
-    raw = to_device(batch, device)
+    raw = to_device(batch, device, compact)
     return expand_adjacency(raw, cfg), raw[9], raw[10].float()
 
 

@@ -160,6 +160,15 @@ int ekaid_adj_prep_fwd(const float* adj0, const float* adj1, int g_split, const 
 /* dw_part[g,c] = sum_ij adj[g,j,i,c] * sum_p dlbias_part[p,g,i,j] */
 int ekaid_adj_prep_bwd(const float* adj0, const float* adj1, int g_split, const float* dlbias_part, int nparts, int G,
                        int N, int Kn, int L, float* dw_part, void* stream);
+/* The same on the loader's integer label matrices (int8 [*, S, S]; 0 = no edge, c+1 = plane c of process_matrix,
+ * utils/mimic_utils.py:119-149): cond = (1 <= label <= L), lbias = w[label - 1]; the fp32 one-hot planes are never built.
+ * This is what ChangeDetector.forward runs when it is handed label matrices instead of one-hot adjacency. */
+int ekaid_adj_labels_fwd(const int8_t* lab0, const int8_t* lab1, int g_split, int S, const float* w, int G, int N, int Kn,
+                         int L, float* cond, float* lbias, void* stream);
+int ekaid_adj_labels_bwd(const int8_t* lab0, const int8_t* lab1, int g_split, int S, const float* dlbias_part, int nparts,
+                         int G, int N, int Kn, int L, float* dw_part, void* stream);
+/* process_matrix from int8 labels (for callers that want the reference's one-hot tensors) */
+int ekaid_onehot_adj_i8(const int8_t* labels, int B, int S, int N, int L, float* out, void* stream);
 /* gbias[g,i,j,h] = log(max(relu(Wp[h,:] . posemb(pair) + bp[h]), 1e-6)) straight from fp64 boxes [G,N,4]
  * (modules.py:162-166, utils/mimic_utils.py:152-208, graph_att_layer.py:113-135; Q7, Q13).
  * dim_t: 8 fp32 wave lengths 1000^(t/8) */

@@ -104,6 +104,21 @@ def test_synthetic_loader_shapes_and_rules():
     assert all(torch.equal(x, y) for x, y in zip(b, same))
 
 
+def test_collate_narrows_label_matrices_to_int8_losslessly():
+    """select_fields(compact=True): the four label matrices travel as int8 and hold the same labels."""
+    from ekaid_b200.step import select_fields
+    from ekaid_b200.synthetic import synthetic_batch
+    b = synthetic_batch(3, 52, seed=5)
+    wide, narrow = select_fields(b, compact=False), select_fields(b)
+    for i in (2, 3, 4, 5):
+        assert wide[i].dtype == torch.float64 and narrow[i].dtype == torch.int8
+        assert torch.equal(narrow[i].double(), wide[i])
+    for i in (0, 1, 6, 7, 8, 9, 10):
+        assert narrow[i].dtype == wide[i].dtype and torch.equal(narrow[i], wide[i])
+    per_sample = lambda t: sum(x.numel() * x.element_size() for x in t) // 3    # noqa: E731
+    assert per_sample(wide) - per_sample(narrow) == 4 * 100 * 100 * 7
+
+
 def test_golden_manifest_complete():
     from helpers import CASES
     for c in CASES:

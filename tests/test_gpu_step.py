@@ -202,3 +202,41 @@ def test_second_gradient_contribution_accumulates_instead_of_overwriting():
     finally:
         functions.GRAD_SLOTS.clear()
         functions.slots_reset()
+
+
+@pytest.mark.parametrize("case", ["c1_b3_n52_all_grads", "c4_b2_n60_k52_all"])
+def test_int8_label_matrices_equal_the_onehot_path_bit_for_bit(case):
+    """ChangeDetector fed the loader's label matrices (int8 [B,S,S]) must give exactly what it
+    gives on process_matrix's one-hot tensors (utils/mimic_utils.py:119-149) -- every output and every parameter
+    gradient, including the label-bias tables that the labels index -- and onehot_adj(int8) == process_matrix."""
+    from ekaid_b200.functions import onehot_adj
+    from ekaid_b200.step import select_fields
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z, meta = load_case(case)
+    sd, inp, batch = case_inputs(meta)
+    dinp = to_dev(inp, dev)
+    raw = tuple(t.to(dev) for t in select_fields(batch))
+    assert raw[2].dtype == torch.int8 and raw[2].dim() == 3
+    N = meta["N"]
+    assert torch.equal(onehot_adj(raw[2], N, 11).cpu(), O.process_matrix(batch[6], N, 11))
+    assert torch.equal(onehot_adj(raw[4], N, 3).cpu(), O.process_matrix(batch[8], N, 3))
+    for precision in ("fp32", "bf16"):
+        res = []
+        for inputs in (dinp, raw[:9]):
+            m = build_model(meta, sd, precision, dev)
+            outs = m(*inputs)
+            _loss(outs).backward()
+            res.append(([o.detach().clone() for o in outs],
+                        {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+        for a, b in zip(res[0][0], res[1][0]):
+            assert torch.equal(a, b)
+        assert set(res[0][1]) == set(res[1][1])
+        for k in res[0][1]:
+            if "explicit_relation.bias" in k:
+                # the table gradient is a sum over edges in a different association order (per-label select vs fma)
+                assert rel_err(res[1][1][k], res[0][1][k]) < 1e-5, k
+            else:
+                # split-K partial sums land through fp32 atomics (order varies run to run); on the 16-bit path a last-bit
+                # difference of a wgrad feeds bf16-rounded gradients downstream
+                assert rel_err(res[1][1][k], res[0][1][k]) < (1e-5 if precision == "fp32" else 5e-3), k
