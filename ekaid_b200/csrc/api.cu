@@ -47,6 +47,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, int fmt, cudaStream_t stream);
 void ek_gemm_debug(int flags, unsigned long long* ts);
 int ek_cast_f32_bf16_launch(const float*, long long, bf16*, long long, long long, int, int, cudaStream_t);
+int ek_split3_bf16_launch(const float*, long long, bf16*, long long, long long, int, int, int, cudaStream_t);
 int ek_cast_bf16_f32_launch(const bf16*, long long, float*, long long, long long, int, float, cudaStream_t);
 int ek_copy_f32_launch(const float*, long long, float*, long long, long long, int, cudaStream_t);
 int ek_colsum_launch(int, const void*, long long, long long, int, const float*, float*, float*, cudaStream_t);
@@ -214,6 +215,10 @@ int ekaid_gemm_tc(int transA, int transB, int M, int N, int K, const void* A, in
 int ekaid_gemm_debug(int flags, void* ts) {
   ek_gemm_debug(flags, (unsigned long long*)ts);
   return EK_OK;
+}
+int ekaid_split3_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, int pattern,
+                      int along_rows, void* stream) {
+  return ek_split3_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, pattern, along_rows, ST);
 }
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream) {
   return ek_cast_f32_bf16_launch(src, lds, (bf16*)dst, ldd, rows, cols, 0, ST);

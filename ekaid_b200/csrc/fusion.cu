@@ -20,6 +20,40 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
     *(uint2*)(dst + r * ldd + c) = pk;
   }
 }
+// fp32 operand -> three bf16 planes for the split-precision tensor-core product of the fp32 parity path:
+//   x = hi + lo + eps,  hi = bf16(x), lo = bf16(x - hi), |eps| <= 2^-17 |x|
+//   A B^T ~= Ah Bh^T + Al Bh^T + Ah Bl^T      (the dropped Al Bl^T term is <= 2^-16 of the product)
+// which is ONE bf16 GEMM over a contraction axis three times as long: A' = [Al | Ah | Ah], B' = [Bh | Bl | Bh].
+// The two small products come FIRST: the tensor core's accumulator adds with truncation, an error proportional to the
+// running sum, so the correction terms are accumulated while the sum is still 2^-9 of its final size.
+// pattern 0 = (lo, hi, hi) for the A operand, 1 = (hi, lo, hi) for B.  along_rows = 0: the contraction axis is the
+// column axis of src [rows, cols] -> dst [rows, 3 cols]; 1: it is the row axis -> dst [3 rows, cols].
+__global__ void split3_bf16_kernel(const float* __restrict__ src, long long lds, bf16* __restrict__ dst, long long ldd,
+                                   long long rows, int cols, int pattern, int along_rows) {
+  ek_pdl_prologue();
+  const long long total = rows * (cols / 4);
+  const long long plane = along_rows ? rows * ldd : (long long)cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / (cols / 4);
+    const int c = (int)(e % (cols / 4)) * 4;
+    const float4 v = *(const float4*)(src + r * lds + c);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __bfloat162float(__float2bfloat16_rn(x[i]));
+      l[i] = x[i] - h[i];                       // exact in fp32
+    }
+    uint2 ph, pl;
+    ph.x = pack16x2(h[0], h[1], 0); ph.y = pack16x2(h[2], h[3], 0);
+    pl.x = pack16x2(l[0], l[1], 0); pl.y = pack16x2(l[2], l[3], 0);
+    bf16* d = dst + r * ldd + c;
+    *(uint2*)d = pattern ? ph : pl;
+    *(uint2*)(d + plane) = pattern ? pl : ph;
+    *(uint2*)(d + 2 * plane) = ph;
+  }
+}
 // Up to CM_MAX strided 2-D blocks in one launch (blockIdx.y = block): fp32 -> bf16 casts (mode 0), fp32 -> fp32 copies
 // (mode 1), raw 16-byte copies of `cols` BYTES per row (mode 2: the captured step's input staging), fp32 -> fp16 casts
 // (mode 3, saturating) or fp16 -> bf16 conversions (mode 4: the backward's copy of a forward activation).
@@ -958,6 +992,17 @@ inline int grid_for(long long total, int block = 256) {
 }
 
 }  // namespace
+
+int ek_split3_bf16_launch(const float* src, long long lds, bf16* dst, long long ldd, long long rows, int cols,
+                          int pattern, int along_rows, cudaStream_t st) {
+  EK_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 7) == 0,
+             EK_ERR_ALIGN, "split3_bf16: cols/pitch must be multiples of 4 and pointers aligned");
+  if (rows * cols == 0) return EK_OK;
+  ek_launch(split3_bf16_kernel, grid_for(rows * cols / 4), 256, 0, st, src, lds, dst, ldd, rows, cols, pattern,
+            along_rows);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
 
 int ek_cast_f32_bf16_launch(const float* src, long long lds, bf16* dst, long long ldd, long long rows, int cols,
                             int fmt, cudaStream_t st) {

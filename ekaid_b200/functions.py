@@ -205,8 +205,41 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
              info=info)
     else:
         assert A.dtype == torch.float32 and B.dtype == torch.float32 and Cb is None and Cb2 is None
+        if _split3_ok(A, B, M, N, K, transA, transB):
+            # fp32 parity path on the tensor cores: each operand as bf16 (hi, lo) planes, three products accumulated in
+            # the same fp32 TMEM accumulator = ONE tcgen05 GEMM over a 3x longer contraction axis (split3_bf16_kernel)
+            A3 = _split3(A, K if transA else M, M if transA else K, 0, transA)
+            B3 = _split3(B, K if transB else N, N if transB else K, 1, transB)
+            info3 = dict(info, split3=True)
+            # no automatic split-K here: its partial sums meet in fp32 atomics whose order varies from run to run, and the
+            # fp32 path is the reproducible one (same bits every run, like the SIMT kernel it replaces)
+            call("gemm_tc", transA, transB, M, N, 3 * K, A3.data_ptr(), A3.stride(0), 0, B3.data_ptr(), B3.stride(0), 0,
+                 ctypes.addressof(ep), force_bn, splits if splits > 0 else 1, info=info3)
+            return
         call("gemm_f32", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
              ctypes.addressof(ep), info=info)
+
+
+# fp32 GEMMs: "split" (default) = 3 x bf16 split-precision products on tcgen05 for every product big enough to fill the
+# machine, "simt" = the register-tiled fp32 FMA kernel everywhere (the test oracle of the split path)
+FP32_GEMM = os.environ.get("EKAID_B200_FP32_GEMM", "split")
+SPLIT3_MIN_MACS = 1 << 27
+
+
+def _split3_ok(A, B, M, N, K, transA, transB) -> bool:
+    if FP32_GEMM != "split" or M * N * K < SPLIT3_MIN_MACS:
+        return False
+    # TMA: 16-byte row pitches and base addresses of the bf16 planes; float4 reads of the fp32 source
+    a_cols, b_cols = (M if transA else K), (N if transB else K)
+    return (a_cols % 8 == 0 and b_cols % 8 == 0 and A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0
+            and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0)
+
+
+def _split3(X, rows, cols, pattern, along_rows):
+    """fp32 [rows, cols] view -> bf16 planes: [rows, 3*cols] (contraction axis = columns) or [3*rows, cols] (= rows)."""
+    out = torch.empty((3 * rows, cols) if along_rows else (rows, 3 * cols), dtype=torch.bfloat16, device=X.device)
+    call("split3_bf16", X.data_ptr(), X.stride(0), out.data_ptr(), out.stride(0), rows, cols, pattern, 1 if along_rows else 0)
+    return out
 
 
 def gemm_T(pc: PC, A, B, M, N, K, transA=0, transB=0, *, want_f32=False, **kw):

@@ -115,6 +115,12 @@ int ekaid_gemm_debug(int flags, void* ts);
 
 /* ---- casts / reductions / glue -------------------------------------------------------------------------- */
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
+/* fp32 operand -> three bf16 planes (hi, lo) for the split-precision tensor-core product of the fp32 parity path:
+ * A B^T ~= Al Bh^T + Ah Bl^T + Ah Bh^T = one bf16 GEMM over a 3x longer contraction axis (every addmm/mm of the reference
+ * in fp32, e.g. models/fc.py:25-32, on tcgen05 instead of SIMT FMA).  pattern 0 = planes (lo, hi, hi) [A operand],
+ * 1 = (hi, lo, hi) [B operand]; along_rows 0: dst [rows, 3*cols], 1: dst [3*rows, cols]. */
+int ekaid_split3_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, int pattern,
+                      int along_rows, void* stream);
 int ekaid_cast_bf16_f32(const void* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int cols, void* stream);
 /* dst = scale * float(src): the receiving side of the bf16 gradient exchange (scale = 1 / world size after a SUM
  * all-reduce, which -- unlike AVG -- NCCL can run inside the NVSwitch) */

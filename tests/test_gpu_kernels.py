@@ -80,7 +80,11 @@ def test_gemm_epilogue(dtype):
     Cb = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if dtype == torch.bfloat16 else None
     gemm(A, W[:, :K], M, N, K, bias=bias, addend=add, rowb=rowb, rowb_div=Nn, rowb_mod=Bsz, rowflag=flags,
          rowb_alt=alt, act=ACT_TANH, C=C, Cb=Cb)
-    assert float((C - torch.tanh(ref)).abs().max()) < 2e-5
+    # fp32 operands take the split-precision tensor-core product: operand planes carry 2^-17 relative, the pre-activation
+    # spans +-25, so near tanh's linear range that is ~1e-4 absolute (4e-6 of the pre-activation scale)
+    assert float((C - torch.tanh(ref)).abs().max()) < (2e-5 if dtype == torch.bfloat16 else 2e-4)
+    assert float((torch.atanh(C.double().clamp(-0.999, 0.999)) - torch.atanh(torch.tanh(ref.double()).clamp(-0.999, 0.999))).abs().max()
+                 / ref.abs().max()) < 2e-5
     if Cb is not None:
         assert float((Cb.float() - torch.tanh(ref)).abs().max()) < 1e-2
     # in-place accumulate (addend aliases C), narrow N with scalar tail path
@@ -257,3 +261,37 @@ def test_small_linear_weighted_sums_wn_many():
         assert float((o - o2).abs().max()) == 0.0
         assert float((v.grad - v2.grad).abs().max()) <= 1e-6 * float(v2.grad.abs().max()) + 1e-9
         assert abs(float(g.grad) - float(g2.grad)) <= 1e-5 * abs(float(g2.grad)) + 1e-7
+
+
+@pytest.mark.parametrize("transA,transB,M,N,K", [(0, 0, 6656, 1024, 1024), (0, 1, 6656, 1024, 4096), (1, 1, 1024, 2048, 6656),
+                                                 (0, 0, 1280, 3072, 600), (1, 0, 520, 1024, 1032)])
+def test_gemm_fp32_split3_on_tensor_cores(transA, transB, M, N, K, monkeypatch):
+    """fp32 operands -> three bf16-plane products in one tcgen05 GEMM (split3_bf16 + K' = 3K): close to the SIMT fp32
+    kernel (its test oracle) and to the fp64 product, with the fused epilogue (bias + addend) unchanged."""
+    from ekaid_b200 import functions, lib
+    from ekaid_b200.functions import gemm
+    dev = _dev()
+    A = _mk((K, M) if transA else (M, K), dev, 11, torch.float32)
+    B = _mk((K, N) if transB else (N, K), dev, 12, torch.float32)
+    bias = _mk((N,), dev, 13, torch.float32)
+    add = _mk((M, N), dev, 14, torch.float32)
+    ref = (A.double().t() if transA else A.double()) @ (B.double() if transB else B.double().t()) + bias.double() + add.double()
+    out = {}
+    for mode in ("split", "simt"):
+        monkeypatch.setattr(functions, "FP32_GEMM", mode)
+        C = torch.full((M, N), float("nan"), device=dev)
+        before = lib.LAUNCHES
+        gemm(A, B, M, N, K, transA, transB, bias=bias, addend=add, C=C)
+        assert lib.LAUNCHES - before == (3 if mode == "split" else 1)      # two operand splits + one tcgen05 GEMM
+        out[mode] = C
+    e_split = float((out["split"].double() - ref).abs().max() / ref.abs().max())
+    e_simt = float((out["simt"].double() - ref).abs().max() / ref.abs().max())
+    print("split3 err %.2e, simt err %.2e" % (e_split, e_simt))
+    # (the tensor core accumulates with truncation: the error grows with the contraction length, 6656 / 4096 here)
+    assert e_split < 2e-5 and e_simt < 1e-5
+    # the planes reproduce the operand to 2^-16: lo + hi of a value, and the two plane orders (A: lo, hi, hi; B: hi, lo, hi)
+    X = _mk((64, 256), dev, 15, torch.float32)
+    P = functions._split3(X, 64, 256, 0, 0).float()
+    assert torch.equal(P[:, 256:512], P[:, 512:]) and float((P[:, :256] + P[:, 256:512] - X).abs().max() / X.abs().max()) < 2 ** -16
+    Q = functions._split3(X, 64, 256, 1, 1).float()
+    assert torch.equal(Q[:64], Q[128:]) and torch.equal(Q[:64], P[:, 256:512]) and torch.equal(Q[64:128], P[:, :256])

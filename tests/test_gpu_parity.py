@@ -21,6 +21,11 @@ TOL = {"fp32": 1e-4, "bf16": 2e-2}
 GTOL = {"fp32": 5e-4, "bf16": 5e-2}
 
 
+# analytically zero: a constant added to every logit of the batch-axis softmax (Q4) changes nothing; what either side
+# computes for it is cancellation noise
+ZERO_GRAD = ("q_att.W2_self_att_q.main.0.bias",)
+
+
 def grad_err(g, ref, precision):
     """fp32 path: max-abs error / max-abs.  16-bit path: relative L2 error (activation gradients are stored in bf16,
     so single entries of cancelling sums carry ~2^-9 of the TERM size; the L2 norm is the meaningful scale)."""
@@ -105,9 +110,14 @@ def test_forward_matches_golden_and_oracle(name, precision):
 @pytest.mark.parametrize("name", ["c1_b3_n52_all_grads", "c7_b2_n52_zero_bias", "c4_b2_n60_k52_all",
                                   "c2_b2_n52_ips"])
 def test_gradients_match_oracle(name, precision):
+    z, meta = load_case(name)
+    check_gradients(meta, precision, name)
+
+
+def check_gradients(meta, precision, name=""):
+    """Forward + gradient of every live parameter against the oracle's autograd on the inputs / weights `meta` seeds."""
     from ekaid_b200 import functions
     dev = _dev()
-    z, meta = load_case(name)
     sd, inp, _ = case_inputs(meta)
     m = build_model(meta, sd, precision, dev)
     functions.DEBUG_SINK = []
@@ -133,7 +143,7 @@ def test_gradients_match_oracle(name, precision):
     table = []
     for k, p in m.named_parameters():
         g_ref = sdg[k].grad
-        if g_ref is None or float(g_ref.abs().max()) < 1e-4:
+        if g_ref is None or float(g_ref.abs().max()) < 1e-4 or k in ZERO_GRAD:
             # dead parameters (Q2, Q3, Q11) and analytically-zero gradients (softmax shift invariance)
             if p.grad is not None:
                 assert float(p.grad.abs().max()) < (1e-3 if precision == "fp32" else 0.5), (k, float(p.grad.abs().max()))

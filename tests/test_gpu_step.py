@@ -233,10 +233,8 @@ def test_int8_label_matrices_equal_the_onehot_path_bit_for_bit(case):
             assert torch.equal(a, b)
         assert set(res[0][1]) == set(res[1][1])
         for k in res[0][1]:
-            if "explicit_relation.bias" in k:
-                # the table gradient is a sum over edges in a different association order (per-label select vs fma)
-                assert rel_err(res[1][1][k], res[0][1][k]) < 1e-5, k
-            else:
-                # split-K partial sums land through fp32 atomics (order varies run to run); on the 16-bit path a last-bit
-                # difference of a wgrad feeds bf16-rounded gradients downstream
-                assert rel_err(res[1][1][k], res[0][1][k]) < (1e-5 if precision == "fp32" else 5e-3), k
+            # fp32 path: same kernels in the same order except the table gradient (per-label select vs fma with a one-hot).
+            # 16-bit path: split-K partial sums land through fp32 atomics (order varies run to run) and a last-bit difference
+            # of a wgrad feeds bf16-rounded gradients downstream; scalar gains are cancelling projections of those
+            tol = 1e-5 if precision == "fp32" else (2e-2 if k.endswith("weight_g") else 5e-3)
+            assert rel_err(res[1][1][k], res[0][1][k]) < tol, (precision, k)
