@@ -164,6 +164,37 @@ static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
 }
 
 #define ST ((cudaStream_t)stream)
+// speaker.cu (answer decoder)
+int ek_dec_embed_launch(const long long*, long long, long long, int, int, int, const float*, int, int, void*, long long, int,
+                        EkDrop, int*, cudaStream_t);
+int ek_dec_lstm_fwd_launch(const float*, long long, const float*, long long, const float*, long long, const float*,
+                           const long long*, const float*, const float*, const float*, int, int, float*, float*, float*, void*,
+                           long long, void*, long long, int, EkDrop, unsigned long long, cudaStream_t);
+int ek_dec_lstm_bwd_launch(const float*, long long, EkDrop, unsigned long long, const float*, long long, const float*,
+                           long long, const float*, const float*, const float*, const float*, int, int, void*, long long, int,
+                           float*, float*, cudaStream_t);
+int ek_dec_att_fwd_launch(const float*, const float*, long long, const float* const*, const float*, const float*, const float*,
+                          int, int, int, int, EkDrop, EkDrop, unsigned long long, float*, float*, float*, float*, float*, void*,
+                          long long, int, cudaStream_t);
+int ek_dec_att_bwd_launch(const float*, long long, const float*, const float* const*, const float*, const float*, const float*,
+                          const float*, const float*, const float*, int, int, int, int, EkDrop, EkDrop, unsigned long long,
+                          float*, float*, float*, float*, float*, float*, void*, long long, int, cudaStream_t);
+int ek_dec_gate_fwd_launch(const float*, const float*, long long, float*, void*, int, cudaStream_t);
+int ek_dec_gate_bwd_launch(const float*, const float*, const float*, long long, float*, void*, int, cudaStream_t);
+int ek_dec_drop_op_launch(const float*, long long, int, int, int, EkDrop, unsigned long long, void*, long long, int,
+                          cudaStream_t);
+int ek_dec_lsm_bwd_launch(const float*, const float*, int, int, int, int, void*, long long, int, cudaStream_t);
+int ek_dec_relu_drop_bwd_launch(const float*, long long, const void*, long long, int, int, int, float, void*, long long, int,
+                                float*, long long, cudaStream_t);
+int ek_dec_masked_sum_t_launch(const float*, long long, int, int, int, EkDrop, unsigned long long, float*, cudaStream_t);
+int ek_dec_token_launch(const float*, long long, int, int, int, int, long long*, float*, unsigned char*, int*, long long*,
+                        float*, cudaStream_t);
+int ek_dec_nll_launch(const float*, long long, int, int, int, const long long*, long long, const float*, long long, int, float*,
+                      int, float*, const float*, const float*, void*, long long, int, int*, cudaStream_t);
+int ek_dec_nll_reduce_launch(const float*, int, const float*, long long, int, int, float*, cudaStream_t);
+int ek_dec_outer_small_launch(const float*, long long, int, const float*, long long, int, int, float*, long long, int,
+                              cudaStream_t);
+
 static EkDrop mk_drop(const uint64_t* seed, uint32_t site, float p) {
   EkDrop d;
   d.seed = (p > 0.f) ? (const unsigned long long*)seed : nullptr;
@@ -465,3 +496,87 @@ int ekaid_onehot_adj_i8(const int8_t* labels, int B, int S, int N, int L, float*
   EK_REQUIRE(N <= S && L >= 1, EK_ERR_SHAPE, "onehot_adj_i8: N=%d > S=%d", N, S);
   return ek_onehot_adj_i8_launch(labels, B, S, N, L, out, ST);
 }
+
+extern "C" {
+/* ---- answer decoder (speaker.cu) ---- */
+int ekaid_dec_embed(const int64_t* seq, int64_t sb, int64_t st, int t0, int B, int rows, const float* emb, int V, int We,
+                    void* out, int64_t ldo, int opf, const uint64_t* seed, uint32_t site, float p, int32_t* err,
+                    void* stream) {
+  return ek_dec_embed_launch((const long long*)seq, sb, st, t0, B, rows, emb, V, We, out, ldo, opf, mk_drop(seed, site, p),
+                             err, ST);
+}
+int ekaid_dec_lstm_fwd(const float* s0, int64_t l0, const float* s1, int64_t l1, const float* s2, int64_t l2,
+                       const float* tbl, const int64_t* tok, const float* b1, const float* b2, const float* c_prev, int B,
+                       int R, float* gates, float* c_out, float* h_out, void* h_op, int64_t ldh, void* out_op, int64_t ldo,
+                       int opf, const uint64_t* seed, uint32_t site, float p, int64_t drop_base, void* stream) {
+  return ek_dec_lstm_fwd_launch(s0, l0, s1, l1, s2, l2, tbl, (const long long*)tok, b1, b2, c_prev, B, R, gates, c_out, h_out,
+                                h_op, ldh, out_op, ldo, opf, mk_drop(seed, site, p), (unsigned long long)drop_base, ST);
+}
+int ekaid_dec_lstm_bwd(const float* dh_a, int64_t lda, const uint64_t* seed, uint32_t site, float p, int64_t drop_base,
+                       const float* dh_b, int64_t ldb, const float* dh_c, int64_t ldc, const float* dc_in,
+                       const float* gates, const float* c, const float* c_prev, int B, int R, void* dpre_op, int64_t ldp,
+                       int opf, float* dpre_f, float* dc_out, void* stream) {
+  return ek_dec_lstm_bwd_launch(dh_a, lda, mk_drop(seed, site, p), (unsigned long long)drop_base, dh_b, ldb, dh_c, ldc, dc_in,
+                                gates, c, c_prev, B, R, dpre_op, ldp, opf, dpre_f, dc_out, ST);
+}
+int ekaid_dec_att_fwd(const float* h_mod, const float* p1pre, int64_t ldp1, const float* const* w7, const float* bef,
+                      const float* diff, const float* aft, int B, int R, int P, int D, const uint64_t* seed, uint32_t site1,
+                      float p1, uint32_t site5, float p5, int64_t row_base, float* mw, float* pw, float* dposd, float* vpos,
+                      float* att, void* gi2, int64_t ldg, int opf, void* stream) {
+  EK_REQUIRE(R >= 32 && P >= 32 && P <= 4096, EK_ERR_SHAPE, "dec_att_fwd: R=%d P=%d", R, P);
+  return ek_dec_att_fwd_launch(h_mod, p1pre, ldp1, w7, bef, diff, aft, B, R, P, D, mk_drop(seed, site1, p1),
+                               mk_drop(seed, site5, p5), (unsigned long long)row_base, mw, pw, dposd, vpos, att, gi2, ldg,
+                               opf, ST);
+}
+int ekaid_dec_att_bwd(const float* dgi2, int64_t ldg, const float* datt_g, const float* const* w7, const float* bef,
+                      const float* diff, const float* aft, const float* mw, const float* pw, const float* vpos, int B, int R,
+                      int P, int D, const uint64_t* seed, uint32_t site1, float p1, uint32_t site5, float p5,
+                      int64_t row_base, float* dbef, float* ddiff, float* daft, float* dfc, float* ddpos, float* dhmod_fc,
+                      void* dvp_op, int64_t ldv, int opf, void* stream) {
+  return ek_dec_att_bwd_launch(dgi2, ldg, datt_g, w7, bef, diff, aft, mw, pw, vpos, B, R, P, D, mk_drop(seed, site1, p1),
+                               mk_drop(seed, site5, p5), (unsigned long long)row_base, dbef, ddiff, daft, dfc, ddpos, dhmod_fc,
+                               dvp_op, ldv, opf, ST);
+}
+int ekaid_dec_gate_fwd(const float* pre, const float* att, int64_t n, float* gate, void* gated, int opf, void* stream) {
+  return ek_dec_gate_fwd_launch(pre, att, n, gate, gated, opf, ST);
+}
+int ekaid_dec_gate_bwd(const float* dgated, const float* gate, const float* att, int64_t n, float* datt_g, void* dpre,
+                       int opf, void* stream) {
+  return ek_dec_gate_bwd_launch(dgated, gate, att, n, datt_g, dpre, opf, ST);
+}
+int ekaid_dec_drop_op(const float* x, int64_t ldx, int rows, int n, int xmod, const uint64_t* seed, uint32_t site, float p,
+                      int64_t base, void* out, int64_t ldo, int opf, void* stream) {
+  return ek_dec_drop_op_launch(x, ldx, rows, n, xmod, mk_drop(seed, site, p), (unsigned long long)base, out, ldo, opf, ST);
+}
+int ekaid_dec_lsm_bwd(const float* dlogp, const float* logp, int rows, int B, int V, int Tout, void* dlogits, int64_t ldd,
+                      int opf, void* stream) {
+  return ek_dec_lsm_bwd_launch(dlogp, logp, rows, B, V, Tout, dlogits, ldd, opf, ST);
+}
+int ekaid_dec_relu_drop_bwd(const float* dy, int64_t ldd, const void* y, int64_t ldy, int yf, int rows, int n, float keep,
+                            void* out, int64_t ldo, int opf, float* out_f, int64_t ldf, void* stream) {
+  return ek_dec_relu_drop_bwd_launch(dy, ldd, y, ldy, yf, rows, n, keep, out, ldo, opf, out_f, ldf, ST);
+}
+int ekaid_dec_masked_sum_t(const float* x, int64_t ldx, int T, int B, int n, const uint64_t* seed, uint32_t site, float p,
+                           int64_t base, float* acc, void* stream) {
+  return ek_dec_masked_sum_t_launch(x, ldx, T, B, n, mk_drop(seed, site, p), (unsigned long long)base, acc, ST);
+}
+int ekaid_dec_token(const float* logits, int64_t ldl, int B, int V, int t, int T, int64_t* seq, float* seq_logp,
+                    uint8_t* unfinished, int32_t* state, int64_t* next_tok, float* logp_out, void* stream) {
+  return ek_dec_token_launch(logits, ldl, B, V, t, T, (long long*)seq, seq_logp, unfinished, state, (long long*)next_tok,
+                             logp_out, ST);
+}
+int ekaid_dec_nll(const float* logits, int64_t ldl, int rows, int B, int V, const int64_t* labels, int64_t lsb,
+                  const float* masks, int64_t msb, int mode, float* out, int Tout, float* row_loss, const float* gscale,
+                  const float* inv_msum, void* dlogits, int64_t ldd, int opf, int32_t* err, void* stream) {
+  return ek_dec_nll_launch(logits, ldl, rows, B, V, (const long long*)labels, lsb, masks, msb, mode, out, Tout, row_loss,
+                           gscale, inv_msum, dlogits, ldd, opf, err, ST);
+}
+int ekaid_dec_nll_reduce(const float* row_loss, int rows, const float* masks, int64_t msb, int B, int T, float* res,
+                         void* stream) {
+  return ek_dec_nll_reduce_launch(row_loss, rows, masks, msb, B, T, res, ST);
+}
+int ekaid_dec_outer_small(const float* a, int64_t lda, int m, const float* b, int64_t ldb, int n, int rows, float* out,
+                          int64_t ldo, int transpose_out, void* stream) {
+  return ek_dec_outer_small_launch(a, lda, m, b, ldb, n, rows, out, ldo, transpose_out, ST);
+}
+}  // extern "C"

@@ -340,6 +340,73 @@ int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream);
 int ekaid_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                     float wd, const float* pow_state, int max_ctas, void* stream);
 
+/* ---- answer decoder: DynamicSpeaker / DynamicCore (models/dynamic_speaker_change_pos.py:94-131, 182-240, 287-357) and
+ * LanguageModelCriterion (utils/utils.py:204-216).  One decode step = dense products through ekaid_gemm_tc / ekaid_gemm_f32
+ * plus these kernels.  opf: operand type of the GEMM-operand outputs (0 fp32, 1 bf16).  Dropout sites take
+ * (seed, site, p) like the rest of the library; *_base = index of the first element at that site (steps are laid out one
+ * after the other: (t * B + b) * width + column). ----------------------------------------------------------------- */
+/* out[r, j] = Dropout(relu(emb[seq[b*sb + (t0+t)*st], j])), r = t*B + b, zero for We <= j < ldo (speaker.embed, :157-160).
+ * err (optional) is set to 1 when a token id is outside [0, V). */
+int ekaid_dec_embed(const int64_t* seq, int64_t sb, int64_t st, int t0, int B, int rows, const float* emb, int V, int We,
+                    void* out, int64_t ldo, int opf, const uint64_t* seed, uint32_t site, float p, int32_t* err,
+                    void* stream);
+/* nn.LSTMCell point-wise part (:103, :123): pre = s0 + s1 + s2 (partial products, each optional) + tbl[tok] (optional table
+ * row per token) + b1 + b2; gates [B,4R] (activated i,f,g,o), c_out, h_out fp32; h_op / out_op (optional) = h and
+ * F.dropout(h) (:125) as operands. */
+int ekaid_dec_lstm_fwd(const float* s0, int64_t l0, const float* s1, int64_t l1, const float* s2, int64_t l2,
+                       const float* tbl, const int64_t* tok, const float* b1, const float* b2, const float* c_prev, int B,
+                       int R, float* gates, float* c_out, float* h_out, void* h_op, int64_t ldh, void* out_op, int64_t ldo,
+                       int opf, const uint64_t* seed, uint32_t site, float p, int64_t drop_base, void* stream);
+/* dh = dh_a * mask + dh_b + dh_c (each optional); -> gate pre-activation gradients (operand + optional fp32) and dc_prev */
+int ekaid_dec_lstm_bwd(const float* dh_a, int64_t lda, const uint64_t* seed, uint32_t site, float p, int64_t drop_base,
+                       const float* dh_b, int64_t ldb, const float* dh_c, int64_t ldc, const float* dc_in,
+                       const float* gates, const float* c, const float* c_prev, int B, int R, void* dpre_op, int64_t ldp,
+                       int opf, float* dpre_f, float* dc_out, void* stream);
+/* module attention + position branch of DynamicCore.forward (:104-119), one CTA per sample.
+ * w7 = {weight_fc.W [3,R], weight_fc.b, pos1.b [P], weight_pos.W [16,P], weight_pos.b, pos2.W [R,16], pos2.b} (host array of
+ * device pointers); p1pre = prev_h pos1.W^T.  Outputs: mw [B,4], pw [B,16], dposd [B,16] (= output_pos), vpos [B,P],
+ * att [B,D], gi2 [B, R+D] = [ppos | att_feat] (operand). */
+int ekaid_dec_att_fwd(const float* h_mod, const float* p1pre, int64_t ldp1, const float* const* w7, const float* bef,
+                      const float* diff, const float* aft, int B, int R, int P, int D, const uint64_t* seed, uint32_t site1,
+                      float p1, uint32_t site5, float p5, int64_t row_base, float* mw, float* pw, float* dposd, float* vpos,
+                      float* att, void* gi2, int64_t ldg, int opf, void* stream);
+/* backward of the above: dgi2 [B,R+D] fp32, datt_g [B,D]; dbef/ddiff/daft are accumulated (+=) */
+int ekaid_dec_att_bwd(const float* dgi2, int64_t ldg, const float* datt_g, const float* const* w7, const float* bef,
+                      const float* diff, const float* aft, const float* mw, const float* pw, const float* vpos, int B, int R,
+                      int P, int D, const uint64_t* seed, uint32_t site1, float p1, uint32_t site5, float p5,
+                      int64_t row_base, float* dbef, float* ddiff, float* daft, float* dfc, float* ddpos, float* dhmod_fc,
+                      void* dvp_op, int64_t ldv, int opf, void* stream);
+/* gate = sigmoid(pre); gated = gate * att (:121-123) and its backward */
+int ekaid_dec_gate_fwd(const float* pre, const float* att, int64_t n, float* gate, void* gated, int opf, void* stream);
+int ekaid_dec_gate_bwd(const float* dgated, const float* gate, const float* att, int64_t n, float* datt_g, void* dpre,
+                       int opf, void* stream);
+/* Dropout on an activation that feeds a GEMM; backward through Dropout(ReLU(.)) given the stored output y */
+int ekaid_dec_drop_op(const float* x, int64_t ldx, int rows, int n, int xmod, const uint64_t* seed, uint32_t site, float p,
+                      int64_t base, void* out, int64_t ldo, int opf, void* stream);
+/* backward of F.log_softmax (:238) for callers that differentiate _forward's log-probabilities themselves */
+int ekaid_dec_lsm_bwd(const float* dlogp, const float* logp, int rows, int B, int V, int Tout, void* dlogits, int64_t ldd,
+                      int opf, void* stream);
+int ekaid_dec_relu_drop_bwd(const float* dy, int64_t ldd, const void* y, int64_t ldy, int yf, int rows, int n, float keep,
+                            void* out, int64_t ldo, int opf, float* out_f, int64_t ldf, void* stream);
+/* acc[b, j] = sum_t x[(t*B+b), j] * mask(t, b, j): gradient of the step-invariant core.embed output */
+int ekaid_dec_masked_sum_t(const float* x, int64_t ldx, int T, int B, int n, const uint64_t* seed, uint32_t site, float p,
+                           int64_t base, float* acc, void* stream);
+/* one greedy sampling step on the device (:312-355): log-softmax, arg-max, unfinished bookkeeping, next token; state[0] = 1
+ * while the reference's loop would still run (replaces the host synchronisation of :354) */
+int ekaid_dec_token(const float* logits, int64_t ldl, int B, int V, int t, int T, int64_t* seq, float* seq_logp,
+                    uint8_t* unfinished, int32_t* state, int64_t* next_tok, float* logp_out, void* stream);
+/* log-softmax + masked NLL + gradient over the logits of all steps (utils/utils.py:204-216; train_mimic.py:242):
+ * mode bit 0: out[b,t,:] = logp; bit 1: row_loss; bit 2: dlogits (operand, pitch ldd) */
+int ekaid_dec_nll(const float* logits, int64_t ldl, int rows, int B, int V, const int64_t* labels, int64_t lsb,
+                  const float* masks, int64_t msb, int mode, float* out, int Tout, float* row_loss, const float* gscale,
+                  const float* inv_msum, void* dlogits, int64_t ldd, int opf, int32_t* err, void* stream);
+/* res[0] = sum(row_loss) / sum(mask), res[1] = 1 / sum(mask), mask = masks[:, 1 .. T] */
+int ekaid_dec_nll_reduce(const float* row_loss, int rows, const float* masks, int64_t msb, int B, int T, float* res,
+                         void* stream);
+/* out[i, j] = sum_r a[r, i] b[r, j], i < m <= 16 (weight gradients of weight_fc, weight_pos, pos2) */
+int ekaid_dec_outer_small(const float* a, int64_t lda, int m, const float* b, int64_t ldb, int n, int rows, float* out,
+                          int64_t ldo, int transpose_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,197 @@
+"""The answer decoder (ekaid_b200.speaker.DynamicSpeaker) on a B200 against the oracle's
+restatement of models/dynamic_speaker_change_pos.py (which tests/test_oracle_golden.py pins to the reference's own greedy
+tokens): teacher-forced log-probabilities, the masked NLL of utils/utils.py:204-216 and the gradients of every decoder
+parameter and of the three input vectors, greedy decoding with the stop condition kept on the device."""
+import contextlib
+import io
+
+import pytest
+import torch
+
+from helpers import rel_err, speaker_spec
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+GTOL = {"fp32": 5e-4, "bf16": 5e-2}
+
+
+def _dev():
+    from ekaid_b200 import lib
+    lib.require_device()
+    return torch.device("cuda:0")
+
+
+def _setup(B, seed, dev, precision, logit_scale=1.0, feat_scale=3.0):
+    from ekaid_b200.config import default_cfg
+    from ekaid_b200.speaker import DynamicSpeaker
+    from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
+    ssd = synthetic_state_dict(speaker_spec(), 4321)
+    if logit_scale != 1.0:
+        ssd["logit.weight"] = ssd["logit.weight"] * logit_scale     # trained-like margins between the top tokens
+    cfg = default_cfg("all")
+    with contextlib.redirect_stdout(io.StringIO()):
+        sp = DynamicSpeaker(cfg, vocab_size=148)
+    sp.load_state_dict(ssd)
+    sp.to(dev).eval().set_precision(precision)
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(B, 1024, generator=g) * feat_scale for _ in range(3)]      # bef, aft, diff
+    batch = synthetic_batch(B, 52, seed=seed)
+    labels, masks = batch[2].squeeze(1), batch[4].squeeze(1).float()
+    return sp, ssd, feats, labels, masks
+
+
+def test_state_dict_keys_match_the_reference_spec():
+    from ekaid_b200.config import default_cfg
+    from ekaid_b200.speaker import DynamicSpeaker
+    with contextlib.redirect_stdout(io.StringIO()):
+        sp = DynamicSpeaker(default_cfg("all"), vocab_size=148)
+    spec = speaker_spec()
+    assert {k: tuple(v.shape) for k, v in sp.state_dict().items()} == spec
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_teacher_forced_logprobs_loss_and_gradients_match_oracle(precision):
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B = 3
+    sp, ssd, feats, labels, masks = _setup(B, 77, dev, precision)
+    # oracle (CPU, autograd)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+    fr = [f.clone().requires_grad_(True) for f in feats]
+    ref = O.speaker_teacher_forced(sdg, fr[0], fr[1], fr[2], labels, 90, 512)
+    ref_loss = O.lm_criterion(ref, labels[:, 1:], masks[:, 1:])
+    ref_loss.backward()
+    # CUDA path: the reference's two-call form ...
+    fd = [f.clone().to(dev).requires_grad_(True) for f in feats]
+    out, out_pos = sp._forward(fd[0], fd[1], fd[2], labels.to(dev))
+    assert out.shape == (B, 90, 148) and out_pos.shape == (B, 90, 16)
+    e = rel_err(out, ref)
+    print(precision, "teacher-forced logp rel err %.2e (abs %.2e)" % (e, float((out.cpu() - ref).abs().max())))
+    assert e < TOL[precision]
+    T = sp._steps(labels)
+    assert float(out[:, T:].abs().max()) == 0.0 and float(ref[:, T:].abs().max()) == 0.0
+    assert sp.get_module_weights().shape == (B, T, 3)
+    from ekaid_b200.speaker import LanguageModelCriterion
+    loss2 = LanguageModelCriterion()(out, labels.to(dev)[:, 1:], masks.to(dev)[:, 1:])
+    loss2.backward()
+    g2 = {k: p.grad.clone() for k, p in sp.named_parameters()}
+    f2 = [f.grad.clone() for f in fd]
+    sp.zero_grad()
+    # ... and the fused masked NLL
+    fd = [f.clone().to(dev).requires_grad_(True) for f in feats]
+    loss = sp.masked_nll(fd[0], fd[1], fd[2], labels.to(dev), masks.to(dev))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref_loss)) < TOL[precision] * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    assert abs(float(loss2) - float(ref_loss)) < TOL[precision] * abs(float(ref_loss))
+    assert int(sp._tok_err.item()) == 0
+
+    def gerr(a, b):
+        a, b = a.detach().double().cpu(), b.detach().double().cpu()
+        if precision == "fp32":
+            return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        return float((a - b).norm() / (b.norm() + 1e-30))
+
+    table = []
+    for k, p in sp.named_parameters():
+        table.append((gerr(p.grad, sdg[k].grad), k))
+        table.append((gerr(g2[k], sdg[k].grad), k + " (two-call form)"))
+    for name, a, a2, r in zip(("d bef", "d aft", "d diff"), fd, f2, fr):
+        table.append((gerr(a.grad, r.grad), name))
+        table.append((gerr(a2, r.grad), name + " (two-call form)"))
+    table.sort(reverse=True)
+    print(precision, "worst decoder grads:", [("%.1e" % e_, k) for e_, k in table[:6]])
+    bad = [(k, e_) for e_, k in table if e_ > GTOL[precision]]
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_greedy_decode_matches_oracle_tokens(precision):
+    """_sample(sample_max=1) with trained-like logit margins: identical tokens at every step, log-probs of the chosen
+    tokens within tolerance, no host synchronisation per step (the stop flag is read every 16 steps)."""
+    from ekaid_b200.config import default_cfg
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B = 5
+    sp, ssd, feats, labels, masks = _setup(B, 91, dev, precision, logit_scale=30.0)
+    ref = O.speaker_greedy(ssd, feats[0], feats[1], feats[2], 90, 512)
+    seq, lp = sp._sample(feats[0].to(dev), feats[1].to(dev), feats[2].to(dev), labels.to(dev), default_cfg("all"), sample_max=1)
+    assert seq.shape == (B, 90) and seq.dtype == torch.int64
+    agree = float((seq.cpu() == ref).float().mean())
+    print(precision, "greedy token agreement %.4f; distinct tokens %d" % (agree, len(set(ref.flatten().tolist()))))
+    assert torch.equal(seq.cpu(), ref)
+    assert len(set(ref.flatten().tolist())) > 3
+    # single-step entry point against the oracle's step
+    state = sp.init_hidden(B)
+    it = torch.full((B,), 2, dtype=torch.long, device=dev)
+    lp1, st1, lpos = sp.get_logprobs_state(it, feats[0].to(dev), feats[1].to(dev), feats[2].to(dev), state)
+    rl, rs, rd = O.speaker_logprobs(ssd, it.cpu(), feats[0], feats[1], feats[2], (torch.zeros(2, B, 512), torch.zeros(2, B, 512)))
+    assert rel_err(lp1, rl) < TOL[precision]
+    assert rel_err(st1[0], rs[0]) < TOL[precision] and rel_err(st1[1], rs[1]) < TOL[precision]
+    assert rel_err(lpos, torch.log_softmax(rd, 1)) < TOL[precision]
+
+
+def test_stop_condition_stays_on_the_device():
+    """Every sequence emits token 0 at step 1: the reference breaks out of its loop there (:354); here the flag is set by
+    the token kernel, later steps write nothing, and the host looks at it only every `check_every` steps."""
+    from ekaid_b200 import lib
+    from ekaid_b200.config import default_cfg
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B = 4
+    sp, ssd, feats, labels, masks = _setup(B, 5, dev, "fp32")
+    ssd["logit.bias"][0] = 50.0
+    sp.load_state_dict(ssd)
+    ref = O.speaker_greedy(ssd, feats[0], feats[1], feats[2], 90, 512)
+    assert int((ref[:, 1:] != 0).sum()) == 0 and int((ref[:, 0] != 0).sum()) == B
+    fd = [f.to(dev) for f in feats]
+    before = lib.LAUNCHES
+    seq, lp = sp._sample(fd[0], fd[1], fd[2], labels.to(dev), default_cfg("all"), sample_max=1, check_every=4)
+    short = lib.LAUNCHES - before
+    assert torch.equal(seq.cpu(), ref)
+    assert float(lp[:, 2:].abs().max()) == 0.0 and float(lp[:, :2].abs().min()) >= 0.0
+    before = lib.LAUNCHES
+    seq2, _ = sp._sample(fd[0], fd[1], fd[2], labels.to(dev), default_cfg("all"), sample_max=1, check_every=0)
+    assert torch.equal(seq2, seq)
+    assert short < (lib.LAUNCHES - before) / 10          # 4 steps instead of 91
+
+
+def test_train_mode_draws_fresh_masks_and_stays_finite():
+    dev = _dev()
+    B = 4
+    sp, ssd, feats, labels, masks = _setup(B, 13, dev, "bf16")
+    sp.train()
+    fd = [f.to(dev).requires_grad_(True) for f in feats]
+    l1 = sp.masked_nll(fd[0], fd[1], fd[2], labels.to(dev), masks.to(dev))
+    l1.backward()
+    g1 = sp.core.gate2x.weight.grad.clone()
+    sp.zero_grad()
+    l2 = sp.masked_nll(fd[0], fd[1], fd[2], labels.to(dev), masks.to(dev))
+    l2.backward()
+    assert torch.isfinite(l1) and torch.isfinite(l2) and float(l1) != float(l2)
+    for k, p in sp.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    assert float((g1 - sp.core.gate2x.weight.grad).abs().max()) > 0
+    sp.eval()
+    l3 = sp.masked_nll(fd[0], fd[1], fd[2], labels.to(dev), masks.to(dev))
+    l4 = sp.masked_nll(fd[0], fd[1], fd[2], labels.to(dev), masks.to(dev))
+    # (eval mode: no masks; the 16-bit path's split-K partial sums meet in fp32 atomics, so not bit-for-bit)
+    assert abs(float(l3) - float(l4)) < 1e-4 * abs(float(l3))
+
+
+def test_fixed_step_count_equals_the_data_dependent_one():
+    """steps=... (what a captured CUDA graph needs) runs past the last non-empty label column: same loss, same gradients."""
+    dev = _dev()
+    B = 3
+    sp, ssd, feats, labels, masks = _setup(B, 21, dev, "fp32")
+    res = []
+    for steps in (None, 40):
+        fd = [f.to(dev).requires_grad_(True) for f in feats]
+        sp.zero_grad()
+        loss = sp.masked_nll(fd[0], fd[1], fd[2], labels.to(dev), masks.to(dev), steps=steps)
+        loss.backward()
+        res.append((float(loss), fd[0].grad.clone(), sp.core.lang_lstm.weight_hh.grad.clone()))
+    assert sp._steps(labels) < 40
+    assert abs(res[0][0] - res[1][0]) < 1e-6 * abs(res[0][0])
+    assert rel_err(res[1][1], res[0][1]) < 1e-5 and rel_err(res[1][2], res[0][2]) < 1e-5
