@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import lib
-from .functions import (ACT_RELU, PC, Drop, _f32c, cast_many, colsum, gemm, ptr, rng_advance)
+from .functions import (ACT_RELU, PC, Drop, _dst, _f32c, cast_many, colsum, gemm, ptr, rng_advance)
 from .lib import call
 
 # dropout sites of the decoder (functions.Drop site numbering: relation encoders 100-399, question path 10-11, fusion 20-21)
@@ -282,7 +282,10 @@ class SpeakerSeqFn(torch.autograd.Function):
             dout = _f32c(grads[0])
             call("dec_lsm_bwd", dout.data_ptr(), ctx.outputs.data_ptr(), TB, B, V, sp.seq_length, dLG.data_ptr(), Vp, opf)
         Xo = OUT if don else HL[B:]
-        dW_lo, db_lo = f32(V, R), f32(V)
+        # parameter gradients are written where the optimizer wants them (its flat slot on first use after a reset)
+        P = dict(zip(sp._param_names, ctx.params))
+        slot = lambda name, *shape: _dst(P[name].data_ptr(), tuple(shape), dev)     # noqa: E731
+        dW_lo, db_lo = slot("logit.weight", V, R), slot("logit.bias", V)
         gemm(dLG, Xo, V, R, TB, transA=1, transB=1, C=dW_lo)
         colsum(dLG, TB, V, out=db_lo)
         dOUT = f32(TB, R)
@@ -327,9 +330,9 @@ class SpeakerSeqFn(torch.autograd.Function):
         c = sp.core
         dWcat = f32(NH, R)
         gemm(dS1, HL[:TB], NH, R, TB, transA=1, transB=1, C=dWcat)
-        dW_hh_m = f32(4 * R, R)
+        dW_hh_m = slot("core.module_att_lstm.weight_hh", 4 * R, R)
         gemm(dS1[:, :4 * R], HM[:TB], 4 * R, R, TB, transA=1, transB=1, C=dW_hh_m)
-        dW_ih_m = f32(4 * R, E + R)
+        dW_ih_m = slot("core.module_att_lstm.weight_ih", 4 * R, E + R)
         dEMB = f32(TB, E)
         gemm(dS1[:, :4 * R], w.W_ih_me, TB, E, 4 * R, transB=1, C=dEMB)
         demb0 = f32(B, E)
@@ -342,53 +345,64 @@ class SpeakerSeqFn(torch.autograd.Function):
             gemm(_op(pc, dGsum), EMBD, 4 * R, E, B, transA=1, transB=1, C=dW_ih_m[:, :E], splits=1)
             demb0 = dEMB.view(T, B, E).sum(0)
         dW_ih_m[:, E:] = dWcat[:4 * R]
-        dW_p1 = dWcat[w.o_p1:w.o_g1].contiguous()
-        dW_g1 = f32(G, G)
+        dW_p1 = slot("core.pos1.0.weight", 512, R)
+        dW_p1.copy_(dWcat[w.o_p1:w.o_g1])
+        dW_g1 = slot("core.gate1x.0.weight", G, G)
         dW_g1[:, :R] = dWcat[w.o_g1:w.o_lh]
         gemm(dS1[:, w.o_g1:w.o_lh], GI2, G, R + D, TB, transA=1, transB=1, C=dW_g1[:, R:])
-        dW_g2 = f32(D, G)
+        dW_g2 = slot("core.gate2x.weight", D, G)
         gemm(DG2, G1, D, G, TB, transA=1, transB=1, C=dW_g2)
-        dW_ih_l = f32(4 * R, w.We + D)
+        dW_ih_l = slot("core.lang_lstm.weight_ih", 4 * R, w.We + D)
         gemm(dS1[:, w.o_lh:], GATED, 4 * R, D, TB, transA=1, transB=1, C=dW_ih_l[:, w.We:])
         dWx = f32(4 * R, Wex)
         gemm(dS1[:, w.o_lh:], XT, 4 * R, Wex, TB, transA=1, transB=1, C=dWx)
         dW_ih_l[:, :w.We] = dWx[:, :w.We]
-        dW_hh_l = dWcat[w.o_lh:].contiguous()
+        dW_hh_l = slot("core.lang_lstm.weight_hh", 4 * R, R)
+        dW_hh_l.copy_(dWcat[w.o_lh:])
         # biases: column sums of the pre-activation gradients (fp32 copies)
-        db_m, db_l, db_g1 = colsum(dGm_f, TB, 4 * R), colsum(dGl_f, TB, 4 * R), colsum(dG1_f, TB, G)
-        db_g2 = colsum(DG2, TB, D)
-        db_p1 = colsum(dS1[:, w.o_p1:w.o_g1], TB, 512)
+        db_m = colsum(dGm_f, TB, 4 * R, out=slot("core.module_att_lstm.bias_ih", 4 * R))
+        db_m2 = slot("core.module_att_lstm.bias_hh", 4 * R)
+        db_m2.copy_(db_m)
+        db_l = colsum(dGl_f, TB, 4 * R, out=slot("core.lang_lstm.bias_ih", 4 * R))
+        db_l2 = slot("core.lang_lstm.bias_hh", 4 * R)
+        db_l2.copy_(db_l)
+        db_g1 = colsum(dG1_f, TB, G, out=slot("core.gate1x.0.bias", G))
+        db_g2 = colsum(DG2, TB, D, out=slot("core.gate2x.bias", D))
+        db_p1 = colsum(dS1[:, w.o_p1:w.o_g1], TB, 512, out=slot("core.pos1.0.bias", 512))
         # word embedding: dXT = dgl W_ih[:, :We] -> ReLU / Dropout mask (XT > 0) -> scatter-add over the tokens
         dXT = f32(TB, Wex)
         gemm(dS1[:, w.o_lh:], w.W_ih_x, TB, Wex, 4 * R, transB=1, C=dXT)
         dXTm = f32(TB, Wex)
         call("dec_relu_drop_bwd", dXT.data_ptr(), Wex, XT.data_ptr(), Wex, opf, TB, Wex, keep, None, 0, 0, dXTm.data_ptr(), Wex)
         tok = seq[:, :T].t().reshape(-1)
-        demb_w = torch.zeros(V, w.We, dtype=torch.float32, device=dev).index_add_(0, tok, dXTm[:, :w.We])
+        demb_w = slot("embed.0.weight", V, w.We)
+        demb_w.zero_().index_add_(0, tok, dXTm[:, :w.We])
         # core.embed: ReLU mask, then its own weight / input gradients
         demb0p = f32(B, E)
         call("dec_relu_drop_bwd", demb0.data_ptr(), E, emb0.data_ptr(), E, 0, B, E, 1.0, None, 0, 0, demb0p.data_ptr(), E)
         dE_op = _op(pc, demb0p)
-        dW_e = f32(E, 3 * D)
+        dW_e = slot("core.embed.0.weight", E, 3 * D)
         gemm(dE_op, EI, E, 3 * D, B, transA=1, transB=1, C=dW_e, splits=1)
-        db_e = colsum(demb0p, B, E)
+        db_e = colsum(demb0p, B, E, out=slot("core.embed.0.bias", E))
         dEI = f32(B, 3 * D)
         gemm(dE_op, w.W_e, B, 3 * D, E, transB=1, C=dEI)
         dbef += dEI[:, :D]
         ddiff += dEI[:, D:2 * D]
         daft += dEI[:, 2 * D:]
         # the three tiny layers
-        dW_fc, dW_wp, dW_p2 = f32(3, R), f32(16, 512), f32(R, 16)
+        dW_fc, dW_wp = slot("core.weight_fc.0.weight", 3, R), slot("core.weight_pos.weight", 16, 512)
+        dW_p2 = slot("core.pos2.weight", R, 16)
         call("dec_outer_small", DFC.data_ptr(), 4, 3, HMf[B:].data_ptr(), R, R, TB, dW_fc.data_ptr(), R, 0)
         call("dec_outer_small", DDPOS.data_ptr(), 16, 16, VPOS.data_ptr(), 512, 512, TB, dW_wp.data_ptr(), 512, 0)
         call("dec_outer_small", PW.data_ptr(), 16, 16, DGI2.data_ptr(), R + D, R, TB, dW_p2.data_ptr(), 16, 1)
-        db_fc = colsum(DFC, TB, 4)[:3].contiguous()
-        db_wp = colsum(DDPOS, TB, 16)
-        db_p2 = colsum(DGI2, TB, R)
+        db_fc = slot("core.weight_fc.0.bias", 3)
+        db_fc.copy_(colsum(DFC, TB, 4)[:3])
+        db_wp = colsum(DDPOS, TB, 16, out=slot("core.weight_pos.bias", 16))
+        db_p2 = colsum(DGI2, TB, R, out=slot("core.pos2.bias", R))
         by_name = {
             "embed.0.weight": demb_w, "core.embed.0.weight": dW_e, "core.embed.0.bias": db_e,
             "core.module_att_lstm.weight_ih": dW_ih_m, "core.module_att_lstm.weight_hh": dW_hh_m,
-            "core.module_att_lstm.bias_ih": db_m, "core.module_att_lstm.bias_hh": db_m.clone(),
+            "core.module_att_lstm.bias_ih": db_m, "core.module_att_lstm.bias_hh": db_m2,
             "core.weight_fc.0.weight": dW_fc, "core.weight_fc.0.bias": db_fc,
             "core.pos1.0.weight": dW_p1, "core.pos1.0.bias": db_p1,
             "core.weight_pos.weight": dW_wp, "core.weight_pos.bias": db_wp,
@@ -396,7 +410,7 @@ class SpeakerSeqFn(torch.autograd.Function):
             "core.gate1x.0.weight": dW_g1, "core.gate1x.0.bias": db_g1,
             "core.gate2x.weight": dW_g2, "core.gate2x.bias": db_g2,
             "core.lang_lstm.weight_ih": dW_ih_l, "core.lang_lstm.weight_hh": dW_hh_l,
-            "core.lang_lstm.bias_ih": db_l, "core.lang_lstm.bias_hh": db_l.clone(),
+            "core.lang_lstm.bias_ih": db_l, "core.lang_lstm.bias_hh": db_l2,
             "logit.weight": dW_lo, "logit.bias": db_lo,
         }
         pg = tuple(by_name[n] for n in sp._param_names)

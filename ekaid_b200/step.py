@@ -182,10 +182,20 @@ class GraphFusionStep:
     """One data-parallel rank of the reference's train/test step for the graph+fusion path."""
 
     def __init__(self, change_detector: ChangeDetector, cfg, graph: str = "all", lr: float = 1e-4,
-                 decoder_loss: Optional[Callable] = None, process_group=None):
+                 decoder_loss: Optional[Callable] = None, process_group=None, speaker=None,
+                 decoder_steps: Optional[int] = None):
+        """speaker: an ekaid_b200.speaker.DynamicSpeaker closes the loop like train_mimic.py:230-248 -- its fused masked
+        NLL is the decoder loss and its parameters join the optimizer (the reference's Adam covers both modules,
+        train_mimic.py:163-165).  decoder_steps: fixed number of decoder steps (needed to capture the step in a CUDA
+        graph; None = stop at the first all-empty label column like the reference's loop, one host read per step)."""
         self.cd = change_detector
         self.cfg = cfg
         self.graph = graph
+        self.speaker = speaker
+        self.decoder_steps = decoder_steps
+        if speaker is not None and decoder_loss is None:
+            def decoder_loss(bef, aft, diff, labels, masks):
+                return speaker.masked_nll(bef, aft, diff, labels, masks, steps=self.decoder_steps)
         self.decoder_loss = decoder_loss
         self.pg = process_group
         # Flat parameter order = the order in which backward FINISHES the gradients, in contiguous segments:
@@ -197,8 +207,13 @@ class GraphFusionStep:
         # go out on the optimizer stream and overlap the rest of backward; segment 4 goes out when BPTT is launched
         # and runs next to the recurrence; only segment 5 is left for the end.
         named = change_detector.live_named_parameters()
+        if speaker is not None:
+            # the decoder's backward is the first thing backward does: its gradients complete with segment 0
+            named = named + [("speaker." + n, p) for n, p in speaker.named_parameters()]
 
         def segment_of(name: str) -> int:
+            if name.startswith("speaker."):
+                return 0
             if name.startswith(("w_emb.", "q_emb.", "q_att.")):
                 return 5
             if name.startswith(("context1.", "context2.", "gate1.", "gate2.", "embed.", "att.", "fc1.")):
@@ -434,6 +449,9 @@ class GraphFusionStep:
         launches at batch 64; replaying a graph removes the Python/launch overhead between them."""
         self._static = [t.clone() for t in raw_example]
         self._train = train
+        if train and self.speaker is not None and self.decoder_steps is None:
+            raise RuntimeError("capturing a step with the answer decoder needs a fixed decoder_steps (the reference's "
+                               "data-dependent loop length cannot be part of a CUDA graph)")
 
         def body():
             inputs = expand_adjacency(self._static, self.cfg)
@@ -479,6 +497,14 @@ class GraphFusionStep:
     def pipeline(self) -> "StepPipeline":
         """Input pipeline for the captured step (see StepPipeline)."""
         return StepPipeline(self)
+
+    @torch.no_grad()
+    def infer_decode(self, inputs, check_every: int = 16):
+        """test_mimic.py:116-122: graph + fusion forward, then the greedy answer tokens [B, seq_length]."""
+        if self.speaker is None:
+            raise RuntimeError("infer_decode needs GraphFusionStep(speaker=...)")
+        out = self.cd(*inputs, setting="mode2", graph=self.graph)
+        return self.speaker._sample(out[3], out[4], out[5], None, self.cfg, sample_max=1, check_every=check_every)[0]
 
     @torch.no_grad()
     def infer_step(self, inputs):

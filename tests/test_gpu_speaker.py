@@ -195,3 +195,102 @@ def test_fixed_step_count_equals_the_data_dependent_one():
     assert sp._steps(labels) < 40
     assert abs(res[0][0] - res[1][0]) < 1e-6 * abs(res[0][0])
     assert rel_err(res[1][1], res[0][1]) < 1e-5 and rel_err(res[1][2], res[0][2]) < 1e-5
+
+
+def _full_setup(dev, precision):
+    from helpers import case_inputs, load_case
+    from test_gpu_parity import build_model
+    from ekaid_b200.speaker import DynamicSpeaker
+    from ekaid_b200.step import select_fields
+    from ekaid_b200.synthetic import synthetic_state_dict
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, batch = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    ssd = synthetic_state_dict(speaker_spec(), 4321)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sp = DynamicSpeaker(m.cfg, vocab_size=148)
+    sp.load_state_dict(ssd)
+    sp.to(dev).eval().set_precision(precision)
+    raw = tuple(t.to(dev) for t in select_fields(batch))
+    return m, sp, sd, ssd, inp, batch, raw
+
+
+def test_full_training_objective_with_the_decoder_matches_oracle():
+    """train_mimic.py:230-248 end to end: graph + fusion -> teacher-forced decoder -> masked NLL + 2.5e-3 * attention sums;
+    loss and gradients (through the decoder into the graph encoder) against the oracle's autograd."""
+    from ekaid_b200 import functions
+    from ekaid_b200.step import GraphFusionStep, expand_adjacency
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    m, sp, sd, ssd, inp, batch, raw = _full_setup(dev, "fp32")
+    try:
+        step = GraphFusionStep(m, m.cfg, speaker=sp)
+        step.opt.zero_grad()
+        loss = step.loss(expand_adjacency(raw, m.cfg), raw[9], raw[10].float())
+        loss.backward()
+        torch.cuda.synchronize()
+        sdg = {k: v.clone().requires_grad_(v.is_floating_point() and k != "w_emb.emb_.weight") for k, v in sd.items()}
+        ssg = {k: v.clone().requires_grad_(True) for k, v in ssd.items()}
+        ro = O.change_detector_forward(sdg, *inp)
+        labels, masks = batch[2].squeeze(1), batch[4].squeeze(1).float()
+        logp = O.speaker_teacher_forced(ssg, ro[3], ro[4], ro[5], labels, 90, 512)
+        ref = O.lm_criterion(logp, labels[:, 1:], masks[:, 1:]) + 2.5e-3 * (ro[1].sum() + ro[2].sum()) / (2 * labels.shape[0])
+        ref.backward()
+        assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)), (float(loss), float(ref))
+
+        def l2(a, b):
+            a, b = a.detach().double().cpu(), b.detach().double().cpu()
+            return float((a - b).norm() / (b.norm() + 1e-30))
+
+        names = dict(m.named_parameters())
+        errs = {k: l2(names[k].grad, sdg[k].grad) for k in ("img.weight", "context2.weight", "q_emb.rnn.weight_hh_l0",
+                                                            "embed.0.weight", "gate1.weight")}
+        errs.update({"speaker." + k: l2(p.grad, ssg[k].grad) for k, p in sp.named_parameters()
+                     if k in ("logit.weight", "core.gate1x.0.weight", "core.lang_lstm.weight_ih", "embed.0.weight")})
+        print("full objective grads:", {k: "%.1e" % v for k, v in errs.items()})
+        # (ReLU pre-activations within rounding distance of zero may fall on either side: 2e-3 in relative L2 covers it)
+        assert max(errs.values()) < 2e-3, errs
+        # decoder gradients sit in the optimizer's flat slots: the decoder's parameters are part of the same Adam
+        for p in sp.parameters():
+            assert any(p.grad.data_ptr() == s_.data_ptr() for s_ in step.opt.slots)
+        before = sp.logit.weight.detach().clone()
+        step.train_step(expand_adjacency(raw, m.cfg), raw[9], raw[10].float())
+        torch.cuda.synchronize()
+        assert float((sp.logit.weight.detach() - before).abs().max()) > 0
+    finally:
+        functions.GRAD_SLOTS.clear()
+
+
+def test_captured_step_with_decoder_replays_like_eager_and_decodes():
+    from ekaid_b200 import functions
+    from ekaid_b200.step import GraphFusionStep, expand_adjacency
+    dev = _dev()
+    losses = {}
+    try:
+        for mode in ("eager", "graph"):
+            functions.GRAD_SLOTS.clear()
+            m, sp, sd, ssd, inp, batch, raw = _full_setup(dev, "fp32")
+            step = GraphFusionStep(m, m.cfg, lr=1e-3, speaker=sp, decoder_steps=34)
+            if mode == "graph":
+                step.capture(raw, train=True, warmup=2)
+                with torch.no_grad():
+                    m.load_state_dict(sd)
+                    sp.load_state_dict(ssd)
+                step.opt.m.zero_()
+                step.opt.v.zero_()
+                step.opt.pow_state.fill_(1.0)
+            out = []
+            for _ in range(3):
+                if mode == "graph":
+                    out.append(float(step.replay(raw)))
+                else:
+                    out.append(float(step.train_step(expand_adjacency(raw, m.cfg), raw[9], raw[10].float())))
+            losses[mode] = out
+        assert losses["eager"] == pytest.approx(losses["graph"], rel=1e-5)
+        assert losses["eager"][2] < losses["eager"][0]            # the same batch three times: the loss goes down
+        m.eval()
+        sp.eval()
+        toks = step.infer_decode(expand_adjacency(raw, m.cfg))
+        assert toks.shape == (2, 90) and toks.dtype == torch.int64 and int(toks[:, 0].min()) > 0
+    finally:
+        functions.GRAD_SLOTS.clear()
