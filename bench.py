@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--nodes", type=int, default=52)
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-decoder", action="store_true", help="skip the answer-decoder section of the report")
     ap.add_argument("--graph", default="all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager comparator on the same GPU")
@@ -322,6 +323,70 @@ def emit(line):
     out.flush()
 
 
+def decoder_section(args, dev):
+    """The consumer side of the path, reported next to the headline, not inside it:
+    (a) the reference's whole training step -- graph + fusion -> teacher-forced DynamicSpeaker -> masked NLL -> backward ->
+    Adam over both modules (train_mimic.py:220-269) -- as one captured CUDA graph; (b) the test path (test_mimic.py:116-122):
+    graph + fusion forward + greedy decode of seq_length tokens, stop condition on the device."""
+    import contextlib
+    import io
+    from ekaid_b200 import functions, lib
+    from ekaid_b200.config import WORD_TO_IDX, default_cfg
+    from ekaid_b200.modules import ChangeDetector
+    from ekaid_b200.speaker import DynamicSpeaker
+    from ekaid_b200.step import GraphFusionStep, expand_adjacency, select_fields
+    from ekaid_b200.synthetic import synthetic_batch, synthetic_state_dict
+    B, N = args.batch, args.nodes
+    cfg = default_cfg(args.graph, nongt_dim=max(52, N))
+    with contextlib.redirect_stdout(io.StringIO()):
+        cd = ChangeDetector(cfg, WORD_TO_IDX)
+        sp = DynamicSpeaker(cfg, vocab_size=148)
+    cd.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in cd.state_dict().items()}, 1238))
+    sp.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in sp.state_dict().items()}, 4321))
+    cd.to(dev).set_precision(args.precision).train()
+    sp.to(dev).set_precision(args.precision).train()
+    raws = [tuple(t.to(dev) for t in select_fields(synthetic_batch(B, N, seed=777 + i, q_len=args.qlen))) for i in range(2)]
+    tsteps = max(sp._steps(r[9]) for r in raws)
+    step = GraphFusionStep(cd, cfg, graph=args.graph, speaker=sp, decoder_steps=tsteps)
+    step.capture(raws[0], train=True)
+    for i in range(3):
+        step.replay(raws[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for i in range(n):
+        step.replay(raws[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms_train = e0.elapsed_time(e1) / n
+    out = {"train_step_with_decoder": {"ms_per_step": ms_train, "samples_s": B / (ms_train * 1e-3), "decoder_steps": tsteps,
+                                       "launches_per_step": step.launches_per_replay,
+                                       "what": "graph+fusion fwd/bwd + teacher-forced answer decoder fwd/bwd + masked NLL + "
+                                               "Adam over both modules, one CUDA graph, batch %d" % B}}
+    cd.eval()
+    sp.eval()
+    inputs = expand_adjacency(raws[0], cfg)
+    with torch.no_grad():
+        for _ in range(2):
+            step.infer_decode(inputs, check_every=0)
+        torch.cuda.synchronize()
+        before = lib.LAUNCHES
+        e0.record()
+        for _ in range(3):
+            toks = step.infer_decode(inputs, check_every=0)
+        e1.record()
+        torch.cuda.synchronize()
+    ms_inf = e0.elapsed_time(e1) / 3
+    out["greedy_inference"] = {"ms_per_batch": ms_inf, "samples_s": B / (ms_inf * 1e-3), "tokens_per_sample": int(toks.shape[1]),
+                               "launches_per_batch": (lib.LAUNCHES - before) // 3,
+                               "what": "graph+fusion forward + %d greedy decode steps (eager launches, no host sync per "
+                                       "step), batch %d" % (int(toks.shape[1]), B)}
+    step.opt.close()
+    step._graph = None
+    return out
+
+
 def main():
     args = parse()
     guard_stdout()
@@ -557,6 +622,11 @@ def main():
             "gpu_launches": launches, "cuda_graph": use_graph, "roofline": roof, "kernel_time_share_pct": breakdown,
             "gemm_shapes": gemm_shapes}
     line["roofline_non_gemm"] = non_gemm_roofline(agg, nprof, pk, pk_kind, ms_step)
+    if rank == 0 and world == 1 and args.mode == "train" and not args.no_decoder:
+        try:
+            line["decoder"] = decoder_section(args, dev)
+        except Exception as e:           # noqa: BLE001
+            line["decoder"] = {"error": repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         line["gpu_eager_baseline"] = gpu_eager_baseline(args, dev)
         best = max((v.get("value", 0.0) for k, v in line["gpu_eager_baseline"].items() if isinstance(v, dict)), default=0.0)
