@@ -444,6 +444,7 @@ class DynamicSpeaker(nn.Module):
         self._param_names = [n for n, _ in self.named_parameters()]
         self._last_state = None
         self._tok_err = None
+        self._runners = {}
 
     def set_precision(self, precision: str):
         PC(precision)
@@ -498,102 +499,25 @@ class DynamicSpeaker(nn.Module):
 
     # ---- inference -------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def _decode(self, feat_bef, feat_aft, feat_diff, tokens0, state, nsteps, greedy, want_logp=False, check_every=0):
-        """Shared eval-mode step loop.  greedy: the next token is chosen on the device; else `tokens0` [B, nsteps] are fed."""
-        lib.require_device()
-        pc = PC(self.precision)
-        w = _W(pc, self)
-        R, E, D, G, V, NH, Wex = w.R, w.E, w.D, w.G, w.V, w.NH, w.Wex
-        dev = feat_bef.device
-        B = feat_bef.shape[0]
-        opf, OT = _opf(pc), pc.T
-        bef, aft, diff = _f32c(feat_bef), _f32c(feat_aft), _f32c(feat_diff)
-        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)      # noqa: E731
-        opt = lambda *s: torch.empty(*s, dtype=OT, device=dev)                 # noqa: E731
-        EI = opt(B, 3 * D)
-        cast_many(pc, [(bef, EI[:, :D]), (diff, EI[:, D:2 * D]), (aft, EI[:, 2 * D:])])
-        emb0 = opt(B, E)
-        _gemm_op(pc, EI, w.W_e, B, E, 3 * D, emb0, bias=w.b_e, act=ACT_RELU)
-        S3 = f32(B, 4 * R)
-        gemm(emb0, w.W_ih_me, B, 4 * R, E, C=S3)
-        # word-embedding half of the language LSTM's input product as a [V, 4R] table: one row per possible token
-        vocab = torch.arange(V, device=dev, dtype=torch.int64).view(V, 1)
-        ET = opt(V, Wex)
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
-        call("dec_embed", vocab.data_ptr(), 1, 0, 0, V, V, w.emb.data_ptr(), V, w.We, ET.data_ptr(), Wex, opf, None, 0, 0.0,
-             err.data_ptr())
-        TBL = f32(V, 4 * R)
-        gemm(ET, w.W_ih_x, V, 4 * R, Wex, C=TBL)
-        h, c = state
-        hm, hl = opt(B, R), opt(B, R)
-        cast_many(pc, [(_f32c(h[0]), hm), (_f32c(h[1]), hl)])
-        hmf, hlf = _f32c(h[0]).clone(), _f32c(h[1]).clone()
-        cm, cl = _f32c(c[0]).clone(), _f32c(c[1]).clone()
-        gm, gl = f32(B, 4 * R), f32(B, 4 * R)
-        S1, S2, S6, g2pre = f32(B, NH), f32(B, 4 * R), f32(B, 4 * R), f32(B, D)
-        mw, pw, dpos, vpos, att = f32(B, 4), f32(B, 16), f32(B, 16), f32(B, 512), f32(B, D)
-        gi2, g1, gate, gated = opt(B, R + D), opt(B, G), f32(B, D), opt(B, D)
-        logits = f32(B, V)
-        T = nsteps
-        seq = torch.zeros(B, max(T, 1), dtype=torch.int64, device=dev)
-        seq_lp = torch.zeros(B, max(T, 1), dtype=torch.float32, device=dev)
-        unfinished = torch.ones(B, dtype=torch.uint8, device=dev)
-        running = torch.ones(1, dtype=torch.int32, device=dev)
-        tok = tokens0[:, 0].contiguous().clone() if not greedy else torch.full((B,), 2, dtype=torch.int64, device=dev)
-        logps, mws, dposs = [], [], []
-        flag_host = torch.ones(1, dtype=torch.int32).pin_memory() if check_every else None
-        for t in range(T + (1 if greedy else 0)):
-            if not greedy and t > 0:
-                tok = tokens0[:, t].contiguous()
-            gemm(hl, w.Wcat_h, B, NH, R, C=S1)
-            gemm(hm, w.W_hh_m, B, 4 * R, R, C=S2)
-            call("dec_lstm_fwd", S1.data_ptr(), NH, S2.data_ptr(), 4 * R, S3.data_ptr(), 4 * R, None, None, w.b_mi.data_ptr(),
-                 w.b_mh.data_ptr(), cm.data_ptr(), B, R, gm.data_ptr(), cm.data_ptr(), hmf.data_ptr(), hm.data_ptr(), R, None, 0,
-                 opf, None, 0, 0.0, 0)
-            call("dec_att_fwd", hmf.data_ptr(), S1[:, w.o_p1:].data_ptr(), NH, ctypes.addressof(w.att_ptrs), bef.data_ptr(),
-                 diff.data_ptr(), aft.data_ptr(), B, R, 512, D, None, 0, 0.0, 0, 0.0, 0, mw.data_ptr(), pw.data_ptr(),
-                 dpos.data_ptr(), vpos.data_ptr(), att.data_ptr(), gi2.data_ptr(), R + D, opf)
-            _gemm_op(pc, gi2, w.W_g1r, B, G, R + D, g1, bias=w.b_g1, addend=S1[:, w.o_g1:w.o_lh], act=ACT_RELU)
-            gemm(g1, w.W_g2, B, D, G, bias=w.b_g2, C=g2pre)
-            call("dec_gate_fwd", g2pre.data_ptr(), att.data_ptr(), B * D, gate.data_ptr(), gated.data_ptr(), opf)
-            gemm(gated, w.W_ih_lg, B, 4 * R, D, C=S6)
-            call("dec_lstm_fwd", S6.data_ptr(), 4 * R, S1[:, w.o_lh:].data_ptr(), NH, None, 0, TBL.data_ptr(), tok.data_ptr(),
-                 w.b_li.data_ptr(), w.b_lh.data_ptr(), cl.data_ptr(), B, R, gl.data_ptr(), cl.data_ptr(), hlf.data_ptr(),
-                 hl.data_ptr(), R, None, 0, opf, None, 0, 0.0, 0)
-            gemm(hl, w.W_lo, B, V, R, bias=w.b_lo, C=logits)
-            if greedy:
-                if t == T:
-                    break
-                lp = f32(B, V) if want_logp else None
-                call("dec_token", logits.data_ptr(), V, B, V, t, T, seq.data_ptr(), seq_lp.data_ptr(), unfinished.data_ptr(),
-                     running.data_ptr(), tok.data_ptr(), ptr(lp))
-                if want_logp:
-                    logps.append(lp)
-                if check_every and (t + 1) % check_every == 0:
-                    flag_host.copy_(running, non_blocking=False)
-                    if int(flag_host[0]) == 0:
-                        break
-            else:
-                logps.append(torch.log_softmax(logits, dim=1))
-                mws.append(mw[:, :3].clone())
-                dposs.append(dpos.clone())
-        state = (torch.stack([hmf, hlf]), torch.stack([cm, cl]))
-        return seq, seq_lp, logps, mws, dposs, state
-
-    @torch.no_grad()
     def get_logprobs_state(self, it, feat_bef, feat_aft, feat_diff, state):
         """:225-240, one eval-mode step: (log_probs [B,V], state, log_pos_probs [B,16])."""
         if self.training:
             raise NotImplementedError("get_logprobs_state is the inference step; training goes through _forward / masked_nll")
-        _, _, logps, mws, dposs, state = self._decode(feat_bef, feat_aft, feat_diff, it.view(-1, 1), state, 1, False)
-        self.core.module_weights = mws[0]
-        self.module_weights.append(mws[0])
-        return logps[0], state, torch.log_softmax(dposs[0], dim=1)
+        r = _StepRunner(self, feat_bef.shape[0], feat_bef.device)
+        r.load(feat_bef, feat_aft, feat_diff, state)
+        r.prepare()
+        r.tok.copy_(it.view(-1))
+        r.step(0, sample=False)
+        self.core.module_weights = r.mw[:, :3].clone()
+        self.module_weights.append(self.core.module_weights)
+        return torch.log_softmax(r.logits, dim=1), r.state(), torch.log_softmax(r.dpos, dim=1)
 
     @torch.no_grad()
-    def _sample(self, feat_bef, feat_aft, feat_diff, seq, cfg={}, sample_max=0, check_every=16):
+    def _sample(self, feat_bef, feat_aft, feat_diff, seq, cfg={}, sample_max=0, check_every=16, use_graph=True):
         """:287-357 with beam_size = 1, sample_max = 1 (the reference's test path, test_mimic.py:119-122):
-        -> (seq [B, seq_length] int64, seq_logprobs [B, seq_length])."""
+        -> (seq [B, seq_length] int64, seq_logprobs [B, seq_length]).
+        The token loop runs in blocks of `check_every` steps; the host reads the device-side stop flag once per block
+        (0 = never, always seq_length steps).  use_graph: every block is a captured CUDA graph, kept per batch size."""
         sp = cfg.model.speaker if hasattr(cfg, "model") else {}
         if (sp.get('beam_size', 1) if hasattr(sp, "get") else 1) > 1:
             raise NotImplementedError("beam search is not implemented (the reference's test script uses beam_size 1)")
@@ -602,10 +526,155 @@ class DynamicSpeaker(nn.Module):
         if self.training:
             raise NotImplementedError("_sample is an inference entry point: call eval() first")
         self.module_weights = []
-        B = feat_bef.shape[0]
-        out = self._decode(feat_bef, feat_aft, feat_diff, None, self.init_hidden(B), self.seq_length, True,
-                           check_every=check_every)
-        return out[0], out[1]
+        B, dev = feat_bef.shape[0], feat_bef.device
+        T = self.seq_length
+        ce = check_every if check_every and check_every > 0 else T + 1
+        key = (B, str(dev), self.precision, ce, bool(use_graph), self.logit.weight.data_ptr())
+        r = self._runners.get(key)
+        if r is None:
+            if len(self._runners) > 4:
+                self._runners.clear()
+            r = _StepRunner(self, B, dev)
+            self._runners[key] = r
+        r.load(feat_bef, feat_aft, feat_diff, None)
+        blocks = [(t0, min(t0 + ce, T + 1)) for t0 in range(0, T + 1, ce)]
+        for bi, (t0, t1) in enumerate(blocks):
+            if use_graph:
+                g = r.graphs.get((t0, t1))
+                if g is None:
+                    if not r.graphs:
+                        # first use: one eager pass warms every kernel up outside the capture (and is thrown away)
+                        r.run_block(0, min(2, T + 1), first=True)
+                        r.load(feat_bef, feat_aft, feat_diff, None)
+                        torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    before = lib.LAUNCHES
+                    with torch.cuda.graph(g):
+                        r.run_block(t0, t1, first=(bi == 0))
+                    r.graphs[(t0, t1)] = g
+                    r.graph_launches[(t0, t1)] = lib.LAUNCHES - before
+                g.replay()
+                lib.LAUNCHES += r.graph_launches[(t0, t1)]
+            else:
+                r.run_block(t0, t1, first=(bi == 0))
+            if bi + 1 < len(blocks):
+                r.flag_host.copy_(r.running)
+                if int(r.flag_host[0]) == 0:
+                    break
+        return r.seq.clone(), r.seq_lp.clone()
+
+
+class _StepRunner:
+    """Buffers and launches of the eval-mode decode step for one batch size (static addresses: its blocks of steps can be
+    captured into CUDA graphs and replayed on new inputs)."""
+
+    def __init__(self, sp: DynamicSpeaker, B: int, dev):
+        lib.require_device()
+        self.sp, self.B, self.dev = sp, B, dev
+        self.pc = pc = PC(sp.precision)
+        c = sp.core
+        R, E, D, V = sp.rnn_size, c.embed_dim, c.input_dim, sp.vocab_size
+        G, T = 2 * R + D, sp.seq_length
+        self.NH = 4 * R + 512 + G + 4 * R
+        OT = pc.T
+        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)      # noqa: E731
+        opt = lambda *s: torch.zeros(*s, dtype=OT, device=dev)                 # noqa: E731
+        self.bef, self.aft, self.diff = f32(B, D), f32(B, D), f32(B, D)
+        self.h0, self.c0 = f32(2, B, R), f32(2, B, R)
+        self.hm, self.hl = opt(B, R), opt(B, R)
+        self.hmf, self.hlf, self.cm, self.cl = f32(B, R), f32(B, R), f32(B, R), f32(B, R)
+        self.gm, self.gl = f32(B, 4 * R), f32(B, 4 * R)
+        self.S1, self.S2, self.S3, self.S6, self.g2pre = f32(B, self.NH), f32(B, 4 * R), f32(B, 4 * R), f32(B, 4 * R), f32(B, D)
+        self.mw, self.pw, self.dpos, self.vpos, self.att = f32(B, 4), f32(B, 16), f32(B, 16), f32(B, 512), f32(B, D)
+        self.gi2, self.g1, self.gate, self.gated = opt(B, R + D), opt(B, G), f32(B, D), opt(B, D)
+        self.logits = f32(B, V)
+        self.seq = torch.zeros(B, T, dtype=torch.int64, device=dev)
+        self.seq_lp = f32(B, T)
+        self.unfinished = torch.ones(B, dtype=torch.uint8, device=dev)
+        self.running = torch.ones(1, dtype=torch.int32, device=dev)
+        self.tok = torch.full((B,), 2, dtype=torch.int64, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.flag_host = torch.ones(1, dtype=torch.int32).pin_memory()
+        self.vocab = torch.arange(V, device=dev, dtype=torch.int64).view(V, 1)
+        self.graphs, self.graph_launches = {}, {}
+        self.w = None
+
+    def load(self, bef, aft, diff, state):
+        self.bef.copy_(bef)
+        self.aft.copy_(aft)
+        self.diff.copy_(diff)
+        if state is None:
+            self.h0.zero_()
+            self.c0.zero_()
+        else:
+            self.h0.copy_(state[0])
+            self.c0.copy_(state[1])
+
+    def state(self):
+        return torch.stack([self.hmf, self.hlf]), torch.stack([self.cm, self.cl])
+
+    def prepare(self):
+        """Per sequence: operand copies of the weights, the step-invariant embedding products, the token table, state."""
+        pc, sp = self.pc, self.sp
+        self.w = w = _W(pc, sp)
+        B, dev = self.B, self.dev
+        R, E, D, V, Wex = w.R, w.E, w.D, w.V, w.Wex
+        OT, opf = pc.T, _opf(pc)
+        EI = torch.empty(B, 3 * D, dtype=OT, device=dev)
+        cast_many(pc, [(self.bef, EI[:, :D]), (self.diff, EI[:, D:2 * D]), (self.aft, EI[:, 2 * D:])])
+        emb0 = torch.empty(B, E, dtype=OT, device=dev)
+        _gemm_op(pc, EI, w.W_e, B, E, 3 * D, emb0, bias=w.b_e, act=ACT_RELU)
+        gemm(emb0, w.W_ih_me, B, 4 * R, E, C=self.S3)
+        # word-embedding half of the language LSTM's input product as a [V, 4R] table: one row per possible token
+        ET = torch.empty(V, Wex, dtype=OT, device=dev)
+        call("dec_embed", self.vocab.data_ptr(), 1, 0, 0, V, V, w.emb.data_ptr(), V, w.We, ET.data_ptr(), Wex, opf, None, 0, 0.0,
+             self.err.data_ptr())
+        self.TBL = torch.empty(V, 4 * R, dtype=torch.float32, device=dev)
+        gemm(ET, w.W_ih_x, V, 4 * R, Wex, C=self.TBL)
+        self.hmf.copy_(self.h0[0])
+        self.hlf.copy_(self.h0[1])
+        self.cm.copy_(self.c0[0])
+        self.cl.copy_(self.c0[1])
+        cast_many(pc, [(self.hmf, self.hm), (self.hlf, self.hl)])
+        self.seq.zero_()
+        self.seq_lp.zero_()
+        self.unfinished.fill_(1)
+        self.running.fill_(1)
+        self.tok.fill_(2)                                  # <bos> (:303)
+
+    def step(self, t: int, sample: bool = True):
+        pc, w, B = self.pc, self.w, self.B
+        R, D, G, V, NH = w.R, w.D, w.G, w.V, w.NH
+        opf = _opf(pc)
+        gemm(self.hl, w.Wcat_h, B, NH, R, C=self.S1)
+        gemm(self.hm, w.W_hh_m, B, 4 * R, R, C=self.S2)
+        call("dec_lstm_fwd", self.S1.data_ptr(), NH, self.S2.data_ptr(), 4 * R, self.S3.data_ptr(), 4 * R, None, None,
+             w.b_mi.data_ptr(), w.b_mh.data_ptr(), self.cm.data_ptr(), B, R, self.gm.data_ptr(), self.cm.data_ptr(),
+             self.hmf.data_ptr(), self.hm.data_ptr(), R, None, 0, opf, None, 0, 0.0, 0)
+        call("dec_att_fwd", self.hmf.data_ptr(), self.S1[:, w.o_p1:].data_ptr(), NH, ctypes.addressof(w.att_ptrs),
+             self.bef.data_ptr(), self.diff.data_ptr(), self.aft.data_ptr(), B, R, 512, D, None, 0, 0.0, 0, 0.0, 0,
+             self.mw.data_ptr(), self.pw.data_ptr(), self.dpos.data_ptr(), self.vpos.data_ptr(), self.att.data_ptr(),
+             self.gi2.data_ptr(), R + D, opf)
+        _gemm_op(pc, self.gi2, w.W_g1r, B, G, R + D, self.g1, bias=w.b_g1, addend=self.S1[:, w.o_g1:w.o_lh], act=ACT_RELU)
+        gemm(self.g1, w.W_g2, B, D, G, bias=w.b_g2, C=self.g2pre)
+        call("dec_gate_fwd", self.g2pre.data_ptr(), self.att.data_ptr(), B * D, self.gate.data_ptr(), self.gated.data_ptr(), opf)
+        gemm(self.gated, w.W_ih_lg, B, 4 * R, D, C=self.S6)
+        call("dec_lstm_fwd", self.S6.data_ptr(), 4 * R, self.S1[:, w.o_lh:].data_ptr(), NH, None, 0, self.TBL.data_ptr(),
+             self.tok.data_ptr(), w.b_li.data_ptr(), w.b_lh.data_ptr(), self.cl.data_ptr(), B, R, self.gl.data_ptr(),
+             self.cl.data_ptr(), self.hlf.data_ptr(), self.hl.data_ptr(), R, None, 0, opf, None, 0, 0.0, 0)
+        gemm(self.hl, w.W_lo, B, V, R, bias=w.b_lo, C=self.logits)
+        if sample:
+            T = self.sp.seq_length
+            call("dec_token", self.logits.data_ptr(), V, B, V, t, T, self.seq.data_ptr(), self.seq_lp.data_ptr(),
+                 self.unfinished.data_ptr(), self.running.data_ptr(), self.tok.data_ptr(), None)
+
+    def run_block(self, t0: int, t1: int, first: bool):
+        """Steps t0 .. t1-1 of the reference's `for t in range(seq_length + 1)` loop (:299); its last iteration only advances
+        the state (:334-335), so nothing is launched for it."""
+        if first:
+            self.prepare()
+        for t in range(t0, min(t1, self.sp.seq_length)):
+            self.step(t)
 
 
 class LanguageModelCriterion(nn.Module):

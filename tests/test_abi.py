@@ -119,6 +119,43 @@ def test_collate_narrows_label_matrices_to_int8_losslessly():
     assert per_sample(wide) - per_sample(narrow) == 4 * 100 * 100 * 7
 
 
+def test_loader_schema_round_trip_and_sample_rules(tmp_path):
+    """ekaid_b200.loader: arrays with the reference's HDF5 schema -> the dataset's samples -> rcc_collate must reproduce the
+    13-tuple the synthetic loader emits for the same seed (same tensors, same dtypes), through an .npz round trip; the mask
+    rule of rcc_dataset_pos_mimic.py:258-263; int8 label matrices in compact mode."""
+    from ekaid_b200.loader import FEATURE_KEYS, LABEL_KEYS, RCCArrays, RCCDataset, batches, rcc_collate
+    from ekaid_b200.step import select_fields
+    from ekaid_b200.synthetic import synthetic_batch
+    arr = RCCArrays.synthetic(6, 52, seed=11)
+    assert arr["image_features"].shape == (12, 52, 1024) and arr["image_features"].dtype.name == "float32"
+    assert arr["image_adj_matrix"].shape == (12, 100, 100) and arr["image_adj_matrix"].dtype.name == "int64"
+    assert arr["questions"].shape == (6, 20) and arr["answers"].shape == (6, 90) and arr["feature_idx"].shape == (6, 2)
+    path = str(tmp_path / "rcc.npz")
+    arr.save_npz(path)
+    arr2 = RCCArrays.from_npz(path)
+    assert set(FEATURE_KEYS + LABEL_KEYS) <= set(arr2.a)
+    ds = RCCDataset(arr2)
+    assert len(ds) == 6
+    got = rcc_collate([ds[i] for i in range(6)])
+    ref = synthetic_batch(6, 52, seed=11)
+    assert len(got) == 13
+    for i, (g, r) in enumerate(zip(got, ref)):
+        assert g.shape == r.shape, i
+        if i in (10, 11):
+            assert g.dtype == torch.float64 and float((g - r.float().double()).abs().max()) == 0.0      # boxes: f32 on disk
+        else:
+            assert g.dtype == r.dtype and torch.equal(g, r), i
+    seq, mask = got[2][:, 0], got[4][:, 0]
+    assert torch.equal(mask.sum(1), (seq != 0).sum(1) + 1) and int(seq[:, -1].abs().max()) == 0
+    comp = next(batches(ds, 4, compact=True))
+    assert comp[6].dtype == torch.int8 and torch.equal(comp[6].double(), got[6][:4])
+    assert select_fields(comp)[2] is comp[6]                      # already compact: passed through untouched
+    with pytest.raises(KeyError):
+        RCCArrays({"image_features": arr["image_features"]})
+    with pytest.raises(ImportError):
+        RCCArrays.from_hdf5("a.h5", "b.h5")                       # no h5py in this image: loud, not emulated
+
+
 def test_golden_manifest_complete():
     from helpers import CASES
     for c in CASES:
