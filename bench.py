@@ -380,8 +380,8 @@ def decoder_section(args, dev):
     ms_inf = e0.elapsed_time(e1) / 3
     out["greedy_inference"] = {"ms_per_batch": ms_inf, "samples_s": B / (ms_inf * 1e-3), "tokens_per_sample": int(toks.shape[1]),
                                "launches_per_batch": (lib.LAUNCHES - before) // 3,
-                               "what": "graph+fusion forward + %d greedy decode steps (eager launches, no host sync per "
-                                       "step), batch %d" % (int(toks.shape[1]), B)}
+                               "what": "graph+fusion forward (eager launches) + %d greedy decode steps (one captured CUDA graph, "
+                                       "stop condition on the device), batch %d" % (int(toks.shape[1]), B)}
     step.opt.close()
     step._graph = None
     return out

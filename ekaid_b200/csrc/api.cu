@@ -195,6 +195,7 @@ int ek_dec_nll_reduce_launch(const float*, int, const float*, long long, int, in
 int ek_dec_outer_small_launch(const float*, long long, int, const float*, long long, int, int, float*, long long, int,
                               cudaStream_t);
 
+int ek_drop_mask_launch(EkDrop, long long, float*, cudaStream_t);
 static EkDrop mk_drop(const uint64_t* seed, uint32_t site, float p) {
   EkDrop d;
   d.seed = (p > 0.f) ? (const unsigned long long*)seed : nullptr;
@@ -499,6 +500,9 @@ int ekaid_onehot_adj_i8(const int8_t* labels, int B, int S, int N, int L, float*
 
 extern "C" {
 /* ---- answer decoder (speaker.cu) ---- */
+int ekaid_drop_mask(const uint64_t* seed, uint32_t site, float p, int64_t n, float* out, void* stream) {
+  return ek_drop_mask_launch(mk_drop(seed, site, p), n, out, ST);
+}
 int ekaid_dec_embed(const int64_t* seq, int64_t sb, int64_t st, int t0, int B, int rows, const float* emb, int V, int We,
                     void* out, int64_t ldo, int opf, const uint64_t* seed, uint32_t site, float p, int32_t* err,
                     void* stream) {

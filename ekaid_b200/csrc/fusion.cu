@@ -20,6 +20,15 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld
     *(uint2*)(dst + r * ldd + c) = pk;
   }
 }
+// test hook: the dropout multipliers (0 or 1 / (1 - p)) of elements [0, n) at one site, exactly as every kernel of the
+// library derives them from (seed, site, element index) -- lets a test hand the SAME masks to the oracle
+__global__ void drop_mask_kernel(EkDrop dr, long long n, float* __restrict__ out) {
+  ek_pdl_prologue();
+  const unsigned long long seedv = ek_seed(dr);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    out[e] = ek_drop_mult(dr, seedv, (unsigned long long)e);
+}
+
 // fp32 operand -> three bf16 planes for the split-precision tensor-core product of the fp32 parity path:
 //   x = hi + lo + eps,  hi = bf16(x), lo = bf16(x - hi), |eps| <= 2^-17 |x|
 //   A B^T ~= Ah Bh^T + Al Bh^T + Ah Bl^T      (the dropped Al Bl^T term is <= 2^-16 of the product)
@@ -992,6 +1001,13 @@ inline int grid_for(long long total, int block = 256) {
 }
 
 }  // namespace
+
+int ek_drop_mask_launch(EkDrop dr, long long n, float* out, cudaStream_t st) {
+  if (n <= 0) return EK_OK;
+  ek_launch(drop_mask_kernel, grid_for(n), 256, 0, st, dr, n, out);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
 
 int ek_split3_bf16_launch(const float* src, long long lds, bf16* dst, long long ldd, long long rows, int cols,
                           int pattern, int along_rows, cudaStream_t st) {

@@ -333,6 +333,10 @@ int ekaid_drop_fanout(int is_bf16, const void* in, int64_t ldi, const uint64_t* 
                       uint32_t site1, float p1, int64_t M, int C, void* out0, void* out1, int64_t ldo, void* out0B,
                       void* out1B, void* stream);
 
+/* test hook: out[e] = dropout multiplier (0 or 1/(1-p)) of element e < n at `site` for the current seed -- the same
+ * function of (seed, site, index) every kernel uses, so a test can hand identical masks to the oracle */
+int ekaid_drop_mask(const uint64_t* seed, uint32_t site, float p, int64_t n, float* out, void* stream);
+
 /* ---- optimizer (utils/utils.py:96-99 -> torch.optim.Adam semantics) -------------------------------------- */
 /* pow_state: device float[2] = {beta1^t, beta2^t}; call ekaid_adam_advance once per step before the updates */
 int ekaid_adam_advance(float* pow_state, float b1, float b2, void* stream);

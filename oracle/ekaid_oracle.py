@@ -68,23 +68,27 @@ def gru_all(sd, x: Tensor) -> Tensor:
     return torch.stack(outs, 1)
 
 
-def question_self_attention(sd, h: Tensor) -> Tensor:
+def question_self_attention(sd, h: Tensor, drop: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """models/language_model.py:127-156 incl. quirk Q4 (softmax over the BATCH axis, then the
-    contiguous [L,B] result is re-viewed as [B,1,L])."""
+    contiguous [L,B] result is re-viewed as [B,1,L]).
+    drop (train mode with GIVEN masks; multipliers 0 or 1/(1-p)): 'w1' [B, L, Hd] = the Dropout in front of W1's Linear
+    (fc.py:25-32), 'qv' [B, Hd] = self.drop on the pooled vector (:155)."""
     B, L, Hd = h.shape
     w1 = wn(sd, "q_att.W1_self_att_q.main.1")
     b1 = sd["q_att.W1_self_att_q.main.1.bias"]
     w2 = wn(sd, "q_att.W2_self_att_q.main.0")
     b2 = sd["q_att.W2_self_att_q.main.0.bias"]
-    a1 = torch.tanh(h.reshape(-1, Hd) @ w1.t() + b1)
+    hin = h if drop is None else h * drop["w1"]
+    a1 = torch.tanh(hin.reshape(-1, Hd) @ w1.t() + b1)
     a = (a1 @ w2.t() + b2).view(B, L)
     weight = F.softmax(a.t(), dim=1).contiguous().view(-1, 1, L)      # Q4
-    return torch.bmm(weight, h).view(-1, Hd)
+    out = torch.bmm(weight, h).view(-1, Hd)
+    return out if drop is None else out * drop["qv"]
 
 
-def question_vector(sd, question: Tensor) -> Tensor:
+def question_vector(sd, question: Tensor, drop: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """models/modules.py:200-206."""
-    return question_self_attention(sd, gru_all(sd, word_embedding(sd, question)))
+    return question_self_attention(sd, gru_all(sd, word_embedding(sd, question)), drop)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -120,12 +124,16 @@ def position_embedding(pos_mat: Tensor, feat_dim: int = 64, wave_length: float =
 # one relation encoder step (GAT)
 # ----------------------------------------------------------------------------------------------
 def gat_relation(sd, R: str, X: Tensor, qv: Tensor, adj: Optional[Tensor], pos_emb: Optional[Tensor],
-                 num_heads: int, nongt_dim: int, return_aux: bool = False, relu_mask: Optional[Tensor] = None):
+                 num_heads: int, nongt_dim: int, return_aux: bool = False, relu_mask: Optional[Tensor] = None,
+                 drop: Optional[Dict[str, Tensor]] = None):
     """X <- X + GAT(cat(X, q), adj)   (models/relation_encoder.py:57-84 / :112-132,
     models/graph_att.py:53-106, models/graph_att_layer.py:60-178), eval mode.
 
     adj: [B,N,N,label] float (explicit) or None (implicit: all-ones, bias is a constant shift, Q5).
-    Only direction 1 (transposed adjacency) is live and its output is doubled (Q2)."""
+    Only direction 1 (transposed adjacency) is live and its output is doubled (Q2).
+    drop (train mode with GIVEN masks; multipliers 0 or 1/(1-p)), every FCNet applies Dropout BEFORE its Linear
+    (fc.py:25-32): 'vq' [B,N,D+Dq] self_weights' input, 'q' / 'k' [B,N,D] the query / key inputs, 'pos' [B,N*K,64]
+    pair_pos_fc1's input, 'out' [B,N,D] GAttNet.dropout on the doubled output before the ReLU (graph_att.py:103-104)."""
     B, N, D = X.shape
     K = min(nongt_dim, N)
     Hn = num_heads
@@ -134,15 +142,20 @@ def gat_relation(sd, R: str, X: Tensor, qv: Tensor, adj: Optional[Tensor], pos_e
     qe = qv.view(B, 1, -1).expand(B, N, qv.shape[1]).clone()
     qe = qe * (X.sum(-1, keepdim=True) != 0).to(X.dtype)
     vq = torch.cat((X, qe), -1)
+    if drop is not None:
+        vq = vq * drop["vq"]
     sf = vq @ wn(sd, R + ".self_weights.main.1").t() + sd[R + ".self_weights.main.1.bias"]
     nn_ = R + ".neighbor_net.1"                                       # Q2: direction 1 only
-    q = (sf @ wn(sd, nn_ + ".query.main.1").t() + sd[nn_ + ".query.main.1.bias"]).view(B, N, Hn, dh).transpose(1, 2)
-    k = (sf[:, :K] @ wn(sd, nn_ + ".key.main.1").t() + sd[nn_ + ".key.main.1.bias"]).view(B, K, Hn, dh).transpose(1, 2)
+    sq, sk = (sf, sf) if drop is None else (sf * drop["q"], sf * drop["k"])
+    q = (sq @ wn(sd, nn_ + ".query.main.1").t() + sd[nn_ + ".query.main.1.bias"]).view(B, N, Hn, dh).transpose(1, 2)
+    k = (sk[:, :K] @ wn(sd, nn_ + ".key.main.1").t() + sd[nn_ + ".key.main.1.bias"]).view(B, K, Hn, dh).transpose(1, 2)
     aff = (1.0 / math.sqrt(float(dh))) * (q @ k.transpose(2, 3))      # [B,H,N,K]
     aff = aff.transpose(1, 2)                                         # [B,N,H,K]
     if pos_emb is not None:
         # Q7 / Q13  graph_att_layer.py:113-135
         pe = pos_emb.to(X.dtype).reshape(B, -1, pos_emb.shape[-1])
+        if drop is not None:
+            pe = pe * drop["pos"]
         pf = F.relu(pe @ wn(sd, nn_ + ".pair_pos_fc1.main.1").t() + sd[nn_ + ".pair_pos_fc1.main.1.bias"])
         aw = pf.view(B, -1, K, Hn).transpose(2, 3)
         aff = aff + torch.log(torch.clamp(aw, min=1e-6))
@@ -159,12 +172,13 @@ def gat_relation(sd, R: str, X: Tensor, qv: Tensor, adj: Optional[Tensor], pos_e
     out_t = P.reshape(B, N * Hn, K) @ sf[:, :K]                       # Q3
     out = out_t.reshape(B * N, Hn * D) @ sd[nn_ + ".linear_out_2.weight"].t() + sd[nn_ + ".linear_out_2.bias"]
     out = out.view(B, N, D)
+    out2 = (out + out) if drop is None else (out + out) * drop["out"]
     if relu_mask is None:
-        Xn = X + F.relu(out + out)                                    # Q2 doubling; graph_att.py:102-104
+        Xn = X + F.relu(out2)                                         # Q2 doubling; graph_att.py:102-104
     else:
         # gradient checks only: use the active set chosen by the implementation under test, so that ReLU kinks
         # (pre-activations within rounding distance of 0) do not show up as gradient differences
-        Xn = X + (out + out) * relu_mask.to(out.dtype).view_as(out)
+        Xn = X + out2 * relu_mask.to(out.dtype).view_as(out)
     if return_aux:
         return Xn, {"self_feat": sf, "P": P, "out": out}
     return Xn
@@ -178,13 +192,18 @@ def change_detector_forward(sd: Dict[str, Tensor], input_1: Tensor, input_2: Ten
                             d_bb: Tensor, q_bb: Tensor, question: Tensor, *, graph: str = "all",
                             num_heads: int = 4, nongt_dim: int = 52, pos_emb_dim: int = 64,
                             coef_sem: float = 0.333, coef_spa: float = 0.333, return_aux: bool = False,
-                            relu_masks: Optional[Sequence[Tensor]] = None):
-    """models/modules.py:169-313 (eval mode, empty_image False, feature_mode != 'mode0')."""
+                            relu_masks: Optional[Sequence[Tensor]] = None, drop: Optional[Dict] = None):
+    """models/modules.py:169-313 (eval mode, empty_image False, feature_mode != 'mode0').
+    drop: train mode with GIVEN dropout multipliers (the reference draws them from torch's generator; a test that wants
+    to compare a train-mode forward hands both sides the same ones): {'question': {...}, 'sem' / 'spa' / 'imp':
+    ({...bef}, {...aft}) as gat_relation takes them, 'ctx' / 'gate': (bef, aft) [B,N,D] (modules.py:279-287),
+    'embed': (bef, aft) [B,N,dim] (Linear -> Dropout -> ReLU, modules.py:105-111)}."""
     dt = input_1.dtype
     aux = {}
     Xb = input_1 @ sd["img.weight"].t() + sd["img.bias"]              # modules.py:195-196
     Xa = input_2 @ sd["img.weight"].t() + sd["img.bias"]
-    qv = question_vector(sd, question)                                # modules.py:200-206
+    qv = question_vector(sd, question, None if drop is None else drop["question"])        # modules.py:200-206
+    dr = (lambda key, i: None) if drop is None else (lambda key, i: drop[key][i])
     aux["qv"] = qv
     kw = dict(num_heads=num_heads, nongt_dim=nongt_dim)
     # relu_masks (gradient checks only): one [2*B*N, D] mask per relation in execution order (main rows, then
@@ -200,18 +219,18 @@ def change_detector_forward(sd: Dict[str, Tensor], input_1: Tensor, input_2: Ten
 
     if graph in ("semantic", "all"):                                  # modules.py:216-218
         mb, ma = nxt()
-        Xb = gat_relation(sd, REL_SEM, Xb, qv, d_sem_adj, None, relu_mask=mb, **kw)
-        Xa = gat_relation(sd, REL_SEM, Xa, qv, q_sem_adj, None, relu_mask=ma, **kw)
+        Xb = gat_relation(sd, REL_SEM, Xb, qv, d_sem_adj, None, relu_mask=mb, drop=dr("sem", 0), **kw)
+        Xa = gat_relation(sd, REL_SEM, Xa, qv, q_sem_adj, None, relu_mask=ma, drop=dr("sem", 1), **kw)
     if graph in ("spatial", "all", "i+s"):                            # modules.py:221-223
         mb, ma = nxt()
-        Xb = gat_relation(sd, REL_SPA, Xb, qv, d_adj, None, relu_mask=mb, **kw)
-        Xa = gat_relation(sd, REL_SPA, Xa, qv, q_adj, None, relu_mask=ma, **kw)
+        Xb = gat_relation(sd, REL_SPA, Xb, qv, d_adj, None, relu_mask=mb, drop=dr("spa", 0), **kw)
+        Xa = gat_relation(sd, REL_SPA, Xa, qv, q_adj, None, relu_mask=ma, drop=dr("spa", 1), **kw)
     if graph in ("implicit", "all", "i+s"):                           # modules.py:226-230
         pe_b = position_embedding(position_matrix(d_bb, nongt_dim), pos_emb_dim)
         pe_a = position_embedding(position_matrix(q_bb, nongt_dim), pos_emb_dim)
         mb, ma = nxt()
-        Xb = gat_relation(sd, REL_IMP, Xb, qv, None, pe_b, relu_mask=mb, **kw)
-        Xa = gat_relation(sd, REL_IMP, Xa, qv, None, pe_a, relu_mask=ma, **kw)
+        Xb = gat_relation(sd, REL_IMP, Xb, qv, None, pe_b, relu_mask=mb, drop=dr("imp", 0), **kw)
+        Xa = gat_relation(sd, REL_IMP, Xa, qv, None, pe_a, relu_mask=ma, drop=dr("imp", 1), **kw)
     emb, ema = nxt()
     # Q1: input_bef1/2/3 alias ONE tensor  (modules.py:233-247)
     if graph == "all":
@@ -225,19 +244,23 @@ def change_detector_forward(sd: Dict[str, Tensor], input_1: Tensor, input_2: Ten
     c1, g1 = sd["context1.weight"], sd["gate1.weight"]
     c2, g2 = sd["context2.weight"], sd["gate2.weight"]
 
-    def fuse(X):                                                      # modules.py:278-288
+    def fuse(X, i):                                                   # modules.py:278-288
         ctx = torch.tanh(diff @ c1.t() + X @ c2.t() + sd["context2.bias"])
         gate = torch.sigmoid(diff @ g1.t() + X @ g2.t() + sd["gate2.bias"])
+        if drop is not None:
+            ctx, gate = ctx * drop["ctx"][i], gate * drop["gate"][i]
         return gate * ctx
 
-    def pool(X, Xs, emask):                                           # modules.py:290-308
+    def pool(X, Xs, emask, i):                                        # modules.py:290-308
         pre = torch.cat([X, diff, Xs], -1) @ sd["embed.0.weight"].t() + sd["embed.0.bias"]
+        if drop is not None:
+            pre = pre * drop["embed"][i]
         e = F.relu(pre) if emask is None else pre * emask.to(pre.dtype).view_as(pre)
         att = torch.sigmoid(e @ sd["att.weight"].t() + sd["att.bias"])          # [B,N,1]
         return att.transpose(1, 2), (X * att).sum(1)
 
-    att_b, attended_1 = pool(Xb, fuse(Xb), emb)
-    att_a, attended_2 = pool(Xa, fuse(Xa), ema)
+    att_b, attended_1 = pool(Xb, fuse(Xb, 0), emb, 0)
+    att_a, attended_2 = pool(Xa, fuse(Xa, 1), ema, 1)
     input_attended = attended_2 - attended_1                          # modules.py:309
     pred = input_attended @ sd["fc1.weight"].t() + sd["fc1.bias"]     # modules.py:310
     outs = (pred.to(dt), att_b, att_a, attended_1, attended_2, input_attended)

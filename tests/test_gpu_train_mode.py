@@ -180,3 +180,86 @@ def test_every_train_forward_draws_fresh_masks(precision):
         torch.manual_seed(torch.initial_seed() + 1)
         s1 = int(rng_state(dev).item())
         assert s0 != s1, "torch.manual_seed did not re-derive the device-side dropout seed"
+
+
+def _site_mask(dev, site, p, shape):
+    """The product's own dropout multipliers of one site for the current seed (ekaid_drop_mask), on the CPU."""
+    from ekaid_b200 import lib
+    from ekaid_b200.functions import rng_state
+    n = 1
+    for s_ in shape:
+        n *= s_
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    lib.call("drop_mask", rng_state(dev).data_ptr(), site, float(p), n, out.data_ptr())
+    return out.cpu().view(*shape)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_mode_forward_and_gradients_match_oracle_on_the_same_masks(precision):
+    """Train mode with the REAL dropout probabilities: the masks every kernel derives from (seed, site, element) are read
+    back through ekaid_drop_mask and handed to the oracle, whose dropout sits where the reference's modules put it --
+    in front of every FCNet Linear (fc.py:25-32), on the doubled GAT output before the ReLU (graph_att.py:103-104), after
+    tanh / sigmoid of the fusion (modules.py:279-287), between embed's Linear and ReLU (modules.py:105-111), in front of
+    W1 and on the pooled question vector (language_model.py:141,155).  A mask applied at the wrong place, to the wrong
+    tensor or with the wrong scale shows up as an O(1) output error."""
+    from ekaid_b200 import functions
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z, meta = load_case("c1_b3_n52_all_grads")
+    sd, inp, _ = case_inputs(meta)
+    m = build_model(meta, sd, precision, dev)
+    m.train()
+    m.freeze_dropout_seed = True                  # the forward below and ekaid_drop_mask see the same seed
+    functions.DEBUG_SINK = []
+    try:
+        outs = m(*to_dev(inp, dev), setting="mode2", graph=meta["graph"])
+        relu_masks = functions.DEBUG_SINK
+    finally:
+        functions.DEBUG_SINK = None
+    B, N, D, L = meta["B"], meta["N"], 1024, inp[8].shape[1]
+    K, BN, M, dim = N, B * N, 2 * B * N, m.dim
+    halves = lambda t, *shape: (t[:t.shape[0] // 2].reshape(B, *shape), t[t.shape[0] // 2:].reshape(B, *shape))   # noqa: E731
+    drop = {"question": {"w1": _site_mask(dev, 10, m.q_att.W1_self_att_q.main[0].p, (L, B, D)).transpose(0, 1),
+                         "qv": _site_mask(dev, 11, m.q_att.drop.p, (B, D))}}
+    gats = {"sem": (m.semantic_relation.explicit_relation, 100), "spa": (m.spatial_relation.explicit_relation, 200),
+            "imp": (m.imp_relation.implicit_relation, 300)}
+    for key, (g, s0) in gats.items():
+        p_fc, p_gat = g.self_weights.main[0].p, g.dropout.p
+        assert 0.0 < p_fc < 1.0 and 0.0 < p_gat < 1.0
+        vq = halves(_site_mask(dev, s0 + 1, p_fc, (M, 2 * D)), N, 2 * D)
+        q = halves(_site_mask(dev, s0 + 2, p_fc, (M, D)), N, D)
+        k = halves(_site_mask(dev, s0 + 3, p_fc, (M, D)), N, D)
+        out = halves(_site_mask(dev, s0 + 5, p_gat, (M, D)), N, D)
+        pos = halves(_site_mask(dev, s0 + 4, p_fc, (2 * B, N * K, 64)), N * K, 64) if key == "imp" else (None, None)
+        drop[key] = tuple({"vq": vq[i], "q": q[i], "k": k[i], "out": out[i], "pos": pos[i]} for i in range(2))
+    drop["ctx"] = halves(_site_mask(dev, 20, m.dropout.p, (M, D)), N, D)
+    drop["gate"] = halves(_site_mask(dev, 21, m.dropout.p, (M, D)), N, D)
+    drop["embed"] = halves(_site_mask(dev, 22, m.embed[1].p, (M, dim)), N, dim)
+    frac = float((drop["ctx"][0] == 0).float().mean())
+    assert 0.45 < frac < 0.55 and abs(float(drop["ctx"][0].max()) - 2.0) < 1e-6        # p = 0.5, scale 1 / (1 - p)
+    cd = m.cfg.model.change_detector
+    sdg = {k_: v.clone().requires_grad_(v.is_floating_point() and k_ != "w_emb.emb_.weight") for k_, v in sd.items()}
+    ro = O.change_detector_forward(sdg, *inp, graph=meta["graph"], num_heads=cd.att_head, nongt_dim=meta["nongt_dim"],
+                                   relu_masks=relu_masks, drop=drop)
+    with torch.no_grad():
+        ev = oracle_forward(sd, inp, meta)
+    errs = {k_: rel_err(o, r) for k_, o, r in zip(OUT_NAMES[1:], outs[1:], ro[1:])}
+    print(precision, "train mode, same masks:", {k_: "%.1e" % v for k_, v in errs.items()},
+          "| eval vs train (oracle): %.2f" % rel_err(ro[3], ev[3]))
+    assert rel_err(ro[3], ev[3]) > 5e-2                       # the masks really change the result
+    for k_, e in errs.items():
+        assert e < TOL[precision], (precision, k_, e)
+    ws = loss_weights(outs)
+    sum((o * w.to(dev)).sum() for o, w in zip(outs[1:], ws)).backward()
+    sum((o * w).sum() for o, w in zip(ro[1:], ws)).backward()
+    bad = []
+    n_checked = 0
+    for k_, p in m.named_parameters():
+        g_ref = sdg[k_].grad
+        if g_ref is None or float(g_ref.abs().max()) < 1e-4 or k_ == "q_att.W2_self_att_q.main.0.bias":
+            continue
+        e = param_err(precision, k_, p.grad, {n_: t.grad for n_, t in sdg.items() if t.grad is not None}, sd)
+        n_checked += 1
+        if e > GTOL[precision]:
+            bad.append((k_, e))
+    assert n_checked > 40 and not bad, bad
