@@ -12,5 +12,6 @@ for spec in "gemm_bf16_tc_kernel:60:gemm:4" "agg_fwd_mma_kernel:3:aggfwd:1" "agg
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c $cnt -f -o gpurun_out/r02_prof_$name $CMD > gpurun_out/r02_ncu_full_$name.log 2>&1
   echo "$name rc=$?"
   ncu -i gpurun_out/r02_prof_$name.ncu-rep --page raw --csv > gpurun_out/r02_ncu_full_$name.csv 2>/dev/null
+  rm -f gpurun_out/r02_prof_$name.ncu-rep      # (gpurun brings back at most 64 MiB: keep the CSV pages only)
 done
 ls -la gpurun_out | grep r02_ | head -40
