@@ -553,10 +553,13 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
   const int dh = D / H;
   const int DS = dh + 8;                         // row pitch (elements); dh % 16 == 0 -> conflict-free ldmatrix
   constexpr int KR = NT * 8;
+  constexpr int TS = KR + 1;                     // pitch of the fp32 tile (odd: rows fall on different banks)
   bf16* Qs = (bf16*)smraw;                       // [MR][DS]
   bf16* Ks = Qs + (size_t)MR * DS;               // [KR][DS]
+  float* Ts = (float*)(Ks + (size_t)KR * DS);    // [MR][TS]: additive score terms on the way in, probabilities on the way out
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunks = dh / 8;
+#pragma unroll 1
   for (int e = tid; e < (MR + KR) * chunks; e += 256) {
     const int r = e / chunks, ch = e % chunks;
     const bool isq = r < MR;
@@ -566,106 +569,101 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
     if (ok) cp_async16(dst, QKZ + ((size_t)g * N + row) * ld + (isq ? 0 : D) + h * dh + ch * 8);
     else *(uint4*)dst = make_uint4(0, 0, 0, 0);
   }
-  // additive terms of this thread's score elements, fetched while the Q / K tiles are still in flight:
-  // score = cond > 0 ? scale * qk + pre + post : -9e15 + post   (pre = geometry bias, post = label bias; masked: pre = -inf)
-  const int mt = warp;
+  // Additive term of every score element, fetched while the Q / K tiles are still in flight, in ONE rolled loop with
+  // coalesced reads:   score = masked ? -9e15 : scale * qk + (geometry bias + label bias);   masked (cond <= 0) = -inf here.
+  // (The reference adds the label bias to the -9e15 of a masked edge as well; in fp32 that sum IS -9e15 for any bias
+  // below 2.7e8.)  The previous form -- 96 guarded scalar loads per thread in fully unrolled loops -- made this kernel
+  // 6.7 k instructions long and instruction-fetch bound (34 % of warp samples `stall_no_inst`, profiles/r02_notes.md).
   const size_t total = (size_t)N * Kn;
-  float pre[NT][4], post[NT][4];
-  if (mt * 16 < N) {
-#pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      const int i = mt * 16 + (lane >> 2) + hh * 8;
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int j = nt * 8 + 2 * (lane & 3) + c;
-          float a = 0.f, b = 0.f;
-          if (i < N && j < Kn) {
-            const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
-            if (gbias) a = gbias[ge * H + h];
-            if (cond && !(cond[ge] > 0.f)) a = -INFINITY;
-            if (lbias) b = lbias[ge];
-          }
-          pre[nt][2 * hh + c] = a;
-          post[nt][2 * hh + c] = b;
-        }
-    }
+#pragma unroll 1
+  for (int e = tid; e < N * Kn; e += 256) {
+    const int i = e / Kn, j = e - i * Kn;
+    const size_t ge = (size_t)g * total + e;
+    float a = gbias ? gbias[ge * H + h] : 0.f;
+    if (lbias) a += lbias[ge];
+    if (cond && !(cond[ge] > 0.f)) a = -INFINITY;
+    Ts[i * TS + j] = a;
   }
   cp_async_wait_all();
   __syncthreads();
-  if (mt * 16 >= N) return;
-  float acc[NT][4];
+  const int mt = warp;
+  if (mt * 16 < N) {
+    float acc[NT][4];
 #pragma unroll
-  for (int a = 0; a < NT; ++a)
+    for (int a = 0; a < NT; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-  for (int kt = 0; kt < dh / 16; ++kt) {
-    uint32_t af[4];
-    ldsm_x4(af, Qs + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DS + kt * 16 + (lane >> 4) * 8);
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll 2
+    for (int kt = 0; kt < dh / 16; ++kt) {
+      uint32_t af[4];
+      ldsm_x4(af, Qs + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * DS + kt * 16 + (lane >> 4) * 8);
 #pragma unroll
-    for (int np = 0; np < NT / 2; ++np) {
-      uint32_t bfr[4];
-      // B(k = d, n = j) = K[j][d]: stored [n][k] -> plain ldmatrix
-      ldsm_x4(bfr, Ks + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * DS + kt * 16 + ((lane >> 3) & 1) * 8);
-      mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
-      mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t bfr[4];
+        // B(k = d, n = j) = K[j][d]: stored [n][k] -> plain ldmatrix
+        ldsm_x4(bfr, Ks + (np * 16 + (lane >> 4) * 8 + (lane & 7)) * DS + kt * 16 + ((lane >> 3) & 1) * 8);
+        mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
+        mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
+      }
     }
-  }
-  const float scale = 1.0f / sqrtf((float)dh);
+    const float scale = 1.0f / sqrtf((float)dh);
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    const int i = mt * 16 + (lane >> 2) + hh * 8;
-    const bool rok = i < N;
-    float mx = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int j = nt * 8 + 2 * (lane & 3) + c;
-        float sv = -INFINITY;
-        if (rok && j < Kn) {
-          const float a = pre[nt][2 * hh + c];
-          sv = (a == -INFINITY) ? NEG_MASK_MMA : scale * acc[nt][2 * hh + c] + a;
-          sv += post[nt][2 * hh + c];
-        }
-        acc[nt][2 * hh + c] = sv;
-        mx = fmaxf(mx, sv);
-      }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float sum = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int j = nt * 8 + 2 * (lane & 3) + c;
-        const float ev = (rok && j < Kn) ? expf(acc[nt][2 * hh + c] - mx) : 0.f;
-        acc[nt][2 * hh + c] = ev;
-        sum += ev;
-      }
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-    if (rok) {
-      const float inv = 1.f / sum;
-      float* Pr = P + (((size_t)g * N + i) * H + h) * Kn;
+    for (int hh = 0; hh < 2; ++hh) {
+      const int i = mt * 16 + (lane >> 2) + hh * 8;
+      const bool rok = i < N;
+      float* Tr = Ts + i * TS + 2 * (lane & 3);
+      float mx = -INFINITY;
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const int j = nt * 8 + 2 * (lane & 3) + c;
-          if (j < Kn) {
-            const float pv = acc[nt][2 * hh + c] * inv;
-            Pr[j] = pv;
-            if (Phl) {      // bf16 hi + lo planes for the aggregation kernels (16 significant bits)
-              const bf16 hi = __float2bfloat16_rn(pv);
-              const size_t o = (((size_t)g * N + i) * H + h) * Kn + j;
-              Phl[o] = hi;
-              Phl[plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
-              if (p16) ((f16*)Phl)[2 * plane + o] = from_f32<f16>(pv);     // fp16 plane for the fp16 forward aggregation
-            }
+          float sv = -INFINITY;
+          if (rok && j < Kn) {
+            const float a = Tr[nt * 8 + c];
+            sv = (a == -INFINITY) ? NEG_MASK_MMA : scale * acc[nt][2 * hh + c] + a;
           }
+          acc[nt][2 * hh + c] = sv;
+          mx = fmaxf(mx, sv);
         }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = nt * 8 + 2 * (lane & 3) + c;
+          const float ev = (rok && j < Kn) ? expf(acc[nt][2 * hh + c] - mx) : 0.f;
+          acc[nt][2 * hh + c] = ev;
+          sum += ev;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (rok) {
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+            if (nt * 8 + 2 * (lane & 3) + c < Kn) Tr[nt * 8 + c] = acc[nt][2 * hh + c] * inv;
+      }
+    }
+  }
+  __syncthreads();
+  // probabilities out: P fp32 + the 16-bit planes the aggregation kernels stage (bf16 hi + lo = 16 significant bits for the
+  // backward, fp16 for the fp16 forward aggregation), one rolled loop, consecutive threads on consecutive keys of a row
+#pragma unroll 1
+  for (int e = tid; e < N * Kn; e += 256) {
+    const int i = e / Kn, j = e - i * Kn;
+    const float pv = Ts[i * TS + j];
+    const size_t o = (((size_t)g * N + i) * H + h) * Kn + j;
+    P[o] = pv;
+    if (Phl) {
+      const bf16 hi = __float2bfloat16_rn(pv);
+      Phl[o] = hi;
+      Phl[plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+      if (p16) ((f16*)Phl)[2 * plane + o] = from_f32<f16>(pv);
     }
   }
 }
@@ -701,45 +699,47 @@ softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dP
   }
   const size_t total = (size_t)N * Kn;
   {
-    // ds = P * (dP - <P, dP>) per query row; a warp owns rows warp, warp+8, ...  All global operands of the warp's rows
-    // are fetched before the first reduction (the per-row load -> shuffle chains were the kernel's main stall).
-    constexpr int RPW = MR / 8;                // rows per warp
+    // ds = P * (dP - <P, dP>) per query row; a warp owns rows warp, warp+8, ...  A ROLLED loop over the rows (two in flight):
+    // the fully unrolled form (all rows' guarded loads hoisted in front of the reductions, the slice loop unrolled inside)
+    // compiled to 14 k instructions -- 576 LDG, 4 k IMAD of address arithmetic -- and the kernel was instruction-fetch
+    // bound (38 % of warp samples `stall_no_inst`, profiles/r02_notes.md).
     constexpr int NR = (MR + 31) / 32;         // key columns per lane
-    float pv[RPW][NR], dpv[RPW][NR], cv[RPW][NR];
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      const int i = warp + 8 * rr;
-      const float* Pr = P + (((size_t)g * N + (i < N ? i : 0)) * H + h) * Kn;
+    const size_t sstride = (size_t)G * N * HK; // one slice of dPpart
+#pragma unroll 2
+    for (int i = warp; i < MR; i += 8) {
+      const bool iok = i < N;
+      const size_t row = (size_t)g * N + (iok ? i : 0);
+      const float* Pr = P + (row * H + h) * Kn;
+      const float* dPr = dPpart + row * HK + (size_t)h * Kn;
+      const float* cr = cond ? cond + (size_t)g * total + (size_t)(iok ? i : 0) * Kn : nullptr;
+      float pv[NR], dpv[NR], cv[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const int j = lane + 32 * r;
         float pj = 0.f, dp = 0.f, cj = 1.f;
-        if (i < N && j < Kn) {
+        if (iok && j < Kn) {
           pj = Pr[j];
-          for (int sidx = 0; sidx < nslices; ++sidx) dp += dPpart[(((size_t)sidx * G + g) * N + i) * HK + h * Kn + j];
-          if (cond) cj = cond[(size_t)g * total + (size_t)i * Kn + j];
+#pragma unroll 1
+          for (int sidx = 0; sidx < nslices; ++sidx) dp += dPr[(size_t)sidx * sstride + j];
+          if (cr) cj = cr[j];
         }
-        pv[rr][r] = pj; dpv[rr][r] = dp; cv[rr][r] = cj;
+        pv[r] = pj; dpv[r] = dp; cv[r] = cj;
       }
-    }
-#pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) {
-      const int i = warp + 8 * rr;
       float dot = 0.f;
 #pragma unroll
-      for (int r = 0; r < NR; ++r) dot = fmaf(pv[rr][r], dpv[rr][r], dot);
+      for (int r = 0; r < NR; ++r) dot = fmaf(pv[r], dpv[r], dot);
       dot = warp_sum(dot);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         const int j = lane + 32 * r;
         if (j < MR) {
           float ds = 0.f;
-          if (i < N && j < Kn) {
-            ds = pv[rr][r] * (dpv[rr][r] - dot);
+          if (iok && j < Kn) {
+            ds = pv[r] * (dpv[r] - dot);
             const size_t ge = (size_t)g * total + (size_t)i * Kn + j;
             if (dgbias) dgbias[ge * H + h] = ds;
             if (dlbias_part) dlbias_part[(size_t)h * G * total + ge] = ds;
-            if (cond && !(cv[rr][r] > 0.f)) ds = 0.f;
+            if (cond && !(cv[r] > 0.f)) ds = 0.f;
           }
           const bf16 hi = __float2bfloat16_rn(ds);
           Shi[i * SS + j] = hi;
@@ -913,7 +913,7 @@ int ek_softmax_fwd_mma_launch(const bf16* QKZ, long long ld, int D, const float*
   const int dh = D / H;
   const int MR = ((N + 15) / 16) * 16;
   const int NT = Kn <= 64 ? 8 : 16;
-  const size_t smem = (size_t)(MR + NT * 8) * (dh + 8) * sizeof(bf16);
+  const size_t smem = (size_t)(MR + NT * 8) * (dh + 8) * sizeof(bf16) + (size_t)MR * (NT * 8 + 1) * sizeof(float);
   static size_t c8 = 0, c16 = 0;
   dim3 grid(G, H);
   if (NT == 8) {

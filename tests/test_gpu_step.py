@@ -236,7 +236,50 @@ def test_int8_label_matrices_equal_the_onehot_path_bit_for_bit(case):
             # fp32 path: same kernels in the same order except the table gradient (per-label select vs fma with a one-hot).
             # 16-bit path: split-K partial sums land through fp32 atomics (order varies run to run) and a last-bit difference
             # of a wgrad feeds bf16-rounded gradients downstream; scalar gains are cancelling projections of those
-            tol = 1e-5 if precision == "fp32" else (2e-2 if k.endswith("weight_g") else 5e-3)
-            if precision != "fp32" and float(res[0][1][k].abs().max()) < 1e-3:
-                continue        # analytically zero (key bias: softmax shift invariance): rounding noise on both sides
-            assert rel_err(res[1][1][k], res[0][1][k]) < tol, (precision, k)
+            a, b = res[1][1][k].double(), res[0][1][k].double()
+            if precision == "fp32":
+                assert rel_err(a, b) < 1e-5, (precision, k)
+            elif float(b.abs().max()) >= 1e-3:      # (below: analytically zero, e.g. the key bias -- noise on both sides)
+                # run-to-run noise of the 16-bit path, in the gradient metric of the parity tests (relative L2)
+                assert float((a - b).norm() / b.norm()) < 2e-2, (precision, k)
+
+
+def test_eval_pass_and_second_model_between_training_steps_do_not_interfere():
+    """The reference's loop runs a validation pass inside training (train_mimic.py:292-345) and nothing stops a process
+    from holding two models: an eval forward of the SAME model, and a forward + backward of a SECOND ChangeDetector, between
+    two training steps must leave the training trajectory (losses, parameters) exactly as it is without them."""
+    from ekaid_b200 import functions
+    from ekaid_b200.step import GraphFusionStep, expand_adjacency, select_fields
+    from ekaid_b200.synthetic import synthetic_batch
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, _ = case_inputs(meta)
+    batches = [tuple(t.to(dev) for t in select_fields(synthetic_batch(2, 52, seed=s))) for s in (11, 12, 13)]
+    runs = {}
+    try:
+        for mode in ("plain", "interleaved"):
+            functions.GRAD_SLOTS.clear()
+            m = build_model(meta, sd, "fp32", dev)
+            m.train()
+            m.dropout_override = 0.0            # same function in both runs regardless of how often the seed advances
+            step = GraphFusionStep(m, m.cfg, lr=1e-3)
+            other = build_model(meta, sd, "fp32", dev) if mode == "interleaved" else None
+            losses = []
+            for i, b in enumerate(batches):
+                losses.append(float(step.train_step(expand_adjacency(b, m.cfg), b[9], b[10].float())))
+                if mode == "interleaved":
+                    m.eval()
+                    with torch.no_grad():
+                        ev = m(*expand_adjacency(batches[(i + 1) % 3], m.cfg)[:9])
+                    assert torch.isfinite(ev[3]).all()
+                    m.train()
+                    o = other(*expand_adjacency(b, m.cfg)[:9])          # a second model, with its own backward
+                    _loss(o).backward()
+                    assert other.img.weight.grad is not None
+                    other.zero_grad()
+            runs[mode] = (losses, {k: p.detach().clone() for k, p in m.named_parameters()})
+    finally:
+        functions.GRAD_SLOTS.clear()
+    assert runs["plain"][0] == runs["interleaved"][0]
+    for k in runs["plain"][1]:
+        assert torch.equal(runs["plain"][1][k], runs["interleaved"][1][k]), k
