@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libekaid_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "edge.cu", "edge_mma.cu", "fusion.cu", "question.cu", "gru_seq.cu", "speaker.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_skinny.cu", "edge.cu", "edge_mma.cu", "fusion.cu", "question.cu", "gru_seq.cu", "speaker.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O3"]
 

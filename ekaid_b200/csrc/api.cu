@@ -74,6 +74,8 @@ int ek_att_pool_bwd_launch(int, const float*, const float*, const float*, const 
                            long long, int, int, int, float*, void*, float*, float, cudaStream_t);
 int ek_onehot_adj_launch(const double*, int, int, int, int, float*, cudaStream_t);
 int ek_spatial_labels_launch(const double*, int, int, int, double, double, double*, cudaStream_t);
+int ek_semantic_labels_launch(const int*, int, int, int, int, const int*, const unsigned char*, const unsigned char*,
+                              const int*, const int*, int, signed char*, cudaStream_t);
 int ek_adam_launch(float*, const float*, float*, float*, long long, float, float, float, float, float, const float*,
                    int, cudaStream_t);
 int ek_adam_advance_launch(float*, float, float, cudaStream_t);
@@ -196,6 +198,7 @@ int ek_dec_outer_small_launch(const float*, long long, int, const float*, long l
                               cudaStream_t);
 
 int ek_drop_mask_launch(EkDrop, long long, float*, cudaStream_t);
+long long ek_gemm_skinny_count();
 static EkDrop mk_drop(const uint64_t* seed, uint32_t site, float p) {
   EkDrop d;
   d.seed = (p > 0.f) ? (const unsigned long long*)seed : nullptr;
@@ -244,6 +247,7 @@ int ekaid_gemm_tc(int transA, int transB, int M, int N, int K, const void* A, in
   return ek_gemm_bf16_tc_launch(transA, transB, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, to_ep(ep), force_bn,
                                 splits, (a_fp16 ? 1 : 0) | (b_fp16 ? 2 : 0), ST);
 }
+int ekaid_gemm_skinny_count(void) { return (int)(ek_gemm_skinny_count() & 0x7fffffff); }
 int ekaid_gemm_debug(int flags, void* ts) {
   ek_gemm_debug(flags, (unsigned long long*)ts);
   return EK_OK;
@@ -283,6 +287,12 @@ int ekaid_group_rowsum(int is_bf16, const void* src, int64_t ld, int N, int B, i
 int ekaid_onehot_adj(const double* labels, int B, int S, int N, int L, float* out, void* stream) {
   EK_REQUIRE(N <= S && L >= 1, EK_ERR_SHAPE, "onehot_adj: N=%d > S=%d", N, S);
   return ek_onehot_adj_launch(labels, B, S, N, L, out, ST);
+}
+int ekaid_semantic_labels(const int32_t* classes, int B, int T, int S, int ncls, const int32_t* group, const uint8_t* in_ana,
+                          const uint8_t* in_di, const int32_t* small_idx, const int32_t* small_adj, int ns, int8_t* labels,
+                          void* stream) {
+  EK_REQUIRE(B >= 0 && T >= 0 && T <= S && ncls >= 1 && ns >= 0, EK_ERR_SHAPE, "semantic_labels: T=%d S=%d ncls=%d", T, S, ncls);
+  return ek_semantic_labels_launch(classes, B, T, S, ncls, group, in_ana, in_di, small_idx, small_adj, ns, labels, ST);
 }
 int ekaid_spatial_labels(const double* boxes, int B, int N, int S, double lx, double ly, double* labels, void* stream) {
   EK_REQUIRE(B >= 0 && N >= 0 && N <= S, EK_ERR_SHAPE, "spatial_labels: N=%d > S=%d", N, S);

@@ -621,6 +621,35 @@ __global__ void spatial_labels_kernel(const double* __restrict__ boxes, int N, i
   }
 }
 
+// ---------------------------------------------------------------- semantic adjacency labels from detected classes
+// get_semantic_adj ("feature extraction/combine_dicts.py":106-151): classes int32 [B, T] (anatomy ids, then disease ids
+// offset by the anatomy count; ncls = background) -> int8 labels [B, S, S].  For the pair (a, b) = (min, max) of (i, j):
+//   1 if both classes belong to the same organ group of the knowledge graph and one is an anatomy class, the other a disease
+//     class; then, if both classes are among the co-occurrence diseases, max(co-occurrence[a-th, b-th], that value);
+// the result is written at (i, j) and (j, i) alike.  The dictionaries of the reference arrive as per-class tables.
+__global__ void semantic_labels_kernel(const int* __restrict__ cls, int T, int S, int ncls, const int* __restrict__ group,
+                                       const unsigned char* __restrict__ in_ana, const unsigned char* __restrict__ in_di,
+                                       const int* __restrict__ small_idx, const int* __restrict__ small_adj, int ns,
+                                       long long total, signed char* __restrict__ labels) {
+  ek_pdl_prologue();
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / ((long long)S * S);
+    const int ij = (int)(e % ((long long)S * S));
+    const int i = ij / S, j = ij % S;
+    int v = 0;
+    if (i < T && j < T) {
+      const int ca = cls[b * T + min(i, j)], cb = cls[b * T + max(i, j)];
+      if (ca >= 0 && cb >= 0 && ca < ncls && cb < ncls) {
+        if (group[ca] == group[cb] && ((in_ana[ca] && in_di[cb]) || (in_ana[cb] && in_di[ca]))) v = 1;
+        const int sa = small_idx[ca], sb = small_idx[cb];
+        if (sa >= 0 && sb >= 0) v = max(small_adj[sa * ns + sb], v);
+      }
+    }
+    labels[e] = (signed char)v;
+  }
+}
+
 // ---------------------------------------------------------------- Adam (utils/utils.py:96-99 -> torch.optim.Adam)
 __device__ __forceinline__ void adam_one(float& pv, float gr, float& mv, float& vv, float lr_bc1, float rs_bc2, float b1,
                                          float b2, float eps, float wd) {
@@ -1198,6 +1227,17 @@ int ek_spatial_labels_launch(const double* boxes, int B, int N, int S, double lx
   const long long total = (long long)B * S * S;
   if (total == 0) return EK_OK;
   ek_launch(spatial_labels_kernel, grid_for(total), 256, 0, st, boxes, N, S, (lx + ly) / 3., total, labels);
+  EK_CHECK_LAUNCH();
+  return EK_OK;
+}
+
+int ek_semantic_labels_launch(const int* cls, int B, int T, int S, int ncls, const int* group, const unsigned char* in_ana,
+                              const unsigned char* in_di, const int* small_idx, const int* small_adj, int ns,
+                              signed char* labels, cudaStream_t st) {
+  const long long total = (long long)B * S * S;
+  if (total == 0) return EK_OK;
+  ek_launch(semantic_labels_kernel, grid_for(total), 256, 0, st, cls, T, S, ncls, group, in_ana, in_di, small_idx,
+            small_adj, ns, total, labels);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

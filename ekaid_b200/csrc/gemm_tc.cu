@@ -882,6 +882,12 @@ int launch_bn(int bn, int cl, const CUtensorMap& ta, const CUtensorMap& tb, int 
 
 }  // namespace
 
+// gemm_skinny.cu: the M <= 64 form (answer decoder's per-step products)
+int ek_gemm_skinny_ok(int transA, int transB, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb,
+                      const EkEpilogue& ep, int fmt);
+int ek_gemm_skinny_launch(int transB, int M, int N, int K, const bf16* A, long long lda, const bf16* B, long long ldb,
+                          const EkEpilogue& ep, int fmt, int splits_req, cudaStream_t st);
+
 // transA: A stored [K, M];  transB: B stored [K, N]  (see file header)
 void ek_gemm_debug(int flags, unsigned long long* ts) {
   g_dbg_flags = flags;
@@ -893,6 +899,9 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
                            long long ldb, const EkEpilogue& ep, int force_bn, int splits, int fmt, cudaStream_t stream) {
   const int flags = fmt & (GF_A_F16 | GF_B_F16);
   EK_REQUIRE(M > 0 && N > 0 && K > 0, EK_ERR_SHAPE, "gemm_tc: bad shape M=%d N=%d K=%d", M, N, K);
+  // at most 64 rows: half of a 128-row tcgen05 tile would be empty and its fixed costs dominate -> the lean warp-MMA form
+  if (force_bn == 0 && g_dbg_flags == 0 && ek_gemm_skinny_ok(transA, transB, M, N, K, A, lda, B, ldb, ep, fmt))
+    return ek_gemm_skinny_launch(transB, M, N, K, A, lda, B, ldb, ep, fmt, splits, stream);
   // force_bn = 1000 + width selects the CTA-pair (cluster of 2, multicast B) variant of that width.  It is NOT the
   // default: measured on B200 it is no faster than independent CTAs (L2 already merges the two CTAs' requests for the
   // same B tile), and the lock-step coupling costs ~10-40 % on some shapes (profiles/r01_notes.md).

@@ -1535,6 +1535,35 @@ def spatial_labels(boxes: torch.Tensor, size: int = 100, lx: float = 1024.0, ly:
     return out
 
 
+def semantic_tables(ana_classes, di_classes, kg_ana: dict, small_name2index: dict, small_adj, device):
+    """The reference's dictionaries ("feature extraction/combine_dicts.py":106-151: class-name lists, knowledge-graph organ
+    of every class, the co-occurrence matrix of the CheXpert diseases and its name index) as the per-class device tables
+    `semantic_labels` takes."""
+    names = list(ana_classes) + list(di_classes)
+    organs = {o: k for k, o in enumerate(sorted({kg_ana[n] for n in names}))}
+    ana_set, di_set = set(ana_classes), set(di_classes)
+    t = lambda x, dt: torch.tensor(x, dtype=dt, device=device)      # noqa: E731
+    return {"ncls": len(names), "group": t([organs[kg_ana[n]] for n in names], torch.int32),
+            "in_ana": t([n in ana_set for n in names], torch.uint8), "in_di": t([n in di_set for n in names], torch.uint8),
+            "small_idx": t([small_name2index.get(n.lower(), -1) for n in names], torch.int32),
+            "small_adj": torch.as_tensor(small_adj).to(device=device, dtype=torch.int32).contiguous()}
+
+
+def semantic_labels(classes: torch.Tensor, tables: dict, size: int = 100) -> torch.Tensor:
+    """get_semantic_adj ("feature extraction/combine_dicts.py":106-151) as one kernel: detected classes [B,T] (anatomy ids,
+    then disease ids offset by the anatomy count; tables['ncls'] = background) -> int8 labels [B,S,S], S = max(size, T)."""
+    lib.require_device()
+    cls = classes.detach().to(torch.int32).contiguous()
+    Bn, T = cls.shape
+    S = max(int(size), T)
+    out = torch.empty(Bn, S, S, dtype=torch.int8, device=cls.device)
+    sa = tables["small_adj"]
+    call("semantic_labels", cls.data_ptr(), Bn, T, S, int(tables["ncls"]), tables["group"].data_ptr(),
+         tables["in_ana"].data_ptr(), tables["in_di"].data_ptr(), tables["small_idx"].data_ptr(), sa.data_ptr(),
+         int(sa.shape[0]), out.data_ptr())
+    return out
+
+
 def onehot_adj(labels: torch.Tensor, num_objects: int, label_num: int) -> torch.Tensor:
     """process_matrix (utils/mimic_utils.py:141-149) as one kernel: labels [B,S,S] (any real dtype) on the device
     -> fp32 one-hot [B,N,N,L]."""

@@ -112,6 +112,9 @@ int ekaid_gemm_tc(int transA, int transB, int M, int N, int K, const void* A, in
  * 32 = no TMA loads, 64 = no MMAs, 256 = no TMEM drain; results are then garbage), 128 = early programmatic-launch
  * trigger; ts = device buffer of grid x 32 uint64 globaltimer stamps or NULL.  0 / NULL restores normal operation. */
 int ekaid_gemm_debug(int flags, void* ts);
+/* how many products ekaid_gemm_tc has routed to the M <= 64 warp-MMA kernel (gemm_skinny.cu) so far: the answer decoder's
+ * per-step products, models/dynamic_speaker_change_pos.py:94-131 (tests; EKAID_B200_SKINNY=0 turns the routing off) */
+int ekaid_gemm_skinny_count(void);
 
 /* ---- casts / reductions / glue -------------------------------------------------------------------------- */
 int ekaid_cast_f32_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int64_t rows, int cols, void* stream);
@@ -158,6 +161,14 @@ int ekaid_onehot_adj(const double* labels, int B, int S, int N, int L, float* ou
  * (0 = far, 1 inside, 2 cover, 3 IoU >= 0.5, 4..11 = 45-degree sector; entry (j,i), j > i, = reverse_type of (i,j);
  * rows / columns >= N are 0).  lx, ly: image extent (1024 x 1024 in the reference); "far" = (lx+ly)/3 */
 int ekaid_spatial_labels(const double* boxes, int B, int N, int S, double lx, double ly, double* labels, void* stream);
+/* get_semantic_adj ("feature extraction/combine_dicts.py":106-151): detected classes int32 [B,T] (anatomy ids, then disease
+ * ids offset by the anatomy count; ncls = background) -> int8 labels [B,S,S] (the HDF5 `semantic_adj_matrix` layout): 1 for an
+ * anatomy / disease pair of the same organ group, raised to the disease co-occurrence value where both classes have one.
+ * The reference's dictionaries arrive as per-class tables: group [ncls], in_ana / in_di [ncls] (0/1), small_idx [ncls]
+ * (-1 = not a co-occurrence disease), small_adj [ns*ns]. */
+int ekaid_semantic_labels(const int32_t* classes, int B, int T, int S, int ncls, const int32_t* group, const uint8_t* in_ana,
+                          const uint8_t* in_di, const int32_t* small_idx, const int32_t* small_adj, int ns, int8_t* labels,
+                          void* stream);
 
 /* ---- relation-aware graph attention (models/graph_att.py:53-106, models/graph_att_layer.py:60-178) ------- */
 /* cond[g,i,j] = sum_c adj[g,j,i,c], lbias[g,i,j] = sum_c adj[g,j,i,c] w[c]   (graph_att.py:76,88-92; Q2,Q5) */

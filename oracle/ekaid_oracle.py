@@ -316,6 +316,32 @@ def spatial_adj_matrix(boxes, size: int = 100, lx: float = 1024.0, ly: float = 1
     return out
 
 
+def semantic_adj_matrix(pred_classes, ana_classes, di_classes, kg_ana, small_adj, small_name2index, size: int = 100):
+    """get_semantic_adj ("feature extraction/combine_dicts.py":106-151) pair by pair like the reference: pred_classes
+    [B, T] ints (anatomy ids, then disease ids already offset by len(ana_classes); len(ana) + len(di) = background)
+    -> int64 [B, S, S].  Pinned by tests/golden/semantic_labels.npz (made by the reference's own function)."""
+    import numpy as np
+    thing = list(ana_classes) + list(di_classes)
+    ana_set, di_set = set(ana_classes), set(di_classes)
+    pred = np.asarray(pred_classes)
+    B, T = pred.shape
+    S = max(size, T)
+    out = np.zeros([B, S, S], dtype=np.int64)
+    for b in range(B):
+        pc = pred[b]
+        for i in range(T):
+            for j in range(i, T):
+                if pc[i] == len(thing) or pc[j] == len(thing):
+                    continue
+                ni, nj = thing[pc[i]], thing[pc[j]]
+                if kg_ana[ni] == kg_ana[nj] and ((ni in ana_set and nj in di_set) or (nj in ana_set and ni in di_set)):
+                    out[b, i, j] = out[b, j, i] = 1
+                if ni.lower() in small_name2index and nj.lower() in small_name2index:
+                    v = max(small_adj[small_name2index[ni.lower()], small_name2index[nj.lower()]], out[b, i, j])
+                    out[b, i, j] = out[b, j, i] = v
+    return torch.from_numpy(out)
+
+
 # ----------------------------------------------------------------------------------------------
 # answer decoder (boundary consumer) -- greedy decode used for the arg-max token parity check
 # ----------------------------------------------------------------------------------------------

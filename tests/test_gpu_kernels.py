@@ -295,3 +295,64 @@ def test_gemm_fp32_split3_on_tensor_cores(transA, transB, M, N, K, monkeypatch):
     assert torch.equal(P[:, 256:512], P[:, 512:]) and float((P[:, :256] + P[:, 256:512] - X).abs().max() / X.abs().max()) < 2 ** -16
     Q = functions._split3(X, 64, 256, 1, 1).float()
     assert torch.equal(Q[:64], Q[128:]) and torch.equal(Q[:64], P[:, 256:512]) and torch.equal(Q[64:128], P[:, :256])
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("transB", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(64, 6656, 512), (64, 2048, 1536), (3, 1024, 2048), (64, 512, 6656), (1, 148, 512),
+                                   (64, 1536, 2048), (17, 304, 72)])
+def test_gemm_skinny_rows(dtype, transB, M, N, K):
+    """Products with at most 64 rows (the answer decoder's per-step GEMMs) take the warp-MMA kernel (gemm_skinny.cu): plain
+    output (split-K), fused epilogue (bias + addend + activation, fp32 and 16-bit outputs), both weight layouts, both 16-bit
+    formats; same results as the tcgen05 kernel and as the fp64 product."""
+    from ekaid_b200 import lib
+    from ekaid_b200.functions import gemm, ACT_RELU, ACT_SIGMOID
+    dev = _dev()
+    so = lib.load()
+    if transB and N % 8:
+        pytest.skip("N-contiguous weights need 16-byte rows")
+    A = _mk((M, K), dev, 21, dtype)
+    B = _mk((K, N) if transB else (N, K), dev, 22, dtype)
+    bias = _mk((N,), dev, 23, torch.float32)
+    add = _mk((M, N), dev, 24, torch.float32)
+    prod = A.double() @ (B.double() if transB else B.double().t())
+    scale = float(prod.abs().max())
+    n0 = so.ekaid_gemm_skinny_count()
+    C = torch.full((M, N), float("nan"), device=dev)
+    gemm(A, B, M, N, K, 0, transB, C=C)                                    # plain: may split K
+    assert so.ekaid_gemm_skinny_count() == n0 + 1
+    assert float((C.double() - prod).abs().max()) / scale < 1e-5
+    Ct = torch.full((M, N), float("nan"), device=dev)
+    gemm(A, B, M, N, K, 0, transB, C=Ct, force_bn=64)                      # the tcgen05 kernel on the same operands
+    assert so.ekaid_gemm_skinny_count() == n0 + 1
+    assert float((C - Ct).abs().max()) / scale < 1e-5
+    C2 = torch.full((M, N), float("nan"), device=dev)
+    Cb = torch.full((M, N), float("nan"), device=dev, dtype=dtype)
+    gemm(A, B, M, N, K, 0, transB, bias=bias, addend=add, act=ACT_RELU, C=C2, Cb=Cb)
+    ref = torch.relu(prod + bias.double() + add.double())
+    assert so.ekaid_gemm_skinny_count() == n0 + 2
+    assert float((C2.double() - ref).abs().max()) / scale < 1e-5
+    assert float((Cb.double() - ref).abs().max()) / scale < (1e-2 if dtype == torch.bfloat16 else 2e-3)
+    C3 = add.clone()
+    gemm(A, B, M, N, K, 0, transB, addend=C3, act=ACT_SIGMOID, C=C3)       # in place: C = act(C + A B)
+    assert float((C3.double() - torch.sigmoid(prod + add.double())).abs().max()) < 1e-5
+
+
+def test_semantic_labels_from_classes_golden():
+    """semantic_labels kernel (get_semantic_adj, "feature extraction/combine_dicts.py":106-151): bit-identical to labels made
+    by the reference's own function; background detections, classes present in both name lists, asymmetric co-occurrence
+    values are all in the fixture; the result feeds the relation encoders as it is (int8 label matrix)."""
+    import json
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    from ekaid_b200.functions import onehot_adj, semantic_labels, semantic_tables
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    z = np.load(os.path.join(GOLDEN, "semantic_labels.npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    tables = semantic_tables(meta["ana"], meta["di"], meta["kg"], meta["name2idx"], z["small_adj"], dev)
+    got = semantic_labels(torch.from_numpy(z["classes"]).to(dev), tables)
+    assert got.dtype == torch.int8 and got.shape == (6, 100, 100)
+    assert torch.equal(got.cpu(), torch.from_numpy(z["labels"]))
+    assert torch.equal(onehot_adj(got, 52, 3).cpu(), O.process_matrix(torch.from_numpy(z["labels"]).double(), 52, 3))

@@ -114,3 +114,20 @@ def test_spatial_labels_scalar_vs_vectorised_on_integer_boxes(seed):
     upper = torch.triu(torch.ones(24, 24, dtype=torch.bool), 1)
     assert torch.equal(lab.transpose(1, 2)[:, upper], _REVERSE[lab[:, upper]])
     assert len(torch.unique(lab)) >= 8                    # the draw exercises most label values
+
+
+def test_semantic_adjacency_oracle_matches_reference_labels():
+    """oracle.semantic_adj_matrix (get_semantic_adj, "feature extraction/combine_dicts.py":106-151) against labels made by
+    the reference's own function (tests/golden/make_semantic_golden.py)."""
+    import json
+    import os
+    import numpy as np
+    import torch
+    from helpers import GOLDEN
+    from oracle import ekaid_oracle as O
+    z = np.load(os.path.join(GOLDEN, "semantic_labels.npz"), allow_pickle=False)
+    meta = json.loads(str(z["meta"]))
+    got = O.semantic_adj_matrix(z["classes"], meta["ana"], meta["di"], meta["kg"], z["small_adj"], meta["name2idx"])
+    assert got.shape == (6, 100, 100)
+    assert torch.equal(got, torch.from_numpy(z["labels"].astype(np.int64)))
+    assert int(got.max()) == 2 and torch.equal(got, got.transpose(1, 2))
