@@ -194,7 +194,7 @@ int ek_dec_token_launch(const float*, long long, int, int, int, int, long long*,
 int ek_dec_nll_launch(const float*, long long, int, int, int, const long long*, long long, const float*, long long, int, float*,
                       int, float*, const float*, const float*, void*, long long, int, int*, cudaStream_t);
 int ek_dec_nll_reduce_launch(const float*, int, const float*, long long, int, int, float*, cudaStream_t);
-int ek_dec_outer_small_launch(const float*, long long, int, const float*, long long, int, int, float*, long long, int,
+int ek_dec_outer_small_launch(const float*, long long, int, const float*, long long, int, int, float*, int, int,
                               cudaStream_t);
 
 int ek_drop_mask_launch(EkDrop, long long, float*, cudaStream_t);
@@ -589,8 +589,8 @@ int ekaid_dec_nll_reduce(const float* row_loss, int rows, const float* masks, in
                          void* stream) {
   return ek_dec_nll_reduce_launch(row_loss, rows, masks, msb, B, T, res, ST);
 }
-int ekaid_dec_outer_small(const float* a, int64_t lda, int m, const float* b, int64_t ldb, int n, int rows, float* out,
-                          int64_t ldo, int transpose_out, void* stream) {
-  return ek_dec_outer_small_launch(a, lda, m, b, ldb, n, rows, out, ldo, transpose_out, ST);
+int ekaid_dec_outer_small(const float* a, int64_t lda, int m, const float* b, int64_t ldb, int n, int rows, float* part,
+                          int nchunks, int transpose_out, void* stream) {
+  return ek_dec_outer_small_launch(a, lda, m, b, ldb, n, rows, part, nchunks, transpose_out, ST);
 }
 }  // extern "C"

@@ -463,27 +463,38 @@ dec_nll_reduce_kernel(const float* __restrict__ row_loss, int rows, const float*
 }
 
 // ---------------------------------------------------------------- tiny weight gradients
-// out[i, j] = sum_r a[r * lda + i] * b[r * ldb + j]   (i < m <= 16; transpose_out: stored at out[j * ldo + i])
+// part[c][i, j] = sum_{r in chunk c} a[r * lda + i] * b[r * ldb + j]   (i < m <= 16; transpose_out: stored as [j, i]).
+// The rows are split over gridDim.y chunks; the caller adds the chunks up with the deterministic column-sum kernel.
 __global__ void dec_outer_small_kernel(const float* __restrict__ a, long long lda, int m, const float* __restrict__ bm,
-                                       long long ldb, int n, int rows, float* __restrict__ out, long long ldo,
-                                       int transpose_out) {
+                                       long long ldb, int n, int rows, float* __restrict__ part, int transpose_out) {
   ek_pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+  const int per = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+  __shared__ float as[64][16];
   float acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const float bv = bm[r * ldb + j];
+  for (int rb = r0; rb < r1; rb += 64) {
+    const int nr = min(64, r1 - rb);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * m; e += blockDim.x) as[e / m][e % m] = a[(long long)(rb + e / m) * lda + e % m];
+    __syncthreads();
+    if (j < n)
+      for (int r = 0; r < nr; ++r) {
+        const float bv = bm[(long long)(rb + r) * ldb + j];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < m) acc[i] = fmaf(a[r * lda + i], bv, acc[i]);
+        for (int i = 0; i < 16; ++i)
+          if (i < m) acc[i] = fmaf(as[r][i], bv, acc[i]);
+      }
   }
+  if (j >= n) return;
+  float* p = part + (long long)blockIdx.y * m * n;
 #pragma unroll
   for (int i = 0; i < 16; ++i)
     if (i < m) {
-      if (transpose_out) out[j * ldo + i] = acc[i];
-      else out[i * ldo + j] = acc[i];
+      if (transpose_out) p[(long long)j * m + i] = acc[i];
+      else p[(long long)i * n + j] = acc[i];
     }
 }
 
@@ -601,10 +612,11 @@ int ek_dec_nll_reduce_launch(const float* row_loss, int rows, const float* masks
   EK_CHECK_LAUNCH();
   return EK_OK;
 }
-int ek_dec_outer_small_launch(const float* a, long long lda, int m, const float* b, long long ldb, int n, int rows, float* out,
-                              long long ldo, int transpose_out, cudaStream_t s) {
-  EK_REQUIRE(m >= 1 && m <= 16, EK_ERR_SHAPE, "dec_outer_small: m=%d (1..16)", m);
-  ek_launch(dec_outer_small_kernel, (n + 127) / 128, 128, 0, s, a, lda, m, b, ldb, n, rows, out, ldo, transpose_out);
+int ek_dec_outer_small_launch(const float* a, long long lda, int m, const float* b, long long ldb, int n, int rows,
+                              float* part, int nchunks, int transpose_out, cudaStream_t s) {
+  EK_REQUIRE(m >= 1 && m <= 16 && nchunks >= 1, EK_ERR_SHAPE, "dec_outer_small: m=%d (1..16) chunks=%d", m, nchunks);
+  ek_launch(dec_outer_small_kernel, dim3((n + 127) / 128, nchunks), 128, 0, s, a, lda, m, b, ldb, n, rows, part,
+            transpose_out);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

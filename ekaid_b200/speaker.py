@@ -392,9 +392,16 @@ class SpeakerSeqFn(torch.autograd.Function):
         # the three tiny layers
         dW_fc, dW_wp = slot("core.weight_fc.0.weight", 3, R), slot("core.weight_pos.weight", 16, 512)
         dW_p2 = slot("core.pos2.weight", R, 16)
-        call("dec_outer_small", DFC.data_ptr(), 4, 3, HMf[B:].data_ptr(), R, R, TB, dW_fc.data_ptr(), R, 0)
-        call("dec_outer_small", DDPOS.data_ptr(), 16, 16, VPOS.data_ptr(), 512, 512, TB, dW_wp.data_ptr(), 512, 0)
-        call("dec_outer_small", PW.data_ptr(), 16, 16, DGI2.data_ptr(), R + D, R, TB, dW_p2.data_ptr(), 16, 1)
+        nck = max(1, min(64, TB // 32))            # row chunks: partial sums, then the deterministic column-sum kernel
+
+        def outer_small(a, lda, m, bmat, ldb, n, out, transpose):
+            part = f32(nck, m * n)
+            call("dec_outer_small", a.data_ptr(), lda, m, bmat.data_ptr(), ldb, n, TB, part.data_ptr(), nck, transpose)
+            colsum(part, nck, m * n, out=out.view(-1))
+
+        outer_small(DFC, 4, 3, HMf[B:], R, R, dW_fc, 0)
+        outer_small(DDPOS, 16, 16, VPOS, 512, 512, dW_wp, 0)
+        outer_small(PW, 16, 16, DGI2, R + D, R, dW_p2, 1)
         db_fc = slot("core.weight_fc.0.bias", 3)
         db_fc.copy_(colsum(DFC, TB, 4)[:3])
         db_wp = colsum(DDPOS, TB, 16, out=slot("core.weight_pos.bias", 16))

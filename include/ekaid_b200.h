@@ -418,9 +418,10 @@ int ekaid_dec_nll(const float* logits, int64_t ldl, int rows, int B, int V, cons
 /* res[0] = sum(row_loss) / sum(mask), res[1] = 1 / sum(mask), mask = masks[:, 1 .. T] */
 int ekaid_dec_nll_reduce(const float* row_loss, int rows, const float* masks, int64_t msb, int B, int T, float* res,
                          void* stream);
-/* out[i, j] = sum_r a[r, i] b[r, j], i < m <= 16 (weight gradients of weight_fc, weight_pos, pos2) */
-int ekaid_dec_outer_small(const float* a, int64_t lda, int m, const float* b, int64_t ldb, int n, int rows, float* out,
-                          int64_t ldo, int transpose_out, void* stream);
+/* part[c][i, j] = sum over the rows of chunk c of a[r, i] b[r, j], i < m <= 16 (weight gradients of weight_fc, weight_pos,
+ * pos2; part is [nchunks, m*n], stored [j, i] per chunk when transpose_out; ekaid_colsum over the chunks finishes it) */
+int ekaid_dec_outer_small(const float* a, int64_t lda, int m, const float* b, int64_t ldb, int n, int rows, float* part,
+                          int nchunks, int transpose_out, void* stream);
 
 #ifdef __cplusplus
 }

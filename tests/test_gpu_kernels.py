@@ -335,7 +335,8 @@ def test_gemm_skinny_rows(dtype, transB, M, N, K):
     assert float((Cb.double() - ref).abs().max()) / scale < (1e-2 if dtype == torch.bfloat16 else 2e-3)
     C3 = add.clone()
     gemm(A, B, M, N, K, 0, transB, addend=C3, act=ACT_SIGMOID, C=C3)       # in place: C = act(C + A B)
-    assert float((C3.double() - torch.sigmoid(prod + add.double())).abs().max()) < 1e-5
+    # sigmoid' <= 1/4: the 1e-5 * scale bound on the pre-activation carries over with that factor
+    assert float((C3.double() - torch.sigmoid(prod + add.double())).abs().max()) < 0.25e-5 * scale + 2e-6
 
 
 def test_semantic_labels_from_classes_golden():
