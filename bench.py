@@ -63,14 +63,14 @@ def peaks():
 
 def gemm_traffic_profile(args):
     """DRAM bytes per tcgen05 GEMM launch of the default workload, from the committed ncu capture of this command
-    (profiles/r01_v14_gemm_traffic.json, made by scripts/gemm_traffic.py); None for any other workload."""
-    p = os.path.join(ROOT, "profiles", "r01_v14_gemm_traffic.json")
+    (profiles/r02_gemm_traffic.json, made by scripts/gemm_traffic.py); None for any other workload."""
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     default = (args.batch, args.nodes, args.mode, args.precision, args.graph, args.qlen) == (64, 52, "train", "bf16", "all", 20)
     if not default or args.no_dropout or not os.path.exists(p):
         return None
     d = json.load(open(p))
     d["note"] = ("ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over %d GEMM launches (%d per step) of "
-                 "`bench.py --steps 1 --warmup 1 --no-graph`: profiles/r01_v14_gemm_traffic.json"
+                 "`bench.py --steps 1 --warmup 1 --no-graph`: profiles/r02_gemm_traffic.json"
                  % (d["launches"], d["launches_per_step"]))
     return d
 
