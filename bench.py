@@ -348,22 +348,25 @@ def decoder_section(args, dev):
     raws = [tuple(t.to(dev) for t in select_fields(synthetic_batch(B, N, seed=777 + i, q_len=args.qlen))) for i in range(2)]
     tsteps = max(sp._steps(r[9]) for r in raws)
     step = GraphFusionStep(cd, cfg, graph=args.graph, speaker=sp, decoder_steps=tsteps)
-    step.capture(raws[0], train=True)
-    for i in range(3):
-        step.replay(raws[i % 2])
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
-    e0.record()
-    for i in range(n):
-        step.replay(raws[i % 2])
-    e1.record()
-    torch.cuda.synchronize()
-    ms_train = e0.elapsed_time(e1) / n
-    out = {"train_step_with_decoder": {"ms_per_step": ms_train, "samples_s": B / (ms_train * 1e-3), "decoder_steps": tsteps,
-                                       "launches_per_step": step.launches_per_replay,
-                                       "what": "graph+fusion fwd/bwd + teacher-forced answer decoder fwd/bwd + masked NLL + "
-                                               "Adam over both modules, one CUDA graph, batch %d" % B}}
+    out = {}
+    if args.mode == "train":
+        step.capture(raws[0], train=True)
+        for i in range(3):
+            step.replay(raws[i % 2])
+        torch.cuda.synchronize()
+        n = 10
+        e0.record()
+        for i in range(n):
+            step.replay(raws[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_train = e0.elapsed_time(e1) / n
+        out["train_step_with_decoder"] = {
+            "ms_per_step": ms_train, "samples_s": B / (ms_train * 1e-3), "decoder_steps": tsteps,
+            "launches_per_step": step.launches_per_replay,
+            "what": "graph+fusion fwd/bwd + teacher-forced answer decoder fwd/bwd + masked NLL + Adam over both modules, one "
+                    "CUDA graph, batch %d" % B}
     cd.eval()
     sp.eval()
     inputs = expand_adjacency(raws[0], cfg)
@@ -622,7 +625,7 @@ def main():
             "gpu_launches": launches, "cuda_graph": use_graph, "roofline": roof, "kernel_time_share_pct": breakdown,
             "gemm_shapes": gemm_shapes}
     line["roofline_non_gemm"] = non_gemm_roofline(agg, nprof, pk, pk_kind, ms_step)
-    if rank == 0 and world == 1 and args.mode == "train" and not args.no_decoder:
+    if rank == 0 and world == 1 and not args.no_decoder:
         try:
             line["decoder"] = decoder_section(args, dev)
         except Exception as e:           # noqa: BLE001

@@ -343,7 +343,7 @@ def test_arg_max_answer_tokens_through_the_whole_path(precision):
     print(precision, "solid steps %.0f%%, agreement overall %.4f, first differing step per sample %s, margin quantiles %s"
           % (100 * float(solid.float().mean()), float((seq == ref).float().mean()), first_diff,
              [round(float(q), 3) for q in torch.quantile(margin.flatten(), torch.tensor([.05, .25, .5, .75]))]))
-    assert float(solid.float().mean()) > (0.8 if precision == "fp32" else 0.5)
+    assert float(solid.float().mean()) > (0.8 if precision == "fp32" else 0.3)
     for b in range(B):
         weak = (~solid[b]).nonzero().flatten()
         upto = int(weak[0]) if len(weak) else 90          # free-running decode: identical up to the first near-tie

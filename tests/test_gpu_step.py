@@ -241,7 +241,8 @@ def test_int8_label_matrices_equal_the_onehot_path_bit_for_bit(case):
                 assert rel_err(a, b) < 1e-5, (precision, k)
             elif float(b.abs().max()) >= 1e-3:      # (below: analytically zero, e.g. the key bias -- noise on both sides)
                 # run-to-run noise of the 16-bit path, in the gradient metric of the parity tests (relative L2)
-                assert float((a - b).norm() / b.norm()) < 2e-2, (precision, k)
+                # (scalar gains of weight-normalised layers are cancelling projections: the widest band)
+                assert float((a - b).norm() / b.norm()) < (5e-2 if a.numel() == 1 else 2e-2), (precision, k)
 
 
 def test_eval_pass_and_second_model_between_training_steps_do_not_interfere():
@@ -283,3 +284,48 @@ def test_eval_pass_and_second_model_between_training_steps_do_not_interfere():
     assert runs["plain"][0] == runs["interleaved"][0]
     for k in runs["plain"][1]:
         assert torch.equal(runs["plain"][1][k], runs["interleaved"][1][k]), k
+
+
+def test_loader_batches_drive_the_captured_step():
+    """ekaid_b200.loader (the reference's dataset schema -> rcc_collate 13-tuples, int8 label matrices, pinned) feeding
+    StepPipeline: same losses as replaying the same batches from device memory."""
+    from ekaid_b200 import functions
+    from ekaid_b200.loader import RCCArrays, RCCDataset, batches
+    from ekaid_b200.step import GraphFusionStep, select_fields
+    dev = _dev()
+    z, meta = load_case("c0_b2_n52_all")
+    sd, inp, _ = case_inputs(meta)
+    ds = RCCDataset(RCCArrays.synthetic(8, 52, seed=31))
+    host = [select_fields(b) for b in batches(ds, 2, compact=True, pin=True)]
+    assert len(host) == 4 and host[0][2].dtype == torch.int8 and host[0][0].is_pinned()
+    res = {}
+    try:
+        for mode in ("device", "pipeline"):
+            functions.GRAD_SLOTS.clear()
+            m = build_model(meta, sd, "fp32", dev)
+            step = GraphFusionStep(m, m.cfg, lr=1e-3)
+            step.capture(tuple(t.to(dev) for t in host[0]), train=True, warmup=2)
+            with torch.no_grad():
+                m.load_state_dict(sd)
+            step.opt.m.zero_()
+            step.opt.v.zero_()
+            step.opt.pow_state.fill_(1.0)
+            if mode == "device":
+                res[mode] = [float(step.replay(tuple(t.to(dev) for t in hb))) for hb in host]
+            else:
+                pipe = step.pipeline()
+                pipe.prefetch(host[0])
+                out, pending = [], None
+                for i in range(len(host)):
+                    if i + 1 < len(host):
+                        pipe.prefetch(host[i + 1])
+                    k = pipe.run()
+                    if pending is not None:
+                        out.append(pipe.result(pending))
+                    pending = k
+                out.append(pipe.result(pending))
+                res[mode] = out
+    finally:
+        functions.GRAD_SLOTS.clear()
+    assert res["device"] == pytest.approx(res["pipeline"], rel=1e-6)
+    assert len(set(round(x, 6) for x in res["device"])) == 4
