@@ -536,7 +536,7 @@ class DynamicSpeaker(nn.Module):
         B, dev = feat_bef.shape[0], feat_bef.device
         T = self.seq_length
         ce = check_every if check_every and check_every > 0 else T + 1
-        key = (B, str(dev), self.precision, ce, bool(use_graph), self.logit.weight.data_ptr())
+        key = (B, str(dev), self.precision, ce, bool(use_graph), T, self.logit.weight.data_ptr())
         r = self._runners.get(key)
         if r is None:
             if len(self._runners) > 4:

@@ -156,6 +156,59 @@ def test_loader_schema_round_trip_and_sample_rules(tmp_path):
         RCCArrays.from_hdf5("a.h5", "b.h5")                       # no h5py in this image: loud, not emulated
 
 
+def test_speaker_constructor_state_dict_and_host_logic():
+    """ekaid_b200.speaker.DynamicSpeaker on the CPU: the reference's parameter tree (tests/golden/speaker_spec.json, made from
+    the reference's own module), the step count of its teacher-forcing loop (dynamic_speaker_change_pos.py:210-214), the
+    entry points that are deliberately not implemented, and a loud failure without a GPU."""
+    from helpers import speaker_spec
+    from ekaid_b200 import lib
+    from ekaid_b200.config import default_cfg
+    from ekaid_b200.speaker import DynamicSpeaker, LanguageModelCriterion
+    from oracle import ekaid_oracle as O
+    cfg = default_cfg("all")
+    with contextlib.redirect_stdout(io.StringIO()):
+        sp = DynamicSpeaker(cfg, vocab_size=148)
+    assert {k: tuple(v.shape) for k, v in sp.state_dict().items()} == speaker_spec()
+    h, c = sp.init_hidden(5)
+    assert h.shape == (2, 5, 512) and c.shape == (2, 5, 512) and float(h.abs().max()) == 0.0
+    # the loop stops at the first all-empty column i >= 1, else runs seq_length steps
+    seq = torch.zeros(3, 91, dtype=torch.long)
+    seq[:, 0] = 1
+    seq[0, 1:7] = 5
+    seq[1, 1:4] = 9
+    assert sp._steps(seq) == 7
+    seq[2, 1:91] = 3
+    assert sp._steps(seq) == 90
+    seq[:, 0] = 0                      # column 0 is never a stop column (the reference tests i >= 1 only)
+    assert sp._steps(seq) == 90
+    # masked NLL restatement == oracle's on random log-probabilities
+    g = torch.Generator().manual_seed(0)
+    logp = torch.log_softmax(torch.randn(3, 90, 148, generator=g), 2)
+    tgt = torch.randint(0, 148, (3, 90), generator=g)
+    mask = (torch.rand(3, 90, generator=g) > 0.4).float()
+    assert torch.allclose(LanguageModelCriterion()(logp, tgt, mask), O.lm_criterion(logp, tgt, mask))
+    x = torch.zeros(3, 1024)
+    sp.eval()
+    with pytest.raises(NotImplementedError):
+        sp._sample(x, x, x, seq, cfg, sample_max=0)                 # multinomial sampling
+    cfg2 = default_cfg("all")
+    cfg2.model.speaker.beam_size = 3
+    with pytest.raises(NotImplementedError):
+        sp._sample(x, x, x, seq, cfg2, sample_max=1)                # beam search
+    sp.train()
+    with pytest.raises(NotImplementedError):
+        sp._sample(x, x, x, seq, cfg, sample_max=1)                 # inference entry point in train mode
+    sp.ss_prob = 0.25
+    with pytest.raises(NotImplementedError):
+        sp._forward(x, x, x, seq)                                   # scheduled sampling
+    sp.ss_prob = 0.0
+    if not torch.cuda.is_available():
+        with pytest.raises(lib.EkaidError):
+            sp.eval()._forward(x, x, x, seq)                        # no CPU fallback
+        with pytest.raises(lib.EkaidError):
+            sp._sample(x, x, x, seq, cfg, sample_max=1)
+
+
 def test_golden_manifest_complete():
     from helpers import CASES
     for c in CASES:
