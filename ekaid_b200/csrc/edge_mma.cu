@@ -62,7 +62,7 @@ __device__ __forceinline__ void load_z_chunk(bf16* Zs, const bf16* __restrict__ 
 // F16: Z (at Zsrc, pitch ldz, head 0 at column zoff) and the attention weights (plane 2 of Phl) hold IEEE fp16 -- one
 // MMA per product instead of the bf16 path's hi + lo pair, and 11 significant bits in Z; XoutT is then written as fp16 too.
 template <int MR, bool F16>   // padded query rows per CTA pass: 64 or 128
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (F16 && MR == 64) ? 3 : 1)
 agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, long long ld, int D,
                    const float* __restrict__ b_out, const float* __restrict__ Xin, int N, int Kn, int H,
                    float* __restrict__ Xout, bf16* __restrict__ XoutT, long long ldt, uint8_t* __restrict__ mask,
@@ -169,7 +169,6 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
       const int item = warp + it * 8;
       const int mt = item >> 1, nh = item & 1;
       const int colb = c0 + nh * 64 + 2 * (lane & 3);          // column of nt = 0
-      float2 bo[8], xi[2][8];
       size_t rbase[2];
       bool rok[2];
 #pragma unroll
@@ -178,8 +177,13 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
         rok[hh] = i < N;
         rbase[hh] = ((size_t)g * N + (rok[hh] ? i : 0)) * D + colb;
       }
+      // two halves of four column tiles: the loads of a half are all in flight before its first use, and the live
+      // operand registers stay at 24 (three CTAs per SM need <= 85 registers per thread)
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nh4 = 0; nh4 < 2; ++nh4) {
+      float2 bo[8], xi[2][8];
+#pragma unroll
+      for (int nt = 4 * nh4; nt < 4 * nh4 + 4; ++nt) {
         const bool cok = colb + nt * 8 < D;
         bo[nt] = cok ? *(const float2*)(b_out + colb + nt * 8) : make_float2(0.f, 0.f);
 #pragma unroll
@@ -187,7 +191,7 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
           xi[hh][nt] = (cok && rok[hh] && Xin) ? *(const float2*)(Xin + rbase[hh] + nt * 8) : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
+      for (int nt = 4 * nh4; nt < 4 * nh4 + 4; ++nt) {
         if (colb + nt * 8 >= D) continue;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -221,6 +225,7 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
             *(uchar2*)(mask + idx) = mk;
           }
         }
+      }
       }
     }
   }
@@ -830,7 +835,12 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
   const int MR = N <= 64 ? 64 : 128;
   if (Phl && ((HK % 8) || ((uintptr_t)Phl & 15))) Phl = nullptr;      // planes need 16-byte-aligned rows
   const long long plane = (long long)G * N * HK;
-  const size_t smem = ((size_t)kchunk * ZS + 2 * (size_t)MR * (kchunk + 8)) * sizeof(bf16);
+  // fp16 forward: one weight plane, and (h, j) chunks of about half the rows -- 46 KB instead of 112 KB per CTA, so three
+  // CTAs share an SM (the kernel is latency bound at 2 CTAs = 16 warps: 33 % stall_wait, 12 % issuing, profiles/r02_notes.md)
+  int kc = kchunk;
+  if (Z16 && HKp > 128) kc = ((HKp / 2) + 15) & ~15;
+  const size_t smem = Z16 ? ((size_t)kc * ZS + (size_t)MR * (kc + 8)) * sizeof(bf16)
+                          : ((size_t)kchunk * ZS + 2 * (size_t)MR * (kchunk + 8)) * sizeof(bf16);
   dim3 grid(G, ek_div_up(D, NC));
   static size_t c64 = 0, c128 = 0;
   static size_t h64 = 0, h128 = 0;
@@ -838,12 +848,12 @@ int ek_agg_fwd_mma_launch(const float* P, const bf16* QKZ, long long ld, int D, 
     int rc = set_smem(agg_fwd_mma_kernel<64, true>, smem, h64, "agg_fwd_mma");
     if (rc) return rc;
     ek_launch(agg_fwd_mma_kernel<64, true>, grid, 256, smem, st, P, Z16, ldz16, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
-                                                          kchunk, dr, Phl, plane, 0);
+                                                          kc, dr, Phl, plane, 0);
   } else if (Z16) {
     int rc = set_smem(agg_fwd_mma_kernel<128, true>, smem, h128, "agg_fwd_mma");
     if (rc) return rc;
     ek_launch(agg_fwd_mma_kernel<128, true>, grid, 256, smem, st, P, Z16, ldz16, D, b_out, Xin, N, Kn, H, Xout, XoutT, ldt, mask,
-                                                           kchunk, dr, Phl, plane, 0);
+                                                           kc, dr, Phl, plane, 0);
   } else if (MR == 64) {
     int rc = set_smem(agg_fwd_mma_kernel<64, false>, smem, c64, "agg_fwd_mma");
     if (rc) return rc;
