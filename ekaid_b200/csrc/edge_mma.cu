@@ -580,14 +580,27 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
   // below 2.7e8.)  The previous form -- 96 guarded scalar loads per thread in fully unrolled loops -- made this kernel
   // 6.7 k instructions long and instruction-fetch bound (34 % of warp samples `stall_no_inst`, profiles/r02_notes.md).
   const size_t total = (size_t)N * Kn;
+  // (a warp per row, lanes over the keys: no index division; all loads of a row are issued before the first use)
 #pragma unroll 1
-  for (int e = tid; e < N * Kn; e += 256) {
-    const int i = e / Kn, j = e - i * Kn;
-    const size_t ge = (size_t)g * total + e;
-    float a = gbias ? gbias[ge * H + h] : 0.f;
-    if (lbias) a += lbias[ge];
-    if (cond && !(cond[ge] > 0.f)) a = -INFINITY;
-    Ts[i * TS + j] = a;
+  for (int i = warp; i < N; i += 8) {
+    const size_t gr = (size_t)g * total + (size_t)i * Kn;
+    float a[KR / 32], cv[KR / 32];
+#pragma unroll
+    for (int r = 0; r < KR / 32; ++r) {
+      const int j = lane + 32 * r;
+      a[r] = 0.f;
+      cv[r] = 1.f;
+      if (j < Kn) {
+        if (gbias) a[r] = gbias[(gr + j) * H + h];
+        if (lbias) a[r] += lbias[gr + j];
+        if (cond) cv[r] = cond[gr + j];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < KR / 32; ++r) {
+      const int j = lane + 32 * r;
+      if (j < Kn) Ts[i * TS + j] = (cv[r] > 0.f) ? a[r] : -INFINITY;
+    }
   }
   cp_async_wait_all();
   __syncthreads();
@@ -659,16 +672,22 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
   // probabilities out: P fp32 + the 16-bit planes the aggregation kernels stage (bf16 hi + lo = 16 significant bits for the
   // backward, fp16 for the fp16 forward aggregation), one rolled loop, consecutive threads on consecutive keys of a row
 #pragma unroll 1
-  for (int e = tid; e < N * Kn; e += 256) {
-    const int i = e / Kn, j = e - i * Kn;
-    const float pv = Ts[i * TS + j];
-    const size_t o = (((size_t)g * N + i) * H + h) * Kn + j;
-    P[o] = pv;
-    if (Phl) {
-      const bf16 hi = __float2bfloat16_rn(pv);
-      Phl[o] = hi;
-      Phl[plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
-      if (p16) ((f16*)Phl)[2 * plane + o] = from_f32<f16>(pv);
+  for (int i = warp; i < N; i += 8) {
+    const size_t orow = (((size_t)g * N + i) * H + h) * Kn;
+#pragma unroll
+    for (int r = 0; r < KR / 32; ++r) {
+      const int j = lane + 32 * r;
+      if (j < Kn) {
+        const float pv = Ts[i * TS + j];
+        const size_t o = orow + j;
+        P[o] = pv;
+        if (Phl) {
+          const bf16 hi = __float2bfloat16_rn(pv);
+          Phl[o] = hi;
+          Phl[plane + o] = __float2bfloat16_rn(pv - __bfloat162float(hi));
+          if (p16) ((f16*)Phl)[2 * plane + o] = from_f32<f16>(pv);
+        }
+      }
     }
   }
 }
