@@ -477,10 +477,21 @@ class DynamicSpeaker(nn.Module):
                                       "it off (scheduled_sampling_start = -1)")
         pc = PC(self.precision)
         dev = feat_bef.device
+        if seq.dim() != 2 or seq.shape[0] != feat_bef.shape[0]:
+            raise ValueError("seq must be [batch, tokens] with the batch of the features, got %s" % (tuple(seq.shape),))
+        seq = seq.to(device=dev, dtype=torch.int64)
+        T = int(steps) if steps is not None else self._steps(seq)
+        if T < 1 or T > min(self.seq_length, seq.shape[1]):
+            raise ValueError("steps=%d outside 1..%d" % (T, min(self.seq_length, seq.shape[1])))
+        if fused:
+            if masks is None or tuple(masks.shape) != tuple(seq.shape):
+                raise ValueError("masked_nll needs masks of the labels' shape %s" % (tuple(seq.shape),))
+            if seq.shape[1] < T + 1:
+                raise ValueError("labels need %d columns (step t predicts column t + 1), got %d" % (T + 1, seq.shape[1]))
+            masks = masks.to(device=dev, dtype=torch.float32)
         if self.training:
             rng_advance(dev)
         drop = Drop(dev, self.training)
-        T = int(steps) if steps is not None else self._steps(seq)
         params = [p for _, p in self.named_parameters()]
         return SpeakerSeqFn.apply(pc, drop, self, T, fused, seq, masks, feat_bef, feat_aft, feat_diff, *params)
 
