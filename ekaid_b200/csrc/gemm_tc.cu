@@ -678,6 +678,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                   case 11: epi_rows_fast<1, true, true>(ep, k, bv, add4, dseed); break;
                   case 16: epi_rows_fast<2, false>(ep, k, bv, add4); break;
                   case 17: epi_rows_fast<2, true>(ep, k, bv, add4); break;
+                  case 18: epi_rows_fast<2, false, true>(ep, k, bv, add4, dseed); break;
                   case 20: epi_rows_fast<2, false, false, true>(ep, k, bv, add4, 0ull, rowb_lane); break;
                   case 24: epi_rows_fast<3, false>(ep, k, bv, add4); break;
                   case 25: epi_rows_fast<3, true>(ep, k, bv, add4); break;
