@@ -190,7 +190,7 @@ int ek_dec_relu_drop_bwd_launch(const float*, long long, const void*, long long,
                                 float*, long long, cudaStream_t);
 int ek_dec_masked_sum_t_launch(const float*, long long, int, int, int, EkDrop, unsigned long long, float*, cudaStream_t);
 int ek_dec_token_launch(const float*, long long, int, int, int, int, long long*, float*, unsigned char*, int*, long long*,
-                        float*, cudaStream_t);
+                        float*, int, float, EkDrop, cudaStream_t);
 int ek_dec_nll_launch(const float*, long long, int, int, int, const long long*, long long, const float*, long long, int, float*,
                       int, float*, const float*, const float*, void*, long long, int, int*, cudaStream_t);
 int ek_dec_nll_reduce_launch(const float*, int, const float*, long long, int, int, float*, cudaStream_t);
@@ -575,9 +575,10 @@ int ekaid_dec_masked_sum_t(const float* x, int64_t ldx, int T, int B, int n, con
   return ek_dec_masked_sum_t_launch(x, ldx, T, B, n, mk_drop(seed, site, p), (unsigned long long)base, acc, ST);
 }
 int ekaid_dec_token(const float* logits, int64_t ldl, int B, int V, int t, int T, int64_t* seq, float* seq_logp,
-                    uint8_t* unfinished, int32_t* state, int64_t* next_tok, float* logp_out, void* stream) {
+                    uint8_t* unfinished, int32_t* state, int64_t* next_tok, float* logp_out, int multinomial,
+                    float temperature, const uint64_t* seed, uint32_t site, void* stream) {
   return ek_dec_token_launch(logits, ldl, B, V, t, T, (long long*)seq, seq_logp, unfinished, state, (long long*)next_tok,
-                             logp_out, ST);
+                             logp_out, multinomial, temperature, mk_drop(seed, site, 0.5f), ST);
 }
 int ekaid_dec_nll(const float* logits, int64_t ldl, int rows, int B, int V, const int64_t* labels, int64_t lsb,
                   const float* masks, int64_t msb, int mode, float* out, int Tout, float* row_loss, const float* gscale,

@@ -332,17 +332,21 @@ __global__ void dec_masked_sum_t_kernel(const float* __restrict__ x, long long l
   }
 }
 
-// ---------------------------------------------------------------- greedy sampling step (dynamic_speaker_change_pos.py:312-355)
+// ---------------------------------------------------------------- sampling step (dynamic_speaker_change_pos.py:312-355)
 // state[0] = 1 while the reference's loop would still be running (it breaks once every sequence has produced token 0);
-// unfinished [B] u8.  One CTA; a warp per row: log-softmax over V logits, arg-max (first maximum, like torch.max), then
-// it = it * unfinished, seq[b, t] = it, seq_logprobs[b, t] = max log-prob -- both only while state[0] -- next[b] = it.
+// unfinished [B] u8.  One CTA; a warp per row: log-softmax over V logits, then either the arg-max (sample_max = 1: first
+// maximum, like torch.max) or a multinomial draw from exp(logp / temperature) (sample_max = 0, :341-349; inverse CDF over
+// the tokens in index order, one counter-based uniform per (row, step) from the device seed);  it = it * unfinished,
+// seq[b, t] = it, seq_logprobs[b, t] = log-prob of the chosen token -- both only while state[0] -- next[b] = it.
 __global__ void __launch_bounds__(1024)
 dec_token_kernel(const float* __restrict__ logits, long long ldl, int B, int V, int t, int T, long long* __restrict__ seq,
                  float* __restrict__ seq_logp, unsigned char* __restrict__ unfinished, int* __restrict__ state,
-                 long long* __restrict__ next_tok, float* __restrict__ logp_out) {
+                 long long* __restrict__ next_tok, float* __restrict__ logp_out, int multinomial, float inv_temp,
+                 EkDrop rng) {
   ek_pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int running = state[0];
+  const unsigned long long seedv = ek_seed(rng);
   int any = 0;
   for (int b = warp; b < B; b += nw) {
     const float* lg = logits + b * ldl;
@@ -355,17 +359,62 @@ dec_token_kernel(const float* __restrict__ logits, long long ldl, int B, int V, 
     const float lse = mx + logf(s);
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int v = lane; v < V; v += 32) {
-      float lp = lg[v] - lse;
-      if (t == 0 && v == 0) lp = -INFINITY;                 // never sample NULL at the first step (:329-332)
-      if (logp_out) logp_out[(long long)b * V + v] = lp;
-      if (lp > best) { best = lp; bi = v; }
-    }
+    if (!multinomial) {
+      for (int v = lane; v < V; v += 32) {
+        float lp = lg[v] - lse;
+        if (t == 0 && v == 0) lp = -INFINITY;                 // never sample NULL at the first step (:329-332)
+        if (logp_out) logp_out[(long long)b * V + v] = lp;
+        if (lp > best) { best = lp; bi = v; }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+    } else {
+      // weights w_v = exp(logp_v / temperature) in blocks of 32 consecutive tokens; total, then the first token whose
+      // inclusive prefix sum reaches u * total
+      // (relative to the largest allowed logit, so a small temperature cannot underflow every weight)
+      float m2 = -INFINITY;
+      for (int v = lane; v < V; v += 32)
+        if (!(t == 0 && v == 0)) m2 = fmaxf(m2, lg[v]);
+      m2 = warp_max(m2);
+      float tot = 0.f;
+      for (int v0 = 0; v0 < V; v0 += 32) {
+        const int v = v0 + lane;
+        float w = 0.f;
+        if (v < V && !(t == 0 && v == 0)) w = expf((lg[v] - m2) * inv_temp);
+        if (logp_out && v < V) logp_out[(long long)b * V + v] = (t == 0 && v == 0) ? -INFINITY : lg[v] - lse;
+        tot += w;
+      }
+      tot = warp_sum(tot);
+      const float u = (float)(ek_rand32(seedv, rng.site, (unsigned long long)b * (T + 1) + t) >> 8) * (1.0f / 16777216.0f);
+      const float target = u * tot;
+      float carry = 0.f;
+      int pick = -1;
+      for (int v0 = 0; v0 < V && pick < 0; v0 += 32) {
+        const int v = v0 + lane;
+        float w = 0.f;
+        if (v < V && !(t == 0 && v == 0)) w = expf((lg[v] - m2) * inv_temp);
+        float c = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float n = __shfl_up_sync(0xffffffffu, c, o);
+          if (lane >= o) c += n;
+        }
+        c += carry;
+        const unsigned hit = __ballot_sync(0xffffffffu, w > 0.f && c > target);
+        if (hit) pick = v0 + __ffs(hit) - 1;
+        carry = __shfl_sync(0xffffffffu, c, 31);
+      }
+      if (pick < 0) {                                         // u * total landed on the rounding of the last prefix sum
+        for (int v = V - 1; v >= 0 && pick < 0; --v)
+          if (!(t == 0 && v == 0) && expf((lg[v] - m2) * inv_temp) > 0.f) pick = v;
+        if (pick < 0) pick = (t == 0) ? 1 : 0;
+      }
+      bi = pick;
+      best = lg[pick] - lse;
     }
     if (lane == 0) {
       int un = (t == 0) ? (bi > 0) : (unfinished[b] && bi > 0);
@@ -591,8 +640,11 @@ int ek_dec_masked_sum_t_launch(const float* x, long long ldx, int T, int B, int 
   return EK_OK;
 }
 int ek_dec_token_launch(const float* logits, long long ldl, int B, int V, int t, int T, long long* seq, float* seq_logp,
-                        unsigned char* unfinished, int* state, long long* next_tok, float* logp_out, cudaStream_t s) {
-  ek_launch(dec_token_kernel, 1, 1024, 0, s, logits, ldl, B, V, t, T, seq, seq_logp, unfinished, state, next_tok, logp_out);
+                        unsigned char* unfinished, int* state, long long* next_tok, float* logp_out, int multinomial,
+                        float temperature, EkDrop rng, cudaStream_t s) {
+  EK_REQUIRE(!multinomial || (temperature > 0.f && rng.seed), EK_ERR_SHAPE, "dec_token: sampling needs temperature > 0 and a seed");
+  ek_launch(dec_token_kernel, 1, 1024, 0, s, logits, ldl, B, V, t, T, seq, seq_logp, unfinished, state, next_tok, logp_out,
+            multinomial, multinomial ? 1.0f / temperature : 1.0f, rng);
   EK_CHECK_LAUNCH();
   return EK_OK;
 }

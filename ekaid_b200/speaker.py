@@ -30,7 +30,7 @@ from .functions import (ACT_RELU, PC, Drop, _dst, _f32c, cast_many, colsum, gemm
 from .lib import call
 
 # dropout sites of the decoder (functions.Drop site numbering: relation encoders 100-399, question path 10-11, fusion 20-21)
-SITE_WORD, SITE_EMBED, SITE_POS1, SITE_DPOS, SITE_GATE1, SITE_OUT = 400, 401, 402, 403, 404, 405
+SITE_WORD, SITE_EMBED, SITE_POS1, SITE_DPOS, SITE_GATE1, SITE_OUT, SITE_SAMPLE = 400, 401, 402, 403, 404, 405, 406
 
 
 def _default_precision() -> str:
@@ -532,28 +532,35 @@ class DynamicSpeaker(nn.Module):
 
     @torch.no_grad()
     def _sample(self, feat_bef, feat_aft, feat_diff, seq, cfg={}, sample_max=0, check_every=16, use_graph=True):
-        """:287-357 with beam_size = 1, sample_max = 1 (the reference's test path, test_mimic.py:119-122):
+        """:287-357 with beam_size = 1: greedy (sample_max = 1, the reference's test path, test_mimic.py:119-122) or
+        multinomial sampling from exp(logprobs / temperature) (sample_max = 0, :341-349; the uniforms come from the
+        library's counter RNG, so the draws are not torch.multinomial's -- their distribution is)
         -> (seq [B, seq_length] int64, seq_logprobs [B, seq_length]).
         The token loop runs in blocks of `check_every` steps; the host reads the device-side stop flag once per block
         (0 = never, always seq_length steps).  use_graph: every block is a captured CUDA graph, kept per batch size."""
         sp = cfg.model.speaker if hasattr(cfg, "model") else {}
         if (sp.get('beam_size', 1) if hasattr(sp, "get") else 1) > 1:
             raise NotImplementedError("beam search is not implemented (the reference's test script uses beam_size 1)")
-        if not sample_max:
-            raise NotImplementedError("multinomial sampling is not implemented; use sample_max=1 (greedy, the test path)")
+        temperature = float(sp.get('temperature', 1.0) if hasattr(sp, "get") else 1.0)
+        if not sample_max and temperature <= 0.0:
+            raise ValueError("temperature must be positive, got %r" % (temperature,))
         if self.training:
             raise NotImplementedError("_sample is an inference entry point: call eval() first")
         self.module_weights = []
         B, dev = feat_bef.shape[0], feat_bef.device
         T = self.seq_length
         ce = check_every if check_every and check_every > 0 else T + 1
-        key = (B, str(dev), self.precision, ce, bool(use_graph), T, self.logit.weight.data_ptr())
+        key = (B, str(dev), self.precision, ce, bool(use_graph), T, bool(sample_max), temperature,
+               self.logit.weight.data_ptr())
         r = self._runners.get(key)
         if r is None:
             if len(self._runners) > 4:
                 self._runners.clear()
             r = _StepRunner(self, B, dev)
+            r.multinomial, r.temperature = (0 if sample_max else 1), temperature
             self._runners[key] = r
+        if not sample_max:
+            rng_advance(dev)             # a fresh stream of uniforms per call (a kernel: valid inside a captured graph too)
         r.load(feat_bef, feat_aft, feat_diff, None)
         blocks = [(t0, min(t0 + ce, T + 1)) for t0 in range(0, T + 1, ce)]
         for bi, (t0, t1) in enumerate(blocks):
@@ -616,6 +623,7 @@ class _StepRunner:
         self.vocab = torch.arange(V, device=dev, dtype=torch.int64).view(V, 1)
         self.graphs, self.graph_launches = {}, {}
         self.w = None
+        self.multinomial, self.temperature = 0, 1.0
 
     def load(self, bef, aft, diff, state):
         self.bef.copy_(bef)
@@ -683,8 +691,10 @@ class _StepRunner:
         gemm(self.hl, w.W_lo, B, V, R, bias=w.b_lo, C=self.logits)
         if sample:
             T = self.sp.seq_length
+            from .functions import rng_state
             call("dec_token", self.logits.data_ptr(), V, B, V, t, T, self.seq.data_ptr(), self.seq_lp.data_ptr(),
-                 self.unfinished.data_ptr(), self.running.data_ptr(), self.tok.data_ptr(), None)
+                 self.unfinished.data_ptr(), self.running.data_ptr(), self.tok.data_ptr(), None, self.multinomial,
+                 float(self.temperature), rng_state(self.dev).data_ptr(), SITE_SAMPLE)
 
     def run_block(self, t0: int, t1: int, first: bool):
         """Steps t0 .. t1-1 of the reference's `for t in range(seq_length + 1)` loop (:299); its last iteration only advances

@@ -406,10 +406,12 @@ int ekaid_dec_relu_drop_bwd(const float* dy, int64_t ldd, const void* y, int64_t
 /* acc[b, j] = sum_t x[(t*B+b), j] * mask(t, b, j): gradient of the step-invariant core.embed output */
 int ekaid_dec_masked_sum_t(const float* x, int64_t ldx, int T, int B, int n, const uint64_t* seed, uint32_t site, float p,
                            int64_t base, float* acc, void* stream);
-/* one greedy sampling step on the device (:312-355): log-softmax, arg-max, unfinished bookkeeping, next token; state[0] = 1
- * while the reference's loop would still run (replaces the host synchronisation of :354) */
+/* one sampling step on the device (:312-355): log-softmax, arg-max (multinomial = 0) or a draw from
+ * exp(logp / temperature) (multinomial = 1; uniform from the counter RNG at (seed, site, b*(T+1)+t)), unfinished bookkeeping,
+ * next token; state[0] = 1 while the reference's loop would still run (replaces the host synchronisation of :354) */
 int ekaid_dec_token(const float* logits, int64_t ldl, int B, int V, int t, int T, int64_t* seq, float* seq_logp,
-                    uint8_t* unfinished, int32_t* state, int64_t* next_tok, float* logp_out, void* stream);
+                    uint8_t* unfinished, int32_t* state, int64_t* next_tok, float* logp_out, int multinomial,
+                    float temperature, const uint64_t* seed, uint32_t site, void* stream);
 /* log-softmax + masked NLL + gradient over the logits of all steps (utils/utils.py:204-216; train_mimic.py:242):
  * mode bit 0: out[b,t,:] = logp; bit 1: row_loss; bit 2: dlogits (operand, pitch ldd) */
 int ekaid_dec_nll(const float* logits, int64_t ldl, int rows, int B, int V, const int64_t* labels, int64_t lsb,

@@ -189,8 +189,6 @@ def test_speaker_constructor_state_dict_and_host_logic():
     assert torch.allclose(LanguageModelCriterion()(logp, tgt, mask), O.lm_criterion(logp, tgt, mask))
     x = torch.zeros(3, 1024)
     sp.eval()
-    with pytest.raises(NotImplementedError):
-        sp._sample(x, x, x, seq, cfg, sample_max=0)                 # multinomial sampling
     cfg2 = default_cfg("all")
     cfg2.model.speaker.beam_size = 3
     with pytest.raises(NotImplementedError):

@@ -348,3 +348,40 @@ def test_arg_max_answer_tokens_through_the_whole_path(precision):
         weak = (~solid[b]).nonzero().flatten()
         upto = int(weak[0]) if len(weak) else 90          # free-running decode: identical up to the first near-tie
         assert torch.equal(seq[b, :upto], ref[b, :upto]), (b, upto, first_diff[b])
+
+
+def test_multinomial_sampling_follows_the_distribution():
+    """_sample(sample_max=0) (:341-349): tokens drawn from exp(logprobs / temperature).  8192 identical samples: the
+    first-step token frequencies must match the oracle's first-step distribution (token 0 excluded at t = 0), the reported
+    log-prob is the chosen token's, two calls draw different tokens, and temperature -> 0 approaches the arg-max."""
+    from ekaid_b200.config import default_cfg
+    from oracle import ekaid_oracle as O
+    dev = _dev()
+    B = 8192
+    sp, ssd, feats, labels, masks = _setup(2, 3, dev, "fp32", logit_scale=8.0)
+    f1 = [f[:1].expand(B, -1).contiguous() for f in feats]
+    it = torch.full((1,), 2, dtype=torch.long)
+    lp0, _, _ = O.speaker_logprobs(ssd, it, feats[0][:1], feats[1][:1], feats[2][:1], (torch.zeros(2, 1, 512), torch.zeros(2, 1, 512)))
+    for temp in (1.0, 0.5):
+        cfg = default_cfg("all")
+        cfg.model.speaker.temperature = temp
+        w = torch.exp(lp0[0] / temp)
+        w[0] = 0.0
+        p = (w / w.sum()).double()
+        seq, lp = sp._sample(f1[0].to(dev), f1[1].to(dev), f1[2].to(dev), None, cfg, sample_max=0, check_every=0)
+        tok = seq[:, 0].cpu()
+        assert int(tok.min()) > 0
+        freq = torch.bincount(tok, minlength=148).double() / B
+        # total variation distance of B draws from p: ~ sqrt(support / (2 pi B)) = 0.053 for pure sampling noise
+        tv = 0.5 * float((freq - p).abs().sum())
+        support = int((p > 1e-3).sum())
+        print("temperature %.1f: support %d tokens, total variation %.3f" % (temp, support, tv))
+        assert support > 5 and tv < 0.08
+        assert float((lp[:, 0].cpu() - lp0[0][tok]).abs().max()) < 1e-3
+        seq2, _ = sp._sample(f1[0].to(dev), f1[1].to(dev), f1[2].to(dev), None, cfg, sample_max=0, check_every=0)
+        assert not torch.equal(seq2, seq)
+    cfg = default_cfg("all")
+    cfg.model.speaker.temperature = 1e-3
+    cold, _ = sp._sample(f1[0].to(dev), f1[1].to(dev), f1[2].to(dev), None, cfg, sample_max=0, check_every=0)
+    greedy, _ = sp._sample(f1[0].to(dev), f1[1].to(dev), f1[2].to(dev), None, cfg, sample_max=1, check_every=0)
+    assert torch.equal(cold[:, 0], greedy[:, 0])
