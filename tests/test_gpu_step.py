@@ -242,7 +242,7 @@ def test_int8_label_matrices_equal_the_onehot_path_bit_for_bit(case):
             elif float(b.abs().max()) >= 1e-3:      # (below: analytically zero, e.g. the key bias -- noise on both sides)
                 # run-to-run noise of the 16-bit path, in the gradient metric of the parity tests (relative L2)
                 # (scalar gains of weight-normalised layers are cancelling projections: the widest band)
-                assert float((a - b).norm() / b.norm()) < (5e-2 if a.numel() == 1 else 2e-2), (precision, k)
+                assert float((a - b).norm() / b.norm()) < (8e-2 if a.numel() == 1 else 3e-2), (precision, k)
 
 
 def test_eval_pass_and_second_model_between_training_steps_do_not_interfere():
