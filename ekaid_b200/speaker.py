@@ -540,7 +540,9 @@ class DynamicSpeaker(nn.Module):
         (0 = never, always seq_length steps).  use_graph: every block is a captured CUDA graph, kept per batch size."""
         sp = cfg.model.speaker if hasattr(cfg, "model") else {}
         if (sp.get('beam_size', 1) if hasattr(sp, "get") else 1) > 1:
-            raise NotImplementedError("beam search is not implemented (the reference's test script uses beam_size 1)")
+            raise NotImplementedError("beam search is not implemented: the reference's test script uses beam_size 1, and its "
+                                      "_sample_beam cannot run (it unpacks get_logprobs_state's three results into two "
+                                      "names, dynamic_speaker_change_pos.py:270)")
         temperature = float(sp.get('temperature', 1.0) if hasattr(sp, "get") else 1.0)
         if not sample_max and temperature <= 0.0:
             raise ValueError("temperature must be positive, got %r" % (temperature,))
