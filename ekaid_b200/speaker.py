@@ -542,7 +542,7 @@ class DynamicSpeaker(nn.Module):
         if (sp.get('beam_size', 1) if hasattr(sp, "get") else 1) > 1:
             raise NotImplementedError("beam search is not implemented: the reference's test script uses beam_size 1, and its "
                                       "_sample_beam cannot run (it unpacks get_logprobs_state's three results into two "
-                                      "names, dynamic_speaker_change_pos.py:270)")
+                                      "names, dynamic_speaker_change_pos.py:273)")
         temperature = float(sp.get('temperature', 1.0) if hasattr(sp, "get") else 1.0)
         if not sample_max and temperature <= 0.0:
             raise ValueError("temperature must be positive, got %r" % (temperature,))
