@@ -162,6 +162,10 @@ static EkEpilogue to_ep(const ekaid_epilogue_t* e) {
   r.ldcb2 = e->ldcb2;
   r.cb2_fmt = e->cb2_fmt;
   r.cb2_n0 = e->cb2_n0;
+  r.C2 = e->C2;
+  r.ldc2 = e->ldc2;
+  r.c_n1 = e->c_n1;
+  r.add_n1 = e->add_n1;
   return r;
 }
 
@@ -244,6 +248,8 @@ int ekaid_gemm_tc(int transA, int transB, int M, int N, int K, const void* A, in
   EK_REQUIRE(ep && (ep->C || ep->Cb || ep->Cb2), EK_ERR_SHAPE, "gemm_tc: no output");
   EK_REQUIRE((ep->cb_n1 % 32) == 0 && (ep->cb2_n0 % 32) == 0 && ep->cb_n1 >= 0 && ep->cb2_n0 >= 0, EK_ERR_SHAPE,
              "gemm_tc: cb_n1 / cb2_n0 must be non-negative multiples of 32");
+  EK_REQUIRE((ep->c_n1 % 32) == 0 && (ep->add_n1 % 32) == 0 && ep->c_n1 >= 0 && ep->add_n1 >= 0 && (!ep->C2 || ep->C),
+             EK_ERR_SHAPE, "gemm_tc: c_n1 / add_n1 must be non-negative multiples of 32, C2 needs C");
   return ek_gemm_bf16_tc_launch(transA, transB, M, N, K, (const bf16*)A, lda, (const bf16*)B, ldb, to_ep(ep), force_bn,
                                 splits, (a_fp16 ? 1 : 0) | (b_fp16 ? 2 : 0), ST);
 }

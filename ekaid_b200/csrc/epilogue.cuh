@@ -30,6 +30,10 @@ struct EkEpilogue {
   long long ldcb2;
   int cb2_fmt;
   int cb2_n0;
+  float* C2;          // optional second fp32 output: columns n >= c_n1, stored at column n - c_n1
+  long long ldc2;
+  int c_n1;
+  int add_n1;         // addend only for columns n < add_n1 (0 = all)
 };
 
 __device__ __forceinline__ float ek_act(float v, int act) {
@@ -46,13 +50,14 @@ __device__ __forceinline__ void ek_epilogue_store(const EkEpilogue& e, long long
   float v = acc;
   if (e.bias) v += __ldg(e.bias + n);
   if (e.drop.seed) v *= ek_drop_mult(e.drop, ek_seed(e.drop), (unsigned long long)m * e.dropN + e.dropOff + n);
-  if (e.addend) v += e.addend[m * e.ldadd + n];
+  if (e.addend && (e.add_n1 == 0 || n < e.add_n1)) v += e.addend[m * e.ldadd + n];
   if (e.rowb) {
     if (e.rowflag && e.rowflag[m]) v += __ldg(e.rowb_alt + n);
     else v += __ldg(e.rowb + (long long)((m / e.rowb_div) % e.rowb_mod) * e.ldrowb + n);
   }
   v = ek_act(v, e.act);
-  if (e.C) e.C[m * e.ldc + n] = v;
+  if (e.C2 && n >= e.c_n1) e.C2[m * e.ldc2 + (n - e.c_n1)] = v;
+  else if (e.C) e.C[m * e.ldc + n] = v;
   if (e.Cb && (e.cb_n1 == 0 || n < e.cb_n1)) ek_store16(e.Cb + m * e.ldcb + n, v, e.cb_fmt);
   if (e.Cb2 && n >= e.cb2_n0) ek_store16(e.Cb2 + m * e.ldcb2 + (n - e.cb2_n0), v, e.cb2_fmt);
 }

@@ -241,7 +241,7 @@ int ek_gemm_skinny_ok(int transA, int transB, int M, int N, int K, const void* A
   if ((fmt & 1) != ((fmt >> 1) & 1)) return 0;                          // one MMA takes one 16-bit format
   if ((K % 8) || (lda % 8) || (ldb % 8) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return 0;
   if (transB && (N % 8)) return 0;
-  if (ep.rowb || ep.drop.seed || ep.Cb2 || ep.cb_n1 || ep.cb2_n0) return 0;
+  if (ep.rowb || ep.drop.seed || ep.Cb2 || ep.cb_n1 || ep.cb2_n0 || ep.C2 || ep.add_n1) return 0;
   if (!ep.C && !ep.Cb) return 0;
   return 1;
 }

@@ -231,6 +231,8 @@ struct EpiChunk {
   int nvalid;             // row groups of this lane inside the matrix
   long long row0;         // first row of this lane
   int n, nb;              // this lane's first column, the chunk's first column
+  float* pc;              // fp32 destination of this lane's first element (C, or C2 for chunks at / beyond c_n1)
+  long long sc;           // its stride per row group (4 rows)
 };
 
 __device__ __forceinline__ void epi_load8(const EpiChunk& k, float4* vt) {
@@ -246,10 +248,10 @@ __device__ __forceinline__ void epi_rows_fast(const EkEpilogue& ep, const EpiChu
                                               unsigned long long dseed = 0ull, const float* rowb_lane = nullptr) {
   float4 vt[8];
   epi_load8(k, vt);
-  float* pc = ep.C + k.row0 * ep.ldc + k.n;
+  float* pc = k.pc;
   bf16* pb = ep.Cb + k.row0 * ep.ldcb + k.n;
   bf16* pb2 = ep.Cb2 + k.row0 * ep.ldcb2 + (k.n - ep.cb2_n0);
-  const long long sc = 4 * ep.ldc, sb = 4 * ep.ldcb, sb2 = 4 * ep.ldcb2;
+  const long long sc = k.sc, sb = 4 * ep.ldcb, sb2 = 4 * ep.ldcb2;
   const int fb = ep.cb_fmt, fb2 = ep.cb2_fmt;
   // dropout counter of this lane's first element; one 64-bit draw covers the four columns (n is a multiple of 4)
   unsigned long long e0 = DROP ? (unsigned long long)k.row0 * ep.dropN + ep.dropOff + k.n : 0ull;
@@ -300,7 +302,8 @@ __device__ __forceinline__ void epi_rows_red(const EkEpilogue& ep, const EpiChun
 
 // four consecutive columns of one row -> C (fp32) / Cb / Cb2 (16-bit, per-output format and column range)
 __device__ __forceinline__ void epi_store4(const EkEpilogue& ep, long long mm, int n, int nb, float4 v) {
-  if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
+  if (ep.C2 && nb >= ep.c_n1) *(float4*)(ep.C2 + mm * ep.ldc2 + (n - ep.c_n1)) = v;
+  else if (ep.C) *(float4*)(ep.C + mm * ep.ldc + n) = v;
   if (ep.Cb && (ep.cb_n1 == 0 || nb < ep.cb_n1)) {
     uint2 pk;
     pk.x = pack16x2(v.x, v.y, ep.cb_fmt);
@@ -333,7 +336,7 @@ __device__ __forceinline__ void epi_rows_general(const EkEpilogue& ep, const Epi
         ek_drop_multv<4>(ep.drop, dseed, (unsigned long long)mm * ep.dropN + ep.dropOff + k.n, mk);
         v.x *= mk[0]; v.y *= mk[1]; v.z *= mk[2]; v.w *= mk[3];
       }
-      if (ep.addend) {
+      if (ep.addend && (ep.add_n1 == 0 || k.nb < ep.add_n1)) {
         const float4 a4 = *(const float4*)(ep.addend + mm * ep.ldadd + k.n);
         v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
       }
@@ -632,7 +635,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int n = nb + cg * 4;
           // operand prefetch in the transposed layout, before waiting for the accumulator chunk
           float4 add4[8];
-          if (fast && lean && ep.addend && splits == 1) {
+          const bool add_here = ep.addend && (ep.add_n1 == 0 || nb < ep.add_n1);     // (add_n1, c_n1: multiples of 32)
+          if (fast && lean && add_here && splits == 1) {
             const float* pa = ep.addend + (mrow0 + rg) * ep.ldadd + n;
             const long long sa = 4 * ep.ldadd;
             const int nvalid = (rows_here - rg + 3) >> 2;
@@ -662,6 +666,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             {
               EpiChunk k;
               k.stg = stg; k.rg = rg; k.cg = cg; k.nvalid = (rows_here - rg + 3) >> 2; k.row0 = mrow0 + rg; k.n = n; k.nb = nb;
+              if (ep.C2 && nb >= ep.c_n1) { k.pc = ep.C2 + k.row0 * ep.ldc2 + (n - ep.c_n1); k.sc = 4 * ep.ldc2; }
+              else { k.pc = ep.C + k.row0 * ep.ldc + n; k.sc = 4 * ep.ldc; }
               if (flags & GF_NOGST) {
               } else if (splits > 1) {
                 epi_rows_red(ep, k);
@@ -670,7 +676,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int om = fastmask == 0 ? 0
                              : ((ep.C ? 1 : 0) | ((ep.Cb && (ep.cb_n1 == 0 || nb < ep.cb_n1)) ? 2 : 0) |
                                 ((ep.Cb2 && nb >= ep.cb2_n0) ? 4 : 0));
-                const int feat = (ep.addend ? 1 : 0) | (ep.drop.seed ? 2 : 0) | (ep.rowb ? 4 : 0);
+                const int feat = (add_here ? 1 : 0) | (ep.drop.seed ? 2 : 0) | (ep.rowb ? 4 : 0);
                 switch (om * 8 + feat) {
                   case 8: epi_rows_fast<1, false>(ep, k, bv, add4); break;
                   case 9: epi_rows_fast<1, true>(ep, k, bv, add4); break;
@@ -912,8 +918,8 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   // Split-K candidates: plain fp32 outputs, or "C += A B" (addend aliases C, nothing else in the epilogue) where the
   // partial sums are reduced straight onto the existing values.
   const bool acc_alias = ep.addend && ep.addend == ep.C && ep.ldadd == ep.ldc;
-  const bool plain_out = ep.C && !ep.Cb && !ep.Cb2 && !ep.bias && (!ep.addend || acc_alias) && !ep.rowb &&
-                         ep.act == EK_ACT_NONE && !ep.drop.seed;
+  const bool plain_out = ep.C && !ep.C2 && !ep.Cb && !ep.Cb2 && !ep.bias && (!ep.addend || acc_alias) && !ep.rowb &&
+                         ep.act == EK_ACT_NONE && !ep.drop.seed && ep.add_n1 == 0;
   const int nkb = ek_div_up(K, BK);
   int bn = 256;
   if (force_bn == 64 || force_bn == 128 || force_bn == 256) {
@@ -970,6 +976,7 @@ int ek_gemm_bf16_tc_launch(int transA, int transB, int M, int N, int K, const bf
   // bit 0: 16-byte vector stores possible; bits 1..3: vector loads of bias / addend / row-broadcast operands
   int vec_ok = 15;
   if (ep.C && (((uintptr_t)ep.C & 15) || (ep.ldc & 3))) vec_ok &= ~1;
+  if (ep.C2 && (((uintptr_t)ep.C2 & 15) || (ep.ldc2 & 3))) vec_ok &= ~1;
   if (ep.Cb && (((uintptr_t)ep.Cb & 15) || (ep.ldcb & 7))) vec_ok &= ~1;
   if (ep.Cb2 && (((uintptr_t)ep.Cb2 & 15) || (ep.ldcb2 & 7))) vec_ok &= ~1;
   if (ep.bias && ((uintptr_t)ep.bias & 15)) vec_ok &= ~2;

@@ -162,7 +162,7 @@ class PC:
 # ------------------------------------------------------------------------------------------------
 def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None, rowb_div=1, rowb_mod=1,
          rowflag=None, rowb_alt=None, act=ACT_NONE, C=None, Cb=None, splits=0, force_bn=0, drop=None,
-         Cb2=None, cb_n1=0, cb2_n0=0):
+         Cb2=None, cb_n1=0, cb2_n0=0, C2=None, c_n1=0, add_n1=0):
     """C[M,N] = op(A) op(B) with the fused epilogue; dtype of A selects tcgen05 (16-bit operands: bf16 or fp16, chosen
     per operand) or SIMT (fp32).  Cb / Cb2: 16-bit outputs (bf16 or fp16 by their dtype): Cb takes columns < cb_n1
     (0 = all), Cb2 columns >= cb2_n0."""
@@ -191,6 +191,11 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
     ep.ldcb2 = Cb2.stride(0) if Cb2 is not None else 0
     ep.cb2_fmt = 1 if (Cb2 is not None and Cb2.dtype == torch.float16) else 0
     ep.cb2_n0 = cb2_n0
+    # fp32 output split by column (C2 takes columns >= c_n1), addend limited to columns < add_n1
+    ep.C2 = ptr(C2)
+    ep.ldc2 = C2.stride(0) if C2 is not None else 0
+    ep.c_n1 = c_n1 if C2 is not None else 0
+    ep.add_n1 = add_n1
     assert A.stride(-1) == 1 and B.stride(-1) == 1
     # algorithmic bytes: both operands once, every output once, the epilogue addend once
     nbytes = A.element_size() * (M * K + K * N) + M * N * ((4 if C is not None else 0) + (2 if Cb is not None else 0) +
@@ -219,6 +224,9 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
         call("gemm_f32", transA, transB, M, N, K, A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
              ctypes.addressof(ep), info=info)
 
+
+# one GEMM for both halves of d[v | q] in the relation backward (EKAID_B200_FUSE_DVQ=0: two launches, for A/B measurements)
+FUSE_DVQ = os.environ.get("EKAID_B200_FUSE_DVQ", "1") != "0"
 
 # fp32 GEMMs: "split" (default) = 3 x bf16 split-precision products on tcgen05 for every product big enough to fill the
 # machine, "simt" = the register-tiled fp32 FMA kernel everywhere (the test oracle of the split path)
@@ -1386,12 +1394,21 @@ class RelationFn(torch.autograd.Function):
             with fk.branch(0):
                 gemm(dSf, XT, D, D + Dq, M, transA=1, transB=1, C=dWsw)            # XT = dropped [v | q]
                 colsum_many([(dOut, dbout), (dQKZ[:, :D], dbq), (dQKZ[:, D:2 * D], dbk), (dSf, dbsw)], M)   # one launch
-            with fk.branch(1):
-                # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogues
-                # (index = row * (D + Dq) + column)
-                gemm(dSf, WswT[:, D:], M, Dq, D, transB=1, C=dVq, drop=s1 + (D + Dq, D))
-                call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(), dqv.data_ptr())
-            gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX, drop=s1 + (D + Dq, 0))   # + residual gradient
+            # d[v | q] = dropout-mask * (dSf W_sw): the mask of the forward concat is re-applied in the GEMM epilogue
+            # (index = row * (D + Dq) + column).  Tensor-core path: ONE product over all D + Dq columns -- the node half plus
+            # the residual gradient goes to dX, the question half to dVq (fp32 output split by column): twice the tiles per
+            # launch instead of two 1.4-wave launches.
+            if pc.bf16 and FUSE_DVQ:
+                gemm(dSf, WswT, M, D + Dq, D, transB=1, addend=dXn, add_n1=D, C=dX, C2=dVq, c_n1=D, drop=s1 + (D + Dq, 0))
+                with fk.branch(1, resync=True):          # (the row sum waits for the product just enqueued on this stream)
+                    call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(),
+                         dqv.data_ptr())
+            else:
+                with fk.branch(1):
+                    gemm(dSf, WswT[:, D:], M, Dq, D, transB=1, C=dVq, drop=s1 + (D + Dq, D))
+                    call("group_rowsum", 0, dVq.data_ptr(), dVq.stride(0), N, B, G // B, Dq, flags.data_ptr(),
+                         dqv.data_ptr())
+                gemm(dSf, WswT[:, :D], M, D, D, transB=1, addend=dXn, C=dX, drop=s1 + (D + Dq, 0))   # + residual gradient
             fk.join()
         fkp.join()
         return (None, None, None, None, None, dX, None, dqv, dWsw, dbsw, dWq, dbq, dWk, dbk, dWo2, dbout, dp0, dp1,

@@ -5,7 +5,9 @@ There is no CPU fallback: if the shared library is missing the import of a kerne
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import gc
 import os
 import re
 from typing import Dict, List, Tuple
@@ -30,6 +32,7 @@ class Epilogue(ctypes.Structure):
         ("cb_fmt", ctypes.c_int32), ("cb_n1", ctypes.c_int32),
         ("Cb2", ctypes.c_void_p), ("ldcb2", ctypes.c_int64),
         ("cb2_fmt", ctypes.c_int32), ("cb2_n0", ctypes.c_int32),
+        ("C2", ctypes.c_void_p), ("ldc2", ctypes.c_int64), ("c_n1", ctypes.c_int32), ("add_n1", ctypes.c_int32),
     ]
 
 
@@ -122,6 +125,25 @@ def call(name: str, *args, info=None) -> None:
         PROFILE.append((name, e0, e1, info))
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
+
+
+@contextlib.contextmanager
+def graph_capture(graph: "torch.cuda.CUDAGraph"):
+    """`with torch.cuda.graph(graph)` with Python's cyclic garbage collector held off for the duration of the capture.
+    torch captures in the `global` error mode, where a prohibited runtime call from anywhere in the process invalidates the
+    capture -- and torch.cuda.graph no longer collects garbage before it starts (torch/cuda/graphs.py, `force_cudagraph_gc`).
+    A collection that happens to run while the step is being captured and frees an OLD CUDAGraph (a runner of another
+    batch size, a previous GraphFusionStep: they sit in reference cycles) calls cudaGraphExecDestroy mid-capture, and every
+    later launch fails with cudaErrorStreamCaptureInvalidated.  So: collect first, then keep the collector off inside."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 _device_ok = False

@@ -576,7 +576,7 @@ class DynamicSpeaker(nn.Module):
                         torch.cuda.synchronize()
                     g = torch.cuda.CUDAGraph()
                     before = lib.LAUNCHES
-                    with torch.cuda.graph(g):
+                    with lib.graph_capture(g):
                         r.run_block(t0, t1, first=(bi == 0))
                     r.graphs[(t0, t1)] = g
                     r.graph_launches[(t0, t1)] = lib.LAUNCHES - before

@@ -474,7 +474,7 @@ class GraphFusionStep:
             # after a replay each kernel's duration inside the replayed step can be read with cudaEventElapsedTime
             lib.PROFILE, lib.PROFILE_EXTERNAL = [], True
         try:
-            with torch.cuda.graph(self._graph):
+            with lib.graph_capture(self._graph):
                 self._static_out = body()
         finally:
             if profile:

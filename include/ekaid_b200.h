@@ -75,6 +75,14 @@ typedef struct ekaid_epilogue {
   int64_t ldcb2;
   int32_t cb2_fmt;
   int32_t cb2_n0;
+  /* the fp32 output may be split by column too: C2 (optional) receives columns n >= c_n1 at C2[m * ldc2 + n - c_n1], C the
+   * rest; the addend is applied to columns n < add_n1 only (0 = all).  c_n1 and add_n1 are multiples of 32.  ONE GEMM then
+   * yields both halves of d[v | q] = mask * (dSf W_sw) in the backward of self_weights (graph_att.py:80): the node half plus
+   * the residual gradient into dX, the question half into its own buffer. */
+  float* C2;
+  int64_t ldc2;
+  int32_t c_n1;
+  int32_t add_n1;
 } ekaid_epilogue_t;
 
 /* Dropout convention (train mode; eval / p = 0 passes seed = NULL): masks are never stored.  Every dropout site of the

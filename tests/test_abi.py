@@ -41,6 +41,36 @@ def test_epilogue_struct_layout_matches_header(tmp_path):
     assert nums[1:] == [getattr(Epilogue, f).offset for f in fields]
 
 
+def test_graph_capture_holds_the_garbage_collector_off(monkeypatch):
+    """lib.graph_capture: no cyclic collection may run while a step is being captured (an old CUDAGraph freed mid-capture
+    invalidates it); the collector's previous state comes back afterwards, also when the capture raises."""
+    import gc
+    from ekaid_b200 import lib
+    seen = {}
+
+    @contextlib.contextmanager
+    def fake_graph(g):
+        seen["enabled_inside"] = gc.isenabled()
+        yield
+
+    monkeypatch.setattr(torch.cuda, "graph", fake_graph)
+    assert gc.isenabled()
+    with lib.graph_capture(object()):
+        assert not gc.isenabled()
+    assert gc.isenabled() and seen["enabled_inside"] is False
+    with pytest.raises(RuntimeError):
+        with lib.graph_capture(object()):
+            raise RuntimeError("capture failed")
+    assert gc.isenabled()
+    gc.disable()
+    try:
+        with lib.graph_capture(object()):
+            pass
+        assert not gc.isenabled()                # was off before: stays off
+    finally:
+        gc.enable()
+
+
 def test_no_gpu_fails_loudly():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

@@ -87,6 +87,15 @@ def test_gemm_epilogue(dtype):
                  / ref.abs().max()) < 2e-5
     if Cb is not None:
         assert float((Cb.float() - torch.tanh(ref)).abs().max()) < 1e-2
+    # fp32 output split by column (C2 from column 512 on) with the addend on the first 256 columns only, plus dropout-free
+    # bias: what the relation backward uses to get both halves of d[v | q] from one product
+    Ca = torch.full((M, 512), float("nan"), device=dev)
+    Cc = torch.full((M, N - 512), float("nan"), device=dev)
+    gemm(A, W[:, :K], M, N, K, bias=bias, addend=add, add_n1=256, C=Ca, C2=Cc, c_n1=512)
+    full = A.float() @ W[:, :K].float().t() + bias
+    full[:, :256] += add[:, :256]
+    tol2 = 1e-5 * float(full.abs().max()) + 2e-5
+    assert float((Ca - full[:, :512]).abs().max()) < tol2 and float((Cc - full[:, 512:]).abs().max()) < tol2
     # in-place accumulate (addend aliases C), narrow N with scalar tail path
     C2 = add[:, :100].clone()
     gemm(A, W[:100, :K], M, 100, K, addend=C2, act=ACT_RELU, C=C2)
