@@ -8,6 +8,7 @@
 //
 // P is split into bf16 hi + lo parts in the forward so the attention weights keep 16 significant bits.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -70,6 +71,9 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
   ek_pdl_prologue();
   extern __shared__ __align__(16) uint8_t smraw[];
   const unsigned long long sd = ek_seed(dr);
+  const bool don = dr.seed != nullptr && dr.p > 0.f;          // dropout constants of the epilogue (common.cuh rule)
+  const unsigned int dthr = (unsigned int)(dr.p * 65536.0f);
+  const float dkeep = 1.f / (1.f - dr.p);
   const int PS = kchunk + 8;                        // P row pitch (elements)
   bf16* Zs = (bf16*)smraw;                          // [kchunk][ZS]
   bf16* Phi = Zs + (size_t)kchunk * ZS;             // [MR][PS]
@@ -169,13 +173,14 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
       const int item = warp + it * 8;
       const int mt = item >> 1, nh = item & 1;
       const int colb = c0 + nh * 64 + 2 * (lane & 3);          // column of nt = 0
-      size_t rbase[2];
+      size_t rbase[2], tbase[2];                             // element offsets of this thread's two rows in Xout / XoutT
       bool rok[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int i = r0 + mt * 16 + (lane >> 2) + hh * 8;
         rok[hh] = i < N;
         rbase[hh] = ((size_t)g * N + (rok[hh] ? i : 0)) * D + colb;
+        tbase[hh] = ((size_t)g * N + (rok[hh] ? i : 0)) * (size_t)ldt + colb;
       }
       // two halves of four column tiles: the loads of a half are all in flight before its first use, and the live
       // operand registers stay at 24 (three CTAs per SM need <= 85 registers per thread)
@@ -205,19 +210,22 @@ agg_fwd_mma_kernel(const float* __restrict__ P, const bf16* __restrict__ QKZ, lo
             x1 = xi[hh][nt].y + o1;
           } else {
             // train mode: Dropout(0.2) on the doubled output before the ReLU (graph_att.py:103-104)
-            float dm[2];
-            ek_drop_multv<2>(dr, sd, idx, dm);                 // even column: both lanes come from one draw
-            p0 = (o0 + o0) * dm[0];
-            p1 = (o1 + o1) * dm[1];
+            // (idx is even -- D % 8 == 0, even column -- so both elements come from one draw: ek_drop_multv<2>'s rule with
+            // the threshold hoisted and without its odd-index fallback, which doubled the size of this epilogue)
+            float dm0 = 1.f, dm1 = 1.f;
+            if (don) {
+              const unsigned long long z = ek_draw64(sd, dr.site, idx >> 2) >> (16 * (idx & 3));
+              dm0 = ((unsigned int)z & 0xFFFFu) >= dthr ? dkeep : 0.f;
+              dm1 = ((unsigned int)(z >> 16) & 0xFFFFu) >= dthr ? dkeep : 0.f;
+            }
+            p0 = (o0 + o0) * dm0;
+            p1 = (o1 + o1) * dm1;
             x0 = xi[hh][nt].x + fmaxf(p0, 0.f);
             x1 = xi[hh][nt].y + fmaxf(p1, 0.f);
           }
           *(float2*)(Xout + idx) = make_float2(x0, x1);
-          if (XoutT) {
-            const size_t row = idx / D;                         // only when the operand copy has its own pitch
-            const size_t tix = (ldt == D) ? idx : row * ldt + (idx - row * D);
-            *(uint32_t*)(XoutT + tix) = F16 ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
-          }
+          if (XoutT)          // (the operand copy may have its own pitch; no 64-bit `idx / D` per element to find its row)
+            *(uint32_t*)(XoutT + tbase[hh] + nt * 8) = F16 ? pack_f16x2_sat(x0, x1) : pack_bf16x2(x0, x1);
           if (mask) {
             uchar2 mk;
             mk.x = p0 > 0.f ? 1 : 0;
@@ -386,12 +394,23 @@ agg_bwd_mma_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
 // The CTA walks the D/128 column slices itself: P is staged once, Z slices are double-buffered with cp.async (the next
 // slice streams in while this one is multiplied), and dP = sum_c dout[i,c] Z[(h,j),c] stays in registers across the
 // slices -- no [slices, G, N, H*K] partial tensor, no re-reading of P, and loads overlap the MMAs.
-__global__ void __launch_bounds__(256, 1)
+// NW = warps per CTA.  With 8 warps (two per scheduler, 238 registers) the kernel was bound by the latency of its own
+// dependent instructions: 27 % issue slots busy, 7.4 cycles between two instructions of a warp, stall_wait /
+// short_scoreboard on top (profiles/r02_ncu_full_aggbwdimg.csv).  16 warps split every warp's accumulators in two (dZ: 64
+// instead of 128 columns per item, dP: a quarter instead of half of the (h,j) tiles), which fits 128 registers and gives
+// every scheduler four warps to choose from; shared memory and global traffic are unchanged.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
 agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ mask, const bf16* __restrict__ QKZ,
                    long long ld, int D, int N, int Kn, int H, bf16* __restrict__ dQKZ, float* __restrict__ dOut,
                    float* __restrict__ dP, float gscale, const bf16* __restrict__ Phl) {
   ek_pdl_prologue();
   constexpr int MR = 64;
+  constexpr int NTHR = NW * 32;
+  constexpr int NSPL = NW / 8;                      // a dZ item covers NC / NSPL columns of one 16-row (h,j) tile
+  constexpr int ZC = NC / NSPL;
+  constexpr int NPART = NW / 4;                     // warps that share one 16-row query tile of dP
+  constexpr int ACCN = 32 / NPART;                  // (h,j) 8-column tiles of dP per warp (HKP < 256: at most 31 in all)
   extern __shared__ __align__(16) uint8_t smraw[];
   const int HK = H * Kn;
   const int HKP = (HK + 15) & ~15;
@@ -408,13 +427,13 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
   auto issue_slice = [&](int s) {
     const int c0 = s * NC;
     load_z_chunk(Zs0 + (size_t)(s & 1) * HKP * ZS, QKZ, ld, D, g, N, Kn, HK, 0, HKP, c0, 2 * D);
-    for (int e = tid; e < MR * (NC / 4); e += 256) {           // 16-byte pieces of the fp32 rows
+    for (int e = tid; e < MR * (NC / 4); e += NTHR) {          // 16-byte pieces of the fp32 rows
       const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
       float* dst = raw + i * NC + c;
       if (i < N) cp_async16(dst, dXout + ((size_t)g * N + i) * D + c0 + c);
       else *(float4*)dst = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int e = tid; e < MR * (NC / 16); e += 256) {
+    for (int e = tid; e < MR * (NC / 16); e += NTHR) {
       const int i = e / (NC / 16), c = (e % (NC / 16)) * 16;
       uint8_t* dst = mk + i * NC + c;
       if (i < N) cp_async16(dst, mask + ((size_t)g * N + i) * D + c0 + c);
@@ -424,7 +443,7 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
 
   {
     const int cpr = HKP / 8;
-    for (int e = tid; e < MR * cpr; e += 256) {
+    for (int e = tid; e < MR * cpr; e += NTHR) {
       const int i = e / cpr, ch = e % cpr;
       bf16* dst = Ps + i * PS + ch * 8;
       if (i < N && ch * 8 < HK) cp_async16(dst, Phl + ((size_t)g * N + i) * HK + ch * 8);
@@ -433,14 +452,14 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
   }
   issue_slice(0);
 
-  // this warp's share of dP: 16 query rows x half of the (h,j) tiles, accumulated over all slices
+  // this warp's share of dP: 16 query rows x 1/NPART of the (h,j) tiles, accumulated over all slices
   const int ntiles = HKP / 8;
-  const int nhalf = (ntiles + 1) / 2;               // <= 16
-  const int pmt = warp >> 1, pnb = (warp & 1) * nhalf;
-  const int pcnt = min(nhalf, ntiles - pnb);
-  float accp[16][4];
+  const int nper = (ntiles + NPART - 1) / NPART;    // <= ACCN
+  const int pmt = warp / NPART, pnb = (warp % NPART) * nper;
+  const int pcnt = max(0, min(nper, ntiles - pnb));
+  float accp[ACCN][4];
 #pragma unroll
-  for (int a = 0; a < 16; ++a)
+  for (int a = 0; a < ACCN; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) accp[a][c] = 0.f;
 
@@ -450,7 +469,7 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
     cp_async_wait_all();
     __syncthreads();                                 // slice s has landed; everybody is done with slice s-1
     // dout = gscale * mask * dX  -> global (fp32, for the b_out column sum) and shared (bf16 operand)
-    for (int e = tid; e < MR * (NC / 4); e += 256) {
+    for (int e = tid; e < MR * (NC / 4); e += NTHR) {
       const int i = e / (NC / 4), c = (e % (NC / 4)) * 4;
       const float4 d = *(const float4*)(raw + i * NC + c);
       const uchar4 m = *(const uchar4*)(mk + i * NC + c);
@@ -466,10 +485,11 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
     __syncthreads();
     if (s + 1 < S) issue_slice(s + 1);               // streams in while this slice is multiplied
     // ---- dZ[(h,j), c] = sum_i P[i,(h,j)] dout[i,c]
-    for (int mt = warp; mt < HKP / 16; mt += 8) {
-      float acc[16][4];
+    for (int item = warp; item < (HKP / 16) * NSPL; item += NW) {
+      const int mt = item / NSPL, zc0 = (item % NSPL) * ZC;      // 16 (h,j) rows x columns [zc0, zc0 + ZC) of the slice
+      float acc[2 * (ZC / 16)][4];
 #pragma unroll
-      for (int a = 0; a < 16; ++a)
+      for (int a = 0; a < 2 * (ZC / 16); ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
 #pragma unroll
@@ -479,10 +499,10 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
         const int acol = mt * 16 + ((lane >> 3) & 1) * 8;
         ldsm_x4_t(af, Ps + arow * PS + acol);
 #pragma unroll
-        for (int np = 0; np < 8; ++np) {
+        for (int np = 0; np < ZC / 16; ++np) {
           uint32_t bfr[4];
           const int brow = kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-          const int bcol = np * 16 + (lane >> 4) * 8;
+          const int bcol = zc0 + np * 16 + (lane >> 4) * 8;
           ldsm_x4_t(bfr, dOs + brow * ZS + bcol);
           mma_bf16_16816(acc[2 * np], af, bfr[0], bfr[1]);
           mma_bf16_16816(acc[2 * np + 1], af, bfr[2], bfr[3]);
@@ -494,14 +514,14 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
       for (int hh = 0; hh < 2; ++hh) {
         const int k = mt * 16 + (lane >> 2) + hh * 8;
         const int h = k / Kn, j = k - h * Kn;
-        rowp[hh] = (k < HK) ? dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + 2 * (lane & 3)
+        rowp[hh] = (k < HK) ? dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + zc0 + 2 * (lane & 3)
                             : nullptr;
       }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         if (rowp[hh] == nullptr) continue;
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt)
+        for (int nt = 0; nt < 2 * (ZC / 16); ++nt)
           *(__nv_bfloat162*)(rowp[hh] + nt * 8) = __floats2bfloat162_rn(acc[nt][2 * hh], acc[nt][2 * hh + 1]);
       }
     }
@@ -513,7 +533,7 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
       const int acol = kt * 16 + (lane >> 4) * 8;
       ldsm_x4(af, dOs + arow * ZS + acol);
 #pragma unroll
-      for (int np = 0; np < 8; ++np) {
+      for (int np = 0; np < ACCN / 2; ++np) {
         if (2 * np < pcnt) {
           uint32_t bfr[4];
           int nrow = (pnb + 2 * np) * 8 + (lane >> 4) * 8 + (lane & 7);
@@ -528,7 +548,7 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
   }
   float* dPg = dP + (size_t)g * N * HK;
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt) {
+  for (int nt = 0; nt < ACCN; ++nt) {
     if (nt >= pcnt) continue;
     const int kk = (pnb + nt) * 8 + 2 * (lane & 3);
 #pragma unroll
@@ -905,10 +925,18 @@ int ek_agg_bwd_mma_launch(const float* dXout, const uint8_t* mask, const float* 
   if (Phl && (((H * Kn) % 8) || ((uintptr_t)Phl & 15))) Phl = nullptr;
   if (ek_agg_bwd_img_ok(D, N, Kn, H, Phl != nullptr) && !((uintptr_t)dXout & 15) && !((uintptr_t)mask & 15)) {
     const size_t smem = agg_bwd_img_smem(N, Kn, H);
-    static size_t cimg = 0;
-    int rc = set_smem(agg_bwd_img_kernel, smem, cimg, "agg_bwd_img");
-    if (rc) return rc;
-    ek_launch(agg_bwd_img_kernel, G, 256, smem, st, dXout, mask, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, gscale, Phl);
+    static size_t cimg8 = 0, cimg16 = 0;
+    // 16 warps per CTA by default; EKAID_B200_AGG_BWD_WARPS=8 selects the 8-warp form (A/B measurements)
+    static const int nwarps = [] { const char* e = getenv("EKAID_B200_AGG_BWD_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+    if (nwarps == 16) {
+      int rc = set_smem(agg_bwd_img_kernel<16>, smem, cimg16, "agg_bwd_img");
+      if (rc) return rc;
+      ek_launch(agg_bwd_img_kernel<16>, G, 512, smem, st, dXout, mask, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, gscale, Phl);
+    } else {
+      int rc = set_smem(agg_bwd_img_kernel<8>, smem, cimg8, "agg_bwd_img");
+      if (rc) return rc;
+      ek_launch(agg_bwd_img_kernel<8>, G, 256, smem, st, dXout, mask, QKZ, ld, D, N, Kn, H, dQKZ, dOut, dPpart, gscale, Phl);
+    }
     EK_CHECK_LAUNCH();
     return EK_OK;
   }

@@ -37,17 +37,27 @@ embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict
   const int v = blockIdx.x;
   const int total = B * L;
   if (threadIdx.x < 32) {
+    // eight token loads in flight per pass (one at a time made this scan -- 40 dependent L2 round trips at B*L = 1280 --
+    // the whole 46 us of the kernel, on the serial tail of the step); the list order (ascending row) is unchanged
+    constexpr int U = 8;
     int n = 0;
-    for (int r0 = 0; r0 < total; r0 += 32) {
-      const int row = r0 + threadIdx.x;
-      bool hit = false;
-      if (row < total) {
-        const int l = row / B, b = row % B;
-        hit = (q[(size_t)b * L + l] == v);
+    for (int r0 = 0; r0 < total; r0 += 32 * U) {
+      bool hit[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int row = r0 + u * 32 + (int)threadIdx.x;
+        hit[u] = false;
+        if (row < total) {
+          const int l = row / B, b = row % B;
+          hit[u] = (q[(size_t)b * L + l] == v);
+        }
       }
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) rows[n + __popc(m & ((1u << threadIdx.x) - 1))] = row;
-      n += __popc(m);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned m = __ballot_sync(0xffffffffu, hit[u]);
+        if (hit[u]) rows[n + __popc(m & ((1u << threadIdx.x) - 1))] = r0 + u * 32 + (int)threadIdx.x;
+        n += __popc(m);
+      }
     }
     if (threadIdx.x == 0) count = n;
   }
@@ -56,8 +66,10 @@ embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + lane;
   float s = 0.f;
-  if (c < ed)
+  if (c < ed) {
+#pragma unroll 4
     for (int k = rl; k < n; k += 4) s += dE[(size_t)rows[k] * ldde + c];
+  }
   part[rl][lane] = s;
   __syncthreads();
   if (rl == 0 && c < ed) demb[(size_t)v * ed + c] = ((part[0][lane] + part[1][lane]) + part[2][lane]) + part[3][lane];
