@@ -43,17 +43,22 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 // stage rows k0..k0+kc of the (h,j)-indexed Z matrix, columns [c0, c0+NC), into Zs[kc_pad][ZS]
 __device__ __forceinline__ void load_z_chunk(bf16* Zs, const bf16* __restrict__ QKZ, long long ld, int D, int g, int N,
                                              int Kn, int HK, int k0, int kc_pad, int c0, int zoff) {
+  // thread -> (row kk, 16-byte piece ch); a thread's rows are kstep apart, so (h, j) = (k / Kn, k % Kn) is divided out once
+  // and stepped from row to row (a division per copy was a third of the instructions the 16-warp aggregate backward issued)
   const int tid = threadIdx.x;
-  for (int e = tid; e < kc_pad * (NC / 8); e += blockDim.x) {
-    const int kk = e / (NC / 8), ch = e % (NC / 8);
-    const int k = k0 + kk;
+  const int ch = tid % (NC / 8);
+  const int kstep = blockDim.x / (NC / 8);          // block sizes are multiples of NC / 8 = 16
+  const bool cok = c0 + ch * 8 < D;
+  int k = k0 + tid / (NC / 8);
+  int h = k / Kn, j = k - h * Kn;
+  for (int kk = tid / (NC / 8); kk < kc_pad; kk += kstep, k += kstep) {
     bf16* dst = Zs + kk * ZS + ch * 8;
-    if (k < HK && c0 + ch * 8 < D) {
-      const int h = k / Kn, j = k % Kn;
+    if (k < HK && cok)
       cp_async16(dst, QKZ + ((size_t)g * N + j) * ld + (size_t)zoff + (size_t)h * D + c0 + ch * 8);
-    } else {
+    else
       *(uint4*)dst = make_uint4(0, 0, 0, 0);
-    }
+    j += kstep;
+    while (j >= Kn) { j -= Kn; ++h; }
   }
 }
 
@@ -485,7 +490,13 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
     __syncthreads();
     if (s + 1 < S) issue_slice(s + 1);               // streams in while this slice is multiplied
     // ---- dZ[(h,j), c] = sum_i P[i,(h,j)] dout[i,c]
-    for (int item = warp; item < (HKP / 16) * NSPL; item += NW) {
+    // (CTA-uniform trip counts and no warp-dependent branch around the ldmatrix / mma instructions below: the compiler
+    // cannot see that `warp` is uniform inside a warp and would fence every one of them with WARPSYNC / BSSY otherwise; a
+    // warp without an item in the last round multiplies tile 0 again and stores nothing)
+    const int nitems = (HKP / 16) * NSPL;
+    for (int it0 = 0; it0 < nitems; it0 += NW) {
+      const bool live = it0 + warp < nitems;
+      const int item = live ? it0 + warp : 0;
       const int mt = item / NSPL, zc0 = (item % NSPL) * ZC;      // 16 (h,j) rows x columns [zc0, zc0 + ZC) of the slice
       float acc[2 * (ZC / 16)][4];
 #pragma unroll
@@ -514,8 +525,8 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
       for (int hh = 0; hh < 2; ++hh) {
         const int k = mt * 16 + (lane >> 2) + hh * 8;
         const int h = k / Kn, j = k - h * Kn;
-        rowp[hh] = (k < HK) ? dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + zc0 + 2 * (lane & 3)
-                            : nullptr;
+        rowp[hh] = (live && k < HK) ? dQKZ + ((size_t)g * N + j) * ld + 2 * (size_t)D + (size_t)h * D + c0 + zc0 + 2 * (lane & 3)
+                                    : nullptr;
       }
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -533,16 +544,14 @@ agg_bwd_img_kernel(const float* __restrict__ dXout, const uint8_t* __restrict__ 
       const int acol = kt * 16 + (lane >> 4) * 8;
       ldsm_x4(af, dOs + arow * ZS + acol);
 #pragma unroll
-      for (int np = 0; np < ACCN / 2; ++np) {
-        if (2 * np < pcnt) {
-          uint32_t bfr[4];
-          int nrow = (pnb + 2 * np) * 8 + (lane >> 4) * 8 + (lane & 7);
-          if (nrow >= HKP) nrow = HKP - 1;           // odd tile count: second tile unused
-          const int kcol = kt * 16 + ((lane >> 3) & 1) * 8;
-          ldsm_x4(bfr, Zs + nrow * ZS + kcol);
-          mma_bf16_16816(accp[2 * np], af, bfr[0], bfr[1]);
-          if (2 * np + 1 < pcnt) mma_bf16_16816(accp[2 * np + 1], af, bfr[2], bfr[3]);
-        }
+      for (int np = 0; np < ACCN / 2; ++np) {          // all tile pairs, unconditionally (see above): tiles >= pcnt
+        uint32_t bfr[4];                                //  read a clamped row and are never stored
+        int nrow = (pnb + 2 * np) * 8 + (lane >> 4) * 8 + (lane & 7);
+        if (nrow >= HKP) nrow = HKP - 1;
+        const int kcol = kt * 16 + ((lane >> 3) & 1) * 8;
+        ldsm_x4(bfr, Zs + nrow * ZS + kcol);
+        mma_bf16_16816(accp[2 * np], af, bfr[0], bfr[1]);
+        mma_bf16_16816(accp[2 * np + 1], af, bfr[2], bfr[3]);
       }
     }
   }
@@ -716,7 +725,7 @@ softmax_fwd_mma_kernel(const bf16* __restrict__ QKZ, long long ld, int D, const 
 //   ds = P * (dP - sum_j P dP), dP = sum_slices dPpart;  outputs dgbias / dlbias_part;  ds_m = cond > 0 ? ds : 0
 //   dQ = scale * ds_m K,  dK = scale * ds_m^T Q      (ds_m kept as bf16 hi + lo)
 template <int MR>   // padded rows for both queries and keys: 64 or 128
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MR == 64 ? 2 : 1)      // MR = 64: 86 KB of shared memory, two CTAs per SM
 softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dPpart, int nslices,
                        const bf16* __restrict__ QKZ, long long ld, int D, const float* __restrict__ cond, int N, int Kn,
                        int H, bf16* __restrict__ dQKZ, float* __restrict__ dlbias_part, float* __restrict__ dgbias) {
@@ -750,7 +759,8 @@ softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dP
     constexpr int NR = (MR + 31) / 32;         // key columns per lane
     const size_t sstride = (size_t)G * N * HK; // one slice of dPpart
 #pragma unroll 2
-    for (int i = warp; i < MR; i += 8) {
+    for (int i0 = 0; i0 < MR; i0 += 8) {         // (uniform trip count: the warp reductions below need no reconvergence fence)
+      const int i = i0 + warp;
       const bool iok = i < N;
       const size_t row = (size_t)g * N + (iok ? i : 0);
       const float* Pr = P + (row * H + h) * Kn;
@@ -798,9 +808,16 @@ softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dP
   // items: (which: dQ/dK, 16-row tile, 128-column block of d); every item has MR/16 k-steps
   const int nblk = dh / 128 + ((dh % 128) ? 1 : 0);
   const int per = (MR / 16) * nblk;
-  for (int item = warp; item < 2 * per; item += 8) {
-    const int which = item / per;
-    const int mt = (item % per) / nblk, nb = (item % per) % nblk;
+  // which (dQ / dK) and the round are CTA-uniform loop variables, and a warp without an item in the last round recomputes
+  // item 0 and stores nothing: no warp-dependent branch around the ldmatrix / mma instructions (the compiler cannot see
+  // that `warp` is uniform inside a warp and fenced them with WARPSYNC / BSSY: 61 of them for 128 HMMA)
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which)
+#pragma unroll 1
+  for (int it0 = 0; it0 < per; it0 += 8) {
+    const bool live = it0 + warp < per;
+    const int pitem = live ? it0 + warp : 0;
+    const int mt = pitem / nblk, nb = pitem % nblk;
     float acc[16][4];
 #pragma unroll
     for (int a = 0; a < 16; ++a)
@@ -821,15 +838,14 @@ softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dP
       }
 #pragma unroll
       for (int np = 0; np < 8; ++np) {
-        const int ncol = nb * 128 + np * 16;
-        if (ncol < dh) {
-          uint32_t bfr[4];
-          ldsm_x4_t(bfr, Bs + (kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * DS + ncol + (lane >> 4) * 8);
-          mma_bf16_16816(acc[2 * np], ah, bfr[0], bfr[1]);
-          mma_bf16_16816(acc[2 * np], al, bfr[0], bfr[1]);
-          mma_bf16_16816(acc[2 * np + 1], ah, bfr[2], bfr[3]);
-          mma_bf16_16816(acc[2 * np + 1], al, bfr[2], bfr[3]);
-        }
+        // (columns beyond dh -- only when dh is no multiple of 128 -- read column block 0 and are not stored)
+        const int ncol = (nb * 128 + np * 16 < dh) ? nb * 128 + np * 16 : 0;
+        uint32_t bfr[4];
+        ldsm_x4_t(bfr, Bs + (kt * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * DS + ncol + (lane >> 4) * 8);
+        mma_bf16_16816(acc[2 * np], ah, bfr[0], bfr[1]);
+        mma_bf16_16816(acc[2 * np], al, bfr[0], bfr[1]);
+        mma_bf16_16816(acc[2 * np + 1], ah, bfr[2], bfr[3]);
+        mma_bf16_16816(acc[2 * np + 1], al, bfr[2], bfr[3]);
       }
     }
     // rows of dK beyond Kn are zero by construction (ds columns j >= Kn are zero), rows >= N are not written
@@ -841,7 +857,7 @@ softmax_bwd_mma_kernel(const float* __restrict__ P, const float* __restrict__ dP
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int r = mt * 16 + (lane >> 2) + hh * 8;
-        if (r < N)
+        if (live && r < N)
           *(__nv_bfloat162*)(dst + (size_t)r * ld + d) =
               __floats2bfloat162_rn(scale * acc[nt][2 * hh], scale * acc[nt][2 * hh + 1]);
       }
