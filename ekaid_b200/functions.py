@@ -225,6 +225,9 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
              ctypes.addressof(ep), info=info)
 
 
+# question path: only what the recurrence needs is enqueued in front of it (EKAID_B200_QHEAD_SPLIT=0: everything in order)
+QHEAD_SPLIT = os.environ.get("EKAID_B200_QHEAD_SPLIT", "1") != "0"
+
 # one GEMM for both halves of d[v | q] in the relation backward (EKAID_B200_FUSE_DVQ=0: two launches, for A/B measurements)
 FUSE_DVQ = os.environ.get("EKAID_B200_FUSE_DVQ", "1") != "0"
 
@@ -660,7 +663,8 @@ _barrier_bufs = {}
 
 
 def _barrier_ws(dev):
-    """4 bytes of device memory per (device, stream) for the persistent GRU kernels' grid barrier."""
+    """Two zeroed words of device memory per (device, stream) for the persistent GRU kernels' grid barrier; every launch
+    leaves them zero again (gru_seq.cu: grid_barrier_retire), so launches ordered on one stream share them."""
     key = (str(dev), torch.cuda.current_stream().cuda_stream)
     if key not in _barrier_bufs:
         _barrier_bufs[key] = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -821,6 +825,7 @@ class QuestionFn(torch.autograd.Function):
         E = torch.empty(L * B, 2 * ed, dtype=pc.TF, device=dev)
         call("embed_gather", pc.ff, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
         srcs = [_f32c(Wih), _f32c(Whh), _f32c(W1)]
+        fkq = None
         if pc.bf16:
             WihT, WhhT, W1T = (torch.empty(t.shape, dtype=pc.TF, device=dev) for t in srcs)
             jobs = list(zip(srcs, (WihT, WhhT, W1T)))
@@ -829,7 +834,16 @@ class QuestionFn(torch.autograd.Function):
                 jobs += list(zip(srcs, (WihB, WhhB, W1B)))
             else:
                 WihB, WhhB, W1B = WihT, WhhT, W1T
-            cast_many(pc, jobs)
+            if QHEAD_SPLIT and len(jobs) > 2:
+                # This stream is the serial head of the step (nothing of the first relation encoder can start before qv):
+                # only the two copies the recurrence reads go in front of it; W1's copy and the backward's bf16 copies are
+                # made on a branch stream next to the recurrence and joined before the attention MLP.
+                cast_many(pc, jobs[:2])
+                fkq = Fork(dev, 1, pool="qhead")
+                with fkq.branch(0):
+                    cast_many(pc, jobs[2:])
+            else:
+                cast_many(pc, jobs)
         else:
             WihT, WhhT, W1T = srcs
             WihB, WhhB, W1B = srcs
@@ -837,8 +851,18 @@ class QuestionFn(torch.autograd.Function):
         gi = gemm_f32out(E, WihT, L * B, 3 * H, 2 * ed, bias=bihc)
         Hs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
         # operand-type copy with one leading zero block: HsT[t] = h_{t-1}, so "previous h of every step" is a view
-        HsT = torch.zeros((L + 1) * B, H, dtype=pc.TF, device=dev)
-        HsB = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev) if dual else HsT
+        # (the recurrence writes every other block; only block 0 is cleared)
+        if QHEAD_SPLIT:
+            HsT = torch.empty((L + 1) * B, H, dtype=pc.TF, device=dev)
+            HsT[:B].zero_()
+            if dual:
+                HsB = torch.empty((L + 1) * B, H, dtype=pc.T, device=dev)
+                HsB[:B].zero_()
+            else:
+                HsB = HsT
+        else:
+            HsT = torch.zeros((L + 1) * B, H, dtype=pc.TF, device=dev)
+            HsB = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev) if dual else HsT
         gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
         if _gru_seq_ok(pc, dev, B, H):
             # the whole recurrence in one persistent launch (gru_seq.cu)
@@ -857,6 +881,8 @@ class QuestionFn(torch.autograd.Function):
                      bhhc.data_ptr())
             if dual:
                 bcopy([(HsT[B:], HsB[B:])])
+        if fkq is not None:
+            fkq.join()                            # W1T and the bf16 copies are complete from here on
         HsT_cur = HsT[B:]
         if drop is not None and drop.on:          # Dropout(0.2) on the input of W1 (language_model.py:123-124)
             Hd = torch.empty(L * B, H, dtype=pc.TF, device=dev)
@@ -976,11 +1002,12 @@ class QuestionFn(torch.autograd.Function):
             gemm_f32out(dghT, HsT[:L * B], 3 * H, H, L * B, transA=1, transB=1, out=dWhh)
             colsum(dgh, L * B, 3 * H, out=dbhh)
         with torch.cuda.stream(br2):
-            gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1, out=dE)       # only the trainable table's columns
-            call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr(),
-                 ctx.padding_idx)
-        gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=dWih)
-        colsum(dgi, L * B, 3 * H, out=dbih)
+            gemm_f32out(dgiT, E, 3 * H, 2 * ed, L * B, transA=1, transB=1, out=dWih)
+            colsum(dgi, L * B, 3 * H, out=dbih)
+        # the two-kernel chain (dE, then the table gradient) stays on this stream: it starts without a cross-stream hop,
+        # and its second kernel runs next to the other two products instead of after them
+        gemm_f32out(dgiT, WihT, L * B, ed, 3 * H, transB=1, out=dE)           # only the trainable table's columns
+        call("embed_gather_bwd", q.data_ptr(), dE.data_ptr(), dE.stride(0), B, L, ed, V, demb.data_ptr(), ctx.padding_idx)
         cur.wait_stream(br1)
         cur.wait_stream(br2)
         return None, None, None, demb, None, dWih, dWhh, dbih, dbhh, dW1, db1, dw2, db2, None

@@ -279,7 +279,9 @@ int ekaid_gru_cell_bwd(int is_bf16, const float* dh, const float* gates, const f
  * hidden units 8c..8c+7, keeps its slice of W_hh in shared memory, and a grid-wide barrier separates the time steps.
  * Rows are time-major (t*B + b).  gi [L*B,3H] = x W_ih^T + b_ih; Whh [3H,H] bf16; Hs [L*B,H] fp32; HsT [(L+1)*B,H] bf16
  * whose block 0 (h_{-1} = 0) the caller zeroes; gates [L,B,4H] saves (r,z,n,gh_n); dHs [L*B,H] = gradient reaching h_t from
- * outside the recurrence; dgi/dgh [L*B,3H] fp32 with bf16 copies dgiT/dghT.  barrier_ws: 4 bytes of device memory.
+ * outside the recurrence; dgi/dgh [L*B,3H] fp32 with bf16 copies dgiT/dghT.  barrier_ws: 8 bytes of device memory, ZERO
+ * before the first launch that uses them; every launch leaves them zero again (the last CTA out clears both words), so no
+ * memset sits in front of the kernel.  One workspace serves launches that are ordered on a stream, not concurrent ones.
  * Requires H % 512 == 0 and H/8 <= number of SMs (EKAID_ERR_UNSUPPORTED otherwise: use the per-step entry points).
  * fp16_ops = 1: Whh and HsT hold IEEE fp16 (the forward operand format of the 16-bit path; h is bounded by 1); HsB
  * (optional): bf16 copy of HsT for the backward wgrad, whose other operand is a bf16 gradient. */
