@@ -668,7 +668,33 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const float lr_bc1 = lr / bc1, rs_bc2 = 1.f / sqrtf(bc2);
   const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
   const long long n4 = vec ? n / 4 : 0;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+  // Four 16-byte groups per thread and pass, all 16 loads issued before the first use: the update that runs next to the
+  // question-path BPTT is capped at one CTA per SM (step.py, EKAID_B200_BG_CTAS), and with one group per pass those 256
+  // threads kept only 16 KB per SM in flight -- 3.9-4.3 TB/s on 1 GB of traffic (profiles/r02b_launches_summary.txt).
+  constexpr int U = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; e + (U - 1) * stride < n4; e += U * stride) {
+    float4 pv[U], mv[U], vv[U], gr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pv[u] = ((float4*)p)[e + u * stride];
+      mv[u] = ((float4*)m)[e + u * stride];
+      vv[u] = ((float4*)v)[e + u * stride];
+      gr[u] = ((const float4*)g)[e + u * stride];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      adam_one(pv[u].x, gr[u].x, mv[u].x, vv[u].x, lr_bc1, rs_bc2, b1, b2, eps, wd);
+      adam_one(pv[u].y, gr[u].y, mv[u].y, vv[u].y, lr_bc1, rs_bc2, b1, b2, eps, wd);
+      adam_one(pv[u].z, gr[u].z, mv[u].z, vv[u].z, lr_bc1, rs_bc2, b1, b2, eps, wd);
+      adam_one(pv[u].w, gr[u].w, mv[u].w, vv[u].w, lr_bc1, rs_bc2, b1, b2, eps, wd);
+      ((float4*)m)[e + u * stride] = mv[u];
+      ((float4*)v)[e + u * stride] = vv[u];
+      ((float4*)p)[e + u * stride] = pv[u];
+    }
+  }
+  for (; e < n4; e += stride) {
     float4 pv = ((float4*)p)[e], mv = ((float4*)m)[e], vv = ((float4*)v)[e];
     const float4 gr = ((const float4*)g)[e];
     adam_one(pv.x, gr.x, mv.x, vv.x, lr_bc1, rs_bc2, b1, b2, eps, wd);

@@ -225,9 +225,6 @@ def gemm(A, B, M, N, K, transA=0, transB=0, *, bias=None, addend=None, rowb=None
              ctypes.addressof(ep), info=info)
 
 
-# question path: only what the recurrence needs is enqueued in front of it (EKAID_B200_QHEAD_SPLIT=0: everything in order)
-QHEAD_SPLIT = os.environ.get("EKAID_B200_QHEAD_SPLIT", "1") != "0"
-
 # one GEMM for both halves of d[v | q] in the relation backward (EKAID_B200_FUSE_DVQ=0: two launches, for A/B measurements)
 FUSE_DVQ = os.environ.get("EKAID_B200_FUSE_DVQ", "1") != "0"
 
@@ -825,7 +822,6 @@ class QuestionFn(torch.autograd.Function):
         E = torch.empty(L * B, 2 * ed, dtype=pc.TF, device=dev)
         call("embed_gather", pc.ff, q.data_ptr(), embc.data_ptr(), emb2c.data_ptr(), B, L, ed, E.data_ptr())
         srcs = [_f32c(Wih), _f32c(Whh), _f32c(W1)]
-        fkq = None
         if pc.bf16:
             WihT, WhhT, W1T = (torch.empty(t.shape, dtype=pc.TF, device=dev) for t in srcs)
             jobs = list(zip(srcs, (WihT, WhhT, W1T)))
@@ -834,16 +830,9 @@ class QuestionFn(torch.autograd.Function):
                 jobs += list(zip(srcs, (WihB, WhhB, W1B)))
             else:
                 WihB, WhhB, W1B = WihT, WhhT, W1T
-            if QHEAD_SPLIT and len(jobs) > 2:
-                # This stream is the serial head of the step (nothing of the first relation encoder can start before qv):
-                # only the two copies the recurrence reads go in front of it; W1's copy and the backward's bf16 copies are
-                # made on a branch stream next to the recurrence and joined before the attention MLP.
-                cast_many(pc, jobs[:2])
-                fkq = Fork(dev, 1, pool="qhead")
-                with fkq.branch(0):
-                    cast_many(pc, jobs[2:])
-            else:
-                cast_many(pc, jobs)
+            # (measured: casting only the recurrence's two copies ahead of it and the rest on a branch stream changes
+            # nothing -- 3.2565 vs 3.2536 ms/step, profiles/r02_notes.md -- so all copies go out in one launch)
+            cast_many(pc, jobs)
         else:
             WihT, WhhT, W1T = srcs
             WihB, WhhB, W1B = srcs
@@ -852,17 +841,13 @@ class QuestionFn(torch.autograd.Function):
         Hs = torch.empty(L * B, H, dtype=torch.float32, device=dev)
         # operand-type copy with one leading zero block: HsT[t] = h_{t-1}, so "previous h of every step" is a view
         # (the recurrence writes every other block; only block 0 is cleared)
-        if QHEAD_SPLIT:
-            HsT = torch.empty((L + 1) * B, H, dtype=pc.TF, device=dev)
-            HsT[:B].zero_()
-            if dual:
-                HsB = torch.empty((L + 1) * B, H, dtype=pc.T, device=dev)
-                HsB[:B].zero_()
-            else:
-                HsB = HsT
+        HsT = torch.empty((L + 1) * B, H, dtype=pc.TF, device=dev)
+        HsT[:B].zero_()
+        if dual:
+            HsB = torch.empty((L + 1) * B, H, dtype=pc.T, device=dev)
+            HsB[:B].zero_()
         else:
-            HsT = torch.zeros((L + 1) * B, H, dtype=pc.TF, device=dev)
-            HsB = torch.zeros((L + 1) * B, H, dtype=pc.T, device=dev) if dual else HsT
+            HsB = HsT
         gates = torch.empty(L, B, 4 * H, dtype=torch.float32, device=dev)
         if _gru_seq_ok(pc, dev, B, H):
             # the whole recurrence in one persistent launch (gru_seq.cu)
@@ -881,8 +866,6 @@ class QuestionFn(torch.autograd.Function):
                      bhhc.data_ptr())
             if dual:
                 bcopy([(HsT[B:], HsB[B:])])
-        if fkq is not None:
-            fkq.join()                            # W1T and the bf16 copies are complete from here on
         HsT_cur = HsT[B:]
         if drop is not None and drop.on:          # Dropout(0.2) on the input of W1 (language_model.py:123-124)
             Hd = torch.empty(L * B, H, dtype=pc.TF, device=dev)
