@@ -42,16 +42,16 @@ embed_gather_bwd_kernel(const long long* __restrict__ q, const float* __restrict
     constexpr int U = 8;
     int n = 0;
     for (int r0 = 0; r0 < total; r0 += 32 * U) {
+      long long tok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {            // unguarded loads of a clamped row: nothing orders them behind a branch
+        const int row = min(r0 + u * 32 + (int)threadIdx.x, total - 1);
+        const int l = row / B, b = row - l * B;
+        tok[u] = q[(size_t)b * L + l];
+      }
       bool hit[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int row = r0 + u * 32 + (int)threadIdx.x;
-        hit[u] = false;
-        if (row < total) {
-          const int l = row / B, b = row % B;
-          hit[u] = (q[(size_t)b * L + l] == v);
-        }
-      }
+      for (int u = 0; u < U; ++u) hit[u] = (r0 + u * 32 + (int)threadIdx.x < total) && (tok[u] == v);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const unsigned m = __ballot_sync(0xffffffffu, hit[u]);
