@@ -1287,7 +1287,10 @@ int ek_onehot_adj_i8_launch(const int8_t* labels, int B, int S, int N, int L, fl
 int ek_adam_launch(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                    float wd, const float* pow_state, int max_ctas, cudaStream_t st) {
   if (n == 0) return EK_OK;
-  int grid = grid_for(n / 4 + 1);
+  // one thread per FOUR 16-byte groups (the kernel's unrolled pass): a segment smaller than the capped grid x 4 groups
+  // would otherwise run entirely in the one-group remainder loop, at two CTAs per SM (122 registers) -- measured 35 us
+  // instead of 27 us for the question-path segment that closes the step (profiles/r02b_ncu_adam_embed.csv)
+  int grid = grid_for(n / 16 + 1);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;      // background mode: leave SM slots to concurrent kernels
   static bool carveout_set = false;
   if (!carveout_set) {
